@@ -1,0 +1,199 @@
+/*
+ * maestro_b200.h -- C ABI of the B200-native MAESTRO advective hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces the per-box ("L2") kernels that
+ * one public multifab-level ("L3") routine of the reference calls, and takes exactly what that
+ * routine hands to its kernels: raw fp64 arrays (Fortran order, x fastest, component slowest,
+ * ghost cells included), the valid box lo/hi, ghost widths, dx, dt, integer BC tables and the
+ * runtime parameters that live in Fortran modules (`probin_module`, `variables`, `network`).
+ * The reference has no FFI of its own; the cut is the L3->L2 call in each file cited below.
+ * A Fortran ISO_C_BINDING module that binds these symbols is in shim/maestro_b200_shim.f90 and
+ * described in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, no torch/CUDA types.  Pointers are HOST pointers when params->mem_space ==
+ *    MGPU_HOST (the library stages host<->device itself, synchronously) or DEVICE pointers when
+ *    MGPU_DEVICE (device-resident episode; asynchronous on the library stream until
+ *    mgpu_synchronize()).
+ *  - component numbers (rho_comp, scomp, bccomp ...) are 1-based exactly as in the Fortran.
+ *  - adv_bc is the contiguous copy of `the_bc_level(n)%adv_bc_level_array(i,:,:,:)`, i.e.
+ *    adv_bc[(d-1) + dm*((side-1) + 2*(bccomp-1))], d=1..dm, side=1(lo),2(hi).
+ *  - base-state arrays (w0, rho0_old, ...) are the 1-D slice for the level: element r = 0..nr.
+ *  - every function returns 0 on success; nonzero => mgpu_last_error() holds the message and the
+ *    Fortran wrapper calls bl_error (reference convention, e.g. make_edge_scal.f90:853).
+ */
+#ifndef MAESTRO_B200_H
+#define MAESTRO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* bc_module constants of FBoxLib (external to the reference tree; treated as opaque enums that the
+ * Fortran shim passes through unchanged). */
+enum {
+  MGPU_BC_PERIODIC = -1,
+  MGPU_BC_INTERIOR = 0,
+  MGPU_BC_INLET = 11,
+  MGPU_BC_OUTLET = 12,
+  MGPU_BC_SYMMETRY = 13,
+  MGPU_BC_SLIP_WALL = 14,
+  MGPU_BC_NO_SLIP_WALL = 15,
+  MGPU_BC_REFLECT_ODD = 20,
+  MGPU_BC_REFLECT_EVEN = 21,
+  MGPU_BC_FOEXTRAP = 22,
+  MGPU_BC_EXT_DIR = 23,
+  MGPU_BC_HOEXTRAP = 24
+};
+
+enum { MGPU_HOST = 0, MGPU_DEVICE = 1 };
+
+/* species_pred_type / enthalpy_pred_type: Source/pred_parameters.f90:5-17 */
+enum { MGPU_PREDICT_RHOPRIME_AND_X = 1, MGPU_PREDICT_RHOX = 2, MGPU_PREDICT_RHO_AND_X = 3 };
+enum {
+  MGPU_PREDICT_RHOH = 0,
+  MGPU_PREDICT_RHOHPRIME = 1,
+  MGPU_PREDICT_H = 2,
+  MGPU_PREDICT_T_THEN_RHOHPRIME = 3,
+  MGPU_PREDICT_T_THEN_H = 4,
+  MGPU_PREDICT_HPRIME = 5,
+  MGPU_PREDICT_TPRIME_THEN_H = 6
+};
+
+/* One fab = what `dataptr(mf,i)` + `get_box(mf,i)` + `nghost(mf)` give the reference kernels
+ * (e.g. make_edge_scal.f90:70-76).  ptr addresses element (lo-ng, lo-ng, lo-ng, comp 1).
+ * Extent in dim d (< dm) is hi[d]-lo[d]+1 + 2*ng + nodal[d]; dims >= dm have extent 1. */
+typedef struct {
+  double* ptr;
+  int lo[3];
+  int hi[3];
+  int ng;
+  int nc;
+  int nodal[3];
+} mgpu_fab;
+
+/* Runtime parameters the reference keeps in module variables (probin_module: Source/_parameters;
+ * variables: Source/variables.f90:100-124; network: nspec).  Passed on every call because the
+ * reference mutates ppm_type/bds_type at run time (Exec/UNIT_TESTS/test_advect/varden.f90:278,287). */
+typedef struct {
+  int dm;                 /* 2 or 3 */
+  int mem_space;          /* MGPU_HOST or MGPU_DEVICE */
+  int ppm_type;           /* 0,1,2  (_parameters:500) */
+  int bds_type;           /* 0,1    (_parameters:504) */
+  int slope_order;        /* 0,2,4  (_parameters:492) */
+  int ppm_trace_forces;   /* 0,1    (_parameters:509) */
+  int species_pred_type;  /* 1,2,3 */
+  int enthalpy_pred_type; /* 0..6 */
+  int spherical;          /* 0 planar, 1 spherical */
+  int evolve_base_state;  /* logical */
+  int do_sponge;          /* logical */
+  int do_eos_h_above_cutoff; /* logical; EOS work itself stays with the Fortran caller */
+  int rho_comp, rhoh_comp, spec_comp, temp_comp, pi_comp, trac_comp; /* 1-based */
+  int nspec, ntrac, nscal;
+  int domlo[3], domhi[3]; /* problem domain, cell-centred */
+  int nr;                 /* nr_fine: base state arrays have r = 0..nr (edge) / 0..nr-1 (cell) */
+  double dt;
+  double dx[3];
+  double rel_eps;            /* variables.f90:17, set in estdt.f90:231 */
+  double base_cutoff_density;
+} mgpu_params;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int mgpu_init(int device);            /* binds the calling rank to one GPU, creates streams/pool */
+int mgpu_finalize(void);
+int mgpu_synchronize(void);
+const char* mgpu_last_error(void);
+const char* mgpu_version(void);
+/* number of kernel launches issued by the library since the last reset (bench "gpu_launches") */
+long mgpu_launch_count(int reset);
+/* raw CUstream used for all launches (for CUDA-event timing by the caller) */
+void* mgpu_stream(void);
+
+/* device memory helpers for device-resident episodes (tests/bench own their buffers) */
+int mgpu_malloc(double** dptr, long n);
+int mgpu_free(double* dptr);
+int mgpu_memcpy_h2d(double* dst, const double* src, long n);
+int mgpu_memcpy_d2h(double* dst, const double* src, long n);
+
+/* ---- ghost fill (replaces FBoxLib multifab_fill_boundary + Source/multifab_physbc.f90:16) ---- */
+/* Single-box-per-rank fill: periodic wrap inside the box for dims with pmask[d]=1, then physical
+ * BCs per adv_bc (physbc_2d :150, physbc_3d :329) for comps scomp..scomp+ncomp-1. */
+int mgpu_fill_boundary(const mgpu_params* p, mgpu_fab* s, int scomp, int bccomp, int ncomp,
+                       const int* adv_bc, const int* pmask);
+
+/* ---- L3 operators ---------------------------------------------------------------------- */
+/* make_edge_scal (Source/make_edge_scal.f90:26): edge states of comps start_scomp.. of s on all
+ * faces; sedge[d] nodal in d, written in comps start_scomp...  umac[d] nodal in d with 1 ghost. */
+int mgpu_make_edge_scal(const mgpu_params* p, int nfabs, const mgpu_fab* s, mgpu_fab* const* sedge,
+                        const mgpu_fab* const* umac, const mgpu_fab* force, const int* adv_bc,
+                        int is_vel, int start_scomp, int start_bccomp, int num_comp,
+                        int is_conservative);
+
+/* bds (Source/bds.f90:16): same contract as make_edge_scal, Bell-Dawson-Shubin reconstruction. */
+int mgpu_bds(const mgpu_params* p, int nfabs, const mgpu_fab* s, mgpu_fab* const* sedge,
+             const mgpu_fab* const* umac, const mgpu_fab* force, const int* adv_bc, int is_vel,
+             int start_scomp, int start_bccomp, int num_comp, int is_conservative);
+
+/* mk_rhoX_flux (Source/mkflux.f90:48), planar geometry (_2d :272, _3d_cart :370). */
+int mgpu_mk_rhoX_flux(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, mgpu_fab* etarhoflux,
+                      const mgpu_fab* const* sedge, const mgpu_fab* const* umac, const double* w0,
+                      const double* rho0_old, const double* rho0_edge_old, const double* rho0_new,
+                      const double* rho0_edge_new, const double* rho0_predicted_edge, int startcomp,
+                      int endcomp);
+
+/* mk_rhoh_flux (Source/mkflux.f90:652), planar geometry (_2d :920, _3d_cart :1070). */
+int mgpu_mk_rhoh_flux(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux,
+                      const mgpu_fab* const* sedge, const mgpu_fab* const* umac, const double* w0,
+                      const double* rho0_old, const double* rho0_edge_old, const double* rho0_new,
+                      const double* rho0_edge_new, const double* rhoh0_old,
+                      const double* rhoh0_edge_old, const double* rhoh0_new,
+                      const double* rhoh0_edge_new);
+
+/* update_scal (Source/update_scal.f90:16), planar (_2d :246, _3d_cart :370); valid cells only, the
+ * caller follows with mgpu_fill_boundary (update_scal.f90:110-122). EOS-below-cutoff zones
+ * (:421-447) are left to the caller. */
+int mgpu_update_scal(const mgpu_params* p, int nfabs, int nstart, int nstop, const mgpu_fab* sold,
+                     mgpu_fab* snew, const mgpu_fab* const* sflux, const mgpu_fab* force);
+
+/* update_velocity (Source/update_vel.f90:15), planar (_2d :174, _3d :227). */
+int mgpu_update_velocity(const mgpu_params* p, int nfabs, const mgpu_fab* uold, mgpu_fab* unew,
+                         const mgpu_fab* const* umac, const mgpu_fab* const* uedge,
+                         const mgpu_fab* force, const mgpu_fab* sponge, const double* w0);
+
+/* addw0 (Source/addw0.f90:19), planar: umac[dm-1] += mult*w0 (no ghost exchange). */
+int mgpu_addw0(const mgpu_params* p, int nfabs, mgpu_fab* const* umac, const double* w0, double mult);
+
+/* mkutrans (Source/mkutrans.f90:17) planar (_2d :257, _3d :461). */
+int mgpu_mkutrans(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                  mgpu_fab* const* utrans, const double* w0, const int* adv_bc, const int* phys_bc);
+
+/* velpred (Source/velpred.f90:21) planar (_2d :266, _3d :640). */
+int mgpu_velpred(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                 mgpu_fab* const* umac, const mgpu_fab* const* utrans, const mgpu_fab* force,
+                 const double* w0, const int* adv_bc, const int* phys_bc);
+
+/* glue used inside the drivers: modify_scal_force (modify_scal_force.f90:15, planar),
+ * convert_rhoX_to_X (convert_rhoX_to_X.f90:20), put_in_pert_form (put_in_pert_form.f90:22, planar);
+ * valid cells only, the caller follows with mgpu_fill_boundary. */
+int mgpu_modify_scal_force(const mgpu_params* p, int nfabs, mgpu_fab* force, const mgpu_fab* s,
+                           const mgpu_fab* const* umac, const double* s0, const double* s0_edge,
+                           const double* w0, int comp, int fullform);
+int mgpu_convert_rhoX_to_X(const mgpu_params* p, int nfabs, mgpu_fab* s, int flag);
+int mgpu_put_in_pert_form(const mgpu_params* p, int nfabs, mgpu_fab* s, const double* base, int comp,
+                          int flag);
+
+/* ---- L4 episode: density_advance (Source/density_advance.f90:20), planar, one level ------
+ * Signature mirrors the Fortran argument list; sold is modified in place exactly as the reference
+ * does (rhoX->X->rhoX, rho->rho'->rho round trips), umac is (umac+w0)-w0 on return, sedge, sflux,
+ * etarhoflux, scal_force and snew (valid + ghost cells) are fully populated on return.
+ * pmask[d]=1 => periodic in d (FBoxLib layout pmask); single box per rank (slab). */
+int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgpu_fab* snew,
+                         mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
+                         mgpu_fab* const* umac, const double* w0, mgpu_fab* etarhoflux,
+                         const double* rho0_old, const double* rho0_new, const double* p0_dummy,
+                         const double* rho0_predicted_edge, const int* adv_bc, const int* pmask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAESTRO_B200_H */

@@ -1,0 +1,254 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (see mo_array.h).
+//
+// extern "C" surface of the oracle, mirroring include/maestro_b200.h one to one (prefix mo_ instead
+// of mgpu_) so that the parity tests call both with identical arguments.  Host pointers only.
+#include <stdexcept>
+#include <string>
+
+#include "mo_kernels.h"
+
+namespace mo {
+void density_advance_box(const mgpu_params& P, int which_step, Arr& sold, Arr& snew, Arr* sedge, Arr* sflux,
+                         Arr& scal_force, Arr* umac, const double* w0, Arr& etarhoflux, const double* rho0_old,
+                         const double* rho0_new, const double* rho0_predicted_edge, const int* lo,
+                         const int* hi, int ng_s, int ng_f, const int* adv_bc, const int* pmask);
+void test_advect_run(int dm, int n, int ppm_type, int bds_type, int itest_dir, double cflfac, double stop_time,
+                     double* abs_norm, double* rel_norm, double* rho_final_out);
+}  // namespace mo
+
+using namespace mo;
+
+static std::string g_err;
+
+#define MO_TRY try {
+#define MO_CATCH                         \
+  }                                      \
+  catch (const std::exception& e) {      \
+    g_err = e.what();                    \
+    return 1;                            \
+  }                                      \
+  return 0;
+
+static void views(const mgpu_params* p, const mgpu_fab* const* f, int i, Arr* out) {
+  for (int d = 0; d < p->dm; ++d) out[d] = Arr::view(f[d][i], p->dm);
+}
+
+extern "C" {
+
+const char* mo_last_error(void) { return g_err.c_str(); }
+
+int mo_fill_boundary(const mgpu_params* p, mgpu_fab* s, int scomp, int bccomp, int ncomp, const int* adv_bc,
+                     const int* pmask) {
+  MO_TRY
+  Arr a = Arr::view(*s, p->dm);
+  if (s->nodal[0] || s->nodal[1] || s->nodal[2]) {
+    int dir = s->nodal[0] ? 0 : (s->nodal[1] ? 1 : 2);
+    fill_boundary_face(*p, a, s->lo, s->hi, s->ng, dir, pmask);
+  } else {
+    fill_boundary_box(*p, a, s->lo, s->hi, s->ng, scomp, bccomp, ncomp, adv_bc, pmask);
+  }
+  MO_CATCH
+}
+
+int mo_make_edge_scal(const mgpu_params* p, int nfabs, const mgpu_fab* s, mgpu_fab* const* sedge,
+                      const mgpu_fab* const* umac, const mgpu_fab* force, const int* adv_bc, int is_vel,
+                      int start_scomp, int start_bccomp, int num_comp, int is_conservative) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr sa = Arr::view(s[i], p->dm), fa = Arr::view(force[i], p->dm);
+    Arr se[3], um[3];
+    views(p, (const mgpu_fab* const*)sedge, i, se);
+    views(p, umac, i, um);
+    for (int scomp = start_scomp; scomp < start_scomp + num_comp; ++scomp) {
+      int bccomp = start_bccomp + scomp - start_scomp;
+      make_edge_scal_box(*p, sa, se, um, fa, s[i].lo, s[i].hi, adv_bc, scomp - 1, bccomp, is_vel != 0,
+                         is_conservative != 0, s[i].ng);
+    }
+  }
+  MO_CATCH
+}
+
+int mo_bds(const mgpu_params* p, int nfabs, const mgpu_fab* s, mgpu_fab* const* sedge,
+           const mgpu_fab* const* umac, const mgpu_fab* force, const int* adv_bc, int is_vel, int start_scomp,
+           int start_bccomp, int num_comp, int is_conservative) {
+  MO_TRY
+  (void)adv_bc; (void)is_vel; (void)start_bccomp;
+  for (int i = 0; i < nfabs; ++i) {
+    Arr sa = Arr::view(s[i], p->dm), fa = Arr::view(force[i], p->dm);
+    Arr se[3], um[3];
+    views(p, (const mgpu_fab* const*)sedge, i, se);
+    views(p, umac, i, um);
+    for (int scomp = start_scomp; scomp < start_scomp + num_comp; ++scomp)
+      bds_box(*p, sa, se, um, fa, s[i].lo, s[i].hi, scomp - 1, is_conservative != 0);
+  }
+  MO_CATCH
+}
+
+int mo_mk_rhoX_flux(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, mgpu_fab* etarhoflux,
+                    const mgpu_fab* const* sedge, const mgpu_fab* const* umac, const double* w0,
+                    const double* rho0_old, const double* rho0_edge_old, const double* rho0_new,
+                    const double* rho0_edge_new, const double* rho0_predicted_edge, int startcomp, int endcomp) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr sf[3], se[3], um[3];
+    views(p, (const mgpu_fab* const*)sflux, i, sf);
+    views(p, sedge, i, se);
+    views(p, umac, i, um);
+    Arr eta = Arr::view(etarhoflux[i], p->dm);
+    mk_rhoX_flux_box(*p, sf, eta, se, um, w0, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new,
+                     rho0_predicted_edge, startcomp, endcomp, umac[0][i].lo, umac[0][i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_mk_rhoh_flux(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, const mgpu_fab* const* sedge,
+                    const mgpu_fab* const* umac, const double* w0, const double* rho0_old,
+                    const double* rho0_edge_old, const double* rho0_new, const double* rho0_edge_new,
+                    const double* rhoh0_old, const double* rhoh0_edge_old, const double* rhoh0_new,
+                    const double* rhoh0_edge_new) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr sf[3], se[3], um[3];
+    views(p, (const mgpu_fab* const*)sflux, i, sf);
+    views(p, sedge, i, se);
+    views(p, umac, i, um);
+    mk_rhoh_flux_box(*p, sf, se, um, w0, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new, rhoh0_old,
+                     rhoh0_edge_old, rhoh0_new, rhoh0_edge_new, umac[0][i].lo, umac[0][i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_update_scal(const mgpu_params* p, int nfabs, int nstart, int nstop, const mgpu_fab* sold, mgpu_fab* snew,
+                   const mgpu_fab* const* sflux, const mgpu_fab* force) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr so = Arr::view(sold[i], p->dm), sn = Arr::view(snew[i], p->dm), fa = Arr::view(force[i], p->dm);
+    Arr sf[3];
+    views(p, sflux, i, sf);
+    update_scal_box(*p, nstart, nstop, so, sn, sf, fa, sold[i].lo, sold[i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_update_velocity(const mgpu_params* p, int nfabs, const mgpu_fab* uold, mgpu_fab* unew,
+                       const mgpu_fab* const* umac, const mgpu_fab* const* uedge, const mgpu_fab* force,
+                       const mgpu_fab* sponge, const double* w0) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr uo = Arr::view(uold[i], p->dm), un = Arr::view(unew[i], p->dm), fa = Arr::view(force[i], p->dm);
+    Arr sp = Arr::view(sponge[i], p->dm);
+    Arr um[3], ue[3];
+    views(p, umac, i, um);
+    views(p, uedge, i, ue);
+    update_velocity_box(*p, uo, un, um, ue, fa, sp, w0, uold[i].lo, uold[i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_addw0(const mgpu_params* p, int nfabs, mgpu_fab* const* umac, const double* w0, double mult) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr um[3];
+    views(p, (const mgpu_fab* const*)umac, i, um);
+    addw0_box(*p, um, w0, mult, umac[0][i].lo, umac[0][i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_mkutrans(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                mgpu_fab* const* utrans, const double* w0, const int* adv_bc, const int* phys_bc) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr ut = Arr::view(utilde[i], p->dm), uf = Arr::view(ufull[i], p->dm);
+    Arr tr[3];
+    views(p, (const mgpu_fab* const*)utrans, i, tr);
+    mkutrans_box(*p, ut, uf, tr, w0, utilde[i].lo, utilde[i].hi, adv_bc, phys_bc, utilde[i].ng);
+  }
+  MO_CATCH
+}
+
+int mo_velpred(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+               mgpu_fab* const* umac, const mgpu_fab* const* utrans, const mgpu_fab* force, const double* w0,
+               const int* adv_bc, const int* phys_bc) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr ut = Arr::view(utilde[i], p->dm), uf = Arr::view(ufull[i], p->dm), fa = Arr::view(force[i], p->dm);
+    Arr um[3], tr[3];
+    views(p, (const mgpu_fab* const*)umac, i, um);
+    views(p, utrans, i, tr);
+    velpred_box(*p, ut, uf, um, tr, fa, w0, utilde[i].lo, utilde[i].hi, adv_bc, phys_bc, utilde[i].ng);
+  }
+  MO_CATCH
+}
+
+int mo_modify_scal_force(const mgpu_params* p, int nfabs, mgpu_fab* force, const mgpu_fab* s,
+                         const mgpu_fab* const* umac, const double* s0, const double* s0_edge, const double* w0,
+                         int comp, int fullform) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr fa = Arr::view(force[i], p->dm), sa = Arr::view(s[i], p->dm);
+    Arr um[3];
+    views(p, umac, i, um);
+    modify_scal_force_box(*p, fa, sa, um, s0, s0_edge, w0, comp, fullform != 0, s[i].lo, s[i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_convert_rhoX_to_X(const mgpu_params* p, int nfabs, mgpu_fab* s, int flag) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr sa = Arr::view(s[i], p->dm);
+    Box vb = grown(s[i].lo, s[i].hi, p->dm, 0);
+    for (int n = 0; n < p->nspec; ++n) {
+      const int c = p->spec_comp - 1 + n, r = p->rho_comp - 1;
+      for_box(vb, [&](int ii, int j, int k) {
+        sa(ii, j, k, c) = flag ? sa(ii, j, k, c) / sa(ii, j, k, r) : sa(ii, j, k, c) * sa(ii, j, k, r);
+      });
+    }
+  }
+  MO_CATCH
+}
+
+int mo_put_in_pert_form(const mgpu_params* p, int nfabs, mgpu_fab* s, const double* base, int comp, int flag) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr sa = Arr::view(s[i], p->dm);
+    Box vb = grown(s[i].lo, s[i].hi, p->dm, 0);
+    const int mult = flag ? -1 : +1, r = p->dm - 1;
+    for_box(vb, [&](int ii, int j, int k) { sa(ii, j, k, comp - 1) = sa(ii, j, k, comp - 1) + mult * base[r == 1 ? j : k]; });
+  }
+  MO_CATCH
+}
+
+int mo_cell_to_edge(const double* s0_cell, double* s0_edge, int nr) {
+  MO_TRY
+  cell_to_edge(s0_cell, s0_edge, nr);
+  MO_CATCH
+}
+
+int mo_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgpu_fab* snew,
+                       mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
+                       mgpu_fab* const* umac, const double* w0, mgpu_fab* etarhoflux, const double* rho0_old,
+                       const double* rho0_new, const double* p0_dummy, const double* rho0_predicted_edge,
+                       const int* adv_bc, const int* pmask) {
+  MO_TRY
+  (void)p0_dummy;
+  Arr so = Arr::view(*sold, p->dm), sn = Arr::view(*snew, p->dm), fa = Arr::view(*scal_force, p->dm);
+  Arr eta = Arr::view(*etarhoflux, p->dm);
+  Arr se[3], sf[3], um[3];
+  views(p, (const mgpu_fab* const*)sedge, 0, se);
+  views(p, (const mgpu_fab* const*)sflux, 0, sf);
+  views(p, (const mgpu_fab* const*)umac, 0, um);
+  density_advance_box(*p, which_step, so, sn, se, sf, fa, um, w0, eta, rho0_old, rho0_new, rho0_predicted_edge,
+                      sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
+  MO_CATCH
+}
+
+int mo_test_advect(int dm, int n, int ppm_type, int bds_type, int itest_dir, double cflfac, double stop_time,
+                   double* abs_norm, double* rel_norm, double* rho_final) {
+  MO_TRY
+  test_advect_run(dm, n, ppm_type, bds_type, itest_dir, cflfac, stop_time, abs_norm, rel_norm, rho_final);
+  MO_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (see mo_array.h).  Declarations of the restated kernels.
+#pragma once
+#include "mo_array.h"
+
+namespace mo {
+
+struct Box {
+  int lo[3];
+  int hi[3];
+};
+
+// valid box grown by g in every active dimension (dims >= dm stay [0,0])
+inline Box grown(const int* lo, const int* hi, int dm, int g) {
+  Box b;
+  for (int d = 0; d < 3; ++d) {
+    if (d < dm) {
+      b.lo[d] = lo[d] - g;
+      b.hi[d] = hi[d] + g;
+    } else {
+      b.lo[d] = b.hi[d] = 0;
+    }
+  }
+  return b;
+}
+
+// loop nest in Fortran order; OpenMP over the outermost non-degenerate index, which is where the
+// reference puts its !$OMP PARALLEL DO (k in 3-D).
+template <class F>
+inline void for_box(const Box& b, F f) {
+  if (b.hi[2] > b.lo[2]) {
+#pragma omp parallel for
+    for (int k = b.lo[2]; k <= b.hi[2]; ++k)
+      for (int j = b.lo[1]; j <= b.hi[1]; ++j)
+        for (int i = b.lo[0]; i <= b.hi[0]; ++i) f(i, j, k);
+  } else {
+    for (int k = b.lo[2]; k <= b.hi[2]; ++k)
+      for (int j = b.lo[1]; j <= b.hi[1]; ++j)
+        for (int i = b.lo[0]; i <= b.hi[0]; ++i) f(i, j, k);
+  }
+}
+
+struct Ctx {  // module variables of the reference, per call
+  mgpu_params p;
+};
+
+void slope_dir(const Arr& s, Arr& slp, const int* lo, const int* hi, int dm, int d, int bclo, int bchi,
+               int slope_order);
+
+void ppm(const Arr& s, const Arr* vel, Arr& Ip, Arr& Im, const int* lo, const int* hi, int dm,
+         const int bc[3][2], const double* dx, double dt, bool is_umac, int ppm_type, double rel_eps,
+         int ng_s);
+
+// make_edge_scal_2d / _3d for one component (0-based comp index into s/sedge/force; 1-based bccomp)
+void make_edge_scal_box(const mgpu_params& P, const Arr& s, Arr* sedge, const Arr* umac, const Arr& force,
+                        const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel,
+                        bool is_conservative, int ng_s);
+
+void mk_rhoX_flux_box(const mgpu_params& P, Arr* sflux, Arr& etarhoflux, const Arr* sedge, const Arr* umac,
+                      const double* w0, const double* rho0_old, const double* rho0_edge_old,
+                      const double* rho0_new, const double* rho0_edge_new, const double* rho0_predicted_edge,
+                      int startcomp, int endcomp, const int* lo, const int* hi);
+
+void mk_rhoh_flux_box(const mgpu_params& P, Arr* sflux, const Arr* sedge, const Arr* umac, const double* w0,
+                      const double* rho0_old, const double* rho0_edge_old, const double* rho0_new,
+                      const double* rho0_edge_new, const double* rhoh0_old, const double* rhoh0_edge_old,
+                      const double* rhoh0_new, const double* rhoh0_edge_new, const int* lo, const int* hi);
+
+void update_scal_box(const mgpu_params& P, int nstart, int nstop, const Arr& sold, Arr& snew, const Arr* sflux,
+                     const Arr& force, const int* lo, const int* hi);
+
+void update_velocity_box(const mgpu_params& P, const Arr& uold, Arr& unew, const Arr* umac, const Arr* uedge,
+                         const Arr& force, const Arr& sponge, const double* w0, const int* lo, const int* hi);
+
+void addw0_box(const mgpu_params& P, Arr* umac, const double* w0, double mult, const int* lo, const int* hi);
+
+void modify_scal_force_box(const mgpu_params& P, Arr& force, const Arr& s, const Arr* umac, const double* s0,
+                           const double* s0_edge, const double* w0, int comp, bool fullform, const int* lo,
+                           const int* hi);
+
+void cell_to_edge(const double* s0_cell, double* s0_edge, int nr);
+
+void mkutrans_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr* utrans, const double* w0,
+                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u);
+
+void velpred_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr* umac, const Arr* utrans,
+                 const Arr& force, const double* w0, const int* lo, const int* hi, const int* adv_bc,
+                 const int* phys_bc, int ng_u);
+
+void bds_box(const mgpu_params& P, const Arr& s, Arr* sedge, const Arr* umac, const Arr& force, const int* lo,
+             const int* hi, int comp, bool is_conservative);
+
+// ghost fill of a single box covering the whole domain: periodic wrap + multifab_physbc
+void fill_boundary_box(const mgpu_params& P, Arr& s, const int* lo, const int* hi, int ng, int scomp, int bccomp,
+                       int ncomp, const int* adv_bc, const int* pmask);
+// face-centred periodic fill (multifab_fill_boundary on a nodal multifab), 1 ghost layer
+void fill_boundary_face(const mgpu_params& P, Arr& u, const int* lo, const int* hi, int ng, int dir,
+                        const int* pmask);
+
+}  // namespace mo
