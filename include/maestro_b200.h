@@ -106,8 +106,13 @@ const char* mgpu_last_error(void);
 const char* mgpu_version(void);
 /* number of kernel launches issued by the library since the last reset (bench "gpu_launches") */
 long mgpu_launch_count(int reset);
-/* raw CUstream used for all launches (for CUDA-event timing by the caller) */
+/* raw cudaStream_t used for all launches (for CUDA-event timing by the caller) */
 void* mgpu_stream(void);
+/* run on a caller-owned stream instead (e.g. the framework's current stream) */
+int mgpu_set_stream(void* stream);
+/* pin caller-owned host memory (multifab data) so host-pointer calls copy at full PCIe rate */
+int mgpu_host_register(double* hptr, long n);
+int mgpu_host_unregister(double* hptr);
 
 /* device memory helpers for device-resident episodes (tests/bench own their buffers) */
 int mgpu_malloc(double** dptr, long n);

@@ -1,0 +1,117 @@
+"""ctypes mirror of include/maestro_b200.h (structs, constants, prototypes).
+
+Only declarations live here; `maestro_b200.lib` loads the CUDA library.  The same declarations are
+applied to the CPU oracle's `mo_*` symbols by the tests (the oracle mirrors the ABI one to one).
+"""
+import ctypes as C
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+# bc_module constants (FBoxLib), see include/maestro_b200.h
+PERIODIC, INTERIOR = -1, 0
+INLET, OUTLET, SYMMETRY, SLIP_WALL, NO_SLIP_WALL = 11, 12, 13, 14, 15
+REFLECT_ODD, REFLECT_EVEN, FOEXTRAP, EXT_DIR, HOEXTRAP = 20, 21, 22, 23, 24
+HOST, DEVICE = 0, 1
+PREDICT_RHOPRIME_AND_X, PREDICT_RHOX, PREDICT_RHO_AND_X = 1, 2, 3
+PREDICT_RHOH, PREDICT_RHOHPRIME, PREDICT_H = 0, 1, 2
+PREDICT_T_THEN_RHOHPRIME, PREDICT_T_THEN_H, PREDICT_HPRIME, PREDICT_TPRIME_THEN_H = 3, 4, 5, 6
+
+
+class mgpu_fab(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("lo", C.c_int * 3),
+        ("hi", C.c_int * 3),
+        ("ng", C.c_int),
+        ("nc", C.c_int),
+        ("nodal", C.c_int * 3),
+    ]
+
+
+class mgpu_params(C.Structure):
+    _fields_ = [
+        ("dm", C.c_int),
+        ("mem_space", C.c_int),
+        ("ppm_type", C.c_int),
+        ("bds_type", C.c_int),
+        ("slope_order", C.c_int),
+        ("ppm_trace_forces", C.c_int),
+        ("species_pred_type", C.c_int),
+        ("enthalpy_pred_type", C.c_int),
+        ("spherical", C.c_int),
+        ("evolve_base_state", C.c_int),
+        ("do_sponge", C.c_int),
+        ("do_eos_h_above_cutoff", C.c_int),
+        ("rho_comp", C.c_int),
+        ("rhoh_comp", C.c_int),
+        ("spec_comp", C.c_int),
+        ("temp_comp", C.c_int),
+        ("pi_comp", C.c_int),
+        ("trac_comp", C.c_int),
+        ("nspec", C.c_int),
+        ("ntrac", C.c_int),
+        ("nscal", C.c_int),
+        ("domlo", C.c_int * 3),
+        ("domhi", C.c_int * 3),
+        ("nr", C.c_int),
+        ("dt", C.c_double),
+        ("dx", C.c_double * 3),
+        ("rel_eps", C.c_double),
+        ("base_cutoff_density", C.c_double),
+    ]
+
+
+P_ = C.POINTER(mgpu_params)
+F_ = C.POINTER(mgpu_fab)
+FF_ = C.POINTER(F_)  # array of dm pointers, each to an array of nfabs fabs
+
+# name -> (restype, argtypes) for every operator symbol shared by the library (mgpu_) and the oracle (mo_)
+OPERATORS = {
+    "fill_boundary": (C.c_int, [P_, F_, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p]),
+    "make_edge_scal": (C.c_int, [P_, C.c_int, F_, FF_, FF_, F_, c_int_p] + [C.c_int] * 5),
+    "bds": (C.c_int, [P_, C.c_int, F_, FF_, FF_, F_, c_int_p] + [C.c_int] * 5),
+    "mk_rhoX_flux": (C.c_int, [P_, C.c_int, FF_, F_, FF_, FF_] + [c_double_p] * 6 + [C.c_int] * 2),
+    "mk_rhoh_flux": (C.c_int, [P_, C.c_int, FF_, FF_, FF_] + [c_double_p] * 9),
+    "update_scal": (C.c_int, [P_, C.c_int, C.c_int, C.c_int, F_, F_, FF_, F_]),
+    "update_velocity": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, F_, c_double_p]),
+    "addw0": (C.c_int, [P_, C.c_int, FF_, c_double_p, C.c_double]),
+    "mkutrans": (C.c_int, [P_, C.c_int, F_, F_, FF_, c_double_p, c_int_p, c_int_p]),
+    "velpred": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, c_double_p, c_int_p, c_int_p]),
+    "modify_scal_force": (C.c_int, [P_, C.c_int, F_, F_, FF_] + [c_double_p] * 3 + [C.c_int] * 2),
+    "convert_rhoX_to_X": (C.c_int, [P_, C.c_int, F_, C.c_int]),
+    "put_in_pert_form": (C.c_int, [P_, C.c_int, F_, c_double_p, C.c_int, C.c_int]),
+    "density_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, FF_, c_double_p, F_] + [c_double_p] * 4
+                        + [c_int_p] * 2),
+}
+
+# symbols only the library has
+LIFECYCLE = {
+    "mgpu_init": (C.c_int, [C.c_int]),
+    "mgpu_finalize": (C.c_int, []),
+    "mgpu_synchronize": (C.c_int, []),
+    "mgpu_last_error": (C.c_char_p, []),
+    "mgpu_version": (C.c_char_p, []),
+    "mgpu_launch_count": (C.c_long, [C.c_int]),
+    "mgpu_stream": (C.c_void_p, []),
+    "mgpu_set_stream": (C.c_int, [C.c_void_p]),
+    "mgpu_host_register": (C.c_int, [C.c_void_p, C.c_long]),
+    "mgpu_host_unregister": (C.c_int, [C.c_void_p]),
+    "mgpu_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_long]),
+    "mgpu_free": (C.c_int, [C.c_void_p]),
+    "mgpu_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long]),
+    "mgpu_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long]),
+}
+
+
+def declare(lib, prefix):
+    """Attach prototypes for every operator symbol `prefix+name` of OPERATORS to a ctypes library."""
+    for name, (res, args) in OPERATORS.items():
+        fn = getattr(lib, prefix + name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def all_symbols():
+    return ["mgpu_" + n for n in OPERATORS] + list(LIFECYCLE)

@@ -1,0 +1,409 @@
+// Streaming (pointwise / 1-stencil) kernels of the path, planar geometry:
+//   mk_rhoX_flux   Source/mkflux.f90:272 (2-D), :370 (3-D cart)
+//   mk_rhoh_flux   Source/mkflux.f90:920 (2-D), :1070 (3-D cart)
+//   update_scal    Source/update_scal.f90:246 (2-D), :370 (3-D cart)
+//   update_velocity Source/update_vel.f90:174 (2-D), :227 (3-D, spherical==0)
+//   addw0          Source/addw0.f90:133,150
+//   modify_scal_force Source/modify_scal_force.f90:163,206;  pert_form put_in_pert_form.f90:138,162
+//   rhoX<->X       Source/convert_rhoX_to_X.f90:44-56
+//   ghost fill     FBoxLib multifab_fill_boundary (periodic wrap) + Source/multifab_physbc.f90:150,329
+// All are HBM-bound: one thread per zone/face, x-contiguous so every warp reads/writes whole lines.
+#include "mgpu_stream.cuh"
+
+namespace mgpu {
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_rhoX_flux(FluxArgs a, int d, int c) {
+  int ix[3];
+  Box3 fb = a.vb;
+  fb.hi[d] += 1;
+  if (!decode(fb, MGPU_TID, ix)) return;
+  const int r = a.dm - 1;
+  const int ir = ix[r];
+  double rho0_edge, vel = a.umac[d](ix[0], ix[1], ix[2]);
+  if (d != r) {
+    rho0_edge = 0.5 * (a.rho0_old[ir] + a.rho0_new[ir]);
+  } else {
+    rho0_edge = 0.5 * (a.rho0_edge_old[ir] + a.rho0_edge_new[ir]);
+    vel = vel + a.w0[ir];
+  }
+  const DV& se = a.sedge[d];
+  const long o = se.off(ix[0], ix[1], ix[2]);
+  double f;
+  if (a.species_pred_type == MGPU_PREDICT_RHOPRIME_AND_X)
+    f = vel * (rho0_edge + se.p[o + se.cs * a.rho]) * se.p[o + se.cs * c];
+  else if (a.species_pred_type == MGPU_PREDICT_RHOX)
+    f = vel * se.p[o + se.cs * c];
+  else
+    f = vel * se.p[o + se.cs * a.rho] * se.p[o + se.cs * c];
+  a.sflux[d](ix[0], ix[1], ix[2], c) = f;
+  if (d == r && a.evolve_base_state) {
+    double e = a.eta(ix[0], ix[1], ix[2]);
+    if (c >= a.spec0 && c <= a.spec0 + a.nspec - 1) e = e + f;
+    if (c == a.spec0 + a.nspec - 1) e = e - a.w0[ir] * a.rho0_predicted_edge[ir];
+    a.eta(ix[0], ix[1], ix[2]) = e;
+  }
+}
+
+void mk_rhoX_flux_dev(const mgpu_params& P, FluxArgs& a, int startcomp, int endcomp) {
+  Context& cx = ctx();
+  for (int comp = startcomp; comp <= endcomp; ++comp)
+    for (int d = 0; d < P.dm; ++d) {
+      Box3 fb = a.vb;
+      fb.hi[d] += 1;
+      k_rhoX_flux<<<nblocks(fb.npts(), 256), 256, 0, cx.stream>>>(a, d, comp - 1);
+      MGPU_LAUNCH_CHECK();
+    }
+}
+
+__global__ void k_rhoh_flux(FluxArgs a, int d, int mode) {
+  int ix[3];
+  Box3 fb = a.vb;
+  fb.hi[d] += 1;
+  if (!decode(fb, MGPU_TID, ix)) return;
+  const int r = a.dm - 1;
+  const int ir = ix[r];
+  double rho0_edge, rhoh0_edge, vel = a.umac[d](ix[0], ix[1], ix[2]);
+  if (d != r) {
+    rho0_edge = 0.5 * (a.rho0_old[ir] + a.rho0_new[ir]);
+    rhoh0_edge = 0.5 * (a.rhoh0_old[ir] + a.rhoh0_new[ir]);
+  } else {
+    rho0_edge = 0.5 * (a.rho0_edge_old[ir] + a.rho0_edge_new[ir]);
+    rhoh0_edge = 0.5 * (a.rhoh0_edge_old[ir] + a.rhoh0_edge_new[ir]);
+    vel = vel + a.w0[ir];
+  }
+  const DV& se = a.sedge[d];
+  const long o = se.off(ix[0], ix[1], ix[2]);
+  const double erho = se.p[o + se.cs * a.rho], erhoh = se.p[o + se.cs * a.rhoh];
+  double f;
+  if (mode == 0) {  // have_h
+    if (a.species_pred_type == MGPU_PREDICT_RHOPRIME_AND_X)
+      f = vel * (rho0_edge + erho) * erhoh;
+    else
+      f = vel * erho * erhoh;
+  } else if (mode == 1) {  // have_rhoh
+    f = vel * erhoh;
+  } else {  // (rho h)'
+    f = vel * (rhoh0_edge + erhoh);
+  }
+  a.sflux[d](ix[0], ix[1], ix[2], a.rhoh) = f;
+}
+
+void mk_rhoh_flux_dev(const mgpu_params& P, FluxArgs& a) {
+  Context& cx = ctx();
+  const int ept = P.enthalpy_pred_type;
+  const bool have_h = (ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H);
+  if (ept == MGPU_PREDICT_HPRIME) throw Error("mk_rhoh_flux : predict_hprime not coded yet");  // mkflux.f90:1167
+  const int mode = have_h ? 0 : (ept == MGPU_PREDICT_RHOH ? 1 : 2);
+  for (int d = 0; d < P.dm; ++d) {
+    Box3 fb = a.vb;
+    fb.hi[d] += 1;
+    k_rhoh_flux<<<nblocks(fb.npts(), 256), 256, 0, cx.stream>>>(a, d, mode);
+    MGPU_LAUNCH_CHECK();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_update_scal(UpdArgs a, int c) {
+  int ix[3];
+  if (!decode(a.vb, MGPU_TID, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  double divterm = (a.sflux[0](i + 1, j, k, c) - a.sflux[0](i, j, k, c)) / a.dx[0] +
+                   (a.sflux[1](i, j + 1, k, c) - a.sflux[1](i, j, k, c)) / a.dx[1];
+  if (a.dm == 3) divterm = divterm + (a.sflux[2](i, j, k + 1, c) - a.sflux[2](i, j, k, c)) / a.dx[2];
+  a.snew(i, j, k, c) = a.sold(i, j, k, c) + a.dt * (-divterm + a.force(i, j, k, c));
+}
+
+__global__ void k_copy(double* dst, const double* src, long n) {
+  long t = MGPU_TID;
+  if (t < n) dst[t] = src[t];
+}
+__global__ void k_set(double* dst, double v, long n) {
+  long t = MGPU_TID;
+  if (t < n) dst[t] = v;
+}
+
+// density from the species updates + floor + negative-species redistribution, update_scal.f90:453-505
+__global__ void k_update_rho(UpdArgs a, int c0, int c1, int rho, double bcd) {
+  int ix[3];
+  if (!decode(a.vb, MGPU_TID, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  const long on = a.snew.off(i, j, k), oo = a.sold.off(i, j, k);
+  double* sn = a.snew.p + on;
+  const double* so = a.sold.p + oo;
+  const long cn = a.snew.cs, co = a.sold.cs;
+  bool neg = false;
+  double r = sn[cn * rho];
+  for (int c = c0; c <= c1; ++c) {
+    r = r + (sn[cn * c] - so[co * c]);
+    if (sn[cn * c] < 0.0) neg = true;
+  }
+  if (r < 0.5 * bcd) {
+    for (int c = c0; c <= c1; ++c) sn[cn * c] = sn[cn * c] * 0.5 * bcd / r;
+    r = 0.5 * bcd;
+  }
+  sn[cn * rho] = r;
+  if (neg) {
+    for (int c = c0; c <= c1; ++c) {
+      if (sn[cn * c] < 0.0) {
+        double delta = -sn[cn * c];
+        double sumX = 0.0;
+        for (int c2 = c0; c2 <= c1; ++c2)
+          if (c2 != c && sn[cn * c2] >= 0.0) sumX = sumX + sn[cn * c2];
+        for (int c2 = c0; c2 <= c1; ++c2)
+          if (c2 != c && sn[cn * c2] >= 0.0) {
+            double frac = sn[cn * c2] / sumX;
+            sn[cn * c2] = sn[cn * c2] - frac * delta;
+          }
+        sn[cn * c] = 0.0;
+      }
+    }
+  }
+}
+
+void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop) {
+  Context& cx = ctx();
+  const long nv = a.vb.npts();
+  for (int comp = nstart; comp <= nstop; ++comp) {
+    k_update_scal<<<nblocks(nv, 256), 256, 0, cx.stream>>>(a, comp - 1);
+    MGPU_LAUNCH_CHECK();
+  }
+  if (nstart == P.spec_comp && nstop == P.spec_comp + P.nspec - 1) {
+    const int rho = P.rho_comp - 1;
+    if (a.snew.cs != a.sold.cs) throw Error("update_scal: sold and snew must have the same ghost width");
+    k_copy<<<nblocks(a.snew.cs, 256), 256, 0, cx.stream>>>(a.snew.p + a.snew.cs * rho, a.sold.p + a.sold.cs * rho,
+                                                          a.snew.cs);
+    MGPU_LAUNCH_CHECK();
+    k_update_rho<<<nblocks(nv, 256), 256, 0, cx.stream>>>(a, nstart - 1, nstop - 1, rho, P.base_cutoff_density);
+    MGPU_LAUNCH_CHECK();
+  }
+}
+
+// dst comp = sum of ncomp comps starting at c0 (multifab_copy_c + multifab_plus_plus_c, density_advance.f90:204-213)
+__global__ void k_sum_comps(DV a, int dst, int c0, int ncomp) {
+  long t = MGPU_TID;
+  if (t >= a.cs) return;
+  double r = a.p[t + a.cs * c0];
+  for (int n = 1; n < ncomp; ++n) r = r + a.p[t + a.cs * (c0 + n)];
+  a.p[t + a.cs * dst] = r;
+}
+void sum_comps_dev(const DV& a, int dst, int c0, int ncomp) {
+  k_sum_comps<<<nblocks(a.cs, 256), 256, 0, ctx().stream>>>(a, dst, c0, ncomp);
+  MGPU_LAUNCH_CHECK();
+}
+
+void set_dev(double* p, double v, long n) {
+  k_set<<<nblocks(n, 256), 256, 0, ctx().stream>>>(p, v, n);
+  MGPU_LAUNCH_CHECK();
+}
+void copy_dev(double* dst, const double* src, long n) {
+  k_copy<<<nblocks(n, 256), 256, 0, ctx().stream>>>(dst, src, n);
+  MGPU_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_update_vel(VelArgs a) {
+  int ix[3];
+  if (!decode(a.vb, MGPU_TID, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  const int dm = a.dm, r = dm - 1;
+  double bar[3];
+  bar[0] = 0.5 * (a.umac[0](i, j, k) + a.umac[0](i + 1, j, k));
+  bar[1] = 0.5 * (a.umac[1](i, j, k) + a.umac[1](i, j + 1, k));
+  bar[2] = (dm == 3) ? 0.5 * (a.umac[2](i, j, k) + a.umac[2](i, j, k + 1)) : 0.0;
+  const int ir = ix[r];
+  const double wbar = 0.5 * (a.w0[ir] + a.w0[ir + 1]);
+  for (int n = 0; n < dm; ++n) {
+    double ugrad = bar[0] * (a.uedge[0](i + 1, j, k, n) - a.uedge[0](i, j, k, n)) / a.dx[0] +
+                   bar[1] * (a.uedge[1](i, j + 1, k, n) - a.uedge[1](i, j, k, n)) / a.dx[1];
+    if (dm == 3) ugrad = ugrad + bar[2] * (a.uedge[2](i, j, k + 1, n) - a.uedge[2](i, j, k, n)) / a.dx[2];
+    double un = a.uold(i, j, k, n) - a.dt * ugrad + a.dt * a.force(i, j, k, n);
+    const double hi_e = (r == 1) ? a.uedge[1](i, j + 1, k, n) : a.uedge[2](i, j, k + 1, n);
+    const double lo_e = a.uedge[r](i, j, k, n);
+    un = un - a.dt * wbar * (hi_e - lo_e) / a.dx[r];
+    if (a.do_sponge) un = un * a.sponge(i, j, k);
+    a.unew(i, j, k, n) = un;
+  }
+}
+void update_velocity_dev(VelArgs& a) {
+  k_update_vel<<<nblocks(a.vb.npts(), 256), 256, 0, ctx().stream>>>(a);
+  MGPU_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_addw0(DV wm, Box3 b, int r, const double* w0, double mult) {
+  int ix[3];
+  if (!decode(b, MGPU_TID, ix)) return;
+  wm(ix[0], ix[1], ix[2]) = wm(ix[0], ix[1], ix[2]) + mult * w0[ix[r]];
+}
+void addw0_dev(const mgpu_params& P, DV* umac, const double* w0_dev, double mult, const int* lo, const int* hi) {
+  const int r = P.dm - 1;
+  Box3 b = grown(lo, hi, P.dm, 1);
+  b.lo[r] = lo[r];
+  b.hi[r] = hi[r] + 1;
+  k_addw0<<<nblocks(b.npts(), 256), 256, 0, ctx().stream>>>(umac[r], b, r, w0_dev, mult);
+  MGPU_LAUNCH_CHECK();
+}
+
+__global__ void k_modify_scal_force(DV force, DV s, DV u, DV v, DV w, Box3 vb, int dm, const double* s0,
+                                    const double* s0_edge, const double* w0, double dx0, double dx1, double dx2,
+                                    bool fullform) {
+  int ix[3];
+  if (!decode(vb, MGPU_TID, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  const int ir = ix[dm - 1];
+  double divu, divs0u, f = force(i, j, k);
+  if (dm == 2) {
+    divu = (u(i + 1, j, k) - u(i, j, k)) / dx0 + (v(i, j + 1, k) - v(i, j, k)) / dx1;
+    divu = divu + (w0[ir + 1] - w0[ir]) / dx1;
+    if (fullform) {
+      f = f - s(i, j, k) * divu;
+    } else {
+      divs0u = s0[ir] * (u(i + 1, j, k) - u(i, j, k)) / dx0 +
+               (v(i, j + 1, k) * s0_edge[ir + 1] - v(i, j, k) * s0_edge[ir]) / dx1;
+      f = f - (s(i, j, k) - s0[ir]) * divu - divs0u;
+    }
+  } else {
+    divu = (u(i + 1, j, k) - u(i, j, k)) / dx0 + (v(i, j + 1, k) - v(i, j, k)) / dx1 +
+           (w(i, j, k + 1) - w(i, j, k)) / dx2;
+    divu = divu + (w0[ir + 1] - w0[ir]) / dx2;
+    if (fullform) {
+      f = f - s(i, j, k) * divu;
+    } else {
+      divs0u = s0[ir] * ((u(i + 1, j, k) - u(i, j, k)) / dx0 + (v(i, j + 1, k) - v(i, j, k)) / dx1) +
+               (w(i, j, k + 1) * s0_edge[ir + 1] - w(i, j, k) * s0_edge[ir]) / dx2;
+      f = f - (s(i, j, k) - s0[ir]) * divu - divs0u;
+    }
+  }
+  force(i, j, k) = f;
+}
+void modify_scal_force_dev(const mgpu_params& P, const DV& force, const DV& s, const DV* umac, const double* s0,
+                           const double* s0_edge, const double* w0, int comp, bool fullform, const int* lo,
+                           const int* hi) {
+  Box3 vb = grown(lo, hi, P.dm, 0);
+  k_modify_scal_force<<<nblocks(vb.npts(), 256), 256, 0, ctx().stream>>>(
+      force.comp(comp - 1), s.comp(comp - 1), umac[0], umac[1], P.dm == 3 ? umac[2] : umac[1], vb, P.dm, s0, s0_edge,
+      w0, P.dx[0], P.dx[1], P.dx[2], fullform);
+  MGPU_LAUNCH_CHECK();
+}
+
+// op: 0 = a/b, 1 = a*b (b = another component), 2 = a + mult*base(ir)
+__global__ void k_pointwise(DV a, DV b, Box3 vb, int op, int r, const double* base, double mult) {
+  int ix[3];
+  if (!decode(vb, MGPU_TID, ix)) return;
+  double& x = a(ix[0], ix[1], ix[2]);
+  if (op == 0) x = x / b(ix[0], ix[1], ix[2]);
+  else if (op == 1) x = x * b(ix[0], ix[1], ix[2]);
+  else x = x + mult * base[ix[r]];
+}
+void convert_rhoX_to_X_dev(const mgpu_params& P, const DV& s, bool flag, const int* lo, const int* hi) {
+  Box3 vb = grown(lo, hi, P.dm, 0);
+  for (int n = 0; n < P.nspec; ++n) {
+    k_pointwise<<<nblocks(vb.npts(), 256), 256, 0, ctx().stream>>>(s.comp(P.spec_comp - 1 + n), s.comp(P.rho_comp - 1),
+                                                                  vb, flag ? 0 : 1, 0, nullptr, 0.0);
+    MGPU_LAUNCH_CHECK();
+  }
+}
+void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_dev, int comp, bool flag,
+                          const int* lo, const int* hi) {
+  Box3 vb = grown(lo, hi, P.dm, 0);
+  k_pointwise<<<nblocks(vb.npts(), 256), 256, 0, ctx().stream>>>(s.comp(comp - 1), s.comp(comp - 1), vb, 2, P.dm - 1,
+                                                                base_dev, flag ? -1.0 : 1.0);
+  MGPU_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// ghost fill.  Periodic wrap in direction d over the full allocated transverse extent (done for
+// d = x, y, z in turn, so edges/corners come out right), then physbc in the reference's order.
+__global__ void k_wrap(DV a, Box3 tb, int d, int lo, int hi, int ng, int nodal) {
+  int ix[3];
+  if (!decode(tb, MGPU_TID, ix)) return;  // tb: d collapsed to [0, 2*ng-1] = ghost slot
+  const int g = ix[d];                    // 0..ng-1: lo side, ng..2ng-1: hi side
+  const int n = hi - lo + 1;
+  int dst, src;
+  if (g < ng) {
+    dst = lo - 1 - g;
+    src = dst + n;
+  } else {
+    dst = hi + nodal + 1 + (g - ng);
+    src = dst - n;
+  }
+  int id[3] = {ix[0], ix[1], ix[2]}, is[3] = {ix[0], ix[1], ix[2]};
+  id[d] = dst;
+  is[d] = src;
+  a(id[0], id[1], id[2]) = a(is[0], is[1], is[2]);
+}
+
+__global__ void k_physbc(DV s, Box3 tb, int d, int side, int bc, int lo, int hi, int ng) {
+  int ix[3];
+  if (!decode(tb, MGPU_TID, ix)) return;  // tb: d collapsed to a single index
+  const int e = (side == 0) ? lo : hi;
+  const int sg = (side == 0) ? -1 : 1;
+  const long st = s.stride(d);
+  int ib[3] = {ix[0], ix[1], ix[2]};
+  ib[d] = e;
+  double* q = s.p + s.off(ib[0], ib[1], ib[2]);  // first valid cell next to the wall
+  if (bc == MGPU_BC_EXT_DIR) {
+    for (int g = 1; g <= ng; ++g) q[sg * g * st] = 0.0;
+  } else if (bc == MGPU_BC_FOEXTRAP) {
+    for (int g = 1; g <= ng; ++g) q[sg * g * st] = q[0];
+  } else if (bc == MGPU_BC_HOEXTRAP) {
+    const double v = (15.0 * q[0] - 10.0 * q[-sg * st] + 3.0 * q[-2 * sg * st]) * 0.125;
+    for (int g = 1; g <= ng; ++g) q[sg * g * st] = v;
+  } else if (bc == MGPU_BC_REFLECT_EVEN) {
+    for (int g = 1; g <= ng; ++g) q[sg * g * st] = q[-sg * (g - 1) * st];
+  } else if (bc == MGPU_BC_REFLECT_ODD) {
+    for (int g = 1; g <= ng; ++g) q[sg * g * st] = -q[-sg * (g - 1) * st];
+  }
+}
+
+void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, const int* hi, int ng,
+                       const int* nodal, int scomp, int bccomp, int ncomp, const int* adv_bc, const int* pmask,
+                       bool same_boundary) {
+  Context& cx = ctx();
+  const int dm = P.dm;
+  if (ng == 0) return;
+  const bool is_nodal = nodal && (nodal[0] || nodal[1] || nodal[2]);
+  for (int n = 0; n < ncomp; ++n) {
+    DV s = sfull.comp(scomp - 1 + n);
+    for (int d = 0; d < dm; ++d) {
+      if (!pmask[d]) continue;
+      Box3 tb;
+      for (int q = 0; q < 3; ++q) { tb.lo[q] = s.lo[q]; tb.hi[q] = s.lo[q] + s.n[q] - 1; }
+      tb.lo[d] = 0;
+      tb.hi[d] = 2 * ng - 1;
+      k_wrap<<<nblocks(tb.npts(), 256), 256, 0, cx.stream>>>(s, tb, d, lo[d], hi[d], ng, nodal ? nodal[d] : 0);
+      MGPU_LAUNCH_CHECK();
+    }
+    if (is_nodal) continue;  // multifab_physbc_edgevel (FBoxLib) is left to the caller
+    const int bcc = same_boundary ? bccomp : bccomp + n;
+    int bc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    for (int d = 0; d < dm; ++d) {
+      bc[d][0] = adv_bc[d + dm * (0 + 2 * (bcc - 1))];
+      bc[d][1] = adv_bc[d + dm * (1 + 2 * (bcc - 1))];
+    }
+    for (int d = 0; d < dm; ++d)
+      for (int side = 0; side < 2; ++side) {
+        const int b = bc[d][side];
+        if (b == MGPU_BC_INTERIOR || b == MGPU_BC_PERIODIC) continue;
+        if (b != MGPU_BC_EXT_DIR && b != MGPU_BC_FOEXTRAP && b != MGPU_BC_HOEXTRAP && b != MGPU_BC_REFLECT_EVEN &&
+            b != MGPU_BC_REFLECT_ODD)
+          throw Error("physbc: bc not yet supported");
+        Box3 tb;
+        for (int t = 0; t < 3; ++t) {
+          if (t >= dm || t == d) { tb.lo[t] = tb.hi[t] = 0; continue; }
+          int glo = ng, ghi = ng;
+          if (t > d && b != MGPU_BC_EXT_DIR) {
+            glo = (bc[t][0] == MGPU_BC_INTERIOR) ? ng : 0;
+            ghi = (bc[t][1] == MGPU_BC_INTERIOR) ? ng : 0;
+          }
+          tb.lo[t] = lo[t] - glo;
+          tb.hi[t] = hi[t] + ghi;
+        }
+        k_physbc<<<nblocks(tb.npts(), 256), 256, 0, cx.stream>>>(s, tb, d, side, b, lo[d], hi[d], ng);
+        MGPU_LAUNCH_CHECK();
+      }
+  }
+}
+
+}  // namespace mgpu

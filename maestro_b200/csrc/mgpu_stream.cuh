@@ -1,0 +1,51 @@
+// Argument blocks + host launchers of the streaming kernels (see mgpu_stream.cu).
+#pragma once
+#include "mgpu_common.cuh"
+
+namespace mgpu {
+
+struct FluxArgs {
+  int dm, species_pred_type;
+  bool evolve_base_state;
+  int rho, rhoh, spec0, nspec;  // 0-based component indices
+  Box3 vb;
+  DV sflux[3], sedge[3], umac[3], eta;
+  // base state (device pointers)
+  const double *w0, *rho0_old, *rho0_edge_old, *rho0_new, *rho0_edge_new, *rho0_predicted_edge;
+  const double *rhoh0_old, *rhoh0_edge_old, *rhoh0_new, *rhoh0_edge_new;
+};
+void mk_rhoX_flux_dev(const mgpu_params& P, FluxArgs& a, int startcomp, int endcomp);
+void mk_rhoh_flux_dev(const mgpu_params& P, FluxArgs& a);
+
+struct UpdArgs {
+  int dm;
+  double dt, dx[3];
+  Box3 vb;
+  DV sold, snew, force, sflux[3];
+};
+void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop);
+
+struct VelArgs {
+  int dm;
+  bool do_sponge;
+  double dt, dx[3];
+  Box3 vb;
+  DV uold, unew, force, sponge, umac[3], uedge[3];
+  const double* w0;
+};
+void update_velocity_dev(VelArgs& a);
+
+void addw0_dev(const mgpu_params& P, DV* umac, const double* w0_dev, double mult, const int* lo, const int* hi);
+void modify_scal_force_dev(const mgpu_params& P, const DV& force, const DV& s, const DV* umac, const double* s0,
+                           const double* s0_edge, const double* w0, int comp, bool fullform, const int* lo,
+                           const int* hi);
+void convert_rhoX_to_X_dev(const mgpu_params& P, const DV& s, bool flag, const int* lo, const int* hi);
+void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_dev, int comp, bool flag,
+                          const int* lo, const int* hi);
+void fill_boundary_dev(const mgpu_params& P, const DV& s, const int* lo, const int* hi, int ng, const int* nodal,
+                       int scomp, int bccomp, int ncomp, const int* adv_bc, const int* pmask, bool same_boundary);
+void sum_comps_dev(const DV& a, int dst, int c0, int ncomp);
+void set_dev(double* p, double v, long n);
+void copy_dev(double* dst, const double* src, long n);
+
+}  // namespace mgpu

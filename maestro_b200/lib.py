@@ -1,0 +1,69 @@
+"""Loader of the CUDA C-ABI library (maestro_b200/lib/libmaestro_b200.so, built in-tree for sm_100a).
+
+There is no CPU path: if the library is missing, or no CUDA device is present when `init()` is
+called, this raises -- it never falls back to the oracle or to PyTorch ops.
+"""
+import ctypes as C
+import os
+
+from . import abi
+from .operators import MaestroError, Operators
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmaestro_b200.so")
+
+_lib = None
+_ops = None
+
+
+def load():
+    """dlopen the library and declare every prototype (works without a GPU; no compute is done)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MaestroError(
+                "CUDA library %s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        abi.declare(_lib, "mgpu_")
+        for name, (res, args) in abi.LIFECYCLE.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def init(device=0, use_torch_stream=False):
+    """Bind this process to one GPU.  With use_torch_stream the library launches on torch's current
+    stream so torch.cuda.Event timing brackets its kernels."""
+    lib = load()
+    if lib.mgpu_init(int(device)) != 0:
+        raise MaestroError(lib.mgpu_last_error().decode())
+    if use_torch_stream:
+        import torch
+
+        s = torch.cuda.current_stream(device).cuda_stream
+        if lib.mgpu_set_stream(C.c_void_p(s)) != 0:
+            raise MaestroError(lib.mgpu_last_error().decode())
+    return ops()
+
+
+def ops():
+    global _ops
+    if _ops is None:
+        _ops = Operators(load(), "mgpu_")
+    return _ops
+
+
+def synchronize():
+    if load().mgpu_synchronize() != 0:
+        raise MaestroError(_lib.mgpu_last_error().decode())
+
+
+def launch_count(reset=False):
+    return int(load().mgpu_launch_count(1 if reset else 0))
+
+
+def finalize():
+    if _lib is not None:
+        _lib.mgpu_finalize()

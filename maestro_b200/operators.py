@@ -1,0 +1,138 @@
+"""Host-side mirror of the reference's multifab-level (L3/L4) operators for this path.
+
+Same names, argument order and meaning as the Fortran routines they stand for, so that parity tests
+read like the reference's own drivers:
+
+    make_edge_scal   Source/make_edge_scal.f90:26      mk_rhoX_flux  Source/mkflux.f90:48
+    bds              Source/bds.f90:16                 mk_rhoh_flux  Source/mkflux.f90:652
+    update_scal      Source/update_scal.f90:16         update_velocity Source/update_vel.f90:15
+    addw0            Source/addw0.f90:19               mkutrans / velpred  mkutrans.f90:17 / velpred.f90:21
+    modify_scal_force / convert_rhoX_to_X / put_in_pert_form (glue)
+    density_advance  Source/density_advance.f90:20
+
+`Operators(lib, prefix)` binds the wrappers to any library exporting the ABI; the product binds the
+CUDA library (prefix "mgpu_"), the tests additionally bind the CPU oracle (prefix "mo_").
+Errors follow the reference convention (`bl_error` -> abort): a nonzero return raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .fab import as_double_p, as_int_p, fab_pp, fab_ptr
+
+
+class MaestroError(RuntimeError):
+    pass
+
+
+class Operators:
+    def __init__(self, lib, prefix):
+        self.lib = abi.declare(lib, prefix)
+        self.prefix = prefix
+        self._err = getattr(lib, prefix + "last_error")
+        self._err.restype = C.c_char_p
+
+    def _call(self, name, *args):
+        rc = getattr(self.lib, self.prefix + name)(*args)
+        if rc != 0:
+            raise MaestroError("%s%s: %s" % (self.prefix, name, self._err().decode()))
+
+    # ---- ghost fill ----------------------------------------------------------------------------
+    def fill_boundary(self, p, s, scomp, bccomp, ncomp, adv_bc, pmask):
+        bc, bcp = as_int_p(adv_bc)
+        pm, pmp = as_int_p(pmask)
+        f = fab_ptr(s)
+        self._call("fill_boundary", C.byref(p), f, scomp, bccomp, ncomp, bcp, pmp)
+
+    # ---- edge states ---------------------------------------------------------------------------
+    def make_edge_scal(self, p, s, sedge, umac, force, adv_bc, is_vel, start_scomp, start_bccomp, num_comp,
+                       is_conservative):
+        bc, bcp = as_int_p(adv_bc)
+        sf, ff = fab_ptr(s), fab_ptr(force)
+        se, k1 = fab_pp(sedge)
+        um, k2 = fab_pp(umac)
+        name = "bds" if p.bds_type == 1 else "make_edge_scal"
+        self._call(name, C.byref(p), 1, sf, se, um, ff, bcp, int(is_vel), start_scomp, start_bccomp, num_comp,
+                   int(is_conservative))
+
+    bds = make_edge_scal
+
+    # ---- fluxes --------------------------------------------------------------------------------
+    def mk_rhoX_flux(self, p, sflux, etarhoflux, sedge, umac, w0, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new,
+                     rho0_predicted_edge, startcomp, endcomp):
+        keep = [as_double_p(x) for x in (w0, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new, rho0_predicted_edge)]
+        sf, k1 = fab_pp(sflux)
+        se, k2 = fab_pp(sedge)
+        um, k3 = fab_pp(umac)
+        eta = fab_ptr(etarhoflux)
+        self._call("mk_rhoX_flux", C.byref(p), 1, sf, eta, se, um, *[k[1] for k in keep], startcomp, endcomp)
+
+    def mk_rhoh_flux(self, p, sflux, sedge, umac, w0, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new, rhoh0_old,
+                     rhoh0_edge_old, rhoh0_new, rhoh0_edge_new):
+        keep = [as_double_p(x) for x in (w0, rho0_old, rho0_edge_old, rho0_new, rho0_edge_new, rhoh0_old,
+                                         rhoh0_edge_old, rhoh0_new, rhoh0_edge_new)]
+        sf, k1 = fab_pp(sflux)
+        se, k2 = fab_pp(sedge)
+        um, k3 = fab_pp(umac)
+        self._call("mk_rhoh_flux", C.byref(p), 1, sf, se, um, *[k[1] for k in keep])
+
+    # ---- updates -------------------------------------------------------------------------------
+    def update_scal(self, p, nstart, nstop, sold, snew, sflux, scal_force):
+        sf, k1 = fab_pp(sflux)
+        self._call("update_scal", C.byref(p), 1, nstart, nstop, fab_ptr(sold), fab_ptr(snew), sf, fab_ptr(scal_force))
+
+    def update_velocity(self, p, uold, unew, umac, uedge, force, sponge, w0):
+        w, wp = as_double_p(w0)
+        um, k1 = fab_pp(umac)
+        ue, k2 = fab_pp(uedge)
+        self._call("update_velocity", C.byref(p), 1, fab_ptr(uold), fab_ptr(unew), um, ue, fab_ptr(force),
+                   fab_ptr(sponge), wp)
+
+    def addw0(self, p, umac, w0, mult):
+        w, wp = as_double_p(w0)
+        um, k1 = fab_pp(umac)
+        self._call("addw0", C.byref(p), 1, um, wp, float(mult))
+
+    # ---- velocity prediction -------------------------------------------------------------------
+    def mkutrans(self, p, utilde, ufull, utrans, w0, adv_bc, phys_bc):
+        w, wp = as_double_p(w0)
+        bc, bcp = as_int_p(adv_bc)
+        pb, pbp = as_int_p(phys_bc)
+        ut, k1 = fab_pp(utrans)
+        self._call("mkutrans", C.byref(p), 1, fab_ptr(utilde), fab_ptr(ufull), ut, wp, bcp, pbp)
+
+    def velpred(self, p, utilde, ufull, umac, utrans, force, w0, adv_bc, phys_bc):
+        w, wp = as_double_p(w0)
+        bc, bcp = as_int_p(adv_bc)
+        pb, pbp = as_int_p(phys_bc)
+        um, k1 = fab_pp(umac)
+        ut, k2 = fab_pp(utrans)
+        self._call("velpred", C.byref(p), 1, fab_ptr(utilde), fab_ptr(ufull), um, ut, fab_ptr(force), wp, bcp, pbp)
+
+    # ---- glue ----------------------------------------------------------------------------------
+    def modify_scal_force(self, p, force, s, umac, s0, s0_edge, w0, comp, fullform=False):
+        keep = [as_double_p(x) for x in (s0, s0_edge, w0)]
+        um, k1 = fab_pp(umac)
+        self._call("modify_scal_force", C.byref(p), 1, fab_ptr(force), fab_ptr(s), um, *[k[1] for k in keep], comp,
+                   int(fullform))
+
+    def convert_rhoX_to_X(self, p, s, flag):
+        self._call("convert_rhoX_to_X", C.byref(p), 1, fab_ptr(s), int(flag))
+
+    def put_in_pert_form(self, p, s, base, comp, flag):
+        b, bp = as_double_p(base)
+        self._call("put_in_pert_form", C.byref(p), 1, fab_ptr(s), bp, comp, int(flag))
+
+    # ---- L4 driver -----------------------------------------------------------------------------
+    def density_advance(self, p, which_step, sold, snew, sedge, sflux, scal_force, umac, w0, etarhoflux, rho0_old,
+                        rho0_new, p0_dummy, rho0_predicted_edge, adv_bc, pmask):
+        keep = [as_double_p(x) for x in (w0, rho0_old, rho0_new, p0_dummy, rho0_predicted_edge)]
+        bc, bcp = as_int_p(adv_bc)
+        pm, pmp = as_int_p(pmask)
+        se, k1 = fab_pp(sedge)
+        sf, k2 = fab_pp(sflux)
+        um, k3 = fab_pp(umac)
+        self._call("density_advance", C.byref(p), which_step, fab_ptr(sold), fab_ptr(snew), se, sf,
+                   fab_ptr(scal_force), um, keep[0][1], fab_ptr(etarhoflux), keep[1][1], keep[2][1], keep[3][1],
+                   keep[4][1], bcp, pmp)

@@ -1,0 +1,143 @@
+"""CPU tests of the oracle itself (no GPU): pins against the reference's own test properties
+(Exec/UNIT_TESTS/test_advect), committed golden vectors, loop-range validation with the
+bounds-checked build, and analytic invariants for the rows the reference has no test for."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from maestro_b200 import Fab, abi, face_fabs
+from synth import make_state, relerr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "test_advect_norms.json")))
+
+WALLS_3D = [[abi.PERIODIC, abi.PERIODIC], [abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]
+INOUT_3D = [[abi.INLET, abi.OUTLET], [abi.NO_SLIP_WALL, abi.SLIP_WALL], [abi.SYMMETRY, abi.SYMMETRY]]
+WALLS_2D = [[abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]
+INOUT_2D = [[abi.SYMMETRY, abi.INLET], [abi.OUTLET, abi.NO_SLIP_WALL]]
+
+
+@pytest.mark.parametrize("dm,n,tol", [(2, 32, 5e-13), (3, 16, 5e-14)])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+def test_advect_direction_independence(oracle, dm, n, ppm_type, tol):
+    """The reference's own pass criterion (test_advect/varden.f90:642-668): errors of the 2*dm
+    advection directions agree to advect_test_tol (5e-13 in 2-D inputs_2d, 5e-14 in 3-D inputs_3d)."""
+    norms = [oracle_lib.test_advect(oracle, dm, n, ppm_type, 0, sgn * (d + 1), stop_time=0.25)
+             for d in range(dm) for sgn in (1, -1)]
+    a = np.array([x[0] for x in norms])
+    r = np.array([x[1] for x in norms])
+    assert a.max() - a.min() < tol * a.max()
+    assert r.max() - r.min() < tol * r.max()
+
+
+@pytest.mark.parametrize("key", sorted(GOLD["cases"]))
+def test_advect_golden_norms(oracle, key):
+    """Regression against committed oracle outputs (tests/golden/make_golden.py)."""
+    c = GOLD["cases"][key]
+    a, r = oracle_lib.test_advect(oracle, c["dm"], c["n"], c["ppm_type"], 0, c["dir"], stop_time=c["stop_time"])
+    assert abs(a - c["abs"]) <= 1e-13 * c["abs"]
+    assert abs(r - c["rel"]) <= 1e-13 * c["rel"]
+
+
+def test_archived_report_is_soft():
+    """advect_3d_report_example.out predates the current driver (soft golden): its absolute
+    norms are recorded next to the oracle's 64^3 values (make_golden.py --full), not gated.  What both
+    share is the ordering ppm 0 > 1 > 2 and direction independence (gated above)."""
+    ref, mine = GOLD["archived_3d_64"], GOLD["oracle_3d_64"]
+    assert ref["ppm0"] > ref["ppm1"] > ref["ppm2"]
+    assert mine["ppm0"]["abs"] > mine["ppm1"]["abs"] > mine["ppm2"]["abs"]
+
+
+@pytest.mark.parametrize("dm,n", [(2, 12), (3, 8)])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
+def test_bounds_checked_build_agrees(oracle, dm, n, ppm_type, bcset):
+    """Every restated loop range is inside the reference's array bounds (abort otherwise) and the
+    checked build gives the same bits as the optimised one."""
+    dbg = oracle_lib.load(debug=True)
+    phys = {"periodic": None, "walls": WALLS_3D if dm == 3 else WALLS_2D,
+            "inout": INOUT_3D if dm == 3 else INOUT_2D}[bcset]
+    for cons in (False, True):
+        st = make_state(dm, n, phys_bc=phys, ppm_type=ppm_type)
+        p = st["p"]
+        out = []
+        for o in (oracle, dbg):
+            sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+            o.make_edge_scal(p, st["s"], sedge, st["umac"], st["force"], st["adv_bc"], False, 1, dm + 1, p.nscal, cons)
+            o.make_edge_scal(p, st["s"], sedge, st["umac"], st["force"], st["adv_bc"], True, 1, 1, dm, cons)
+            out.append(sedge)
+        for d in range(dm):
+            assert np.array_equal(out[0][d].a, out[1][d].a)
+            assert np.isfinite(out[0][d].a).all()
+
+
+@pytest.mark.parametrize("dm,n", [(2, 16), (3, 10)])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+@pytest.mark.parametrize("bcset", ["periodic", "walls"])
+def test_uniform_state_is_preserved(oracle, dm, n, ppm_type, bcset):
+    """Invariant for rows without a reference test: a constant scalar in a sheared, divergent velocity
+    field has edge states equal to the constant (advective form), whatever the limiter/BC branch."""
+    phys = None if bcset == "periodic" else (WALLS_3D if dm == 3 else WALLS_2D)
+    st = make_state(dm, n, phys_bc=phys, ppm_type=ppm_type)
+    p = st["p"]
+    st["s"].a[...] = 3.25
+    st["force"].a[...] = 0.0
+    sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+    oracle.make_edge_scal(p, st["s"], sedge, st["umac"], st["force"], st["adv_bc"], False, 1, dm + 1, 2, False)
+    for d in range(dm):
+        assert np.abs(sedge[d].a[:2] - 3.25).max() < 1e-14
+
+
+@pytest.mark.parametrize("dm,n", [(2, 16), (3, 10)])
+def test_conservation(oracle, dm, n):
+    """Periodic box: sum(snew) - sum(sold) = dt*sum(force) exactly up to rounding (update_scal.f90:401-415)."""
+    st = make_state(dm, n)
+    p, b = st["p"], st["base"]
+    oracle.fill_boundary(p, st["s"], 1, dm + 1, p.nscal, st["adv_bc"], st["pmask"])
+    for u in st["umac"]:
+        oracle.fill_boundary(p, u, 1, 1, 1, st["adv_bc"], st["pmask"])
+    # make umac periodic-consistent: face hi+1 == face lo
+    for d, u in enumerate(st["umac"]):
+        v = u.valid(0)
+        sl_hi = [slice(None)] * 3
+        sl_lo = [slice(None)] * 3
+        sl_hi[2 - d], sl_lo[2 - d] = -1, 0
+        v[tuple(sl_hi)] = v[tuple(sl_lo)]
+    sold = st["s"].clone()
+    snew = sold.clone()
+    sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+    sflux = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+    eta = Fab(st["lo"], st["hi"], 0, 1, nodal=[1 if d == dm - 1 else 0 for d in range(3)], dm=dm)
+    zero = np.zeros(p.nr + 1)
+    oracle.density_advance(p, 1, sold, snew, sedge, sflux, st["force"], st["umac"], zero, eta, zero[:-1],
+                           zero[:-1], zero[:-1], zero, st["adv_bc"], st["pmask"])
+    for c in range(p.spec_comp - 1, p.spec_comp - 1 + p.nspec):
+        d0 = snew.valid(c).sum() - st["s"].valid(c).sum()
+        assert abs(d0) < 1e-10 * np.abs(st["s"].valid(c)).sum()
+    # sold round trips (rhoX -> X -> rhoX, rho -> rho' -> rho) stay within an ulp or two
+    assert relerr(sold.valid(), st["s"].valid()) < 1e-15
+
+
+def test_mirror_symmetry_across_reflecting_wall(oracle):
+    """SYMMETRY walls: an even state with an odd normal velocity gives edge states that are mirror
+    images; checks the REFLECT_EVEN/ODD branches against a periodic-free analytic property."""
+    dm, n = 2, 16
+    phys = [[abi.SYMMETRY, abi.SYMMETRY], [abi.PERIODIC, abi.PERIODIC]]
+    st = make_state(dm, n, phys_bc=phys, ppm_type=1, vel="B", noise=0.0)
+    p = st["p"]
+    s = st["s"]
+    v = s.a
+    v[...] = 0.5 * (v + v[..., ::-1])  # even in x about the domain centre
+    oracle.fill_boundary(p, s, 1, dm + 1, p.nscal, st["adv_bc"], st["pmask"])
+    u, w = st["umac"]
+    u.a[...] = 0.5 * (u.a - u.a[..., ::-1])  # odd in x
+    w.a[...] = 0.5 * (w.a + w.a[..., ::-1])
+    st["force"].a[...] = 0.0
+    sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+    oracle.make_edge_scal(p, s, sedge, st["umac"], st["force"], st["adv_bc"], False, 1, dm + 1, 1, False)
+    ex, ey = sedge[0].a[0], sedge[1].a[0]
+    assert np.abs(ey - ey[..., ::-1]).max() < 1e-13
+    assert np.abs(ex - ex[..., ::-1]).max() < 1e-13

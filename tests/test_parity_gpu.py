@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA library (through the C ABI, host-pointer calls) against the CPU oracle on
+identical seeded inputs.  Tolerance from the north star: 1e-12 relative (max-norm per field); the
+parity build (-fmad=false) is expected to be bit-identical, which is asserted where noted."""
+import numpy as np
+import pytest
+
+from maestro_b200 import Fab, abi, face_fabs
+from synth import make_state, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+WALLS_3D = [[abi.PERIODIC, abi.PERIODIC], [abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]
+INOUT_3D = [[abi.INLET, abi.OUTLET], [abi.NO_SLIP_WALL, abi.SLIP_WALL], [abi.SYMMETRY, abi.SYMMETRY]]
+WALLS_2D = [[abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]
+INOUT_2D = [[abi.SYMMETRY, abi.INLET], [abi.OUTLET, abi.NO_SLIP_WALL]]
+
+
+def edge_pair(ops, oracle, st, comps, is_vel=False, cons=False, bccomp0=None):
+    p, dm = st["p"], st["dm"]
+    out = []
+    for o in (ops, oracle):
+        sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm, fill=-777.0)
+        scomp, ncomp = comps
+        o.make_edge_scal(p, st["s"], sedge, st["umac"], st["force"], st["adv_bc"], is_vel, scomp,
+                         (dm + scomp) if bccomp0 is None else bccomp0, ncomp, cons)
+        out.append(sedge)
+    return out
+
+
+@pytest.mark.parametrize("dm,n", [(2, 24), (3, 16)])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
+@pytest.mark.parametrize("cons", [False, True])
+def test_make_edge_scal(gpu_ops, oracle, dm, n, ppm_type, bcset, cons):
+    phys = {"periodic": None, "walls": WALLS_3D if dm == 3 else WALLS_2D,
+            "inout": INOUT_3D if dm == 3 else INOUT_2D}[bcset]
+    st = make_state(dm, n, phys_bc=phys, ppm_type=ppm_type)
+    st["p"].rel_eps = 1e-8 * max(np.abs(u.a).max() for u in st["umac"])
+    g, c = edge_pair(gpu_ops, oracle, st, (1, st["p"].nscal), cons=cons)
+    for d in range(dm):
+        assert relerr(g[d].a, c[d].a) <= TOL
+        assert np.array_equal(g[d].a, c[d].a), "parity build should be bit-identical"
+
+
+@pytest.mark.parametrize("dm,n", [(2, 20), (3, 12)])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+def test_make_edge_scal_velocity(gpu_ops, oracle, dm, n, ppm_type):
+    """is_vel=.true. (velocity_advance.f90:102): comps 1..dm with the inflow clamps at FOEXTRAP/HOEXTRAP"""
+    st = make_state(dm, n, phys_bc=INOUT_3D if dm == 3 else INOUT_2D, ppm_type=ppm_type)
+    g, c = edge_pair(gpu_ops, oracle, st, (1, dm), is_vel=True, bccomp0=1)
+    for d in range(dm):
+        assert np.array_equal(g[d].a, c[d].a)
+
+
+@pytest.mark.parametrize("slope_order", [0, 2])
+def test_slope_orders(gpu_ops, oracle, slope_order):
+    st = make_state(3, 12, phys_bc=WALLS_3D, ppm_type=0, slope_order=slope_order)
+    g, c = edge_pair(gpu_ops, oracle, st, (1, 2))
+    for d in range(3):
+        assert np.array_equal(g[d].a, c[d].a)
+
+
+def test_ppm_trace_forces(gpu_ops, oracle):
+    st = make_state(3, 12, ng_f=4, phys_bc=WALLS_3D, ppm_type=1, ppm_trace_forces=1)
+    g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
+    for d in range(3):
+        assert np.array_equal(g[d].a, c[d].a)
+
+
+def test_ppm2_needs_4_ghosts(gpu_ops):
+    st = make_state(3, 8, ng_s=3, ppm_type=2)
+    with pytest.raises(RuntimeError, match="4 ghost"):
+        edge_pair(gpu_ops, gpu_ops, st, (1, 1))
+
+
+def test_invalid_bc_is_an_error(gpu_ops):
+    st = make_state(2, 8)
+    st["adv_bc"][:] = 99
+    with pytest.raises(RuntimeError, match="invalid boundary"):
+        edge_pair(gpu_ops, gpu_ops, st, (1, 1))
+
+
+@pytest.mark.parametrize("dm,n", [(2, 24), (3, 16)])
+@pytest.mark.parametrize("spt", [1, 2, 3])
+def test_flux_update(gpu_ops, oracle, dm, n, spt):
+    st = make_state(dm, n, species_pred_type=spt)
+    p, b = st["p"], st["base"]
+    rng = np.random.default_rng(7)
+    sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+    for f in sedge:
+        f.a[...] = rng.uniform(0.5, 1.5, size=f.shape)
+    e_old = np.linspace(1.0, 2.0, p.nr + 1)
+    e_new = e_old * 1.01
+    res = []
+    for o in (gpu_ops, oracle):
+        sflux = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+        eta = Fab(st["lo"], st["hi"], 0, 1, nodal=[1 if d == dm - 1 else 0 for d in range(3)], dm=dm)
+        o.mk_rhoX_flux(p, sflux, eta, sedge, st["umac"], b["w0"], b["rho0_old"], e_old, b["rho0_new"], e_new,
+                       b["rho0_predicted_edge"], p.spec_comp, p.spec_comp + p.nspec - 1)
+        o.mk_rhoX_flux(p, sflux, eta, sedge, st["umac"], b["w0"], b["rho0_old"], e_old, b["rho0_new"], e_new,
+                       b["rho0_predicted_edge"], p.trac_comp, p.trac_comp)
+        for ept in (0, 1, 2):
+            p.enthalpy_pred_type = ept
+            o.mk_rhoh_flux(p, sflux, sedge, st["umac"], b["w0"], b["rho0_old"], e_old, b["rho0_new"], e_new,
+                           b["rhoh0_old"], e_old, b["rhoh0_new"], e_new)
+        snew = st["s"].clone()
+        snew.a[...] = -5.0
+        o.update_scal(p, p.spec_comp, p.spec_comp + p.nspec - 1, st["s"], snew, sflux, st["force"])
+        o.update_scal(p, p.rhoh_comp, p.rhoh_comp, st["s"], snew, sflux, st["force"])
+        o.update_scal(p, p.trac_comp, p.trac_comp, st["s"], snew, sflux, st["force"])
+        res.append((sflux, eta, snew))
+    (gf, ge, gs), (cf, ce, cs) = res
+    for d in range(dm):
+        assert np.array_equal(gf[d].a, cf[d].a)
+    assert np.array_equal(ge.a, ce.a)
+    assert np.array_equal(gs.a, cs.a)
+
+
+def test_update_scal_floor_and_negative_species(gpu_ops, oracle):
+    """density floor + negative-species redistribution (update_scal.f90:453-505)"""
+    st = make_state(3, 8)
+    p = st["p"]
+    p.base_cutoff_density = 3.0  # everything is below the floor
+    rng = np.random.default_rng(3)
+    sflux = face_fabs(st["lo"], st["hi"], 0, p.nscal, 3)
+    for f in sflux:
+        f.a[...] = rng.uniform(-30, 30, size=f.shape)  # large fluxes => negative species
+    res = []
+    for o in (gpu_ops, oracle):
+        snew = st["s"].clone()
+        o.update_scal(p, p.spec_comp, p.spec_comp + p.nspec - 1, st["s"], snew, sflux, st["force"])
+        res.append(snew.a)
+    assert (res[1][p.spec_comp - 1] == 0.0).any()
+    assert np.array_equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("dm,n", [(2, 16), (3, 12)])
+def test_update_velocity_addw0_glue(gpu_ops, oracle, dm, n):
+    st = make_state(dm, n)
+    p, b = st["p"], st["base"]
+    p.do_sponge = 1
+    rng = np.random.default_rng(11)
+    uold = Fab(st["lo"], st["hi"], 3, dm, dm=dm)
+    uold.a[...] = rng.uniform(-1, 1, size=uold.shape)
+    uedge = face_fabs(st["lo"], st["hi"], 0, dm, dm)
+    for f in uedge:
+        f.a[...] = rng.uniform(-1, 1, size=f.shape)
+    force = Fab(st["lo"], st["hi"], 1, dm, dm=dm)
+    force.a[...] = rng.uniform(-1, 1, size=force.shape)
+    sponge = Fab(st["lo"], st["hi"], 0, 1, dm=dm)
+    sponge.a[...] = rng.uniform(0.5, 1, size=sponge.shape)
+    res = []
+    for o in (gpu_ops, oracle):
+        unew = uold.clone()
+        o.update_velocity(p, uold, unew, st["umac"], uedge, force, sponge, b["w0"])
+        um = [u.clone() for u in st["umac"]]
+        o.addw0(p, um, b["w0"], 1.0)
+        o.addw0(p, um, b["w0"], -1.0)
+        f2, s2 = st["force"].clone(), st["s"].clone()
+        e_old = np.linspace(1.0, 2.0, p.nr + 1)
+        o.modify_scal_force(p, f2, s2, st["umac"], b["rho0_old"], e_old, b["w0"], p.rho_comp, False)
+        o.modify_scal_force(p, f2, s2, st["umac"], b["rho0_old"], e_old, b["w0"], p.rhoh_comp, True)
+        o.convert_rhoX_to_X(p, s2, True)
+        o.put_in_pert_form(p, s2, b["rho0_old"], p.rho_comp, True)
+        o.put_in_pert_form(p, s2, b["rho0_old"], p.rho_comp, False)
+        o.convert_rhoX_to_X(p, s2, False)
+        res.append((unew.a, um[dm - 1].a, f2.a, s2.a))
+    for x, y in zip(*res):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("dm,n", [(2, 12), (3, 10)])
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
+def test_fill_boundary(gpu_ops, oracle, dm, n, bcset):
+    phys = {"periodic": None, "walls": WALLS_3D if dm == 3 else WALLS_2D,
+            "inout": INOUT_3D if dm == 3 else INOUT_2D}[bcset]
+    st = make_state(dm, n, phys_bc=phys)
+    p = st["p"]
+    res = []
+    for o in (gpu_ops, oracle):
+        s = st["s"].clone()
+        o.fill_boundary(p, s, 1, dm + 1, p.nscal, st["adv_bc"], st["pmask"])
+        um = [u.clone() for u in st["umac"]]
+        for u in um:
+            o.fill_boundary(p, u, 1, 1, 1, st["adv_bc"], st["pmask"])
+        res.append([s.a] + [u.a for u in um])
+    for x, y in zip(*res):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("dm,n", [(2, 32), (3, 16)])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+@pytest.mark.parametrize("spt,which_step,bcset", [(1, 1, "periodic"), (1, 2, "walls"), (2, 2, "periodic"),
+                                                 (3, 1, "walls")])
+def test_density_advance(gpu_ops, oracle, dm, n, ppm_type, spt, which_step, bcset):
+    """Whole L4 episode (density_advance.f90:20) through the C ABI with host buffers."""
+    phys = None if bcset == "periodic" else (WALLS_3D if dm == 3 else WALLS_2D)
+    st = make_state(dm, n, phys_bc=phys, ppm_type=ppm_type, species_pred_type=spt)
+    p, b = st["p"], st["base"]
+    p.rel_eps = 1e-8 * max(np.abs(u.a).max() for u in st["umac"])
+    res = []
+    for o in (gpu_ops, oracle):
+        sold = st["s"].clone()
+        oracle.fill_boundary(p, sold, 1, dm + 1, p.nscal, st["adv_bc"], st["pmask"])
+        snew = sold.clone()
+        snew.a[...] = 0.0
+        umac = [u.clone() for u in st["umac"]]
+        sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+        sflux = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+        force = st["force"].clone()
+        eta = Fab(st["lo"], st["hi"], 0, 1, nodal=[1 if d == dm - 1 else 0 for d in range(3)], dm=dm)
+        o.density_advance(p, which_step, sold, snew, sedge, sflux, force, umac, b["w0"], eta, b["rho0_old"],
+                          b["rho0_new"], b["p0"], b["rho0_predicted_edge"], st["adv_bc"], st["pmask"])
+        res.append(dict(sold=sold.a, snew=snew.a, eta=eta.a, force=force.a,
+                        **{"sedge%d" % d: sedge[d].a for d in range(dm)},
+                        **{"sflux%d" % d: sflux[d].a for d in range(dm)},
+                        **{"umac%d" % d: umac[d].valid() for d in range(dm)}))
+    for k in res[0]:
+        assert relerr(res[0][k], res[1][k]) <= TOL, k
+        assert np.array_equal(res[0][k], res[1][k]), k
