@@ -106,6 +106,15 @@ const char* mgpu_last_error(void);
 const char* mgpu_version(void);
 /* number of kernel launches issued by the library since the last reset (bench "gpu_launches") */
 long mgpu_launch_count(int reset);
+/* tuning/testing switches: "fused" (1: fused 3-D edge kernel when applicable, 0: staged general path),
+ * "kchunk" (z planes per CTA of the fused kernel) */
+int mgpu_set_option(const char* key, int value);
+/* per-kernel-class device timing with CUDA events on the launching stream (bench roofline line):
+ * mgpu_profile(1) starts/reset, mgpu_profile_get(tag,...) returns accumulated ms and launch count.
+ * tags: 0 edge:cell-states 1 edge:simh 2 edge:transverse 3 edge:final 4 flux 5 update 6 fill 7 glue
+ *       8 fused edge+flux+update 9 velpred 10 bds 11 halo */
+int mgpu_profile(int on);
+int mgpu_profile_get(int tag, double* ms, long* launches);
 /* raw cudaStream_t used for all launches (for CUDA-event timing by the caller) */
 void* mgpu_stream(void);
 /* run on a caller-owned stream instead (e.g. the framework's current stream) */

@@ -94,6 +94,9 @@ LIFECYCLE = {
     "mgpu_version": (C.c_char_p, []),
     "mgpu_launch_count": (C.c_long, [C.c_int]),
     "mgpu_stream": (C.c_void_p, []),
+    "mgpu_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "mgpu_profile": (C.c_int, [C.c_int]),
+    "mgpu_profile_get": (C.c_int, [C.c_int, c_double_p, C.POINTER(C.c_long)]),
     "mgpu_set_stream": (C.c_int, [C.c_void_p]),
     "mgpu_host_register": (C.c_int, [C.c_void_p, C.c_long]),
     "mgpu_host_unregister": (C.c_int, [C.c_void_p]),

@@ -16,10 +16,37 @@ namespace mgpu {
 
 static Context g_ctx;
 static std::string g_err;
+static int g_opt_fused = 1;    // use the fused 3-D edge kernel when it covers the case
+static int g_opt_kchunk = 64;  // z planes per CTA of the fused kernel
 Context& ctx() { return g_ctx; }
 
 void require_init() {
   if (!g_ctx.initialised) throw Error("mgpu: library not initialised (call mgpu_init; a CUDA device is required)");
+}
+
+// ---- optional kernel-class profiling --------------------------------------------------------------
+struct Prof {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[TAG_COUNT];
+  size_t used[TAG_COUNT] = {0};
+  cudaEvent_t cur = nullptr;
+};
+static Prof g_prof;
+void prof_begin(int tag) {
+  if (!g_prof.on) return;
+  auto& v = g_prof.ev[tag];
+  if (g_prof.used[tag] == v.size()) {
+    cudaEvent_t a, b;
+    MGPU_CUDA(cudaEventCreate(&a));
+    MGPU_CUDA(cudaEventCreate(&b));
+    v.push_back({a, b});
+  }
+  MGPU_CUDA(cudaEventRecord(v[g_prof.used[tag]].first, g_ctx.stream));
+}
+void prof_end(int tag) {
+  if (!g_prof.on) return;
+  MGPU_CUDA(cudaEventRecord(g_prof.ev[tag][g_prof.used[tag]].second, g_ctx.stream));
+  g_prof.used[tag]++;
 }
 
 // ---- arena -------------------------------------------------------------------------------------
@@ -164,6 +191,27 @@ static void fill_flux_args(const mgpu_params& P, FluxArgs& a, const int* lo, con
   a.vb = grown(lo, hi, P.dm, 0);
 }
 
+// make_edge_scal for one component: fused single-launch kernel when it covers the case, else the staged path
+static void edge_one_comp(const mgpu_params& P, const DV& s, DV* sedge, const DV* umac, const DV& force,
+                          const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel,
+                          bool is_cons, int ng_s, int ng_f) {
+  for (int d = 0; d < P.dm; ++d) {  // validate BC codes up front (make_edge_scal.f90:853)
+    for (int side = 0; side < 2; ++side) {
+      const int bc = adv_bc[d + P.dm * (side + 2 * (bccomp - 1))];
+      if (bc != MGPU_BC_EXT_DIR && bc != MGPU_BC_FOEXTRAP && bc != MGPU_BC_HOEXTRAP && bc != MGPU_BC_REFLECT_EVEN &&
+          bc != MGPU_BC_REFLECT_ODD && bc != MGPU_BC_INTERIOR)
+        throw Error("make_edge_scal: invalid boundary type adv_bc");
+    }
+  }
+  if (g_opt_fused && fused_edge_supported(P, is_cons)) {
+    fused_edge_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, ng_s, ng_f, g_opt_kchunk);
+  } else {
+    size_t mark = arena_mark();
+    make_edge_scal_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, is_cons, ng_s, ng_f);
+    arena_release(mark);
+  }
+}
+
 // ---- density_advance on the device (general path) ----------------------------------------------
 static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, DV& snew, DV* sedge, DV* sflux,
                                 DV& scal_force, DV* umac, const double* w0_h, DV& eta, const double* rho0_old_h,
@@ -204,12 +252,9 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   }
   auto edge = [&](int scomp, int ncomp, bool cons) {
     if (P.bds_type != 0) throw Error("bds: not available on the device yet");
-    for (int n = 0; n < ncomp; ++n) {
-      size_t mark = arena_mark();
-      make_edge_scal_dev(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, scomp - 1 + n, dm + scomp + n, false, cons,
-                         ng_s, ng_f);
-      arena_release(mark);
-    }
+    for (int n = 0; n < ncomp; ++n)
+      edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, scomp - 1 + n, dm + scomp + n, false, cons, ng_s,
+                    ng_f);
   };
   if (spt == MGPU_PREDICT_RHOX) edge(P.spec_comp, P.nspec, true);  // :190-198
   else edge(P.spec_comp, P.nspec, false);                            // :178-186
@@ -319,6 +364,40 @@ int mgpu_finalize(void) {
   MGPU_CATCH
 }
 
+int mgpu_set_option(const char* key, int value) {
+  MGPU_TRY
+  std::string k(key ? key : "");
+  if (k == "fused") g_opt_fused = value;
+  else if (k == "kchunk") g_opt_kchunk = value;
+  else throw Error("mgpu_set_option: unknown key " + k);
+  MGPU_CATCH
+}
+
+int mgpu_profile(int on) {
+  MGPU_TRY
+  require_init();
+  MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  g_prof.on = on != 0;
+  for (int t = 0; t < TAG_COUNT; ++t) g_prof.used[t] = 0;
+  MGPU_CATCH
+}
+/* accumulated device time (ms) and launch count of kernel class `tag` since mgpu_profile(1) */
+int mgpu_profile_get(int tag, double* ms, long* launches) {
+  MGPU_TRY
+  require_init();
+  if (tag < 0 || tag >= TAG_COUNT) throw Error("mgpu_profile_get: bad tag");
+  MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  double tot = 0.0;
+  for (size_t i = 0; i < g_prof.used[tag]; ++i) {
+    float f = 0.f;
+    MGPU_CUDA(cudaEventElapsedTime(&f, g_prof.ev[tag][i].first, g_prof.ev[tag][i].second));
+    tot += f;
+  }
+  *ms = tot;
+  *launches = (long)g_prof.used[tag];
+  MGPU_CATCH
+}
+
 int mgpu_synchronize(void) {
   MGPU_TRY
   require_init();
@@ -397,12 +476,9 @@ int mgpu_make_edge_scal(const mgpu_params* p, int nfabs, const mgpu_fab* s, mgpu
     // sedge holds other components the caller may already have filled: copy in as well as out
     c.views((const mgpu_fab* const*)sedge, i, true, true, se);
     c.views(umac, i, true, false, um);
-    for (int scomp = start_scomp; scomp < start_scomp + num_comp; ++scomp) {
-      size_t mark = arena_mark();
-      make_edge_scal_dev(*p, sv, se, um, fv, s[i].lo, s[i].hi, adv_bc, scomp - 1, start_bccomp + scomp - start_scomp,
-                         is_vel != 0, is_conservative != 0, s[i].ng, force[i].ng);
-      arena_release(mark);
-    }
+    for (int scomp = start_scomp; scomp < start_scomp + num_comp; ++scomp)
+      edge_one_comp(*p, sv, se, um, fv, s[i].lo, s[i].hi, adv_bc, scomp - 1, start_bccomp + scomp - start_scomp,
+                    is_vel != 0, is_conservative != 0, s[i].ng, force[i].ng);
   }
   c.finish();
   MGPU_CATCH

@@ -123,6 +123,22 @@ inline void count_launch(int n = 1) { ctx().launches += n; }
     mgpu::count_launch();               \
   } while (0)
 
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline
+// line): MGPU_TIMED(tag, launch-statement) brackets one launch when profiling is switched on.
+enum KernelTag {
+  TAG_EDGE_CELL = 0, TAG_EDGE_SIMH, TAG_EDGE_TRANS, TAG_EDGE_FINAL, TAG_FLUX, TAG_UPDATE, TAG_FILL, TAG_GLUE,
+  TAG_FUSED_EDGE, TAG_VELPRED, TAG_BDS, TAG_HALO, TAG_COUNT
+};
+void prof_begin(int tag);
+void prof_end(int tag);
+#define MGPU_TIMED(tag, stmt) \
+  do {                        \
+    mgpu::prof_begin(tag);    \
+    stmt;                     \
+    MGPU_LAUNCH_CHECK();      \
+    mgpu::prof_end(tag);      \
+  } while (0)
+
 #ifdef __CUDACC__
 // thread id -> (i,j,k) of a box, x fastest
 __device__ __forceinline__ bool decode(const Box3& b, long t, int* ix) {

@@ -293,18 +293,12 @@ void make_edge_scal_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, 
       for (int t = 0; t < 3; ++t)
         if (t != d) a.simht[d][t] = tmp(1);
   const int bs = 256;
-  k_cell_states<<<nblocks(nt, bs), bs, 0, c.stream>>>(a);
-  MGPU_LAUNCH_CHECK();
-  k_simh<<<nblocks(nt, bs), bs, 0, c.stream>>>(a);
-  MGPU_LAUNCH_CHECK();
-  if (dm == 3) {
-    k_transverse<<<nblocks(nt, bs), bs, 0, c.stream>>>(a);
-    MGPU_LAUNCH_CHECK();
-  }
+  MGPU_TIMED(TAG_EDGE_CELL, (k_cell_states<<<nblocks(nt, bs), bs, 0, c.stream>>>(a)));
+  MGPU_TIMED(TAG_EDGE_SIMH, (k_simh<<<nblocks(nt, bs), bs, 0, c.stream>>>(a)));
+  if (dm == 3) MGPU_TIMED(TAG_EDGE_TRANS, (k_transverse<<<nblocks(nt, bs), bs, 0, c.stream>>>(a)));
   Box3 fb = a.vb;
   for (int d = 0; d < dm; ++d) fb.hi[d] += 1;
-  k_final<<<nblocks(fb.npts(), bs), bs, 0, c.stream>>>(a);
-  MGPU_LAUNCH_CHECK();
+  MGPU_TIMED(TAG_EDGE_FINAL, (k_final<<<nblocks(fb.npts(), bs), bs, 0, c.stream>>>(a)));
 }
 
 }  // namespace mgpu

@@ -1,0 +1,386 @@
+// Fused 3-D edge-state kernel: make_edge_scal_3d (Source/make_edge_scal.f90:677) + the ppm_3d /
+// slope calls it makes (Source/ppm.f90:1629, Source/slope.f90) in ONE launch per component, with
+// no intermediate array in HBM.  The reference streams ~45 box-sized temporaries through DRAM per
+// component; here every temporary lives in shared memory or registers.
+//
+// Design ("2.5-D streaming"): a CTA owns a BX x BY column of cells (one thread per (i,j), one halo
+// cell on each side in x and y because every stage reaches one cell sideways) and marches in z.
+// The z-direction PPM stencil lives in a register window; the x/y stencils read a shared-memory
+// tile of the current plane; the normal-predictor, transverse and final stages of plane q-1/q are
+// exchanged between neighbouring threads through double-buffered shared-memory planes:
+//
+//   step q:  P1(q)   : Ip/Im in x,y,z of cell plane q          -> simhz(q)
+//            S2(q)   : slx,srx,sly,sry, simhx(q), simhy(q)
+//            T1(q)   : simhxy(q), simhyx(q)        T3(q): simhzx(q), simhzy(q)   (z-face q)
+//            T2(q-1) : simhxz(q-1), simhyz(q-1)    (needs simhz(q-1), simhz(q))
+//            F_z(q)  : sedgez on z-face q           F_xy(q-1): sedgex, sedgey of plane q-1
+//
+// Only cells (i,j) strictly inside the CTA's tile produce output, so each plane costs
+// (BX*BY)/((BX-2)*(BY-2)) of the minimal work and nothing is recomputed along z except two planes
+// per z-chunk.  All BC branches of the reference (EXT_DIR, FOEXTRAP/HOEXTRAP with the inflow
+// clamp, REFLECT_EVEN/ODD, wall stencils of PPM/slopes, and its asymmetries) are evaluated from
+// global indices, so the kernel is valid for any box, not just the periodic interior.
+// Expression order matches the reference: with -fmad=false the results are bit-identical to the
+// general path (mgpu_edge.cu) and to the CPU oracle.
+#include "mgpu_fused.cuh"
+#include "mgpu_recon.cuh"
+
+namespace mgpu {
+
+template <int H, int BX, int BY>
+struct FusedSmem {
+  static constexpr int SP = BX + 2 * H;  // pitch of the s tile
+  double S[(BY + 2 * H) * SP];
+  double IPX[BY][BX], IMX[BY][BX], IPY[BY][BX], IMY[BY][BX];
+  double Z[2][BY][BX], SHX[2][BY][BX], SHY[2][BY][BX];
+  double XY[2][BY][BX], YX[2][BY][BX], ZX[2][BY][BX], ZY[2][BY][BX];
+  double XZ[BY][BX], YZ[BY][BX];
+  double U[2][BY][BX + 1], V[2][BY + 1][BX], W[2][BY][BX];
+  double FRC[2][BY][BX];
+};
+
+__device__ __forceinline__ void bc_states(const FusedArgs& a, int d, int f, double s_lo_m1, double s_lo_0,
+                                          double s_hi_p1, int stage, double& sl, double& sr) {
+  // same as lr_bc of the general path, with the needed s values passed in registers:
+  // s_lo_m1 = s(is-1), s_lo_0 = s(is) (only for the z-lo EXT_DIR quirk), s_hi_p1 = s(ie+1)
+  const int is = a.lo[d], ie = a.hi[d];
+  if (f == is) {
+    const int bclo = a.bclo[d];
+    if (bclo == MGPU_BC_EXT_DIR) {
+      sl = (d == 2 && stage == 0) ? s_lo_0 : s_lo_m1;  // QUIRK make_edge_scal.f90:1010-1011
+      sr = sl;
+    } else if (bclo == MGPU_BC_FOEXTRAP || bclo == MGPU_BC_HOEXTRAP) {
+      if (a.velnorm[d]) sr = dmin2(sr, 0.0);
+      sl = sr;
+    } else if (bclo == MGPU_BC_REFLECT_EVEN) {
+      sl = sr;
+    } else if (bclo == MGPU_BC_REFLECT_ODD) {
+      sl = 0.0;
+      sr = 0.0;
+    }
+  }
+  if (f == ie + 1) {
+    const int bchi = a.bchi[d];
+    if (bchi == MGPU_BC_EXT_DIR) {
+      sl = s_hi_p1;
+      sr = sl;
+    } else if (bchi == MGPU_BC_FOEXTRAP || bchi == MGPU_BC_HOEXTRAP) {
+      if (a.velnorm[d]) sl = dmax2(sl, 0.0);
+      sr = sl;
+    } else if (bchi == MGPU_BC_REFLECT_EVEN) {
+      sr = sl;
+    } else if (bchi == MGPU_BC_REFLECT_ODD) {
+      sl = 0.0;
+      sr = 0.0;
+    }
+  }
+}
+
+__device__ __forceinline__ double final_bc(const FusedArgs& a, int d, int f, double e, double sedgel, double sedger,
+                                           double s_left, double s_right) {
+  if (f == a.lo[d]) {
+    const int bc = a.bclo[d];
+    if (bc == MGPU_BC_EXT_DIR) e = s_left;
+    else if (bc == MGPU_BC_FOEXTRAP || bc == MGPU_BC_HOEXTRAP) e = a.velnorm[d] ? dmin2(sedger, 0.0) : sedger;
+    else if (bc == MGPU_BC_REFLECT_EVEN) e = sedger;
+    else if (bc == MGPU_BC_REFLECT_ODD) e = 0.0;
+  }
+  if (f == a.hi[d] + 1) {
+    const int bc = a.bchi[d];
+    if (bc == MGPU_BC_EXT_DIR) e = s_right;
+    else if (bc == MGPU_BC_FOEXTRAP || bc == MGPU_BC_HOEXTRAP) e = a.velnorm[d] ? dmax2(sedgel, 0.0) : sedgel;
+    else if (bc == MGPU_BC_REFLECT_EVEN) e = sedgel;
+    else if (bc == MGPU_BC_REFLECT_ODD) e = 0.0;
+  }
+  return e;
+}
+
+template <int PPM, int BX, int BY>
+__global__ void __launch_bounds__(BX* BY) k_fused_edge(FusedArgs a) {
+  constexpr int H = (PPM == 2) ? 3 : 2;
+  using SM = FusedSmem<H, BX, BY>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  constexpr int SP = SM::SP;
+
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ibase = a.lo[0] - 1 + blockIdx.x * (BX - 2);
+  const int jbase = a.lo[1] - 1 + blockIdx.y * (BY - 2);
+  const int i = ibase + tx, j = jbase + ty;
+  const int kz0 = a.lo[2] + blockIdx.z * a.kchunk;
+  const int kz1 = min(kz0 + a.kchunk - 1, a.hi[2]);
+  const bool active = (i <= a.hi[0] + 1) && (j <= a.hi[1] + 1);
+  // clamped coordinates for loads by inactive threads (values never used)
+  const int ic = min(i, a.hi[0] + 1), jc = min(j, a.hi[1] + 1);
+
+  const LineBC bx = make_linebc(3, 0, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0]);
+  const LineBC by = make_linebc(3, 1, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1]);
+  const LineBC bz = make_linebc(3, 2, a.lo[2], a.hi[2], a.bclo[2], a.bchi[2]);
+
+  const double dt = a.dt, rel_eps = a.rel_eps;
+  const double hx = a.dx[0], hy = a.dx[1], hz = a.dx[2];
+  const double dt2 = 0.5 * dt, dt4 = dt / 4.0, dt6 = dt / 6.0;
+
+  auto sload = [&](int ii, int jj, int kk) -> double { return a.s.p[a.s.off(ii, jj, kk)]; };
+
+  // z register window: sw[m] = s(i,j,q-H+m)
+  double sw[2 * H + 1];
+  {
+    const int q0 = kz0 - 1;
+#pragma unroll
+    for (int m = 1; m <= 2 * H; ++m) sw[m] = sload(ic, jc, q0 - 1 - H + m);  // becomes window of q0-1 shifted below
+    sw[0] = 0.0;
+  }
+  double Ipz_prev = 0.0;
+  double slx_p = 0.0, srx_p = 0.0, sly_p = 0.0, sry_p = 0.0;  // plane q-1 face states
+  double slz_q = 0.0, srz_q = 0.0;
+  double f_p = 0.0;  // force(i,j,q-1)
+  double s_p = 0.0;  // s(i,j,q-1)
+
+  for (int q = kz0 - 1; q <= kz1 + 1; ++q) {
+    const int par = q & 1, opar = par ^ 1;
+    __syncthreads();  // previous step's readers of U/V/W/FRC[par] and S are done
+    // ---- S0: loads ---------------------------------------------------------------------------
+#pragma unroll
+    for (int m = 0; m < 2 * H; ++m) sw[m] = sw[m + 1];
+    sw[2 * H] = sload(ic, jc, q + H);
+    {
+      // s tile of plane q: cells ibase-H .. ibase+BX-1+H, jbase-H .. jbase+BY-1+H (clamped to the fab)
+      const int ilo = a.s.lo[0], ihi = a.s.lo[0] + a.s.n[0] - 1;
+      const int jlo = a.s.lo[1], jhi = a.s.lo[1] + a.s.n[1] - 1;
+      for (int t = ty * BX + tx; t < (BY + 2 * H) * SP; t += BX * BY) {
+        const int yy = t / SP, xx = t - yy * SP;
+        int ii = ibase - H + xx, jj = jbase - H + yy;
+        ii = max(ilo, min(ii, ihi));
+        jj = max(jlo, min(jj, jhi));
+        sm.S[t] = sload(ii, jj, q);
+      }
+    }
+    {
+      const DV& u = a.umac[0];
+      const DV& v = a.umac[1];
+      const DV& w = a.umac[2];
+      sm.U[par][ty][tx] = u(ic, jc, q);
+      if (tx == BX - 1) sm.U[par][ty][BX] = u(min(i + 1, a.hi[0] + 2), jc, q);
+      sm.V[par][ty][tx] = v(ic, jc, q);
+      if (ty == BY - 1) sm.V[par][BY][tx] = v(ic, min(j + 1, a.hi[1] + 2), q);
+      sm.W[par][ty][tx] = w(ic, jc, q);
+    }
+    const double wq1 = a.umac[2](ic, jc, q + 1);
+    const double f_q = a.force(ic, jc, q);
+    sm.FRC[par][ty][tx] = f_q;
+    __syncthreads();
+
+    const double s_q = sw[H];
+    const double uq = sm.U[par][ty][tx], uq1 = sm.U[par][ty][tx + 1];
+    const double vq = sm.V[par][ty][tx], vq1 = sm.V[par][ty + 1][tx];
+    const double wq = sm.W[par][ty][tx];
+
+    // ---- S1: P1(q) ---------------------------------------------------------------------------
+    {
+      double Ip, Im;
+      const double* c = &sm.S[(ty + H) * SP + tx + H];
+      cell_states(PPM, a.slope_order, c, 1, i, bx, uq1, uq, dt, hx, rel_eps, Ip, Im);
+      sm.IPX[ty][tx] = Ip;
+      sm.IMX[ty][tx] = Im;
+      cell_states(PPM, a.slope_order, c, SP, j, by, vq1, vq, dt, hy, rel_eps, Ip, Im);
+      sm.IPY[ty][tx] = Ip;
+      sm.IMY[ty][tx] = Im;
+      cell_states(PPM, a.slope_order, &sw[H], 1, q, bz, wq1, wq, dt, hz, rel_eps, Ip, Im);
+      // z-face q (between planes q-1 and q)
+      slz_q = Ipz_prev;
+      srz_q = Im;
+      Ipz_prev = Ip;
+      bc_states(a, 2, q, s_p, s_q, s_q, 0, slz_q, srz_q);
+      sm.Z[par][ty][tx] = riemann(slz_q, srz_q, wq, rel_eps);
+    }
+    __syncthreads();
+
+    // ---- S2: normal-predictor face states in plane q ------------------------------------------
+    double slx_q = 0.0, srx_q = 0.0, sly_q = 0.0, sry_q = 0.0;
+    if (tx >= 1) {
+      slx_q = sm.IPX[ty][tx - 1];
+      srx_q = sm.IMX[ty][tx];
+      bc_states(a, 0, i, sm.S[(ty + H) * SP + tx + H - 1], 0.0, s_q, 0, slx_q, srx_q);
+      sm.SHX[par][ty][tx] = riemann(slx_q, srx_q, uq, rel_eps);
+    }
+    if (ty >= 1) {
+      sly_q = sm.IPY[ty - 1][tx];
+      sry_q = sm.IMY[ty][tx];
+      bc_states(a, 1, j, sm.S[(ty + H - 1) * SP + tx + H], 0.0, s_q, 0, sly_q, sry_q);
+      sm.SHY[par][ty][tx] = riemann(sly_q, sry_q, vq, rel_eps);
+    }
+    __syncthreads();
+
+    // ---- S3: transverse states ------------------------------------------------------------------
+    // T1(q): x-face corrected by y, y-face corrected by x
+    if (tx >= 1 && ty <= BY - 2) {
+      double l = slx_q - (dt6 / hy) * (sm.V[par][ty + 1][tx - 1] + sm.V[par][ty][tx - 1]) *
+                             (sm.SHY[par][ty + 1][tx - 1] - sm.SHY[par][ty][tx - 1]);
+      double r = srx_q - (dt6 / hy) * (vq1 + vq) * (sm.SHY[par][ty + 1][tx] - sm.SHY[par][ty][tx]);
+      bc_states(a, 0, i, sm.S[(ty + H) * SP + tx + H - 1], 0.0, s_q, 1, l, r);
+      sm.XY[par][ty][tx] = riemann(l, r, uq, rel_eps);
+    }
+    if (ty >= 1 && tx <= BX - 2) {
+      double l = sly_q - (dt6 / hx) * (sm.U[par][ty - 1][tx + 1] + sm.U[par][ty - 1][tx]) *
+                             (sm.SHX[par][ty - 1][tx + 1] - sm.SHX[par][ty - 1][tx]);
+      double r = sry_q - (dt6 / hx) * (uq1 + uq) * (sm.SHX[par][ty][tx + 1] - sm.SHX[par][ty][tx]);
+      bc_states(a, 1, j, sm.S[(ty + H - 1) * SP + tx + H], 0.0, s_q, 1, l, r);
+      sm.YX[par][ty][tx] = riemann(l, r, vq, rel_eps);
+    }
+    if (q >= kz0) {
+      // T3(q): z-face q corrected by x / by y (left cell = plane q-1, right cell = plane q)
+      if (tx <= BX - 2) {
+        double l = slz_q - (dt6 / hx) * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) *
+                               (sm.SHX[opar][ty][tx + 1] - sm.SHX[opar][ty][tx]);
+        double r = srz_q - (dt6 / hx) * (uq1 + uq) * (sm.SHX[par][ty][tx + 1] - sm.SHX[par][ty][tx]);
+        bc_states(a, 2, q, s_p, s_q, s_q, 1, l, r);
+        sm.ZX[par][ty][tx] = riemann(l, r, wq, rel_eps);
+      }
+      if (ty <= BY - 2) {
+        double l = slz_q - (dt6 / hy) * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) *
+                               (sm.SHY[opar][ty + 1][tx] - sm.SHY[opar][ty][tx]);
+        double r = srz_q - (dt6 / hy) * (vq1 + vq) * (sm.SHY[par][ty + 1][tx] - sm.SHY[par][ty][tx]);
+        bc_states(a, 2, q, s_p, s_q, s_q, 1, l, r);
+        sm.ZY[par][ty][tx] = riemann(l, r, wq, rel_eps);
+      }
+    }
+    if (q >= kz0 + 1) {
+      // T2(q-1): x- and y-faces of plane q-1 corrected by z.  w on z-faces q-1 (opar) and q (par).
+      if (tx >= 1) {
+        double l = slx_p - (dt6 / hz) * (sm.W[par][ty][tx - 1] + sm.W[opar][ty][tx - 1]) *
+                               (sm.Z[par][ty][tx - 1] - sm.Z[opar][ty][tx - 1]);
+        double r = srx_p - (dt6 / hz) * (sm.W[par][ty][tx] + sm.W[opar][ty][tx]) * (sm.Z[par][ty][tx] - sm.Z[opar][ty][tx]);
+        // s(is-1) / s(ie+1) of plane q-1 for EXT_DIR: re-read from global (rare branch)
+        if ((i == a.lo[0] && a.bclo[0] == MGPU_BC_EXT_DIR) || (i == a.hi[0] + 1 && a.bchi[0] == MGPU_BC_EXT_DIR))
+          bc_states(a, 0, i, sload(i - 1, jc, q - 1), 0.0, s_p, 1, l, r);
+        else
+          bc_states(a, 0, i, 0.0, 0.0, 0.0, 1, l, r);
+        sm.XZ[ty][tx] = riemann(l, r, sm.U[opar][ty][tx], rel_eps);
+      }
+      if (ty >= 1) {
+        double l = sly_p - (dt6 / hz) * (sm.W[par][ty - 1][tx] + sm.W[opar][ty - 1][tx]) *
+                               (sm.Z[par][ty - 1][tx] - sm.Z[opar][ty - 1][tx]);
+        double r = sry_p - (dt6 / hz) * (sm.W[par][ty][tx] + sm.W[opar][ty][tx]) * (sm.Z[par][ty][tx] - sm.Z[opar][ty][tx]);
+        if ((j == a.lo[1] && a.bclo[1] == MGPU_BC_EXT_DIR) || (j == a.hi[1] + 1 && a.bchi[1] == MGPU_BC_EXT_DIR))
+          bc_states(a, 1, j, sload(ic, j - 1, q - 1), 0.0, s_p, 1, l, r);
+        else
+          bc_states(a, 1, j, 0.0, 0.0, 0.0, 1, l, r);
+        sm.YZ[ty][tx] = riemann(l, r, sm.V[opar][ty][tx], rel_eps);
+      }
+    }
+    __syncthreads();
+
+    // ---- S4: final edge states ------------------------------------------------------------------
+    const bool inx = (tx >= 1 && tx <= BX - 2 && i <= a.hi[0]);
+    const bool iny = (ty >= 1 && ty <= BY - 2 && j <= a.hi[1]);
+    if (q >= kz0 && inx && iny && active) {
+      // F_z(q): transverse terms x then y, left cell plane q-1 (opar), right cell plane q (par)
+      double el = slz_q - (dt4 / hx) * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) *
+                              (sm.XY[opar][ty][tx + 1] - sm.XY[opar][ty][tx]) -
+                  (dt4 / hy) * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) * (sm.YX[opar][ty + 1][tx] - sm.YX[opar][ty][tx]) +
+                  dt2 * f_p;
+      double er = srz_q - (dt4 / hx) * (uq1 + uq) * (sm.XY[par][ty][tx + 1] - sm.XY[par][ty][tx]) -
+                  (dt4 / hy) * (vq1 + vq) * (sm.YX[par][ty + 1][tx] - sm.YX[par][ty][tx]) + dt2 * f_q;
+      double e = riemann(el, er, wq, rel_eps);
+      e = final_bc(a, 2, q, e, el, er, s_p, s_q);
+      if (q <= kz1 || q == a.hi[2] + 1) a.sedge[2](i, j, q) = e;
+    }
+    if (q >= kz0 + 1 && active) {
+      const int k = q - 1;
+      // F_xy(k): x-face (i,j,k): transverse terms y (simhyz) then z (simhzy)
+      if (tx >= 1 && (tx <= BX - 2 || i == a.hi[0] + 1) && iny) {
+        double el = slx_p - (dt4 / hy) * (sm.V[opar][ty + 1][tx - 1] + sm.V[opar][ty][tx - 1]) *
+                                (sm.YZ[ty + 1][tx - 1] - sm.YZ[ty][tx - 1]) -
+                    (dt4 / hz) * (sm.W[par][ty][tx - 1] + sm.W[opar][ty][tx - 1]) *
+                        (sm.ZY[par][ty][tx - 1] - sm.ZY[opar][ty][tx - 1]) +
+                    dt2 * sm.FRC[opar][ty][tx - 1];
+        double er = srx_p - (dt4 / hy) * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) * (sm.YZ[ty + 1][tx] - sm.YZ[ty][tx]) -
+                    (dt4 / hz) * (sm.W[par][ty][tx] + sm.W[opar][ty][tx]) * (sm.ZY[par][ty][tx] - sm.ZY[opar][ty][tx]) +
+                    dt2 * f_p;
+        double e = riemann(el, er, sm.U[opar][ty][tx], rel_eps);
+        if (i == a.lo[0] || i == a.hi[0] + 1) {
+          const double sl_c = (a.bclo[0] == MGPU_BC_EXT_DIR && i == a.lo[0]) ? sload(i - 1, j, k) : 0.0;
+          e = final_bc(a, 0, i, e, el, er, sl_c, s_p);
+        }
+        a.sedge[0](i, j, k) = e;
+      }
+      // y-face (i,j,k): transverse terms x (simhxz) then z (simhzx)
+      if (ty >= 1 && (ty <= BY - 2 || j == a.hi[1] + 1) && inx) {
+        double el = sly_p - (dt4 / hx) * (sm.U[opar][ty - 1][tx + 1] + sm.U[opar][ty - 1][tx]) *
+                                (sm.XZ[ty - 1][tx + 1] - sm.XZ[ty - 1][tx]) -
+                    (dt4 / hz) * (sm.W[par][ty - 1][tx] + sm.W[opar][ty - 1][tx]) *
+                        (sm.ZX[par][ty - 1][tx] - sm.ZX[opar][ty - 1][tx]) +
+                    dt2 * sm.FRC[opar][ty - 1][tx];
+        double er = sry_p - (dt4 / hx) * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) * (sm.XZ[ty][tx + 1] - sm.XZ[ty][tx]) -
+                    (dt4 / hz) * (sm.W[par][ty][tx] + sm.W[opar][ty][tx]) * (sm.ZX[par][ty][tx] - sm.ZX[opar][ty][tx]) +
+                    dt2 * f_p;
+        double e = riemann(el, er, sm.V[opar][ty][tx], rel_eps);
+        if (j == a.lo[1] || j == a.hi[1] + 1) {
+          const double sl_c = (a.bclo[1] == MGPU_BC_EXT_DIR && j == a.lo[1]) ? sload(i, j - 1, k) : 0.0;
+          e = final_bc(a, 1, j, e, el, er, sl_c, s_p);
+        }
+        a.sedge[1](i, j, k) = e;
+      }
+    }
+    // rotate plane q -> q-1
+    slx_p = slx_q; srx_p = srx_q; sly_p = sly_q; sry_p = sry_q;
+    f_p = f_q;
+    s_p = s_q;
+  }
+}
+
+template <int PPM, int BX, int BY>
+static void launch_fused(const FusedArgs& a, int nx, int ny, int nz) {
+  constexpr int H = (PPM == 2) ? 3 : 2;
+  using SM = FusedSmem<H, BX, BY>;
+  Context& c = ctx();
+  static bool configured = false;
+  if (!configured) {
+    MGPU_CUDA(cudaFuncSetAttribute(k_fused_edge<PPM, BX, BY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(SM)));
+    configured = true;
+  }
+  dim3 block(BX, BY, 1);
+  dim3 grid((nx + BX - 3) / (BX - 2), (ny + BY - 3) / (BY - 2), (nz + a.kchunk - 1) / a.kchunk);
+  MGPU_TIMED(TAG_FUSED_EDGE, (k_fused_edge<PPM, BX, BY><<<grid, block, sizeof(SM), c.stream>>>(a)));
+}
+
+bool fused_edge_supported(const mgpu_params& P, bool is_cons) {
+  return P.dm == 3 && P.bds_type == 0 && P.ppm_trace_forces == 0 && !is_cons;
+}
+
+void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
+                    const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
+                    int ng_f, int kchunk) {
+  if (P.ppm_type == 2 && ng_s < 4) throw Error("Need 4 ghost cells for ppm_type=2");  // ppm.f90:1864-1866
+  if (ng_s < 3) throw Error("make_edge_scal: need at least 3 ghost cells");
+  if (ng_f < 1) throw Error("make_edge_scal: force needs at least 1 ghost cell");
+  FusedArgs a;
+  a.slope_order = P.slope_order;
+  a.dt = P.dt;
+  a.rel_eps = P.rel_eps;
+  for (int d = 0; d < 3; ++d) {
+    a.lo[d] = lo[d];
+    a.hi[d] = hi[d];
+    a.dx[d] = P.dx[d];
+    a.bclo[d] = adv_bc[d + 3 * (0 + 2 * (bccomp - 1))];
+    a.bchi[d] = adv_bc[d + 3 * (1 + 2 * (bccomp - 1))];
+    a.velnorm[d] = is_vel && (comp == d);
+    a.umac[d] = umac[d];
+    a.sedge[d] = sedge_full[d].comp(comp);
+  }
+  a.s = s_full.comp(comp);
+  a.force = force_full.comp(comp);
+  const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+  a.kchunk = kchunk > 0 ? kchunk : nz;
+  if (a.kchunk > nz) a.kchunk = nz;
+  switch (P.ppm_type) {
+    case 0: launch_fused<0, MGPU_FUSED_BX, MGPU_FUSED_BY>(a, nx, ny, nz); break;
+    case 1: launch_fused<1, MGPU_FUSED_BX, MGPU_FUSED_BY>(a, nx, ny, nz); break;
+    case 2: launch_fused<2, MGPU_FUSED_BX, MGPU_FUSED_BY>(a, nx, ny, nz); break;
+    default: throw Error("make_edge_scal: invalid ppm_type");
+  }
+}
+
+}  // namespace mgpu

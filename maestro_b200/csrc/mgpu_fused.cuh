@@ -2,4 +2,32 @@
 #pragma once
 #include "mgpu_common.cuh"
 
-namespace mgpu {}  // namespace mgpu
+#ifndef MGPU_FUSED_BX
+#define MGPU_FUSED_BX 32
+#endif
+#ifndef MGPU_FUSED_BY
+#define MGPU_FUSED_BY 8
+#endif
+
+namespace mgpu {
+
+struct FusedArgs {
+  int slope_order;
+  int lo[3], hi[3];
+  int bclo[3], bchi[3];
+  bool velnorm[3];
+  int kchunk;  // z planes per CTA
+  double dt, dx[3], rel_eps;
+  DV s, force;  // single-component views
+  DV umac[3];
+  DV sedge[3];  // single-component views of the output
+};
+
+// true when the fused 3-D kernel covers this case (otherwise the general path of mgpu_edge.cu runs)
+bool fused_edge_supported(const mgpu_params& P, bool is_cons);
+// one component (0-based comp, 1-based bccomp) of one box, device pointers
+void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
+                    const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
+                    int ng_f, int kchunk);
+
+}  // namespace mgpu

@@ -60,6 +60,32 @@ def synchronize():
         raise MaestroError(_lib.mgpu_last_error().decode())
 
 
+def set_option(key, value):
+    if load().mgpu_set_option(key.encode(), int(value)) != 0:
+        raise MaestroError(_lib.mgpu_last_error().decode())
+
+
+def profile(on=True):
+    if load().mgpu_profile(1 if on else 0) != 0:
+        raise MaestroError(_lib.mgpu_last_error().decode())
+
+
+PROFILE_TAGS = ["edge_cell_states", "edge_simh", "edge_transverse", "edge_final", "flux", "update", "fill", "glue",
+                "fused_edge", "velpred", "bds", "halo"]
+
+
+def profile_get():
+    """{kernel class: (total ms, launches)} since profile(True)"""
+    out = {}
+    for t, name in enumerate(PROFILE_TAGS):
+        ms, n = C.c_double(), C.c_long()
+        if load().mgpu_profile_get(t, C.byref(ms), C.byref(n)) != 0:
+            raise MaestroError(_lib.mgpu_last_error().decode())
+        if n.value:
+            out[name] = (ms.value, n.value)
+    return out
+
+
 def launch_count(reset=False):
     return int(load().mgpu_launch_count(1 if reset else 0))
 

@@ -79,3 +79,9 @@ def relerr(a, b):
     if den == 0.0:
         return np.abs(a - b).max()
     return np.abs(a - b).max() / den
+
+
+def same(a, b):
+    """bit-for-bit equality; NaNs (the reference's own 0/0 in the negative-species redistribution when no
+    other species is positive, update_scal.f90:486-494) compare equal whatever their payload"""
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)

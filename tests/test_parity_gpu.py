@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from maestro_b200 import Fab, abi, face_fabs
-from synth import make_state, relerr
+from synth import make_state, relerr, same
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -28,11 +28,50 @@ def edge_pair(ops, oracle, st, comps, is_vel=False, cons=False, bccomp0=None):
     return out
 
 
+@pytest.fixture(params=[1, 0], ids=["fused", "staged"])
+def fused(request):
+    """3-D non-conservative edge states have two device paths: the fused single-launch kernel
+    (mgpu_fused.cu, default) and the staged general path (mgpu_edge.cu).  Both must match the oracle."""
+    from maestro_b200 import lib
+
+    lib.set_option("fused", request.param)
+    yield request.param
+    lib.set_option("fused", 1)
+    lib.set_option("kchunk", 64)
+
+
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
+@pytest.mark.parametrize("shape,kchunk", [((37, 9, 11), 4), ((8, 33, 5), 64), ((64, 16, 7), 3)])
+def test_fused_edge_ragged_boxes(gpu_ops, oracle, ppm_type, bcset, shape, kchunk):
+    """Fused kernel on boxes that are not multiples of the CTA tile, several CTAs in x/y and several
+    z-chunks per column: tile seams, the last face hi+1 and chunk seams must be written exactly once
+    and bit-identically."""
+    from maestro_b200 import lib
+
+    lib.set_option("fused", 1)
+    lib.set_option("kchunk", kchunk)
+    phys = {"periodic": None, "walls": WALLS_3D, "inout": INOUT_3D}[bcset]
+    st = make_state(3, shape, phys_bc=phys, ppm_type=ppm_type)
+    st["p"].rel_eps = 1e-8 * max(np.abs(u.a).max() for u in st["umac"])
+    try:
+        g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
+        gv, cv = edge_pair(gpu_ops, oracle, st, (1, 3), is_vel=True, bccomp0=1)
+    finally:
+        lib.set_option("kchunk", 64)
+    for d in range(3):
+        for c_ in range(3):
+            assert same(g[d].a[c_], c[d].a[c_]), (d, c_)
+            assert same(gv[d].a[c_], cv[d].a[c_]), (d, c_)
+
+
 @pytest.mark.parametrize("dm,n", [(2, 24), (3, 16)])
 @pytest.mark.parametrize("ppm_type", [0, 1, 2])
 @pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
 @pytest.mark.parametrize("cons", [False, True])
-def test_make_edge_scal(gpu_ops, oracle, dm, n, ppm_type, bcset, cons):
+def test_make_edge_scal(gpu_ops, oracle, fused, dm, n, ppm_type, bcset, cons):
+    if fused == 0 and (dm == 2 or cons):
+        pytest.skip("only one device path for this case")
     phys = {"periodic": None, "walls": WALLS_3D if dm == 3 else WALLS_2D,
             "inout": INOUT_3D if dm == 3 else INOUT_2D}[bcset]
     st = make_state(dm, n, phys_bc=phys, ppm_type=ppm_type)
@@ -40,7 +79,7 @@ def test_make_edge_scal(gpu_ops, oracle, dm, n, ppm_type, bcset, cons):
     g, c = edge_pair(gpu_ops, oracle, st, (1, st["p"].nscal), cons=cons)
     for d in range(dm):
         assert relerr(g[d].a, c[d].a) <= TOL
-        assert np.array_equal(g[d].a, c[d].a), "parity build should be bit-identical"
+        assert same(g[d].a, c[d].a), "parity build should be bit-identical"
 
 
 @pytest.mark.parametrize("dm,n", [(2, 20), (3, 12)])
@@ -50,7 +89,7 @@ def test_make_edge_scal_velocity(gpu_ops, oracle, dm, n, ppm_type):
     st = make_state(dm, n, phys_bc=INOUT_3D if dm == 3 else INOUT_2D, ppm_type=ppm_type)
     g, c = edge_pair(gpu_ops, oracle, st, (1, dm), is_vel=True, bccomp0=1)
     for d in range(dm):
-        assert np.array_equal(g[d].a, c[d].a)
+        assert same(g[d].a, c[d].a)
 
 
 @pytest.mark.parametrize("slope_order", [0, 2])
@@ -58,14 +97,14 @@ def test_slope_orders(gpu_ops, oracle, slope_order):
     st = make_state(3, 12, phys_bc=WALLS_3D, ppm_type=0, slope_order=slope_order)
     g, c = edge_pair(gpu_ops, oracle, st, (1, 2))
     for d in range(3):
-        assert np.array_equal(g[d].a, c[d].a)
+        assert same(g[d].a, c[d].a)
 
 
 def test_ppm_trace_forces(gpu_ops, oracle):
     st = make_state(3, 12, ng_f=4, phys_bc=WALLS_3D, ppm_type=1, ppm_trace_forces=1)
     g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
     for d in range(3):
-        assert np.array_equal(g[d].a, c[d].a)
+        assert same(g[d].a, c[d].a)
 
 
 def test_ppm2_needs_4_ghosts(gpu_ops):
@@ -112,9 +151,9 @@ def test_flux_update(gpu_ops, oracle, dm, n, spt):
         res.append((sflux, eta, snew))
     (gf, ge, gs), (cf, ce, cs) = res
     for d in range(dm):
-        assert np.array_equal(gf[d].a, cf[d].a)
-    assert np.array_equal(ge.a, ce.a)
-    assert np.array_equal(gs.a, cs.a)
+        assert same(gf[d].a, cf[d].a)
+    assert same(ge.a, ce.a)
+    assert same(gs.a, cs.a)
 
 
 def test_update_scal_floor_and_negative_species(gpu_ops, oracle):
@@ -132,7 +171,7 @@ def test_update_scal_floor_and_negative_species(gpu_ops, oracle):
         o.update_scal(p, p.spec_comp, p.spec_comp + p.nspec - 1, st["s"], snew, sflux, st["force"])
         res.append(snew.a)
     assert (res[1][p.spec_comp - 1] == 0.0).any()
-    assert np.array_equal(res[0], res[1])
+    assert same(res[0], res[1])
 
 
 @pytest.mark.parametrize("dm,n", [(2, 16), (3, 12)])
@@ -167,7 +206,7 @@ def test_update_velocity_addw0_glue(gpu_ops, oracle, dm, n):
         o.convert_rhoX_to_X(p, s2, False)
         res.append((unew.a, um[dm - 1].a, f2.a, s2.a))
     for x, y in zip(*res):
-        assert np.array_equal(x, y)
+        assert same(x, y)
 
 
 @pytest.mark.parametrize("dm,n", [(2, 12), (3, 10)])
@@ -186,7 +225,7 @@ def test_fill_boundary(gpu_ops, oracle, dm, n, bcset):
             o.fill_boundary(p, u, 1, 1, 1, st["adv_bc"], st["pmask"])
         res.append([s.a] + [u.a for u in um])
     for x, y in zip(*res):
-        assert np.array_equal(x, y)
+        assert same(x, y)
 
 
 @pytest.mark.parametrize("dm,n", [(2, 32), (3, 16)])
@@ -218,4 +257,4 @@ def test_density_advance(gpu_ops, oracle, dm, n, ppm_type, spt, which_step, bcse
                         **{"umac%d" % d: umac[d].valid() for d in range(dm)}))
     for k in res[0]:
         assert relerr(res[0][k], res[1][k]) <= TOL, k
-        assert np.array_equal(res[0][k], res[1][k]), k
+        assert same(res[0][k], res[1][k]), k
