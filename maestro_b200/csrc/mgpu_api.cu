@@ -17,7 +17,8 @@ namespace mgpu {
 static Context g_ctx;
 static std::string g_err;
 static int g_opt_fused = 1;    // use the fused 3-D edge kernel when it covers the case
-static int g_opt_kchunk = 64;  // z planes per CTA of the fused kernel
+static int g_opt_kchunk = 32;  // z planes per CTA of the fused kernel
+static int g_opt_exact = 0;    // 1: bit-identical arithmetic everywhere (fused kernel built with -fmad=false)
 Context& ctx() { return g_ctx; }
 
 void require_init() {
@@ -204,7 +205,8 @@ static void edge_one_comp(const mgpu_params& P, const DV& s, DV* sedge, const DV
     }
   }
   if (g_opt_fused && fused_edge_supported(P, is_cons)) {
-    fused_edge_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, ng_s, ng_f, g_opt_kchunk);
+    fused_edge_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, ng_s, ng_f, g_opt_kchunk,
+                   g_opt_exact != 0);
   } else {
     size_t mark = arena_mark();
     make_edge_scal_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, is_cons, ng_s, ng_f);
@@ -369,6 +371,7 @@ int mgpu_set_option(const char* key, int value) {
   std::string k(key ? key : "");
   if (k == "fused") g_opt_fused = value;
   else if (k == "kchunk") g_opt_kchunk = value;
+  else if (k == "exact") g_opt_exact = value;
   else throw Error("mgpu_set_option: unknown key " + k);
   MGPU_CATCH
 }

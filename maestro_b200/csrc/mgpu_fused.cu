@@ -17,20 +17,33 @@
 //
 // Only cells (i,j) strictly inside the CTA's tile produce output, so each plane costs
 // (BX*BY)/((BX-2)*(BY-2)) of the minimal work and nothing is recomputed along z except two planes
-// per z-chunk.  All BC branches of the reference (EXT_DIR, FOEXTRAP/HOEXTRAP with the inflow
-// clamp, REFLECT_EVEN/ODD, wall stencils of PPM/slopes, and its asymmetries) are evaluated from
-// global indices, so the kernel is valid for any box, not just the periodic interior.
-// Expression order matches the reference: with -fmad=false the results are bit-identical to the
-// general path (mgpu_edge.cu) and to the CPU oracle.
+// per z-chunk.
+//
+// Template switches
+//   BC   : true  -> every BC branch of the reference (EXT_DIR, FOEXTRAP/HOEXTRAP with the inflow clamp,
+//                   REFLECT_EVEN/ODD, wall stencils of PPM/slopes, and its asymmetries) is evaluated from
+//                   global indices, so the kernel is valid for any box;
+//          false -> all six faces are INTERIOR (periodic / box-box): the BC code is compiled out.
+//   FAST : false -> expression order and operations of the reference; this translation unit is built with
+//                   -fmad=false, so results are bit-identical to the staged path and to the CPU oracle;
+//          true  -> (mgpu_fused_fast.cu, built with -fmad=true) dt/dx is folded into one factor (no fp64
+//                   division in the loop) and FMA contraction is allowed: differs from the reference in
+//                   the last bits only (tests: <= 1e-12 relative, the north-star tolerance).
 #include "mgpu_fused.cuh"
 #include "mgpu_recon.cuh"
 
+#ifndef MGPU_FAST
+#define MGPU_FAST 0
+#endif
+
 namespace mgpu {
+namespace {
 
 template <int H, int BX, int BY>
 struct FusedSmem {
   static constexpr int SP = BX + 2 * H;  // pitch of the s tile
-  double S[(BY + 2 * H) * SP];
+  static constexpr int SN = (BY + 2 * H) * SP;
+  double S[SN];
   double IPX[BY][BX], IMX[BY][BX], IPY[BY][BX], IMY[BY][BX];
   double Z[2][BY][BX], SHX[2][BY][BX], SHY[2][BY][BX];
   double XY[2][BY][BX], YX[2][BY][BX], ZX[2][BY][BX], ZY[2][BY][BX];
@@ -39,10 +52,12 @@ struct FusedSmem {
   double FRC[2][BY][BX];
 };
 
+template <bool BC>
 __device__ __forceinline__ void bc_states(const FusedArgs& a, int d, int f, double s_lo_m1, double s_lo_0,
                                           double s_hi_p1, int stage, double& sl, double& sr) {
-  // same as lr_bc of the general path, with the needed s values passed in registers:
+  // lr_bc of the staged path with the needed s values passed in registers:
   // s_lo_m1 = s(is-1), s_lo_0 = s(is) (only for the z-lo EXT_DIR quirk), s_hi_p1 = s(ie+1)
+  if (!BC) return;
   const int is = a.lo[d], ie = a.hi[d];
   if (f == is) {
     const int bclo = a.bclo[d];
@@ -95,13 +110,25 @@ __device__ __forceinline__ double final_bc(const FusedArgs& a, int d, int f, dou
   return e;
 }
 
-template <int PPM, int BX, int BY>
-__global__ void __launch_bounds__(BX* BY) k_fused_edge(FusedArgs a) {
+__device__ __forceinline__ LineBC no_wall() {
+  LineBC b;
+  b.lo = -(1 << 30);
+  b.hi = (1 << 30);
+  b.wlo = false;
+  b.whi = false;
+  b.relimit_last = b.lo + 2;
+  b.hi_reset = true;
+  return b;
+}
+
+template <int PPM, bool BC, bool FAST, int BX, int BY>
+__global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? 2 : 1) k_fused_edge(FusedArgs a) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = FusedSmem<H, BX, BY>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   constexpr int SP = SM::SP;
+  constexpr int NT = (SM::SN + BX * BY - 1) / (BX * BY);  // s-tile elements per thread
 
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ibase = a.lo[0] - 1 + blockIdx.x * (BX - 2);
@@ -113,22 +140,53 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge(FusedArgs a) {
   // clamped coordinates for loads by inactive threads (values never used)
   const int ic = min(i, a.hi[0] + 1), jc = min(j, a.hi[1] + 1);
 
-  const LineBC bx = make_linebc(3, 0, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0]);
-  const LineBC by = make_linebc(3, 1, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1]);
-  const LineBC bz = make_linebc(3, 2, a.lo[2], a.hi[2], a.bclo[2], a.bchi[2]);
+  const LineBC bx = BC ? make_linebc(3, 0, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0]) : no_wall();
+  const LineBC by = BC ? make_linebc(3, 1, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1]) : no_wall();
+  const LineBC bz = BC ? make_linebc(3, 2, a.lo[2], a.hi[2], a.bclo[2], a.bchi[2]) : no_wall();
 
   const double dt = a.dt, rel_eps = a.rel_eps;
   const double hx = a.dx[0], hy = a.dx[1], hz = a.dx[2];
-  const double dt2 = 0.5 * dt, dt4 = dt / 4.0, dt6 = dt / 6.0;
+  const double dt2 = 0.5 * dt;
+  // transverse / final coefficients: (dt6/h) and (dt4/h) exactly as the reference forms them
+  const double c6x = (dt / 6.0) / hx, c6y = (dt / 6.0) / hy, c6z = (dt / 6.0) / hz;
+  const double c4x = (dt / 4.0) / hx, c4y = (dt / 4.0) / hy, c4z = (dt / 4.0) / hz;
+  // tracing: FAST folds dt/h
+  const double tdx = FAST ? dt / hx : dt, tdy = FAST ? dt / hy : dt, tdz = FAST ? dt / hz : dt;
 
-  auto sload = [&](int ii, int jj, int kk) -> double { return a.s.p[a.s.off(ii, jj, kk)]; };
+  // ---- per-thread pointers (plane 0 of the fab) and plane strides, hoisted out of the march ----
+  const long s_sz = a.s.stride(2), f_sz = a.force.stride(2);
+  const long u_sz = a.umac[0].stride(2), v_sz = a.umac[1].stride(2), w_sz = a.umac[2].stride(2);
+  const double* ps = a.s.p + a.s.off(ic, jc, 0);
+  const double* pf = a.force.p + a.force.off(ic, jc, 0);
+  const double* pu = a.umac[0].p + a.umac[0].off(ic, jc, 0);
+  const double* pu1 = a.umac[0].p + a.umac[0].off(min(i + 1, a.hi[0] + 2), jc, 0);
+  const double* pv = a.umac[1].p + a.umac[1].off(ic, jc, 0);
+  const double* pv1 = a.umac[1].p + a.umac[1].off(ic, min(j + 1, a.hi[1] + 2), 0);
+  const double* pw = a.umac[2].p + a.umac[2].off(ic, jc, 0);
+  // note: off(.,.,0) is relative to plane index 0; plane k is reached with + k*stride (k may be negative)
+  // s-tile: in-plane offsets of the elements this thread loads (clamped to the fab)
+  int t_off[NT];
+  {
+    const int ilo = a.s.lo[0], ihi = a.s.lo[0] + a.s.n[0] - 1;
+    const int jlo = a.s.lo[1], jhi = a.s.lo[1] + a.s.n[1] - 1;
+#pragma unroll
+    for (int m = 0; m < NT; ++m) {
+      const int t = ty * BX + tx + m * BX * BY;
+      const int yy = t / SP, xx = t - yy * SP;
+      int ii = ibase - H + xx, jj = jbase - H + yy;
+      ii = max(ilo, min(ii, ihi));
+      jj = max(jlo, min(jj, jhi));
+      t_off[m] = (int)a.s.off(ii, jj, 0);
+    }
+  }
+  const double* s0 = a.s.p;
 
   // z register window: sw[m] = s(i,j,q-H+m)
   double sw[2 * H + 1];
   {
     const int q0 = kz0 - 1;
 #pragma unroll
-    for (int m = 1; m <= 2 * H; ++m) sw[m] = sload(ic, jc, q0 - 1 - H + m);  // becomes window of q0-1 shifted below
+    for (int m = 1; m <= 2 * H; ++m) sw[m] = ps[(long)(q0 - 1 - H + m) * s_sz];
     sw[0] = 0.0;
   }
   double Ipz_prev = 0.0;
@@ -143,31 +201,22 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge(FusedArgs a) {
     // ---- S0: loads ---------------------------------------------------------------------------
 #pragma unroll
     for (int m = 0; m < 2 * H; ++m) sw[m] = sw[m + 1];
-    sw[2 * H] = sload(ic, jc, q + H);
+    sw[2 * H] = ps[(long)(q + H) * s_sz];
     {
-      // s tile of plane q: cells ibase-H .. ibase+BX-1+H, jbase-H .. jbase+BY-1+H (clamped to the fab)
-      const int ilo = a.s.lo[0], ihi = a.s.lo[0] + a.s.n[0] - 1;
-      const int jlo = a.s.lo[1], jhi = a.s.lo[1] + a.s.n[1] - 1;
-      for (int t = ty * BX + tx; t < (BY + 2 * H) * SP; t += BX * BY) {
-        const int yy = t / SP, xx = t - yy * SP;
-        int ii = ibase - H + xx, jj = jbase - H + yy;
-        ii = max(ilo, min(ii, ihi));
-        jj = max(jlo, min(jj, jhi));
-        sm.S[t] = sload(ii, jj, q);
+      const long qo = (long)q * s_sz;
+#pragma unroll
+      for (int m = 0; m < NT; ++m) {
+        const int t = ty * BX + tx + m * BX * BY;
+        if (t < SM::SN) sm.S[t] = s0[t_off[m] + qo];
       }
     }
-    {
-      const DV& u = a.umac[0];
-      const DV& v = a.umac[1];
-      const DV& w = a.umac[2];
-      sm.U[par][ty][tx] = u(ic, jc, q);
-      if (tx == BX - 1) sm.U[par][ty][BX] = u(min(i + 1, a.hi[0] + 2), jc, q);
-      sm.V[par][ty][tx] = v(ic, jc, q);
-      if (ty == BY - 1) sm.V[par][BY][tx] = v(ic, min(j + 1, a.hi[1] + 2), q);
-      sm.W[par][ty][tx] = w(ic, jc, q);
-    }
-    const double wq1 = a.umac[2](ic, jc, q + 1);
-    const double f_q = a.force(ic, jc, q);
+    sm.U[par][ty][tx] = pu[(long)q * u_sz];
+    if (tx == BX - 1) sm.U[par][ty][BX] = pu1[(long)q * u_sz];
+    sm.V[par][ty][tx] = pv[(long)q * v_sz];
+    if (ty == BY - 1) sm.V[par][BY][tx] = pv1[(long)q * v_sz];
+    sm.W[par][ty][tx] = pw[(long)q * w_sz];
+    const double wq1 = pw[(long)(q + 1) * w_sz];
+    const double f_q = pf[(long)q * f_sz];
     sm.FRC[par][ty][tx] = f_q;
     __syncthreads();
 
@@ -175,23 +224,23 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge(FusedArgs a) {
     const double uq = sm.U[par][ty][tx], uq1 = sm.U[par][ty][tx + 1];
     const double vq = sm.V[par][ty][tx], vq1 = sm.V[par][ty + 1][tx];
     const double wq = sm.W[par][ty][tx];
+    const double* c = &sm.S[(ty + H) * SP + tx + H];
 
     // ---- S1: P1(q) ---------------------------------------------------------------------------
     {
       double Ip, Im;
-      const double* c = &sm.S[(ty + H) * SP + tx + H];
-      cell_states(PPM, a.slope_order, c, 1, i, bx, uq1, uq, dt, hx, rel_eps, Ip, Im);
+      cell_states<FAST>(PPM, a.slope_order, c, 1, i, bx, uq1, uq, tdx, hx, rel_eps, Ip, Im);
       sm.IPX[ty][tx] = Ip;
       sm.IMX[ty][tx] = Im;
-      cell_states(PPM, a.slope_order, c, SP, j, by, vq1, vq, dt, hy, rel_eps, Ip, Im);
+      cell_states<FAST>(PPM, a.slope_order, c, SP, j, by, vq1, vq, tdy, hy, rel_eps, Ip, Im);
       sm.IPY[ty][tx] = Ip;
       sm.IMY[ty][tx] = Im;
-      cell_states(PPM, a.slope_order, &sw[H], 1, q, bz, wq1, wq, dt, hz, rel_eps, Ip, Im);
+      cell_states<FAST>(PPM, a.slope_order, &sw[H], 1, q, bz, wq1, wq, tdz, hz, rel_eps, Ip, Im);
       // z-face q (between planes q-1 and q)
       slz_q = Ipz_prev;
       srz_q = Im;
       Ipz_prev = Ip;
-      bc_states(a, 2, q, s_p, s_q, s_q, 0, slz_q, srz_q);
+      bc_states<BC>(a, 2, q, s_p, s_q, s_q, 0, slz_q, srz_q);
       sm.Z[par][ty][tx] = riemann(slz_q, srz_q, wq, rel_eps);
     }
     __syncthreads();
@@ -201,13 +250,13 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge(FusedArgs a) {
     if (tx >= 1) {
       slx_q = sm.IPX[ty][tx - 1];
       srx_q = sm.IMX[ty][tx];
-      bc_states(a, 0, i, sm.S[(ty + H) * SP + tx + H - 1], 0.0, s_q, 0, slx_q, srx_q);
+      bc_states<BC>(a, 0, i, c[-1], 0.0, s_q, 0, slx_q, srx_q);
       sm.SHX[par][ty][tx] = riemann(slx_q, srx_q, uq, rel_eps);
     }
     if (ty >= 1) {
       sly_q = sm.IPY[ty - 1][tx];
       sry_q = sm.IMY[ty][tx];
-      bc_states(a, 1, j, sm.S[(ty + H - 1) * SP + tx + H], 0.0, s_q, 0, sly_q, sry_q);
+      bc_states<BC>(a, 1, j, c[-SP], 0.0, s_q, 0, sly_q, sry_q);
       sm.SHY[par][ty][tx] = riemann(sly_q, sry_q, vq, rel_eps);
     }
     __syncthreads();
@@ -215,57 +264,59 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge(FusedArgs a) {
     // ---- S3: transverse states ------------------------------------------------------------------
     // T1(q): x-face corrected by y, y-face corrected by x
     if (tx >= 1 && ty <= BY - 2) {
-      double l = slx_q - (dt6 / hy) * (sm.V[par][ty + 1][tx - 1] + sm.V[par][ty][tx - 1]) *
+      double l = slx_q - c6y * (sm.V[par][ty + 1][tx - 1] + sm.V[par][ty][tx - 1]) *
                              (sm.SHY[par][ty + 1][tx - 1] - sm.SHY[par][ty][tx - 1]);
-      double r = srx_q - (dt6 / hy) * (vq1 + vq) * (sm.SHY[par][ty + 1][tx] - sm.SHY[par][ty][tx]);
-      bc_states(a, 0, i, sm.S[(ty + H) * SP + tx + H - 1], 0.0, s_q, 1, l, r);
+      double r = srx_q - c6y * (vq1 + vq) * (sm.SHY[par][ty + 1][tx] - sm.SHY[par][ty][tx]);
+      bc_states<BC>(a, 0, i, c[-1], 0.0, s_q, 1, l, r);
       sm.XY[par][ty][tx] = riemann(l, r, uq, rel_eps);
     }
     if (ty >= 1 && tx <= BX - 2) {
-      double l = sly_q - (dt6 / hx) * (sm.U[par][ty - 1][tx + 1] + sm.U[par][ty - 1][tx]) *
+      double l = sly_q - c6x * (sm.U[par][ty - 1][tx + 1] + sm.U[par][ty - 1][tx]) *
                              (sm.SHX[par][ty - 1][tx + 1] - sm.SHX[par][ty - 1][tx]);
-      double r = sry_q - (dt6 / hx) * (uq1 + uq) * (sm.SHX[par][ty][tx + 1] - sm.SHX[par][ty][tx]);
-      bc_states(a, 1, j, sm.S[(ty + H - 1) * SP + tx + H], 0.0, s_q, 1, l, r);
+      double r = sry_q - c6x * (uq1 + uq) * (sm.SHX[par][ty][tx + 1] - sm.SHX[par][ty][tx]);
+      bc_states<BC>(a, 1, j, c[-SP], 0.0, s_q, 1, l, r);
       sm.YX[par][ty][tx] = riemann(l, r, vq, rel_eps);
     }
     if (q >= kz0) {
       // T3(q): z-face q corrected by x / by y (left cell = plane q-1, right cell = plane q)
       if (tx <= BX - 2) {
-        double l = slz_q - (dt6 / hx) * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) *
+        double l = slz_q - c6x * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) *
                                (sm.SHX[opar][ty][tx + 1] - sm.SHX[opar][ty][tx]);
-        double r = srz_q - (dt6 / hx) * (uq1 + uq) * (sm.SHX[par][ty][tx + 1] - sm.SHX[par][ty][tx]);
-        bc_states(a, 2, q, s_p, s_q, s_q, 1, l, r);
+        double r = srz_q - c6x * (uq1 + uq) * (sm.SHX[par][ty][tx + 1] - sm.SHX[par][ty][tx]);
+        bc_states<BC>(a, 2, q, s_p, s_q, s_q, 1, l, r);
         sm.ZX[par][ty][tx] = riemann(l, r, wq, rel_eps);
       }
       if (ty <= BY - 2) {
-        double l = slz_q - (dt6 / hy) * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) *
+        double l = slz_q - c6y * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) *
                                (sm.SHY[opar][ty + 1][tx] - sm.SHY[opar][ty][tx]);
-        double r = srz_q - (dt6 / hy) * (vq1 + vq) * (sm.SHY[par][ty + 1][tx] - sm.SHY[par][ty][tx]);
-        bc_states(a, 2, q, s_p, s_q, s_q, 1, l, r);
+        double r = srz_q - c6y * (vq1 + vq) * (sm.SHY[par][ty + 1][tx] - sm.SHY[par][ty][tx]);
+        bc_states<BC>(a, 2, q, s_p, s_q, s_q, 1, l, r);
         sm.ZY[par][ty][tx] = riemann(l, r, wq, rel_eps);
       }
     }
     if (q >= kz0 + 1) {
       // T2(q-1): x- and y-faces of plane q-1 corrected by z.  w on z-faces q-1 (opar) and q (par).
       if (tx >= 1) {
-        double l = slx_p - (dt6 / hz) * (sm.W[par][ty][tx - 1] + sm.W[opar][ty][tx - 1]) *
+        double l = slx_p - c6z * (sm.W[par][ty][tx - 1] + sm.W[opar][ty][tx - 1]) *
                                (sm.Z[par][ty][tx - 1] - sm.Z[opar][ty][tx - 1]);
-        double r = srx_p - (dt6 / hz) * (sm.W[par][ty][tx] + sm.W[opar][ty][tx]) * (sm.Z[par][ty][tx] - sm.Z[opar][ty][tx]);
-        // s(is-1) / s(ie+1) of plane q-1 for EXT_DIR: re-read from global (rare branch)
-        if ((i == a.lo[0] && a.bclo[0] == MGPU_BC_EXT_DIR) || (i == a.hi[0] + 1 && a.bchi[0] == MGPU_BC_EXT_DIR))
-          bc_states(a, 0, i, sload(i - 1, jc, q - 1), 0.0, s_p, 1, l, r);
-        else
-          bc_states(a, 0, i, 0.0, 0.0, 0.0, 1, l, r);
+        double r = srx_p - c6z * (wq + sm.W[opar][ty][tx]) * (sm.Z[par][ty][tx] - sm.Z[opar][ty][tx]);
+        if (BC) {
+          // s(is-1) of plane q-1 for EXT_DIR: re-read from global (rare branch)
+          double slm = 0.0;
+          if (i == a.lo[0] && a.bclo[0] == MGPU_BC_EXT_DIR) slm = a.s(i - 1, jc, q - 1);
+          bc_states<BC>(a, 0, i, slm, 0.0, s_p, 1, l, r);
+        }
         sm.XZ[ty][tx] = riemann(l, r, sm.U[opar][ty][tx], rel_eps);
       }
       if (ty >= 1) {
-        double l = sly_p - (dt6 / hz) * (sm.W[par][ty - 1][tx] + sm.W[opar][ty - 1][tx]) *
+        double l = sly_p - c6z * (sm.W[par][ty - 1][tx] + sm.W[opar][ty - 1][tx]) *
                                (sm.Z[par][ty - 1][tx] - sm.Z[opar][ty - 1][tx]);
-        double r = sry_p - (dt6 / hz) * (sm.W[par][ty][tx] + sm.W[opar][ty][tx]) * (sm.Z[par][ty][tx] - sm.Z[opar][ty][tx]);
-        if ((j == a.lo[1] && a.bclo[1] == MGPU_BC_EXT_DIR) || (j == a.hi[1] + 1 && a.bchi[1] == MGPU_BC_EXT_DIR))
-          bc_states(a, 1, j, sload(ic, j - 1, q - 1), 0.0, s_p, 1, l, r);
-        else
-          bc_states(a, 1, j, 0.0, 0.0, 0.0, 1, l, r);
+        double r = sry_p - c6z * (wq + sm.W[opar][ty][tx]) * (sm.Z[par][ty][tx] - sm.Z[opar][ty][tx]);
+        if (BC) {
+          double slm = 0.0;
+          if (j == a.lo[1] && a.bclo[1] == MGPU_BC_EXT_DIR) slm = a.s(ic, j - 1, q - 1);
+          bc_states<BC>(a, 1, j, slm, 0.0, s_p, 1, l, r);
+        }
         sm.YZ[ty][tx] = riemann(l, r, sm.V[opar][ty][tx], rel_eps);
       }
     }
@@ -274,50 +325,43 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge(FusedArgs a) {
     // ---- S4: final edge states ------------------------------------------------------------------
     const bool inx = (tx >= 1 && tx <= BX - 2 && i <= a.hi[0]);
     const bool iny = (ty >= 1 && ty <= BY - 2 && j <= a.hi[1]);
-    if (q >= kz0 && inx && iny && active) {
+    if (q >= kz0 && inx && iny) {
       // F_z(q): transverse terms x then y, left cell plane q-1 (opar), right cell plane q (par)
-      double el = slz_q - (dt4 / hx) * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) *
-                              (sm.XY[opar][ty][tx + 1] - sm.XY[opar][ty][tx]) -
-                  (dt4 / hy) * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) * (sm.YX[opar][ty + 1][tx] - sm.YX[opar][ty][tx]) +
+      double el = slz_q - c4x * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) * (sm.XY[opar][ty][tx + 1] - sm.XY[opar][ty][tx]) -
+                  c4y * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) * (sm.YX[opar][ty + 1][tx] - sm.YX[opar][ty][tx]) +
                   dt2 * f_p;
-      double er = srz_q - (dt4 / hx) * (uq1 + uq) * (sm.XY[par][ty][tx + 1] - sm.XY[par][ty][tx]) -
-                  (dt4 / hy) * (vq1 + vq) * (sm.YX[par][ty + 1][tx] - sm.YX[par][ty][tx]) + dt2 * f_q;
+      double er = srz_q - c4x * (uq1 + uq) * (sm.XY[par][ty][tx + 1] - sm.XY[par][ty][tx]) -
+                  c4y * (vq1 + vq) * (sm.YX[par][ty + 1][tx] - sm.YX[par][ty][tx]) + dt2 * f_q;
       double e = riemann(el, er, wq, rel_eps);
-      e = final_bc(a, 2, q, e, el, er, s_p, s_q);
+      if (BC) e = final_bc(a, 2, q, e, el, er, s_p, s_q);
       if (q <= kz1 || q == a.hi[2] + 1) a.sedge[2](i, j, q) = e;
     }
     if (q >= kz0 + 1 && active) {
       const int k = q - 1;
       // F_xy(k): x-face (i,j,k): transverse terms y (simhyz) then z (simhzy)
       if (tx >= 1 && (tx <= BX - 2 || i == a.hi[0] + 1) && iny) {
-        double el = slx_p - (dt4 / hy) * (sm.V[opar][ty + 1][tx - 1] + sm.V[opar][ty][tx - 1]) *
-                                (sm.YZ[ty + 1][tx - 1] - sm.YZ[ty][tx - 1]) -
-                    (dt4 / hz) * (sm.W[par][ty][tx - 1] + sm.W[opar][ty][tx - 1]) *
-                        (sm.ZY[par][ty][tx - 1] - sm.ZY[opar][ty][tx - 1]) +
+        double el = slx_p - c4y * (sm.V[opar][ty + 1][tx - 1] + sm.V[opar][ty][tx - 1]) * (sm.YZ[ty + 1][tx - 1] - sm.YZ[ty][tx - 1]) -
+                    c4z * (sm.W[par][ty][tx - 1] + sm.W[opar][ty][tx - 1]) * (sm.ZY[par][ty][tx - 1] - sm.ZY[opar][ty][tx - 1]) +
                     dt2 * sm.FRC[opar][ty][tx - 1];
-        double er = srx_p - (dt4 / hy) * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) * (sm.YZ[ty + 1][tx] - sm.YZ[ty][tx]) -
-                    (dt4 / hz) * (sm.W[par][ty][tx] + sm.W[opar][ty][tx]) * (sm.ZY[par][ty][tx] - sm.ZY[opar][ty][tx]) +
-                    dt2 * f_p;
+        double er = srx_p - c4y * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) * (sm.YZ[ty + 1][tx] - sm.YZ[ty][tx]) -
+                    c4z * (wq + sm.W[opar][ty][tx]) * (sm.ZY[par][ty][tx] - sm.ZY[opar][ty][tx]) + dt2 * f_p;
         double e = riemann(el, er, sm.U[opar][ty][tx], rel_eps);
-        if (i == a.lo[0] || i == a.hi[0] + 1) {
-          const double sl_c = (a.bclo[0] == MGPU_BC_EXT_DIR && i == a.lo[0]) ? sload(i - 1, j, k) : 0.0;
+        if (BC && (i == a.lo[0] || i == a.hi[0] + 1)) {
+          const double sl_c = (a.bclo[0] == MGPU_BC_EXT_DIR && i == a.lo[0]) ? a.s(i - 1, j, k) : 0.0;
           e = final_bc(a, 0, i, e, el, er, sl_c, s_p);
         }
         a.sedge[0](i, j, k) = e;
       }
       // y-face (i,j,k): transverse terms x (simhxz) then z (simhzx)
       if (ty >= 1 && (ty <= BY - 2 || j == a.hi[1] + 1) && inx) {
-        double el = sly_p - (dt4 / hx) * (sm.U[opar][ty - 1][tx + 1] + sm.U[opar][ty - 1][tx]) *
-                                (sm.XZ[ty - 1][tx + 1] - sm.XZ[ty - 1][tx]) -
-                    (dt4 / hz) * (sm.W[par][ty - 1][tx] + sm.W[opar][ty - 1][tx]) *
-                        (sm.ZX[par][ty - 1][tx] - sm.ZX[opar][ty - 1][tx]) +
+        double el = sly_p - c4x * (sm.U[opar][ty - 1][tx + 1] + sm.U[opar][ty - 1][tx]) * (sm.XZ[ty - 1][tx + 1] - sm.XZ[ty - 1][tx]) -
+                    c4z * (sm.W[par][ty - 1][tx] + sm.W[opar][ty - 1][tx]) * (sm.ZX[par][ty - 1][tx] - sm.ZX[opar][ty - 1][tx]) +
                     dt2 * sm.FRC[opar][ty - 1][tx];
-        double er = sry_p - (dt4 / hx) * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) * (sm.XZ[ty][tx + 1] - sm.XZ[ty][tx]) -
-                    (dt4 / hz) * (sm.W[par][ty][tx] + sm.W[opar][ty][tx]) * (sm.ZX[par][ty][tx] - sm.ZX[opar][ty][tx]) +
-                    dt2 * f_p;
+        double er = sry_p - c4x * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) * (sm.XZ[ty][tx + 1] - sm.XZ[ty][tx]) -
+                    c4z * (wq + sm.W[opar][ty][tx]) * (sm.ZX[par][ty][tx] - sm.ZX[opar][ty][tx]) + dt2 * f_p;
         double e = riemann(el, er, sm.V[opar][ty][tx], rel_eps);
-        if (j == a.lo[1] || j == a.hi[1] + 1) {
-          const double sl_c = (a.bclo[1] == MGPU_BC_EXT_DIR && j == a.lo[1]) ? sload(i, j - 1, k) : 0.0;
+        if (BC && (j == a.lo[1] || j == a.hi[1] + 1)) {
+          const double sl_c = (a.bclo[1] == MGPU_BC_EXT_DIR && j == a.lo[1]) ? a.s(i, j - 1, k) : 0.0;
           e = final_bc(a, 1, j, e, el, er, sl_c, s_p);
         }
         a.sedge[1](i, j, k) = e;
@@ -330,29 +374,50 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge(FusedArgs a) {
   }
 }
 
-template <int PPM, int BX, int BY>
-static void launch_fused(const FusedArgs& a, int nx, int ny, int nz) {
+template <int PPM, bool BC, int BX, int BY>
+void launch_fused(const FusedArgs& a, int nx, int ny, int nz) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = FusedSmem<H, BX, BY>;
   Context& c = ctx();
   static bool configured = false;
+  auto kern = k_fused_edge<PPM, BC, (MGPU_FAST != 0), BX, BY>;
   if (!configured) {
-    MGPU_CUDA(cudaFuncSetAttribute(k_fused_edge<PPM, BX, BY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(SM)));
+    MGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
     configured = true;
   }
   dim3 block(BX, BY, 1);
   dim3 grid((nx + BX - 3) / (BX - 2), (ny + BY - 3) / (BY - 2), (nz + a.kchunk - 1) / a.kchunk);
-  MGPU_TIMED(TAG_FUSED_EDGE, (k_fused_edge<PPM, BX, BY><<<grid, block, sizeof(SM), c.stream>>>(a)));
+  MGPU_TIMED(TAG_FUSED_EDGE, (kern<<<grid, block, sizeof(SM), c.stream>>>(a)));
 }
 
+}  // namespace
+
+#if MGPU_FAST
+void fused_edge_launch_fast(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz)
+#else
+void fused_edge_launch_exact(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz)
+#endif
+{
+  constexpr int BX = MGPU_FUSED_BX, BY = MGPU_FUSED_BY;
+  switch (ppm_type * 2 + (bc ? 1 : 0)) {
+    case 0: launch_fused<0, false, BX, BY>(a, nx, ny, nz); break;
+    case 1: launch_fused<0, true, BX, BY>(a, nx, ny, nz); break;
+    case 2: launch_fused<1, false, BX, BY>(a, nx, ny, nz); break;
+    case 3: launch_fused<1, true, BX, BY>(a, nx, ny, nz); break;
+    case 4: launch_fused<2, false, BX, BY>(a, nx, ny, nz); break;
+    case 5: launch_fused<2, true, BX, BY>(a, nx, ny, nz); break;
+    default: throw Error("make_edge_scal: invalid ppm_type");
+  }
+}
+
+#if !MGPU_FAST
 bool fused_edge_supported(const mgpu_params& P, bool is_cons) {
   return P.dm == 3 && P.bds_type == 0 && P.ppm_trace_forces == 0 && !is_cons;
 }
 
 void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
                     const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
-                    int ng_f, int kchunk) {
+                    int ng_f, int kchunk, bool exact) {
   if (P.ppm_type == 2 && ng_s < 4) throw Error("Need 4 ghost cells for ppm_type=2");  // ppm.f90:1864-1866
   if (ng_s < 3) throw Error("make_edge_scal: need at least 3 ghost cells");
   if (ng_f < 1) throw Error("make_edge_scal: force needs at least 1 ghost cell");
@@ -360,12 +425,14 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
   a.slope_order = P.slope_order;
   a.dt = P.dt;
   a.rel_eps = P.rel_eps;
+  bool any_bc = false;
   for (int d = 0; d < 3; ++d) {
     a.lo[d] = lo[d];
     a.hi[d] = hi[d];
     a.dx[d] = P.dx[d];
     a.bclo[d] = adv_bc[d + 3 * (0 + 2 * (bccomp - 1))];
     a.bchi[d] = adv_bc[d + 3 * (1 + 2 * (bccomp - 1))];
+    if (a.bclo[d] != MGPU_BC_INTERIOR || a.bchi[d] != MGPU_BC_INTERIOR) any_bc = true;
     a.velnorm[d] = is_vel && (comp == d);
     a.umac[d] = umac[d];
     a.sedge[d] = sedge_full[d].comp(comp);
@@ -375,12 +442,11 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
   const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
   a.kchunk = kchunk > 0 ? kchunk : nz;
   if (a.kchunk > nz) a.kchunk = nz;
-  switch (P.ppm_type) {
-    case 0: launch_fused<0, MGPU_FUSED_BX, MGPU_FUSED_BY>(a, nx, ny, nz); break;
-    case 1: launch_fused<1, MGPU_FUSED_BX, MGPU_FUSED_BY>(a, nx, ny, nz); break;
-    case 2: launch_fused<2, MGPU_FUSED_BX, MGPU_FUSED_BY>(a, nx, ny, nz); break;
-    default: throw Error("make_edge_scal: invalid ppm_type");
-  }
+  if (exact)
+    fused_edge_launch_exact(a, P.ppm_type, any_bc, nx, ny, nz);
+  else
+    fused_edge_launch_fast(a, P.ppm_type, any_bc, nx, ny, nz);
 }
+#endif
 
 }  // namespace mgpu

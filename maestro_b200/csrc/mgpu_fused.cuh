@@ -26,8 +26,11 @@ struct FusedArgs {
 // true when the fused 3-D kernel covers this case (otherwise the general path of mgpu_edge.cu runs)
 bool fused_edge_supported(const mgpu_params& P, bool is_cons);
 // one component (0-based comp, 1-based bccomp) of one box, device pointers
+// exact: bit-identical arithmetic (-fmad=false build); otherwise the FAST build (dt/dx folded, FMA)
 void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
                     const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
-                    int ng_f, int kchunk);
+                    int ng_f, int kchunk, bool exact);
+void fused_edge_launch_exact(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
+void fused_edge_launch_fast(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
 
 }  // namespace mgpu

@@ -298,15 +298,18 @@ __device__ __forceinline__ void ppm2_cell(const double* q, long st, int c, const
 // ---------------------------------------------------------------------------------------------
 // characteristic tracing, ppm.f90:2233-2251.  up = velocity used for Ip, um = velocity used for Im
 // ---------------------------------------------------------------------------------------------
+// FAST: dt holds dt/h and h is ignored (no fp64 division; results differ from the reference expression
+// (|u|*dt)/h in the last bit, far inside the 1e-12 parity tolerance)
+template <bool FAST = false>
 __device__ __forceinline__ void ppm_trace(double sc, double sm, double sp, double up, double um, double dt,
                                           double h, double rel_eps, double& Ip, double& Im) {
   const double s6 = 6.0 * sc - 3.0 * (sm + sp);
   {
-    double sigma = fabs(up) * dt / h;
+    double sigma = FAST ? fabs(up) * dt : fabs(up) * dt / h;
     Ip = (up > rel_eps) ? sp - (sigma / 2.0) * (sp - sm - (1.0 - (2.0 / 3.0) * sigma) * s6) : sc;
   }
   {
-    double sigma = fabs(um) * dt / h;
+    double sigma = FAST ? fabs(um) * dt : fabs(um) * dt / h;
     Im = (um < -rel_eps) ? sm + (sigma / 2.0) * (sp - sm + (1.0 - (2.0 / 3.0) * sigma) * s6) : sc;
   }
 }
@@ -320,21 +323,22 @@ __device__ __forceinline__ double riemann(double l, double r, double u, double r
 
 // one cell, one direction: the two 1-D extrapolated states this cell sends to its hi face (Ip) and lo
 // face (Im), for every ppm_type.  uhi/ulo are the face velocities (is_umac) or twice the cell velocity.
+template <bool FAST = false>
 __device__ __forceinline__ void cell_states(int ppm_type, int slope_order, const double* q, long st, int c,
                                             const LineBC& b, double uhi, double ulo, double dt, double h,
                                             double rel_eps, double& Ip, double& Im) {
   if (ppm_type == 0) {  // make_edge_scal.f90:818-819 written per cell
     const double sl = slope_cell(q, st, c, b, slope_order);
     const double dt2 = 0.5 * dt;
-    Ip = q[0] + (0.5 - dt2 * uhi / h) * sl;
-    Im = q[0] - (0.5 + dt2 * ulo / h) * sl;
+    Ip = q[0] + (0.5 - (FAST ? dt2 * uhi : dt2 * uhi / h)) * sl;
+    Im = q[0] - (0.5 + (FAST ? dt2 * ulo : dt2 * ulo / h)) * sl;
   } else {
     double sm, sp;
     if (ppm_type == 1)
       ppm1_cell(q, st, c, b, sm, sp);
     else
       ppm2_cell(q, st, c, b, sm, sp);
-    ppm_trace(q[0], sm, sp, uhi, ulo, dt, h, rel_eps, Ip, Im);
+    ppm_trace<FAST>(q[0], sm, sp, uhi, ulo, dt, h, rel_eps, Ip, Im);
   }
 }
 
