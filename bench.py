@@ -235,14 +235,19 @@ def main():
         for u, u0 in zip(e["umac"], umac0):
             u.a.copy_(u0)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi needs ~0.5 s to produce its first sample: start it before the warm-up
     for _ in range(W):
         reset_inputs()
         run_episode(ops, st, e)
+    t_spin = time.time()
+    while time.time() - t_spin < 1.0:  # keep the GPU under the same load until the sampler is running
+        run_episode(ops, st, e)
+        torch.cuda.synchronize()
+    sampler.lines.clear()
     barrier()
     lib.launch_count(reset=True)
     lib.profile(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for k in range(args.steps):

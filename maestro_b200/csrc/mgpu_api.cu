@@ -287,9 +287,6 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   fa.rho0_new = (which_step == 1) ? rho0_old : rho0_new;  // :280-329
   fa.rho0_edge_new = (which_step == 1) ? rho0_edge_old : rho0_edge_new;
   fa.rho0_predicted_edge = rho0_pe;
-  mk_rhoX_flux_dev(P, fa, P.spec_comp, P.spec_comp + P.nspec - 1);
-  if (P.ntrac >= 1) mk_rhoX_flux_dev(P, fa, P.trac_comp, P.trac_comp + P.ntrac - 1);
-
   set_dev(scal_force.p, 0.0, scal_force.size());  // :349-351
   UpdArgs ua;
   ua.dm = dm;
@@ -300,6 +297,17 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   ua.snew = snew;
   ua.force = scal_force;
   for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
+  if (g_opt_fused) {
+    // :280-366 in one launch: species + tracer fluxes, etarhoflux, update, density, floors
+    flux_update_all_dev(P, fa, ua);
+    fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
+    fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
+    if (P.ntrac >= 1)
+      fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.trac_comp, dm + P.trac_comp, P.ntrac, adv_bc, pmask, false);
+    return;
+  }
+  mk_rhoX_flux_dev(P, fa, P.spec_comp, P.spec_comp + P.nspec - 1);
+  if (P.ntrac >= 1) mk_rhoX_flux_dev(P, fa, P.trac_comp, P.trac_comp + P.ntrac - 1);
   update_scal_dev(P, ua, P.spec_comp, P.spec_comp + P.nspec - 1);  // :360
   fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
   fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);

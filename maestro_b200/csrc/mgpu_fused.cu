@@ -195,30 +195,50 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? 2 : 1) k_fused_edge
   double f_p = 0.0;  // force(i,j,q-1)
   double s_p = 0.0;  // s(i,j,q-1)
 
+  // software prefetch: the loads of plane q+1 are issued right after the first barrier of step q, so the
+  // global-memory latency overlaps the compute of step q instead of stalling the smem stores of step q+1
+  double pre_s, pre_S[NT], pre_u, pre_u1 = 0.0, pre_v, pre_v1 = 0.0, pre_w, pre_w1, pre_f;
+  auto prefetch = [&](int q) {
+    pre_s = ps[(long)(q + H) * s_sz];
+    const long qo = (long)q * s_sz;
+#pragma unroll
+    for (int m = 0; m < NT; ++m) {
+      const int t = ty * BX + tx + m * BX * BY;
+      pre_S[m] = (t < SM::SN) ? s0[t_off[m] + qo] : 0.0;
+    }
+    pre_u = pu[(long)q * u_sz];
+    if (tx == BX - 1) pre_u1 = pu1[(long)q * u_sz];
+    pre_v = pv[(long)q * v_sz];
+    if (ty == BY - 1) pre_v1 = pv1[(long)q * v_sz];
+    pre_w1 = pw[(long)(q + 1) * w_sz];
+    pre_f = pf[(long)q * f_sz];
+  };
+  prefetch(kz0 - 1);
+  pre_w = pw[(long)(kz0 - 1) * w_sz];
+
   for (int q = kz0 - 1; q <= kz1 + 1; ++q) {
     const int par = q & 1, opar = par ^ 1;
     __syncthreads();  // previous step's readers of U/V/W/FRC[par] and S are done
-    // ---- S0: loads ---------------------------------------------------------------------------
+    // ---- S0: publish the prefetched plane q ------------------------------------------------------
 #pragma unroll
     for (int m = 0; m < 2 * H; ++m) sw[m] = sw[m + 1];
-    sw[2 * H] = ps[(long)(q + H) * s_sz];
-    {
-      const long qo = (long)q * s_sz;
+    sw[2 * H] = pre_s;
 #pragma unroll
-      for (int m = 0; m < NT; ++m) {
-        const int t = ty * BX + tx + m * BX * BY;
-        if (t < SM::SN) sm.S[t] = s0[t_off[m] + qo];
-      }
+    for (int m = 0; m < NT; ++m) {
+      const int t = ty * BX + tx + m * BX * BY;
+      if (t < SM::SN) sm.S[t] = pre_S[m];
     }
-    sm.U[par][ty][tx] = pu[(long)q * u_sz];
-    if (tx == BX - 1) sm.U[par][ty][BX] = pu1[(long)q * u_sz];
-    sm.V[par][ty][tx] = pv[(long)q * v_sz];
-    if (ty == BY - 1) sm.V[par][BY][tx] = pv1[(long)q * v_sz];
-    sm.W[par][ty][tx] = pw[(long)q * w_sz];
-    const double wq1 = pw[(long)(q + 1) * w_sz];
-    const double f_q = pf[(long)q * f_sz];
+    sm.U[par][ty][tx] = pre_u;
+    if (tx == BX - 1) sm.U[par][ty][BX] = pre_u1;
+    sm.V[par][ty][tx] = pre_v;
+    if (ty == BY - 1) sm.V[par][BY][tx] = pre_v1;
+    sm.W[par][ty][tx] = pre_w;
+    const double wq1 = pre_w1;
+    const double f_q = pre_f;
     sm.FRC[par][ty][tx] = f_q;
+    pre_w = pre_w1;
     __syncthreads();
+    if (q < kz1 + 1) prefetch(q + 1);
 
     const double s_q = sw[H];
     const double uq = sm.U[par][ty][tx], uq1 = sm.U[par][ty][tx + 1];

@@ -407,3 +407,121 @@ void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, con
 }
 
 }  // namespace mgpu
+
+// ------------------------------------------------------------------------------------------
+// Fused mk_rhoX_flux + update_scal for the species AND tracer ranges of density_advance in one launch
+// (density_advance.f90:280-366): one thread per zone computes the fluxes on its own lo faces (written
+// once; the hi+1 faces by the last cell of each line), re-evaluates the hi-face fluxes from the same
+// edge states (3 multiplies; cheaper than a second pass through HBM), then the conservative update,
+// the density from the species updates, the floor and the negative-species redistribution.
+// Arithmetic is expression-for-expression that of k_rhoX_flux / k_update_scal / k_update_rho.
+namespace mgpu {
+
+__device__ __forceinline__ double rhoX_flux_of(const FluxArgs& a, int d, int i, int j, int k, int c) {
+  const int r = a.dm - 1;
+  const int ir = (r == 1) ? j : k;
+  double rho0_edge, vel = a.umac[d](i, j, k);
+  if (d != r) {
+    rho0_edge = 0.5 * (a.rho0_old[ir] + a.rho0_new[ir]);
+  } else {
+    rho0_edge = 0.5 * (a.rho0_edge_old[ir] + a.rho0_edge_new[ir]);
+    vel = vel + a.w0[ir];
+  }
+  const DV& se = a.sedge[d];
+  const long o = se.off(i, j, k);
+  if (a.species_pred_type == MGPU_PREDICT_RHOPRIME_AND_X) return vel * (rho0_edge + se.p[o + se.cs * a.rho]) * se.p[o + se.cs * c];
+  if (a.species_pred_type == MGPU_PREDICT_RHOX) return vel * se.p[o + se.cs * c];
+  return vel * se.p[o + se.cs * a.rho] * se.p[o + se.cs * c];
+}
+
+__global__ void __launch_bounds__(256) k_flux_update_all(FluxArgs a, UpdArgs u, int t0, int ntrac, int rho, double bcd) {
+  int ix[3];
+  if (!decode(u.vb, MGPU_TID, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  const int dm = a.dm, r = dm - 1;
+  const int c0 = a.spec0, nspec = a.nspec;
+  const int ir = ix[r];
+  double eta = 0.0;
+  const bool do_eta = a.evolve_base_state;
+  if (do_eta) eta = a.eta(i, j, k);
+  double eta_hi = 0.0;
+  const bool last_r = (ix[r] == u.vb.hi[r]);
+  if (do_eta && last_r) eta_hi = (r == 1) ? a.eta(i, j + 1, k) : a.eta(i, j, k + 1);
+  bool neg = false;
+  double rnew = u.sold(i, j, k, rho);
+  const int ncomp = nspec + ntrac;
+  for (int n = 0; n < ncomp; ++n) {
+    const int c = (n < nspec) ? c0 + n : t0 + (n - nspec);
+    double flo[3], fhi[3];
+    for (int d = 0; d < dm; ++d) {
+      int ih[3] = {i, j, k};
+      ih[d] += 1;
+      flo[d] = rhoX_flux_of(a, d, i, j, k, c);
+      fhi[d] = rhoX_flux_of(a, d, ih[0], ih[1], ih[2], c);
+      a.sflux[d](i, j, k, c) = flo[d];
+      if (ix[d] == u.vb.hi[d]) a.sflux[d](ih[0], ih[1], ih[2], c) = fhi[d];
+    }
+    if (do_eta && n < nspec) {  // mkflux.f90:486-494
+      eta = eta + flo[r];
+      if (last_r) eta_hi = eta_hi + fhi[r];
+      if (n == nspec - 1) {
+        eta = eta - a.w0[ir] * a.rho0_predicted_edge[ir];
+        if (last_r) eta_hi = eta_hi - a.w0[ir + 1] * a.rho0_predicted_edge[ir + 1];
+      }
+    }
+    double divterm = (fhi[0] - flo[0]) / u.dx[0] + (fhi[1] - flo[1]) / u.dx[1];
+    if (dm == 3) divterm = divterm + (fhi[2] - flo[2]) / u.dx[2];
+    const double so = u.sold(i, j, k, c);
+    const double sn = so + u.dt * (-divterm + u.force(i, j, k, c));
+    u.snew(i, j, k, c) = sn;
+    if (n < nspec) {
+      rnew = rnew + (sn - so);
+      if (sn < 0.0) neg = true;
+    }
+  }
+  if (do_eta) {
+    a.eta(i, j, k) = eta;
+    if (last_r) {
+      if (r == 1) a.eta(i, j + 1, k) = eta_hi;
+      else a.eta(i, j, k + 1) = eta_hi;
+    }
+  }
+  // density, floor, negative species: update_scal.f90:453-505 (same statements as k_update_rho)
+  double* sn = u.snew.p + u.snew.off(i, j, k);
+  const long cn = u.snew.cs;
+  const int c1 = c0 + nspec - 1;
+  if (rnew < 0.5 * bcd) {
+    for (int c = c0; c <= c1; ++c) sn[cn * c] = sn[cn * c] * 0.5 * bcd / rnew;
+    rnew = 0.5 * bcd;
+  }
+  sn[cn * rho] = rnew;
+  if (neg) {
+    for (int c = c0; c <= c1; ++c) {
+      if (sn[cn * c] < 0.0) {
+        double delta = -sn[cn * c];
+        double sumX = 0.0;
+        for (int c2 = c0; c2 <= c1; ++c2)
+          if (c2 != c && sn[cn * c2] >= 0.0) sumX = sumX + sn[cn * c2];
+        for (int c2 = c0; c2 <= c1; ++c2)
+          if (c2 != c && sn[cn * c2] >= 0.0) {
+            double frac = sn[cn * c2] / sumX;
+            sn[cn * c2] = sn[cn * c2] - frac * delta;
+          }
+        sn[cn * c] = 0.0;
+      }
+    }
+  }
+}
+
+void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u) {
+  Context& cx = ctx();
+  const int rho = P.rho_comp - 1;
+  if (u.snew.cs != u.sold.cs) throw Error("update_scal: sold and snew must have the same ghost width");
+  // snew(:,:,:,rho_comp) = sold(:,:,:,rho_comp) including ghost cells (update_scal.f90:455)
+  MGPU_TIMED(TAG_UPDATE, (k_copy<<<nblocks(u.snew.cs, 256), 256, 0, cx.stream>>>(u.snew.p + u.snew.cs * rho,
+                                                                                 u.sold.p + u.sold.cs * rho, u.snew.cs)));
+  MGPU_TIMED(TAG_UPDATE, (k_flux_update_all<<<nblocks(u.vb.npts(), 256), 256, 0, cx.stream>>>(
+                             a, u, P.trac_comp - 1, P.ntrac, rho, P.base_cutoff_density)));
+}
+
+}  // namespace mgpu

@@ -24,6 +24,8 @@ struct UpdArgs {
   DV sold, snew, force, sflux[3];
 };
 void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop);
+// mk_rhoX_flux (species + tracers) + update_scal (species + tracers + density) of density_advance in one launch
+void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u);
 
 struct VelArgs {
   int dm;
