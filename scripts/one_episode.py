@@ -1,0 +1,22 @@
+"""N device-resident density_advance episodes of the bench workload at n^3 (for ncu launch lists). GPU box only."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+
+import bench
+from maestro_b200 import abi, lib
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+ops = lib.init(0, use_torch_stream=True)
+st = bench.test_advect_state(n)
+st["p"].mem_space = abi.DEVICE
+e = bench.alloc_episode(st, "cuda:0")
+for _ in range(reps):
+    bench.run_episode(ops, st, e)
+torch.cuda.synchronize()
+print("launches per episode:", lib.launch_count() // reps)
