@@ -1,0 +1,299 @@
+! maestro_b200_shim.f90 -- ISO_C_BINDING shim between MAESTRO's multifab-level (L3) operators and
+! libmaestro_b200.so (include/maestro_b200.h).
+!
+! How it is used (see INTEGRATION.md): this file is added to Source/ (GPackage.mak), and the bodies
+! of the public L3 routines -- make_edge_scal (Source/make_edge_scal.f90:26), bds (bds.f90:16),
+! mkutrans (mkutrans.f90:17), velpred (velpred.f90:21), mk_rhoX_flux / mk_rhoh_flux
+! (mkflux.f90:48,652), update_scal (update_scal.f90:16), update_velocity (update_vel.f90:15),
+! addw0 (addw0.f90:19) -- replace their `do i=1,nfabs ... call <kernel>_3d(...)` loops by one call
+! of the matching mgpu_* wrapper below.  Public names and argument lists of the L3 routines and of
+! the L4 drivers (advance_premac, density_advance, enthalpy_advance, velocity_advance) do not change.
+!
+! NOT compiled in the build container (no Fortran compiler, FBoxLib not vendored); it is written
+! against the FBoxLib API the reference uses (dataptr, get_box, lwb, upb, nghost, ncomp, nfabs,
+! nodal_flags) and the C structs of include/maestro_b200.h, field for field.
+module maestro_b200_shim
+
+  use iso_c_binding
+  use bl_types
+  use bl_error_module
+  use multifab_module
+  use define_bc_module
+
+  implicit none
+  private
+
+  ! ---- mirrors of the C structs (include/maestro_b200.h) -------------------------------------
+  type, bind(C), public :: mgpu_fab
+     type(c_ptr)    :: ptr
+     integer(c_int) :: lo(3), hi(3)
+     integer(c_int) :: ng, nc
+     integer(c_int) :: nodal(3)
+  end type mgpu_fab
+
+  type, bind(C), public :: mgpu_params
+     integer(c_int) :: dm, mem_space, ppm_type, bds_type, slope_order, ppm_trace_forces
+     integer(c_int) :: species_pred_type, enthalpy_pred_type, spherical, evolve_base_state
+     integer(c_int) :: do_sponge, do_eos_h_above_cutoff
+     integer(c_int) :: rho_comp, rhoh_comp, spec_comp, temp_comp, pi_comp, trac_comp
+     integer(c_int) :: nspec, ntrac, nscal
+     integer(c_int) :: domlo(3), domhi(3)
+     integer(c_int) :: nr
+     real(c_double) :: dt, dx(3), rel_eps, base_cutoff_density
+  end type mgpu_params
+
+  integer(c_int), parameter :: MGPU_HOST = 0
+
+  interface
+     integer(c_int) function mgpu_init(device) bind(C, name="mgpu_init")
+       import :: c_int
+       integer(c_int), value :: device
+     end function mgpu_init
+     integer(c_int) function mgpu_finalize() bind(C, name="mgpu_finalize")
+       import :: c_int
+     end function mgpu_finalize
+     type(c_ptr) function mgpu_last_error() bind(C, name="mgpu_last_error")
+       import :: c_ptr
+     end function mgpu_last_error
+     integer(c_int) function mgpu_host_register(hptr, n) bind(C, name="mgpu_host_register")
+       import :: c_int, c_long, c_ptr
+       type(c_ptr), value :: hptr
+       integer(c_long), value :: n
+     end function mgpu_host_register
+
+     integer(c_int) function mgpu_make_edge_scal_c(p, nfabs, s, sedge, umac, force, adv_bc, is_vel, &
+          start_scomp, start_bccomp, num_comp, is_conservative) bind(C, name="mgpu_make_edge_scal")
+       import :: c_int, c_ptr, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs, is_vel, start_scomp, start_bccomp, num_comp, is_conservative
+       type(mgpu_fab), intent(in) :: s(*), force(*)
+       type(c_ptr), intent(in) :: sedge(*), umac(*)      ! dm pointers to arrays of nfabs mgpu_fab
+       integer(c_int), intent(in) :: adv_bc(*)
+     end function mgpu_make_edge_scal_c
+
+     integer(c_int) function mgpu_bds_c(p, nfabs, s, sedge, umac, force, adv_bc, is_vel, &
+          start_scomp, start_bccomp, num_comp, is_conservative) bind(C, name="mgpu_bds")
+       import :: c_int, c_ptr, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs, is_vel, start_scomp, start_bccomp, num_comp, is_conservative
+       type(mgpu_fab), intent(in) :: s(*), force(*)
+       type(c_ptr), intent(in) :: sedge(*), umac(*)
+       integer(c_int), intent(in) :: adv_bc(*)
+     end function mgpu_bds_c
+
+     integer(c_int) function mgpu_mk_rhoX_flux_c(p, nfabs, sflux, etarhoflux, sedge, umac, w0, rho0_old, &
+          rho0_edge_old, rho0_new, rho0_edge_new, rho0_predicted_edge, startcomp, endcomp) &
+          bind(C, name="mgpu_mk_rhoX_flux")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs, startcomp, endcomp
+       type(c_ptr), intent(in) :: sflux(*), sedge(*), umac(*)
+       type(mgpu_fab), intent(in) :: etarhoflux(*)
+       real(c_double), intent(in) :: w0(*), rho0_old(*), rho0_edge_old(*), rho0_new(*), rho0_edge_new(*), &
+                                     rho0_predicted_edge(*)
+     end function mgpu_mk_rhoX_flux_c
+
+     integer(c_int) function mgpu_mk_rhoh_flux_c(p, nfabs, sflux, sedge, umac, w0, rho0_old, rho0_edge_old, &
+          rho0_new, rho0_edge_new, rhoh0_old, rhoh0_edge_old, rhoh0_new, rhoh0_edge_new) &
+          bind(C, name="mgpu_mk_rhoh_flux")
+       import :: c_int, c_ptr, c_double, mgpu_params
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(c_ptr), intent(in) :: sflux(*), sedge(*), umac(*)
+       real(c_double), intent(in) :: w0(*), rho0_old(*), rho0_edge_old(*), rho0_new(*), rho0_edge_new(*), &
+                                     rhoh0_old(*), rhoh0_edge_old(*), rhoh0_new(*), rhoh0_edge_new(*)
+     end function mgpu_mk_rhoh_flux_c
+
+     integer(c_int) function mgpu_update_scal_c(p, nfabs, nstart, nstop, sold, snew, sflux, force) &
+          bind(C, name="mgpu_update_scal")
+       import :: c_int, c_ptr, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs, nstart, nstop
+       type(mgpu_fab), intent(in) :: sold(*), snew(*), force(*)
+       type(c_ptr), intent(in) :: sflux(*)
+     end function mgpu_update_scal_c
+
+     integer(c_int) function mgpu_update_velocity_c(p, nfabs, uold, unew, umac, uedge, force, sponge, w0) &
+          bind(C, name="mgpu_update_velocity")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(in) :: uold(*), unew(*), force(*), sponge(*)
+       type(c_ptr), intent(in) :: umac(*), uedge(*)
+       real(c_double), intent(in) :: w0(*)
+     end function mgpu_update_velocity_c
+
+     integer(c_int) function mgpu_addw0_c(p, nfabs, umac, w0, mult) bind(C, name="mgpu_addw0")
+       import :: c_int, c_ptr, c_double, mgpu_params
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: w0(*)
+       real(c_double), value :: mult
+     end function mgpu_addw0_c
+
+     integer(c_int) function mgpu_mkutrans_c(p, nfabs, utilde, ufull, utrans, w0, adv_bc, phys_bc) &
+          bind(C, name="mgpu_mkutrans")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(in) :: utilde(*), ufull(*)
+       type(c_ptr), intent(in) :: utrans(*)
+       real(c_double), intent(in) :: w0(*)
+       integer(c_int), intent(in) :: adv_bc(*), phys_bc(*)
+     end function mgpu_mkutrans_c
+
+     integer(c_int) function mgpu_velpred_c(p, nfabs, utilde, ufull, umac, utrans, force, w0, adv_bc, phys_bc) &
+          bind(C, name="mgpu_velpred")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(in) :: utilde(*), ufull(*), force(*)
+       type(c_ptr), intent(in) :: umac(*), utrans(*)
+       real(c_double), intent(in) :: w0(*)
+       integer(c_int), intent(in) :: adv_bc(*), phys_bc(*)
+     end function mgpu_velpred_c
+  end interface
+
+  public :: mgpu_startup, mgpu_shutdown, mgpu_fill_params, mgpu_describe, mgpu_describe_edges, mgpu_check
+  public :: mgpu_make_edge_scal_c, mgpu_bds_c, mgpu_mk_rhoX_flux_c, mgpu_mk_rhoh_flux_c, mgpu_update_scal_c
+  public :: mgpu_update_velocity_c, mgpu_addw0_c, mgpu_mkutrans_c, mgpu_velpred_c
+  public :: make_edge_scal_gpu
+
+contains
+
+  ! one MPI rank <-> one GPU: call once after boxlib_initialize (Source/main.f90:14)
+  subroutine mgpu_startup()
+    use parallel, only: parallel_myproc
+    integer :: ngpu_per_node
+    ngpu_per_node = 8
+    call mgpu_check(mgpu_init(int(mod(parallel_myproc(), ngpu_per_node), c_int)))
+  end subroutine mgpu_startup
+
+  subroutine mgpu_shutdown()
+    call mgpu_check(mgpu_finalize())
+  end subroutine mgpu_shutdown
+
+  ! reference convention: every failure is bl_error -> abort (e.g. make_edge_scal.f90:853)
+  subroutine mgpu_check(rc)
+    integer(c_int), intent(in) :: rc
+    character(kind=c_char), pointer :: cmsg(:)
+    character(len=512) :: msg
+    integer :: k
+    if (rc == 0) return
+    call c_f_pointer(mgpu_last_error(), cmsg, [512])
+    msg = ' '
+    do k = 1, 512
+       if (cmsg(k) == c_null_char) exit
+       msg(k:k) = cmsg(k)
+    end do
+    call bl_error(trim(msg))
+  end subroutine mgpu_check
+
+  ! module variables of the reference -> the per-call parameter block
+  subroutine mgpu_fill_params(p, dm, dx, dt, domlo, domhi)
+    use probin_module, only: ppm_type, bds_type, slope_order, ppm_trace_forces, species_pred_type, &
+         enthalpy_pred_type, evolve_base_state, do_sponge, do_eos_h_above_cutoff, base_cutoff_density
+    use geometry, only: spherical, nr_fine
+    use variables, only: rho_comp, rhoh_comp, spec_comp, temp_comp, pi_comp, trac_comp, nscal, ntrac, rel_eps
+    use network, only: nspec
+    type(mgpu_params), intent(out) :: p
+    integer, intent(in) :: dm, domlo(:), domhi(:)
+    real(dp_t), intent(in) :: dx(:), dt
+    p%dm = dm; p%mem_space = MGPU_HOST
+    p%ppm_type = ppm_type; p%bds_type = bds_type; p%slope_order = slope_order
+    p%ppm_trace_forces = ppm_trace_forces
+    p%species_pred_type = species_pred_type; p%enthalpy_pred_type = enthalpy_pred_type
+    p%spherical = spherical
+    p%evolve_base_state = merge(1, 0, evolve_base_state)
+    p%do_sponge = merge(1, 0, do_sponge)
+    p%do_eos_h_above_cutoff = merge(1, 0, do_eos_h_above_cutoff)
+    p%rho_comp = rho_comp; p%rhoh_comp = rhoh_comp; p%spec_comp = spec_comp
+    p%temp_comp = temp_comp; p%pi_comp = pi_comp; p%trac_comp = trac_comp
+    p%nspec = nspec; p%ntrac = ntrac; p%nscal = nscal
+    p%domlo = 0; p%domhi = 0; p%dx = 0.d0
+    p%domlo(1:dm) = domlo(1:dm); p%domhi(1:dm) = domhi(1:dm)
+    p%nr = nr_fine
+    p%dt = dt; p%dx(1:dm) = dx(1:dm)
+    p%rel_eps = rel_eps; p%base_cutoff_density = base_cutoff_density
+  end subroutine mgpu_fill_params
+
+  ! what dataptr/get_box/nghost give the reference kernels (make_edge_scal.f90:70-76), per local fab
+  subroutine mgpu_describe(mf, d)
+    type(multifab), intent(in) :: mf
+    type(mgpu_fab), intent(out) :: d(:)
+    real(dp_t), pointer :: fp(:,:,:,:)
+    integer :: i, dm
+    logical :: nod(mf%dim)
+    dm = mf%dim
+    nod = nodal_flags(mf)
+    do i = 1, nfabs(mf)
+       fp => dataptr(mf, i)
+       d(i)%ptr = c_loc(fp(lbound(fp,1), lbound(fp,2), lbound(fp,3), 1))
+       d(i)%lo = 0; d(i)%hi = 0; d(i)%nodal = 0
+       d(i)%lo(1:dm) = lwb(get_box(mf, i))
+       d(i)%hi(1:dm) = upb(get_box(mf, i))
+       d(i)%ng = nghost(mf)
+       d(i)%nc = ncomp(mf)
+       d(i)%nodal(1:dm) = merge(1, 0, nod)
+    end do
+  end subroutine mgpu_describe
+
+  ! dm face-centred multifabs -> dm descriptor arrays + the array of C pointers to them
+  subroutine mgpu_describe_edges(mfs, d, dp)
+    type(multifab), intent(in) :: mfs(:)
+    type(mgpu_fab), intent(out), target :: d(:,:)   ! (nfabs, dm)
+    type(c_ptr), intent(out) :: dp(:)
+    integer :: comp
+    do comp = 1, size(mfs)
+       call mgpu_describe(mfs(comp), d(:,comp))
+       dp(comp) = c_loc(d(1,comp))
+    end do
+  end subroutine mgpu_describe_edges
+
+  ! Body of make_edge_scal (Source/make_edge_scal.f90:26) for one level n: replaces :69-121.
+  subroutine make_edge_scal_gpu(s, sedge, umac, force, dx, dt, is_vel, bc_level, start_scomp, &
+                                start_bccomp, num_comp, is_conservative, domlo, domhi)
+    type(multifab), intent(in)    :: s, umac(:), force
+    type(multifab), intent(inout) :: sedge(:)
+    real(dp_t),     intent(in)    :: dx(:), dt
+    logical,        intent(in)    :: is_vel, is_conservative
+    type(bc_level), intent(in)    :: bc_level
+    integer,        intent(in)    :: start_scomp, start_bccomp, num_comp, domlo(:), domhi(:)
+
+    type(mgpu_params) :: p
+    type(mgpu_fab), allocatable, target :: ds(:), df(:), dse(:,:), dum(:,:)
+    type(c_ptr) :: pse(3), pum(3)
+    integer :: nf, dm, i
+
+    dm = s%dim
+    nf = nfabs(s)
+    allocate(ds(nf), df(nf), dse(nf,dm), dum(nf,dm))
+    call mgpu_fill_params(p, dm, dx, dt, domlo, domhi)
+    call mgpu_describe(s, ds)
+    call mgpu_describe(force, df)
+    call mgpu_describe_edges(sedge, dse, pse)
+    call mgpu_describe_edges(umac, dum, pum)
+    ! adv_bc_level_array(i,:,:,:) is contiguous in (d, side, comp) for fixed i only after a copy:
+    do i = 1, nf
+       call mgpu_check(mgpu_make_edge_scal_c(p, 1_c_int, ds(i:i), fab_slice(pse, dse, i, dm), &
+            fab_slice(pum, dum, i, dm), df(i:i), &
+            reshape(bc_level%adv_bc_level_array(i,:,:,:), [size(bc_level%adv_bc_level_array(i,:,:,:))]), &
+            merge(1_c_int, 0_c_int, is_vel), int(start_scomp, c_int), int(start_bccomp, c_int), &
+            int(num_comp, c_int), merge(1_c_int, 0_c_int, is_conservative)))
+    end do
+  contains
+    function fab_slice(pp, dd, i, dm) result(q)
+      type(c_ptr), intent(in) :: pp(:)
+      type(mgpu_fab), intent(in), target :: dd(:,:)
+      integer, intent(in) :: i, dm
+      type(c_ptr) :: q(3)
+      integer :: c
+      q = c_null_ptr
+      do c = 1, dm
+         q(c) = c_loc(dd(i,c))
+      end do
+    end function fab_slice
+  end subroutine make_edge_scal_gpu
+
+end module maestro_b200_shim
