@@ -5,12 +5,14 @@
 // unchanged Fortran sees exactly what the reference routine would have left in its multifabs.
 // Device-pointer calls (MGPU_DEVICE) skip the copies and stay asynchronous on the library stream.
 // There is no CPU fallback anywhere: without a CUDA device every entry point fails.
+#include <algorithm>
 #include <cstring>
 #include <map>
 
 #include "mgpu_edge.cuh"
 #include "mgpu_fused.cuh"
 #include "mgpu_stream.cuh"
+#include "mgpu_velpred.cuh"
 
 namespace mgpu {
 
@@ -618,15 +620,40 @@ int mgpu_addw0(const mgpu_params* p, int nfabs, mgpu_fab* const* umac, const dou
   MGPU_CATCH
 }
 
-int mgpu_mkutrans(const mgpu_params*, int, const mgpu_fab*, const mgpu_fab*, mgpu_fab* const*, const double*,
-                  const int*, const int*) {
-  g_err = "mgpu_mkutrans: not implemented on the device yet";
-  return 1;
+int mgpu_mkutrans(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                  mgpu_fab* const* utrans, const double* w0, const int* adv_bc, const int* phys_bc) {
+  MGPU_TRY
+  Call c(p, (size_t)(p->nr + 2) * sizeof(double) + 4096);
+  const double* w0d = upload_small(w0, p->nr + 1);
+  for (int i = 0; i < nfabs; ++i) {
+    DV ut = c.view(utilde[i], true, false), uf = c.view(ufull[i], true, false);
+    DV tr[3];
+    c.views((const mgpu_fab* const*)utrans, i, true, true, tr);
+    mkutrans_dev(*p, ut, uf, tr, w0d, utilde[i].lo, utilde[i].hi, adv_bc, phys_bc, utilde[i].ng);
+  }
+  c.finish();
+  MGPU_CATCH
 }
-int mgpu_velpred(const mgpu_params*, int, const mgpu_fab*, const mgpu_fab*, mgpu_fab* const*,
-                 const mgpu_fab* const*, const mgpu_fab*, const double*, const int*, const int*) {
-  g_err = "mgpu_velpred: not implemented on the device yet";
-  return 1;
+
+int mgpu_velpred(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                 mgpu_fab* const* umac, const mgpu_fab* const* utrans, const mgpu_fab* force, const double* w0,
+                 const int* adv_bc, const int* phys_bc) {
+  MGPU_TRY
+  size_t need = 0;
+  for (int i = 0; i < nfabs; ++i) need = std::max(need, velpred_scratch(*p, utilde[i].lo, utilde[i].hi));
+  Call c(p, need + (size_t)(p->nr + 2) * sizeof(double) + 4096);
+  const double* w0d = upload_small(w0, p->nr + 1);
+  for (int i = 0; i < nfabs; ++i) {
+    size_t mark = arena_mark();
+    DV ut = c.view(utilde[i], true, false), uf = c.view(ufull[i], true, false), fv = c.view(force[i], true, false);
+    DV um[3], tr[3];
+    c.views((const mgpu_fab* const*)umac, i, true, true, um);
+    c.views(utrans, i, true, false, tr);
+    velpred_dev(*p, ut, uf, um, tr, fv, w0d, utilde[i].lo, utilde[i].hi, adv_bc, phys_bc, utilde[i].ng, force[i].ng);
+    arena_release(mark);
+  }
+  c.finish();
+  MGPU_CATCH
 }
 
 int mgpu_modify_scal_force(const mgpu_params* p, int nfabs, mgpu_fab* force, const mgpu_fab* s,

@@ -1,0 +1,369 @@
+// mkutrans (Source/mkutrans.f90: _2d :257, _3d :461) and velpred (Source/velpred.f90: _2d :266, _3d :640),
+// planar geometry, every ppm_type and every physical BC branch.
+//
+// Stage structure (temporaries in the arena; the per-cell PPM/slope work is re-evaluated by the two faces
+// that need it instead of being stored, so no Ip/Im arrays ever reach HBM):
+//   k_mkutrans   : one launch per direction: 1-D extrapolation of the normal component, BCs, Riemann with w0
+//   k_vp_face    : per face direction d: u_L^d, u_R^d of every component (+BCs) and the transverse
+//                  components upwinded by utrans                                 (velpred.f90:803-1129)
+//   k_vp_trans   : 3-D only, the six corner-coupled states                      (:1139-1558)
+//   k_vp_final   : umac_L/R, Riemann with w0, BCs                               (:1562-1851, 2-D :528-630)
+#include "mgpu_recon.cuh"
+#include "mgpu_velpred.cuh"
+
+namespace mgpu {
+
+namespace {
+
+__device__ __forceinline__ bool wall3(int bc) {
+  return bc == MGPU_BC_SLIP_WALL || bc == MGPU_BC_NO_SLIP_WALL || bc == MGPU_BC_SYMMETRY;
+}
+
+// 1-D extrapolated states of one cell with the CELL-centred velocity (ppm is_umac=.false.)
+// form3d: velpred_3d writes the slope predictor as (1/2 - dt2*max(0,u)/h); mkutrans and velpred_2d as
+// (1/2 - (dt2/h)*max(0,u))  (velpred.f90:812-813 vs :384-392, mkutrans.f90:543-547)
+__device__ __forceinline__ void vel_cell_states(int ppm_type, int slope_order, bool form3d, const double* q, long st,
+                                                int c, const LineBC& b, double ucell, double dt, double h,
+                                                double rel_eps, double& Ip, double& Im) {
+  if (ppm_type == 0) {
+    const double sl = slope_cell(q, st, c, b, slope_order);
+    const double dt2 = 0.5 * dt;
+    if (form3d) {
+      Ip = q[0] + (0.5 - dt2 * dmax2(0.0, ucell) / h) * sl;
+      Im = q[0] - (0.5 + dt2 * dmin2(0.0, ucell) / h) * sl;
+    } else {
+      Ip = q[0] + (0.5 - (dt2 / h) * dmax2(0.0, ucell)) * sl;
+      Im = q[0] - (0.5 + (dt2 / h) * dmin2(0.0, ucell)) * sl;
+    }
+  } else {
+    double sm, sp;
+    if (ppm_type == 1) ppm1_cell(q, st, c, b, sm, sp);
+    else ppm2_cell(q, st, c, b, sm, sp);
+    ppm_trace<false>(q[0], sm, sp, ucell, ucell, dt, h, rel_eps, Ip, Im);
+  }
+}
+
+// Riemann problem with the full velocity (mkutrans.f90:618-631, velpred.f90:1590-1621)
+__device__ __forceinline__ double riemann_full(double l, double r, bool radial, double w0, double rel_eps) {
+  const double uavg = 0.5 * (l + r);
+  bool test;
+  double v;
+  if (radial) {
+    test = ((l + w0 <= 0.0 && r + w0 >= 0.0) || (fabs(l + r + 2.0 * w0) < rel_eps));
+    v = (uavg + w0 > 0.0) ? l : r;
+  } else {
+    test = ((l <= 0.0 && r >= 0.0) || (fabs(l + r) < rel_eps));
+    v = (uavg > 0.0) ? l : r;
+  }
+  return test ? 0.0 : v;
+}
+
+__device__ __forceinline__ double upwind_trans(double l, double r, double ut, double rel_eps) {
+  const double v = (ut > 0.0) ? l : r;
+  const double uavg = 0.5 * (l + r);
+  return (fabs(ut) < rel_eps) ? uavg : v;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_mkutrans(VpArgs a, int d) {
+  int ix[3];
+  Box3 fb = a.vb;
+  fb.hi[d] += 1;
+  if (!decode(fb, MGPU_TID, ix)) return;
+  const DV u = a.utilde.comp(d), uf = a.ufull.comp(d);
+  const long st = u.stride(d);
+  const LineBC b = make_linebc(a.dm, d, a.lo[d], a.hi[d], a.bclo[d][d], a.bchi[d][d]);
+  const double* q = u.p + u.off(ix[0], ix[1], ix[2]);
+  const double* qf = uf.p + uf.off(ix[0], ix[1], ix[2]);
+  const long fst = uf.stride(d);
+  double ul, ur, dummy;
+  vel_cell_states(a.ppm_type, a.slope_order, false, q - st, st, ix[d] - 1, b, qf[-fst], a.dt, a.dx[d], a.rel_eps, ul,
+                  dummy);
+  vel_cell_states(a.ppm_type, a.slope_order, false, q, st, ix[d], b, qf[0], a.dt, a.dx[d], a.rel_eps, dummy, ur);
+  if (ix[d] == a.lo[d]) {
+    const int p = a.plo[d];
+    if (p == MGPU_BC_INLET) { ul = q[-st]; ur = q[-st]; }
+    else if (wall3(p)) { ul = 0.0; ur = 0.0; }
+    else if (p == MGPU_BC_OUTLET) { ul = dmin2(ur, 0.0); ur = ul; }
+  }
+  if (ix[d] == a.hi[d] + 1) {
+    const int p = a.phi[d];
+    if (p == MGPU_BC_INLET) { ul = q[0]; ur = q[0]; }
+    else if (wall3(p)) { ul = 0.0; ur = 0.0; }
+    else if (p == MGPU_BC_OUTLET) { ul = dmax2(ul, 0.0); ur = ul; }
+  }
+  const bool radial = (d == a.dm - 1);
+  a.utrans[d](ix[0], ix[1], ix[2]) = riemann_full(ul, ur, radial, radial ? a.w0[ix[d]] : 0.0, a.rel_eps);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_vp_face(VpArgs a, int d) {
+  int ix[3];
+  Box3 fb = a.tb;
+  fb.lo[d] = a.lo[d];  // faces lo..hi+1 in d, lo-1..hi+1 transverse
+  if (!decode(fb, MGPU_TID, ix)) return;
+  const int dm = a.dm;
+  const DV ufd = a.ufull.comp(d);
+  const long fo = ufd.off(ix[0], ix[1], ix[2]);
+  const double ucl = ufd.p[fo - ufd.stride(d)], ucr = ufd.p[fo];
+  const long uo = a.utilde.off(ix[0], ix[1], ix[2]);
+  const long st = a.utilde.stride(d);
+  double ul[3], ur[3];
+  for (int c = 0; c < dm; ++c) {
+    const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[c][d], a.bchi[c][d]);
+    const double* q = a.utilde.p + uo + a.utilde.cs * c;
+    double dummy;
+    vel_cell_states(a.ppm_type, a.slope_order, dm == 3, q - st, st, ix[d] - 1, b, ucl, a.dt, a.dx[d], a.rel_eps, ul[c],
+                    dummy);
+    vel_cell_states(a.ppm_type, a.slope_order, dm == 3, q, st, ix[d], b, ucr, a.dt, a.dx[d], a.rel_eps, dummy, ur[c]);
+  }
+  if (ix[d] == a.lo[d]) {
+    const int p = a.plo[d];
+    if (p == MGPU_BC_INLET) {
+      for (int c = 0; c < dm; ++c) ul[c] = ur[c] = a.utilde.p[uo - st + a.utilde.cs * c];
+    } else if (p == MGPU_BC_SLIP_WALL || p == MGPU_BC_SYMMETRY) {
+      for (int c = 0; c < dm; ++c) {
+        if (c == d) ul[c] = ur[c] = 0.0;
+        else ul[c] = ur[c];
+      }
+    } else if (p == MGPU_BC_NO_SLIP_WALL) {
+      for (int c = 0; c < dm; ++c) ul[c] = ur[c] = 0.0;
+    } else if (p == MGPU_BC_OUTLET) {
+      ur[d] = dmin2(ur[d], 0.0);
+      if (d == 0 && dm == 2) {  // QUIRK velpred.f90:415-417: copies the wrong way (urx = ulx)
+        for (int c = 0; c < dm; ++c) ur[c] = ul[c];
+      } else if (d == 0 && dm == 3) {  // QUIRK velpred.f90:861-862: self-assignment
+      } else {
+        for (int c = 0; c < dm; ++c) ul[c] = ur[c];
+      }
+    }
+  }
+  if (ix[d] == a.hi[d] + 1) {
+    const int p = a.phi[d];
+    if (p == MGPU_BC_INLET) {
+      for (int c = 0; c < dm; ++c) ul[c] = ur[c] = a.utilde.p[uo + a.utilde.cs * c];
+    } else if (p == MGPU_BC_SLIP_WALL || p == MGPU_BC_SYMMETRY) {
+      for (int c = 0; c < dm; ++c) {
+        if (c == d) ul[c] = ur[c] = 0.0;
+        else ur[c] = ul[c];
+      }
+    } else if (p == MGPU_BC_NO_SLIP_WALL) {
+      for (int c = 0; c < dm; ++c) ul[c] = ur[c] = 0.0;
+    } else if (p == MGPU_BC_OUTLET) {
+      ul[d] = dmax2(ul[d], 0.0);
+      for (int c = 0; c < dm; ++c) ur[c] = ul[c];
+    }
+  }
+  const double ut = a.utrans[d](ix[0], ix[1], ix[2]);
+  const long to = a.UL[d].off(ix[0], ix[1], ix[2]);
+  for (int c = 0; c < dm; ++c) {
+    a.UL[d].p[to + a.UL[d].cs * c] = ul[c];
+    a.UR[d].p[to + a.UR[d].cs * c] = ur[c];
+    if (c != d) a.UIMH[d].p[to + a.UIMH[d].cs * c] = upwind_trans(ul[c], ur[c], ut, a.rel_eps);
+  }
+}
+
+// coef * (trans_t(cell+e_t) + trans_t(cell)) * (q(cell+e_t) - q(cell))
+__device__ __forceinline__ double tterm(double coef, const DV& tr, const DV& q, long qcomp_off, int t, int ci, int cj,
+                                        int ck) {
+  const long to = tr.off(ci, cj, ck), qo = q.off(ci, cj, ck) + qcomp_off;
+  return coef * (tr.p[to + tr.stride(t)] + tr.p[to]) * (q.p[qo + q.stride(t)] - q.p[qo]);
+}
+
+__global__ void k_vp_trans(VpArgs a) {
+  int ix[3];
+  if (!decode(a.tb, MGPU_TID, ix)) return;
+  const double dt6 = a.dt / 6.0;
+  for (int c = 0; c < 3; ++c)
+    for (int d = 0; d < 3; ++d) {
+      if (d == c) continue;
+      const int t = 3 - c - d;
+      if (ix[d] < a.lo[d] || ix[t] < a.lo[t] || ix[t] > a.hi[t]) continue;
+      int cl[3] = {ix[0], ix[1], ix[2]};
+      cl[d] -= 1;
+      const long fo = a.UL[d].off(ix[0], ix[1], ix[2]) + a.UL[d].cs * c;
+      const long qc = a.UIMH[t].cs * c;
+      double ql = a.UL[d].p[fo] - tterm(dt6 / a.dx[t], a.utrans[t], a.UIMH[t], qc, t, cl[0], cl[1], cl[2]);
+      double qr = a.UR[d].p[fo] - tterm(dt6 / a.dx[t], a.utrans[t], a.UIMH[t], qc, t, ix[0], ix[1], ix[2]);
+      if (ix[d] == a.lo[d]) {
+        const int p = a.plo[d];
+        if (p == MGPU_BC_INLET) ql = qr = a.utilde(cl[0], cl[1], cl[2], c);
+        else if (p == MGPU_BC_SLIP_WALL || p == MGPU_BC_SYMMETRY || p == MGPU_BC_OUTLET) ql = qr;
+        else if (p == MGPU_BC_NO_SLIP_WALL) ql = qr = 0.0;
+      }
+      if (ix[d] == a.hi[d] + 1) {
+        const int p = a.phi[d];
+        if (p == MGPU_BC_INLET) ql = qr = a.utilde(ix[0], ix[1], ix[2], c);
+        else if (p == MGPU_BC_SLIP_WALL || p == MGPU_BC_SYMMETRY || p == MGPU_BC_OUTLET) qr = ql;
+        else if (p == MGPU_BC_NO_SLIP_WALL) ql = qr = 0.0;
+      }
+      a.Q[c][d](ix[0], ix[1], ix[2]) = upwind_trans(ql, qr, a.utrans[d](ix[0], ix[1], ix[2]), a.rel_eps);
+    }
+}
+
+__global__ void k_vp_final(VpArgs a, int d) {
+  int ix[3];
+  Box3 fb = a.vb;
+  fb.hi[d] += 1;
+  if (!decode(fb, MGPU_TID, ix)) return;
+  const int dm = a.dm;
+  const double dt2 = 0.5 * a.dt, dt4 = a.dt / 4.0;
+  int cl[3] = {ix[0], ix[1], ix[2]};
+  cl[d] -= 1;
+  double fl, fr;
+  {
+    const DV f = a.force.comp(d);
+    const long fo = f.off(ix[0], ix[1], ix[2]);
+    const long fst = f.stride(d);
+    if (a.trace) {  // force traced along its own direction with the cell velocity (velpred.f90:783-793)
+      const DV ufd = a.ufull.comp(d);
+      const long uo = ufd.off(ix[0], ix[1], ix[2]);
+      const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[d][d], a.bchi[d][d]);
+      double dummy;
+      vel_cell_states(a.ppm_type, a.slope_order, dm == 3, f.p + fo - fst, fst, ix[d] - 1, b, ufd.p[uo - ufd.stride(d)],
+                      a.dt, a.dx[d], a.rel_eps, fl, dummy);
+      vel_cell_states(a.ppm_type, a.slope_order, dm == 3, f.p + fo, fst, ix[d], b, ufd.p[uo], a.dt, a.dx[d], a.rel_eps,
+                      dummy, fr);
+    } else {
+      fl = f.p[fo - fst];
+      fr = f.p[fo];
+    }
+  }
+  const long fo = a.UL[d].off(ix[0], ix[1], ix[2]) + a.UL[d].cs * d;
+  double ml, mr;
+  if (dm == 2) {
+    const int t = 1 - d;
+    const long qc = a.UIMH[t].cs * d;
+    ml = a.UL[d].p[fo] - tterm(dt4 / a.dx[t], a.utrans[t], a.UIMH[t], qc, t, cl[0], cl[1], cl[2]) + dt2 * fl;
+    mr = a.UR[d].p[fo] - tterm(dt4 / a.dx[t], a.utrans[t], a.UIMH[t], qc, t, ix[0], ix[1], ix[2]) + dt2 * fr;
+  } else {
+    const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
+    ml = a.UL[d].p[fo] - tterm(dt4 / a.dx[t1], a.utrans[t1], a.Q[d][t1], 0, t1, cl[0], cl[1], cl[2]) -
+         tterm(dt4 / a.dx[t2], a.utrans[t2], a.Q[d][t2], 0, t2, cl[0], cl[1], cl[2]) + dt2 * fl;
+    mr = a.UR[d].p[fo] - tterm(dt4 / a.dx[t1], a.utrans[t1], a.Q[d][t1], 0, t1, ix[0], ix[1], ix[2]) -
+         tterm(dt4 / a.dx[t2], a.utrans[t2], a.Q[d][t2], 0, t2, ix[0], ix[1], ix[2]) + dt2 * fr;
+  }
+  const bool radial = (d == dm - 1);
+  double e = riemann_full(ml, mr, radial, radial ? a.w0[ix[d]] : 0.0, a.rel_eps);
+  if (ix[d] == a.lo[d]) {
+    const int p = a.plo[d];
+    if (p == MGPU_BC_INLET) e = a.utilde(cl[0], cl[1], cl[2], d);
+    else if (wall3(p)) e = 0.0;
+    else if (p == MGPU_BC_OUTLET) e = dmin2(mr, 0.0);
+  }
+  if (ix[d] == a.hi[d] + 1) {
+    const int p = a.phi[d];
+    if (p == MGPU_BC_INLET) e = a.utilde(ix[0], ix[1], ix[2], d);
+    else if (wall3(p)) e = 0.0;
+    else if (p == MGPU_BC_OUTLET) e = dmax2(ml, 0.0);
+  }
+  a.umac[d](ix[0], ix[1], ix[2]) = e;
+}
+
+void check_phys(int bc, const char* who) {
+  switch (bc) {
+    case MGPU_BC_INLET: case MGPU_BC_OUTLET: case MGPU_BC_SYMMETRY: case MGPU_BC_SLIP_WALL: case MGPU_BC_NO_SLIP_WALL:
+    case MGPU_BC_INTERIOR: case MGPU_BC_PERIODIC:
+      return;
+    default:
+      throw Error(std::string(who) + ": invalid boundary type phys_bc");
+  }
+}
+
+void fill_common(VpArgs& a, const mgpu_params& P, const DV& utilde, const DV& ufull, const double* w0_dev,
+                 const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const char* who) {
+  const int dm = P.dm;
+  if (P.spherical) throw Error(std::string(who) + ": spherical geometry not available on the device yet");
+  if (P.ppm_type == 2 && ng_u < 4) throw Error("Need 4 ghost cells for ppm_type=2");  // ppm.f90:1864-1866
+  if (ng_u < 3) throw Error(std::string(who) + ": need at least 3 ghost cells");
+  a.dm = dm;
+  a.ppm_type = P.ppm_type;
+  a.slope_order = P.slope_order;
+  a.trace = false;
+  a.dt = P.dt;
+  a.rel_eps = P.rel_eps;
+  for (int d = 0; d < 3; ++d) {
+    a.lo[d] = d < dm ? lo[d] : 0;
+    a.hi[d] = d < dm ? hi[d] : 0;
+    a.dx[d] = P.dx[d < dm ? d : 0];
+    a.plo[d] = a.phi[d] = MGPU_BC_INTERIOR;
+    for (int c = 0; c < 3; ++c) a.bclo[c][d] = a.bchi[c][d] = MGPU_BC_INTERIOR;
+    if (d < dm) {
+      a.plo[d] = phys_bc[d + dm * 0];
+      a.phi[d] = phys_bc[d + dm * 1];
+      check_phys(a.plo[d], who);
+      check_phys(a.phi[d], who);
+      for (int c = 0; c < dm; ++c) {
+        a.bclo[c][d] = adv_bc[d + dm * (0 + 2 * c)];
+        a.bchi[c][d] = adv_bc[d + dm * (1 + 2 * c)];
+      }
+    }
+  }
+  a.tb = grown(lo, hi, dm, 1);
+  a.vb = grown(lo, hi, dm, 0);
+  a.utilde = utilde;
+  a.ufull = ufull;
+  a.w0 = w0_dev;
+}
+
+}  // namespace
+
+void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* utrans, const double* w0_dev,
+                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u) {
+  VpArgs a;
+  fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "mkutrans");
+  for (int d = 0; d < P.dm; ++d) a.utrans[d] = utrans[d];
+  for (int d = 0; d < P.dm; ++d) {
+    Box3 fb = a.vb;
+    fb.hi[d] += 1;
+    MGPU_TIMED(TAG_VELPRED, (k_mkutrans<<<nblocks(fb.npts(), 256), 256, 0, ctx().stream>>>(a, d)));
+  }
+}
+
+size_t velpred_scratch(const mgpu_params& P, const int* lo, const int* hi) {
+  Box3 tb = grown(lo, hi, P.dm, 1);
+  const size_t narr = (size_t)3 * P.dm * P.dm + (P.dm == 3 ? 6 : 0);
+  return narr * ((size_t)tb.npts() * sizeof(double) + 256) + 4096;
+}
+
+void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans, const DV& force,
+                 const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
+                 int ng_f) {
+  VpArgs a;
+  fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "velpred");
+  const int dm = P.dm;
+  a.trace = (P.ppm_trace_forces == 1) && P.ppm_type != 0;
+  if (a.trace && ng_f < ng_u) throw Error("velpred: ppm_trace_forces needs force with as many ghost cells as utilde");
+  if (ng_f < 1) throw Error("velpred: force needs at least 1 ghost cell");
+  a.force = force;
+  for (int d = 0; d < dm; ++d) {
+    a.utrans[d] = utrans[d];
+    a.umac[d] = umac[d];
+  }
+  const long nt = a.tb.npts();
+  int z3[3] = {0, 0, 0};
+  auto tmp = [&](int nc) { return make_view(arena_alloc((size_t)nt * nc), a.tb.lo, a.tb.hi, dm, 0, z3, nc); };
+  for (int d = 0; d < dm; ++d) {
+    a.UL[d] = tmp(dm);
+    a.UR[d] = tmp(dm);
+    a.UIMH[d] = tmp(dm);
+  }
+  if (dm == 3)
+    for (int c = 0; c < 3; ++c)
+      for (int d = 0; d < 3; ++d)
+        if (c != d) a.Q[c][d] = tmp(1);
+  cudaStream_t s = ctx().stream;
+  for (int d = 0; d < dm; ++d) {
+    Box3 fb = a.tb;
+    fb.lo[d] = a.lo[d];
+    MGPU_TIMED(TAG_VELPRED, (k_vp_face<<<nblocks(fb.npts(), 128), 128, 0, s>>>(a, d)));
+  }
+  if (dm == 3) MGPU_TIMED(TAG_VELPRED, (k_vp_trans<<<nblocks(nt, 256), 256, 0, s>>>(a)));
+  for (int d = 0; d < dm; ++d) {
+    Box3 fb = a.vb;
+    fb.hi[d] += 1;
+    MGPU_TIMED(TAG_VELPRED, (k_vp_final<<<nblocks(fb.npts(), 256), 256, 0, s>>>(a, d)));
+  }
+}
+
+}  // namespace mgpu

@@ -1,0 +1,29 @@
+// Argument block + host launchers of mkutrans / velpred (see mgpu_velpred.cu).
+#pragma once
+#include "mgpu_common.cuh"
+
+namespace mgpu {
+
+struct VpArgs {
+  int dm, ppm_type, slope_order;
+  bool trace;
+  int lo[3], hi[3];
+  int bclo[3][3], bchi[3][3];  // [component][direction]: adv_bc(d, side, comp)
+  int plo[3], phi[3];          // phys_bc(d, side)
+  double dt, dx[3], rel_eps;
+  Box3 tb, vb;  // lo-1:hi+1 and lo:hi
+  DV utilde, ufull, force;
+  DV utrans[3], umac[3];
+  DV UL[3], UR[3], UIMH[3];  // per face direction, dm components, on tb
+  DV Q[3][3];                // [component][face direction], 3-D only
+  const double* w0;
+};
+
+void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* utrans, const double* w0_dev,
+                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u);
+void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans, const DV& force,
+                 const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
+                 int ng_f);
+size_t velpred_scratch(const mgpu_params& P, const int* lo, const int* hi);
+
+}  // namespace mgpu

@@ -85,3 +85,66 @@ def same(a, b):
     """bit-for-bit equality; NaNs (the reference's own 0/0 in the negative-species redistribution when no
     other species is positive, update_scal.f90:486-494) compare equal whatever their payload"""
     return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def make_vel_state(dm, n, ng_u=4, ng_f=1, seed=2468, phys_bc=None, noise=0.1, w0amp=0.05, oracle=None, **pkw):
+    """Inputs of mkutrans / velpred (Source/advance_premac.f90:75-116): utilde with ghost cells filled per adv_bc,
+    ufull = utilde + w0 on cells (radial component), force (dm comps), w0 on edges.  Host fabs."""
+    rng = np.random.default_rng(seed)
+    nn = [n] * dm if np.isscalar(n) else list(n)
+    p = make_params(dm, n=nn + [1] * (3 - dm), **pkw)
+    lo, hi = [0, 0, 0], [nn[d] - 1 if d < dm else 0 for d in range(3)]
+    if phys_bc is None:
+        phys_bc = [[abi.PERIODIC, abi.PERIODIC]] * dm
+    pmask = [1 if phys_bc[d][0] == abi.PERIODIC else 0 for d in range(dm)] + [0] * (3 - dm)
+    adv_bc = make_adv_bc(p, phys_bc)
+    pb = np.ascontiguousarray(np.array(phys_bc, dtype=np.int32).T)  # [side, d] == Fortran phys_bc(d+1, side+1)
+    utilde = Fab(lo, hi, ng_u, dm, dm=dm)
+    x, y, z = cell_coords(utilde, p)
+    co = [x, y, z]
+    for c in range(dm):
+        a, b = co[(c + 1) % dm], co[(c + 2) % dm] if dm == 3 else co[(c + 1) % dm]
+        utilde.a[c] = np.sin(2 * np.pi * b) + np.cos(2 * np.pi * a) + 0.3 * np.sin(4 * np.pi * co[c]) + 0.0 * (x + y + z)
+    utilde.a[...] += noise * rng.uniform(-1.0, 1.0, size=utilde.shape)
+    nr = p.nr
+    ze = np.arange(nr + 1) * p.dx[dm - 1]
+    w0 = w0amp * np.sin(2 * np.pi * ze)
+    if oracle is not None:  # ghost cells as the reference's fills leave them (periodic wrap + multifab_physbc)
+        oracle.fill_boundary(p, utilde, 1, 1, dm, adv_bc, pmask)
+    ufull = utilde.clone()
+    w0c = 0.5 * (w0[:-1] + w0[1:])  # put_1d_array_on_cart of the cell-centred w0 (advance_premac.f90:75-78)
+    idx = np.clip(np.arange(-ng_u, nn[dm - 1] + ng_u), 0, nr - 1)
+    shape = [1, 1, 1]
+    shape[2 - (dm - 1)] = idx.size
+    ufull.a[dm - 1] += w0c[idx].reshape(shape)
+    umax = float(np.abs(ufull.a).max())
+    p.dt = 0.7 * p.dx[0] / umax
+    p.rel_eps = 1e-8 * umax
+    force = Fab(lo, hi, ng_f, dm, dm=dm)
+    force.a[...] = rng.uniform(-1.0, 1.0, size=force.shape)
+    return dict(p=p, lo=lo, hi=hi, dm=dm, utilde=utilde, ufull=ufull, force=force, w0=w0, adv_bc=adv_bc, phys_bc=pb,
+                pmask=pmask, phys=phys_bc)
+
+
+def fill_face_ghosts(fabs, pmask, dm):
+    """Ghost faces of utrans/umac as multifab_fill_boundary leaves them on a single periodic box (plain copies);
+    at non-periodic sides the neighbouring valid face is copied (FBoxLib's multifab_physbc_edgevel is not in the
+    reference tree; those values only reach states that the reference overwrites by a BC)."""
+    for f in fabs:
+        a = f.a
+        for d in range(dm):
+            ax = 3 - d
+            n = f.hi[d] - f.lo[d] + 1
+            ng = f.ng
+            nod = f.nodal[d]
+            ext = a.shape[ax]
+            def sl(i0, i1):
+                s = [slice(None)] * 4
+                s[ax] = slice(i0, i1)
+                return tuple(s)
+            if pmask[d]:
+                a[sl(0, ng)] = a[sl(n, n + ng)]
+                a[sl(ng + n + nod, ext)] = a[sl(ng + nod, ng + nod + (ext - ng - n - nod))]
+            else:
+                a[sl(0, ng)] = a[sl(ng, ng + 1)]
+                a[sl(ng + n + nod, ext)] = a[sl(ng + n + nod - 1, ng + n + nod)]

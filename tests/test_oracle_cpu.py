@@ -141,3 +141,89 @@ def test_mirror_symmetry_across_reflecting_wall(oracle):
     ex, ey = sedge[0].a[0], sedge[1].a[0]
     assert np.abs(ey - ey[..., ::-1]).max() < 1e-13
     assert np.abs(ex - ex[..., ::-1]).max() < 1e-13
+
+
+# ---- mkutrans / velpred (no golden vector exists in the reference: pinned by invariants) ----------
+def _premac(ops, st, ng_ut=1):
+    from maestro_b200 import face_fabs
+    from synth import fill_face_ghosts
+
+    p, dm = st["p"], st["dm"]
+    utrans = face_fabs(st["lo"], st["hi"], ng_ut, 1, dm)
+    ops.mkutrans(p, st["utilde"], st["ufull"], utrans, st["w0"], st["adv_bc"], st["phys_bc"])
+    fill_face_ghosts(utrans, st["pmask"], dm)
+    umac = face_fabs(st["lo"], st["hi"], 1, 1, dm)
+    ops.velpred(p, st["utilde"], st["ufull"], umac, utrans, st["force"], st["w0"], st["adv_bc"], st["phys_bc"])
+    return utrans, umac
+
+
+VP_WALLS = {2: [[abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]],
+            3: [[abi.PERIODIC, abi.PERIODIC], [abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]}
+VP_INOUT = {2: [[abi.OUTLET, abi.INLET], [abi.NO_SLIP_WALL, abi.SYMMETRY]],
+            3: [[abi.OUTLET, abi.INLET], [abi.NO_SLIP_WALL, abi.SLIP_WALL], [abi.SYMMETRY, abi.OUTLET]]}
+
+
+@pytest.mark.parametrize("dm,n", [(2, 12), (3, 8)])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+def test_velpred_uniform_flow_is_preserved(oracle, dm, n, ppm_type):
+    from synth import make_vel_state
+
+    st = make_vel_state(dm, n, noise=0.0, w0amp=0.0, ppm_type=ppm_type)
+    vec = [0.7, -0.4, 0.25]
+    for c in range(dm):
+        st["utilde"].a[c] = vec[c]
+        st["ufull"].a[c] = vec[c]
+    st["force"].a[...] = 0.0
+    utrans, umac = _premac(oracle, st)
+    for d in range(dm):
+        assert np.array_equal(utrans[d].valid(0), np.full_like(utrans[d].valid(0), vec[d]))
+        assert np.array_equal(umac[d].valid(0), np.full_like(umac[d].valid(0), vec[d]))
+
+
+@pytest.mark.parametrize("dm,n", [(2, 10), (3, 7)])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
+@pytest.mark.parametrize("trace", [0, 1])
+def test_velpred_bounds_checked_build_agrees(oracle, dm, n, ppm_type, bcset, trace):
+    from synth import make_vel_state
+
+    if trace and ppm_type == 0:
+        pytest.skip("ppm_trace_forces needs ppm_type >= 1")
+    dbg = oracle_lib.load(debug=True)
+    phys = {"periodic": None, "walls": VP_WALLS[dm], "inout": VP_INOUT[dm]}[bcset]
+    st = make_vel_state(dm, n, phys_bc=phys, ppm_type=ppm_type, ppm_trace_forces=trace, ng_f=4 if trace else 1,
+                        oracle=oracle)
+    a = _premac(oracle, st)
+    b = _premac(dbg, st)
+    for x, y in zip(a[0] + a[1], b[0] + b[1]):
+        assert np.array_equal(x.valid(0), y.valid(0))
+        assert np.isfinite(x.valid(0)).all()
+
+
+def test_velpred_wall_normal_velocity_is_zero(oracle):
+    from synth import make_vel_state
+
+    st = make_vel_state(3, 8, phys_bc=VP_WALLS[3], oracle=oracle)
+    utrans, umac = _premac(oracle, st)
+    assert np.all(umac[2].valid(0)[0] == 0.0) and np.all(utrans[2].valid(0)[0] == 0.0)   # slip wall at z-lo
+    assert np.all(umac[2].valid(0)[-1] >= 0.0)  # outlet at z-hi: max(umacl, 0)
+
+
+def test_velpred_axis_permutation_symmetry(oracle):
+    """x->y->z->x relabelling of a periodic problem (w0 = 0) relabels the outputs; only the summation order of the
+    two transverse terms changes, so agreement is to rounding."""
+    from maestro_b200 import Fab
+    from synth import make_vel_state
+
+    st = make_vel_state(3, 8, w0amp=0.0)
+    _, umac = _premac(oracle, st)
+    st2 = make_vel_state(3, 8, w0amp=0.0)
+    for name in ("utilde", "ufull", "force"):
+        a = st[name].a  # (c, z, y, x); new axes: x' = y, y' = z, z' = x ; new comps: c' = (c-1) mod 3
+        b = np.transpose(a, (0, 3, 1, 2))  # b[c, z'=x, y'=z, x'=y]
+        st2[name].a[...] = b[[1, 2, 0]]
+    _, umac2 = _premac(oracle, st2)
+    for d in range(3):  # umac'_{d'} with d' = (d-1) mod 3 equals umac_d transposed
+        ref = np.transpose(umac[d].valid(0), (2, 0, 1))
+        got = umac2[(d - 1) % 3].valid(0)
+        assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()

@@ -286,3 +286,66 @@ def test_density_advance(gpu_ops, oracle, dm, n, ppm_type, spt, which_step, bcse
         assert relerr(res[0][k], res[1][k]) <= TOL, k
         if exact:
             assert same(res[0][k], res[1][k]), k
+
+
+# ---- mkutrans / velpred ---------------------------------------------------------------------------------
+VP_WALLS = {2: [[abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]],
+            3: [[abi.PERIODIC, abi.PERIODIC], [abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]}
+VP_INOUT = {2: [[abi.OUTLET, abi.INLET], [abi.NO_SLIP_WALL, abi.SYMMETRY]],
+            3: [[abi.OUTLET, abi.INLET], [abi.NO_SLIP_WALL, abi.SLIP_WALL], [abi.SYMMETRY, abi.OUTLET]]}
+VP_INOUT2 = {2: [[abi.INLET, abi.OUTLET], [abi.SYMMETRY, abi.NO_SLIP_WALL]],
+             3: [[abi.INLET, abi.OUTLET], [abi.SLIP_WALL, abi.NO_SLIP_WALL], [abi.OUTLET, abi.SYMMETRY]]}
+
+
+@pytest.mark.parametrize("dm,n", [(2, (24, 17)), (3, (16, 9, 12))])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout", "inout2"])
+@pytest.mark.parametrize("trace", [0, 1])
+def test_mkutrans_velpred(gpu_ops, oracle, dm, n, ppm_type, bcset, trace):
+    """advance_premac.f90:90-116: mkutrans -> ghost fill -> velpred, bit-identical to the oracle
+    (utrans on every face direction, umac on every face direction)."""
+    from synth import fill_face_ghosts, make_vel_state
+
+    if trace and ppm_type == 0:
+        pytest.skip("ppm_trace_forces needs ppm_type >= 1")
+    phys = {"periodic": None, "walls": VP_WALLS[dm], "inout": VP_INOUT[dm], "inout2": VP_INOUT2[dm]}[bcset]
+    st = make_vel_state(dm, list(n), phys_bc=phys, ppm_type=ppm_type, ppm_trace_forces=trace, ng_f=4 if trace else 1,
+                        oracle=oracle)
+    p = st["p"]
+    res = []
+    for o in (gpu_ops, oracle):
+        utrans = face_fabs(st["lo"], st["hi"], 1, 1, dm, fill=-777.0)
+        o.mkutrans(p, st["utilde"], st["ufull"], utrans, st["w0"], st["adv_bc"], st["phys_bc"])
+        fill_face_ghosts(utrans, st["pmask"], dm)
+        umac = face_fabs(st["lo"], st["hi"], 1, 1, dm, fill=-777.0)
+        o.velpred(p, st["utilde"], st["ufull"], umac, utrans, st["force"], st["w0"], st["adv_bc"], st["phys_bc"])
+        res.append(utrans + umac)
+    for g, c in zip(*res):
+        check(g.a, c.a)
+
+
+@pytest.mark.parametrize("slope_order", [0, 2])
+def test_velpred_slope_orders(gpu_ops, oracle, slope_order):
+    from synth import fill_face_ghosts, make_vel_state
+
+    st = make_vel_state(3, 10, phys_bc=VP_WALLS[3], ppm_type=0, slope_order=slope_order, oracle=oracle)
+    res = []
+    for o in (gpu_ops, oracle):
+        utrans = face_fabs(st["lo"], st["hi"], 1, 1, 3)
+        o.mkutrans(st["p"], st["utilde"], st["ufull"], utrans, st["w0"], st["adv_bc"], st["phys_bc"])
+        fill_face_ghosts(utrans, st["pmask"], 3)
+        umac = face_fabs(st["lo"], st["hi"], 1, 1, 3)
+        o.velpred(st["p"], st["utilde"], st["ufull"], umac, utrans, st["force"], st["w0"], st["adv_bc"], st["phys_bc"])
+        res.append(utrans + umac)
+    for g, c in zip(*res):
+        assert same(g.a, c.a)
+
+
+def test_velpred_invalid_phys_bc_is_an_error(gpu_ops):
+    from synth import make_vel_state
+
+    st = make_vel_state(2, 8)
+    st["phys_bc"][:] = 99
+    utrans = face_fabs(st["lo"], st["hi"], 1, 1, 2)
+    with pytest.raises(RuntimeError, match="invalid boundary"):
+        gpu_ops.mkutrans(st["p"], st["utilde"], st["ufull"], utrans, st["w0"], st["adv_bc"], st["phys_bc"])
