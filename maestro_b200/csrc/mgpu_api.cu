@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 
+#include "mgpu_bds.cuh"
 #include "mgpu_edge.cuh"
 #include "mgpu_fused.cuh"
 #include "mgpu_stream.cuh"
@@ -255,10 +256,16 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
     fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
   }
   auto edge = [&](int scomp, int ncomp, bool cons) {
-    if (P.bds_type != 0) throw Error("bds: not available on the device yet");
-    for (int n = 0; n < ncomp; ++n)
+    for (int n = 0; n < ncomp; ++n) {
+      if (P.bds_type != 0) {  // density_advance.f90:183-185 etc.
+        size_t mark = arena_mark();
+        bds_dev(P, sold, sedge, umac, scal_force, lo, hi, scomp - 1 + n, cons, ng_s, ng_f);
+        arena_release(mark);
+        continue;
+      }
       edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, scomp - 1 + n, dm + scomp + n, false, cons, ng_s,
                     ng_f);
+    }
   };
   if (spt == MGPU_PREDICT_RHOX) edge(P.spec_comp, P.nspec, true);  // :190-198
   else edge(P.spec_comp, P.nspec, false);                            // :178-186
@@ -497,10 +504,27 @@ int mgpu_make_edge_scal(const mgpu_params* p, int nfabs, const mgpu_fab* s, mgpu
   MGPU_CATCH
 }
 
-int mgpu_bds(const mgpu_params*, int, const mgpu_fab*, mgpu_fab* const*, const mgpu_fab* const*, const mgpu_fab*,
-             const int*, int, int, int, int, int) {
-  g_err = "mgpu_bds: not implemented on the device yet";
-  return 1;
+int mgpu_bds(const mgpu_params* p, int nfabs, const mgpu_fab* s, mgpu_fab* const* sedge,
+             const mgpu_fab* const* umac, const mgpu_fab* force, const int* adv_bc, int is_vel, int start_scomp,
+             int start_bccomp, int num_comp, int is_conservative) {
+  MGPU_TRY
+  (void)adv_bc; (void)is_vel; (void)start_bccomp;  // unused by the reference too (bds.f90:16-131)
+  size_t need = 0;
+  for (int i = 0; i < nfabs; ++i) need = std::max(need, bds_scratch(*p, s[i].lo, s[i].hi));
+  Call c(p, need);
+  for (int i = 0; i < nfabs; ++i) {
+    DV sv = c.view(s[i], true, false), fv = c.view(force[i], true, false);
+    DV se[3], um[3];
+    c.views((const mgpu_fab* const*)sedge, i, true, true, se);
+    c.views(umac, i, true, false, um);
+    for (int scomp = start_scomp; scomp < start_scomp + num_comp; ++scomp) {
+      size_t mark = arena_mark();
+      bds_dev(*p, sv, se, um, fv, s[i].lo, s[i].hi, scomp - 1, is_conservative != 0, s[i].ng, force[i].ng);
+      arena_release(mark);
+    }
+  }
+  c.finish();
+  MGPU_CATCH
 }
 
 int mgpu_mk_rhoX_flux(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, mgpu_fab* etarhoflux,
@@ -707,7 +731,8 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
   MGPU_TRY
   (void)p0_dummy;
   if (p->spherical) throw Error("mgpu_density_advance: spherical geometry not available on the device yet");
-  Call c(p, make_edge_scal_scratch(*p, sold->lo, sold->hi) + (size_t)(8 * (p->nr + 2)) * sizeof(double) + 8192);
+  Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
+             (size_t)(8 * (p->nr + 2)) * sizeof(double) + 8192);
   DV so = c.view(*sold, true, true), sn = c.view(*snew, true, true), fv = c.view(*scal_force, true, true);
   DV eta = c.view(*etarhoflux, true, true);
   DV se[3], sf[3], um[3];

@@ -349,3 +349,43 @@ def test_velpred_invalid_phys_bc_is_an_error(gpu_ops):
     utrans = face_fabs(st["lo"], st["hi"], 1, 1, 2)
     with pytest.raises(RuntimeError, match="invalid boundary"):
         gpu_ops.mkutrans(st["p"], st["utilde"], st["ufull"], utrans, st["w0"], st["adv_bc"], st["phys_bc"])
+
+
+# ---- BDS --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dm,n", [(2, (24, 17)), (3, (14, 9, 11))])
+@pytest.mark.parametrize("cons", [False, True])
+@pytest.mark.parametrize("vel", ["A", "C"])
+def test_bds(gpu_ops, oracle, dm, n, cons, vel):
+    """bds (Source/bds.f90:16): bdsslope + bdsconc with sheared, sign-changing velocities (set C exercises the
+    z-face corner quirk), bit-identical to the oracle."""
+    st = make_state(dm, list(n), bds_type=1, vel=vel)
+    p = st["p"]
+    out = []
+    for o in (gpu_ops, oracle):
+        sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm, fill=-777.0)
+        o.bds(p, st["s"], sedge, st["umac"], st["force"], st["adv_bc"], False, 1, dm + 1, p.nscal, cons)
+        out.append(sedge)
+    for d in range(dm):
+        check(out[0][d].a, out[1][d].a)
+
+
+@pytest.mark.parametrize("dm,n", [(2, 20), (3, 12)])
+@pytest.mark.parametrize("spt", [1, 2])
+def test_density_advance_bds(gpu_ops, oracle, dm, n, spt):
+    st = make_state(dm, n, bds_type=1, species_pred_type=spt)
+    p, b = st["p"], st["base"]
+    res = []
+    for o in (gpu_ops, oracle):
+        sold = st["s"].clone()
+        oracle.fill_boundary(p, sold, 1, dm + 1, p.nscal, st["adv_bc"], st["pmask"])
+        snew = sold.clone()
+        umac = [u.clone() for u in st["umac"]]
+        sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+        sflux = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+        force = st["force"].clone()
+        eta = Fab(st["lo"], st["hi"], 0, 1, nodal=[0] * (dm - 1) + [1], dm=dm)
+        o.density_advance(p, 1, sold, snew, sedge, sflux, force, umac, b["w0"], eta, b["rho0_old"], b["rho0_new"],
+                          b["p0"], b["rho0_predicted_edge"], st["adv_bc"], st["pmask"])
+        res.append([snew.a, eta.a] + [f.a for f in sedge] + [f.a for f in sflux])
+    for g, c in zip(*res):
+        check(g, c)
