@@ -136,6 +136,27 @@ int mgpu_memcpy_d2h(double* dst, const double* src, long n);
 int mgpu_fill_boundary(const mgpu_params* p, mgpu_fab* s, int scomp, int bccomp, int ncomp,
                        const int* adv_bc, const int* pmask);
 
+/* ---- multi-GPU: one slab per rank along the slowest index (z in 3-D, y in 2-D); replaces the MPI ghost
+ * exchange inside FBoxLib's multifab_fill_boundary (call sites: SURVEY.md section 2d) by NCCL send/recv between
+ * slab neighbours.  Rank r owns the r-th slab; every fab carries its global lo/hi, params->domlo/domhi the
+ * problem domain.  After mgpu_comm_init every ghost fill of the library (mgpu_fill_boundary and the fills
+ * inside the L4 episodes) exchanges the slab-direction ghost planes with ranks r-1 / r+1 (periodic wrap where
+ * pmask says so) and applies physical BCs only where adv_bc is not INTERIOR. ---- */
+typedef struct {
+  int dir;                    /* slab direction (dm-1) */
+  int up_rank, dn_rank;       /* neighbour owning the next / previous slab; -1: none (physical boundary) */
+  int nplanes;                /* ghost planes exchanged per side (= ng) */
+  long plane_doubles;         /* doubles in one (x[,y]) plane of one component, ghost cells included */
+  int send_up_k0, send_dn_k0; /* first plane index (slab direction, global) sent to up_rank / dn_rank */
+  int recv_lo_k0, recv_hi_k0; /* first ghost plane index received from dn_rank / up_rank */
+} mgpu_halo_plan;
+/* pure host arithmetic (no GPU): the exchange plan of one fab */
+int mgpu_halo_plan_make(const mgpu_params* p, const mgpu_fab* f, const int* pmask, int rank, int nranks,
+                        mgpu_halo_plan* out);
+int mgpu_comm_unique_id(void* out128);                              /* ncclGetUniqueId (rank 0) */
+int mgpu_comm_init(int rank, int nranks, const void* unique_id128); /* ncclCommInitRank on the bound GPU */
+int mgpu_comm_finalize(void);
+
 /* ---- L3 operators ---------------------------------------------------------------------- */
 /* make_edge_scal (Source/make_edge_scal.f90:26): edge states of comps start_scomp.. of s on all
  * faces; sedge[d] nodal in d, written in comps start_scomp...  umac[d] nodal in d with 1 ghost. */

@@ -62,6 +62,20 @@ class mgpu_params(C.Structure):
     ]
 
 
+class mgpu_halo_plan(C.Structure):
+    _fields_ = [
+        ("dir", C.c_int),
+        ("up_rank", C.c_int),
+        ("dn_rank", C.c_int),
+        ("nplanes", C.c_int),
+        ("plane_doubles", C.c_long),
+        ("send_up_k0", C.c_int),
+        ("send_dn_k0", C.c_int),
+        ("recv_lo_k0", C.c_int),
+        ("recv_hi_k0", C.c_int),
+    ]
+
+
 P_ = C.POINTER(mgpu_params)
 F_ = C.POINTER(mgpu_fab)
 FF_ = C.POINTER(F_)  # array of dm pointers, each to an array of nfabs fabs
@@ -104,6 +118,10 @@ LIFECYCLE = {
     "mgpu_free": (C.c_int, [C.c_void_p]),
     "mgpu_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long]),
     "mgpu_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long]),
+    "mgpu_halo_plan_make": (C.c_int, [P_, F_, c_int_p, C.c_int, C.c_int, C.POINTER(mgpu_halo_plan)]),
+    "mgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "mgpu_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "mgpu_comm_finalize": (C.c_int, []),
 }
 
 

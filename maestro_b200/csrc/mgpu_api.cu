@@ -12,6 +12,7 @@
 #include "mgpu_bds.cuh"
 #include "mgpu_edge.cuh"
 #include "mgpu_fused.cuh"
+#include "mgpu_halo.cuh"
 #include "mgpu_stream.cuh"
 #include "mgpu_velpred.cuh"
 
@@ -373,6 +374,7 @@ int mgpu_finalize(void) {
   MGPU_TRY
   if (!g_ctx.initialised) return 0;
   cudaStreamSynchronize(g_ctx.stream);
+  comm_finalize();
   g_pool.clear();
   if (g_ctx.arena) cudaFree(g_ctx.arena);
   g_ctx.arena = nullptr;
@@ -466,6 +468,31 @@ int mgpu_host_register(double* hptr, long n) {
 int mgpu_host_unregister(double* hptr) {
   MGPU_TRY
   MGPU_CUDA(cudaHostUnregister(hptr));
+  MGPU_CATCH
+}
+
+int mgpu_halo_plan_make(const mgpu_params* p, const mgpu_fab* f, const int* pmask, int rank, int nranks,
+                        mgpu_halo_plan* out) {
+  MGPU_TRY
+  if (p->dm != 2 && p->dm != 3) throw Error("mgpu_halo_plan_make: dm must be 2 or 3");
+  long ext[3];
+  for (int d = 0; d < 3; ++d) ext[d] = d < p->dm ? f->hi[d] - f->lo[d] + 1 + 2 * f->ng + f->nodal[d] : 1;
+  halo_plan_make(p->dm, p->domlo, p->domhi, f->lo, f->hi, f->ng, f->nodal, ext, pmask, rank, nranks, out);
+  MGPU_CATCH
+}
+int mgpu_comm_unique_id(void* out128) {
+  MGPU_TRY
+  comm_unique_id(out128);
+  MGPU_CATCH
+}
+int mgpu_comm_init(int rank, int nranks, const void* unique_id128) {
+  MGPU_TRY
+  comm_init(rank, nranks, unique_id128);
+  MGPU_CATCH
+}
+int mgpu_comm_finalize(void) {
+  MGPU_TRY
+  comm_finalize();
   MGPU_CATCH
 }
 

@@ -8,6 +8,7 @@
 //   rhoX<->X       Source/convert_rhoX_to_X.f90:44-56
 //   ghost fill     FBoxLib multifab_fill_boundary (periodic wrap) + Source/multifab_physbc.f90:150,329
 // All are HBM-bound: one thread per zone/face, x-contiguous so every warp reads/writes whole lines.
+#include "mgpu_halo.cuh"
 #include "mgpu_stream.cuh"
 
 namespace mgpu {
@@ -364,10 +365,14 @@ void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, con
   const int dm = P.dm;
   if (ng == 0) return;
   const bool is_nodal = nodal && (nodal[0] || nodal[1] || nodal[2]);
+  // slab-partitioned domain: the slab-direction ghost planes come from the neighbouring ranks (NCCL), first, so
+  // that the in-box wraps and physical BCs below also cover the received planes (corners come out right)
+  const bool slab = halo_exchange_dev(P, sfull, lo, hi, ng, nodal, scomp - 1, ncomp, pmask, cx.stream);
   for (int n = 0; n < ncomp; ++n) {
     DV s = sfull.comp(scomp - 1 + n);
     for (int d = 0; d < dm; ++d) {
       if (!pmask[d]) continue;
+      if (slab && d == dm - 1) continue;
       Box3 tb;
       for (int q = 0; q < 3; ++q) { tb.lo[q] = s.lo[q]; tb.hi[q] = s.lo[q] + s.n[q] - 1; }
       tb.lo[d] = 0;

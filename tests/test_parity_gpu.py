@@ -389,3 +389,25 @@ def test_density_advance_bds(gpu_ops, oracle, dm, n, spt):
         res.append([snew.a, eta.a] + [f.a for f in sedge] + [f.a for f in sflux])
     for g, c in zip(*res):
         check(g, c)
+
+
+# ---- multi-GPU: slab partition + NCCL halo exchange (needs >= 2 GPUs; run with gpurun --gpus 2) -------------
+@pytest.mark.parametrize("dm,bcset,ppm_type", [(3, "periodic", 1), (3, "walls", 2), (2, "walls", 2)])
+def test_multi_gpu_density_advance(gpu_ops, dm, bcset, ppm_type):
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if ng < 4 else 4
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(here, "mgpu_rank_parity.py"), str(dm),
+           bcset, str(ppm_type)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" OK ") == world
