@@ -91,13 +91,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def test_advect_state(n, device=None, seed=67890):
-    """test_advect initial data on an n^3 periodic unit box + velocity set B/C of SURVEY 8d."""
+def test_advect_state(n, device=None, seed=67890, rank=0, world=1):
+    """test_advect initial data + velocity set B/C of SURVEY 8d on this rank's n^3 slab of the periodic
+    n x n x (n*world) domain (world = 1: the n^3 unit box of the reference test)."""
     from maestro_b200 import Fab, abi, face_fabs, make_adv_bc, make_params
 
-    p = make_params(3, n=[n, n, n], ppm_type=1)
+    p = make_params(3, n=[n, n, n * world], ppm_type=1)
     p.base_cutoff_density = 1e-10
-    lo, hi = [0, 0, 0], [n - 1] * 3
+    lo, hi = [0, 0, rank * n], [n - 1, n - 1, rank * n + n - 1]
     W = float(np.float32(0.05))
     x = (np.arange(-4, n + 4) + 0.5) / n
     xp = ((x % 1.0) - 0.5) ** 2
@@ -113,6 +114,7 @@ def test_advect_state(n, device=None, seed=67890):
     umac = face_fabs(lo, hi, 1, 1, 3)
     for d, u in enumerate(umac):
         c = [(np.arange(-1, u.shape[3 - q] - 1) + (0.0 if q == d else 0.5)) / n for q in range(3)]
+        # the fields are 1-periodic, so every slab of the taller domain sees the same (globally periodic) data
         X, Y, Z = c[0][None, None, :], c[1][None, :, None], c[2][:, None, None]
         o = [X, Y, Z]
         a, b = o[(d + 1) % 3], o[(d + 2) % 3]
@@ -122,7 +124,7 @@ def test_advect_state(n, device=None, seed=67890):
     p.dt = 0.7 * p.dx[0] / umax
     p.rel_eps = 1e-8 * umax
     adv_bc = make_adv_bc(p, [[abi.PERIODIC, abi.PERIODIC]] * 3)
-    zero_c, zero_e = np.zeros(n), np.zeros(n + 1)
+    zero_c, zero_e = np.zeros(n * world), np.zeros(n * world + 1)
     st = dict(p=p, lo=lo, hi=hi, sold=sold, umac=umac, adv_bc=adv_bc, pmask=[1, 1, 1],
               base=dict(w0=zero_e, rho0_old=zero_c, rho0_new=zero_c, p0=zero_c, rho0_predicted_edge=zero_e))
     return st
@@ -213,7 +215,11 @@ def main():
     dev = "cuda:%d" % local_rank
     ops = lib.init(local_rank, use_torch_stream=True)
     n = args.n
-    st = test_advect_state(n, seed=67890 + rank)
+    if world > 1:  # NCCL communicator of the library: halo exchange inside every ghost fill of the episode
+        from maestro_b200 import slab
+
+        slab.comm_init_from_torch(lib.load(), dev)
+    st = test_advect_state(n, rank=rank, world=world)
     p = st["p"]
     ncomp = ncomp_advanced(p)
     zone_updates = n ** 3 * ncomp
@@ -302,11 +308,9 @@ def main():
     keep = [pin(f) for f in [eh["sold"], eh["snew"], eh["force"], eh["eta"]] + eh["umac"] + eh["sedge"] + eh["sflux"]]
     sold_h0 = eh["sold"].a.copy()
     umac_h0 = [u.a.copy() for u in eh["umac"]]
-    in_bytes = 8 * (eh["sold"].a.size + eh["snew"].a.size + eh["force"].a.size + eh["eta"].a.size
-                    + sum(u.a.size for u in eh["umac"]) + sum(f.a.size for f in eh["sedge"] + eh["sflux"]))
-    out_bytes = in_bytes
     run_episode(ops, st, eh)  # warm-up (allocates the staging pool)
     barrier()
+    lib.copy_bytes(reset=True)  # the library counts the bytes of every cudaMemcpyAsync it issues
     t_e2e = 0.0
     for _ in range(args.e2e_steps):
         eh["sold"].a[...] = sold_h0  # untimed: restore the in-place-modified host inputs
@@ -316,6 +320,7 @@ def main():
         t0 = time.perf_counter()
         run_episode(ops, st, eh)  # synchronous: H2D of inputs, kernels, D2H of outputs, stream sync
         t_e2e += time.perf_counter() - t0
+    in_bytes, out_bytes = [b // args.e2e_steps for b in lib.copy_bytes()]
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -329,7 +334,8 @@ def main():
                                    "(%d comps: %d species + rho' + %d tracer), ng_s=4, periodic" % (n, ncomp, p.nspec,
                                                                                                   p.ntrac),
                        "zones_per_gpu": n ** 3, "components": ncomp, "l2": "256 MB flush between timed iterations",
-                       "multi_gpu": "one independent periodic box per rank" if world > 1 else "single box"},
+                       "multi_gpu": ("periodic %d x %d x %d domain, one %d^3 slab per rank, NCCL send/recv halo exchange "
+                                     "in every ghost fill (timed)" % (n, n, n * world, n)) if world > 1 else "single box"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "steps": args.e2e_steps, "check_sum_rho_new": snew_sum},

@@ -96,6 +96,10 @@ typedef struct {
   double dx[3];
   double rel_eps;            /* variables.f90:17, set in estdt.f90:231 */
   double base_cutoff_density;
+  /* used by the force builders of the L4 episodes (mkscalforce.f90 / mkforce.f90) */
+  int base_cutoff_density_coord;  /* geometry: first r index with rho0 <= base_cutoff_density */
+  double buoyancy_cutoff_factor;  /* _parameters */
+  double omega, sin_theta, cos_theta, rotation_radius; /* geometry / probin: plane-parallel rotation */
 } mgpu_params;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
@@ -116,6 +120,8 @@ int mgpu_set_option(const char* key, int value);
  *       8 fused edge+flux+update 9 velpred 10 bds 11 halo */
 int mgpu_profile(int on);
 int mgpu_profile_get(int tag, double* ms, long* launches);
+/* bytes moved host->device / device->host by host-pointer calls since the last reset (bench e2e accounting) */
+int mgpu_copy_bytes(long* h2d, long* d2h, int reset);
 /* raw cudaStream_t used for all launches (for CUDA-event timing by the caller) */
 void* mgpu_stream(void);
 /* run on a caller-owned stream instead (e.g. the framework's current stream) */
@@ -228,6 +234,45 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
                          mgpu_fab* const* umac, const double* w0, mgpu_fab* etarhoflux,
                          const double* rho0_old, const double* rho0_new, const double* p0_dummy,
                          const double* rho0_predicted_edge, const int* adv_bc, const int* pmask);
+
+/* ---- force builders inside the L4 drivers ----------------------------------------
+ * mkrhohforce (Source/mkscalforce.f90:31; _2d :249, _3d :310), planar: writes comp rhoh_comp of scal_force on the
+ * valid cells (the caller follows with mgpu_fill_boundary, mkscalforce.f90:177).  grav is the 1-D array
+ * make_grav_cell gives for rho0 = (rho0_1+rho0_2)/2 (host base-state work, stays with the Fortran). */
+int mgpu_mkrhohforce(const mgpu_params* p, int nfabs, mgpu_fab* scal_force, int is_prediction,
+                     const mgpu_fab* thermal, const mgpu_fab* const* umac, const double* p0_1, const double* p0_2,
+                     const double* rho0_1, const double* rho0_2, const double* grav, const double* psi,
+                     int add_thermal);
+/* mk_vel_force (Source/mkforce.f90:22; _2d :283, _3d_cart :342), planar: all dm comps of vel_force (zeroed incl.
+ * ghosts, then valid cells); rho = comp index_rho (1-based) of s; the caller follows with mgpu_fill_boundary. */
+int mgpu_mk_vel_force(const mgpu_params* p, int nfabs, mgpu_fab* vel_force, int is_final_update,
+                      const mgpu_fab* uold, const mgpu_fab* const* uedge, const double* w0, const mgpu_fab* gpi,
+                      const mgpu_fab* s, int index_rho, const double* rho0, const double* grav,
+                      const double* w0_force, int do_add_utilde_force);
+
+/* ---- L4 episodes, planar, one level, one box (slab) per rank; signatures mirror the Fortran argument lists
+ * (multifab -> mgpu_fab, base-state (n,0:nr) arrays -> the level's 1-D slice).  Temporaries the reference
+ * builds and destroys inside the driver (ufull, utrans, force, uedge) are device-only.
+ * advance_premac (Source/advance_premac.f90:21): umac valid faces are written (no ghost fill, as the reference). */
+int mgpu_advance_premac(const mgpu_params* p, const mgpu_fab* uold, const mgpu_fab* sold, mgpu_fab* const* umac,
+                        const mgpu_fab* gpi, const double* w0, const double* w0_force, const double* rho0_old,
+                        const double* grav_cell_old, const int* adv_bc, const int* phys_bc, const int* pmask);
+/* velocity_advance (Source/velocity_advance.f90:16): unew valid + ghost cells; umac is (umac+w0)-w0 on return. */
+int mgpu_velocity_advance(const mgpu_params* p, const mgpu_fab* uold, mgpu_fab* unew, const mgpu_fab* sold,
+                          const mgpu_fab* rhohalf, mgpu_fab* const* umac, const mgpu_fab* gpi, const double* w0,
+                          const double* w0_force, const double* rho0_old, const double* rho0_nph,
+                          const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
+                          const int* adv_bc, const int* pmask);
+/* enthalpy_advance (Source/enthalpy_advance.f90:16), enthalpy_pred_type in {predict_rhoh, predict_rhohprime,
+ * predict_h} (the temperature-based types need the EOS).  grav_old / grav_nph: make_grav_cell of
+ * rho0_old / (rho0_old+rho0_new)/2.  sedge(rho_comp) must hold the density edge states left by density_advance
+ * (mkflux.f90:1126).  EOS-below-cutoff zones of update_scal (:421-447) are left to the caller. */
+int mgpu_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgpu_fab* snew,
+                          mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
+                          const mgpu_fab* thermal, mgpu_fab* const* umac, const double* w0, const double* rho0_old,
+                          const double* rhoh0_old, const double* rho0_new, const double* rhoh0_new,
+                          const double* p0_old, const double* p0_new, const double* psi, const double* grav_old,
+                          const double* grav_nph, const int* adv_bc, const int* pmask);
 
 #ifdef __cplusplus
 }

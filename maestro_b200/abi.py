@@ -59,6 +59,12 @@ class mgpu_params(C.Structure):
         ("dx", C.c_double * 3),
         ("rel_eps", C.c_double),
         ("base_cutoff_density", C.c_double),
+        ("base_cutoff_density_coord", C.c_int),
+        ("buoyancy_cutoff_factor", C.c_double),
+        ("omega", C.c_double),
+        ("sin_theta", C.c_double),
+        ("cos_theta", C.c_double),
+        ("rotation_radius", C.c_double),
     ]
 
 
@@ -95,6 +101,12 @@ OPERATORS = {
     "modify_scal_force": (C.c_int, [P_, C.c_int, F_, F_, FF_] + [c_double_p] * 3 + [C.c_int] * 2),
     "convert_rhoX_to_X": (C.c_int, [P_, C.c_int, F_, C.c_int]),
     "put_in_pert_form": (C.c_int, [P_, C.c_int, F_, c_double_p, C.c_int, C.c_int]),
+    "mkrhohforce": (C.c_int, [P_, C.c_int, F_, C.c_int, F_, FF_] + [c_double_p] * 6 + [C.c_int]),
+    "mk_vel_force": (C.c_int, [P_, C.c_int, F_, C.c_int, F_, FF_, c_double_p, F_, F_, C.c_int] + [c_double_p] * 3
+                     + [C.c_int]),
+    "advance_premac": (C.c_int, [P_, F_, F_, FF_, F_] + [c_double_p] * 4 + [c_int_p] * 3),
+    "velocity_advance": (C.c_int, [P_, F_, F_, F_, F_, FF_, F_] + [c_double_p] * 6 + [F_] + [c_int_p] * 2),
+    "enthalpy_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_] + [c_double_p] * 10 + [c_int_p] * 2),
     "density_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, FF_, c_double_p, F_] + [c_double_p] * 4
                         + [c_int_p] * 2),
 }
@@ -108,6 +120,7 @@ LIFECYCLE = {
     "mgpu_version": (C.c_char_p, []),
     "mgpu_launch_count": (C.c_long, [C.c_int]),
     "mgpu_stream": (C.c_void_p, []),
+    "mgpu_copy_bytes": (C.c_int, [C.POINTER(C.c_long), C.POINTER(C.c_long), C.c_int]),
     "mgpu_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "mgpu_profile": (C.c_int, [C.c_int]),
     "mgpu_profile_get": (C.c_int, [C.c_int, c_double_p, C.POINTER(C.c_long)]),

@@ -127,10 +127,20 @@ struct Pool {
 static Pool g_pool;
 
 // One entry-point invocation: maps fabs to device views, copies in/out for host-pointer calls.
+// Copies are per component (bit c of the masks = component c): an L4 episode moves only the components it reads
+// across PCIe on the way in and only those it writes on the way out.
+static long g_h2d_bytes = 0, g_d2h_bytes = 0;  // PCIe traffic of host-pointer calls (bench e2e accounting)
+typedef unsigned long long cmask_t;
+static const cmask_t ALLC = ~0ull;
+static inline cmask_t crange(int c0, int nc) {  // components c0 .. c0+nc-1 (0-based)
+  cmask_t m = 0;
+  for (int c = c0; c < c0 + nc; ++c) m |= (1ull << c);
+  return m;
+}
 struct Call {
   const mgpu_params& P;
   bool host;
-  struct Item { double* h; double* d; size_t n; bool out; };
+  struct Item { double* h; double* d; size_t cs; int nc; cmask_t out; cmask_t zero; };
   std::vector<Item> items;
   explicit Call(const mgpu_params* p, size_t scratch_bytes) : P(*p), host(p->mem_space == MGPU_HOST) {
     require_init();
@@ -141,28 +151,60 @@ struct Call {
   ~Call() {
     for (auto& it : items) g_pool.put(it.d);
   }
-  DV view(const mgpu_fab& f, bool copy_in, bool copy_out) {
+  // runs of set bits of m (restricted to nc components) -> one cudaMemcpyAsync each
+  template <class F>
+  static void for_runs(cmask_t m, int nc, F f) {
+    int c = 0;
+    while (c < nc) {
+      if (!((m >> c) & 1ull)) { ++c; continue; }
+      int c1 = c;
+      while (c1 < nc && ((m >> c1) & 1ull)) ++c1;
+      f(c, c1 - c);
+      c = c1;
+    }
+  }
+  DV view(const mgpu_fab& f, cmask_t in, cmask_t out) {
     if (!f.ptr) throw Error("mgpu: null fab pointer");
     if (!host) return make_view(f, P.dm);
+    if (f.nc > 64) in = out = (in || out) ? ALLC : 0;
     for (auto& it : items)  // the same host fab passed twice maps to one device buffer
       if (it.h == f.ptr) {
-        it.out = it.out || copy_out;
+        it.out |= out;
         return make_view(f, P.dm, it.d);
       }
     DV v = make_view(f, P.dm);
-    size_t n = (size_t)v.size();
-    double* d = g_pool.get(n);
-    if (copy_in) MGPU_CUDA(cudaMemcpyAsync(d, f.ptr, n * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
-    items.push_back({f.ptr, d, n, copy_out});
+    double* d = g_pool.get((size_t)v.size());
+    for_runs(in, f.nc, [&](int c0, int n) {
+      MGPU_CUDA(cudaMemcpyAsync(d + v.cs * c0, f.ptr + v.cs * c0, (size_t)v.cs * n * sizeof(double),
+                                cudaMemcpyHostToDevice, g_ctx.stream));
+      g_h2d_bytes += (long)v.cs * n * (long)sizeof(double);
+    });
+    items.push_back({f.ptr, d, (size_t)v.cs, f.nc, out, (cmask_t)0});
     return make_view(f, P.dm, d);
   }
+  DV view(const mgpu_fab& f, bool copy_in, bool copy_out) { return view(f, copy_in ? ALLC : 0, copy_out ? ALLC : 0); }
+  // the caller-visible result of this fab is all zeros (setval(...,ZERO,all=.true.) was the last thing the
+  // reference did to it): produce it on the host instead of copying zeros back over PCIe
+  void zero_on_host(const mgpu_fab& f, cmask_t comps = ALLC) {
+    for (auto& it : items)
+      if (it.h == f.ptr) { it.out &= ~comps; it.zero |= comps; }
+  }
   void views(const mgpu_fab* const* f, int i, bool in, bool out, DV* v) {
+    for (int d = 0; d < P.dm; ++d) v[d] = view(f[d][i], in, out);
+  }
+  void views(const mgpu_fab* const* f, int i, cmask_t in, cmask_t out, DV* v) {
     for (int d = 0; d < P.dm; ++d) v[d] = view(f[d][i], in, out);
   }
   void finish() {
     if (!host) return;
     for (auto& it : items)
-      if (it.out) MGPU_CUDA(cudaMemcpyAsync(it.h, it.d, it.n * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+      for_runs(it.out, it.nc, [&](int c0, int n) {
+        MGPU_CUDA(cudaMemcpyAsync(it.h + it.cs * c0, it.d + it.cs * c0, it.cs * n * sizeof(double),
+                                  cudaMemcpyDeviceToHost, g_ctx.stream));
+        g_d2h_bytes += (long)(it.cs * n * sizeof(double));
+      });
+    for (auto& it : items)  // overlaps the asynchronous device-to-host copies
+      for_runs(it.zero, it.nc, [&](int c0, int n) { memset(it.h + it.cs * c0, 0, it.cs * n * sizeof(double)); });
     MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
   }
 };
@@ -309,7 +351,7 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
   if (g_opt_fused) {
     // :280-366 in one launch: species + tracer fluxes, etarhoflux, update, density, floors
-    flux_update_all_dev(P, fa, ua);
+    flux_update_all_dev(P, fa, ua, g_opt_exact != 0);
     fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
     fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
     if (P.ntrac >= 1)
@@ -325,6 +367,232 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
     update_scal_dev(P, ua, P.trac_comp, P.trac_comp + P.ntrac - 1);
     fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.trac_comp, dm + P.trac_comp, P.ntrac, adv_bc, pmask, false);
   }
+}
+
+
+// ---- shared pieces of the other L4 episodes ---------------------------------------------------------
+static const int NODAL_D[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+static void fill_faces_dev(const mgpu_params& P, DV* u, const int* lo, const int* hi, const int* adv_bc,
+                           const int* pmask) {  // addw0.f90:85-93 / mkutrans.f90:105-115
+  for (int d = 0; d < P.dm; ++d) fill_boundary_dev(P, u[d], lo, hi, 1, NODAL_D[d], 1, 1, 1, adv_bc, pmask, false);
+}
+static DV arena_fab(const int* lo, const int* hi, int dm, int ng, const int* nodal, int nc) {
+  DV v = make_view(nullptr, lo, hi, dm, ng, nodal, nc);
+  v.p = arena_alloc((size_t)v.size());
+  return v;
+}
+static size_t fab_bytes(const int* lo, const int* hi, int dm, int ng, int nodal_dirs, int nc) {
+  size_t n = 1;
+  for (int d = 0; d < dm; ++d) n *= (size_t)(hi[d] - lo[d] + 1 + 2 * ng + (nodal_dirs ? 1 : 0));
+  return n * nc * sizeof(double) + 256;
+}
+static void vel_force_dev(const mgpu_params& P, DV& force, bool is_final, const DV& uold, const DV* uedge,
+                          const double* w0, const DV& gpi, const DV& rho1, const double* rho0, const double* grav,
+                          const double* w0_force, const int* lo, const int* hi, int ng_f, const int* adv_bc,
+                          const int* pmask) {
+  VelForceArgs a;
+  a.dm = P.dm;
+  a.nr = P.nr;
+  a.is_final_update = is_final;
+  a.add_utilde = true;
+  a.dr = P.dx[P.dm - 1];
+  a.rho_cut = P.buoyancy_cutoff_factor * P.base_cutoff_density;
+  a.omega = P.omega; a.sin_theta = P.sin_theta; a.cos_theta = P.cos_theta; a.rotation_radius = P.rotation_radius;
+  a.vb = grown(lo, hi, P.dm, 0);
+  a.force = force; a.uold = uold; a.gpi = gpi; a.rho = rho1;
+  for (int d = 0; d < P.dm; ++d) a.uedge[d] = uedge[d];
+  a.w0 = w0; a.rho0 = rho0; a.grav = grav; a.w0_force = w0_force;
+  mk_vel_force_dev(a);
+  fill_boundary_dev(P, force, lo, hi, ng_f, nullptr, 1, 1, P.dm, adv_bc, pmask, false);  // mkforce.f90:209
+}
+
+// advance_premac (Source/advance_premac.f90:21)
+static size_t advance_premac_scratch(const mgpu_params& P, const int* lo, const int* hi, int ng_u) {
+  const int ng_f = P.ppm_trace_forces == 1 ? ng_u : 1;
+  return fab_bytes(lo, hi, P.dm, ng_u, 0, P.dm) + fab_bytes(lo, hi, P.dm, ng_f, 0, P.dm) +
+         P.dm * fab_bytes(lo, hi, P.dm, 1, 1, 1) + velpred_scratch(P, lo, hi) + (size_t)(6 * (P.nr + 2)) * sizeof(double) +
+         8192;
+}
+static void advance_premac_dev(const mgpu_params& P, const DV& uold, const DV& sold, DV* umac, const DV& gpi,
+                               const double* w0_h, const double* w0_force_h, const double* rho0_old_h,
+                               const double* grav_h, const int* lo, const int* hi, int ng_u, const int* adv_bc,
+                               const int* phys_bc, const int* pmask) {
+  const int dm = P.dm, nr = P.nr;
+  const int ng_f = P.ppm_trace_forces == 1 ? ng_u : 1;  // advance_premac.f90:62-66
+  const double* w0 = upload_small(w0_h, nr + 1);
+  const double* w0_force = upload_small(w0_force_h, nr);
+  const double* rho0_old = upload_small(rho0_old_h, nr);
+  const double* grav = upload_small(grav_h, nr);
+  int z3[3] = {0, 0, 0};
+  DV ufull = arena_fab(lo, hi, dm, ng_u, z3, dm), force = arena_fab(lo, hi, dm, ng_f, z3, dm);
+  DV utrans[3];
+  for (int d = 0; d < dm; ++d) utrans[d] = arena_fab(lo, hi, dm, 1, NODAL_D[d], 1);
+  radial_cell_avg_dev(P, ufull, w0, lo, hi);  // :75 put_1d_array_on_cart(w0, ufull, 1, .true., .true.)
+  fill_boundary_dev(P, ufull, lo, hi, ng_u, nullptr, 1, 1, dm, adv_bc, pmask, false);
+  if (ufull.size() != uold.size()) throw Error("advance_premac: internal size mismatch");
+  add_dev(ufull.p, uold.p, ufull.size());  // :76-78
+  mkutrans_dev(P, uold, ufull, utrans, w0, lo, hi, adv_bc, phys_bc, ng_u);  // :90
+  fill_faces_dev(P, utrans, lo, hi, adv_bc, pmask);
+  vel_force_dev(P, force, false, uold, utrans, w0, gpi, sold.comp(P.rho_comp - 1), rho0_old, grav, w0_force, lo, hi, ng_f,
+                adv_bc, pmask);  // :98
+  addw0_dev(P, utrans, w0, 1.0, lo, hi);  // :109
+  fill_faces_dev(P, utrans, lo, hi, adv_bc, pmask);
+  velpred_dev(P, uold, ufull, umac, utrans, force, w0, lo, hi, adv_bc, phys_bc, ng_u, ng_f);  // :116
+}
+
+// velocity_advance (Source/velocity_advance.f90:16)
+static size_t velocity_advance_scratch(const mgpu_params& P, const int* lo, const int* hi, int ng_u) {
+  const int ng_f = P.ppm_trace_forces == 0 ? 1 : ng_u;
+  return fab_bytes(lo, hi, P.dm, ng_f, 0, P.dm) + P.dm * fab_bytes(lo, hi, P.dm, 0, 1, P.dm) +
+         std::max(make_edge_scal_scratch(P, lo, hi), bds_scratch(P, lo, hi)) + (size_t)(8 * (P.nr + 2)) * sizeof(double) +
+         8192;
+}
+static void velocity_advance_dev(const mgpu_params& P, const DV& uold, DV& unew, const DV& sold, const DV& rhohalf,
+                                 DV* umac, const DV& gpi, const double* w0_h, const double* w0_force_h,
+                                 const double* rho0_old_h, const double* rho0_nph_h, const double* grav_old_h,
+                                 const double* grav_nph_h, const DV& sponge, const int* lo, const int* hi, int ng_u,
+                                 const int* adv_bc, const int* pmask) {
+  const int dm = P.dm, nr = P.nr;
+  const int ng_f = P.ppm_trace_forces == 0 ? 1 : ng_u;  // velocity_advance.f90:69-75
+  const double* w0 = upload_small(w0_h, nr + 1);
+  const double* w0_force = upload_small(w0_force_h, nr);
+  const double* rho0_old = upload_small(rho0_old_h, nr);
+  const double* rho0_nph = upload_small(rho0_nph_h, nr);
+  const double* grav_old = upload_small(grav_old_h, nr);
+  const double* grav_nph = upload_small(grav_nph_h, nr);
+  int z3[3] = {0, 0, 0};
+  DV force = arena_fab(lo, hi, dm, ng_f, z3, dm);
+  DV uedge[3];
+  for (int d = 0; d < dm; ++d) uedge[d] = arena_fab(lo, hi, dm, 0, NODAL_D[d], dm);
+  vel_force_dev(P, force, false, uold, umac, w0, gpi, sold.comp(P.rho_comp - 1), rho0_old, grav_old, w0_force, lo, hi,
+                ng_f, adv_bc, pmask);  // :80
+  addw0_dev(P, umac, w0, 1.0, lo, hi);  // :90
+  fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
+  for (int c = 0; c < dm; ++c) {  // :102-109: is_vel, comps 1..dm, bc comps 1..dm, advective form
+    size_t mark = arena_mark();
+    if (P.bds_type != 0) bds_dev(P, uold, uedge, umac, force, lo, hi, c, false, ng_u, ng_f);
+    else edge_one_comp(P, uold, uedge, umac, force, lo, hi, adv_bc, c, 1 + c, true, false, ng_u, ng_f);
+    arena_release(mark);
+  }
+  addw0_dev(P, umac, w0, -1.0, lo, hi);  // :115
+  fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
+  vel_force_dev(P, force, true, uold, umac, w0, gpi, rhohalf.comp(0), rho0_nph, grav_nph, w0_force, lo, hi, ng_f, adv_bc,
+                pmask);  // :122
+  VelArgs a;
+  a.dm = dm;
+  a.do_sponge = P.do_sponge != 0;
+  a.dt = P.dt;
+  for (int d = 0; d < 3; ++d) a.dx[d] = P.dx[d];
+  a.vb = grown(lo, hi, dm, 0);
+  a.uold = uold; a.unew = unew; a.force = force; a.sponge = sponge;
+  for (int d = 0; d < dm; ++d) { a.umac[d] = umac[d]; a.uedge[d] = uedge[d]; }
+  a.w0 = w0;
+  update_velocity_dev(a);  // :132
+  fill_boundary_dev(P, unew, lo, hi, ng_u, nullptr, 1, 1, dm, adv_bc, pmask, false);  // update_vel.f90:121
+}
+
+// enthalpy_advance (Source/enthalpy_advance.f90:16)
+static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold, DV& snew, DV* sedge, DV* sflux,
+                                 DV& scal_force, const DV& thermal, DV* umac, const double* w0_h,
+                                 const double* rho0_old_h, const double* rhoh0_old_h, const double* rho0_new_h,
+                                 const double* rhoh0_new_h, const double* p0_old_h, const double* p0_new_h,
+                                 const double* psi_h, const double* grav_old_h, const double* grav_nph_h, const int* lo,
+                                 const int* hi, int ng_s, int ng_f, const int* adv_bc, const int* pmask) {
+  const int dm = P.dm, nr = P.nr;
+  const int ept = P.enthalpy_pred_type;
+  const int foextrap_comp = dm + P.nscal + 2;
+  if (ept == MGPU_PREDICT_HPRIME) throw Error("mk_rhoh_flux : predict_hprime not coded yet");  // mkflux.f90:1167
+  if (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H)
+    throw Error("enthalpy_advance: temperature-based prediction needs the EOS (makeHfromRhoT_edge): not on the device");
+  std::vector<double> e[4] = {std::vector<double>(nr + 1), std::vector<double>(nr + 1), std::vector<double>(nr + 1),
+                              std::vector<double>(nr + 1)};
+  cell_to_edge_host(rho0_old_h, e[0].data(), nr);  // enthalpy_advance.f90:114-117
+  cell_to_edge_host(rho0_new_h, e[1].data(), nr);
+  cell_to_edge_host(rhoh0_old_h, e[2].data(), nr);
+  cell_to_edge_host(rhoh0_new_h, e[3].data(), nr);
+  const double* w0 = upload_small(w0_h, nr + 1);
+  const double* rho0_old = upload_small(rho0_old_h, nr);
+  const double* rho0_new = upload_small(rho0_new_h, nr);
+  const double* rhoh0_old = upload_small(rhoh0_old_h, nr);
+  const double* rhoh0_new = upload_small(rhoh0_new_h, nr);
+  const double* p0_old = upload_small(p0_old_h, nr);
+  const double* p0_new = upload_small(p0_new_h, nr);
+  const double* psi = upload_small(psi_h, nr);
+  const double* grav_old = upload_small(grav_old_h, nr);
+  const double* grav_nph = upload_small(grav_nph_h, nr);
+  const double* r0e_old = upload_small(e[0].data(), nr + 1);
+  const double* r0e_new = upload_small(e[1].data(), nr + 1);
+  const double* rh0e_old = upload_small(e[2].data(), nr + 1);
+  const double* rh0e_new = upload_small(e[3].data(), nr + 1);
+  const int rhoh = P.rhoh_comp - 1, rho = P.rho_comp - 1;
+  auto rhoh_force = [&](bool is_pred, const double* p02, const double* r02, const double* grav, bool add_thermal) {
+    if (is_pred && !(ept == MGPU_PREDICT_RHOHPRIME || ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_RHOH))
+      throw Error("ERROR: should only call mkrhohforce when predicting rhoh', h, or rhoh");
+    RhohForceArgs a;
+    a.dm = dm; a.nr = nr; a.cutoff_coord = P.base_cutoff_density_coord;
+    a.with_psi = (is_pred && (ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_RHOH)) || !is_pred;
+    a.add_thermal = add_thermal;
+    a.dr = P.dx[dm - 1];
+    a.vb = grown(lo, hi, dm, 0);
+    a.f = scal_force.comp(rhoh); a.thermal = thermal; a.wm = umac[dm - 1];
+    a.p0_1 = p0_old; a.p0_2 = p02; a.rho0_1 = rho0_old; a.rho0_2 = r02; a.grav = grav; a.psi = psi;
+    mkrhohforce_dev(a);
+    fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask, false);
+  };
+  auto rhoh_to_h = [&](bool flag) {  // convert_rhoh_to_h
+    comp_muldiv_dev(P, sold, rhoh, sold, rho, flag ? 0 : 1, 0, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc,
+                      pmask, false);
+  };
+  auto pert = [&](bool flag) {
+    put_in_pert_form_dev(P, sold, rhoh0_old, P.rhoh_comp, flag, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc,
+                      pmask, false);
+  };
+  if (ept == MGPU_PREDICT_H) rhoh_to_h(true);  // :122-126
+  set_dev(scal_force.p, 0.0, scal_force.size());  // :132-134
+  rhoh_force(true, p0_old, rho0_old, grav_old, true);
+  if (ept == MGPU_PREDICT_RHOHPRIME) {  // :153-156
+    modify_scal_force_dev(P, scal_force, sold, umac, rhoh0_old, rh0e_old, w0, P.rhoh_comp, false, lo, hi);
+    fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask, false);
+  } else if (ept == MGPU_PREDICT_H) {  // :173-178
+    comp_muldiv_dev(P, scal_force, rhoh, sold, rho, 0, 1, lo, hi);
+  }
+  addw0_dev(P, umac, w0, 1.0, lo, hi);  // :201
+  fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
+  if (ept == MGPU_PREDICT_RHOHPRIME) pert(true);  // :204-208
+  {
+    const bool cons = (ept == MGPU_PREDICT_RHOH);  // :232-254
+    size_t mark = arena_mark();
+    if (P.bds_type != 0) bds_dev(P, sold, sedge, umac, scal_force, lo, hi, rhoh, cons, ng_s, ng_f);
+    else edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, rhoh, dm + P.rhoh_comp, false, cons, ng_s, ng_f);
+    arena_release(mark);
+  }
+  if (ept == MGPU_PREDICT_RHOHPRIME) pert(false);  // :257-261
+  if (ept == MGPU_PREDICT_H) rhoh_to_h(false);     // :272-276
+  addw0_dev(P, umac, w0, -1.0, lo, hi);             // :293
+  fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
+  const bool s1 = (which_step == 1);
+  FluxArgs fa;
+  fill_flux_args(P, fa, lo, hi);
+  for (int d = 0; d < dm; ++d) { fa.sflux[d] = sflux[d]; fa.sedge[d] = sedge[d]; fa.umac[d] = umac[d]; }
+  fa.w0 = w0;
+  fa.rho0_old = rho0_old; fa.rho0_edge_old = r0e_old;
+  fa.rho0_new = s1 ? rho0_old : rho0_new; fa.rho0_edge_new = s1 ? r0e_old : r0e_new;
+  fa.rhoh0_old = rhoh0_old; fa.rhoh0_edge_old = rh0e_old;
+  fa.rhoh0_new = s1 ? rhoh0_old : rhoh0_new; fa.rhoh0_edge_new = s1 ? rh0e_old : rh0e_new;
+  mk_rhoh_flux_dev(P, fa);  // :326 / :375
+  set_dev(scal_force.p, 0.0, scal_force.size());  // :401-403
+  rhoh_force(false, s1 ? p0_old : p0_new, s1 ? rho0_old : rho0_new, s1 ? grav_old : grav_nph, false);  // :405-416
+  UpdArgs ua;
+  ua.dm = dm;
+  ua.dt = P.dt;
+  for (int d = 0; d < 3; ++d) ua.dx[d] = P.dx[d];
+  ua.vb = grown(lo, hi, dm, 0);
+  ua.sold = sold; ua.snew = snew; ua.force = scal_force;
+  for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
+  update_scal_dev(P, ua, P.rhoh_comp, P.rhoh_comp);  // :431
+  fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rhoh_comp, dm + P.rhoh_comp, 1, adv_bc, pmask, false);
 }
 
 }  // namespace mgpu
@@ -433,6 +701,12 @@ long mgpu_launch_count(int reset) {
   return n;
 }
 void* mgpu_stream(void) { return (void*)g_ctx.stream; }
+int mgpu_copy_bytes(long* h2d, long* d2h, int reset) {
+  if (h2d) *h2d = g_h2d_bytes;
+  if (d2h) *d2h = g_d2h_bytes;
+  if (reset) g_h2d_bytes = g_d2h_bytes = 0;
+  return 0;
+}
 
 int mgpu_malloc(double** dptr, long n) {
   MGPU_TRY
@@ -760,14 +1034,149 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
   if (p->spherical) throw Error("mgpu_density_advance: spherical geometry not available on the device yet");
   Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
              (size_t)(8 * (p->nr + 2)) * sizeof(double) + 8192);
-  DV so = c.view(*sold, true, true), sn = c.view(*snew, true, true), fv = c.view(*scal_force, true, true);
+  // components the episode reads / writes (density_advance.f90:101-366): rho, the species and the tracers
+  const cmask_t adv = crange(p->rho_comp - 1, 1) | crange(p->spec_comp - 1, p->nspec) |
+                      (p->ntrac >= 1 ? crange(p->trac_comp - 1, p->ntrac) : 0);
+  const cmask_t flx = crange(p->spec_comp - 1, p->nspec) | (p->ntrac >= 1 ? crange(p->trac_comp - 1, p->ntrac) : 0);
+  const cmask_t edg = p->species_pred_type == MGPU_PREDICT_RHOX ? adv : adv;  // rho edge = sum of rhoX edges or predicted
+  // sold: rho and species are transformed in place and restored (round trips); tracers are read only
+  DV so = c.view(*sold, adv, crange(p->rho_comp - 1, 1) | crange(p->spec_comp - 1, p->nspec));
+  // snew: only the advanced components are written; their ghost corners next to physical walls keep the caller's
+  // values (multifab_physbc.f90:165-175), hence copy-in of exactly those components
+  DV sn = c.view(*snew, adv, adv);
+  DV fv = c.view(*scal_force, (cmask_t)0, (cmask_t)0);  // zeroed on entry (:101) and again before the update (:349)
   DV eta = c.view(*etarhoflux, true, true);
   DV se[3], sf[3], um[3];
-  c.views((const mgpu_fab* const*)sedge, 0, true, true, se);
-  c.views((const mgpu_fab* const*)sflux, 0, true, true, sf);
+  c.views((const mgpu_fab* const*)sedge, 0, (cmask_t)0, edg, se);  // every face of the predicted components is written
+  c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, flx, sf);
   c.views((const mgpu_fab* const*)umac, 0, true, true, um);
+  c.zero_on_host(*scal_force);
   density_advance_dev(*p, which_step, so, sn, se, sf, fv, um, w0, eta, rho0_old, rho0_new, rho0_predicted_edge,
                       sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_mkrhohforce(const mgpu_params* p, int nfabs, mgpu_fab* scal_force, int is_prediction, const mgpu_fab* thermal,
+                     const mgpu_fab* const* umac, const double* p0_1, const double* p0_2, const double* rho0_1,
+                     const double* rho0_2, const double* grav, const double* psi, int add_thermal) {
+  MGPU_TRY
+  if (p->spherical) throw Error("mgpu_mkrhohforce: spherical geometry not available on the device yet");
+  const int ept = p->enthalpy_pred_type;
+  if (is_prediction && !(ept == MGPU_PREDICT_RHOHPRIME || ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_RHOH))
+    throw Error("ERROR: should only call mkrhohforce when predicting rhoh', h, or rhoh");  // mkscalforce.f90:87-92
+  Call c(p, (size_t)(8 * (p->nr + 2)) * sizeof(double) + 8192);
+  const int nr = p->nr;
+  RhohForceArgs a;
+  a.dm = p->dm; a.nr = nr; a.cutoff_coord = p->base_cutoff_density_coord;
+  a.with_psi = (is_prediction && (ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_RHOH)) || !is_prediction;
+  a.add_thermal = add_thermal != 0;
+  a.dr = p->dx[p->dm - 1];
+  a.p0_1 = upload_small(p0_1, nr); a.p0_2 = upload_small(p0_2, nr);
+  a.rho0_1 = upload_small(rho0_1, nr); a.rho0_2 = upload_small(rho0_2, nr);
+  a.grav = upload_small(grav, nr); a.psi = upload_small(psi, nr);
+  for (int i = 0; i < nfabs; ++i) {
+    a.vb = grown(scal_force[i].lo, scal_force[i].hi, p->dm, 0);
+    const cmask_t m = crange(p->rhoh_comp - 1, 1);
+    a.f = c.view(scal_force[i], m, m).comp(p->rhoh_comp - 1);
+    a.thermal = c.view(thermal[i], true, false);
+    DV um[3];
+    c.views(umac, i, true, false, um);
+    a.wm = um[p->dm - 1];
+    mkrhohforce_dev(a);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_mk_vel_force(const mgpu_params* p, int nfabs, mgpu_fab* vel_force, int is_final_update, const mgpu_fab* uold,
+                      const mgpu_fab* const* uedge, const double* w0, const mgpu_fab* gpi, const mgpu_fab* s,
+                      int index_rho, const double* rho0, const double* grav, const double* w0_force,
+                      int do_add_utilde_force) {
+  MGPU_TRY
+  if (p->spherical) throw Error("mgpu_mk_vel_force: spherical geometry not available on the device yet");
+  Call c(p, (size_t)(6 * (p->nr + 2)) * sizeof(double) + 8192);
+  const int nr = p->nr;
+  VelForceArgs a;
+  a.dm = p->dm; a.nr = nr;
+  a.is_final_update = is_final_update != 0;
+  a.add_utilde = do_add_utilde_force != 0;
+  a.dr = p->dx[p->dm - 1];
+  a.rho_cut = p->buoyancy_cutoff_factor * p->base_cutoff_density;
+  a.omega = p->omega; a.sin_theta = p->sin_theta; a.cos_theta = p->cos_theta; a.rotation_radius = p->rotation_radius;
+  a.w0 = upload_small(w0, nr + 1); a.rho0 = upload_small(rho0, nr);
+  a.grav = upload_small(grav, nr); a.w0_force = upload_small(w0_force, nr);
+  for (int i = 0; i < nfabs; ++i) {
+    a.vb = grown(vel_force[i].lo, vel_force[i].hi, p->dm, 0);
+    a.force = c.view(vel_force[i], false, true);
+    a.uold = c.view(uold[i], true, false);
+    a.gpi = c.view(gpi[i], true, false);
+    const cmask_t m = crange(index_rho - 1, 1);
+    a.rho = c.view(s[i], m, (cmask_t)0).comp(index_rho - 1);
+    c.views(uedge, i, true, false, a.uedge);
+    mk_vel_force_dev(a);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_advance_premac(const mgpu_params* p, const mgpu_fab* uold, const mgpu_fab* sold, mgpu_fab* const* umac,
+                        const mgpu_fab* gpi, const double* w0, const double* w0_force, const double* rho0_old,
+                        const double* grav_cell_old, const int* adv_bc, const int* phys_bc, const int* pmask) {
+  MGPU_TRY
+  if (p->spherical) throw Error("mgpu_advance_premac: spherical geometry not available on the device yet");
+  Call c(p, advance_premac_scratch(*p, uold->lo, uold->hi, uold->ng));
+  DV uo = c.view(*uold, true, false), gp = c.view(*gpi, true, false);
+  DV so = c.view(*sold, crange(p->rho_comp - 1, 1), (cmask_t)0);
+  DV um[3];
+  c.views((const mgpu_fab* const*)umac, 0, true, true, um);  // ghost faces keep the caller's values
+  advance_premac_dev(*p, uo, so, um, gp, w0, w0_force, rho0_old, grav_cell_old, uold->lo, uold->hi, uold->ng, adv_bc,
+                     phys_bc, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_velocity_advance(const mgpu_params* p, const mgpu_fab* uold, mgpu_fab* unew, const mgpu_fab* sold,
+                          const mgpu_fab* rhohalf, mgpu_fab* const* umac, const mgpu_fab* gpi, const double* w0,
+                          const double* w0_force, const double* rho0_old, const double* rho0_nph,
+                          const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
+                          const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  if (p->spherical) throw Error("mgpu_velocity_advance: spherical geometry not available on the device yet");
+  Call c(p, velocity_advance_scratch(*p, uold->lo, uold->hi, uold->ng));
+  DV uo = c.view(*uold, true, false), un = c.view(*unew, true, true), gp = c.view(*gpi, true, false);
+  DV so = c.view(*sold, crange(p->rho_comp - 1, 1), (cmask_t)0), rh = c.view(*rhohalf, true, false);
+  DV sp = c.view(*sponge, true, false);
+  DV um[3];
+  c.views((const mgpu_fab* const*)umac, 0, true, true, um);
+  velocity_advance_dev(*p, uo, un, so, rh, um, gp, w0, w0_force, rho0_old, rho0_nph, grav_cell_old, grav_cell_nph, sp,
+                       uold->lo, uold->hi, uold->ng, adv_bc, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgpu_fab* snew, mgpu_fab* const* sedge,
+                          mgpu_fab* const* sflux, mgpu_fab* scal_force, const mgpu_fab* thermal, mgpu_fab* const* umac,
+                          const double* w0, const double* rho0_old, const double* rhoh0_old, const double* rho0_new,
+                          const double* rhoh0_new, const double* p0_old, const double* p0_new, const double* psi,
+                          const double* grav_old, const double* grav_nph, const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  if (p->spherical) throw Error("mgpu_enthalpy_advance: spherical geometry not available on the device yet");
+  Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
+                (size_t)(16 * (p->nr + 2)) * sizeof(double) + 16384);
+  // the episode reads rho and rhoh of sold (rhoh is transformed in place and restored), writes rhoh of snew, of the
+  // edge states and of the fluxes, and reads the density edge states density_advance left in sedge(rho_comp)
+  const cmask_t mrho = crange(p->rho_comp - 1, 1), mrhoh = crange(p->rhoh_comp - 1, 1);
+  DV so = c.view(*sold, mrho | mrhoh, mrhoh), sn = c.view(*snew, mrhoh, mrhoh);
+  DV fv = c.view(*scal_force, (cmask_t)0, mrhoh);  // zeroed on entry; only the rhoh component is non-zero on return
+  c.zero_on_host(*scal_force, ~mrhoh);
+  DV th = c.view(*thermal, true, false);
+  DV se[3], sf[3], um[3];
+  c.views((const mgpu_fab* const*)sedge, 0, mrho, mrhoh, se);
+  c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, mrhoh, sf);
+  c.views((const mgpu_fab* const*)umac, 0, true, true, um);
+  enthalpy_advance_dev(*p, which_step, so, sn, se, sf, fv, th, um, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old,
+                       p0_new, psi, grav_old, grav_nph, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
   c.finish();
   MGPU_CATCH
 }

@@ -29,7 +29,7 @@ struct BdsArgs {
 
 __global__ void k_bds_sint(BdsArgs a) {
   int ix[3];
-  if (!decode(a.nb, MGPU_TID, ix)) return;
+  if (!decode3(a.nb, ix)) return;
   const double* q = a.s.p + a.s.off(ix[0], ix[1], ix[2]);
   const long sy = a.s.stride(1), sz = a.s.stride(2);
   if (a.dm == 2) {
@@ -90,7 +90,7 @@ __device__ __forceinline__ void bds_pass(double* sc, const double* smin, const d
 
 __global__ void k_bds_slope(BdsArgs a) {
   int ix[3];
-  if (!decode(a.tb, MGPU_TID, ix)) return;
+  if (!decode3(a.tb, ix)) return;
   const double* q = a.s.p + a.s.off(ix[0], ix[1], ix[2]);
   const long sy = a.s.stride(1), sz = a.s.stride(2);
   const double* nq = a.sint.p + a.sint.off(ix[0], ix[1], ix[2]);
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) k_bds_conc(BdsArgs a) {
   int ix[3];
   Box3 fb = a.vb;
   fb.hi[D] += 1;
-  if (!decode(fb, MGPU_TID, ix)) return;
+  if (!decode3(fb, ix)) return;
   const double dt = a.dt;
   const double dt2 = dt / 2.0, dt3 = dt / 3.0, dt4 = dt / 4.0;
   const double half = 0.5, sixth = 1.0 / 6.0;
@@ -362,19 +362,20 @@ void bds_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* u
   const int nsl = dm == 2 ? 3 : 7;
   a.slope = make_view(arena_alloc((size_t)a.tb.npts() * nsl), a.tb.lo, a.tb.hi, dm, 0, z3, nsl);
   cudaStream_t st = ctx().stream;
-  MGPU_TIMED(TAG_BDS, (k_bds_sint<<<nblocks(a.nb.npts(), 256), 256, 0, st>>>(a)));
-  MGPU_TIMED(TAG_BDS, (k_bds_slope<<<nblocks(a.tb.npts(), 128), 128, 0, st>>>(a)));
+  MGPU_TIMED(TAG_BDS, (k_bds_sint<<<grid3(a.nb, 256), block3(a.nb, 256), 0, st>>>(a)));
+  MGPU_TIMED(TAG_BDS, (k_bds_slope<<<grid3(a.tb, 128), block3(a.tb, 128), 0, st>>>(a)));
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    const unsigned nb = nblocks(fb.npts(), 128);
+    const dim3 nb = grid3(fb, 128);
+    const int bt = block3(fb, 128);
     if (dm == 2) {
-      if (d == 0) MGPU_TIMED(TAG_BDS, (k_bds_conc<2, 0><<<nb, 128, 0, st>>>(a)));
-      else MGPU_TIMED(TAG_BDS, (k_bds_conc<2, 1><<<nb, 128, 0, st>>>(a)));
+      if (d == 0) MGPU_TIMED(TAG_BDS, (k_bds_conc<2, 0><<<nb, bt, 0, st>>>(a)));
+      else MGPU_TIMED(TAG_BDS, (k_bds_conc<2, 1><<<nb, bt, 0, st>>>(a)));
     } else {
-      if (d == 0) MGPU_TIMED(TAG_BDS, (k_bds_conc<3, 0><<<nb, 128, 0, st>>>(a)));
-      else if (d == 1) MGPU_TIMED(TAG_BDS, (k_bds_conc<3, 1><<<nb, 128, 0, st>>>(a)));
-      else MGPU_TIMED(TAG_BDS, (k_bds_conc<3, 2><<<nb, 128, 0, st>>>(a)));
+      if (d == 0) MGPU_TIMED(TAG_BDS, (k_bds_conc<3, 0><<<nb, bt, 0, st>>>(a)));
+      else if (d == 1) MGPU_TIMED(TAG_BDS, (k_bds_conc<3, 1><<<nb, bt, 0, st>>>(a)));
+      else MGPU_TIMED(TAG_BDS, (k_bds_conc<3, 2><<<nb, bt, 0, st>>>(a)));
     }
   }
 }

@@ -151,7 +151,38 @@ __device__ __forceinline__ bool decode(const Box3& b, long t, int* ix) {
   return true;
 }
 #define MGPU_TID ((long)blockIdx.x * blockDim.x + threadIdx.x)
+// linear thread id -> (i,j,k) with 32-bit arithmetic, for thin boxes (ghost shells) where a row per block
+// would leave most lanes idle; requires npts < 2^32
+__device__ __forceinline__ bool decode32(const Box3& b, int* ix) {
+  const unsigned nx = b.hi[0] - b.lo[0] + 1, ny = b.hi[1] - b.lo[1] + 1, nz = b.hi[2] - b.lo[2] + 1;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nx * ny * nz) return false;
+  const unsigned r = t / nx;
+  ix[0] = b.lo[0] + (int)(t - r * nx);
+  const unsigned q = r / ny;
+  ix[1] = b.lo[1] + (int)(r - q * ny);
+  ix[2] = b.lo[2] + (int)q;
+  return true;
+}
+// (i,j,k) of a box from a 3-D launch (grid3/block3 below): x along the threads of a block, one (j,k) row
+// segment per block -- no integer division per thread, every warp reads/writes one contiguous x line
+__device__ __forceinline__ bool decode3(const Box3& b, int* ix) {
+  ix[0] = b.lo[0] + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  ix[1] = b.lo[1] + (int)blockIdx.y;
+  ix[2] = b.lo[2] + (int)blockIdx.z;
+  return ix[0] <= b.hi[0];
+}
 #endif
+inline int block3(const Box3& b, int bs_max) {
+  const int nx = b.hi[0] - b.lo[0] + 1;
+  int bs = 32;
+  while (bs < nx && bs < bs_max) bs *= 2;
+  return bs;
+}
+inline dim3 grid3(const Box3& b, int bs_max) {
+  const int nx = b.hi[0] - b.lo[0] + 1, bs = block3(b, bs_max);
+  return dim3((unsigned)((nx + bs - 1) / bs), (unsigned)(b.hi[1] - b.lo[1] + 1), (unsigned)(b.hi[2] - b.lo[2] + 1));
+}
 inline unsigned nblocks(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // upload a small host array (base state, BC table) into the arena; returns device pointer

@@ -55,7 +55,7 @@ __device__ __forceinline__ void lr_bc(const EdgeArgs& a, int d, int f, const dou
 // ------------------------------------------------------------------------------------------
 __global__ void k_cell_states(EdgeArgs a) {
   int ix[3];
-  if (!decode(a.tb, (long)blockIdx.x * blockDim.x + threadIdx.x, ix)) return;
+  if (!decode3(a.tb, ix)) return;
   const long so = a.s.off(ix[0], ix[1], ix[2]);
   const long to = a.Ip.off(ix[0], ix[1], ix[2]);
   for (int d = 0; d < a.dm; ++d) {
@@ -88,7 +88,7 @@ __device__ __forceinline__ void face_lr(const EdgeArgs& a, int d, const int* ix,
 
 __global__ void k_simh(EdgeArgs a) {
   int ix[3];
-  if (!decode(a.tb, (long)blockIdx.x * blockDim.x + threadIdx.x, ix)) return;
+  if (!decode3(a.tb, ix)) return;
   for (int d = 0; d < a.dm; ++d) {
     if (ix[d] < a.lo[d]) continue;  // faces lo..hi+1 in d, lo-1..hi+1 transverse
     double sl, sr;
@@ -105,7 +105,7 @@ __device__ __forceinline__ double divu_of(const EdgeArgs& a, int i, int j, int k
 
 __global__ void k_transverse(EdgeArgs a) {
   int ix[3];
-  if (!decode(a.tb, (long)blockIdx.x * blockDim.x + threadIdx.x, ix)) return;
+  if (!decode3(a.tb, ix)) return;
   const double dt3 = a.dt / 3.0, dt6 = a.dt / 6.0;
   for (int d = 0; d < 3; ++d) {
     if (ix[d] < a.lo[d]) continue;
@@ -143,7 +143,7 @@ __global__ void k_final(EdgeArgs a) {
   int ix[3];
   Box3 fb = a.vb;
   for (int d = 0; d < a.dm; ++d) fb.hi[d] += 1;
-  if (!decode(fb, (long)blockIdx.x * blockDim.x + threadIdx.x, ix)) return;
+  if (!decode3(fb, ix)) return;
   const double dt2 = 0.5 * a.dt, dt4 = a.dt / 4.0;
   for (int d = 0; d < a.dm; ++d) {
     bool ok = true;
@@ -293,12 +293,12 @@ void make_edge_scal_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, 
       for (int t = 0; t < 3; ++t)
         if (t != d) a.simht[d][t] = tmp(1);
   const int bs = 256;
-  MGPU_TIMED(TAG_EDGE_CELL, (k_cell_states<<<nblocks(nt, bs), bs, 0, c.stream>>>(a)));
-  MGPU_TIMED(TAG_EDGE_SIMH, (k_simh<<<nblocks(nt, bs), bs, 0, c.stream>>>(a)));
-  if (dm == 3) MGPU_TIMED(TAG_EDGE_TRANS, (k_transverse<<<nblocks(nt, bs), bs, 0, c.stream>>>(a)));
+  MGPU_TIMED(TAG_EDGE_CELL, (k_cell_states<<<grid3(a.tb, bs), block3(a.tb, bs), 0, c.stream>>>(a)));
+  MGPU_TIMED(TAG_EDGE_SIMH, (k_simh<<<grid3(a.tb, bs), block3(a.tb, bs), 0, c.stream>>>(a)));
+  if (dm == 3) MGPU_TIMED(TAG_EDGE_TRANS, (k_transverse<<<grid3(a.tb, bs), block3(a.tb, bs), 0, c.stream>>>(a)));
   Box3 fb = a.vb;
   for (int d = 0; d < dm; ++d) fb.hi[d] += 1;
-  MGPU_TIMED(TAG_EDGE_FINAL, (k_final<<<nblocks(fb.npts(), bs), bs, 0, c.stream>>>(a)));
+  MGPU_TIMED(TAG_EDGE_FINAL, (k_final<<<grid3(fb, bs), block3(fb, bs), 0, c.stream>>>(a)));
 }
 
 }  // namespace mgpu

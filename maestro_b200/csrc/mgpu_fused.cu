@@ -190,6 +190,16 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? 2 : 1) k_fused_edge
     sw[0] = 0.0;
   }
   double Ipz_prev = 0.0;
+  // carried z-direction van Leer slope of cell q and edge value on face q (PPM == 1 && !BC only)
+  double dz_c = 0.0, ez_c = 0.0;
+  if constexpr (PPM == 1 && !BC) {
+    // before the first shift sw[1..4] = s(q0-2 .. q0+1), q0 = kz0-1
+    const double dz_m = dsvl_of(&sw[2], 1);  // cell q0-1
+    dz_c = dsvl_of(&sw[3], 1);               // cell q0
+    double e = 0.5 * (sw[3] + sw[2]) - (1.0 / 6.0) * (dz_c - dz_m);
+    e = dmax2(e, dmin2(sw[3], sw[2]));
+    ez_c = dmin2(e, dmax2(sw[3], sw[2]));
+  }
   double slx_p = 0.0, srx_p = 0.0, sly_p = 0.0, sry_p = 0.0;  // plane q-1 face states
   double slz_q = 0.0, srz_q = 0.0;
   double f_p = 0.0;  // force(i,j,q-1)
@@ -255,7 +265,22 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? 2 : 1) k_fused_edge
       cell_states<FAST>(PPM, a.slope_order, c, SP, j, by, vq1, vq, tdy, hy, rel_eps, Ip, Im);
       sm.IPY[ty][tx] = Ip;
       sm.IMY[ty][tx] = Im;
-      cell_states<FAST>(PPM, a.slope_order, &sw[H], 1, q, bz, wq1, wq, tdz, hz, rel_eps, Ip, Im);
+      if constexpr (PPM == 1 && !BC) {
+        // z marches with the thread: the van Leer slope of cell q and the edge value on face q were computed by
+        // the previous step (as those of cell q+1 / face q+1), so each step evaluates one slope and one edge
+        // instead of four and two.  Same expressions as dsvl_of / sedge1_of => same bits.
+        const double dz_n = dsvl_of(&sw[H + 1], 1);
+        double e = 0.5 * (sw[H + 1] + sw[H]) - (1.0 / 6.0) * (dz_n - dz_c);
+        e = dmax2(e, dmin2(sw[H + 1], sw[H]));
+        e = dmin2(e, dmax2(sw[H + 1], sw[H]));
+        double smz = ez_c, spz = e;
+        cw_limit(sw[H], smz, spz);
+        ppm_trace<FAST>(sw[H], smz, spz, wq1, wq, tdz, hz, rel_eps, Ip, Im);
+        dz_c = dz_n;
+        ez_c = e;
+      } else {
+        cell_states<FAST>(PPM, a.slope_order, &sw[H], 1, q, bz, wq1, wq, tdz, hz, rel_eps, Ip, Im);
+      }
       // z-face q (between planes q-1 and q)
       slz_q = Ipz_prev;
       srz_q = Im;

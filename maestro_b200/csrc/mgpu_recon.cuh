@@ -13,8 +13,10 @@
 namespace mgpu {
 
 __device__ __forceinline__ double sign1(double x) { return copysign(1.0, x); }
-__device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a : b; }
-__device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }
+// one DMNMX each instead of DSETP + 2 FSEL.  Same values as the reference's min/max for every non-NaN input
+// (a zero may come out with the other sign, which no comparison or product downstream can tell apart)
+__device__ __forceinline__ double dmin2(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double dmax2(double a, double b) { return fmax(a, b); }
 
 // what a line needs to know about its direction
 struct LineBC {
@@ -112,7 +114,8 @@ __device__ __forceinline__ double dsvl_of(const double* q, long st) {  // ppm.f9
   double dsc = 0.5 * (q[st] - q[-st]);
   double dsl = 2.0 * (q[0] - q[-st]);
   double dsr = 2.0 * (q[st] - q[0]);
-  return (dsl * dsr > 0.0) ? sign1(dsc) * dmin2(dmin2(fabs(dsc), fabs(dsl)), fabs(dsr)) : 0.0;
+  // sign(1,dsc)*min(...) with min(...) >= 0: multiplying by +-1 is exact, so copysign gives the same bits
+  return (dsl * dsr > 0.0) ? copysign(dmin2(dmin2(fabs(dsc), fabs(dsl)), fabs(dsr)), dsc) : 0.0;
 }
 // edge value between cells f-1 and f; q points at s(f).  ppm.f90:1719-1724
 __device__ __forceinline__ double sedge1_of(const double* q, long st) {
@@ -135,14 +138,14 @@ __device__ __forceinline__ double sedge_wall(const double* qw, long st, int sg) 
   return e;
 }
 __device__ __forceinline__ void cw_limit(double sc, double& sm, double& sp) {  // ppm.f90:1742-1749
-  if ((sp - sc) * (sc - sm) <= 0.0) {
-    sp = sc;
-    sm = sc;
-  } else if (fabs(sp - sc) >= 2.0 * fabs(sm - sc)) {
-    sp = 3.0 * sc - 2.0 * sm;
-  } else if (fabs(sm - sc) >= 2.0 * fabs(sp - sc)) {
-    sm = 3.0 * sc - 2.0 * sp;
-  }
+  // the reference's if / else if / else if chain written with selects (no divergent branches): same values
+  const double dp = sp - sc, dm = sm - sc;
+  const bool flat = dp * (sc - sm) <= 0.0;
+  const bool c1 = fabs(dp) >= 2.0 * fabs(dm);
+  const bool c2 = fabs(dm) >= 2.0 * fabs(dp);
+  const double sp1 = 3.0 * sc - 2.0 * sm, sm1 = 3.0 * sc - 2.0 * sp;
+  sp = flat ? sc : (c1 ? sp1 : sp);
+  sm = flat ? sc : ((!c1 && c2) ? sm1 : sm);
 }
 __device__ __forceinline__ void ppm1_cell(const double* q, long st, int c, const LineBC& b, double& sm, double& sp) {
   if (b.wlo) {

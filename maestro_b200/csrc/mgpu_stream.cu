@@ -18,7 +18,7 @@ __global__ void k_rhoX_flux(FluxArgs a, int d, int c) {
   int ix[3];
   Box3 fb = a.vb;
   fb.hi[d] += 1;
-  if (!decode(fb, MGPU_TID, ix)) return;
+  if (!decode3(fb, ix)) return;
   const int r = a.dm - 1;
   const int ir = ix[r];
   double rho0_edge, vel = a.umac[d](ix[0], ix[1], ix[2]);
@@ -52,7 +52,7 @@ void mk_rhoX_flux_dev(const mgpu_params& P, FluxArgs& a, int startcomp, int endc
     for (int d = 0; d < P.dm; ++d) {
       Box3 fb = a.vb;
       fb.hi[d] += 1;
-      k_rhoX_flux<<<nblocks(fb.npts(), 256), 256, 0, cx.stream>>>(a, d, comp - 1);
+      k_rhoX_flux<<<grid3(fb, 256), block3(fb, 256), 0, cx.stream>>>(a, d, comp - 1);
       MGPU_LAUNCH_CHECK();
     }
 }
@@ -61,7 +61,7 @@ __global__ void k_rhoh_flux(FluxArgs a, int d, int mode) {
   int ix[3];
   Box3 fb = a.vb;
   fb.hi[d] += 1;
-  if (!decode(fb, MGPU_TID, ix)) return;
+  if (!decode3(fb, ix)) return;
   const int r = a.dm - 1;
   const int ir = ix[r];
   double rho0_edge, rhoh0_edge, vel = a.umac[d](ix[0], ix[1], ix[2]);
@@ -99,7 +99,7 @@ void mk_rhoh_flux_dev(const mgpu_params& P, FluxArgs& a) {
   for (int d = 0; d < P.dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    k_rhoh_flux<<<nblocks(fb.npts(), 256), 256, 0, cx.stream>>>(a, d, mode);
+    k_rhoh_flux<<<grid3(fb, 256), block3(fb, 256), 0, cx.stream>>>(a, d, mode);
     MGPU_LAUNCH_CHECK();
   }
 }
@@ -107,7 +107,7 @@ void mk_rhoh_flux_dev(const mgpu_params& P, FluxArgs& a) {
 // ------------------------------------------------------------------------------------------
 __global__ void k_update_scal(UpdArgs a, int c) {
   int ix[3];
-  if (!decode(a.vb, MGPU_TID, ix)) return;
+  if (!decode3(a.vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
   double divterm = (a.sflux[0](i + 1, j, k, c) - a.sflux[0](i, j, k, c)) / a.dx[0] +
                    (a.sflux[1](i, j + 1, k, c) - a.sflux[1](i, j, k, c)) / a.dx[1];
@@ -127,7 +127,7 @@ __global__ void k_set(double* dst, double v, long n) {
 // density from the species updates + floor + negative-species redistribution, update_scal.f90:453-505
 __global__ void k_update_rho(UpdArgs a, int c0, int c1, int rho, double bcd) {
   int ix[3];
-  if (!decode(a.vb, MGPU_TID, ix)) return;
+  if (!decode3(a.vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
   const long on = a.snew.off(i, j, k), oo = a.sold.off(i, j, k);
   double* sn = a.snew.p + on;
@@ -166,7 +166,7 @@ void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop) {
   Context& cx = ctx();
   const long nv = a.vb.npts();
   for (int comp = nstart; comp <= nstop; ++comp) {
-    k_update_scal<<<nblocks(nv, 256), 256, 0, cx.stream>>>(a, comp - 1);
+    k_update_scal<<<grid3(a.vb, 256), block3(a.vb, 256), 0, cx.stream>>>(a, comp - 1);
     MGPU_LAUNCH_CHECK();
   }
   if (nstart == P.spec_comp && nstop == P.spec_comp + P.nspec - 1) {
@@ -175,7 +175,7 @@ void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop) {
     k_copy<<<nblocks(a.snew.cs, 256), 256, 0, cx.stream>>>(a.snew.p + a.snew.cs * rho, a.sold.p + a.sold.cs * rho,
                                                           a.snew.cs);
     MGPU_LAUNCH_CHECK();
-    k_update_rho<<<nblocks(nv, 256), 256, 0, cx.stream>>>(a, nstart - 1, nstop - 1, rho, P.base_cutoff_density);
+    k_update_rho<<<grid3(a.vb, 256), block3(a.vb, 256), 0, cx.stream>>>(a, nstart - 1, nstop - 1, rho, P.base_cutoff_density);
     MGPU_LAUNCH_CHECK();
   }
 }
@@ -205,7 +205,7 @@ void copy_dev(double* dst, const double* src, long n) {
 // ------------------------------------------------------------------------------------------
 __global__ void k_update_vel(VelArgs a) {
   int ix[3];
-  if (!decode(a.vb, MGPU_TID, ix)) return;
+  if (!decode3(a.vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
   const int dm = a.dm, r = dm - 1;
   double bar[3];
@@ -227,14 +227,14 @@ __global__ void k_update_vel(VelArgs a) {
   }
 }
 void update_velocity_dev(VelArgs& a) {
-  k_update_vel<<<nblocks(a.vb.npts(), 256), 256, 0, ctx().stream>>>(a);
+  k_update_vel<<<grid3(a.vb, 256), block3(a.vb, 256), 0, ctx().stream>>>(a);
   MGPU_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------
 __global__ void k_addw0(DV wm, Box3 b, int r, const double* w0, double mult) {
   int ix[3];
-  if (!decode(b, MGPU_TID, ix)) return;
+  if (!decode3(b, ix)) return;
   wm(ix[0], ix[1], ix[2]) = wm(ix[0], ix[1], ix[2]) + mult * w0[ix[r]];
 }
 void addw0_dev(const mgpu_params& P, DV* umac, const double* w0_dev, double mult, const int* lo, const int* hi) {
@@ -242,7 +242,7 @@ void addw0_dev(const mgpu_params& P, DV* umac, const double* w0_dev, double mult
   Box3 b = grown(lo, hi, P.dm, 1);
   b.lo[r] = lo[r];
   b.hi[r] = hi[r] + 1;
-  k_addw0<<<nblocks(b.npts(), 256), 256, 0, ctx().stream>>>(umac[r], b, r, w0_dev, mult);
+  k_addw0<<<grid3(b, 256), block3(b, 256), 0, ctx().stream>>>(umac[r], b, r, w0_dev, mult);
   MGPU_LAUNCH_CHECK();
 }
 
@@ -250,7 +250,7 @@ __global__ void k_modify_scal_force(DV force, DV s, DV u, DV v, DV w, Box3 vb, i
                                     const double* s0_edge, const double* w0, double dx0, double dx1, double dx2,
                                     bool fullform) {
   int ix[3];
-  if (!decode(vb, MGPU_TID, ix)) return;
+  if (!decode3(vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
   const int ir = ix[dm - 1];
   double divu, divs0u, f = force(i, j, k);
@@ -282,16 +282,110 @@ void modify_scal_force_dev(const mgpu_params& P, const DV& force, const DV& s, c
                            const double* s0_edge, const double* w0, int comp, bool fullform, const int* lo,
                            const int* hi) {
   Box3 vb = grown(lo, hi, P.dm, 0);
-  k_modify_scal_force<<<nblocks(vb.npts(), 256), 256, 0, ctx().stream>>>(
+  k_modify_scal_force<<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(
       force.comp(comp - 1), s.comp(comp - 1), umac[0], umac[1], P.dm == 3 ? umac[2] : umac[1], vb, P.dm, s0, s0_edge,
       w0, P.dx[0], P.dx[1], P.dx[2], fullform);
+  MGPU_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// mkrhohforce_2d / _3d (Source/mkscalforce.f90:249, :310)
+__global__ void k_mkrhohforce(RhohForceArgs a) {
+  int ix[3];
+  if (!decode3(a.vb, ix)) return;
+  const int r = a.dm - 1, q = ix[r];
+  double gradp0;
+  if (q < a.cutoff_coord) {
+    gradp0 = (0.5 * (a.rho0_1[q] + a.rho0_2[q])) * a.grav[q];
+  } else if (q == a.nr - 1) {
+    gradp0 = (0.5 * (a.p0_1[q] + a.p0_2[q]) - 0.5 * (a.p0_1[q - 1] + a.p0_2[q - 1])) / a.dr;
+  } else {
+    gradp0 = (0.5 * (a.p0_1[q + 1] + a.p0_2[q + 1]) - 0.5 * (a.p0_1[q] + a.p0_2[q])) / a.dr;
+  }
+  const long wo = a.wm.off(ix[0], ix[1], ix[2]);
+  const double wadv = 0.5 * (a.wm.p[wo] + a.wm.p[wo + a.wm.stride(r)]);
+  double v = wadv * gradp0;
+  if (a.with_psi) v = v + a.psi[q];
+  if (a.add_thermal) v = v + a.thermal(ix[0], ix[1], ix[2]);
+  a.f(ix[0], ix[1], ix[2]) = v;
+}
+void mkrhohforce_dev(RhohForceArgs& a) {
+  MGPU_TIMED(TAG_GLUE, (k_mkrhohforce<<<grid3(a.vb, 256), block3(a.vb, 256), 0, ctx().stream>>>(a)));
+}
+
+// mk_vel_force_2d / _3d_cart (Source/mkforce.f90:283, :342)
+__global__ void k_mk_vel_force(VelForceArgs a) {
+  int ix[3];
+  if (!decode3(a.vb, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  const int dm = a.dm, r = dm - 1, q = ix[r];
+  const double rho = a.rho(i, j, k);
+  double rhopert = rho - a.rho0[q];
+  if (rho < a.rho_cut) rhopert = 0.0;
+  double fr;
+  if (dm == 2) {
+    a.force(i, j, k, 0) = -a.gpi(i, j, k, 0) / rho;
+    fr = rhopert / rho * a.grav[q] - a.gpi(i, j, k, 1) / rho - a.w0_force[q];
+  } else {
+    const double omega = a.omega, sin_theta = a.sin_theta, cos_theta = a.cos_theta;
+    const double cen0 = -(omega * omega) * a.rotation_radius * sin_theta * sin_theta;
+    const double cen1 = 0.0;
+    const double cen2 = (omega * omega) * a.rotation_radius * cos_theta * sin_theta - (omega * omega) * a.rotation_radius;
+    double cor0, cor1, cor2;
+    if (a.is_final_update) {
+      cor0 = -2.0 * omega * 0.5 * (a.uedge[1](i, j, k) + a.uedge[1](i, j + 1, k)) * cos_theta;
+      cor1 = 2.0 * omega * (0.5 * (a.uedge[2](i, j, k) + a.w0[k] + a.uedge[2](i, j, k + 1) + a.w0[k + 1]) * sin_theta +
+                            0.5 * (a.uedge[0](i, j, k) + a.uedge[0](i + 1, j, k)) * cos_theta);
+      cor2 = -2.0 * omega * 0.5 * (a.uedge[1](i, j, k) + a.uedge[1](i, j + 1, k)) * sin_theta;
+    } else {
+      cor0 = -2.0 * omega * a.uold(i, j, k, 1) * cos_theta;
+      cor1 = 2.0 * omega * ((a.uold(i, j, k, 2) + 0.5 * (a.w0[k] + a.w0[k + 1])) * sin_theta + a.uold(i, j, k, 0) * cos_theta);
+      cor2 = -2.0 * omega * a.uold(i, j, k, 1) * sin_theta;
+    }
+    a.force(i, j, k, 0) = -cor0 - cen0 - a.gpi(i, j, k, 0) / rho;
+    a.force(i, j, k, 1) = -cor1 - cen1 - a.gpi(i, j, k, 1) / rho;
+    fr = -cor2 - cen2 + (rhopert * a.grav[k] - a.gpi(i, j, k, 2)) / rho - a.w0_force[k];
+  }
+  if (a.add_utilde && q > -1 && q < a.nr) {
+    const DV& we = a.uedge[r];
+    const long o = we.off(i, j, k);
+    fr = fr - (we.p[o + we.stride(r)] + we.p[o]) * (a.w0[q + 1] - a.w0[q]) / (2.0 * a.dr);
+  }
+  a.force(i, j, k, r) = fr;
+}
+void mk_vel_force_dev(VelForceArgs& a) {
+  set_dev(a.force.p, 0.0, a.force.size());  // vel_force = ZERO (mkforce.f90:302 / :371)
+  MGPU_TIMED(TAG_GLUE, (k_mk_vel_force<<<grid3(a.vb, 256), block3(a.vb, 256), 0, ctx().stream>>>(a)));
+}
+
+__global__ void k_radial_cell_avg(DV u, Box3 b, int r, const double* w0) {
+  int ix[3];
+  if (!decode3(b, ix)) return;
+  u(ix[0], ix[1], ix[2]) = 0.5 * (w0[ix[r]] + w0[ix[r] + 1]);
+}
+void radial_cell_avg_dev(const mgpu_params& P, const DV& ufull, const double* w0_dev, const int* lo, const int* hi) {
+  const int r = P.dm - 1;
+  set_dev(ufull.p, 0.0, ufull.size());  // fill_3d_data.f90:164 (s0_cart = ZERO)
+  Box3 b;
+  for (int d = 0; d < 3; ++d) { b.lo[d] = ufull.lo[d]; b.hi[d] = ufull.lo[d] + ufull.n[d] - 1; }
+  b.lo[r] = lo[r];
+  b.hi[r] = hi[r];
+  k_radial_cell_avg<<<grid3(b, 256), block3(b, 256), 0, ctx().stream>>>(ufull.comp(r), b, r, w0_dev);
+  MGPU_LAUNCH_CHECK();
+}
+__global__ void k_add(double* dst, const double* src, long n) {
+  long t = MGPU_TID;
+  if (t < n) dst[t] = dst[t] + src[t];
+}
+void add_dev(double* dst, const double* src, long n) {
+  k_add<<<nblocks(n, 256), 256, 0, ctx().stream>>>(dst, src, n);
   MGPU_LAUNCH_CHECK();
 }
 
 // op: 0 = a/b, 1 = a*b (b = another component), 2 = a + mult*base(ir)
 __global__ void k_pointwise(DV a, DV b, Box3 vb, int op, int r, const double* base, double mult) {
   int ix[3];
-  if (!decode(vb, MGPU_TID, ix)) return;
+  if (!decode3(vb, ix)) return;
   double& x = a(ix[0], ix[1], ix[2]);
   if (op == 0) x = x / b(ix[0], ix[1], ix[2]);
   else if (op == 1) x = x * b(ix[0], ix[1], ix[2]);
@@ -300,15 +394,21 @@ __global__ void k_pointwise(DV a, DV b, Box3 vb, int op, int r, const double* ba
 void convert_rhoX_to_X_dev(const mgpu_params& P, const DV& s, bool flag, const int* lo, const int* hi) {
   Box3 vb = grown(lo, hi, P.dm, 0);
   for (int n = 0; n < P.nspec; ++n) {
-    k_pointwise<<<nblocks(vb.npts(), 256), 256, 0, ctx().stream>>>(s.comp(P.spec_comp - 1 + n), s.comp(P.rho_comp - 1),
+    k_pointwise<<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(s.comp(P.spec_comp - 1 + n), s.comp(P.rho_comp - 1),
                                                                   vb, flag ? 0 : 1, 0, nullptr, 0.0);
     MGPU_LAUNCH_CHECK();
   }
 }
+void comp_muldiv_dev(const mgpu_params& P, const DV& a, int ca, const DV& b, int cb, int op, int g, const int* lo,
+                     const int* hi) {
+  Box3 vb = grown(lo, hi, P.dm, g);
+  k_pointwise<<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(a.comp(ca), b.comp(cb), vb, op, 0, nullptr, 0.0);
+  MGPU_LAUNCH_CHECK();
+}
 void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_dev, int comp, bool flag,
                           const int* lo, const int* hi) {
   Box3 vb = grown(lo, hi, P.dm, 0);
-  k_pointwise<<<nblocks(vb.npts(), 256), 256, 0, ctx().stream>>>(s.comp(comp - 1), s.comp(comp - 1), vb, 2, P.dm - 1,
+  k_pointwise<<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(s.comp(comp - 1), s.comp(comp - 1), vb, 2, P.dm - 1,
                                                                 base_dev, flag ? -1.0 : 1.0);
   MGPU_LAUNCH_CHECK();
 }
@@ -318,7 +418,7 @@ void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_
 // d = x, y, z in turn, so edges/corners come out right), then physbc in the reference's order.
 __global__ void k_wrap(DV a, Box3 tb, int d, int lo, int hi, int ng, int nodal) {
   int ix[3];
-  if (!decode(tb, MGPU_TID, ix)) return;  // tb: d collapsed to [0, 2*ng-1] = ghost slot
+  if (!decode32(tb, ix)) return;  // tb: d collapsed to [0, 2*ng-1] = ghost slot
   const int g = ix[d];                    // 0..ng-1: lo side, ng..2ng-1: hi side
   const int n = hi - lo + 1;
   int dst, src;
@@ -337,7 +437,7 @@ __global__ void k_wrap(DV a, Box3 tb, int d, int lo, int hi, int ng, int nodal) 
 
 __global__ void k_physbc(DV s, Box3 tb, int d, int side, int bc, int lo, int hi, int ng) {
   int ix[3];
-  if (!decode(tb, MGPU_TID, ix)) return;  // tb: d collapsed to a single index
+  if (!decode32(tb, ix)) return;  // tb: d collapsed to a single index
   const int e = (side == 0) ? lo : hi;
   const int sg = (side == 0) ? -1 : 1;
   const long st = s.stride(d);
@@ -422,49 +522,85 @@ void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, con
 // Arithmetic is expression-for-expression that of k_rhoX_flux / k_update_scal / k_update_rho.
 namespace mgpu {
 
-__device__ __forceinline__ double rhoX_flux_of(const FluxArgs& a, int d, int i, int j, int k, int c) {
-  const int r = a.dm - 1;
-  const int ir = (r == 1) ? j : k;
-  double rho0_edge, vel = a.umac[d](i, j, k);
-  if (d != r) {
-    rho0_edge = 0.5 * (a.rho0_old[ir] + a.rho0_new[ir]);
-  } else {
-    rho0_edge = 0.5 * (a.rho0_edge_old[ir] + a.rho0_edge_new[ir]);
-    vel = vel + a.w0[ir];
-  }
-  const DV& se = a.sedge[d];
-  const long o = se.off(i, j, k);
-  if (a.species_pred_type == MGPU_PREDICT_RHOPRIME_AND_X) return vel * (rho0_edge + se.p[o + se.cs * a.rho]) * se.p[o + se.cs * c];
-  if (a.species_pred_type == MGPU_PREDICT_RHOX) return vel * se.p[o + se.cs * c];
-  return vel * se.p[o + se.cs * a.rho] * se.p[o + se.cs * c];
-}
-
+// DM: dimensionality; FAST: multiply by 1/dx instead of dividing (last-bit differences, <= 1e-12 relative)
+template <int DM, bool FAST>
 __global__ void __launch_bounds__(256) k_flux_update_all(FluxArgs a, UpdArgs u, int t0, int ntrac, int rho, double bcd) {
   int ix[3];
-  if (!decode(u.vb, MGPU_TID, ix)) return;
+  if (!decode3(u.vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
-  const int dm = a.dm, r = dm - 1;
+  constexpr int r = DM - 1;
   const int c0 = a.spec0, nspec = a.nspec;
   const int ir = ix[r];
-  double eta = 0.0;
+  const int spt = a.species_pred_type;
+  // face offsets (lo face of this zone; hi face = + stride) in the edge-state and flux fabs of each direction
+  long oe[DM], of[DM], se_st[DM], sf_st[DM];
+  double vlo[DM], vhi[DM], r0lo[DM], r0hi[DM], rdx[DM];
+  bool last[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d) {
+    oe[d] = a.sedge[d].off(i, j, k);
+    of[d] = a.sflux[d].off(i, j, k);
+    se_st[d] = a.sedge[d].stride(d);
+    sf_st[d] = a.sflux[d].stride(d);
+    const long ou = a.umac[d].off(i, j, k);
+    vlo[d] = a.umac[d].p[ou];
+    vhi[d] = a.umac[d].p[ou + a.umac[d].stride(d)];
+    last[d] = (ix[d] == u.vb.hi[d]);
+    rdx[d] = FAST ? 1.0 / u.dx[d] : u.dx[d];
+    double e_lo, e_hi;
+    if (d != r) {  // mkflux.f90:410
+      e_lo = e_hi = 0.5 * (a.rho0_old[ir] + a.rho0_new[ir]);
+    } else {  // mkflux.f90:465
+      e_lo = 0.5 * (a.rho0_edge_old[ir] + a.rho0_edge_new[ir]);
+      e_hi = 0.5 * (a.rho0_edge_old[ir + 1] + a.rho0_edge_new[ir + 1]);
+      vlo[d] = vlo[d] + a.w0[ir];
+      vhi[d] = vhi[d] + a.w0[ir + 1];
+    }
+    // density factor of the flux: (rho0_edge + rho'_edge), 1, or rho_edge by species_pred_type (mkflux.f90:415-431)
+    if (spt == MGPU_PREDICT_RHOX) {
+      r0lo[d] = r0hi[d] = 1.0;
+    } else {
+      const double* pr = a.sedge[d].p + oe[d] + a.sedge[d].cs * a.rho;
+      if (spt == MGPU_PREDICT_RHOPRIME_AND_X) {
+        r0lo[d] = e_lo + pr[0];
+        r0hi[d] = e_hi + pr[se_st[d]];
+      } else {
+        r0lo[d] = pr[0];
+        r0hi[d] = pr[se_st[d]];
+      }
+    }
+  }
   const bool do_eta = a.evolve_base_state;
-  if (do_eta) eta = a.eta(i, j, k);
-  double eta_hi = 0.0;
-  const bool last_r = (ix[r] == u.vb.hi[r]);
-  if (do_eta && last_r) eta_hi = (r == 1) ? a.eta(i, j + 1, k) : a.eta(i, j, k + 1);
+  const bool last_r = last[r];
+  double eta = 0.0, eta_hi = 0.0;
+  long oeta = 0, eta_st = 0;
+  if (do_eta) {
+    oeta = a.eta.off(i, j, k);
+    eta_st = a.eta.stride(r);
+    eta = a.eta.p[oeta];
+    if (last_r) eta_hi = a.eta.p[oeta + eta_st];
+  }
+  const long oso = u.sold.off(i, j, k), osn = u.snew.off(i, j, k), ofo = u.force.off(i, j, k);
   bool neg = false;
-  double rnew = u.sold(i, j, k, rho);
+  double rnew = u.sold.p[oso + u.sold.cs * rho];
   const int ncomp = nspec + ntrac;
   for (int n = 0; n < ncomp; ++n) {
     const int c = (n < nspec) ? c0 + n : t0 + (n - nspec);
-    double flo[3], fhi[3];
-    for (int d = 0; d < dm; ++d) {
-      int ih[3] = {i, j, k};
-      ih[d] += 1;
-      flo[d] = rhoX_flux_of(a, d, i, j, k, c);
-      fhi[d] = rhoX_flux_of(a, d, ih[0], ih[1], ih[2], c);
-      a.sflux[d](i, j, k, c) = flo[d];
-      if (ix[d] == u.vb.hi[d]) a.sflux[d](ih[0], ih[1], ih[2], c) = fhi[d];
+    double flo[DM], fhi[DM];
+#pragma unroll
+    for (int d = 0; d < DM; ++d) {
+      const double* pe = a.sedge[d].p + oe[d] + a.sedge[d].cs * c;
+      // vel * rhofac * X_edge (vel * X_edge for predict_rhoX): expression order of mkflux.f90:415-431
+      if (spt == MGPU_PREDICT_RHOX) {
+        flo[d] = vlo[d] * pe[0];
+        fhi[d] = vhi[d] * pe[se_st[d]];
+      } else {
+        flo[d] = vlo[d] * r0lo[d] * pe[0];
+        fhi[d] = vhi[d] * r0hi[d] * pe[se_st[d]];
+      }
+      double* pf = a.sflux[d].p + of[d] + a.sflux[d].cs * c;
+      pf[0] = flo[d];
+      if (last[d]) pf[sf_st[d]] = fhi[d];
     }
     if (do_eta && n < nspec) {  // mkflux.f90:486-494
       eta = eta + flo[r];
@@ -474,25 +610,28 @@ __global__ void __launch_bounds__(256) k_flux_update_all(FluxArgs a, UpdArgs u, 
         if (last_r) eta_hi = eta_hi - a.w0[ir + 1] * a.rho0_predicted_edge[ir + 1];
       }
     }
-    double divterm = (fhi[0] - flo[0]) / u.dx[0] + (fhi[1] - flo[1]) / u.dx[1];
-    if (dm == 3) divterm = divterm + (fhi[2] - flo[2]) / u.dx[2];
-    const double so = u.sold(i, j, k, c);
-    const double sn = so + u.dt * (-divterm + u.force(i, j, k, c));
-    u.snew(i, j, k, c) = sn;
+    double divterm;
+    if (FAST) {
+      divterm = (fhi[0] - flo[0]) * rdx[0] + (fhi[1] - flo[1]) * rdx[1];
+      if (DM == 3) divterm = divterm + (fhi[DM - 1] - flo[DM - 1]) * rdx[DM - 1];
+    } else {
+      divterm = (fhi[0] - flo[0]) / rdx[0] + (fhi[1] - flo[1]) / rdx[1];
+      if (DM == 3) divterm = divterm + (fhi[DM - 1] - flo[DM - 1]) / rdx[DM - 1];
+    }
+    const double so = u.sold.p[oso + u.sold.cs * c];
+    const double sn = so + u.dt * (-divterm + u.force.p[ofo + u.force.cs * c]);
+    u.snew.p[osn + u.snew.cs * c] = sn;
     if (n < nspec) {
       rnew = rnew + (sn - so);
       if (sn < 0.0) neg = true;
     }
   }
   if (do_eta) {
-    a.eta(i, j, k) = eta;
-    if (last_r) {
-      if (r == 1) a.eta(i, j + 1, k) = eta_hi;
-      else a.eta(i, j, k + 1) = eta_hi;
-    }
+    a.eta.p[oeta] = eta;
+    if (last_r) a.eta.p[oeta + eta_st] = eta_hi;
   }
   // density, floor, negative species: update_scal.f90:453-505 (same statements as k_update_rho)
-  double* sn = u.snew.p + u.snew.off(i, j, k);
+  double* sn = u.snew.p + osn;
   const long cn = u.snew.cs;
   const int c1 = c0 + nspec - 1;
   if (rnew < 0.5 * bcd) {
@@ -518,15 +657,24 @@ __global__ void __launch_bounds__(256) k_flux_update_all(FluxArgs a, UpdArgs u, 
   }
 }
 
-void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u) {
+void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exact) {
   Context& cx = ctx();
   const int rho = P.rho_comp - 1;
   if (u.snew.cs != u.sold.cs) throw Error("update_scal: sold and snew must have the same ghost width");
   // snew(:,:,:,rho_comp) = sold(:,:,:,rho_comp) including ghost cells (update_scal.f90:455)
   MGPU_TIMED(TAG_UPDATE, (k_copy<<<nblocks(u.snew.cs, 256), 256, 0, cx.stream>>>(u.snew.p + u.snew.cs * rho,
                                                                                  u.sold.p + u.sold.cs * rho, u.snew.cs)));
-  MGPU_TIMED(TAG_UPDATE, (k_flux_update_all<<<nblocks(u.vb.npts(), 256), 256, 0, cx.stream>>>(
-                             a, u, P.trac_comp - 1, P.ntrac, rho, P.base_cutoff_density)));
+  const dim3 g = grid3(u.vb, 256);
+  const int b = block3(u.vb, 256);
+  const int t0 = P.trac_comp - 1;
+  const double bcd = P.base_cutoff_density;
+  if (P.dm == 3) {
+    if (exact) MGPU_TIMED(TAG_UPDATE, (k_flux_update_all<3, false><<<g, b, 0, cx.stream>>>(a, u, t0, P.ntrac, rho, bcd)));
+    else MGPU_TIMED(TAG_UPDATE, (k_flux_update_all<3, true><<<g, b, 0, cx.stream>>>(a, u, t0, P.ntrac, rho, bcd)));
+  } else {
+    if (exact) MGPU_TIMED(TAG_UPDATE, (k_flux_update_all<2, false><<<g, b, 0, cx.stream>>>(a, u, t0, P.ntrac, rho, bcd)));
+    else MGPU_TIMED(TAG_UPDATE, (k_flux_update_all<2, true><<<g, b, 0, cx.stream>>>(a, u, t0, P.ntrac, rho, bcd)));
+  }
 }
 
 }  // namespace mgpu

@@ -25,7 +25,7 @@ struct UpdArgs {
 };
 void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop);
 // mk_rhoX_flux (species + tracers) + update_scal (species + tracers + density) of density_advance in one launch
-void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u);
+void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exact);
 
 struct VelArgs {
   int dm;
@@ -36,6 +36,32 @@ struct VelArgs {
   const double* w0;
 };
 void update_velocity_dev(VelArgs& a);
+
+// force builders
+struct RhohForceArgs {
+  int dm, nr, cutoff_coord;
+  bool with_psi, add_thermal;
+  double dr;
+  Box3 vb;
+  DV f, thermal, wm;  // f: the rhoh component of scal_force; wm: umac in the radial direction
+  const double *p0_1, *p0_2, *rho0_1, *rho0_2, *grav, *psi;
+};
+void mkrhohforce_dev(RhohForceArgs& a);
+struct VelForceArgs {
+  int dm, nr;
+  bool is_final_update, add_utilde;
+  double dr, rho_cut, omega, sin_theta, cos_theta, rotation_radius;
+  Box3 vb;
+  DV force, uold, gpi, rho, uedge[3];
+  const double *w0, *rho0, *grav, *w0_force;
+};
+void mk_vel_force_dev(VelForceArgs& a);
+// ufull = put_1d_array_on_cart(w0 -> radial component) (+ ghost fill by the caller) ; dst += src
+void radial_cell_avg_dev(const mgpu_params& P, const DV& ufull, const double* w0_dev, const int* lo, const int* hi);
+void add_dev(double* dst, const double* src, long n);
+// a(comp ca) op= b(comp cb) over the valid box grown by g: op 0 '/', 1 '*'
+void comp_muldiv_dev(const mgpu_params& P, const DV& a, int ca, const DV& b, int cb, int op, int g, const int* lo,
+                     const int* hi);
 
 void addw0_dev(const mgpu_params& P, DV* umac, const double* w0_dev, double mult, const int* lo, const int* hi);
 void modify_scal_force_dev(const mgpu_params& P, const DV& force, const DV& s, const DV* umac, const double* s0,

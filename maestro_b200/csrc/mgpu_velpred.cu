@@ -69,7 +69,7 @@ __global__ void k_mkutrans(VpArgs a, int d) {
   int ix[3];
   Box3 fb = a.vb;
   fb.hi[d] += 1;
-  if (!decode(fb, MGPU_TID, ix)) return;
+  if (!decode3(fb, ix)) return;
   const DV u = a.utilde.comp(d), uf = a.ufull.comp(d);
   const long st = u.stride(d);
   const LineBC b = make_linebc(a.dm, d, a.lo[d], a.hi[d], a.bclo[d][d], a.bchi[d][d]);
@@ -101,7 +101,7 @@ __global__ void k_vp_face(VpArgs a, int d) {
   int ix[3];
   Box3 fb = a.tb;
   fb.lo[d] = a.lo[d];  // faces lo..hi+1 in d, lo-1..hi+1 transverse
-  if (!decode(fb, MGPU_TID, ix)) return;
+  if (!decode3(fb, ix)) return;
   const int dm = a.dm;
   const DV ufd = a.ufull.comp(d);
   const long fo = ufd.off(ix[0], ix[1], ix[2]);
@@ -172,7 +172,7 @@ __device__ __forceinline__ double tterm(double coef, const DV& tr, const DV& q, 
 
 __global__ void k_vp_trans(VpArgs a) {
   int ix[3];
-  if (!decode(a.tb, MGPU_TID, ix)) return;
+  if (!decode3(a.tb, ix)) return;
   const double dt6 = a.dt / 6.0;
   for (int c = 0; c < 3; ++c)
     for (int d = 0; d < 3; ++d) {
@@ -205,7 +205,7 @@ __global__ void k_vp_final(VpArgs a, int d) {
   int ix[3];
   Box3 fb = a.vb;
   fb.hi[d] += 1;
-  if (!decode(fb, MGPU_TID, ix)) return;
+  if (!decode3(fb, ix)) return;
   const int dm = a.dm;
   const double dt2 = 0.5 * a.dt, dt4 = a.dt / 4.0;
   int cl[3] = {ix[0], ix[1], ix[2]};
@@ -316,7 +316,7 @@ void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* u
   for (int d = 0; d < P.dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    MGPU_TIMED(TAG_VELPRED, (k_mkutrans<<<nblocks(fb.npts(), 256), 256, 0, ctx().stream>>>(a, d)));
+    MGPU_TIMED(TAG_VELPRED, (k_mkutrans<<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a, d)));
   }
 }
 
@@ -356,13 +356,13 @@ void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* um
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.tb;
     fb.lo[d] = a.lo[d];
-    MGPU_TIMED(TAG_VELPRED, (k_vp_face<<<nblocks(fb.npts(), 128), 128, 0, s>>>(a, d)));
+    MGPU_TIMED(TAG_VELPRED, (k_vp_face<<<grid3(fb, 128), block3(fb, 128), 0, s>>>(a, d)));
   }
-  if (dm == 3) MGPU_TIMED(TAG_VELPRED, (k_vp_trans<<<nblocks(nt, 256), 256, 0, s>>>(a)));
+  if (dm == 3) MGPU_TIMED(TAG_VELPRED, (k_vp_trans<<<grid3(a.tb, 256), block3(a.tb, 256), 0, s>>>(a)));
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    MGPU_TIMED(TAG_VELPRED, (k_vp_final<<<nblocks(fb.npts(), 256), 256, 0, s>>>(a, d)));
+    MGPU_TIMED(TAG_VELPRED, (k_vp_final<<<grid3(fb, 256), block3(fb, 256), 0, s>>>(a, d)));
   }
 }
 

@@ -109,6 +109,9 @@ def make_params(dm, n=None, lo=None, hi=None, nspec=3, ntrac=1, **kw):
     p.dt = 0.0
     p.rel_eps = 0.0
     p.base_cutoff_density = 1.0e-10
+    p.base_cutoff_density_coord = p.nr  # no cutoff inside the domain
+    p.buoyancy_cutoff_factor = 5.0
+    p.omega, p.sin_theta, p.cos_theta, p.rotation_radius = 0.0, 0.0, 1.0, 1.0e6
     for k, v in kw.items():
         if k == "dx":
             for d in range(3):

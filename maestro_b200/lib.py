@@ -90,6 +90,13 @@ def launch_count(reset=False):
     return int(load().mgpu_launch_count(1 if reset else 0))
 
 
+def copy_bytes(reset=False):
+    """(host->device, device->host) bytes moved by host-pointer calls since the last reset"""
+    a, b = C.c_long(), C.c_long()
+    load().mgpu_copy_bytes(C.byref(a), C.byref(b), 1 if reset else 0)
+    return a.value, b.value
+
+
 def finalize():
     if _lib is not None:
         _lib.mgpu_finalize()

@@ -136,3 +136,46 @@ class Operators:
         self._call("density_advance", C.byref(p), which_step, fab_ptr(sold), fab_ptr(snew), se, sf,
                    fab_ptr(scal_force), um, keep[0][1], fab_ptr(etarhoflux), keep[1][1], keep[2][1], keep[3][1],
                    keep[4][1], bcp, pmp)
+
+    # ---- force builders -------------------------------------------------------------------
+    def mkrhohforce(self, p, scal_force, is_prediction, thermal, umac, p0_1, p0_2, rho0_1, rho0_2, grav, psi,
+                    add_thermal):
+        keep = [as_double_p(x) for x in (p0_1, p0_2, rho0_1, rho0_2, grav, psi)]
+        um, k1 = fab_pp(umac)
+        self._call("mkrhohforce", C.byref(p), 1, fab_ptr(scal_force), int(is_prediction), fab_ptr(thermal), um,
+                   *[k[1] for k in keep], int(add_thermal))
+
+    def mk_vel_force(self, p, vel_force, is_final_update, uold, uedge, w0, gpi, s, index_rho, rho0, grav, w0_force,
+                     do_add_utilde_force=True):
+        keep = [as_double_p(x) for x in (w0, rho0, grav, w0_force)]
+        ue, k1 = fab_pp(uedge)
+        self._call("mk_vel_force", C.byref(p), 1, fab_ptr(vel_force), int(is_final_update), fab_ptr(uold), ue,
+                   keep[0][1], fab_ptr(gpi), fab_ptr(s), index_rho, keep[1][1], keep[2][1], keep[3][1],
+                   int(do_add_utilde_force))
+
+    # ---- the other L4 drivers ---------------------------------------------------------------------------
+    def advance_premac(self, p, uold, sold, umac, gpi, w0, w0_force, rho0_old, grav_cell_old, adv_bc, phys_bc, pmask):
+        keep = [as_double_p(x) for x in (w0, w0_force, rho0_old, grav_cell_old)]
+        ints = [as_int_p(x) for x in (adv_bc, phys_bc, pmask)]
+        um, k1 = fab_pp(umac)
+        self._call("advance_premac", C.byref(p), fab_ptr(uold), fab_ptr(sold), um, fab_ptr(gpi),
+                   *[k[1] for k in keep], *[k[1] for k in ints])
+
+    def velocity_advance(self, p, uold, unew, sold, rhohalf, umac, gpi, w0, w0_force, rho0_old, rho0_nph,
+                         grav_cell_old, grav_cell_nph, sponge, adv_bc, pmask):
+        keep = [as_double_p(x) for x in (w0, w0_force, rho0_old, rho0_nph, grav_cell_old, grav_cell_nph)]
+        ints = [as_int_p(x) for x in (adv_bc, pmask)]
+        um, k1 = fab_pp(umac)
+        self._call("velocity_advance", C.byref(p), fab_ptr(uold), fab_ptr(unew), fab_ptr(sold), fab_ptr(rhohalf), um,
+                   fab_ptr(gpi), *[k[1] for k in keep], fab_ptr(sponge), *[k[1] for k in ints])
+
+    def enthalpy_advance(self, p, which_step, sold, snew, sedge, sflux, scal_force, thermal, umac, w0, rho0_old,
+                         rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old, grav_nph, adv_bc, pmask):
+        keep = [as_double_p(x) for x in (w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old,
+                                         grav_nph)]
+        ints = [as_int_p(x) for x in (adv_bc, pmask)]
+        se, k1 = fab_pp(sedge)
+        sf, k2 = fab_pp(sflux)
+        um, k3 = fab_pp(umac)
+        self._call("enthalpy_advance", C.byref(p), which_step, fab_ptr(sold), fab_ptr(snew), se, sf,
+                   fab_ptr(scal_force), fab_ptr(thermal), um, *[k[1] for k in keep], *[k[1] for k in ints])

@@ -244,6 +244,81 @@ int mo_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgp
   MO_CATCH
 }
 
+int mo_mkrhohforce(const mgpu_params* p, int nfabs, mgpu_fab* scal_force, int is_prediction, const mgpu_fab* thermal,
+                   const mgpu_fab* const* umac, const double* p0_1, const double* p0_2, const double* rho0_1,
+                   const double* rho0_2, const double* grav, const double* psi, int add_thermal) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr f = Arr::view(scal_force[i], p->dm), th = Arr::view(thermal[i], p->dm);
+    Arr um[3];
+    views(p, umac, i, um);
+    mkrhohforce_box(*p, f, is_prediction != 0, th, um, p0_1, p0_2, rho0_1, rho0_2, grav, psi, add_thermal != 0,
+                    scal_force[i].lo, scal_force[i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_mk_vel_force(const mgpu_params* p, int nfabs, mgpu_fab* vel_force, int is_final_update, const mgpu_fab* uold,
+                    const mgpu_fab* const* uedge, const double* w0, const mgpu_fab* gpi, const mgpu_fab* s,
+                    int index_rho, const double* rho0, const double* grav, const double* w0_force,
+                    int do_add_utilde_force) {
+  MO_TRY
+  for (int i = 0; i < nfabs; ++i) {
+    Arr f = Arr::view(vel_force[i], p->dm), uo = Arr::view(uold[i], p->dm), gp = Arr::view(gpi[i], p->dm);
+    Arr sa = Arr::view(s[i], p->dm);
+    Arr ue[3];
+    views(p, uedge, i, ue);
+    mk_vel_force_box(*p, f, is_final_update != 0, uo, ue, w0, gp, sa.comp(index_rho - 1), rho0, grav, w0_force,
+                     vel_force[i].lo, vel_force[i].hi, do_add_utilde_force != 0);
+  }
+  MO_CATCH
+}
+
+int mo_advance_premac(const mgpu_params* p, const mgpu_fab* uold, const mgpu_fab* sold, mgpu_fab* const* umac,
+                      const mgpu_fab* gpi, const double* w0, const double* w0_force, const double* rho0_old,
+                      const double* grav_cell_old, const int* adv_bc, const int* phys_bc, const int* pmask) {
+  MO_TRY
+  Arr uo = Arr::view(*uold, p->dm), so = Arr::view(*sold, p->dm), gp = Arr::view(*gpi, p->dm);
+  Arr um[3];
+  views(p, (const mgpu_fab* const*)umac, 0, um);
+  advance_premac_box(*p, uo, so, um, gp, w0, w0_force, rho0_old, grav_cell_old, uold->lo, uold->hi, uold->ng, adv_bc,
+                     phys_bc, pmask);
+  MO_CATCH
+}
+
+int mo_velocity_advance(const mgpu_params* p, const mgpu_fab* uold, mgpu_fab* unew, const mgpu_fab* sold,
+                        const mgpu_fab* rhohalf, mgpu_fab* const* umac, const mgpu_fab* gpi, const double* w0,
+                        const double* w0_force, const double* rho0_old, const double* rho0_nph,
+                        const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
+                        const int* adv_bc, const int* pmask) {
+  MO_TRY
+  Arr uo = Arr::view(*uold, p->dm), un = Arr::view(*unew, p->dm), so = Arr::view(*sold, p->dm);
+  Arr rh = Arr::view(*rhohalf, p->dm), gp = Arr::view(*gpi, p->dm), sp = Arr::view(*sponge, p->dm);
+  Arr um[3];
+  views(p, (const mgpu_fab* const*)umac, 0, um);
+  velocity_advance_box(*p, uo, un, so, rh, um, gp, w0, w0_force, rho0_old, rho0_nph, grav_cell_old, grav_cell_nph, sp,
+                       uold->lo, uold->hi, uold->ng, adv_bc, pmask);
+  MO_CATCH
+}
+
+int mo_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgpu_fab* snew, mgpu_fab* const* sedge,
+                        mgpu_fab* const* sflux, mgpu_fab* scal_force, const mgpu_fab* thermal, mgpu_fab* const* umac,
+                        const double* w0, const double* rho0_old, const double* rhoh0_old, const double* rho0_new,
+                        const double* rhoh0_new, const double* p0_old, const double* p0_new, const double* psi,
+                        const double* grav_old, const double* grav_nph, const int* adv_bc, const int* pmask) {
+  MO_TRY
+  Arr so = Arr::view(*sold, p->dm), sn = Arr::view(*snew, p->dm), fa = Arr::view(*scal_force, p->dm);
+  Arr th = Arr::view(*thermal, p->dm);
+  Arr se[3], sf[3], um[3];
+  views(p, (const mgpu_fab* const*)sedge, 0, se);
+  views(p, (const mgpu_fab* const*)sflux, 0, sf);
+  views(p, (const mgpu_fab* const*)umac, 0, um);
+  enthalpy_advance_box(*p, which_step, so, sn, se, sf, fa, th, um, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new,
+                       p0_old, p0_new, psi, grav_old, grav_nph, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc,
+                       pmask);
+  MO_CATCH
+}
+
 int mo_test_advect(int dm, int n, int ppm_type, int bds_type, int itest_dir, double cflfac, double stop_time,
                    double* abs_norm, double* rel_norm, double* rho_final) {
   MO_TRY

@@ -89,6 +89,27 @@ void velpred_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr*
 void bds_box(const mgpu_params& P, const Arr& s, Arr* sedge, const Arr* umac, const Arr& force, const int* lo,
              const int* hi, int comp, bool is_conservative);
 
+void mkrhohforce_box(const mgpu_params& P, Arr& scal_force, bool is_prediction, const Arr& thermal, const Arr* umac,
+                     const double* p0_1, const double* p0_2, const double* rho0_1, const double* rho0_2,
+                     const double* grav, const double* psi, bool add_thermal, const int* lo, const int* hi);
+void mk_vel_force_box(const mgpu_params& P, Arr& vel_force, bool is_final_update, const Arr& uold, const Arr* uedge,
+                      const double* w0, const Arr& gpi, const Arr& rho, const double* rho0, const double* grav,
+                      const double* w0_force, const int* lo, const int* hi, bool do_add_utilde_force);
+void advance_premac_box(const mgpu_params& P, const Arr& uold, const Arr& sold, Arr* umac, const Arr& gpi,
+                        const double* w0, const double* w0_force, const double* rho0_old, const double* grav_cell_old,
+                        const int* lo, const int* hi, int ng_u, const int* adv_bc, const int* phys_bc, const int* pmask);
+void velocity_advance_box(const mgpu_params& P, const Arr& uold, Arr& unew, const Arr& sold, const Arr& rhohalf,
+                          Arr* umac, const Arr& gpi, const double* w0, const double* w0_force, const double* rho0_old,
+                          const double* rho0_nph, const double* grav_cell_old, const double* grav_cell_nph,
+                          const Arr& sponge, const int* lo, const int* hi, int ng_u, const int* adv_bc,
+                          const int* pmask);
+void enthalpy_advance_box(const mgpu_params& P, int which_step, Arr& sold, Arr& snew, Arr* sedge, Arr* sflux,
+                          Arr& scal_force, const Arr& thermal, Arr* umac, const double* w0, const double* rho0_old,
+                          const double* rhoh0_old, const double* rho0_new, const double* rhoh0_new,
+                          const double* p0_old, const double* p0_new, const double* psi, const double* grav_old,
+                          const double* grav_nph, const int* lo, const int* hi, int ng_s, int ng_f, const int* adv_bc,
+                          const int* pmask);
+
 // ghost fill of a single box covering the whole domain: periodic wrap + multifab_physbc
 void fill_boundary_box(const mgpu_params& P, Arr& s, const int* lo, const int* hi, int ng, int scomp, int bccomp,
                        int ncomp, const int* adv_bc, const int* pmask);

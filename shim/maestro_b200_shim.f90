@@ -40,6 +40,8 @@ module maestro_b200_shim
      integer(c_int) :: domlo(3), domhi(3)
      integer(c_int) :: nr
      real(c_double) :: dt, dx(3), rel_eps, base_cutoff_density
+     integer(c_int) :: base_cutoff_density_coord
+     real(c_double) :: buoyancy_cutoff_factor, omega, sin_theta, cos_theta, rotation_radius
   end type mgpu_params
 
   integer(c_int), parameter :: MGPU_HOST = 0
@@ -193,8 +195,9 @@ contains
   ! module variables of the reference -> the per-call parameter block
   subroutine mgpu_fill_params(p, dm, dx, dt, domlo, domhi)
     use probin_module, only: ppm_type, bds_type, slope_order, ppm_trace_forces, species_pred_type, &
-         enthalpy_pred_type, evolve_base_state, do_sponge, do_eos_h_above_cutoff, base_cutoff_density
-    use geometry, only: spherical, nr_fine
+         enthalpy_pred_type, evolve_base_state, do_sponge, do_eos_h_above_cutoff, base_cutoff_density, &
+         buoyancy_cutoff_factor, rotation_radius
+    use geometry, only: spherical, nr_fine, base_cutoff_density_coord, omega, sin_theta, cos_theta
     use variables, only: rho_comp, rhoh_comp, spec_comp, temp_comp, pi_comp, trac_comp, nscal, ntrac, rel_eps
     use network, only: nspec
     type(mgpu_params), intent(out) :: p
@@ -216,6 +219,9 @@ contains
     p%nr = nr_fine
     p%dt = dt; p%dx(1:dm) = dx(1:dm)
     p%rel_eps = rel_eps; p%base_cutoff_density = base_cutoff_density
+    p%base_cutoff_density_coord = base_cutoff_density_coord(1)
+    p%buoyancy_cutoff_factor = buoyancy_cutoff_factor
+    p%omega = omega; p%sin_theta = sin_theta; p%cos_theta = cos_theta; p%rotation_radius = rotation_radius
   end subroutine mgpu_fill_params
 
   ! what dataptr/get_box/nghost give the reference kernels (make_edge_scal.f90:70-76), per local fab

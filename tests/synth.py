@@ -148,3 +148,24 @@ def fill_face_ghosts(fabs, pmask, dm):
             else:
                 a[sl(0, ng)] = a[sl(ng, ng + 1)]
                 a[sl(ng + n + nod, ext)] = a[sl(ng + n + nod - 1, ng + n + nod)]
+
+
+def make_episode_extras(st, seed=97):
+    """Extra inputs of enthalpy_advance / velocity_advance / advance_premac on top of make_state / make_vel_state:
+    gpi, rhohalf, sponge, thermal (fabs) and psi, grav, p0, w0_force (1-D).  Deterministic."""
+    rng = np.random.default_rng(seed)
+    p, dm, lo, hi = st["p"], st["dm"], st["lo"], st["hi"]
+    nr = p.nr
+    zr = (np.arange(nr) + 0.5) * p.dx[dm - 1]
+    gpi = Fab(lo, hi, 1, dm, dm=dm)
+    gpi.a[...] = rng.uniform(-0.5, 0.5, size=gpi.shape)
+    rhohalf = Fab(lo, hi, 1, 1, dm=dm)
+    rhohalf.a[...] = 1.5 + rng.uniform(-0.2, 0.2, size=rhohalf.shape)
+    sponge = Fab(lo, hi, 0, 1, dm=dm)
+    sponge.a[...] = rng.uniform(0.8, 1.0, size=sponge.shape)
+    thermal = Fab(lo, hi, 1, 1, dm=dm)
+    thermal.a[...] = rng.uniform(-0.3, 0.3, size=thermal.shape)
+    return dict(gpi=gpi, rhohalf=rhohalf, sponge=sponge, thermal=thermal,
+                psi=0.1 * np.cos(2 * np.pi * zr), grav_old=-1.0 - 0.2 * zr, grav_nph=-1.02 - 0.2 * zr,
+                p0_old=2.0 * np.exp(-zr), p0_new=2.05 * np.exp(-zr), w0_force=0.03 * np.sin(2 * np.pi * zr),
+                rho0_nph=1.0 + 0.51 * np.exp(-zr / 0.5))

@@ -29,10 +29,28 @@ def test_python_abi_mirror_matches_header():
     assert sorted(abi.all_symbols()) == header_symbols()
 
 
-def test_struct_layout_matches_c():
-    # sizes computed by hand from the header: fab = 8 + 12 + 12 + 4 + 4 + 12 = 52 -> padded to 56
-    assert C.sizeof(abi.mgpu_fab) == 56
-    assert C.sizeof(abi.mgpu_params) == 4 * 28 + 8 * 6
+def test_struct_layout_matches_c(tmp_path):
+    """sizeof / offsetof of every struct, as gcc lays out include/maestro_b200.h, against the ctypes mirror"""
+    import subprocess
+
+    src = tmp_path / "layout.c"
+    fields = {"mgpu_fab": [f[0] for f in abi.mgpu_fab._fields_], "mgpu_params": [f[0] for f in abi.mgpu_params._fields_],
+              "mgpu_halo_plan": [f[0] for f in abi.mgpu_halo_plan._fields_]}
+    body = ['#include <stdio.h>', '#include <stddef.h>', '#include "maestro_b200.h"', 'int main(void) {']
+    for st, fs in fields.items():
+        body.append('printf("%s %%zu\\n", sizeof(%s));' % (st, st))
+        for f in fs:
+            body.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (st, f, st, f))
+    body.append('return 0; }')
+    src.write_text("\n".join(body))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for st, fs in fields.items():
+        cls = getattr(abi, st)
+        assert C.sizeof(cls) == int(out[st]), st
+        for f in fs:
+            assert getattr(cls, f).offset == int(out["%s.%s" % (st, f)]), (st, f)
 
 
 def test_no_cpu_fallback():

@@ -284,3 +284,59 @@ def test_bds_test_advect_runs_and_is_accurate(oracle):
     ay, _ = oracle_lib.test_advect(oracle, 2, 32, 0, 1, 2, stop_time=0.25)
     ap, _ = oracle_lib.test_advect(oracle, 2, 32, 1, 0, 1, stop_time=0.25)
     assert abs(ax - ay) <= 1e-2 * ax and ax <= 1.05 * ap
+
+
+# ---- force builders + the other L4 episodes in the oracle -------------------------------------------------
+def test_velocity_advance_uniform_flow_without_forces_is_preserved(oracle):
+    """u = const, gpi = 0, rho = rho0 (no buoyancy), w0 = 0: velocity_advance must return u unchanged."""
+    from synth import make_episode_extras, make_vel_state
+
+    for dm, n in ((2, 10), (3, 7)):
+        st = make_vel_state(dm, n, noise=0.0, w0amp=0.0)
+        p = st["p"]
+        vec = [0.7, -0.4, 0.25]
+        for c in range(dm):
+            st["utilde"].a[c] = vec[c]
+        ex = make_episode_extras(st)
+        ex["gpi"].a[...] = 0.0
+        ex["rhohalf"].a[...] = 2.0
+        ex["sponge"].a[...] = 1.0
+        sc = make_state(dm, n)
+        sc["s"].a[...] = 2.0
+        rho0 = np.full(p.nr, 2.0)
+        umac = face_fabs(st["lo"], st["hi"], 1, 1, dm)
+        for d, u in enumerate(umac):
+            u.a[...] = vec[d]
+        unew = st["utilde"].clone()
+        oracle.velocity_advance(p, st["utilde"], unew, sc["s"], ex["rhohalf"], umac, ex["gpi"], st["w0"], np.zeros(p.nr),
+                                rho0, rho0, ex["grav_old"], ex["grav_nph"], ex["sponge"], st["adv_bc"], st["pmask"])
+        for c in range(dm):
+            assert np.abs(unew.valid(c) - vec[c]).max() <= 1e-15
+
+
+@pytest.mark.parametrize("dm,n", [(2, 10), (3, 7)])
+def test_episodes_bounds_checked_build_agrees(oracle, dm, n):
+    from synth import make_episode_extras, make_vel_state
+
+    dbg = oracle_lib.load(debug=True)
+    phys = VP_WALLS[dm]
+    st = make_vel_state(dm, n, phys_bc=phys, ppm_type=2, oracle=oracle)
+    ex = make_episode_extras(st)
+    sc = make_state(dm, n, phys_bc=phys, ppm_type=2, enthalpy_pred_type=1)
+    oracle.fill_boundary(sc["p"], sc["s"], 1, dm + 1, sc["p"].nscal, sc["adv_bc"], sc["pmask"])
+    p, b = sc["p"], sc["base"]
+    res = []
+    for o in (oracle, dbg):
+        umac = face_fabs(st["lo"], st["hi"], 1, 1, dm)
+        o.advance_premac(st["p"], st["utilde"], sc["s"], umac, ex["gpi"], st["w0"], ex["w0_force"], b["rho0_old"],
+                         ex["grav_old"], st["adv_bc"], st["phys_bc"], st["pmask"])
+        sold, snew = sc["s"].clone(), sc["s"].clone()
+        sedge = face_fabs(sc["lo"], sc["hi"], 0, p.nscal, dm, fill=1.0)
+        sflux = face_fabs(sc["lo"], sc["hi"], 0, p.nscal, dm)
+        um2 = [u.clone() for u in sc["umac"]]
+        o.enthalpy_advance(p, 2, sold, snew, sedge, sflux, sc["force"].clone(), ex["thermal"], um2, b["w0"],
+                           b["rho0_old"], b["rhoh0_old"], b["rho0_new"], b["rhoh0_new"], ex["p0_old"], ex["p0_new"],
+                           ex["psi"], ex["grav_old"], ex["grav_nph"], sc["adv_bc"], sc["pmask"])
+        res.append([u.valid(0).copy() for u in umac] + [snew.a.copy()])
+    for x, y in zip(*res):
+        assert np.array_equal(x, y) and np.isfinite(x).all()

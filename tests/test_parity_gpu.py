@@ -411,3 +411,147 @@ def test_multi_gpu_density_advance(gpu_ops, dm, bcset, ppm_type):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" OK ") == world
+
+
+# ---- force builders and the other L4 episodes -------------------------------------------------------------
+def _base_for_vel(st):
+    nr, dm = st["p"].nr, st["dm"]
+    zr = (np.arange(nr) + 0.5) * st["p"].dx[dm - 1]
+    return dict(rho0_old=1.0 + 0.5 * np.exp(-zr / 0.5))
+
+
+def _scalar_like(st, oracle, seed=5):
+    """a scalar state (for the density used by mk_vel_force) on the box of a velocity state"""
+    sc = make_state(st["dm"], [st["hi"][d] + 1 for d in range(st["dm"])], phys_bc=st["phys"], seed=seed)
+    oracle.fill_boundary(sc["p"], sc["s"], 1, st["dm"] + 1, sc["p"].nscal, sc["adv_bc"], sc["pmask"])
+    return sc["s"]
+
+
+@pytest.mark.parametrize("dm,n", [(2, (20, 14)), (3, (12, 9, 10))])
+@pytest.mark.parametrize("final", [False, True])
+@pytest.mark.parametrize("omega", [0.0, 0.3])
+def test_mk_vel_force(gpu_ops, oracle, dm, n, final, omega):
+    from synth import make_episode_extras, make_vel_state
+
+    st = make_vel_state(dm, list(n), oracle=oracle)
+    p = st["p"]
+    p.omega, p.sin_theta, p.cos_theta = omega, 0.6, 0.8
+    p.base_cutoff_density = 0.25  # buoyancy cutoff 5 * 0.25 = 1.25 cuts part of the density range
+    ex = make_episode_extras(st)
+    s = _scalar_like(st, oracle)
+    uedge = face_fabs(st["lo"], st["hi"], 1, 1, dm)
+    rng = np.random.default_rng(3)
+    for u in uedge:
+        u.a[...] = rng.uniform(-1, 1, size=u.shape)
+    out = []
+    for o in (gpu_ops, oracle):
+        f = Fab(st["lo"], st["hi"], 1, dm, dm=dm, fill=-777.0)
+        o.mk_vel_force(p, f, final, st["utilde"], uedge, st["w0"], ex["gpi"], s, p.rho_comp, _base_for_vel(st)["rho0_old"],
+                       ex["grav_old"], ex["w0_force"], True)
+        out.append(f)
+    check(out[0].a, out[1].a)
+
+
+@pytest.mark.parametrize("dm,n", [(2, (20, 14)), (3, (12, 9, 10))])
+@pytest.mark.parametrize("ept,pred,therm", [(1, True, True), (2, True, False), (0, False, True), (1, False, False)])
+def test_mkrhohforce(gpu_ops, oracle, dm, n, ept, pred, therm):
+    from synth import make_episode_extras
+
+    st = make_state(dm, list(n), enthalpy_pred_type=ept)
+    p, b = st["p"], st["base"]
+    p.base_cutoff_density_coord = p.nr - 3
+    ex = make_episode_extras(st)
+    out = []
+    for o in (gpu_ops, oracle):
+        f = st["force"].clone()
+        o.mkrhohforce(p, f, pred, ex["thermal"], st["umac"], ex["p0_old"], ex["p0_new"], b["rho0_old"], b["rho0_new"],
+                      ex["grav_nph"], ex["psi"], therm)
+        out.append(f)
+    check(out[0].a, out[1].a)
+
+
+@pytest.mark.parametrize("dm,n", [(2, (22, 15)), (3, (14, 9, 11))])
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
+def test_advance_premac(gpu_ops, oracle, dm, n, ppm_type, bcset):
+    """advance_premac.f90:21: ufull, mkutrans, mk_vel_force, addw0, velpred in one device-resident episode"""
+    from synth import make_episode_extras, make_vel_state
+
+    phys = {"periodic": None, "walls": VP_WALLS[dm], "inout": VP_INOUT[dm]}[bcset]
+    st = make_vel_state(dm, list(n), phys_bc=phys, ppm_type=ppm_type, oracle=oracle)
+    p = st["p"]
+    ex = make_episode_extras(st)
+    s = _scalar_like(st, oracle)
+    out = []
+    for o in (gpu_ops, oracle):
+        umac = face_fabs(st["lo"], st["hi"], 1, 1, dm, fill=-777.0)
+        o.advance_premac(p, st["utilde"], s, umac, ex["gpi"], st["w0"], ex["w0_force"], _base_for_vel(st)["rho0_old"],
+                         ex["grav_old"], st["adv_bc"], st["phys_bc"], st["pmask"])
+        out.append(umac)
+    for g, c in zip(*out):
+        check(g.a, c.a)
+
+
+@pytest.mark.parametrize("dm,n", [(2, (22, 15)), (3, (14, 9, 11))])
+@pytest.mark.parametrize("ppm_type,bds", [(0, 0), (1, 0), (2, 0), (1, 1)])
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
+@pytest.mark.parametrize("exact", [1, 0], ids=["exact", "fast"])
+def test_velocity_advance(gpu_ops, oracle, dm, n, ppm_type, bds, bcset, exact):
+    """velocity_advance.f90:16: forces, is_vel edge states of all dm components, update_velocity, ghost fill"""
+    from maestro_b200 import lib
+    from synth import fill_face_ghosts, make_episode_extras, make_vel_state
+
+    lib.set_option("exact", exact)
+    phys = {"periodic": None, "walls": VP_WALLS[dm], "inout": VP_INOUT[dm]}[bcset]
+    st = make_vel_state(dm, list(n), phys_bc=phys, ppm_type=ppm_type, bds_type=bds, do_sponge=1, oracle=oracle)
+    p = st["p"]
+    ex = make_episode_extras(st)
+    s = _scalar_like(st, oracle)
+    rng = np.random.default_rng(8)
+    umac0 = face_fabs(st["lo"], st["hi"], 1, 1, dm)
+    for u in umac0:
+        u.a[...] = rng.uniform(-1, 1, size=u.shape)
+    fill_face_ghosts(umac0, st["pmask"], dm)
+    out = []
+    for o in (gpu_ops, oracle):
+        umac = [u.clone() for u in umac0]
+        unew = st["utilde"].clone()
+        o.velocity_advance(p, st["utilde"], unew, s, ex["rhohalf"], umac, ex["gpi"], st["w0"], ex["w0_force"],
+                           _base_for_vel(st)["rho0_old"], ex["rho0_nph"], ex["grav_old"], ex["grav_nph"], ex["sponge"],
+                           st["adv_bc"], st["pmask"])
+        out.append([unew] + umac)
+    for g, c in zip(*out):
+        check(g.a, c.a, bitwise=bool(exact))
+
+
+@pytest.mark.parametrize("dm,n", [(2, (22, 15)), (3, (14, 9, 11))])
+@pytest.mark.parametrize("ept", [0, 1, 2])
+@pytest.mark.parametrize("which_step", [1, 2])
+@pytest.mark.parametrize("bcset,bds", [("periodic", 0), ("walls", 0), ("periodic", 1)])
+def test_enthalpy_advance(gpu_ops, oracle, dm, n, ept, which_step, bcset, bds):
+    """enthalpy_advance.f90:16 for predict_rhoh / predict_rhohprime / predict_h"""
+    from synth import make_episode_extras
+
+    phys = {"periodic": None, "walls": WALLS_3D if dm == 3 else WALLS_2D}[bcset]
+    st = make_state(dm, list(n), phys_bc=phys, enthalpy_pred_type=ept, bds_type=bds, ppm_type=2 if bcset == "walls" else 1)
+    p, b = st["p"], st["base"]
+    ex = make_episode_extras(st)
+    rng = np.random.default_rng(21)
+    sedge0 = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+    for f in sedge0:  # density edge states "left by density_advance"
+        f.a[p.rho_comp - 1] = 1.0 + rng.uniform(0.0, 0.5, size=f.a[0].shape)
+    out = []
+    for o in (gpu_ops, oracle):
+        sold = st["s"].clone()
+        oracle.fill_boundary(p, sold, 1, dm + 1, p.nscal, st["adv_bc"], st["pmask"])
+        snew = sold.clone()
+        umac = [u.clone() for u in st["umac"]]
+        sedge = [f.clone() for f in sedge0]
+        sflux = face_fabs(st["lo"], st["hi"], 0, p.nscal, dm)
+        force = st["force"].clone()
+        o.enthalpy_advance(p, which_step, sold, snew, sedge, sflux, force, ex["thermal"], umac, b["w0"], b["rho0_old"],
+                           b["rhoh0_old"], b["rho0_new"], b["rhoh0_new"], ex["p0_old"], ex["p0_new"], ex["psi"],
+                           ex["grav_old"], ex["grav_nph"], st["adv_bc"], st["pmask"])
+        out.append([sold, snew, force] + sedge + sflux + umac)
+    for g, c in zip(*out):
+        check(g.a, c.a)
