@@ -35,6 +35,9 @@
 #ifndef MGPU_FAST
 #define MGPU_FAST 0
 #endif
+#ifndef MGPU_FUSED_MINB
+#define MGPU_FUSED_MINB 3  // resident CTAs per SM the register allocation is tuned for
+#endif
 
 namespace mgpu {
 namespace {
@@ -122,7 +125,7 @@ __device__ __forceinline__ LineBC no_wall() {
 }
 
 template <int PPM, bool BC, bool FAST, int BX, int BY>
-__global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? 2 : 1) k_fused_edge(FusedArgs a) {
+__global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? MGPU_FUSED_MINB : 1) k_fused_edge(FusedArgs a) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = FusedSmem<H, BX, BY>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -197,8 +200,10 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? 2 : 1) k_fused_edge
     const double dz_m = dsvl_of(&sw[2], 1);  // cell q0-1
     dz_c = dsvl_of(&sw[3], 1);               // cell q0
     double e = 0.5 * (sw[3] + sw[2]) - (1.0 / 6.0) * (dz_c - dz_m);
-    e = dmax2(e, dmin2(sw[3], sw[2]));
-    ez_c = dmin2(e, dmax2(sw[3], sw[2]));
+    double elo, ehi;
+    dminmax(sw[3], sw[2], elo, ehi);
+    e = dmax2(e, elo);
+    ez_c = dmin2(e, ehi);
   }
   double slx_p = 0.0, srx_p = 0.0, sly_p = 0.0, sry_p = 0.0;  // plane q-1 face states
   double slz_q = 0.0, srz_q = 0.0;
@@ -271,8 +276,10 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? 2 : 1) k_fused_edge
         // instead of four and two.  Same expressions as dsvl_of / sedge1_of => same bits.
         const double dz_n = dsvl_of(&sw[H + 1], 1);
         double e = 0.5 * (sw[H + 1] + sw[H]) - (1.0 / 6.0) * (dz_n - dz_c);
-        e = dmax2(e, dmin2(sw[H + 1], sw[H]));
-        e = dmin2(e, dmax2(sw[H + 1], sw[H]));
+        double elo, ehi;
+        dminmax(sw[H + 1], sw[H], elo, ehi);
+        e = dmax2(e, elo);
+        e = dmin2(e, ehi);
         double smz = ez_c, spz = e;
         cw_limit(sw[H], smz, spz);
         ppm_trace<FAST>(sw[H], smz, spz, wq1, wq, tdz, hz, rel_eps, Ip, Im);

@@ -13,10 +13,16 @@
 namespace mgpu {
 
 __device__ __forceinline__ double sign1(double x) { return copysign(1.0, x); }
-// one DMNMX each instead of DSETP + 2 FSEL.  Same values as the reference's min/max for every non-NaN input
-// (a zero may come out with the other sign, which no comparison or product downstream can tell apart)
-__device__ __forceinline__ double dmin2(double a, double b) { return fmin(a, b); }
-__device__ __forceinline__ double dmax2(double a, double b) { return fmax(a, b); }
+// compare + select (DSETP + 2 FSEL): sm_100a has no fp64 min/max instruction -- fmin()/fmax() expand to a
+// NaN-aware sequence three times as long (measured: profiles/r01b_notes.md)
+__device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }
+// (min, max) of a pair from a single compare: same values as dmin2/dmax2
+__device__ __forceinline__ void dminmax(double a, double b, double& lo, double& hi) {
+  const bool c = a < b;
+  lo = c ? a : b;
+  hi = c ? b : a;
+}
 
 // what a line needs to know about its direction
 struct LineBC {
@@ -120,8 +126,10 @@ __device__ __forceinline__ double dsvl_of(const double* q, long st) {  // ppm.f9
 // edge value between cells f-1 and f; q points at s(f).  ppm.f90:1719-1724
 __device__ __forceinline__ double sedge1_of(const double* q, long st) {
   double e = 0.5 * (q[0] + q[-st]) - (1.0 / 6.0) * (dsvl_of(q, st) - dsvl_of(q - st, st));
-  e = dmax2(e, dmin2(q[0], q[-st]));
-  e = dmin2(e, dmax2(q[0], q[-st]));
+  double lo, hi;
+  dminmax(q[0], q[-st], lo, hi);
+  e = dmax2(e, lo);
+  e = dmin2(e, hi);
   return e;
 }
 // modified stencil on the first interior edge next to a wall: ppm.f90:1773-1781 (lo), :1823-1831 (hi)

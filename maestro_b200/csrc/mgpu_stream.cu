@@ -194,6 +194,11 @@ void sum_comps_dev(const DV& a, int dst, int c0, int ncomp) {
 }
 
 void set_dev(double* p, double v, long n) {
+  if (v == 0.0) {  // all-zero bit pattern: the copy engine's memset runs at full write bandwidth
+    MGPU_CUDA(cudaMemsetAsync(p, 0, (size_t)n * sizeof(double), ctx().stream));
+    count_launch();
+    return;
+  }
   k_set<<<nblocks(n, 256), 256, 0, ctx().stream>>>(p, v, n);
   MGPU_LAUNCH_CHECK();
 }
@@ -524,7 +529,7 @@ namespace mgpu {
 
 // DM: dimensionality; FAST: multiply by 1/dx instead of dividing (last-bit differences, <= 1e-12 relative)
 template <int DM, bool FAST>
-__global__ void __launch_bounds__(256) k_flux_update_all(FluxArgs a, UpdArgs u, int t0, int ntrac, int rho, double bcd) {
+__global__ void __launch_bounds__(256, 4) k_flux_update_all(FluxArgs a, UpdArgs u, int t0, int ntrac, int rho, double bcd) {
   int ix[3];
   if (!decode3(u.vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
@@ -543,8 +548,8 @@ __global__ void __launch_bounds__(256) k_flux_update_all(FluxArgs a, UpdArgs u, 
     se_st[d] = a.sedge[d].stride(d);
     sf_st[d] = a.sflux[d].stride(d);
     const long ou = a.umac[d].off(i, j, k);
-    vlo[d] = a.umac[d].p[ou];
-    vhi[d] = a.umac[d].p[ou + a.umac[d].stride(d)];
+    vlo[d] = __ldg(a.umac[d].p + ou);
+    vhi[d] = __ldg(a.umac[d].p + ou + a.umac[d].stride(d));
     last[d] = (ix[d] == u.vb.hi[d]);
     rdx[d] = FAST ? 1.0 / u.dx[d] : u.dx[d];
     double e_lo, e_hi;
@@ -562,11 +567,11 @@ __global__ void __launch_bounds__(256) k_flux_update_all(FluxArgs a, UpdArgs u, 
     } else {
       const double* pr = a.sedge[d].p + oe[d] + a.sedge[d].cs * a.rho;
       if (spt == MGPU_PREDICT_RHOPRIME_AND_X) {
-        r0lo[d] = e_lo + pr[0];
-        r0hi[d] = e_hi + pr[se_st[d]];
+        r0lo[d] = e_lo + __ldg(pr);
+        r0hi[d] = e_hi + __ldg(pr + se_st[d]);
       } else {
-        r0lo[d] = pr[0];
-        r0hi[d] = pr[se_st[d]];
+        r0lo[d] = __ldg(pr);
+        r0hi[d] = __ldg(pr + se_st[d]);
       }
     }
   }
@@ -592,11 +597,11 @@ __global__ void __launch_bounds__(256) k_flux_update_all(FluxArgs a, UpdArgs u, 
       const double* pe = a.sedge[d].p + oe[d] + a.sedge[d].cs * c;
       // vel * rhofac * X_edge (vel * X_edge for predict_rhoX): expression order of mkflux.f90:415-431
       if (spt == MGPU_PREDICT_RHOX) {
-        flo[d] = vlo[d] * pe[0];
-        fhi[d] = vhi[d] * pe[se_st[d]];
+        flo[d] = vlo[d] * __ldg(pe);
+        fhi[d] = vhi[d] * __ldg(pe + se_st[d]);
       } else {
-        flo[d] = vlo[d] * r0lo[d] * pe[0];
-        fhi[d] = vhi[d] * r0hi[d] * pe[se_st[d]];
+        flo[d] = vlo[d] * r0lo[d] * __ldg(pe);
+        fhi[d] = vhi[d] * r0hi[d] * __ldg(pe + se_st[d]);
       }
       double* pf = a.sflux[d].p + of[d] + a.sflux[d].cs * c;
       pf[0] = flo[d];
@@ -618,8 +623,8 @@ __global__ void __launch_bounds__(256) k_flux_update_all(FluxArgs a, UpdArgs u, 
       divterm = (fhi[0] - flo[0]) / rdx[0] + (fhi[1] - flo[1]) / rdx[1];
       if (DM == 3) divterm = divterm + (fhi[DM - 1] - flo[DM - 1]) / rdx[DM - 1];
     }
-    const double so = u.sold.p[oso + u.sold.cs * c];
-    const double sn = so + u.dt * (-divterm + u.force.p[ofo + u.force.cs * c]);
+    const double so = __ldg(u.sold.p + oso + u.sold.cs * c);
+    const double sn = so + u.dt * (-divterm + __ldg(u.force.p + ofo + u.force.cs * c));
     u.snew.p[osn + u.snew.cs * c] = sn;
     if (n < nspec) {
       rnew = rnew + (sn - so);
