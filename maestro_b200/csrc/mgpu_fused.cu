@@ -42,18 +42,21 @@
 namespace mgpu {
 namespace {
 
+// Shared-memory layout: the s tile, then planes of one common shape (BY+1 rows of pitch BX+1) so that every
+// access is [per-thread base + compile-time constant]: six single planes, then two parity blocks of eleven planes.
 template <int H, int BX, int BY>
 struct FusedSmem {
   static constexpr int SP = BX + 2 * H;  // pitch of the s tile
   static constexpr int SN = (BY + 2 * H) * SP;
-  double S[SN];
-  double IPX[BY][BX], IMX[BY][BX], IPY[BY][BX], IMY[BY][BX];
-  double Z[2][BY][BX], SHX[2][BY][BX], SHY[2][BY][BX];
-  double XY[2][BY][BX], YX[2][BY][BX], ZX[2][BY][BX], ZY[2][BY][BX];
-  double XZ[BY][BX], YZ[BY][BX];
-  double U[2][BY][BX + 1], V[2][BY + 1][BX], W[2][BY][BX];
-  double FRC[2][BY][BX];
+  static constexpr int P = BX + 1;        // pitch of every other plane
+  static constexpr int PL = (BY + 1) * P; // doubles per plane
+  enum { IPX = 0, IMX, IPY, IMY, XZ, YZ, NSINGLE };
+  enum { Z = 0, SHX, SHY, XY, YX, ZX, ZY, U, V, W, FRC, NPAR };
+  static constexpr int TOTAL = SN + (NSINGLE + 2 * NPAR) * PL;
+  double buf[TOTAL];
 };
+// plane A of block B (a double* already offset to this thread's cell) at row offset dy, column offset dx
+#define SMP(B, A, dy, dx) (B)[SM::A * SM::PL + (dy) * SM::P + (dx)]
 
 template <bool BC>
 __device__ __forceinline__ void bc_states(const FusedArgs& a, int d, int f, double s_lo_m1, double s_lo_0,
@@ -125,15 +128,17 @@ __device__ __forceinline__ LineBC no_wall() {
 }
 
 template <int PPM, bool BC, bool FAST, int BX, int BY>
-__global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? MGPU_FUSED_MINB : 1) k_fused_edge(FusedArgs a) {
+__global__ void __launch_bounds__(BX* BY, MGPU_FUSED_MINB) k_fused_edge(FusedArgs a) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = FusedSmem<H, BX, BY>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  double* const sS = reinterpret_cast<double*>(smem_raw);
   constexpr int SP = SM::SP;
   constexpr int NT = (SM::SN + BX * BY - 1) / (BX * BY);  // s-tile elements per thread
 
   const int tx = threadIdx.x, ty = threadIdx.y;
+  double* const sg = sS + SM::SN + ty * SM::P + tx;  // this thread's cell in the single planes
+  double* const pb = sg + SM::NSINGLE * SM::PL;      // ... in parity block 0
   const int ibase = a.lo[0] - 1 + blockIdx.x * (BX - 2);
   const int jbase = a.lo[1] - 1 + blockIdx.y * (BY - 2);
   const int i = ibase + tx, j = jbase + ty;
@@ -213,26 +218,32 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? MGPU_FUSED_MINB : 1
   // software prefetch: the loads of plane q+1 are issued right after the first barrier of step q, so the
   // global-memory latency overlaps the compute of step q instead of stalling the smem stores of step q+1
   double pre_s, pre_S[NT], pre_u, pre_u1 = 0.0, pre_v, pre_v1 = 0.0, pre_w, pre_w1, pre_f;
-  auto prefetch = [&](int q) {
-    pre_s = ps[(long)(q + H) * s_sz];
-    const long qo = (long)q * s_sz;
+  // running plane offsets (advanced by one plane per prefetch: no 64-bit multiplies in the march)
+  long o_s = (long)(kz0 - 1) * s_sz, o_u = (long)(kz0 - 1) * u_sz, o_v = (long)(kz0 - 1) * v_sz,
+       o_w = (long)(kz0 - 1) * w_sz, o_f = (long)(kz0 - 1) * f_sz;
+  const long hs = (long)H * s_sz;
+  auto prefetch = [&]() {  // loads plane q, where o_* address plane q; then advances to q+1
+    pre_s = ps[o_s + hs];
 #pragma unroll
     for (int m = 0; m < NT; ++m) {
       const int t = ty * BX + tx + m * BX * BY;
-      pre_S[m] = (t < SM::SN) ? s0[t_off[m] + qo] : 0.0;
+      pre_S[m] = (t < SM::SN) ? s0[t_off[m] + o_s] : 0.0;
     }
-    pre_u = pu[(long)q * u_sz];
-    if (tx == BX - 1) pre_u1 = pu1[(long)q * u_sz];
-    pre_v = pv[(long)q * v_sz];
-    if (ty == BY - 1) pre_v1 = pv1[(long)q * v_sz];
-    pre_w1 = pw[(long)(q + 1) * w_sz];
-    pre_f = pf[(long)q * f_sz];
+    pre_u = pu[o_u];
+    if (tx == BX - 1) pre_u1 = pu1[o_u];
+    pre_v = pv[o_v];
+    if (ty == BY - 1) pre_v1 = pv1[o_v];
+    pre_w1 = pw[o_w + w_sz];
+    pre_f = pf[o_f];
+    o_s += s_sz; o_u += u_sz; o_v += v_sz; o_w += w_sz; o_f += f_sz;
   };
-  prefetch(kz0 - 1);
-  pre_w = pw[(long)(kz0 - 1) * w_sz];
+  pre_w = pw[o_w];
+  prefetch();
 
   for (int q = kz0 - 1; q <= kz1 + 1; ++q) {
-    const int par = q & 1, opar = par ^ 1;
+    const int par = q & 1;
+    double* const cur = pb + par * (SM::NPAR * SM::PL);        // parity block of plane q
+    double* const prv = pb + (par ^ 1) * (SM::NPAR * SM::PL);  // parity block of plane q-1
     __syncthreads();  // previous step's readers of U/V/W/FRC[par] and S are done
     // ---- S0: publish the prefetched plane q ------------------------------------------------------
 #pragma unroll
@@ -241,35 +252,35 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? MGPU_FUSED_MINB : 1
 #pragma unroll
     for (int m = 0; m < NT; ++m) {
       const int t = ty * BX + tx + m * BX * BY;
-      if (t < SM::SN) sm.S[t] = pre_S[m];
+      if (t < SM::SN) sS[t] = pre_S[m];
     }
-    sm.U[par][ty][tx] = pre_u;
-    if (tx == BX - 1) sm.U[par][ty][BX] = pre_u1;
-    sm.V[par][ty][tx] = pre_v;
-    if (ty == BY - 1) sm.V[par][BY][tx] = pre_v1;
-    sm.W[par][ty][tx] = pre_w;
+    SMP(cur, U, 0, 0) = pre_u;
+    if (tx == BX - 1) SMP(cur, U, 0, 1) = pre_u1;
+    SMP(cur, V, 0, 0) = pre_v;
+    if (ty == BY - 1) SMP(cur, V, 1, 0) = pre_v1;
+    SMP(cur, W, 0, 0) = pre_w;
     const double wq1 = pre_w1;
     const double f_q = pre_f;
-    sm.FRC[par][ty][tx] = f_q;
+    SMP(cur, FRC, 0, 0) = f_q;
     pre_w = pre_w1;
     __syncthreads();
-    if (q < kz1 + 1) prefetch(q + 1);
+    if (q < kz1 + 1) prefetch();
 
     const double s_q = sw[H];
-    const double uq = sm.U[par][ty][tx], uq1 = sm.U[par][ty][tx + 1];
-    const double vq = sm.V[par][ty][tx], vq1 = sm.V[par][ty + 1][tx];
-    const double wq = sm.W[par][ty][tx];
-    const double* c = &sm.S[(ty + H) * SP + tx + H];
+    const double uq = SMP(cur, U, 0, 0), uq1 = SMP(cur, U, 0, +1);
+    const double vq = SMP(cur, V, 0, 0), vq1 = SMP(cur, V, +1, 0);
+    const double wq = SMP(cur, W, 0, 0);
+    const double* c = &sS[(ty + H) * SP + tx + H];
 
     // ---- S1: P1(q) ---------------------------------------------------------------------------
     {
       double Ip, Im;
       cell_states<FAST>(PPM, a.slope_order, c, 1, i, bx, uq1, uq, tdx, hx, rel_eps, Ip, Im);
-      sm.IPX[ty][tx] = Ip;
-      sm.IMX[ty][tx] = Im;
+      SMP(sg, IPX, 0, 0) = Ip;
+      SMP(sg, IMX, 0, 0) = Im;
       cell_states<FAST>(PPM, a.slope_order, c, SP, j, by, vq1, vq, tdy, hy, rel_eps, Ip, Im);
-      sm.IPY[ty][tx] = Ip;
-      sm.IMY[ty][tx] = Im;
+      SMP(sg, IPY, 0, 0) = Ip;
+      SMP(sg, IMY, 0, 0) = Im;
       if constexpr (PPM == 1 && !BC) {
         // z marches with the thread: the van Leer slope of cell q and the edge value on face q were computed by
         // the previous step (as those of cell q+1 / face q+1), so each step evaluates one slope and one edge
@@ -293,83 +304,83 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? MGPU_FUSED_MINB : 1
       srz_q = Im;
       Ipz_prev = Ip;
       bc_states<BC>(a, 2, q, s_p, s_q, s_q, 0, slz_q, srz_q);
-      sm.Z[par][ty][tx] = riemann(slz_q, srz_q, wq, rel_eps);
+      SMP(cur, Z, 0, 0) = riemann(slz_q, srz_q, wq, rel_eps);
     }
     __syncthreads();
 
     // ---- S2: normal-predictor face states in plane q ------------------------------------------
     double slx_q = 0.0, srx_q = 0.0, sly_q = 0.0, sry_q = 0.0;
     if (tx >= 1) {
-      slx_q = sm.IPX[ty][tx - 1];
-      srx_q = sm.IMX[ty][tx];
+      slx_q = SMP(sg, IPX, 0, -1);
+      srx_q = SMP(sg, IMX, 0, 0);
       bc_states<BC>(a, 0, i, c[-1], 0.0, s_q, 0, slx_q, srx_q);
-      sm.SHX[par][ty][tx] = riemann(slx_q, srx_q, uq, rel_eps);
+      SMP(cur, SHX, 0, 0) = riemann(slx_q, srx_q, uq, rel_eps);
     }
     if (ty >= 1) {
-      sly_q = sm.IPY[ty - 1][tx];
-      sry_q = sm.IMY[ty][tx];
+      sly_q = SMP(sg, IPY, -1, 0);
+      sry_q = SMP(sg, IMY, 0, 0);
       bc_states<BC>(a, 1, j, c[-SP], 0.0, s_q, 0, sly_q, sry_q);
-      sm.SHY[par][ty][tx] = riemann(sly_q, sry_q, vq, rel_eps);
+      SMP(cur, SHY, 0, 0) = riemann(sly_q, sry_q, vq, rel_eps);
     }
     __syncthreads();
 
     // ---- S3: transverse states ------------------------------------------------------------------
     // T1(q): x-face corrected by y, y-face corrected by x
     if (tx >= 1 && ty <= BY - 2) {
-      double l = slx_q - c6y * (sm.V[par][ty + 1][tx - 1] + sm.V[par][ty][tx - 1]) *
-                             (sm.SHY[par][ty + 1][tx - 1] - sm.SHY[par][ty][tx - 1]);
-      double r = srx_q - c6y * (vq1 + vq) * (sm.SHY[par][ty + 1][tx] - sm.SHY[par][ty][tx]);
+      double l = slx_q - c6y * (SMP(cur, V, +1, -1) + SMP(cur, V, 0, -1)) *
+                             (SMP(cur, SHY, +1, -1) - SMP(cur, SHY, 0, -1));
+      double r = srx_q - c6y * (vq1 + vq) * (SMP(cur, SHY, +1, 0) - SMP(cur, SHY, 0, 0));
       bc_states<BC>(a, 0, i, c[-1], 0.0, s_q, 1, l, r);
-      sm.XY[par][ty][tx] = riemann(l, r, uq, rel_eps);
+      SMP(cur, XY, 0, 0) = riemann(l, r, uq, rel_eps);
     }
     if (ty >= 1 && tx <= BX - 2) {
-      double l = sly_q - c6x * (sm.U[par][ty - 1][tx + 1] + sm.U[par][ty - 1][tx]) *
-                             (sm.SHX[par][ty - 1][tx + 1] - sm.SHX[par][ty - 1][tx]);
-      double r = sry_q - c6x * (uq1 + uq) * (sm.SHX[par][ty][tx + 1] - sm.SHX[par][ty][tx]);
+      double l = sly_q - c6x * (SMP(cur, U, -1, +1) + SMP(cur, U, -1, 0)) *
+                             (SMP(cur, SHX, -1, +1) - SMP(cur, SHX, -1, 0));
+      double r = sry_q - c6x * (uq1 + uq) * (SMP(cur, SHX, 0, +1) - SMP(cur, SHX, 0, 0));
       bc_states<BC>(a, 1, j, c[-SP], 0.0, s_q, 1, l, r);
-      sm.YX[par][ty][tx] = riemann(l, r, vq, rel_eps);
+      SMP(cur, YX, 0, 0) = riemann(l, r, vq, rel_eps);
     }
     if (q >= kz0) {
       // T3(q): z-face q corrected by x / by y (left cell = plane q-1, right cell = plane q)
       if (tx <= BX - 2) {
-        double l = slz_q - c6x * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) *
-                               (sm.SHX[opar][ty][tx + 1] - sm.SHX[opar][ty][tx]);
-        double r = srz_q - c6x * (uq1 + uq) * (sm.SHX[par][ty][tx + 1] - sm.SHX[par][ty][tx]);
+        double l = slz_q - c6x * (SMP(prv, U, 0, +1) + SMP(prv, U, 0, 0)) *
+                               (SMP(prv, SHX, 0, +1) - SMP(prv, SHX, 0, 0));
+        double r = srz_q - c6x * (uq1 + uq) * (SMP(cur, SHX, 0, +1) - SMP(cur, SHX, 0, 0));
         bc_states<BC>(a, 2, q, s_p, s_q, s_q, 1, l, r);
-        sm.ZX[par][ty][tx] = riemann(l, r, wq, rel_eps);
+        SMP(cur, ZX, 0, 0) = riemann(l, r, wq, rel_eps);
       }
       if (ty <= BY - 2) {
-        double l = slz_q - c6y * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) *
-                               (sm.SHY[opar][ty + 1][tx] - sm.SHY[opar][ty][tx]);
-        double r = srz_q - c6y * (vq1 + vq) * (sm.SHY[par][ty + 1][tx] - sm.SHY[par][ty][tx]);
+        double l = slz_q - c6y * (SMP(prv, V, +1, 0) + SMP(prv, V, 0, 0)) *
+                               (SMP(prv, SHY, +1, 0) - SMP(prv, SHY, 0, 0));
+        double r = srz_q - c6y * (vq1 + vq) * (SMP(cur, SHY, +1, 0) - SMP(cur, SHY, 0, 0));
         bc_states<BC>(a, 2, q, s_p, s_q, s_q, 1, l, r);
-        sm.ZY[par][ty][tx] = riemann(l, r, wq, rel_eps);
+        SMP(cur, ZY, 0, 0) = riemann(l, r, wq, rel_eps);
       }
     }
     if (q >= kz0 + 1) {
       // T2(q-1): x- and y-faces of plane q-1 corrected by z.  w on z-faces q-1 (opar) and q (par).
       if (tx >= 1) {
-        double l = slx_p - c6z * (sm.W[par][ty][tx - 1] + sm.W[opar][ty][tx - 1]) *
-                               (sm.Z[par][ty][tx - 1] - sm.Z[opar][ty][tx - 1]);
-        double r = srx_p - c6z * (wq + sm.W[opar][ty][tx]) * (sm.Z[par][ty][tx] - sm.Z[opar][ty][tx]);
+        double l = slx_p - c6z * (SMP(cur, W, 0, -1) + SMP(prv, W, 0, -1)) *
+                               (SMP(cur, Z, 0, -1) - SMP(prv, Z, 0, -1));
+        double r = srx_p - c6z * (wq + SMP(prv, W, 0, 0)) * (SMP(cur, Z, 0, 0) - SMP(prv, Z, 0, 0));
         if (BC) {
           // s(is-1) of plane q-1 for EXT_DIR: re-read from global (rare branch)
           double slm = 0.0;
           if (i == a.lo[0] && a.bclo[0] == MGPU_BC_EXT_DIR) slm = a.s(i - 1, jc, q - 1);
           bc_states<BC>(a, 0, i, slm, 0.0, s_p, 1, l, r);
         }
-        sm.XZ[ty][tx] = riemann(l, r, sm.U[opar][ty][tx], rel_eps);
+        SMP(sg, XZ, 0, 0) = riemann(l, r, SMP(prv, U, 0, 0), rel_eps);
       }
       if (ty >= 1) {
-        double l = sly_p - c6z * (sm.W[par][ty - 1][tx] + sm.W[opar][ty - 1][tx]) *
-                               (sm.Z[par][ty - 1][tx] - sm.Z[opar][ty - 1][tx]);
-        double r = sry_p - c6z * (wq + sm.W[opar][ty][tx]) * (sm.Z[par][ty][tx] - sm.Z[opar][ty][tx]);
+        double l = sly_p - c6z * (SMP(cur, W, -1, 0) + SMP(prv, W, -1, 0)) *
+                               (SMP(cur, Z, -1, 0) - SMP(prv, Z, -1, 0));
+        double r = sry_p - c6z * (wq + SMP(prv, W, 0, 0)) * (SMP(cur, Z, 0, 0) - SMP(prv, Z, 0, 0));
         if (BC) {
           double slm = 0.0;
           if (j == a.lo[1] && a.bclo[1] == MGPU_BC_EXT_DIR) slm = a.s(ic, j - 1, q - 1);
           bc_states<BC>(a, 1, j, slm, 0.0, s_p, 1, l, r);
         }
-        sm.YZ[ty][tx] = riemann(l, r, sm.V[opar][ty][tx], rel_eps);
+        SMP(sg, YZ, 0, 0) = riemann(l, r, SMP(prv, V, 0, 0), rel_eps);
       }
     }
     __syncthreads();
@@ -379,11 +390,11 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? MGPU_FUSED_MINB : 1
     const bool iny = (ty >= 1 && ty <= BY - 2 && j <= a.hi[1]);
     if (q >= kz0 && inx && iny) {
       // F_z(q): transverse terms x then y, left cell plane q-1 (opar), right cell plane q (par)
-      double el = slz_q - c4x * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) * (sm.XY[opar][ty][tx + 1] - sm.XY[opar][ty][tx]) -
-                  c4y * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) * (sm.YX[opar][ty + 1][tx] - sm.YX[opar][ty][tx]) +
+      double el = slz_q - c4x * (SMP(prv, U, 0, +1) + SMP(prv, U, 0, 0)) * (SMP(prv, XY, 0, +1) - SMP(prv, XY, 0, 0)) -
+                  c4y * (SMP(prv, V, +1, 0) + SMP(prv, V, 0, 0)) * (SMP(prv, YX, +1, 0) - SMP(prv, YX, 0, 0)) +
                   dt2 * f_p;
-      double er = srz_q - c4x * (uq1 + uq) * (sm.XY[par][ty][tx + 1] - sm.XY[par][ty][tx]) -
-                  c4y * (vq1 + vq) * (sm.YX[par][ty + 1][tx] - sm.YX[par][ty][tx]) + dt2 * f_q;
+      double er = srz_q - c4x * (uq1 + uq) * (SMP(cur, XY, 0, +1) - SMP(cur, XY, 0, 0)) -
+                  c4y * (vq1 + vq) * (SMP(cur, YX, +1, 0) - SMP(cur, YX, 0, 0)) + dt2 * f_q;
       double e = riemann(el, er, wq, rel_eps);
       if (BC) e = final_bc(a, 2, q, e, el, er, s_p, s_q);
       if (q <= kz1 || q == a.hi[2] + 1) a.sedge[2](i, j, q) = e;
@@ -392,12 +403,12 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? MGPU_FUSED_MINB : 1
       const int k = q - 1;
       // F_xy(k): x-face (i,j,k): transverse terms y (simhyz) then z (simhzy)
       if (tx >= 1 && (tx <= BX - 2 || i == a.hi[0] + 1) && iny) {
-        double el = slx_p - c4y * (sm.V[opar][ty + 1][tx - 1] + sm.V[opar][ty][tx - 1]) * (sm.YZ[ty + 1][tx - 1] - sm.YZ[ty][tx - 1]) -
-                    c4z * (sm.W[par][ty][tx - 1] + sm.W[opar][ty][tx - 1]) * (sm.ZY[par][ty][tx - 1] - sm.ZY[opar][ty][tx - 1]) +
-                    dt2 * sm.FRC[opar][ty][tx - 1];
-        double er = srx_p - c4y * (sm.V[opar][ty + 1][tx] + sm.V[opar][ty][tx]) * (sm.YZ[ty + 1][tx] - sm.YZ[ty][tx]) -
-                    c4z * (wq + sm.W[opar][ty][tx]) * (sm.ZY[par][ty][tx] - sm.ZY[opar][ty][tx]) + dt2 * f_p;
-        double e = riemann(el, er, sm.U[opar][ty][tx], rel_eps);
+        double el = slx_p - c4y * (SMP(prv, V, +1, -1) + SMP(prv, V, 0, -1)) * (SMP(sg, YZ, +1, -1) - SMP(sg, YZ, 0, -1)) -
+                    c4z * (SMP(cur, W, 0, -1) + SMP(prv, W, 0, -1)) * (SMP(cur, ZY, 0, -1) - SMP(prv, ZY, 0, -1)) +
+                    dt2 * SMP(prv, FRC, 0, -1);
+        double er = srx_p - c4y * (SMP(prv, V, +1, 0) + SMP(prv, V, 0, 0)) * (SMP(sg, YZ, +1, 0) - SMP(sg, YZ, 0, 0)) -
+                    c4z * (wq + SMP(prv, W, 0, 0)) * (SMP(cur, ZY, 0, 0) - SMP(prv, ZY, 0, 0)) + dt2 * f_p;
+        double e = riemann(el, er, SMP(prv, U, 0, 0), rel_eps);
         if (BC && (i == a.lo[0] || i == a.hi[0] + 1)) {
           const double sl_c = (a.bclo[0] == MGPU_BC_EXT_DIR && i == a.lo[0]) ? a.s(i - 1, j, k) : 0.0;
           e = final_bc(a, 0, i, e, el, er, sl_c, s_p);
@@ -406,12 +417,12 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY <= 256) ? MGPU_FUSED_MINB : 1
       }
       // y-face (i,j,k): transverse terms x (simhxz) then z (simhzx)
       if (ty >= 1 && (ty <= BY - 2 || j == a.hi[1] + 1) && inx) {
-        double el = sly_p - c4x * (sm.U[opar][ty - 1][tx + 1] + sm.U[opar][ty - 1][tx]) * (sm.XZ[ty - 1][tx + 1] - sm.XZ[ty - 1][tx]) -
-                    c4z * (sm.W[par][ty - 1][tx] + sm.W[opar][ty - 1][tx]) * (sm.ZX[par][ty - 1][tx] - sm.ZX[opar][ty - 1][tx]) +
-                    dt2 * sm.FRC[opar][ty - 1][tx];
-        double er = sry_p - c4x * (sm.U[opar][ty][tx + 1] + sm.U[opar][ty][tx]) * (sm.XZ[ty][tx + 1] - sm.XZ[ty][tx]) -
-                    c4z * (wq + sm.W[opar][ty][tx]) * (sm.ZX[par][ty][tx] - sm.ZX[opar][ty][tx]) + dt2 * f_p;
-        double e = riemann(el, er, sm.V[opar][ty][tx], rel_eps);
+        double el = sly_p - c4x * (SMP(prv, U, -1, +1) + SMP(prv, U, -1, 0)) * (SMP(sg, XZ, -1, +1) - SMP(sg, XZ, -1, 0)) -
+                    c4z * (SMP(cur, W, -1, 0) + SMP(prv, W, -1, 0)) * (SMP(cur, ZX, -1, 0) - SMP(prv, ZX, -1, 0)) +
+                    dt2 * SMP(prv, FRC, -1, 0);
+        double er = sry_p - c4x * (SMP(prv, U, 0, +1) + SMP(prv, U, 0, 0)) * (SMP(sg, XZ, 0, +1) - SMP(sg, XZ, 0, 0)) -
+                    c4z * (wq + SMP(prv, W, 0, 0)) * (SMP(cur, ZX, 0, 0) - SMP(prv, ZX, 0, 0)) + dt2 * f_p;
+        double e = riemann(el, er, SMP(prv, V, 0, 0), rel_eps);
         if (BC && (j == a.lo[1] || j == a.hi[1] + 1)) {
           const double sl_c = (a.bclo[1] == MGPU_BC_EXT_DIR && j == a.lo[1]) ? a.s(i, j - 1, k) : 0.0;
           e = final_bc(a, 1, j, e, el, er, sl_c, s_p);
