@@ -659,6 +659,7 @@ int mgpu_set_option(const char* key, int value) {
   if (k == "fused") g_opt_fused = value;
   else if (k == "kchunk") g_opt_kchunk = value;
   else if (k == "exact") g_opt_exact = value;
+  else if (k == "fused_variant") fused_edge_set_variant(value);
   else throw Error("mgpu_set_option: unknown key " + k);
   MGPU_CATCH
 }

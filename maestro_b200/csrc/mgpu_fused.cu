@@ -474,6 +474,9 @@ void fused_edge_launch_exact(const FusedArgs& a, int ppm_type, bool bc, int nx, 
 }
 
 #if !MGPU_FAST
+static int g_variant = 1;
+void fused_edge_set_variant(int v) { g_variant = v; }
+
 bool fused_edge_supported(const mgpu_params& P, bool is_cons) {
   return P.dm == 3 && P.bds_type == 0 && P.ppm_trace_forces == 0 && !is_cons;
 }
@@ -507,6 +510,8 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
   if (a.kchunk > nz) a.kchunk = nz;
   if (exact)
     fused_edge_launch_exact(a, P.ppm_type, any_bc, nx, ny, nz);
+  else if (!any_bc && g_variant == 1)
+    fused_edge2_launch(a, P.ppm_type, nx, ny, nz);
   else
     fused_edge_launch_fast(a, P.ppm_type, any_bc, nx, ny, nz);
 }

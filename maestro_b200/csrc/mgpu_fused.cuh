@@ -9,6 +9,10 @@
 #define MGPU_FUSED_BY 8
 #endif
 
+#ifndef MGPU_FUSED2_BY
+#define MGPU_FUSED2_BY 8
+#endif
+
 namespace mgpu {
 
 struct FusedArgs {
@@ -32,5 +36,9 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
                     int ng_f, int kchunk, bool exact);
 void fused_edge_launch_exact(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
 void fused_edge_launch_fast(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
+// second design (mgpu_fused2.cu): upwind-first, all faces INTERIOR, FAST arithmetic only
+void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz);
+// 0: always the literal kernel; 1 (default): the upwind-first kernel wherever it applies
+void fused_edge_set_variant(int v);
 
 }  // namespace mgpu

@@ -1,0 +1,466 @@
+// Fused 3-D edge-state kernel, second design ("upwind-first"): make_edge_scal_3d
+// (Source/make_edge_scal.f90:677) + ppm_3d / slope (Source/ppm.f90:1629, Source/slope.f90) for one
+// component in one launch, for boxes whose six faces are INTERIOR (periodic / box-box), FAST arithmetic
+// (FMA contraction, dt/dx folded; <= 1e-12 relative to the reference, not bit-identical).
+//
+// Why a second design.  The first fused kernel (mgpu_fused.cu) evaluates the reference literally: at every
+// face and for each of the 12 Riemann problems per cell it forms the left AND the right state and then lets
+// the upwind test (make_edge_scal.f90:881-883) throw one away.  ncu showed that kernel is bound by
+// instruction issue and the fp64 pipe, not by HBM (profiles/r01b_tuned.md).  All Riemann problems on one face
+// share one velocity, so when |u| > rel_eps the whole chain
+//     Ip/Im -> simh -> simhxy/simhxz -> sedge      (make_edge_scal.f90:861-1560)
+// of a face only ever uses quantities of its UPWIND cell.  This kernel therefore
+//   * picks the upwind cell of each face first and traces ONE parabola end to that face (ppm.f90:2233-2251),
+//   * writes every transverse correction as  face_state - c * T(upwind cell)  where
+//       T_x = (u(i+1)+u(i)) (simhx(i+1)-simhx(i)),  T_y, T_z likewise
+//     are CELL-centred and evaluated once per cell (the reference evaluates each of them four times),
+//   * the final states likewise as  simh - G(upwind cell),  G_x = c4y vs dy(simhyz) + c4z ws dz(simhzy) - dt/2 f.
+//   * faces with |u| <= rel_eps (the reference averages left and right) take the same formulas with the mean
+//     of the two neighbouring cells' T / G: identical in exact arithmetic, one rounding apart in fp64.
+// About 1/3 of the fp64 operations of the literal form.
+//
+// Schedule.  One thread per (i,j) column marching in z, BX x BY columns per CTA with a one-cell halo (only
+// the interior (BX-2) x (BY-2) columns store results).  Work alternates between CELL phases and FACE phases;
+// three planes are in flight (software pipeline) so that one step costs only two barriers:
+//
+//   step t, cell phase:  C1(t)   limited parabolas of cell plane t in x,y (-> smem) and z (registers)
+//                        Z(t)    simhz on z-face t                 (registers: z neighbours are this thread's)
+//                        C2(t-1) T_x, T_y, T_z of plane t-1        (-> smem), simhzx/simhzy(t-1) (registers)
+//                        C3(t-2) G_x, G_y of plane t-2             (-> smem), G_z and sedgez(t-2) -> HBM
+//   step t, face phase:  F1(t)   simhx, simhy of plane t           (-> smem)
+//                        F2(t-1) simhxy, simhxz, simhyx, simhyz    (-> smem)
+//                        F3(t-2) sedgex, sedgey of plane t-2       -> HBM
+//                        publish the s tile of plane t+1 (register-prefetched one step ahead)
+#include "mgpu_fused.cuh"
+#include "mgpu_recon.cuh"
+
+#ifndef MGPU_FUSED2_MINB
+#define MGPU_FUSED2_MINB 2
+#endif
+
+namespace mgpu {
+namespace {
+
+template <int H, int BX, int BY>
+struct Smem2 {
+  static constexpr int SP = BX + 2 * H;  // pitch of the s tile
+  static constexpr int SN = (BY + 2 * H) * SP;
+  static constexpr int P = BX;             // pitch of every other plane
+  static constexpr int PL = (BY + 1) * P;  // doubles per plane (one spare row: reads at row+1 stay inside)
+  enum { AX0 = 0, AX1, AY0, AY1, TX, TY, TZ, GX, GY, SHX, SHY, XY, YX, XZ, YZ, NPL };
+  static constexpr int TOTAL = 2 * SN + NPL * PL;
+  static constexpr int NHALO = SN - BX * BY;  // s-tile elements outside the CTA's own columns
+  static constexpr int NH = (NHALO + BX * BY - 1) / (BX * BY);
+};
+#define PLN(A, dy, dx) pl[SM::A * SM::PL + (dy) * SM::P + (dx)]
+
+// one traced state on a face from the parabola (a0=sm, a1=sp) / slope (a0) of its upwind cell.
+// a = u dt/h (signed CFL number), up = (u > 0): the upwind cell is the face's low neighbour.
+//   up : Ip = sp - s/2 (sp - sm - (1 - 2/3 s) s6),  s = |a|      (ppm.f90:2236-2241)
+//  !up : Im = sm + s/2 (sp - sm + (1 - 2/3 s) s6)                (ppm.f90:2244-2249)
+// both are  base - a/2 (d + m s6),  m = 2/3 a -+ 1
+template <int PPM>
+__device__ __forceinline__ double trace1(double a0, double a1, double sc, double a, bool up) {
+  if constexpr (PPM == 0) {  // make_edge_scal.f90:818-819
+    return fma((up ? 0.5 : -0.5) - 0.5 * a, a0, sc);
+  } else {
+    const double s6 = 6.0 * sc - 3.0 * (a0 + a1);
+    const double d = a1 - a0;
+    const double m = fma(2.0 / 3.0, a, up ? -1.0 : 1.0);
+    return fma(-0.5 * a, fma(m, s6, d), up ? a1 : a0);
+  }
+}
+// face with |u| <= rel_eps: the reference's 0.5*(l+r) with l = Ip(low cell), r = Im(high cell)
+template <int PPM>
+__device__ __forceinline__ double trace_slow(double a0l, double scl, double a0r, double scr, double a) {
+  if constexpr (PPM == 0) {
+    return 0.5 * (fma(0.5 - 0.5 * a, a0l, scl) + fma(-0.5 - 0.5 * a, a0r, scr));
+  } else {
+    return 0.5 * (scl + scr);  // Ip = Im = s when the velocity does not exceed rel_eps (ppm.f90:2240,2248)
+  }
+}
+
+// limited parabola (PPM>=1: a0 = sm, a1 = sp) or slope (PPM==0: a0) of one cell along a line in memory
+template <int PPM>
+__device__ __forceinline__ void cell_par(const double* q, int st, int slope_order, const LineBC& nb, double& a0,
+                                         double& a1) {
+  if constexpr (PPM == 0) {
+    a0 = slope_cell(q, st, 0, nb, slope_order);
+    a1 = 0.0;
+  } else if constexpr (PPM == 1) {
+    a0 = sedge1_of(q, st);
+    a1 = sedge1_of(q + st, st);
+    cw_limit(q[0], a0, a1);
+  } else {
+    ppm2_cell(q, st, 0, nb, a0, a1);
+  }
+}
+
+__device__ __forceinline__ LineBC no_wall2() {
+  LineBC b;
+  b.lo = -(1 << 30);
+  b.hi = (1 << 30);
+  b.wlo = false;
+  b.whi = false;
+  b.relimit_last = b.lo + 2;
+  b.hi_reset = true;
+  return b;
+}
+
+template <int PPM, int BX, int BY>
+__global__ void __launch_bounds__(BX* BY, MGPU_FUSED2_MINB) k_fused_edge2(FusedArgs a) {
+  constexpr int H = (PPM == 2) ? 3 : 2;
+  using SM = Smem2<H, BX, BY>;
+  constexpr int SP = SM::SP, P = SM::P;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* const sS = reinterpret_cast<double*>(smem_raw);  // two s tiles
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * BX + tx;
+  double* const pl = sS + 2 * SM::SN + ty * P + tx;  // this thread's cell in plane 0
+  const int sc_idx = (ty + H) * SP + tx + H;         // this thread's cell in an s tile
+
+  const int ibase = a.lo[0] - 1 + blockIdx.x * (BX - 2);
+  const int jbase = a.lo[1] - 1 + blockIdx.y * (BY - 2);
+  const int i = ibase + tx, j = jbase + ty;
+  const int kz0 = a.lo[2] + blockIdx.z * a.kchunk;
+  const int kz1 = min(kz0 + a.kchunk - 1, a.hi[2]);
+  const bool top = (kz1 == a.hi[2]);
+  const int ic = min(i, a.hi[0] + 1), jc = min(j, a.hi[1] + 1);
+  const LineBC nb = no_wall2();
+
+  const double rel_eps = a.rel_eps;
+  const double tdx = a.dt / a.dx[0], tdy = a.dt / a.dx[1], tdz = a.dt / a.dx[2];
+  const double c6x = tdx * (1.0 / 6.0), c6y = tdy * (1.0 / 6.0), c6z = tdz * (1.0 / 6.0);
+  const double c4x = tdx * 0.25, c4y = tdy * 0.25, c4z = tdz * 0.25;
+  const double dt2 = 0.5 * a.dt;
+
+  // ---- element offsets of this thread inside each fab (32-bit; advanced by one plane per step) -----------------
+  // s is staged into the tile from this thread's own window: clamp to the fab, not to hi+1 (the tile rows of the
+  // columns beyond hi+1 feed the stencils of the cells at hi+1)
+  const int o_s = (int)a.s.off(min(i, a.s.lo[0] + a.s.n[0] - 1), min(j, a.s.lo[1] + a.s.n[1] - 1), a.s.lo[2]);
+  const int v_row = a.umac[1].n[0];
+  const int s_sz = (int)a.s.stride(2), f_sz = (int)a.force.stride(2);
+  const int u_sz = (int)a.umac[0].stride(2), v_sz = (int)a.umac[1].stride(2), w_sz = (int)a.umac[2].stride(2);
+  const int s_k0 = a.s.lo[2], s_k1 = a.s.lo[2] + a.s.n[2] - 1;
+  const int f_k0 = a.force.lo[2], f_k1 = a.force.lo[2] + a.force.n[2] - 1;
+  const int u_k0 = a.umac[0].lo[2], u_k1 = a.umac[0].lo[2] + a.umac[0].n[2] - 1;
+  const int w_k0 = a.umac[2].lo[2], w_k1 = a.umac[2].lo[2] + a.umac[2].n[2] - 1;
+  // offset of plane k clamped to the fab's planes [k0,k1] (planes outside are only touched by warm-up / drain
+  // steps whose results are never stored)
+  auto clampk = [](int k, int k0, int k1) { return max(k0, min(k, k1)) - k0; };
+  // advance an offset that addresses (clamped) plane k to (clamped) plane k+1
+  auto adv = [](int& q, int k, int k0, int k1, int sz) {
+    if (k >= k0 && k < k1) q += sz;
+  };
+  const double* __restrict__ gs = a.s.p;
+  const double* __restrict__ gf = a.force.p;
+  const double* __restrict__ gu = a.umac[0].p;
+  const double* __restrict__ gv = a.umac[1].p;
+  const double* __restrict__ gw = a.umac[2].p;
+
+  // s-tile halo elements this thread stages: tile index and in-plane global offset (clamped to the fab)
+  int h_idx[SM::NH], h_off[SM::NH];
+#pragma unroll
+  for (int m = 0; m < SM::NH; ++m) {
+    const int h = tid + m * BX * BY;
+    int yy, xx;
+    if (h < H * SP) {
+      yy = h / SP;
+      xx = h - yy * SP;
+    } else if (h < 2 * H * SP) {
+      const int h2 = h - H * SP;
+      yy = h2 / SP;
+      xx = h2 - yy * SP;
+      yy += BY + H;
+    } else {
+      const int h2 = h - 2 * H * SP;
+      const int r = h2 / (2 * H), c = h2 - r * (2 * H);
+      yy = H + r;
+      xx = (c < H) ? c : BX + c;
+    }
+    int ii = ibase - H + xx, jj = jbase - H + yy;
+    ii = max(a.s.lo[0], min(ii, a.s.lo[0] + a.s.n[0] - 1));
+    jj = max(a.s.lo[1], min(jj, a.s.lo[1] + a.s.n[1] - 1));
+    h_idx[m] = (h < SM::NHALO) ? yy * SP + xx : -1;
+    h_off[m] = (int)a.s.off(ii, jj, a.s.lo[2]);
+  }
+
+  // ---- prologue ----------------------------------------------------------------------------------------------
+  const int t0 = kz0 - 1;
+  const int t1 = kz1 + 2 + (top ? 1 : 0);
+  double sw[2 * H + 1];  // z window: sw[m] = s(i,j,t-H+m) after the shift at the top of step t
+#pragma unroll
+  for (int m = 1; m <= 2 * H; ++m) sw[m] = gs[o_s + clampk(t0 - 1 - H + m, s_k0, s_k1) * s_sz];
+  // running offsets: q_s -> plane t+1+H of s (window), q_h -> plane t+1 (tile halo), q_u/q_v -> plane t+1,
+  // q_w -> z-face t+2, q_f -> plane t-2, all for the step t about to start
+  int q_s = o_s + clampk(t0 + 1 + H, s_k0, s_k1) * s_sz;
+  int q_u = (int)a.umac[0].off(ic, jc, a.umac[0].lo[2]) + clampk(t0 + 1, u_k0, u_k1) * u_sz;
+  int q_v = (int)a.umac[1].off(ic, jc, a.umac[1].lo[2]) + clampk(t0 + 1, u_k0, u_k1) * v_sz;
+  int q_w = (int)a.umac[2].off(ic, jc, a.umac[2].lo[2]) + clampk(t0 + 2, w_k0, w_k1) * w_sz;
+  int q_f = (int)a.force.off(ic, jc, a.force.lo[2]) + clampk(t0 - 2, f_k0, f_k1) * f_sz;
+  sw[0] = 0.0;
+  double dz_c = 0.0, ez_c = 0.0;  // PPM==1: van Leer slope of cell t-1 / edge value on z-face t (carried)
+  if constexpr (PPM == 1) {
+    const double dz_m = dsvl_of(&sw[2], 1);
+    dz_c = dsvl_of(&sw[3], 1);
+    double e = 0.5 * (sw[3] + sw[2]) - (1.0 / 6.0) * (dz_c - dz_m);
+    double elo, ehi;
+    dminmax(sw[3], sw[2], elo, ehi);
+    ez_c = dmin2(dmax2(e, elo), ehi);
+  }
+  // s tile of plane t0
+  {
+    double* S = sS + (t0 & 1) * SM::SN;
+    S[sc_idx] = sw[H + 1];
+#pragma unroll
+    for (int m = 0; m < SM::NH; ++m)
+      if (h_idx[m] >= 0) S[h_idx[m]] = gs[h_off[m] + clampk(t0, s_k0, s_k1) * s_sz];
+#pragma unroll
+    for (int m = 0; m < SM::NH; ++m) h_off[m] += clampk(t0 + 1, s_k0, s_k1) * s_sz;
+  }
+  // loads in flight across one step
+  double ld_s = gs[o_s + clampk(t0 + H, s_k0, s_k1) * s_sz];
+  double ld_u, ld_u1, ld_v, ld_v1, ld_w1;
+  double w0c;  // w on z-face t
+  {
+    const int ou = (int)a.umac[0].off(ic, jc, a.umac[0].lo[2]) + clampk(t0, u_k0, u_k1) * u_sz;
+    const int ov = (int)a.umac[1].off(ic, jc, a.umac[1].lo[2]) + clampk(t0, u_k0, u_k1) * v_sz;
+    const int ow = (int)a.umac[2].off(ic, jc, a.umac[2].lo[2]);
+    ld_u = gu[ou];
+    ld_u1 = gu[ou + 1];
+    ld_v = gv[ov];
+    ld_v1 = gv[ov + v_row];
+    ld_w1 = gw[ow + clampk(t0 + 1, w_k0, w_k1) * w_sz];
+    w0c = gw[ow + clampk(t0, w_k0, w_k1) * w_sz];
+  }
+
+  // carried state, suffix = age in planes relative to t
+  double pz0_1 = 0.0, pz1_1 = 0.0;                      // z parabola of cell t-1
+  double w1 = 0.0, w2 = 0.0;                            // w on z-faces t-1, t-2
+  double shz1 = 0.0, shz2 = 0.0;                        // simhz on z-faces t-1, t-2
+  double tx2 = 0.0, ty2 = 0.0;                          // T_x, T_y of cell t-2
+  double zx2 = 0.0, zy2 = 0.0;                          // simhzx, simhzy on z-face t-2
+  double gz3 = 0.0;                                     // G_z of cell t-3
+  double us1 = 0.0, us2 = 0.0, vs1 = 0.0, vs2 = 0.0;    // u(i+1)+u(i), v(j+1)+v(j) of planes t-1, t-2
+  double shx1 = 0.0, shx2 = 0.0, shy1 = 0.0, shy2 = 0.0;  // simhx, simhy of this thread's faces, planes t-1, t-2
+  unsigned selx = 0, sely = 0;  // 2 bits per plane (age 0,1,2): bit0 = upwind is the low cell, bit1 = |u| <= rel_eps
+
+  const bool st_x = (tx >= 1) && (tx <= BX - 2 || i == a.hi[0] + 1) && (i <= a.hi[0] + 1) && (ty >= 1) &&
+                    (ty <= BY - 2) && (j <= a.hi[1]);
+  const bool st_y = (ty >= 1) && (ty <= BY - 2 || j == a.hi[1] + 1) && (j <= a.hi[1] + 1) && (tx >= 1) &&
+                    (tx <= BX - 2) && (i <= a.hi[0]);
+  const bool st_z = (tx >= 1) && (tx <= BX - 2) && (i <= a.hi[0]) && (ty >= 1) && (ty <= BY - 2) && (j <= a.hi[1]);
+  const int ex_sz = (int)a.sedge[0].stride(2), ey_sz = (int)a.sedge[1].stride(2), ez_sz = (int)a.sedge[2].stride(2);
+  // offsets of the planes stored at step t (t-2), advanced every step
+  int q_ex = (st_x ? (int)a.sedge[0].off(i, j, a.sedge[0].lo[2]) : 0) + (t0 - 2 - a.sedge[0].lo[2]) * ex_sz;
+  int q_ey = (st_y ? (int)a.sedge[1].off(i, j, a.sedge[1].lo[2]) : 0) + (t0 - 2 - a.sedge[1].lo[2]) * ey_sz;
+  int q_ez = (st_z ? (int)a.sedge[2].off(i, j, a.sedge[2].lo[2]) : 0) + (t0 - 2 - a.sedge[2].lo[2]) * ez_sz;
+  double* __restrict__ gex = a.sedge[0].p;
+  double* __restrict__ gey = a.sedge[1].p;
+  double* __restrict__ gez = a.sedge[2].p;
+
+  for (int t = t0; t <= t1; ++t) {
+    // ---- rotate in the loads issued one step ago, issue the next ones ----------------------------------------
+#pragma unroll
+    for (int m = 0; m < 2 * H; ++m) sw[m] = sw[m + 1];
+    sw[2 * H] = ld_s;
+    const double u0 = ld_u, v0 = ld_v;  // face velocities of plane t
+    const double us0 = ld_u1 + ld_u, vs0 = ld_v1 + ld_v;
+    const double wn = ld_w1;  // w on z-face t+1
+    double hS[SM::NH];  // halo of the s tile of plane t+1, published at the end of this step's face phase
+    ld_u = gu[q_u];
+    ld_u1 = gu[q_u + 1];
+    ld_v = gv[q_v];
+    ld_v1 = gv[q_v + v_row];
+    ld_w1 = gw[q_w];
+    ld_s = gs[q_s];
+    const double f2 = gf[q_f];  // consumed at the end of this cell phase
+#pragma unroll
+    for (int m = 0; m < SM::NH; ++m) {
+      hS[m] = (h_idx[m] >= 0) ? gs[h_off[m]] : 0.0;
+      adv(h_off[m], t + 1, s_k0, s_k1, s_sz);
+    }
+    adv(q_u, t + 1, u_k0, u_k1, u_sz);
+    adv(q_v, t + 1, u_k0, u_k1, v_sz);
+    adv(q_w, t + 2, w_k0, w_k1, w_sz);
+    adv(q_s, t + 1 + H, s_k0, s_k1, s_sz);
+    adv(q_f, t - 2, f_k0, f_k1, f_sz);
+
+    __syncthreads();  // A: s tile(t), simhx/simhy(t-1), simhxy..simhyz(t-2) are visible
+    const double* S = sS + (t & 1) * SM::SN + sc_idx;
+    const double s0 = sw[H], s1 = sw[H - 1];
+
+    // ==== cell phase ============================================================================================
+    // C1(t): limited parabolas
+    double pz0_0, pz1_0;
+    {
+      double a0, a1;
+      cell_par<PPM>(S, 1, a.slope_order, nb, a0, a1);
+      PLN(AX0, 0, 0) = a0;
+      if (PPM != 0) PLN(AX1, 0, 0) = a1;
+      cell_par<PPM>(S, SP, a.slope_order, nb, a0, a1);
+      PLN(AY0, 0, 0) = a0;
+      if (PPM != 0) PLN(AY1, 0, 0) = a1;
+      if constexpr (PPM == 1) {
+        const double dz_n = dsvl_of(&sw[H + 1], 1);
+        double e = 0.5 * (sw[H + 1] + sw[H]) - (1.0 / 6.0) * (dz_n - dz_c);
+        double elo, ehi;
+        dminmax(sw[H + 1], sw[H], elo, ehi);
+        e = dmin2(dmax2(e, elo), ehi);
+        pz0_0 = ez_c;
+        pz1_0 = e;
+        cw_limit(sw[H], pz0_0, pz1_0);
+        dz_c = dz_n;
+        ez_c = e;
+      } else {
+        cell_par<PPM>(&sw[H], 1, a.slope_order, nb, pz0_0, pz1_0);
+      }
+    }
+    // Z(t): simhz on z-face t (between cells t-1 and t)
+    const bool upz0 = w0c > 0.0, slz0 = !(fabs(w0c) > rel_eps);
+    double shz0 = trace1<PPM>(upz0 ? pz0_1 : pz0_0, upz0 ? pz1_1 : pz1_0, upz0 ? s1 : s0, w0c * tdz, upz0);
+    if (slz0) shz0 = trace_slow<PPM>(pz0_1, s1, pz0_0, s0, w0c * tdz);
+    // C2(t-1): cell-centred transverse terms of plane t-1
+    const double ws1 = w0c + w1;
+    const double tx1 = us1 * (PLN(SHX, 0, 1) - shx1);
+    const double ty1 = vs1 * (PLN(SHY, 1, 0) - shy1);
+    const double tz1 = ws1 * (shz0 - shz1);
+    PLN(TX, 0, 0) = tx1;
+    PLN(TY, 0, 0) = ty1;
+    PLN(TZ, 0, 0) = tz1;
+    const bool upz1 = w1 > 0.0, slz1 = !(fabs(w1) > rel_eps);
+    double txs = upz1 ? tx2 : tx1, tys = upz1 ? ty2 : ty1;
+    if (slz1) {
+      txs = 0.5 * (tx2 + tx1);
+      tys = 0.5 * (ty2 + ty1);
+    }
+    const double zx1 = fma(-c6x, txs, shz1);  // simhzx on z-face t-1
+    const double zy1 = fma(-c6y, tys, shz1);  // simhzy
+    // C3(t-2): cell-centred final corrections of plane t-2
+    const double ws2 = w1 + w2;
+    const double hf = dt2 * f2;
+    const double dzy = c4z * ws2 * (zy1 - zy2), dzx = c4z * ws2 * (zx1 - zx2);
+    const double gx2 = fma(c4y * vs2, PLN(YZ, 1, 0) - PLN(YZ, 0, 0), dzy) - hf;
+    const double gy2 = fma(c4x * us2, PLN(XZ, 0, 1) - PLN(XZ, 0, 0), dzx) - hf;
+    const double gz2 =
+        fma(c4x * us2, PLN(XY, 0, 1) - PLN(XY, 0, 0), c4y * vs2 * (PLN(YX, 1, 0) - PLN(YX, 0, 0))) - hf;
+    PLN(GX, 0, 0) = gx2;
+    PLN(GY, 0, 0) = gy2;
+    {
+      const bool upz2 = w2 > 0.0, slz2 = !(fabs(w2) > rel_eps);
+      double g = upz2 ? gz3 : gz2;
+      if (slz2) g = 0.5 * (gz3 + gz2);
+      const int f = t - 2;  // z-face index
+      if (st_z && f >= kz0 && (f <= kz1 || (top && f == kz1 + 1))) gez[q_ez] = shz2 - g;
+    }
+
+    __syncthreads();  // B: parabolas(t), T(t-1), G(t-2) are visible
+    // ==== face phase ============================================================================================
+    // F1(t): simhx, simhy
+    double shx0, shy0;
+    {
+      const bool up = u0 > 0.0, slow = !(fabs(u0) > rel_eps);
+      const int off = up ? -1 : 0;
+      shx0 = trace1<PPM>((pl + off)[SM::AX0 * SM::PL], (pl + off)[SM::AX1 * SM::PL], S[off], u0 * tdx, up);
+      if (slow) shx0 = trace_slow<PPM>(PLN(AX0, 0, -1), S[-1], PLN(AX0, 0, 0), S[0], u0 * tdx);
+      selx = (selx << 2) | (up ? 1u : 0u) | (slow ? 2u : 0u);
+      PLN(SHX, 0, 0) = shx0;
+    }
+    {
+      const bool up = v0 > 0.0, slow = !(fabs(v0) > rel_eps);
+      const int off = up ? -P : 0;
+      shy0 = trace1<PPM>((pl + off)[SM::AY0 * SM::PL], (pl + off)[SM::AY1 * SM::PL], S[up ? -SP : 0], v0 * tdy, up);
+      if (slow) shy0 = trace_slow<PPM>(PLN(AY0, -1, 0), S[-SP], PLN(AY0, 0, 0), S[0], v0 * tdy);
+      sely = (sely << 2) | (up ? 1u : 0u) | (slow ? 2u : 0u);
+      PLN(SHY, 0, 0) = shy0;
+    }
+    // F2(t-1): transverse face states of plane t-1
+    {
+      const int off = (selx & 4u) ? -1 : 0;
+      double tys = (pl + off)[SM::TY * SM::PL], tzs = (pl + off)[SM::TZ * SM::PL];
+      if (selx & 8u) {
+        tys = 0.5 * (PLN(TY, 0, -1) + PLN(TY, 0, 0));
+        tzs = 0.5 * (PLN(TZ, 0, -1) + PLN(TZ, 0, 0));
+      }
+      PLN(XY, 0, 0) = fma(-c6y, tys, shx1);
+      PLN(XZ, 0, 0) = fma(-c6z, tzs, shx1);
+    }
+    {
+      const int off = (sely & 4u) ? -P : 0;
+      double txs2 = (pl + off)[SM::TX * SM::PL], tzs = (pl + off)[SM::TZ * SM::PL];
+      if (sely & 8u) {
+        txs2 = 0.5 * (PLN(TX, -1, 0) + PLN(TX, 0, 0));
+        tzs = 0.5 * (PLN(TZ, -1, 0) + PLN(TZ, 0, 0));
+      }
+      PLN(YX, 0, 0) = fma(-c6x, txs2, shy1);
+      PLN(YZ, 0, 0) = fma(-c6z, tzs, shy1);
+    }
+    // F3(t-2): final edge states of plane t-2
+    {
+      const int k = t - 2;
+      const bool kin = (k >= kz0) && (k <= kz1);
+      if (kin && st_x) {
+        double g = (pl + ((selx & 16u) ? -1 : 0))[SM::GX * SM::PL];
+        if (selx & 32u) g = 0.5 * (PLN(GX, 0, -1) + PLN(GX, 0, 0));
+        gex[q_ex] = shx2 - g;
+      }
+      if (kin && st_y) {
+        double g = (pl + ((sely & 16u) ? -P : 0))[SM::GY * SM::PL];
+        if (sely & 32u) g = 0.5 * (PLN(GY, -1, 0) + PLN(GY, 0, 0));
+        gey[q_ey] = shy2 - g;
+      }
+    }
+    // publish the s tile of plane t+1
+    {
+      double* Sn = sS + ((t + 1) & 1) * SM::SN;
+      Sn[sc_idx] = sw[H + 1];
+#pragma unroll
+      for (int m = 0; m < SM::NH; ++m)
+        if (h_idx[m] >= 0) Sn[h_idx[m]] = hS[m];
+    }
+    q_ex += ex_sz; q_ey += ey_sz; q_ez += ez_sz;
+    // ---- age the carried state -----------------------------------------------------------------------------------
+    pz0_1 = pz0_0; pz1_1 = pz1_0;
+    w2 = w1; w1 = w0c; w0c = wn;
+    shz2 = shz1; shz1 = shz0;
+    tx2 = tx1; ty2 = ty1;
+    zx2 = zx1; zy2 = zy1;
+    gz3 = gz2;
+    us2 = us1; us1 = us0; vs2 = vs1; vs1 = vs0;
+    shx2 = shx1; shx1 = shx0; shy2 = shy1; shy1 = shy0;
+  }
+}
+
+template <int PPM, int BX, int BY>
+void launch_fused2(const FusedArgs& a, int nx, int ny, int nz) {
+  constexpr int H = (PPM == 2) ? 3 : 2;
+  using SM = Smem2<H, BX, BY>;
+  Context& c = ctx();
+  static bool configured = false;
+  auto kern = k_fused_edge2<PPM, BX, BY>;
+  constexpr int bytes = SM::TOTAL * (int)sizeof(double);
+  if (!configured) {
+    MGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    configured = true;
+  }
+  dim3 block(BX, BY, 1);
+  dim3 grid((nx + BX - 3) / (BX - 2), (ny + BY - 3) / (BY - 2), (nz + a.kchunk - 1) / a.kchunk);
+  MGPU_TIMED(TAG_FUSED_EDGE, (kern<<<grid, block, bytes, c.stream>>>(a)));
+}
+
+}  // namespace
+
+// all six faces INTERIOR, FAST arithmetic.  a.kchunk: z planes per CTA.
+void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz) {
+  constexpr int BX = MGPU_FUSED_BX, BY = MGPU_FUSED2_BY;
+  // 32-bit in-plane offsets
+  for (const DV* v : {&a.s, &a.force, &a.umac[0], &a.umac[1], &a.umac[2], &a.sedge[0], &a.sedge[1], &a.sedge[2]})
+    if (v->cs >= (1L << 31)) throw Error("make_edge_scal: fab too large for the fused kernel's 32-bit offsets");
+  switch (ppm_type) {
+    case 0: launch_fused2<0, BX, BY>(a, nx, ny, nz); break;
+    case 1: launch_fused2<1, BX, BY>(a, nx, ny, nz); break;
+    case 2: launch_fused2<2, BX, BY>(a, nx, ny, nz); break;
+    default: throw Error("make_edge_scal: invalid ppm_type");
+  }
+}
+
+}  // namespace mgpu
