@@ -285,7 +285,7 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   set_dev(scal_force.p, 0.0, scal_force.size());  // :101-103
   if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {  // :119-128
     modify_scal_force_dev(P, scal_force, sold, umac, rho0_old, rho0_edge_old, w0, P.rho_comp,
-                          spt == MGPU_PREDICT_RHO_AND_X, lo, hi);
+                          spt == MGPU_PREDICT_RHO_AND_X, lo, hi, g_opt_exact == 0);
     fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
   }
   addw0_dev(P, umac, w0, 1.0, lo, hi);  // :148
@@ -553,7 +553,7 @@ static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold,
   set_dev(scal_force.p, 0.0, scal_force.size());  // :132-134
   rhoh_force(true, p0_old, rho0_old, grav_old, true);
   if (ept == MGPU_PREDICT_RHOHPRIME) {  // :153-156
-    modify_scal_force_dev(P, scal_force, sold, umac, rhoh0_old, rh0e_old, w0, P.rhoh_comp, false, lo, hi);
+    modify_scal_force_dev(P, scal_force, sold, umac, rhoh0_old, rh0e_old, w0, P.rhoh_comp, false, lo, hi, g_opt_exact == 0);
     fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask, false);
   } else if (ept == MGPU_PREDICT_H) {  // :173-178
     comp_muldiv_dev(P, scal_force, rhoh, sold, rho, 0, 1, lo, hi);
@@ -660,6 +660,7 @@ int mgpu_set_option(const char* key, int value) {
   else if (k == "kchunk") g_opt_kchunk = value;
   else if (k == "exact") g_opt_exact = value;
   else if (k == "fused_variant") fused_edge_set_variant(value);
+  else if (k == "fused_by") fused_edge2_set_by(value);
   else throw Error("mgpu_set_option: unknown key " + k);
   MGPU_CATCH
 }
@@ -995,7 +996,7 @@ int mgpu_modify_scal_force(const mgpu_params* p, int nfabs, mgpu_fab* force, con
     DV fv = c.view(force[i], true, true), sv = c.view(s[i], true, false);
     DV um[3];
     c.views(umac, i, true, false, um);
-    modify_scal_force_dev(*p, fv, sv, um, s0d, s0ed, w0d, comp, fullform != 0, s[i].lo, s[i].hi);
+    modify_scal_force_dev(*p, fv, sv, um, s0d, s0ed, w0d, comp, fullform != 0, s[i].lo, s[i].hi, g_opt_exact == 0);
   }
   c.finish();
   MGPU_CATCH

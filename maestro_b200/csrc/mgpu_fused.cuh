@@ -40,5 +40,6 @@ void fused_edge_launch_fast(const FusedArgs& a, int ppm_type, bool bc, int nx, i
 void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz);
 // 0: always the literal kernel; 1 (default): the upwind-first kernel wherever it applies
 void fused_edge_set_variant(int v);
+void fused_edge2_set_by(int by);  // rows per CTA of the upwind-first kernel: 8 or 16
 
 }  // namespace mgpu

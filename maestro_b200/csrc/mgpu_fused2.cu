@@ -80,6 +80,25 @@ __device__ __forceinline__ double trace_slow(double a0l, double scl, double a0r,
   }
 }
 
+// FAST forms of the ppm_type=1 building blocks (ppm.f90:1697-1752): same values as dsvl_of / sedge1_of up to the
+// last bit, written without data-dependent branches.
+//   van Leer slope: sign(dsc) min(|dsc|, 2|dl|, 2|dr|) if dl*dr > 0 else 0
+__device__ __forceinline__ double dsvl_fast(double sm, double s0, double sp) {
+  const double dl = s0 - sm, dr = sp - s0;
+  const double dsc = 0.5 * (sp - sm);
+  const double mn = dmin2(fabs(dl), fabs(dr));
+  double lim = dmin2(fabs(dsc), mn + mn);
+  lim = (dl * dr > 0.0) ? lim : 0.0;
+  return copysign(lim, dsc);
+}
+//   edge value between cells (sl | sr) with van Leer slopes (dl | dr), clipped to the two cell values
+__device__ __forceinline__ double edge_fast(double sl, double sr, double dl, double dr) {
+  const double e = fma(-1.0 / 6.0, dr - dl, 0.5 * (sr + sl));
+  double lo, hi;
+  dminmax(sl, sr, lo, hi);
+  return dmin2(dmax2(e, lo), hi);
+}
+
 // limited parabola (PPM>=1: a0 = sm, a1 = sp) or slope (PPM==0: a0) of one cell along a line in memory
 template <int PPM>
 __device__ __forceinline__ void cell_par(const double* q, int st, int slope_order, const LineBC& nb, double& a0,
@@ -88,9 +107,11 @@ __device__ __forceinline__ void cell_par(const double* q, int st, int slope_orde
     a0 = slope_cell(q, st, 0, nb, slope_order);
     a1 = 0.0;
   } else if constexpr (PPM == 1) {
-    a0 = sedge1_of(q, st);
-    a1 = sedge1_of(q + st, st);
-    cw_limit(q[0], a0, a1);
+    const double m2 = q[-2 * st], m1 = q[-st], c0 = q[0], p1 = q[st], p2 = q[2 * st];
+    const double dm = dsvl_fast(m2, m1, c0), d0 = dsvl_fast(m1, c0, p1), dp = dsvl_fast(c0, p1, p2);
+    a0 = edge_fast(m1, c0, dm, d0);
+    a1 = edge_fast(c0, p1, d0, dp);
+    cw_limit(c0, a0, a1);
   } else {
     ppm2_cell(q, st, 0, nb, a0, a1);
   }
@@ -108,7 +129,7 @@ __device__ __forceinline__ LineBC no_wall2() {
 }
 
 template <int PPM, int BX, int BY>
-__global__ void __launch_bounds__(BX* BY, MGPU_FUSED2_MINB) k_fused_edge2(FusedArgs a) {
+__global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_fused_edge2(FusedArgs a) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = Smem2<H, BX, BY>;
   constexpr int SP = SM::SP, P = SM::P;
@@ -150,6 +171,9 @@ __global__ void __launch_bounds__(BX* BY, MGPU_FUSED2_MINB) k_fused_edge2(FusedA
   // advance an offset that addresses (clamped) plane k to (clamped) plane k+1
   auto adv = [](int& q, int k, int k0, int k1, int sz) {
     if (k >= k0 && k < k1) q += sz;
+  };
+  auto adv_hi = [](int& q, int k, int k1, int sz) {  // for planes that never fall below the fab (k >= k0 always)
+    if (k < k1) q += sz;
   };
   const double* __restrict__ gs = a.s.p;
   const double* __restrict__ gf = a.force.p;
@@ -200,12 +224,9 @@ __global__ void __launch_bounds__(BX* BY, MGPU_FUSED2_MINB) k_fused_edge2(FusedA
   sw[0] = 0.0;
   double dz_c = 0.0, ez_c = 0.0;  // PPM==1: van Leer slope of cell t-1 / edge value on z-face t (carried)
   if constexpr (PPM == 1) {
-    const double dz_m = dsvl_of(&sw[2], 1);
-    dz_c = dsvl_of(&sw[3], 1);
-    double e = 0.5 * (sw[3] + sw[2]) - (1.0 / 6.0) * (dz_c - dz_m);
-    double elo, ehi;
-    dminmax(sw[3], sw[2], elo, ehi);
-    ez_c = dmin2(dmax2(e, elo), ehi);
+    const double dz_m = dsvl_fast(sw[1], sw[2], sw[3]);
+    dz_c = dsvl_fast(sw[2], sw[3], sw[4]);
+    ez_c = edge_fast(sw[2], sw[3], dz_m, dz_c);
   }
   // s tile of plane t0
   {
@@ -277,12 +298,12 @@ __global__ void __launch_bounds__(BX* BY, MGPU_FUSED2_MINB) k_fused_edge2(FusedA
 #pragma unroll
     for (int m = 0; m < SM::NH; ++m) {
       hS[m] = (h_idx[m] >= 0) ? gs[h_off[m]] : 0.0;
-      adv(h_off[m], t + 1, s_k0, s_k1, s_sz);
+      adv_hi(h_off[m], t + 1, s_k1, s_sz);
     }
-    adv(q_u, t + 1, u_k0, u_k1, u_sz);
-    adv(q_v, t + 1, u_k0, u_k1, v_sz);
-    adv(q_w, t + 2, w_k0, w_k1, w_sz);
-    adv(q_s, t + 1 + H, s_k0, s_k1, s_sz);
+    adv_hi(q_u, t + 1, u_k1, u_sz);
+    adv_hi(q_v, t + 1, u_k1, v_sz);
+    adv_hi(q_w, t + 2, w_k1, w_sz);
+    adv_hi(q_s, t + 1 + H, s_k1, s_sz);
     adv(q_f, t - 2, f_k0, f_k1, f_sz);
 
     __syncthreads();  // A: s tile(t), simhx/simhy(t-1), simhxy..simhyz(t-2) are visible
@@ -301,11 +322,8 @@ __global__ void __launch_bounds__(BX* BY, MGPU_FUSED2_MINB) k_fused_edge2(FusedA
       PLN(AY0, 0, 0) = a0;
       if (PPM != 0) PLN(AY1, 0, 0) = a1;
       if constexpr (PPM == 1) {
-        const double dz_n = dsvl_of(&sw[H + 1], 1);
-        double e = 0.5 * (sw[H + 1] + sw[H]) - (1.0 / 6.0) * (dz_n - dz_c);
-        double elo, ehi;
-        dminmax(sw[H + 1], sw[H], elo, ehi);
-        e = dmin2(dmax2(e, elo), ehi);
+        const double dz_n = dsvl_fast(sw[H], sw[H + 1], sw[H + 2]);
+        const double e = edge_fast(sw[H], sw[H + 1], dz_c, dz_n);
         pz0_0 = ez_c;
         pz1_0 = e;
         cw_limit(sw[H], pz0_0, pz1_0);
@@ -450,8 +468,9 @@ void launch_fused2(const FusedArgs& a, int nx, int ny, int nz) {
 }  // namespace
 
 // all six faces INTERIOR, FAST arithmetic.  a.kchunk: z planes per CTA.
-void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz) {
-  constexpr int BX = MGPU_FUSED_BX, BY = MGPU_FUSED2_BY;
+template <int BY>
+static void fused_edge2_launch_by(const FusedArgs& a, int ppm_type, int nx, int ny, int nz) {
+  constexpr int BX = MGPU_FUSED_BX;
   // 32-bit in-plane offsets
   for (const DV* v : {&a.s, &a.force, &a.umac[0], &a.umac[1], &a.umac[2], &a.sedge[0], &a.sedge[1], &a.sedge[2]})
     if (v->cs >= (1L << 31)) throw Error("make_edge_scal: fab too large for the fused kernel's 32-bit offsets");
@@ -461,6 +480,13 @@ void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz
     case 2: launch_fused2<2, BX, BY>(a, nx, ny, nz); break;
     default: throw Error("make_edge_scal: invalid ppm_type");
   }
+}
+
+static int g_by = MGPU_FUSED2_BY;
+void fused_edge2_set_by(int by) { g_by = by; }
+void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz) {
+  if (g_by == 16) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz);
+  else fused_edge2_launch_by<8>(a, ppm_type, nx, ny, nz);
 }
 
 }  // namespace mgpu

@@ -250,6 +250,7 @@ void addw0_dev(const mgpu_params& P, DV* umac, const double* w0_dev, double mult
   MGPU_LAUNCH_CHECK();
 }
 
+template <bool FAST>
 __global__ void k_modify_scal_force(DV force, DV s, DV u, DV v, DV w, Box3 vb, int dm, const double* s0,
                                     const double* s0_edge, const double* w0, double dx0, double dx1, double dx2,
                                     bool fullform) {
@@ -257,38 +258,46 @@ __global__ void k_modify_scal_force(DV force, DV s, DV u, DV v, DV w, Box3 vb, i
   if (!decode3(vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
   const int ir = ix[dm - 1];
+  // FAST: dx0..dx2 hold 1/dx and the divisions become multiplications (last-bit differences)
+#define MGPU_DIV(x, h) (FAST ? (x) * (h) : (x) / (h))
   double divu, divs0u, f = force(i, j, k);
   if (dm == 2) {
-    divu = (u(i + 1, j, k) - u(i, j, k)) / dx0 + (v(i, j + 1, k) - v(i, j, k)) / dx1;
-    divu = divu + (w0[ir + 1] - w0[ir]) / dx1;
+    divu = MGPU_DIV(u(i + 1, j, k) - u(i, j, k), dx0) + MGPU_DIV(v(i, j + 1, k) - v(i, j, k), dx1);
+    divu = divu + MGPU_DIV(w0[ir + 1] - w0[ir], dx1);
     if (fullform) {
       f = f - s(i, j, k) * divu;
     } else {
-      divs0u = s0[ir] * (u(i + 1, j, k) - u(i, j, k)) / dx0 +
-               (v(i, j + 1, k) * s0_edge[ir + 1] - v(i, j, k) * s0_edge[ir]) / dx1;
+      divs0u = MGPU_DIV(s0[ir] * (u(i + 1, j, k) - u(i, j, k)), dx0) +
+               MGPU_DIV(v(i, j + 1, k) * s0_edge[ir + 1] - v(i, j, k) * s0_edge[ir], dx1);
       f = f - (s(i, j, k) - s0[ir]) * divu - divs0u;
     }
   } else {
-    divu = (u(i + 1, j, k) - u(i, j, k)) / dx0 + (v(i, j + 1, k) - v(i, j, k)) / dx1 +
-           (w(i, j, k + 1) - w(i, j, k)) / dx2;
-    divu = divu + (w0[ir + 1] - w0[ir]) / dx2;
+    divu = MGPU_DIV(u(i + 1, j, k) - u(i, j, k), dx0) + MGPU_DIV(v(i, j + 1, k) - v(i, j, k), dx1) +
+           MGPU_DIV(w(i, j, k + 1) - w(i, j, k), dx2);
+    divu = divu + MGPU_DIV(w0[ir + 1] - w0[ir], dx2);
     if (fullform) {
       f = f - s(i, j, k) * divu;
     } else {
-      divs0u = s0[ir] * ((u(i + 1, j, k) - u(i, j, k)) / dx0 + (v(i, j + 1, k) - v(i, j, k)) / dx1) +
-               (w(i, j, k + 1) * s0_edge[ir + 1] - w(i, j, k) * s0_edge[ir]) / dx2;
+      divs0u = s0[ir] * (MGPU_DIV(u(i + 1, j, k) - u(i, j, k), dx0) + MGPU_DIV(v(i, j + 1, k) - v(i, j, k), dx1)) +
+               MGPU_DIV(w(i, j, k + 1) * s0_edge[ir + 1] - w(i, j, k) * s0_edge[ir], dx2);
       f = f - (s(i, j, k) - s0[ir]) * divu - divs0u;
     }
   }
   force(i, j, k) = f;
+#undef MGPU_DIV
 }
 void modify_scal_force_dev(const mgpu_params& P, const DV& force, const DV& s, const DV* umac, const double* s0,
                            const double* s0_edge, const double* w0, int comp, bool fullform, const int* lo,
-                           const int* hi) {
+                           const int* hi, bool fast) {
   Box3 vb = grown(lo, hi, P.dm, 0);
-  k_modify_scal_force<<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(
-      force.comp(comp - 1), s.comp(comp - 1), umac[0], umac[1], P.dm == 3 ? umac[2] : umac[1], vb, P.dm, s0, s0_edge,
-      w0, P.dx[0], P.dx[1], P.dx[2], fullform);
+  if (fast)
+    k_modify_scal_force<true><<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(
+        force.comp(comp - 1), s.comp(comp - 1), umac[0], umac[1], P.dm == 3 ? umac[2] : umac[1], vb, P.dm, s0, s0_edge,
+        w0, 1.0 / P.dx[0], 1.0 / P.dx[1], 1.0 / P.dx[2], fullform);
+  else
+    k_modify_scal_force<false><<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(
+        force.comp(comp - 1), s.comp(comp - 1), umac[0], umac[1], P.dm == 3 ? umac[2] : umac[1], vb, P.dm, s0, s0_edge,
+        w0, P.dx[0], P.dx[1], P.dx[2], fullform);
   MGPU_LAUNCH_CHECK();
 }
 
@@ -423,6 +432,7 @@ void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_
 __global__ void k_wrap(DV a, Box3 tb, int d, int lo, int hi, int ng, int nodal) {
   int ix[3];
   if (!decode32(tb, ix)) return;  // tb: d collapsed to [0, 2*ng-1] = ghost slot
+  a.p += a.cs * blockIdx.y;       // one grid row per component
   const int g = ix[d];                    // 0..ng-1: lo side, ng..2ng-1: hi side
   const int n = hi - lo + 1;
   int dst, src;
@@ -472,18 +482,20 @@ void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, con
   // slab-partitioned domain: the slab-direction ghost planes come from the neighbouring ranks (NCCL), first, so
   // that the in-box wraps and physical BCs below also cover the received planes (corners come out right)
   const bool slab = halo_exchange_dev(P, sfull, lo, hi, ng, nodal, scomp - 1, ncomp, pmask, cx.stream);
+  // periodic wraps: x, then y, then z (so edges/corners come out right), all components of the call per launch
+  for (int d = 0; d < dm; ++d) {
+    if (!pmask[d]) continue;
+    if (slab && d == dm - 1) continue;
+    DV s = sfull.comp(scomp - 1);
+    Box3 tb;
+    for (int q = 0; q < 3; ++q) { tb.lo[q] = s.lo[q]; tb.hi[q] = s.lo[q] + s.n[q] - 1; }
+    tb.lo[d] = 0;
+    tb.hi[d] = 2 * ng - 1;
+    k_wrap<<<dim3(nblocks(tb.npts(), 256), ncomp), 256, 0, cx.stream>>>(s, tb, d, lo[d], hi[d], ng, nodal ? nodal[d] : 0);
+    MGPU_LAUNCH_CHECK();
+  }
   for (int n = 0; n < ncomp; ++n) {
     DV s = sfull.comp(scomp - 1 + n);
-    for (int d = 0; d < dm; ++d) {
-      if (!pmask[d]) continue;
-      if (slab && d == dm - 1) continue;
-      Box3 tb;
-      for (int q = 0; q < 3; ++q) { tb.lo[q] = s.lo[q]; tb.hi[q] = s.lo[q] + s.n[q] - 1; }
-      tb.lo[d] = 0;
-      tb.hi[d] = 2 * ng - 1;
-      k_wrap<<<nblocks(tb.npts(), 256), 256, 0, cx.stream>>>(s, tb, d, lo[d], hi[d], ng, nodal ? nodal[d] : 0);
-      MGPU_LAUNCH_CHECK();
-    }
     if (is_nodal) continue;  // multifab_physbc_edgevel (FBoxLib) is left to the caller
     const int bcc = same_boundary ? bccomp : bccomp + n;
     int bc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -661,6 +673,191 @@ __global__ void __launch_bounds__(256, 4) k_flux_update_all(FluxArgs a, UpdArgs 
   }
 }
 
+// 3-D FAST specialisation of k_flux_update_all: 32-bit element offsets (the 64-bit index arithmetic of the
+// general kernel costs it a third of its issue slots and spills), sedge and sflux share one layout per
+// direction, sold/snew share one layout, two components in flight per thread.  Same statements as above.
+struct FU3 {
+  const double* sedge[3];
+  double* sflux[3];
+  const double* umac[3];
+  const double *sold, *force;
+  double *snew, *eta;
+  int e_lo[3][3], e_n0[3], e_n01[3], e_cs[3];  // face fabs (sedge == sflux layout), per direction
+  int u_lo[3][3], u_n0[3], u_n01[3];
+  int s_lo[3], s_n0, s_n01, s_cs;  // sold / snew
+  int f_lo[3], f_n0, f_n01, f_cs;  // force
+  int t_lo[3], t_n0, t_n01;        // etarhoflux
+  int lo[3], hi[3];
+  int spt, do_eta, rho, spec0, nspec, trac0, ntrac;
+  double dt, rdx[3], half_bcd;
+  const double *w0, *rho0_old, *rho0_edge_old, *rho0_new, *rho0_edge_new, *rho0_predicted_edge;
+};
+
+__global__ void __launch_bounds__(256, 3) k_flux_update3_fast(const __grid_constant__ FU3 a) {
+  const int i = a.lo[0] + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int j = a.lo[1] + (int)blockIdx.y, k = a.lo[2] + (int)blockIdx.z;
+  if (i > a.hi[0]) return;
+  int oe[3], se[3];
+  double vlo[3], vhi[3], r0lo[3], r0hi[3];
+  bool last[3];
+  const int ix[3] = {i, j, k};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    oe[d] = (i - a.e_lo[d][0]) + a.e_n0[d] * (j - a.e_lo[d][1]) + a.e_n01[d] * (k - a.e_lo[d][2]);
+    se[d] = d == 0 ? 1 : (d == 1 ? a.e_n0[d] : a.e_n01[d]);
+    const int ou = (i - a.u_lo[d][0]) + a.u_n0[d] * (j - a.u_lo[d][1]) + a.u_n01[d] * (k - a.u_lo[d][2]);
+    const int su = d == 0 ? 1 : (d == 1 ? a.u_n0[d] : a.u_n01[d]);
+    vlo[d] = __ldg(a.umac[d] + ou);
+    vhi[d] = __ldg(a.umac[d] + ou + su);
+    last[d] = (ix[d] == a.hi[d]);
+  }
+  {
+    const double ec = 0.5 * (a.rho0_old[k] + a.rho0_new[k]);                                   // mkflux.f90:410
+    const double el = 0.5 * (a.rho0_edge_old[k] + a.rho0_edge_new[k]);                         // mkflux.f90:465
+    const double eh = 0.5 * (a.rho0_edge_old[k + 1] + a.rho0_edge_new[k + 1]);
+    vlo[2] += a.w0[k];
+    vhi[2] += a.w0[k + 1];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (a.spt == MGPU_PREDICT_RHOX) {
+        r0lo[d] = r0hi[d] = 1.0;
+      } else {
+        const double* pr = a.sedge[d] + oe[d] + a.e_cs[d] * a.rho;
+        const double add_lo = (a.spt == MGPU_PREDICT_RHOPRIME_AND_X) ? (d == 2 ? el : ec) : 0.0;
+        const double add_hi = (a.spt == MGPU_PREDICT_RHOPRIME_AND_X) ? (d == 2 ? eh : ec) : 0.0;
+        r0lo[d] = add_lo + __ldg(pr);
+        r0hi[d] = add_hi + __ldg(pr + se[d]);
+      }
+      // fold the velocity in: flux = (vel * rhofac) * X_edge
+      r0lo[d] *= vlo[d];
+      r0hi[d] *= vhi[d];
+    }
+  }
+  const int os = (i - a.s_lo[0]) + a.s_n0 * (j - a.s_lo[1]) + a.s_n01 * (k - a.s_lo[2]);
+  const int of = (i - a.f_lo[0]) + a.f_n0 * (j - a.f_lo[1]) + a.f_n01 * (k - a.f_lo[2]);
+  double eta = 0.0, eta_hi = 0.0;
+  int ot = 0;
+  if (a.do_eta) {
+    ot = (i - a.t_lo[0]) + a.t_n0 * (j - a.t_lo[1]) + a.t_n01 * (k - a.t_lo[2]);
+    eta = a.eta[ot];
+    if (last[2]) eta_hi = a.eta[ot + a.t_n01];
+  }
+  bool neg = false;
+  double rnew = __ldg(a.sold + os + a.s_cs * a.rho);
+  const int ncomp = a.nspec + a.ntrac;
+#pragma unroll 2
+  for (int n = 0; n < ncomp; ++n) {
+    const int c = (n < a.nspec) ? a.spec0 + n : a.trac0 + (n - a.nspec);
+    double flo[3], fhi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double* pe = a.sedge[d] + oe[d] + a.e_cs[d] * c;
+      flo[d] = r0lo[d] * __ldg(pe);
+      fhi[d] = r0hi[d] * __ldg(pe + se[d]);
+    }
+    const double so = __ldg(a.sold + os + a.s_cs * c);
+    const double fo = __ldg(a.force + of + a.f_cs * c);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double* pf = a.sflux[d] + oe[d] + a.e_cs[d] * c;
+      pf[0] = flo[d];
+      if (last[d]) pf[se[d]] = fhi[d];
+    }
+    if (a.do_eta && n < a.nspec) {  // mkflux.f90:486-494
+      eta += flo[2];
+      if (last[2]) eta_hi += fhi[2];
+    }
+    const double divterm = (fhi[0] - flo[0]) * a.rdx[0] + (fhi[1] - flo[1]) * a.rdx[1] + (fhi[2] - flo[2]) * a.rdx[2];
+    const double sn = so + a.dt * (fo - divterm);
+    a.snew[os + a.s_cs * c] = sn;
+    if (n < a.nspec) {
+      rnew += sn - so;
+      neg = neg || (sn < 0.0);
+    }
+  }
+  if (a.do_eta) {
+    if (a.nspec > 0) {
+      eta -= a.w0[k] * a.rho0_predicted_edge[k];
+      eta_hi -= a.w0[k + 1] * a.rho0_predicted_edge[k + 1];
+    }
+    a.eta[ot] = eta;
+    if (last[2]) a.eta[ot + a.t_n01] = eta_hi;
+  }
+  // density, floor, negative species: update_scal.f90:453-505
+  double* sn = a.snew + os;
+  const int cn = a.s_cs, c0 = a.spec0, c1 = a.spec0 + a.nspec - 1;
+  if (rnew < a.half_bcd) {
+    for (int c = c0; c <= c1; ++c) sn[cn * c] = sn[cn * c] * a.half_bcd / rnew;
+    rnew = a.half_bcd;
+  }
+  sn[cn * a.rho] = rnew;
+  if (neg) {
+    for (int c = c0; c <= c1; ++c) {
+      if (sn[cn * c] < 0.0) {
+        const double delta = -sn[cn * c];
+        double sumX = 0.0;
+        for (int c2 = c0; c2 <= c1; ++c2)
+          if (c2 != c && sn[cn * c2] >= 0.0) sumX = sumX + sn[cn * c2];
+        for (int c2 = c0; c2 <= c1; ++c2)
+          if (c2 != c && sn[cn * c2] >= 0.0) {
+            const double frac = sn[cn * c2] / sumX;
+            sn[cn * c2] = sn[cn * c2] - frac * delta;
+          }
+        sn[cn * c] = 0.0;
+      }
+    }
+  }
+}
+
+static bool same_layout(const DV& x, const DV& y) {
+  for (int d = 0; d < 3; ++d)
+    if (x.lo[d] != y.lo[d] || x.n[d] != y.n[d]) return false;
+  return x.cs == y.cs;
+}
+// true if the specialised kernel covers this call (and then launches it)
+static bool flux_update3_fast(const mgpu_params& P, const FluxArgs& a, const UpdArgs& u) {
+  if (P.dm != 3) return false;
+  const long lim = 1L << 31;
+  for (int d = 0; d < 3; ++d)
+    if (!same_layout(a.sedge[d], a.sflux[d]) || a.sedge[d].cs * a.sedge[d].nc >= lim || a.umac[d].cs >= lim) return false;
+  if (!same_layout(u.sold, u.snew) || u.sold.cs * u.sold.nc >= lim || u.force.cs * u.force.nc >= lim) return false;
+  FU3 f;
+  memset(&f, 0, sizeof(f));
+  for (int d = 0; d < 3; ++d) {
+    f.sedge[d] = a.sedge[d].p;
+    f.sflux[d] = a.sflux[d].p;
+    f.umac[d] = a.umac[d].p;
+    for (int q = 0; q < 3; ++q) {
+      f.e_lo[d][q] = a.sedge[d].lo[q];
+      f.u_lo[d][q] = a.umac[d].lo[q];
+    }
+    f.e_n0[d] = a.sedge[d].n[0];
+    f.e_n01[d] = a.sedge[d].n[0] * a.sedge[d].n[1];
+    f.e_cs[d] = (int)a.sedge[d].cs;
+    f.u_n0[d] = a.umac[d].n[0];
+    f.u_n01[d] = a.umac[d].n[0] * a.umac[d].n[1];
+    f.s_lo[d] = u.sold.lo[d];
+    f.f_lo[d] = u.force.lo[d];
+    f.t_lo[d] = a.eta.lo[d];
+    f.lo[d] = u.vb.lo[d];
+    f.hi[d] = u.vb.hi[d];
+    f.rdx[d] = 1.0 / u.dx[d];
+  }
+  f.sold = u.sold.p; f.snew = u.snew.p; f.force = u.force.p; f.eta = a.eta.p;
+  f.s_n0 = u.sold.n[0]; f.s_n01 = u.sold.n[0] * u.sold.n[1]; f.s_cs = (int)u.sold.cs;
+  f.f_n0 = u.force.n[0]; f.f_n01 = u.force.n[0] * u.force.n[1]; f.f_cs = (int)u.force.cs;
+  f.t_n0 = a.eta.n[0]; f.t_n01 = a.eta.n[0] * a.eta.n[1];
+  f.spt = a.species_pred_type; f.do_eta = a.evolve_base_state ? 1 : 0;
+  f.rho = a.rho; f.spec0 = a.spec0; f.nspec = a.nspec; f.trac0 = P.trac_comp - 1; f.ntrac = P.ntrac;
+  f.dt = u.dt; f.half_bcd = 0.5 * P.base_cutoff_density;
+  f.w0 = a.w0; f.rho0_old = a.rho0_old; f.rho0_edge_old = a.rho0_edge_old; f.rho0_new = a.rho0_new;
+  f.rho0_edge_new = a.rho0_edge_new; f.rho0_predicted_edge = a.rho0_predicted_edge;
+  const dim3 g = grid3(u.vb, 256);
+  const int b = block3(u.vb, 256);
+  MGPU_TIMED(TAG_UPDATE, (k_flux_update3_fast<<<g, b, 0, ctx().stream>>>(f)));
+  return true;
+}
+
 void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exact) {
   Context& cx = ctx();
   const int rho = P.rho_comp - 1;
@@ -668,6 +865,7 @@ void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exa
   // snew(:,:,:,rho_comp) = sold(:,:,:,rho_comp) including ghost cells (update_scal.f90:455)
   MGPU_TIMED(TAG_UPDATE, (k_copy<<<nblocks(u.snew.cs, 256), 256, 0, cx.stream>>>(u.snew.p + u.snew.cs * rho,
                                                                                  u.sold.p + u.sold.cs * rho, u.snew.cs)));
+  if (!exact && flux_update3_fast(P, a, u)) return;
   const dim3 g = grid3(u.vb, 256);
   const int b = block3(u.vb, 256);
   const int t0 = P.trac_comp - 1;

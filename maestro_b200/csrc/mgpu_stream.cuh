@@ -66,7 +66,7 @@ void comp_muldiv_dev(const mgpu_params& P, const DV& a, int ca, const DV& b, int
 void addw0_dev(const mgpu_params& P, DV* umac, const double* w0_dev, double mult, const int* lo, const int* hi);
 void modify_scal_force_dev(const mgpu_params& P, const DV& force, const DV& s, const DV* umac, const double* s0,
                            const double* s0_edge, const double* w0, int comp, bool fullform, const int* lo,
-                           const int* hi);
+                           const int* hi, bool fast);
 void convert_rhoX_to_X_dev(const mgpu_params& P, const DV& s, bool flag, const int* lo, const int* hi);
 void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_dev, int comp, bool flag,
                           const int* lo, const int* hi);

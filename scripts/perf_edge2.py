@@ -35,10 +35,11 @@ for ppm in (1, 2, 0):
     p.dt = 0.7 / n
     p.rel_eps = 1e-8
     zones = n ** 3
-    for variant in (0, 1):
+    for variant, by in ((0, 8), (1, 8), (1, 16)):
         lib.set_option("fused_variant", variant)
-        for kchunk in (16, 32, 64, 128, 256):
+        lib.set_option("fused_by", by)
+        for kchunk in (16, 32, 64, 128):
             lib.set_option("kchunk", kchunk)
             t = timeit(lambda: ops.make_edge_scal(p, s, sedge, umac, force, adv_bc, False, 1, 4, 1, False))
-            print("variant %d ppm%d n=%d kchunk=%3d: %.3f ms/comp -> %.2f Gzone/s, %.0f GB/s (64 B/zone algorithmic)"
-                  % (variant, ppm, n, kchunk, t, zones / t / 1e6, 64 * zones / t / 1e6), flush=True)
+            print("variant %d by %d ppm%d n=%d kchunk=%3d: %.3f ms/comp -> %.2f Gzone/s, %.0f GB/s (64 B/zone algorithmic)"
+                  % (variant, by, ppm, n, kchunk, t, zones / t / 1e6, 64 * zones / t / 1e6), flush=True)
