@@ -224,6 +224,65 @@ int mgpu_convert_rhoX_to_X(const mgpu_params* p, int nfabs, mgpu_fab* s, int fla
 int mgpu_put_in_pert_form(const mgpu_params* p, int nfabs, mgpu_fab* s, const double* base, int comp,
                           int flag);
 
+/* ---- spherical geometry (SURVEY a3/a4/a7-a12 "_3d_sphr" branches, and 8f2) ------------------------------
+ * geometry module (Source/geometry.f90: center, dr(1), nr_fine, r_cc_loc(1,:), r_edge_loc(1,:)) and the
+ * interpolation switches of probin (Source/_parameters:632-651), passed per call like mgpu_params. */
+typedef struct {
+  double center[3];
+  double prob_lo[3];
+  double dr;                /* dr(1) = dx/drdxfac */
+  int nr_fine;
+  const double* r_cc_loc;   /* (0:nr_fine-1) host */
+  const double* r_edge_loc; /* (0:nr_fine)   host */
+  int s0_interp_type;       /* 1 constant, 2 linear, 3 quadratic: bin-centred 1-D array -> cell centres */
+  int w0_interp_type;       /* same for an edge-centred 1-D array */
+  int s0mac_interp_type;    /* 1 via cell centres then average, 2 linear to faces, 3 quadratic to faces */
+  int w0mac_interp_type;    /* 1, 2, 3 as above, 4 via nodes */
+} mgpu_geom;
+
+/* put_1d_array_on_cart_3d_sphr (Source/fill_3d_data.f90:269): valid cells lo:hi of s0_cart (1 comp, or 3 comps
+ * = value * unit radial vector if is_output_a_vector); ghost cells are the caller's mgpu_fill_boundary. */
+int mgpu_put_1d_array_on_cart(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* s0,
+                              mgpu_fab* s0_cart, int is_input_edge_centered, int is_output_a_vector);
+/* make_w0mac_3d_sphr (fill_3d_data.f90:621): normal component of w0 on faces lo-1:hi+1(+1), ng_w0 = 1.
+ * w0_cart (3 comps, ng >= 2, ghosts filled) is read only when w0mac_interp_type == 1. */
+int mgpu_make_w0mac(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* w0,
+                    mgpu_fab* const* w0mac, const mgpu_fab* w0_cart);
+/* make_s0mac_3d_sphr (fill_3d_data.f90:1017): s0_cart (1 comp, ng >= 2) read only when s0mac_interp_type == 1. */
+int mgpu_make_s0mac(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* s0,
+                    mgpu_fab* const* s0mac, const mgpu_fab* s0_cart);
+/* addw0_3d_sphr (Source/addw0.f90:171): umac_d += mult * w0mac_d on the valid faces of every direction. */
+int mgpu_addw0_sphr(const mgpu_params* p, int nfabs, mgpu_fab* const* umac, const mgpu_fab* const* w0mac,
+                    double mult);
+/* mk_rhoX_flux_3d_sphr (Source/mkflux.f90:509) and mk_rhoh_flux_3d_sphr (:1289). */
+int mgpu_mk_rhoX_flux_sphr(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, const mgpu_fab* const* sedge,
+                           const mgpu_fab* const* umac, const mgpu_fab* const* w0mac,
+                           const mgpu_fab* const* rho0mac_old, const mgpu_fab* const* rho0mac_new, int startcomp,
+                           int endcomp);
+int mgpu_mk_rhoh_flux_sphr(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, const mgpu_fab* const* sedge,
+                           const mgpu_fab* const* umac, const mgpu_fab* const* w0mac,
+                           const mgpu_fab* const* rho0mac_old, const mgpu_fab* const* rho0mac_new,
+                           const mgpu_fab* const* h0mac_old, const mgpu_fab* const* h0mac_new);
+/* update_velocity_3d, spherical branch (Source/update_vel.f90:227, :317-360). */
+int mgpu_update_velocity_sphr(const mgpu_params* p, int nfabs, const mgpu_fab* uold, mgpu_fab* unew,
+                              const mgpu_fab* const* umac, const mgpu_fab* const* uedge, const mgpu_fab* force,
+                              const mgpu_fab* sponge, const mgpu_fab* const* w0mac);
+/* mkutrans_3d / velpred_3d with spherical == 1: every Riemann problem carries w0mac of its direction
+ * (mkutrans.f90:601,709,817; velpred.f90:1588,1687,1786). */
+int mgpu_mkutrans_sphr(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                       mgpu_fab* const* utrans, const mgpu_fab* const* w0mac, const int* adv_bc,
+                       const int* phys_bc);
+int mgpu_velpred_sphr(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                      mgpu_fab* const* umac, const mgpu_fab* const* utrans, const mgpu_fab* force,
+                      const mgpu_fab* const* w0mac, const int* adv_bc, const int* phys_bc);
+/* modify_scal_force_3d_sphr (Source/modify_scal_force.f90:256) and pert_form_3d_sphr
+ * (Source/put_in_pert_form.f90:185).  s0_cart: 1 comp, ng >= 1 with ghosts filled. */
+int mgpu_modify_scal_force_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* force,
+                                const mgpu_fab* s, const mgpu_fab* const* umac, const mgpu_fab* s0_cart,
+                                const double* w0, int comp, int fullform);
+int mgpu_put_in_pert_form_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* s,
+                               const double* s0, int comp, int flag);
+
 /* ---- L4 episode: density_advance (Source/density_advance.f90:20), planar, one level ------
  * Signature mirrors the Fortran argument list; sold is modified in place exactly as the reference
  * does (rhoX->X->rhoX, rho->rho'->rho round trips), umac is (umac+w0)-w0 on return, sedge, sflux,

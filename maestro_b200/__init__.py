@@ -7,6 +7,6 @@ operators.py  host mirror of the reference's L3/L4 operators (make_edge_scal, mk
 lib.py  loader of the CUDA library; no CPU fallback
 """
 from . import abi  # noqa: F401
-from .fab import Fab, face_fabs, make_adv_bc, make_params, nbc_comps  # noqa: F401
+from .fab import Fab, Geom, face_fabs, make_adv_bc, make_params, nbc_comps  # noqa: F401
 from .operators import MaestroError, Operators  # noqa: F401
 from . import slab  # noqa: F401,E402

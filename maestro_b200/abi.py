@@ -82,7 +82,24 @@ class mgpu_halo_plan(C.Structure):
     ]
 
 
+class mgpu_geom(C.Structure):
+    """spherical geometry (geometry module + interpolation switches of probin), include/maestro_b200.h"""
+    _fields_ = [
+        ("center", C.c_double * 3),
+        ("prob_lo", C.c_double * 3),
+        ("dr", C.c_double),
+        ("nr_fine", C.c_int),
+        ("r_cc_loc", c_double_p),
+        ("r_edge_loc", c_double_p),
+        ("s0_interp_type", C.c_int),
+        ("w0_interp_type", C.c_int),
+        ("s0mac_interp_type", C.c_int),
+        ("w0mac_interp_type", C.c_int),
+    ]
+
+
 P_ = C.POINTER(mgpu_params)
+G_ = C.POINTER(mgpu_geom)
 F_ = C.POINTER(mgpu_fab)
 FF_ = C.POINTER(F_)  # array of dm pointers, each to an array of nfabs fabs
 
@@ -107,6 +124,18 @@ OPERATORS = {
     "advance_premac": (C.c_int, [P_, F_, F_, FF_, F_] + [c_double_p] * 4 + [c_int_p] * 3),
     "velocity_advance": (C.c_int, [P_, F_, F_, F_, F_, FF_, F_] + [c_double_p] * 6 + [F_] + [c_int_p] * 2),
     "enthalpy_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_] + [c_double_p] * 10 + [c_int_p] * 2),
+    # spherical geometry
+    "put_1d_array_on_cart": (C.c_int, [P_, G_, C.c_int, c_double_p, F_, C.c_int, C.c_int]),
+    "make_w0mac": (C.c_int, [P_, G_, C.c_int, c_double_p, FF_, F_]),
+    "make_s0mac": (C.c_int, [P_, G_, C.c_int, c_double_p, FF_, F_]),
+    "addw0_sphr": (C.c_int, [P_, C.c_int, FF_, FF_, C.c_double]),
+    "mk_rhoX_flux_sphr": (C.c_int, [P_, C.c_int, FF_, FF_, FF_, FF_, FF_, FF_, C.c_int, C.c_int]),
+    "mk_rhoh_flux_sphr": (C.c_int, [P_, C.c_int] + [FF_] * 8),
+    "update_velocity_sphr": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_]),
+    "mkutrans_sphr": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, c_int_p, c_int_p]),
+    "velpred_sphr": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, FF_, c_int_p, c_int_p]),
+    "modify_scal_force_sphr": (C.c_int, [P_, G_, C.c_int, F_, F_, FF_, F_, c_double_p, C.c_int, C.c_int]),
+    "put_in_pert_form_sphr": (C.c_int, [P_, G_, C.c_int, F_, c_double_p, C.c_int, C.c_int]),
     "density_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, FF_, c_double_p, F_] + [c_double_p] * 4
                         + [c_int_p] * 2),
 }

@@ -13,6 +13,7 @@
 #include "mgpu_edge.cuh"
 #include "mgpu_fused.cuh"
 #include "mgpu_halo.cuh"
+#include "mgpu_sphr.cuh"
 #include "mgpu_stream.cuh"
 #include "mgpu_velpred.cuh"
 
@@ -1179,6 +1180,221 @@ int mgpu_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, 
   c.views((const mgpu_fab* const*)umac, 0, true, true, um);
   enthalpy_advance_dev(*p, which_step, so, sn, se, sf, fv, th, um, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old,
                        p0_new, psi, grav_old, grav_nph, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+// ---- spherical geometry (mgpu_sphr.cu) ----------------------------------------------------------------------
+static size_t geom_scratch(const mgpu_geom* g) { return (size_t)(6 * (g->nr_fine + 4)) * sizeof(double) + 8192; }
+static void need_sphr(const mgpu_params* p, const mgpu_geom* g) {
+  if (p->dm != 3) throw Error("spherical geometry is 3-D only");
+  if (g && g->nr_fine < 3) throw Error("spherical geometry: nr_fine must be at least 3");
+}
+
+int mgpu_put_1d_array_on_cart(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* s0, mgpu_fab* s0_cart,
+                              int is_input_edge_centered, int is_output_a_vector) {
+  MGPU_TRY
+  need_sphr(p, g);
+  Call c(p, geom_scratch(g));
+  Geom gd = make_geom(*p, *g);
+  const double* s0d = upload_small(s0, (size_t)g->nr_fine + (is_input_edge_centered ? 1 : 0));
+  for (int i = 0; i < nfabs; ++i) {
+    DV cv = c.view(s0_cart[i], true, true);
+    put_1d_array_on_cart_dev(*p, *g, gd, s0d, cv, is_input_edge_centered != 0, is_output_a_vector != 0, s0_cart[i].lo,
+                             s0_cart[i].hi);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+static int make_mac_api(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* s0, mgpu_fab* const* mac,
+                        const mgpu_fab* cart, int kind) {
+  MGPU_TRY
+  need_sphr(p, g);
+  Call c(p, geom_scratch(g));
+  Geom gd = make_geom(*p, *g);
+  const double* s0d = upload_small(s0, (size_t)g->nr_fine + (kind == 0 ? 1 : 0));
+  for (int i = 0; i < nfabs; ++i) {
+    if (mac[0][i].ng != 1)  // fill_3d_data.f90:588, :992
+      throw Error(kind == 0 ? "Error: make_w0mac_3d_sphr assumes one ghost cell"
+                            : "Error: make_s0mac assumes one ghost cell in s0mac");
+    DV m[3], cv;
+    c.views((const mgpu_fab* const*)mac, i, true, true, m);
+    if (cart) cv = c.view(cart[i], true, false);
+    make_mac_dev(*g, gd, s0d, m, cart ? &cv : nullptr, kind, mac[0][i].lo, mac[0][i].hi);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+int mgpu_make_w0mac(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* w0, mgpu_fab* const* w0mac,
+                    const mgpu_fab* w0_cart) {
+  return make_mac_api(p, g, nfabs, w0, w0mac, w0_cart, 0);
+}
+int mgpu_make_s0mac(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* s0, mgpu_fab* const* s0mac,
+                    const mgpu_fab* s0_cart) {
+  return make_mac_api(p, g, nfabs, s0, s0mac, s0_cart, 1);
+}
+
+int mgpu_addw0_sphr(const mgpu_params* p, int nfabs, mgpu_fab* const* umac, const mgpu_fab* const* w0mac, double mult) {
+  MGPU_TRY
+  need_sphr(p, nullptr);
+  Call c(p, 0);
+  for (int i = 0; i < nfabs; ++i) {
+    DV um[3], wm[3];
+    c.views((const mgpu_fab* const*)umac, i, true, true, um);
+    c.views(w0mac, i, true, false, wm);
+    addw0_sphr_dev(um, wm, mult, umac[0][i].lo, umac[0][i].hi);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+static void fill_sphr_flux(Call& c, const mgpu_params* p, int i, SphrFluxArgs& a, mgpu_fab* const* sflux,
+                           const mgpu_fab* const* sedge, const mgpu_fab* const* umac, const mgpu_fab* const* w0mac,
+                           const mgpu_fab* const* r0o, const mgpu_fab* const* r0n, const mgpu_fab* const* h0o,
+                           const mgpu_fab* const* h0n) {
+  a.spt = p->species_pred_type;
+  a.rho = p->rho_comp - 1;
+  a.rhoh = p->rhoh_comp - 1;
+  a.vb = grown(sflux[0][i].lo, sflux[0][i].hi, 3, 0);
+  c.views((const mgpu_fab* const*)sflux, i, true, true, a.sflux);
+  c.views(sedge, i, true, false, a.sedge);
+  c.views(umac, i, true, false, a.umac);
+  c.views(w0mac, i, true, false, a.w0mac);
+  c.views(r0o, i, true, false, a.r0o);
+  c.views(r0n, i, true, false, a.r0n);
+  for (int d = 0; d < 3; ++d) a.h0o[d] = a.h0n[d] = a.r0o[d];
+  if (h0o) c.views(h0o, i, true, false, a.h0o);
+  if (h0n) c.views(h0n, i, true, false, a.h0n);
+}
+
+int mgpu_mk_rhoX_flux_sphr(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, const mgpu_fab* const* sedge,
+                           const mgpu_fab* const* umac, const mgpu_fab* const* w0mac, const mgpu_fab* const* rho0mac_old,
+                           const mgpu_fab* const* rho0mac_new, int startcomp, int endcomp) {
+  MGPU_TRY
+  need_sphr(p, nullptr);
+  Call c(p, 0);
+  for (int i = 0; i < nfabs; ++i) {
+    SphrFluxArgs a;
+    fill_sphr_flux(c, p, i, a, sflux, sedge, umac, w0mac, rho0mac_old, rho0mac_new, nullptr, nullptr);
+    mk_rhoX_flux_sphr_dev(a, startcomp, endcomp);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_mk_rhoh_flux_sphr(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, const mgpu_fab* const* sedge,
+                           const mgpu_fab* const* umac, const mgpu_fab* const* w0mac, const mgpu_fab* const* rho0mac_old,
+                           const mgpu_fab* const* rho0mac_new, const mgpu_fab* const* h0mac_old,
+                           const mgpu_fab* const* h0mac_new) {
+  MGPU_TRY
+  need_sphr(p, nullptr);
+  Call c(p, 0);
+  for (int i = 0; i < nfabs; ++i) {
+    SphrFluxArgs a;
+    fill_sphr_flux(c, p, i, a, sflux, sedge, umac, w0mac, rho0mac_old, rho0mac_new, h0mac_old, h0mac_new);
+    mk_rhoh_flux_sphr_dev(*p, a);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_update_velocity_sphr(const mgpu_params* p, int nfabs, const mgpu_fab* uold, mgpu_fab* unew,
+                              const mgpu_fab* const* umac, const mgpu_fab* const* uedge, const mgpu_fab* force,
+                              const mgpu_fab* sponge, const mgpu_fab* const* w0mac) {
+  MGPU_TRY
+  need_sphr(p, nullptr);
+  Call c(p, 0);
+  for (int i = 0; i < nfabs; ++i) {
+    VelArgs a;
+    a.dm = 3;
+    a.do_sponge = p->do_sponge != 0;
+    a.dt = p->dt;
+    for (int d = 0; d < 3; ++d) a.dx[d] = p->dx[d];
+    a.vb = grown(uold[i].lo, uold[i].hi, 3, 0);
+    a.uold = c.view(uold[i], true, false);
+    a.unew = c.view(unew[i], true, true);
+    a.force = c.view(force[i], true, false);
+    a.sponge = c.view(sponge[i], true, false);
+    c.views(umac, i, true, false, a.umac);
+    c.views(uedge, i, true, false, a.uedge);
+    a.w0 = nullptr;
+    DV wm[3];
+    c.views(w0mac, i, true, false, wm);
+    update_velocity_sphr_dev(a, wm);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_mkutrans_sphr(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                       mgpu_fab* const* utrans, const mgpu_fab* const* w0mac, const int* adv_bc, const int* phys_bc) {
+  MGPU_TRY
+  need_sphr(p, nullptr);
+  if (!p->spherical) throw Error("mkutrans_sphr: params.spherical must be 1");
+  Call c(p, 4096);
+  for (int i = 0; i < nfabs; ++i) {
+    DV ut = c.view(utilde[i], true, false), uf = c.view(ufull[i], true, false);
+    DV tr[3], wm[3];
+    c.views((const mgpu_fab* const*)utrans, i, true, true, tr);
+    c.views(w0mac, i, true, false, wm);
+    mkutrans_dev(*p, ut, uf, tr, nullptr, utilde[i].lo, utilde[i].hi, adv_bc, phys_bc, utilde[i].ng, wm);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_velpred_sphr(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                      mgpu_fab* const* umac, const mgpu_fab* const* utrans, const mgpu_fab* force,
+                      const mgpu_fab* const* w0mac, const int* adv_bc, const int* phys_bc) {
+  MGPU_TRY
+  need_sphr(p, nullptr);
+  if (!p->spherical) throw Error("velpred_sphr: params.spherical must be 1");
+  size_t need = 0;
+  for (int i = 0; i < nfabs; ++i) need = std::max(need, velpred_scratch(*p, utilde[i].lo, utilde[i].hi));
+  Call c(p, need + 4096);
+  for (int i = 0; i < nfabs; ++i) {
+    size_t mark = arena_mark();
+    DV ut = c.view(utilde[i], true, false), uf = c.view(ufull[i], true, false), fv = c.view(force[i], true, false);
+    DV um[3], tr[3], wm[3];
+    c.views((const mgpu_fab* const*)umac, i, true, true, um);
+    c.views(utrans, i, true, false, tr);
+    c.views(w0mac, i, true, false, wm);
+    velpred_dev(*p, ut, uf, um, tr, fv, nullptr, utilde[i].lo, utilde[i].hi, adv_bc, phys_bc, utilde[i].ng, force[i].ng, wm);
+    arena_release(mark);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_modify_scal_force_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* force, const mgpu_fab* s,
+                                const mgpu_fab* const* umac, const mgpu_fab* s0_cart, const double* w0, int comp,
+                                int fullform) {
+  MGPU_TRY
+  need_sphr(p, g);
+  Call c(p, geom_scratch(g));
+  Geom gd = make_geom(*p, *g);
+  for (int i = 0; i < nfabs; ++i) {
+    DV fv = c.view(force[i], true, true), sv = c.view(s[i], true, false), sc = c.view(s0_cart[i], true, false);
+    DV um[3];
+    c.views(umac, i, true, false, um);
+    modify_scal_force_sphr_dev(*p, *g, gd, fv, sv, um, sc, w0, comp, fullform != 0, s[i].lo, s[i].hi);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_put_in_pert_form_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* s, const double* s0,
+                               int comp, int flag) {
+  MGPU_TRY
+  need_sphr(p, g);
+  Call c(p, geom_scratch(g));
+  Geom gd = make_geom(*p, *g);
+  const double* s0d = upload_small(s0, (size_t)g->nr_fine);
+  for (int i = 0; i < nfabs; ++i) {
+    DV sv = c.view(s[i], true, true);
+    pert_form_sphr_dev(*g, gd, sv, s0d, comp, flag != 0, s[i].lo, s[i].hi);
+  }
   c.finish();
   MGPU_CATCH
 }

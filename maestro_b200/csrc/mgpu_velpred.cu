@@ -92,8 +92,9 @@ __global__ void k_mkutrans(VpArgs a, int d) {
     else if (wall3(p)) { ul = 0.0; ur = 0.0; }
     else if (p == MGPU_BC_OUTLET) { ul = dmax2(ul, 0.0); ur = ul; }
   }
-  const bool radial = (d == a.dm - 1);
-  a.utrans[d](ix[0], ix[1], ix[2]) = riemann_full(ul, ur, radial, radial ? a.w0[ix[d]] : 0.0, a.rel_eps);
+  const bool radial = a.spherical || (d == a.dm - 1);
+  const double w0f = a.spherical ? a.w0mac[d](ix[0], ix[1], ix[2]) : (radial ? a.w0[ix[d]] : 0.0);
+  a.utrans[d](ix[0], ix[1], ix[2]) = riemann_full(ul, ur, radial, w0f, a.rel_eps);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -243,8 +244,9 @@ __global__ void k_vp_final(VpArgs a, int d) {
     mr = a.UR[d].p[fo] - tterm(dt4 / a.dx[t1], a.utrans[t1], a.Q[d][t1], 0, t1, ix[0], ix[1], ix[2]) -
          tterm(dt4 / a.dx[t2], a.utrans[t2], a.Q[d][t2], 0, t2, ix[0], ix[1], ix[2]) + dt2 * fr;
   }
-  const bool radial = (d == dm - 1);
-  double e = riemann_full(ml, mr, radial, radial ? a.w0[ix[d]] : 0.0, a.rel_eps);
+  const bool radial = a.spherical || (d == dm - 1);
+  const double w0f = a.spherical ? a.w0mac[d](ix[0], ix[1], ix[2]) : (radial ? a.w0[ix[d]] : 0.0);
+  double e = riemann_full(ml, mr, radial, w0f, a.rel_eps);
   if (ix[d] == a.lo[d]) {
     const int p = a.plo[d];
     if (p == MGPU_BC_INLET) e = a.utilde(cl[0], cl[1], cl[2], d);
@@ -271,9 +273,12 @@ void check_phys(int bc, const char* who) {
 }
 
 void fill_common(VpArgs& a, const mgpu_params& P, const DV& utilde, const DV& ufull, const double* w0_dev,
-                 const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const char* who) {
+                 const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const char* who,
+                 const DV* w0mac) {
   const int dm = P.dm;
-  if (P.spherical) throw Error(std::string(who) + ": spherical geometry not available on the device yet");
+  if (P.spherical && (!w0mac || dm != 3)) throw Error(std::string(who) + ": spherical geometry needs w0mac (3-D)");
+  a.spherical = P.spherical != 0;
+  for (int d = 0; d < 3; ++d) a.w0mac[d] = (a.spherical ? w0mac[d] : utilde);
   if (P.ppm_type == 2 && ng_u < 4) throw Error("Need 4 ghost cells for ppm_type=2");  // ppm.f90:1864-1866
   if (ng_u < 3) throw Error(std::string(who) + ": need at least 3 ghost cells");
   a.dm = dm;
@@ -309,9 +314,9 @@ void fill_common(VpArgs& a, const mgpu_params& P, const DV& utilde, const DV& uf
 }  // namespace
 
 void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* utrans, const double* w0_dev,
-                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u) {
+                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const DV* w0mac) {
   VpArgs a;
-  fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "mkutrans");
+  fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "mkutrans", w0mac);
   for (int d = 0; d < P.dm; ++d) a.utrans[d] = utrans[d];
   for (int d = 0; d < P.dm; ++d) {
     Box3 fb = a.vb;
@@ -328,9 +333,9 @@ size_t velpred_scratch(const mgpu_params& P, const int* lo, const int* hi) {
 
 void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans, const DV& force,
                  const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
-                 int ng_f) {
+                 int ng_f, const DV* w0mac) {
   VpArgs a;
-  fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "velpred");
+  fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "velpred", w0mac);
   const int dm = P.dm;
   a.trace = (P.ppm_trace_forces == 1) && P.ppm_type != 0;
   if (a.trace && ng_f < ng_u) throw Error("velpred: ppm_trace_forces needs force with as many ghost cells as utilde");

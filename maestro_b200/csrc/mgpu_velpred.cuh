@@ -17,13 +17,16 @@ struct VpArgs {
   DV UL[3], UR[3], UIMH[3];  // per face direction, dm components, on tb
   DV Q[3][3];                // [component][face direction], 3-D only
   const double* w0;
+  bool spherical;  // every direction's Riemann problem carries w0mac[d] (mkutrans.f90:601, velpred.f90:1588)
+  DV w0mac[3];
 };
 
 void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* utrans, const double* w0_dev,
-                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u);
+                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
+                  const DV* w0mac = nullptr);
 void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans, const DV& force,
                  const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
-                 int ng_f);
+                 int ng_f, const DV* w0mac = nullptr);
 size_t velpred_scratch(const mgpu_params& P, const int* lo, const int* hi);
 
 }  // namespace mgpu

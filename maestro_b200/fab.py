@@ -194,3 +194,36 @@ def fab_pp(fabs):
     keep = [fab_ptr(f) for f in fabs]
     pp = (abi.F_ * len(fabs))(*[C.cast(k, abi.F_) for k in keep])
     return pp, keep
+
+
+class Geom:
+    """Spherical geometry as MAESTRO's geometry module builds it (Source/geometry.f90: init_radial /
+    init_spherical): dr = dx/drdxfac, nr_fine radial bins reaching the domain corner, r_cc_loc = (r+1/2) dr,
+    r_edge_loc = r dr; centre = middle of the domain.  Owns the arrays the C struct points to."""
+
+    def __init__(self, p, drdxfac=5, center=None, prob_lo=(0.0, 0.0, 0.0), s0_interp_type=3, w0_interp_type=2,
+                 s0mac_interp_type=1, w0mac_interp_type=1, nr_fine=None):
+        n = [p.domhi[d] - p.domlo[d] + 1 for d in range(3)]
+        prob_hi = [prob_lo[d] + n[d] * p.dx[d] for d in range(3)]
+        self.dr = p.dx[0] / drdxfac
+        if center is None:
+            center = [0.5 * (prob_lo[d] + prob_hi[d]) for d in range(3)]
+        # far enough for every cell / face / node of the box grown by two ghost cells
+        far = max(np.sqrt(sum((max(abs(prob_lo[d] - 3 * p.dx[d] - center[d]), abs(prob_hi[d] + 3 * p.dx[d] - center[d]))) ** 2
+                              for d in range(3))), 0.0)
+        self.nr_fine = int(far / self.dr) + 4 if nr_fine is None else nr_fine
+        self.r_cc_loc = (np.arange(self.nr_fine) + 0.5) * self.dr
+        self.r_edge_loc = np.arange(self.nr_fine + 1) * self.dr
+        c = abi.mgpu_geom()
+        for d in range(3):
+            c.center[d] = center[d]
+            c.prob_lo[d] = prob_lo[d]
+        c.dr = self.dr
+        c.nr_fine = self.nr_fine
+        c.r_cc_loc = self.r_cc_loc.ctypes.data_as(abi.c_double_p)
+        c.r_edge_loc = self.r_edge_loc.ctypes.data_as(abi.c_double_p)
+        c.s0_interp_type, c.w0_interp_type = s0_interp_type, w0_interp_type
+        c.s0mac_interp_type, c.w0mac_interp_type = s0mac_interp_type, w0mac_interp_type
+        self.c = c
+        self.center = list(center)
+        self.prob_lo = list(prob_lo)

@@ -124,6 +124,65 @@ class Operators:
         b, bp = as_double_p(base)
         self._call("put_in_pert_form", C.byref(p), 1, fab_ptr(s), bp, comp, int(flag))
 
+    # ---- spherical geometry (the reference's *_3d_sphr branches; fill_3d_data.f90) ----------------
+    def put_1d_array_on_cart(self, p, geom, s0, s0_cart, is_input_edge_centered, is_output_a_vector):
+        a, ap = as_double_p(s0)
+        self._call("put_1d_array_on_cart", C.byref(p), C.byref(geom.c), 1, ap, fab_ptr(s0_cart),
+                   int(is_input_edge_centered), int(is_output_a_vector))
+
+    def make_w0mac(self, p, geom, w0, w0mac, w0_cart=None):
+        a, ap = as_double_p(w0)
+        wm, k1 = fab_pp(w0mac)
+        self._call("make_w0mac", C.byref(p), C.byref(geom.c), 1, ap, wm, fab_ptr(w0_cart) if w0_cart is not None else None)
+
+    def make_s0mac(self, p, geom, s0, s0mac, s0_cart=None):
+        a, ap = as_double_p(s0)
+        sm, k1 = fab_pp(s0mac)
+        self._call("make_s0mac", C.byref(p), C.byref(geom.c), 1, ap, sm, fab_ptr(s0_cart) if s0_cart is not None else None)
+
+    def addw0_sphr(self, p, umac, w0mac, mult):
+        um, k1 = fab_pp(umac)
+        wm, k2 = fab_pp(w0mac)
+        self._call("addw0_sphr", C.byref(p), 1, um, wm, float(mult))
+
+    def mk_rhoX_flux_sphr(self, p, sflux, sedge, umac, w0mac, rho0mac_old, rho0mac_new, startcomp, endcomp):
+        ptrs = [fab_pp(x) for x in (sflux, sedge, umac, w0mac, rho0mac_old, rho0mac_new)]
+        self._call("mk_rhoX_flux_sphr", C.byref(p), 1, *[q[0] for q in ptrs], startcomp, endcomp)
+
+    def mk_rhoh_flux_sphr(self, p, sflux, sedge, umac, w0mac, rho0mac_old, rho0mac_new, h0mac_old, h0mac_new):
+        ptrs = [fab_pp(x) for x in (sflux, sedge, umac, w0mac, rho0mac_old, rho0mac_new, h0mac_old, h0mac_new)]
+        self._call("mk_rhoh_flux_sphr", C.byref(p), 1, *[q[0] for q in ptrs])
+
+    def update_velocity_sphr(self, p, uold, unew, umac, uedge, force, sponge, w0mac):
+        ptrs = [fab_pp(x) for x in (umac, uedge, w0mac)]
+        self._call("update_velocity_sphr", C.byref(p), 1, fab_ptr(uold), fab_ptr(unew), ptrs[0][0], ptrs[1][0],
+                   fab_ptr(force), fab_ptr(sponge), ptrs[2][0])
+
+    def mkutrans_sphr(self, p, utilde, ufull, utrans, w0mac, adv_bc, phys_bc):
+        bc, bcp = as_int_p(adv_bc)
+        pb, pbp = as_int_p(phys_bc)
+        ut, k1 = fab_pp(utrans)
+        wm, k2 = fab_pp(w0mac)
+        self._call("mkutrans_sphr", C.byref(p), 1, fab_ptr(utilde), fab_ptr(ufull), ut, wm, bcp, pbp)
+
+    def velpred_sphr(self, p, utilde, ufull, umac, utrans, force, w0mac, adv_bc, phys_bc):
+        bc, bcp = as_int_p(adv_bc)
+        pb, pbp = as_int_p(phys_bc)
+        um, k1 = fab_pp(umac)
+        ut, k2 = fab_pp(utrans)
+        wm, k3 = fab_pp(w0mac)
+        self._call("velpred_sphr", C.byref(p), 1, fab_ptr(utilde), fab_ptr(ufull), um, ut, fab_ptr(force), wm, bcp, pbp)
+
+    def modify_scal_force_sphr(self, p, geom, force, s, umac, s0_cart, w0, comp, fullform=False):
+        w, wp = as_double_p(w0)
+        um, k1 = fab_pp(umac)
+        self._call("modify_scal_force_sphr", C.byref(p), C.byref(geom.c), 1, fab_ptr(force), fab_ptr(s), um,
+                   fab_ptr(s0_cart), wp, comp, int(fullform))
+
+    def put_in_pert_form_sphr(self, p, geom, s, s0, comp, flag):
+        b, bp = as_double_p(s0)
+        self._call("put_in_pert_form_sphr", C.byref(p), C.byref(geom.c), 1, fab_ptr(s), bp, comp, int(flag))
+
     # ---- L4 driver -----------------------------------------------------------------------------
     def density_advance(self, p, which_step, sold, snew, sedge, sflux, scal_force, umac, w0, etarhoflux, rho0_old,
                         rho0_new, p0_dummy, rho0_predicted_edge, adv_bc, pmask):

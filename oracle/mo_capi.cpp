@@ -18,7 +18,8 @@ void test_advect_run(int dm, int n, int ppm_type, int bds_type, int itest_dir, d
 
 using namespace mo;
 
-static std::string g_err;
+std::string mo_g_err;  // shared with mo_sphr.cpp
+#define g_err mo_g_err
 
 #define MO_TRY try {
 #define MO_CATCH                         \

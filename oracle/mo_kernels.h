@@ -80,11 +80,12 @@ void modify_scal_force_box(const mgpu_params& P, Arr& force, const Arr& s, const
 void cell_to_edge(const double* s0_cell, double* s0_edge, int nr);
 
 void mkutrans_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr* utrans, const double* w0,
-                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u);
+                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
+                  const Arr* w0mac = nullptr);
 
 void velpred_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr* umac, const Arr* utrans,
                  const Arr& force, const double* w0, const int* lo, const int* hi, const int* adv_bc,
-                 const int* phys_bc, int ng_u);
+                 const int* phys_bc, int ng_u, const Arr* w0mac = nullptr);
 
 void bds_box(const mgpu_params& P, const Arr& s, Arr* sedge, const Arr* umac, const Arr& force, const int* lo,
              const int* hi, int comp, bool is_conservative);

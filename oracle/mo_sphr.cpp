@@ -1,0 +1,515 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (see mo_array.h).
+//
+// Spherical-geometry branches of the path, restated loop for loop:
+//   put_1d_array_on_cart_3d_sphr  Source/fill_3d_data.f90:269      quad_interp :535
+//   make_w0mac_3d_sphr            Source/fill_3d_data.f90:621      make_s0mac_3d_sphr :1017
+//   addw0_3d_sphr                 Source/addw0.f90:171
+//   mk_rhoX_flux_3d_sphr          Source/mkflux.f90:509            mk_rhoh_flux_3d_sphr :1289
+//   update_velocity_3d            Source/update_vel.f90:227 (spherical == 1 branch :317-360)
+//   modify_scal_force_3d_sphr     Source/modify_scal_force.f90:256
+//   pert_form_3d_sphr             Source/put_in_pert_form.f90:185
+// Parity unpinned: the reference holds no golden vector for these routines; they are pinned by this
+// restatement plus analytic checks in tests/test_oracle_cpu.py (linear profiles reproduced exactly, unit normal).
+#include <stdexcept>
+#include <string>
+
+#include "mo_kernels.h"
+
+namespace mo {
+
+namespace {
+
+struct I3 {
+  int i, j, k;
+};
+inline I3 sh(int i, int j, int k, int d, int o) { return I3{i + (d == 0 ? o : 0), j + (d == 1 ? o : 0), k + (d == 2 ? o : 0)}; }
+
+inline double max3(double a, double b, double c) { return dmax(dmax(a, b), c); }
+inline double min3(double a, double b, double c) { return dmin(dmin(a, b), c); }
+
+// fill_3d_data.f90:535-546
+inline double quad_interp(double x, double x0, double x1, double x2, double y0, double y1, double y2) {
+  double y = y0 + (y1 - y0) / (x1 - x0) * (x - x0) +
+             ((y2 - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0)) / (x2 - x0) * (x - x0) * (x - x1);
+  if (y > max3(y0, y1, y2)) y = max3(y0, y1, y2);
+  if (y < min3(y0, y1, y2)) y = min3(y0, y1, y2);
+  return y;
+}
+
+// value of an EDGE-centred 1-D array at `radius` (w0_interp_type / w0mac_interp_type semantics 1..3)
+inline double interp_edge(const mgpu_geom& g, int type, const double* s0, double radius) {
+  const double dr = g.dr;
+  int index = (int)(radius / dr);
+  if (type == 1) {  // :308-316
+    const double rfac = (radius - (double)index * dr) / dr;
+    return (rfac > 0.5) ? s0[index + 1] : s0[index];
+  }
+  if (type == 2) {  // :341-349
+    const double rfac = (radius - (double)index * dr) / dr;
+    if (index < g.nr_fine) return rfac * s0[index + 1] + (1.0 - rfac) * s0[index];
+    return s0[g.nr_fine];
+  }
+  // :374-389.  QUIRK: the third test compares a distance with a position, so it is true whenever it is reached
+  if (index <= 0) index = 0;
+  else if (index >= g.nr_fine - 1) index = g.nr_fine - 2;
+  else if (radius - g.r_edge_loc[index] < g.r_edge_loc[index + 1]) index = index - 1;
+  return quad_interp(radius, g.r_edge_loc[index], g.r_edge_loc[index + 1], g.r_edge_loc[index + 2], s0[index],
+                     s0[index + 1], s0[index + 2]);
+}
+
+// value of a BIN-centred 1-D array at `radius` (s0_interp_type / s0mac_interp_type semantics 1..3)
+inline double interp_cc(const mgpu_geom& g, int type, const double* s0, double radius) {
+  const double dr = g.dr;
+  int index = (int)(radius / dr);
+  const int nr = g.nr_fine;
+  if (type == 1) return s0[index];  // :426-428
+  if (type == 2) {                  // :453-471
+    if (radius >= g.r_cc_loc[index]) {
+      if (index >= nr - 1) return s0[nr - 1];
+      return s0[index + 1] * (radius - g.r_cc_loc[index]) / dr + s0[index] * (g.r_cc_loc[index + 1] - radius) / dr;
+    }
+    if (index == 0) return s0[index];
+    if (index > nr - 1) return s0[nr - 1];
+    return s0[index] * (radius - g.r_cc_loc[index - 1]) / dr + s0[index - 1] * (g.r_cc_loc[index] - radius) / dr;
+  }
+  // :496-510
+  if (index == 0) index = 1;
+  else if (index >= nr - 1) index = nr - 2;
+  return quad_interp(radius, g.r_cc_loc[index - 1], g.r_cc_loc[index], g.r_cc_loc[index + 1], s0[index - 1], s0[index],
+                     s0[index + 1]);
+}
+
+// position of index i in direction d: cell centre (half = true) or face/node (half = false)
+inline double pos(const mgpu_geom& g, const mgpu_params& P, int d, int i, bool half) {
+  return g.prob_lo[d] + ((double)i + (half ? 0.5 : 0.0)) * P.dx[d] - g.center[d];
+}
+inline double radius_of(double x, double y, double z) { return std::sqrt(x * x + y * y + z * z); }
+
+void check_types(const mgpu_geom& g) {
+  if (g.nr_fine < 3) fail("spherical geometry: nr_fine must be at least 3");
+}
+
+}  // namespace
+
+void put_1d_array_on_cart_sphr(const mgpu_params& P, const mgpu_geom& g, bool edge_in, bool vec, const double* s0,
+                               Arr& cart, const int* lo, const int* hi) {
+  check_types(g);
+  const int type = edge_in ? g.w0_interp_type : g.s0_interp_type;
+  if (type < 1 || type > 3) fail(edge_in ? "Error: w0_interp_type not defined" : "Error: s0_interp_type not defined");
+#pragma omp parallel for
+  for (int k = lo[2]; k <= hi[2]; ++k) {
+    const double z = pos(g, P, 2, k, true);
+    for (int j = lo[1]; j <= hi[1]; ++j) {
+      const double y = pos(g, P, 1, j, true);
+      for (int i = lo[0]; i <= hi[0]; ++i) {
+        const double x = pos(g, P, 0, i, true);
+        const double radius = radius_of(x, y, z);
+        const double v = edge_in ? interp_edge(g, type, s0, radius) : interp_cc(g, type, s0, radius);
+        if (vec) {
+          cart(i, j, k, 0) = v * x * (1.0 / radius);
+          cart(i, j, k, 1) = v * y * (1.0 / radius);
+          cart(i, j, k, 2) = v * z * (1.0 / radius);
+        } else {
+          cart(i, j, k, 0) = v;
+        }
+      }
+    }
+  }
+}
+
+// loop bounds of the face arrays: lo-1:hi+1 transverse, lo-1:hi+2 normal (fill_3d_data.f90:651-677)
+static Box mac_box(const int* lo, const int* hi, int d) {
+  Box b;
+  for (int q = 0; q < 3; ++q) {
+    b.lo[q] = lo[q] - 1;
+    b.hi[q] = hi[q] + 1 + (q == d ? 1 : 0);
+  }
+  return b;
+}
+
+void make_w0mac_sphr(const mgpu_params& P, const mgpu_geom& g, const double* w0, Arr* w0mac, const Arr* w0_cart,
+                     const int* lo, const int* hi) {
+  check_types(g);
+  const int type = g.w0mac_interp_type;
+  if (type < 1 || type > 4) fail("Error: w0mac_interp_type not defined");
+  if (type == 1 && !w0_cart) fail("make_w0mac: w0mac_interp_type = 1 needs w0_cart");
+  for (int d = 0; d < 3; ++d) {
+    Arr& m = w0mac[d];
+    for_box(mac_box(lo, hi, d), [&](int i, int j, int k) {
+      if (type == 1) {  // :651-677
+        I3 l = sh(i, j, k, d, -1);
+        m(i, j, k) = 0.5 * ((*w0_cart)(l.i, l.j, l.k, d) + (*w0_cart)(i, j, k, d));
+      } else if (type == 2 || type == 3) {  // :684-759, :765-850
+        const double x = pos(g, P, 0, i, d != 0), y = pos(g, P, 1, j, d != 1), z = pos(g, P, 2, k, d != 2);
+        const double radius = radius_of(x, y, z);
+        const double v = interp_edge(g, type, w0, radius);
+        const double c = (d == 0) ? x : (d == 1 ? y : z);
+        m(i, j, k) = v * c / radius;
+      } else {  // :852-935: nodal values averaged over the four nodes of the face
+        auto nodal = [&](int ii, int jj, int kk) {
+          const double x = pos(g, P, 0, ii, false), y = pos(g, P, 1, jj, false), z = pos(g, P, 2, kk, false);
+          const double radius = radius_of(x, y, z);
+          const double v = interp_edge(g, 2, w0, radius);
+          const double c = (d == 0) ? x : (d == 1 ? y : z);
+          return v * c * (1.0 / radius);
+        };
+        const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;  // the two transverse directions, in the source's order
+        I3 a = {i, j, k}, b = sh(i, j, k, t1, 1), c2 = sh(i, j, k, t2, 1);
+        I3 e = sh(b.i, b.j, b.k, t2, 1);
+        m(i, j, k) = 0.25 * (nodal(a.i, a.j, a.k) + nodal(b.i, b.j, b.k) + nodal(c2.i, c2.j, c2.k) + nodal(e.i, e.j, e.k));
+      }
+    });
+  }
+}
+
+void make_s0mac_sphr(const mgpu_params& P, const mgpu_geom& g, const double* s0, Arr* s0mac, const Arr* s0_cart,
+                     const int* lo, const int* hi) {
+  check_types(g);
+  const int type = g.s0mac_interp_type;
+  if (type < 1 || type > 3) fail("Error: s0mac_interp_type not defined");
+  if (type == 1 && !s0_cart) fail("make_s0mac: s0mac_interp_type = 1 needs s0_cart");
+  for (int d = 0; d < 3; ++d) {
+    Arr& m = s0mac[d];
+    for_box(mac_box(lo, hi, d), [&](int i, int j, int k) {
+      if (type == 1) {  // :1046-1072
+        I3 l = sh(i, j, k, d, -1);
+        m(i, j, k) = 0.5 * ((*s0_cart)(i, j, k) + (*s0_cart)(l.i, l.j, l.k));
+      } else {  // :1077-1275
+        const double x = pos(g, P, 0, i, d != 0), y = pos(g, P, 1, j, d != 1), z = pos(g, P, 2, k, d != 2);
+        m(i, j, k) = interp_cc(g, type, s0, radius_of(x, y, z));
+      }
+    });
+  }
+}
+
+void addw0_sphr(Arr* umac, const Arr* w0mac, const int* lo, const int* hi, double mult) {
+  for (int d = 0; d < 3; ++d) {
+    Box b = grown(lo, hi, 3, 0);
+    b.hi[d] += 1;
+    for_box(b, [&](int i, int j, int k) { umac[d](i, j, k) = umac[d](i, j, k) + mult * w0mac[d](i, j, k); });
+  }
+}
+
+void mk_rhoX_flux_sphr(const mgpu_params& P, Arr* sflux, const Arr* sedge, const Arr* umac, const Arr* w0mac,
+                       const Arr* r0o, const Arr* r0n, int startcomp, int endcomp, const int* lo, const int* hi) {
+  const int rho = P.rho_comp - 1;
+  for (int comp = startcomp - 1; comp <= endcomp - 1; ++comp)
+    for (int d = 0; d < 3; ++d) {
+      Box b = grown(lo, hi, 3, 0);
+      b.hi[d] += 1;
+      for_box(b, [&](int i, int j, int k) {
+        const double vel = umac[d](i, j, k) + w0mac[d](i, j, k);
+        if (P.species_pred_type == MGPU_PREDICT_RHOPRIME_AND_X) {
+          const double rho0_edge = 0.5 * (r0o[d](i, j, k) + r0n[d](i, j, k));
+          sflux[d](i, j, k, comp) = vel * (rho0_edge + sedge[d](i, j, k, rho)) * sedge[d](i, j, k, comp);
+        } else if (P.species_pred_type == MGPU_PREDICT_RHOX) {
+          sflux[d](i, j, k, comp) = vel * sedge[d](i, j, k, comp);
+        } else if (P.species_pred_type == MGPU_PREDICT_RHO_AND_X) {
+          sflux[d](i, j, k, comp) = vel * sedge[d](i, j, k, rho) * sedge[d](i, j, k, comp);
+        }
+      });
+    }
+}
+
+void mk_rhoh_flux_sphr(const mgpu_params& P, Arr* sflux, const Arr* sedge, const Arr* umac, const Arr* w0mac,
+                       const Arr* r0o, const Arr* r0n, const Arr* h0o, const Arr* h0n, const int* lo, const int* hi) {
+  const int rho = P.rho_comp - 1, rhoh = P.rhoh_comp - 1;
+  const int ept = P.enthalpy_pred_type, spt = P.species_pred_type;
+  const bool have_h = (ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H);
+  const bool have_hprime = (ept == MGPU_PREDICT_HPRIME), have_rhoh = (ept == MGPU_PREDICT_RHOH);
+  if (have_hprime && spt == MGPU_PREDICT_RHO_AND_X)
+    fail("ERROR: predict_rho_and_X and predict_hprime not supported together");  // mkflux.f90:1408
+  if (have_hprime && spt == MGPU_PREDICT_RHOX) fail("ERROR: predict_rhoX and predict_hprime not supported together");
+  for (int d = 0; d < 3; ++d) {
+    Box b = grown(lo, hi, 3, 0);
+    b.hi[d] += 1;
+    for_box(b, [&](int i, int j, int k) {
+      const double vel = umac[d](i, j, k) + w0mac[d](i, j, k);
+      const double erho = sedge[d](i, j, k, rho), erhoh = sedge[d](i, j, k, rhoh);
+      double f;
+      if (have_h) {
+        if (spt == MGPU_PREDICT_RHOPRIME_AND_X) {
+          const double rho0_edge = 0.5 * (r0o[d](i, j, k) + r0n[d](i, j, k));
+          f = vel * (rho0_edge + erho) * erhoh;
+        } else {
+          f = vel * erho * erhoh;
+        }
+      } else if (have_hprime) {
+        const double rho0_edge = 0.5 * (r0o[d](i, j, k) + r0n[d](i, j, k));
+        const double h0_edge = 0.5 * (h0o[d](i, j, k) + h0n[d](i, j, k));
+        f = vel * (erho + rho0_edge) * (erhoh + h0_edge);
+      } else if (have_rhoh) {
+        f = vel * erhoh;
+      } else {
+        const double rho0_edge = 0.5 * (r0o[d](i, j, k) + r0n[d](i, j, k));
+        const double h0_edge = 0.5 * (h0o[d](i, j, k) + h0n[d](i, j, k));
+        f = vel * (rho0_edge * h0_edge + erhoh);
+      }
+      sflux[d](i, j, k, rhoh) = f;
+    });
+  }
+}
+
+void update_velocity_sphr(const mgpu_params& P, const Arr& uold, Arr& unew, const Arr* umac, const Arr* uedge,
+                          const Arr& force, const Arr& sponge, const Arr* w0mac, const int* lo, const int* hi) {
+  const double dt = P.dt;
+  const double* dx = P.dx;
+  const Arr &ux = uedge[0], &uy = uedge[1], &uz = uedge[2];
+  for_box(grown(lo, hi, 3, 0), [&](int i, int j, int k) {
+    const double ubar = 0.5 * (umac[0](i, j, k) + umac[0](i + 1, j, k));
+    const double vbar = 0.5 * (umac[1](i, j, k) + umac[1](i, j + 1, k));
+    const double wbar = 0.5 * (umac[2](i, j, k) + umac[2](i, j, k + 1));
+    for (int c = 0; c < 3; ++c) {
+      const double ugrad = ubar * (ux(i + 1, j, k, c) - ux(i, j, k, c)) / dx[0] +
+                           vbar * (uy(i, j + 1, k, c) - uy(i, j, k, c)) / dx[1] +
+                           wbar * (uz(i, j, k + 1, c) - uz(i, j, k, c)) / dx[2];
+      unew(i, j, k, c) = uold(i, j, k, c) - dt * ugrad + dt * force(i, j, k, c);
+    }
+  });
+  for_box(grown(lo, hi, 3, 0), [&](int i, int j, int k) {
+    const double w0x = 0.5 * (w0mac[0](i, j, k) + w0mac[0](i + 1, j, k));
+    const double w0y = 0.5 * (w0mac[1](i, j, k) + w0mac[1](i, j + 1, k));
+    const double w0z = 0.5 * (w0mac[2](i, j, k) + w0mac[2](i, j, k + 1));
+    for (int c = 0; c < 3; ++c) {
+      const double gx = (ux(i + 1, j, k, c) - ux(i, j, k, c)) / dx[0];
+      const double gy = (uy(i, j + 1, k, c) - uy(i, j, k, c)) / dx[1];
+      const double gz = (uz(i, j, k + 1, c) - uz(i, j, k, c)) / dx[2];
+      const double w0_grad = gx * w0x + gy * w0y + gz * w0z;
+      unew(i, j, k, c) = unew(i, j, k, c) - dt * w0_grad;
+    }
+    if (P.do_sponge)
+      for (int c = 0; c < 3; ++c) unew(i, j, k, c) = unew(i, j, k, c) * sponge(i, j, k);
+  });
+}
+
+void modify_scal_force_sphr(const mgpu_params& P, const mgpu_geom& g, Arr& force, const Arr& s, const Arr* umac,
+                            const Arr& s0c, const double* w0, bool fullform, const int* lo, const int* hi) {
+  check_types(g);
+  const int nr = g.nr_fine;
+  std::vector<double> divu(nr);
+  for (int r = 0; r < nr; ++r)  // modify_scal_force.f90:293-297
+    divu[r] = (g.r_edge_loc[r + 1] * g.r_edge_loc[r + 1] * w0[r + 1] - g.r_edge_loc[r] * g.r_edge_loc[r] * w0[r]) /
+              (g.dr * (g.r_cc_loc[r] * g.r_cc_loc[r]));
+  Arr divu_cart(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 1);
+  put_1d_array_on_cart_sphr(P, g, false, false, divu.data(), divu_cart, lo, hi);
+  const double* dx = P.dx;
+  const Arr &um = umac[0], &vm = umac[1], &wm = umac[2];
+  for_box(grown(lo, hi, 3, 0), [&](int i, int j, int k) {
+    const double divumac = (um(i + 1, j, k) - um(i, j, k)) / dx[0] + (vm(i, j + 1, k) - vm(i, j, k)) / dx[1] +
+                           (wm(i, j, k + 1) - wm(i, j, k)) / dx[2];
+    if (fullform) {
+      force(i, j, k) = force(i, j, k) - s(i, j, k) * (divumac + divu_cart(i, j, k));
+    } else {
+      const double c = s0c(i, j, k);
+      const double s0_xhi = (i < P.domhi[0]) ? 0.5 * (c + s0c(i + 1, j, k)) : c;
+      const double s0_xlo = (i > P.domlo[0]) ? 0.5 * (c + s0c(i - 1, j, k)) : c;
+      const double s0_yhi = (j < P.domhi[1]) ? 0.5 * (c + s0c(i, j + 1, k)) : c;
+      const double s0_ylo = (j > P.domlo[1]) ? 0.5 * (c + s0c(i, j - 1, k)) : c;
+      const double s0_zhi = (k < P.domhi[2]) ? 0.5 * (c + s0c(i, j, k + 1)) : c;
+      const double s0_zlo = (k > P.domlo[2]) ? 0.5 * (c + s0c(i, j, k - 1)) : c;
+      const double divs0u = (um(i + 1, j, k) * s0_xhi - um(i, j, k) * s0_xlo) / dx[0] +
+                            (vm(i, j + 1, k) * s0_yhi - vm(i, j, k) * s0_ylo) / dx[1] +
+                            (wm(i, j, k + 1) * s0_zhi - wm(i, j, k) * s0_zlo) / dx[2];
+      force(i, j, k) = force(i, j, k) - divs0u - (s(i, j, k) - c) * (divumac + divu_cart(i, j, k));
+    }
+  });
+}
+
+void pert_form_sphr(const mgpu_params& P, const mgpu_geom& g, Arr& s, const double* s0, bool flag, const int* lo,
+                    const int* hi) {
+  Arr s0_cart(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 1);
+  put_1d_array_on_cart_sphr(P, g, false, false, s0, s0_cart, lo, hi);
+  const int mult = flag ? -1 : 1;
+  for_box(grown(lo, hi, 3, 0), [&](int i, int j, int k) { s(i, j, k) = s(i, j, k) + mult * s0_cart(i, j, k); });
+}
+
+}  // namespace mo
+
+// ---------------------------------------------------------------------------------------------
+using namespace mo;
+extern std::string mo_g_err;
+#define MO_TRY try {
+#define MO_CATCH                         \
+  }                                      \
+  catch (const std::exception& e) {      \
+    mo_g_err = e.what();                 \
+    return 1;                            \
+  }                                      \
+  return 0;
+
+static void need3(const mgpu_params* p) {
+  if (p->dm != 3) fail("spherical geometry is 3-D only");
+}
+static void views3(const mgpu_fab* const* f, int i, Arr* out) {
+  for (int d = 0; d < 3; ++d) out[d] = Arr::view(f[d][i], 3);
+}
+
+extern "C" {
+
+int mo_put_1d_array_on_cart(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* s0, mgpu_fab* s0_cart,
+                            int is_input_edge_centered, int is_output_a_vector) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr c = Arr::view(s0_cart[i], 3);
+    if (c.nc < (is_output_a_vector ? 3 : 1)) fail("put_1d_array_on_cart: s0_cart has too few components");
+    put_1d_array_on_cart_sphr(*p, *g, is_input_edge_centered != 0, is_output_a_vector != 0, s0, c, s0_cart[i].lo,
+                              s0_cart[i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_make_w0mac(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* w0, mgpu_fab* const* w0mac,
+                  const mgpu_fab* w0_cart) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    if (w0mac[0][i].ng != 1) fail("Error: make_w0mac_3d_sphr assumes one ghost cell");  // fill_3d_data.f90:588
+    Arr m[3], c;
+    views3((const mgpu_fab* const*)w0mac, i, m);
+    if (w0_cart) c = Arr::view(w0_cart[i], 3);
+    make_w0mac_sphr(*p, *g, w0, m, w0_cart ? &c : nullptr, w0mac[0][i].lo, w0mac[0][i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_make_s0mac(const mgpu_params* p, const mgpu_geom* g, int nfabs, const double* s0, mgpu_fab* const* s0mac,
+                  const mgpu_fab* s0_cart) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    if (s0mac[0][i].ng != 1) fail("Error: make_s0mac assumes one ghost cell in s0mac");  // fill_3d_data.f90:992
+    Arr m[3], c;
+    views3((const mgpu_fab* const*)s0mac, i, m);
+    if (s0_cart) c = Arr::view(s0_cart[i], 3);
+    make_s0mac_sphr(*p, *g, s0, m, s0_cart ? &c : nullptr, s0mac[0][i].lo, s0mac[0][i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_addw0_sphr(const mgpu_params* p, int nfabs, mgpu_fab* const* umac, const mgpu_fab* const* w0mac, double mult) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr um[3], wm[3];
+    views3((const mgpu_fab* const*)umac, i, um);
+    views3(w0mac, i, wm);
+    addw0_sphr(um, wm, umac[0][i].lo, umac[0][i].hi, mult);
+  }
+  MO_CATCH
+}
+
+int mo_mk_rhoX_flux_sphr(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, const mgpu_fab* const* sedge,
+                         const mgpu_fab* const* umac, const mgpu_fab* const* w0mac, const mgpu_fab* const* rho0mac_old,
+                         const mgpu_fab* const* rho0mac_new, int startcomp, int endcomp) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr sf[3], se[3], um[3], wm[3], ro[3], rn[3];
+    views3((const mgpu_fab* const*)sflux, i, sf);
+    views3(sedge, i, se);
+    views3(umac, i, um);
+    views3(w0mac, i, wm);
+    views3(rho0mac_old, i, ro);
+    views3(rho0mac_new, i, rn);
+    mk_rhoX_flux_sphr(*p, sf, se, um, wm, ro, rn, startcomp, endcomp, sflux[0][i].lo, sflux[0][i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_mk_rhoh_flux_sphr(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, const mgpu_fab* const* sedge,
+                         const mgpu_fab* const* umac, const mgpu_fab* const* w0mac, const mgpu_fab* const* rho0mac_old,
+                         const mgpu_fab* const* rho0mac_new, const mgpu_fab* const* h0mac_old,
+                         const mgpu_fab* const* h0mac_new) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr sf[3], se[3], um[3], wm[3], ro[3], rn[3], ho[3], hn[3];
+    views3((const mgpu_fab* const*)sflux, i, sf);
+    views3(sedge, i, se);
+    views3(umac, i, um);
+    views3(w0mac, i, wm);
+    views3(rho0mac_old, i, ro);
+    views3(rho0mac_new, i, rn);
+    views3(h0mac_old, i, ho);
+    views3(h0mac_new, i, hn);
+    mk_rhoh_flux_sphr(*p, sf, se, um, wm, ro, rn, ho, hn, sflux[0][i].lo, sflux[0][i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_update_velocity_sphr(const mgpu_params* p, int nfabs, const mgpu_fab* uold, mgpu_fab* unew,
+                            const mgpu_fab* const* umac, const mgpu_fab* const* uedge, const mgpu_fab* force,
+                            const mgpu_fab* sponge, const mgpu_fab* const* w0mac) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr uo = Arr::view(uold[i], 3), un = Arr::view(unew[i], 3), fo = Arr::view(force[i], 3), sp = Arr::view(sponge[i], 3);
+    Arr um[3], ue[3], wm[3];
+    views3(umac, i, um);
+    views3(uedge, i, ue);
+    views3(w0mac, i, wm);
+    update_velocity_sphr(*p, uo, un, um, ue, fo, sp, wm, uold[i].lo, uold[i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_mkutrans_sphr(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                     mgpu_fab* const* utrans, const mgpu_fab* const* w0mac, const int* adv_bc, const int* phys_bc) {
+  MO_TRY
+  need3(p);
+  if (!p->spherical) fail("mkutrans_sphr: params.spherical must be 1");
+  for (int i = 0; i < nfabs; ++i) {
+    Arr ut = Arr::view(utilde[i], 3), uf = Arr::view(ufull[i], 3);
+    Arr tr[3], wm[3];
+    views3((const mgpu_fab* const*)utrans, i, tr);
+    views3(w0mac, i, wm);
+    mkutrans_box(*p, ut, uf, tr, nullptr, utilde[i].lo, utilde[i].hi, adv_bc, phys_bc, utilde[i].ng, wm);
+  }
+  MO_CATCH
+}
+
+int mo_velpred_sphr(const mgpu_params* p, int nfabs, const mgpu_fab* utilde, const mgpu_fab* ufull,
+                    mgpu_fab* const* umac, const mgpu_fab* const* utrans, const mgpu_fab* force,
+                    const mgpu_fab* const* w0mac, const int* adv_bc, const int* phys_bc) {
+  MO_TRY
+  need3(p);
+  if (!p->spherical) fail("velpred_sphr: params.spherical must be 1");
+  for (int i = 0; i < nfabs; ++i) {
+    Arr ut = Arr::view(utilde[i], 3), uf = Arr::view(ufull[i], 3), fa = Arr::view(force[i], 3);
+    Arr um[3], tr[3], wm[3];
+    views3((const mgpu_fab* const*)umac, i, um);
+    views3(utrans, i, tr);
+    views3(w0mac, i, wm);
+    velpred_box(*p, ut, uf, um, tr, fa, nullptr, utilde[i].lo, utilde[i].hi, adv_bc, phys_bc, utilde[i].ng, wm);
+  }
+  MO_CATCH
+}
+
+int mo_modify_scal_force_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* force, const mgpu_fab* s,
+                              const mgpu_fab* const* umac, const mgpu_fab* s0_cart, const double* w0, int comp,
+                              int fullform) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr fo = Arr::view(force[i], 3).comp(comp - 1), sa = Arr::view(s[i], 3).comp(comp - 1);
+    Arr sc = Arr::view(s0_cart[i], 3);
+    Arr um[3];
+    views3(umac, i, um);
+    modify_scal_force_sphr(*p, *g, fo, sa, um, sc, w0, fullform != 0, s[i].lo, s[i].hi);
+  }
+  MO_CATCH
+}
+
+int mo_put_in_pert_form_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* s, const double* s0,
+                             int comp, int flag) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr sa = Arr::view(s[i], 3).comp(comp - 1);
+    pert_form_sphr(*p, *g, sa, s0, flag != 0, s[i].lo, s[i].hi);
+  }
+  MO_CATCH
+}
+
+}  // extern "C"

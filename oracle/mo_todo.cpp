@@ -9,11 +9,11 @@ void bds_box(const mgpu_params&, const Arr&, Arr*, const Arr*, const Arr&, const
 #endif
 #ifndef MO_HAVE_VELPRED
 void mkutrans_box(const mgpu_params&, const Arr&, const Arr&, Arr*, const double*, const int*, const int*,
-                  const int*, const int*, int) {
+                  const int*, const int*, int, const Arr*) {
   fail("oracle: mkutrans not restated yet");
 }
 void velpred_box(const mgpu_params&, const Arr&, const Arr&, Arr*, const Arr*, const Arr&, const double*,
-                 const int*, const int*, const int*, const int*, int) {
+                 const int*, const int*, const int*, const int*, int, const Arr*) {
   fail("oracle: velpred not restated yet");
 }
 #endif

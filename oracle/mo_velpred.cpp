@@ -62,9 +62,9 @@ void comp_bc(const int* adv_bc, int dm, int c, int bc[3][2]) {
 
 // ---------------------------------------------------------------------------------------------
 void mkutrans_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr* utrans, const double* w0,
-                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u) {
+                  const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const Arr* w0mac) {
   const int dm = P.dm;
-  if (P.spherical) fail("oracle: mkutrans spherical not restated");
+  if (P.spherical && !w0mac) fail("mkutrans: spherical geometry needs w0mac");
   const double dt = P.dt, dt2 = 0.5 * dt, rel_eps = P.rel_eps;
   Box tb = grown(lo, hi, dm, 1), vb = grown(lo, hi, dm, 0);
   Arr vel[3];
@@ -120,7 +120,10 @@ void mkutrans_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr
     Arr& out = utrans[d];
     for_box(fb, [&](int i, int j, int k) {
       const int ir = (d == 0) ? i : (d == 1 ? j : k);
-      out(i, j, k) = riemann_full(ul(i, j, k), ur(i, j, k), radial, radial ? w0[ir] : 0.0, rel_eps);
+      if (P.spherical)  // mkutrans.f90:601-613 (x), :709, :817: every direction carries its w0mac
+        out(i, j, k) = riemann_full(ul(i, j, k), ur(i, j, k), true, w0mac[d](i, j, k), rel_eps);
+      else
+        out(i, j, k) = riemann_full(ul(i, j, k), ur(i, j, k), radial, radial ? w0[ir] : 0.0, rel_eps);
     });
   }
 }
@@ -128,9 +131,9 @@ void mkutrans_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr
 // ---------------------------------------------------------------------------------------------
 void velpred_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr* umac, const Arr* utrans,
                  const Arr& force, const double* w0, const int* lo, const int* hi, const int* adv_bc,
-                 const int* phys_bc, int ng_u) {
+                 const int* phys_bc, int ng_u, const Arr* w0mac) {
   const int dm = P.dm;
-  if (P.spherical) fail("oracle: velpred spherical not restated");
+  if (P.spherical && !w0mac) fail("velpred: spherical geometry needs w0mac");
   const double dt = P.dt, dt2 = 0.5 * dt, dt4 = dt / 4.0, dt6 = dt / 6.0, rel_eps = P.rel_eps;
   const bool trace = (P.ppm_trace_forces == 1) && P.ppm_type != 0;
   Box tb = grown(lo, hi, dm, 1), vb = grown(lo, hi, dm, 0);
@@ -270,7 +273,10 @@ void velpred_box(const mgpu_params& P, const Arr& utilde, const Arr& ufull, Arr*
     const bool radial = (d == dm - 1);
     for_box(fb, [&](int i, int j, int k) {
       const int ir = (d == 0) ? i : (d == 1 ? j : k);
-      out(i, j, k) = riemann_full(ml(i, j, k), mr(i, j, k), radial, radial ? w0[ir] : 0.0, rel_eps);
+      if (P.spherical)  // velpred.f90:1588-1603 (x), :1687, :1786
+        out(i, j, k) = riemann_full(ml(i, j, k), mr(i, j, k), true, w0mac[d](i, j, k), rel_eps);
+      else
+        out(i, j, k) = riemann_full(ml(i, j, k), mr(i, j, k), radial, radial ? w0[ir] : 0.0, rel_eps);
     });
     const int plo = pbc(phys_bc, dm, d, 0), phi = pbc(phys_bc, dm, d, 1);
     Box b = fb;

@@ -340,3 +340,170 @@ def test_episodes_bounds_checked_build_agrees(oracle, dm, n):
         res.append([u.valid(0).copy() for u in umac] + [snew.a.copy()])
     for x, y in zip(*res):
         assert np.array_equal(x, y) and np.isfinite(x).all()
+
+
+# ---- spherical geometry (SURVEY a3/a4/a7-a12 _3d_sphr branches, 8f2): no golden vectors in the reference ----------
+def _radius(fab, p, g, half):
+    """radius at every point of `fab` (incl. ghosts); half[d] = the coordinate is cell-centred in d"""
+    c = []
+    for d in range(3):
+        i = np.arange(fab.shape[3 - d]) + (fab.lo[d] - fab.ng)
+        c.append(g.prob_lo[d] + (i + (0.5 if half[d] else 0.0)) * p.dx[d] - g.center[d])
+    X, Y, Z = c[0][None, None, :], c[1][None, :, None], c[2][:, None, None]
+    return np.sqrt(X ** 2 + Y ** 2 + Z ** 2), (X, Y, Z)
+
+
+@pytest.mark.parametrize("edge", [False, True])
+@pytest.mark.parametrize("itype", [1, 2, 3])
+def test_sphr_put_1d_array_on_cart_linear_profile(oracle, edge, itype):
+    """A linear radial profile is reproduced exactly by the linear and quadratic interpolants and to dr/2 by the
+    piecewise-constant one; the vector form is value * unit radial vector (fill_3d_data.f90:269-533)."""
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state(10, s0_interp_type=itype, w0_interp_type=itype)
+    p, g = st["p"], st["geom"]
+    a, b = 1.5, -0.7
+    prof = a + b * (g.r_edge_loc if edge else g.r_cc_loc)
+    for vec in (False, True):
+        cart = Fab(st["lo"], st["hi"], 2, 3 if vec else 1, dm=3)
+        oracle.put_1d_array_on_cart(p, g, prof, cart, edge, vec)
+        R, (X, Y, Z) = _radius(cart, p, g, [True] * 3)
+        v = slice(2, -2)
+        want = (a + b * R)[v, v, v]
+        tol = 1e-13 if itype > 1 else abs(b) * g.dr * (0.5 if edge else 1.0) + 1e-13
+        if vec:
+            for c, Q in enumerate((X, Y, Z)):
+                got = cart.a[c][v, v, v]
+                unit = (Q / R)[v, v, v] * np.ones_like(want)
+                assert np.abs(got - want * unit).max() <= tol
+        else:
+            assert np.abs(cart.a[0][v, v, v] - want).max() <= tol
+        assert np.all(cart.a[0][:2] == 0.0)  # ghost cells untouched
+
+
+@pytest.mark.parametrize("itype", [1, 2, 3, 4])
+def test_sphr_make_w0mac_linear_profile(oracle, itype):
+    """w0mac_d = w0(r) x_d / r on the faces for every interpolation choice (fill_3d_data.f90:621-940)"""
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state(10, ops=oracle, w0mac_interp_type=itype, center=[0.503, 0.497, 0.501])
+    p, g = st["p"], st["geom"]
+    b = 0.8
+    w0 = b * g.r_edge_loc
+    w0_cart = Fab(st["lo"], st["hi"], 2, 3, dm=3)
+    oracle.put_1d_array_on_cart(p, g, w0, w0_cart, True, True)
+    mac = face_fabs(st["lo"], st["hi"], 1, 1, 3)
+    oracle.make_w0mac(p, g, w0, mac, w0_cart)
+    for d in range(3):
+        R, XYZ = _radius(mac[d], p, g, [q != d for q in range(3)])
+        want = b * XYZ[d] * np.ones_like(R)  # w0(r) x_d / r = b x_d
+        sl = [slice(2, -2)] * 3  # faces whose two cells are valid (type 1 reads w0_cart ghosts that are zero here)
+        got = mac[d].a[0][tuple(sl)]
+        tol = 1e-13 if itype in (2, 3) else 0.3 * b * p.dx[0] ** 2 / 0.05  # averaging error of types 1 and 4
+        assert np.abs(got - want[tuple(sl)]).max() <= tol
+
+
+def test_sphr_make_s0mac_is_face_average(oracle):
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state(8, ops=oracle)
+    cart, mac = st["rho0_old_cart"], st["rho0mac_old"]
+    a = cart.a[0]
+    assert np.array_equal(mac[0].a[0][:, :, 1:-1], 0.5 * (a[1:-1, 1:-1, 2:-1] + a[1:-1, 1:-1, 1:-2])[:, :, :])
+    for t in (2, 3):
+        g = make_sphr_state(8, s0mac_interp_type=t)
+        prof = 2.0 - 0.4 * g["geom"].r_cc_loc
+        m = face_fabs(g["lo"], g["hi"], 1, 1, 3)
+        oracle.make_s0mac(g["p"], g["geom"], prof, m)
+        R, _ = _radius(m[1], g["p"], g["geom"], [True, False, True])
+        assert np.abs(m[1].a[0] - (2.0 - 0.4 * R)).max() <= 1e-13
+
+
+def test_sphr_flux_update_velocity_identities(oracle):
+    """addw0_sphr is undone by its negative; species fluxes equal (umac + w0mac)(rho0_edge + rho')X; uniform edge
+    states give unew = uold + dt force (update_vel.f90:227-360)."""
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state(8, ops=oracle)
+    p, lo, hi = st["p"], st["lo"], st["hi"]
+    um = [u.clone() for u in st["umac"]]
+    oracle.addw0_sphr(p, um, st["w0mac"], 1.0)
+    for d in range(3):
+        sl = [slice(1, -1)] * 3
+        assert np.array_equal(um[d].a[0][tuple(sl)], (st["umac"][d].a[0] + st["w0mac"][d].a[0])[tuple(sl)])
+    rng = np.random.default_rng(5)
+    sedge = face_fabs(lo, hi, 0, p.nscal, 3)
+    for f in sedge:
+        f.a[...] = rng.uniform(0.5, 1.5, f.shape)
+    sflux = face_fabs(lo, hi, 0, p.nscal, 3)
+    oracle.mk_rhoX_flux_sphr(p, sflux, sedge, st["umac"], st["w0mac"], st["rho0mac_old"], st["rho0mac_new"],
+                             p.spec_comp, p.spec_comp + p.nspec - 1)
+    for d in range(3):
+        sl = [slice(1, -1)] * 3
+        vel = (st["umac"][d].a[0] + st["w0mac"][d].a[0])[tuple(sl)]
+        r0 = 0.5 * (st["rho0mac_old"][d].a[0] + st["rho0mac_new"][d].a[0])[tuple(sl)]
+        want = vel * (r0 + sedge[d].a[p.rho_comp - 1]) * sedge[d].a[p.spec_comp - 1]
+        assert np.array_equal(sflux[d].a[p.spec_comp - 1], want)
+    uold = Fab(lo, hi, 3, 3, dm=3)
+    uold.a[...] = rng.uniform(-1, 1, uold.shape)
+    unew = uold.clone()
+    force = Fab(lo, hi, 1, 3, dm=3)
+    force.a[...] = rng.uniform(-1, 1, force.shape)
+    uedge = face_fabs(lo, hi, 0, 3, 3)
+    for f in uedge:
+        for c in range(3):
+            f.a[c] = 0.25 * (c + 1)
+    sponge = Fab(lo, hi, 0, 1, dm=3)
+    sponge.a[...] = 1.0
+    oracle.update_velocity_sphr(p, uold, unew, st["umac"], uedge, force, sponge, st["w0mac"])
+    for c in range(3):
+        assert np.array_equal(unew.valid(c), uold.valid(c) - p.dt * 0.0 + p.dt * force.a[c][1:-1, 1:-1, 1:-1])
+
+
+def test_sphr_modify_scal_force_uniform_state(oracle):
+    """s = s0 = const, w0 = 0: force -= s0 * div(umac) (modify_scal_force.f90:330-356); pert form round trip."""
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state(8, ops=oracle)
+    p, g, lo, hi = st["p"], st["geom"], st["lo"], st["hi"]
+    s = st["s"].clone()
+    s.a[p.rho_comp - 1] = 1.75
+    s0_cart = Fab(lo, hi, 1, 1, dm=3)
+    s0_cart.a[...] = 1.75
+    force = Fab(lo, hi, 1, p.nscal, dm=3)
+    w0 = np.zeros(g.nr_fine + 1)
+    oracle.modify_scal_force_sphr(p, g, force, s, st["umac"], s0_cart, w0, p.rho_comp, False)
+    u, v, w = [m.a[0] for m in st["umac"]]
+    divu = ((u[1:-1, 1:-1, 2:-1] - u[1:-1, 1:-1, 1:-2]) / p.dx[0] + (v[1:-1, 2:-1, 1:-1] - v[1:-1, 1:-2, 1:-1]) / p.dx[1]
+            + (w[2:-1, 1:-1, 1:-1] - w[1:-2, 1:-1, 1:-1]) / p.dx[2])
+    assert np.abs(force.valid(p.rho_comp - 1) + 1.75 * divu).max() <= 1e-12 * np.abs(divu).max() * 1.75 + 1e-12
+    s2 = st["s"].clone()
+    oracle.put_in_pert_form_sphr(p, g, s2, st["rad"]["rho0_old"], p.rho_comp, True)
+    assert np.abs(s2.valid(0) - st["s"].valid(0)).max() > 0.05
+    oracle.put_in_pert_form_sphr(p, g, s2, st["rad"]["rho0_old"], p.rho_comp, False)
+    assert np.abs(s2.valid(0) - st["s"].valid(0)).max() <= 1e-14
+    assert np.array_equal(s2.a[0][:4], st["s"].a[0][:4])  # ghost cells untouched
+
+
+def test_sphr_velpred_runs_and_reduces_to_planar_riemann(oracle):
+    """With w0mac = 0 the spherical Riemann problems of mkutrans / velpred equal the planar ones with w0 = 0
+    (mkutrans.f90:601-631, velpred.f90:1588-1621)."""
+    from sphr_common import make_sphr_state
+    from synth import make_vel_state
+
+    vs = make_vel_state(3, 8, phys_bc=[[abi.OUTLET, abi.OUTLET]] * 3, w0amp=0.0, oracle=oracle)
+    p = vs["p"]
+    lo, hi = vs["lo"], vs["hi"]
+    zero_mac = face_fabs(lo, hi, 1, 1, 3)
+    out = []
+    for sph in (0, 1):
+        p.spherical = sph
+        ut = face_fabs(lo, hi, 1, 1, 3)
+        if sph:
+            oracle.mkutrans_sphr(p, vs["utilde"], vs["ufull"], ut, zero_mac, vs["adv_bc"], vs["phys_bc"])
+        else:
+            oracle.mkutrans(p, vs["utilde"], vs["ufull"], ut, np.zeros(p.nr + 1), vs["adv_bc"], vs["phys_bc"])
+        out.append(ut)
+    p.spherical = 0
+    for d in range(3):
+        assert np.array_equal(out[0][d].a, out[1][d].a)

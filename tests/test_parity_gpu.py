@@ -583,3 +583,159 @@ def test_enthalpy_advance(gpu_ops, oracle, dm, n, ept, which_step, bcset, bds):
         out.append([sold, snew, force] + sedge + sflux + umac)
     for g, c in zip(*out):
         check(g.a, c.a)
+
+
+# ---- spherical geometry (SURVEY config C5 in miniature): every *_3d_sphr operator against the oracle ------------------
+@pytest.mark.parametrize("s0t,w0t", [(3, 2), (1, 1), (2, 3)])
+@pytest.mark.parametrize("vec", [False, True])
+@pytest.mark.parametrize("edge", [False, True])
+def test_sphr_put_1d_array_on_cart(gpu_ops, oracle, s0t, w0t, vec, edge):
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state((12, 10, 14), s0_interp_type=s0t, w0_interp_type=w0t)
+    p, g = st["p"], st["geom"]
+    prof = st["rad"]["w0"] if edge else st["rad"]["rho0_old"]
+    out = []
+    for o in (gpu_ops, oracle):
+        c = Fab(st["lo"], st["hi"], 2, 3 if vec else 1, dm=3)
+        c.a[...] = -5.0
+        o.put_1d_array_on_cart(p, g, prof, c, edge, vec)
+        out.append(c)
+    assert same(out[0].a, out[1].a)
+
+
+@pytest.mark.parametrize("itype", [1, 2, 3, 4])
+def test_sphr_make_w0mac_s0mac(gpu_ops, oracle, itype):
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state((12, 10, 14), ops=oracle, w0mac_interp_type=itype, s0mac_interp_type=min(itype, 3),
+                         center=[0.503, 0.41, 0.58])
+    p, g = st["p"], st["geom"]
+    res = []
+    for o in (gpu_ops, oracle):
+        wm = face_fabs(st["lo"], st["hi"], 1, 1, 3, fill=-3.0)
+        sm = face_fabs(st["lo"], st["hi"], 1, 1, 3, fill=-3.0)
+        o.make_w0mac(p, g, st["rad"]["w0"], wm, st["w0_cart"])
+        o.make_s0mac(p, g, st["rad"]["rho0_old"], sm, st["rho0_old_cart"])
+        res.append(wm + sm)
+    for a, b in zip(*res):
+        assert same(a.a, b.a)
+
+
+@pytest.mark.parametrize("spt", [abi.PREDICT_RHOPRIME_AND_X, abi.PREDICT_RHOX, abi.PREDICT_RHO_AND_X])
+def test_sphr_fluxes_addw0(gpu_ops, oracle, spt):
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state((12, 10, 14), ops=oracle)
+    p, lo, hi = st["p"], st["lo"], st["hi"]
+    p.species_pred_type = spt
+    rng = np.random.default_rng(11)
+    sedge = face_fabs(lo, hi, 0, p.nscal, 3)
+    for f in sedge:
+        f.a[...] = rng.uniform(0.5, 1.5, f.shape)
+    epts = [abi.PREDICT_RHOH, abi.PREDICT_RHOHPRIME, abi.PREDICT_H, abi.PREDICT_T_THEN_H]
+    if spt == abi.PREDICT_RHOPRIME_AND_X:
+        epts.append(abi.PREDICT_HPRIME)
+    res = []
+    for o in (gpu_ops, oracle):
+        um = [u.clone() for u in st["umac"]]
+        o.addw0_sphr(p, um, st["w0mac"], 1.0)
+        sflux = face_fabs(lo, hi, 0, p.nscal, 3, fill=-9.0)
+        o.mk_rhoX_flux_sphr(p, sflux, sedge, st["umac"], st["w0mac"], st["rho0mac_old"], st["rho0mac_new"], p.spec_comp,
+                            p.spec_comp + p.nspec - 1)
+        o.mk_rhoX_flux_sphr(p, sflux, sedge, st["umac"], st["w0mac"], st["rho0mac_old"], st["rho0mac_new"], p.trac_comp,
+                            p.trac_comp + p.ntrac - 1)
+        outs = um + sflux
+        for ept in epts:
+            p.enthalpy_pred_type = ept
+            hf = face_fabs(lo, hi, 0, p.nscal, 3, fill=-9.0)
+            o.mk_rhoh_flux_sphr(p, hf, sedge, st["umac"], st["w0mac"], st["rho0mac_old"], st["rho0mac_new"],
+                                st["rhoh0mac_old"], st["rhoh0mac_new"])
+            outs += hf
+        res.append(outs)
+    for a, b in zip(*res):
+        assert same(a.a, b.a)
+    if spt != abi.PREDICT_RHOPRIME_AND_X:  # mkflux.f90:1406-1412
+        p.enthalpy_pred_type = abi.PREDICT_HPRIME
+        hf = face_fabs(lo, hi, 0, p.nscal, 3)
+        for o in (gpu_ops, oracle):
+            with pytest.raises(Exception, match="not supported together"):
+                o.mk_rhoh_flux_sphr(p, hf, sedge, st["umac"], st["w0mac"], st["rho0mac_old"], st["rho0mac_new"],
+                                    st["rhoh0mac_old"], st["rhoh0mac_new"])
+
+
+@pytest.mark.parametrize("do_sponge", [0, 1])
+def test_sphr_update_velocity(gpu_ops, oracle, do_sponge):
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state((12, 10, 14), ops=oracle)
+    p, lo, hi = st["p"], st["lo"], st["hi"]
+    p.do_sponge = do_sponge
+    rng = np.random.default_rng(21)
+    uold = Fab(lo, hi, 3, 3, dm=3)
+    uold.a[...] = rng.uniform(-1, 1, uold.shape)
+    force = Fab(lo, hi, 1, 3, dm=3)
+    force.a[...] = rng.uniform(-1, 1, force.shape)
+    uedge = face_fabs(lo, hi, 0, 3, 3)
+    for f in uedge:
+        f.a[...] = rng.uniform(-1, 1, f.shape)
+    sponge = Fab(lo, hi, 0, 1, dm=3)
+    sponge.a[...] = rng.uniform(0.5, 1.0, sponge.shape)
+    res = []
+    for o in (gpu_ops, oracle):
+        unew = uold.clone()
+        o.update_velocity_sphr(p, uold, unew, st["umac"], uedge, force, sponge, st["w0mac"])
+        res.append(unew)
+    assert same(res[0].a, res[1].a)
+
+
+@pytest.mark.parametrize("fullform", [False, True])
+@pytest.mark.parametrize("s0t", [1, 2, 3])
+def test_sphr_modify_scal_force_pert_form(gpu_ops, oracle, fullform, s0t):
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state((12, 10, 14), ops=oracle, s0_interp_type=s0t)
+    p, g, lo, hi = st["p"], st["geom"], st["lo"], st["hi"]
+    res = []
+    for o in (gpu_ops, oracle):
+        force = st["force"].clone()
+        o.modify_scal_force_sphr(p, g, force, st["s"], st["umac"], st["rho0_old_cart"], st["rad"]["w0"], p.rho_comp,
+                                 fullform)
+        s2 = st["s"].clone()
+        o.put_in_pert_form_sphr(p, g, s2, st["rad"]["rho0_old"], p.rho_comp, True)
+        s3 = s2.clone()
+        o.put_in_pert_form_sphr(p, g, s3, st["rad"]["rho0_old"], p.rho_comp, False)
+        res.append([force, s2, s3])
+    for a, b in zip(*res):
+        assert same(a.a, b.a)
+
+
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+def test_sphr_mkutrans_velpred(gpu_ops, oracle, ppm_type):
+    """advance_premac's two operators with spherical == 1: w0mac enters every Riemann problem"""
+    from sphr_common import make_sphr_state
+    from synth import fill_face_ghosts, make_vel_state
+
+    vs = make_vel_state(3, (12, 10, 14), phys_bc=[[abi.OUTLET, abi.OUTLET]] * 3, w0amp=0.0, oracle=oracle,
+                        ppm_type=ppm_type)
+    st = make_sphr_state((12, 10, 14), ops=oracle)
+    p, lo, hi = vs["p"], vs["lo"], vs["hi"]
+    p.spherical = 1
+    w0mac = st["w0mac"]
+    for m in w0mac:  # comparable in size to the velocities so that the upwinding decisions change
+        m.a[...] *= 20.0
+    res = []
+    for o in (gpu_ops, oracle):
+        ut = face_fabs(lo, hi, 1, 1, 3)
+        o.mkutrans_sphr(p, vs["utilde"], vs["ufull"], ut, w0mac, vs["adv_bc"], vs["phys_bc"])
+        fill_face_ghosts(ut, vs["pmask"], 3)
+        um = face_fabs(lo, hi, 1, 1, 3)
+        o.velpred_sphr(p, vs["utilde"], vs["ufull"], um, ut, vs["force"], w0mac, vs["adv_bc"], vs["phys_bc"])
+        res.append(ut + um)
+    for a, b in zip(*res):
+        assert same(a.a, b.a)
+    # the spherical Riemann problems must differ from the planar ones for this w0mac
+    p.spherical = 0
+    ut0 = face_fabs(lo, hi, 1, 1, 3)
+    oracle.mkutrans(p, vs["utilde"], vs["ufull"], ut0, np.zeros(p.nr + 1), vs["adv_bc"], vs["phys_bc"])
+    assert not same(ut0[0].a, res[1][0].a)
