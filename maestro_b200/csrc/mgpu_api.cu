@@ -279,8 +279,10 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   const double* rho0_edge_old = upload_small(e_old.data(), nr + 1);
   const double* rho0_edge_new = upload_small(e_new.data(), nr + 1);
   int nodal_d[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-  auto fill_umac = [&]() {  // addw0.f90:85-93
+  auto fill_umac = [&]() {  // addw0.f90:85-93; the dm exchanges travel as one NCCL group
+    FillBatch fb;
     for (int d = 0; d < dm; ++d) fill_boundary_dev(P, umac[d], lo, hi, 1, nodal_d[d], 1, 1, 1, adv_bc, pmask, false);
+    fb.run();
   };
 
   set_dev(scal_force.p, 0.0, scal_force.size());  // :101-103
@@ -291,13 +293,17 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   }
   addw0_dev(P, umac, w0, 1.0, lo, hi);  // :148
   fill_umac();
-  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {  // :160
-    convert_rhoX_to_X_dev(P, sold, true, lo, hi);
-    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, foextrap_comp, P.nspec, adv_bc, pmask, true);
-  }
-  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) {  // :166
-    put_in_pert_form_dev(P, sold, rho0_old, P.rho_comp, true, lo, hi);
-    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
+  // :160-171.  rhoX -> X and rho -> rho' act on the valid cells of different components, so both run before the two
+  // ghost fills, which then share one NCCL group (same values as the reference's convert, fill, perturb, fill)
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) convert_rhoX_to_X_dev(P, sold, true, lo, hi);
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) put_in_pert_form_dev(P, sold, rho0_old, P.rho_comp, true, lo, hi);
+  {
+    FillBatch fb;
+    if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X)
+      fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, foextrap_comp, P.nspec, adv_bc, pmask, true);
+    if (spt == MGPU_PREDICT_RHOPRIME_AND_X)
+      fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
+    fb.run();
   }
   auto edge = [&](int scomp, int ncomp, bool cons) {
     for (int n = 0; n < ncomp; ++n) {
@@ -318,13 +324,16 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   } else {
     edge(P.rho_comp, 1, false);  // :216-224
   }
-  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) {  // :229
-    put_in_pert_form_dev(P, sold, rho0_old, P.rho_comp, false, lo, hi);
-    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
-  }
-  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {  // :235
-    convert_rhoX_to_X_dev(P, sold, false, lo, hi);
-    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
+  // :229-240: rho' -> rho, then X -> rhoX with the restored rho (valid cells), then both ghost fills as one group
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) put_in_pert_form_dev(P, sold, rho0_old, P.rho_comp, false, lo, hi);
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) convert_rhoX_to_X_dev(P, sold, false, lo, hi);
+  {
+    FillBatch fb;
+    if (spt == MGPU_PREDICT_RHOPRIME_AND_X)
+      fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
+    if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X)
+      fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
+    fb.run();
   }
   if (P.ntrac >= 1) edge(P.trac_comp, P.ntrac, false);  // :242-252
   addw0_dev(P, umac, w0, -1.0, lo, hi);                 // :258
@@ -353,10 +362,12 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   if (g_opt_fused) {
     // :280-366 in one launch: species + tracer fluxes, etarhoflux, update, density, floors
     flux_update_all_dev(P, fa, ua, g_opt_exact != 0);
+    FillBatch fb;
     fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
     fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
     if (P.ntrac >= 1)
       fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.trac_comp, dm + P.trac_comp, P.ntrac, adv_bc, pmask, false);
+    fb.run();
     return;
   }
   mk_rhoX_flux_dev(P, fa, P.spec_comp, P.spec_comp + P.nspec - 1);
@@ -375,7 +386,9 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
 static const int NODAL_D[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
 static void fill_faces_dev(const mgpu_params& P, DV* u, const int* lo, const int* hi, const int* adv_bc,
                            const int* pmask) {  // addw0.f90:85-93 / mkutrans.f90:105-115
+  FillBatch fb;
   for (int d = 0; d < P.dm; ++d) fill_boundary_dev(P, u[d], lo, hi, 1, NODAL_D[d], 1, 1, 1, adv_bc, pmask, false);
+  fb.run();
 }
 static DV arena_fab(const int* lo, const int* hi, int dm, int ng, const int* nodal, int nc) {
   DV v = make_view(nullptr, lo, hi, dm, ng, nodal, nc);

@@ -130,6 +130,7 @@ void comm_finalize() {
   g_comm = Comm();
 }
 
+static int g_group_depth = 0;  // > 0: inside halo_group_begin/end (one NCCL launch for the whole batch)
 // ghost planes of comps [c0, c0+nc) of s in the slab direction; returns false when there is nothing to exchange
 // (single rank: the caller wraps locally).  Enqueued on `stream`.
 bool halo_exchange_dev(const mgpu_params& P, const DV& s, const int* lo, const int* hi, int ng, const int* nodal,
@@ -141,7 +142,8 @@ bool halo_exchange_dev(const mgpu_params& P, const DV& s, const int* lo, const i
   const int r = pl.dir;
   const size_t cnt = (size_t)pl.plane_doubles * pl.nplanes;
   auto plane = [&](int c, int k) { return s.p + s.cs * (long)c + (long)(k - s.lo[r]) * pl.plane_doubles; };
-  prof_begin(TAG_HALO);
+  const bool outer = g_group_depth > 0;
+  if (!outer) prof_begin(TAG_HALO);
   MGPU_NCCL(g_nccl.GroupStart());
   for (int c = c0; c < c0 + nc; ++c) {
     // order per peer must be the same on both sides: (send up, recv from down, send down, recv from up)
@@ -151,9 +153,25 @@ bool halo_exchange_dev(const mgpu_params& P, const DV& s, const int* lo, const i
     if (pl.up_rank >= 0) MGPU_NCCL(g_nccl.Recv(plane(c, pl.recv_hi_k0), cnt, ncclDouble, pl.up_rank, g_comm.comm, stream));
   }
   MGPU_NCCL(g_nccl.GroupEnd());
-  count_launch();  // one grouped NCCL kernel
-  prof_end(TAG_HALO);
+  if (!outer) {
+    count_launch();  // one grouped NCCL kernel
+    prof_end(TAG_HALO);
+  }
   return true;
+}
+
+void halo_group_begin() {
+  if (!(g_comm.on && g_comm.nranks > 1)) return;
+  if (g_group_depth++ == 0) prof_begin(TAG_HALO);
+  MGPU_NCCL(g_nccl.GroupStart());
+}
+void halo_group_end() {
+  if (!(g_comm.on && g_comm.nranks > 1)) return;
+  MGPU_NCCL(g_nccl.GroupEnd());
+  if (--g_group_depth == 0) {
+    count_launch();  // one grouped NCCL kernel for every field of the batch
+    prof_end(TAG_HALO);
+  }
 }
 
 cudaStream_t comm_stream() { return g_comm.stream; }

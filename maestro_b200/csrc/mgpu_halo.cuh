@@ -18,6 +18,9 @@ cudaEvent_t comm_event(int which);
 // exchange the ghost planes (slab direction) of comps [c0, c0+nc) of s; false if single rank (caller wraps locally)
 bool halo_exchange_dev(const mgpu_params& P, const DV& s, const int* lo, const int* hi, int ng, const int* nodal,
                        int c0, int nc, const int* pmask, cudaStream_t stream);
+// one NCCL group around several halo_exchange_dev calls (NCCL groups nest): a single launch for all fields
+void halo_group_begin();
+void halo_group_end();
 void allreduce_minmax_dev(double* d_minmax2);
 
 }  // namespace mgpu

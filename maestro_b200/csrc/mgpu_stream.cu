@@ -472,16 +472,37 @@ __global__ void k_physbc(DV s, Box3 tb, int d, int side, int bc, int lo, int hi,
   }
 }
 
-void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, const int* hi, int ng,
-                       const int* nodal, int scomp, int bccomp, int ncomp, const int* adv_bc, const int* pmask,
-                       bool same_boundary) {
+// One ghost fill = (1) slab-direction exchange with the neighbouring ranks (NCCL), (2) in-box periodic wraps and
+// physical BCs.  Inside a FillBatch the requests are only recorded; the batch then issues ALL exchanges as one NCCL
+// group (one launch, one rendezvous with each neighbour instead of one per field) followed by the local parts in
+// the recorded order.  Requests of one batch must touch disjoint (fab, component) sets.
+namespace {
+struct FillReq {
+  mgpu_params P;
+  DV sfull;
+  int lo[3], hi[3], ng, nodal[3];
+  bool has_nodal;
+  int scomp, bccomp, ncomp;
+  const int* adv_bc;
+  int pmask[3];
+  bool same_boundary;
+};
+bool g_batching = false;
+std::vector<FillReq> g_batch;
+
+bool fill_exchange(const FillReq& r) {
+  return halo_exchange_dev(r.P, r.sfull, r.lo, r.hi, r.ng, r.has_nodal ? r.nodal : nullptr, r.scomp - 1, r.ncomp, r.pmask,
+                           ctx().stream);
+}
+
+void fill_local(const FillReq& r, bool slab) {
   Context& cx = ctx();
-  const int dm = P.dm;
-  if (ng == 0) return;
+  const mgpu_params& P = r.P;
+  const int dm = P.dm, ng = r.ng, ncomp = r.ncomp, scomp = r.scomp;
+  const int *lo = r.lo, *hi = r.hi, *pmask = r.pmask, *adv_bc = r.adv_bc;
+  const int* nodal = r.has_nodal ? r.nodal : nullptr;
+  const DV& sfull = r.sfull;
   const bool is_nodal = nodal && (nodal[0] || nodal[1] || nodal[2]);
-  // slab-partitioned domain: the slab-direction ghost planes come from the neighbouring ranks (NCCL), first, so
-  // that the in-box wraps and physical BCs below also cover the received planes (corners come out right)
-  const bool slab = halo_exchange_dev(P, sfull, lo, hi, ng, nodal, scomp - 1, ncomp, pmask, cx.stream);
   // periodic wraps: x, then y, then z (so edges/corners come out right), all components of the call per launch
   for (int d = 0; d < dm; ++d) {
     if (!pmask[d]) continue;
@@ -497,7 +518,7 @@ void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, con
   for (int n = 0; n < ncomp; ++n) {
     DV s = sfull.comp(scomp - 1 + n);
     if (is_nodal) continue;  // multifab_physbc_edgevel (FBoxLib) is left to the caller
-    const int bcc = same_boundary ? bccomp : bccomp + n;
+    const int bcc = r.same_boundary ? r.bccomp : r.bccomp + n;
     int bc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
     for (int d = 0; d < dm; ++d) {
       bc[d][0] = adv_bc[d + dm * (0 + 2 * (bcc - 1))];
@@ -525,6 +546,56 @@ void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, con
         MGPU_LAUNCH_CHECK();
       }
   }
+}
+}  // namespace
+
+void fill_batch_begin() {
+  if (g_batching) throw Error("mgpu: nested ghost-fill batch");
+  g_batching = true;
+  g_batch.clear();
+}
+void fill_batch_end() {
+  if (!g_batching) return;
+  g_batching = false;
+  std::vector<char> slab(g_batch.size(), 0);
+  // slab-partitioned domain: the slab-direction ghost planes come from the neighbouring ranks (NCCL), first, so
+  // that the in-box wraps and physical BCs below also cover the received planes (corners come out right)
+  halo_group_begin();
+  for (size_t q = 0; q < g_batch.size(); ++q) slab[q] = fill_exchange(g_batch[q]) ? 1 : 0;
+  halo_group_end();
+  for (size_t q = 0; q < g_batch.size(); ++q) fill_local(g_batch[q], slab[q] != 0);
+  g_batch.clear();
+}
+void fill_batch_abort() {
+  g_batching = false;
+  g_batch.clear();
+}
+
+void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, const int* hi, int ng,
+                       const int* nodal, int scomp, int bccomp, int ncomp, const int* adv_bc, const int* pmask,
+                       bool same_boundary) {
+  if (ng == 0) return;
+  FillReq r;
+  r.P = P;
+  r.sfull = sfull;
+  for (int d = 0; d < 3; ++d) {
+    r.lo[d] = d < P.dm ? lo[d] : 0;
+    r.hi[d] = d < P.dm ? hi[d] : 0;
+    r.nodal[d] = nodal ? nodal[d] : 0;
+    r.pmask[d] = d < P.dm ? pmask[d] : 0;
+  }
+  r.has_nodal = nodal != nullptr;
+  r.ng = ng;
+  r.scomp = scomp;
+  r.bccomp = bccomp;
+  r.ncomp = ncomp;
+  r.adv_bc = adv_bc;
+  r.same_boundary = same_boundary;
+  if (g_batching) {
+    g_batch.push_back(r);
+    return;
+  }
+  fill_local(r, fill_exchange(r));
 }
 
 }  // namespace mgpu

@@ -70,6 +70,17 @@ void modify_scal_force_dev(const mgpu_params& P, const DV& force, const DV& s, c
 void convert_rhoX_to_X_dev(const mgpu_params& P, const DV& s, bool flag, const int* lo, const int* hi);
 void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_dev, int comp, bool flag,
                           const int* lo, const int* hi);
+// Batched ghost fills: between begin and end fill_boundary_dev only records; end issues every slab exchange of the
+// batch as ONE NCCL group and then the local wraps / physical BCs in the recorded order (mgpu_stream.cu).
+void fill_batch_begin();
+void fill_batch_end();
+void fill_batch_abort();
+struct FillBatch {  // RAII: a throw inside the batch drops the recorded requests
+  bool done = false;
+  FillBatch() { fill_batch_begin(); }
+  void run() { done = true; fill_batch_end(); }
+  ~FillBatch() { if (!done) fill_batch_abort(); }
+};
 void fill_boundary_dev(const mgpu_params& P, const DV& s, const int* lo, const int* hi, int ng, const int* nodal,
                        int scomp, int bccomp, int ncomp, const int* adv_bc, const int* pmask, bool same_boundary);
 void sum_comps_dev(const DV& a, int dst, int c0, int ncomp);

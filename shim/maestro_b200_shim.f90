@@ -44,6 +44,14 @@ module maestro_b200_shim
      real(c_double) :: buoyancy_cutoff_factor, omega, sin_theta, cos_theta, rotation_radius
   end type mgpu_params
 
+  ! spherical geometry (geometry module + probin interpolation switches), include/maestro_b200.h mgpu_geom
+  type, bind(C), public :: mgpu_geom
+     real(c_double) :: center(3), prob_lo(3), dr
+     integer(c_int) :: nr_fine
+     type(c_ptr)    :: r_cc_loc, r_edge_loc      ! c_loc(r_cc_loc(1,0)), c_loc(r_edge_loc(1,0))
+     integer(c_int) :: s0_interp_type, w0_interp_type, s0mac_interp_type, w0mac_interp_type
+  end type mgpu_geom
+
   integer(c_int), parameter :: MGPU_HOST = 0
 
   interface
@@ -155,11 +163,123 @@ module maestro_b200_shim
        real(c_double), intent(in) :: w0(*)
        integer(c_int), intent(in) :: adv_bc(*), phys_bc(*)
      end function mgpu_velpred_c
+
+     ! ---- spherical geometry: the *_3d_sphr branches (fill_3d_data.f90:269,621,1017; addw0.f90:171;
+     !      mkflux.f90:509,1289; update_vel.f90:317; mkutrans.f90:601; velpred.f90:1588;
+     !      modify_scal_force.f90:256; put_in_pert_form.f90:185)
+     integer(c_int) function mgpu_put_1d_array_on_cart_c(p, g, nfabs, s0, s0_cart, is_input_edge_centered, &
+          is_output_a_vector) bind(C, name="mgpu_put_1d_array_on_cart")
+       import :: c_int, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs, is_input_edge_centered, is_output_a_vector
+       real(c_double), intent(in) :: s0(*)
+       type(mgpu_fab), intent(in) :: s0_cart(*)
+     end function mgpu_put_1d_array_on_cart_c
+
+     integer(c_int) function mgpu_make_w0mac_c(p, g, nfabs, w0, w0mac, w0_cart) bind(C, name="mgpu_make_w0mac")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs
+       real(c_double), intent(in) :: w0(*)
+       type(c_ptr), intent(in) :: w0mac(*)
+       type(mgpu_fab), intent(in) :: w0_cart(*)
+     end function mgpu_make_w0mac_c
+
+     integer(c_int) function mgpu_make_s0mac_c(p, g, nfabs, s0, s0mac, s0_cart) bind(C, name="mgpu_make_s0mac")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs
+       real(c_double), intent(in) :: s0(*)
+       type(c_ptr), intent(in) :: s0mac(*)
+       type(mgpu_fab), intent(in) :: s0_cart(*)
+     end function mgpu_make_s0mac_c
+
+     integer(c_int) function mgpu_addw0_sphr_c(p, nfabs, umac, w0mac, mult) bind(C, name="mgpu_addw0_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(c_ptr), intent(in) :: umac(*), w0mac(*)
+       real(c_double), value :: mult
+     end function mgpu_addw0_sphr_c
+
+     integer(c_int) function mgpu_mk_rhoX_flux_sphr_c(p, nfabs, sflux, sedge, umac, w0mac, rho0mac_old, &
+          rho0mac_new, startcomp, endcomp) bind(C, name="mgpu_mk_rhoX_flux_sphr")
+       import :: c_int, c_ptr, mgpu_params
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs, startcomp, endcomp
+       type(c_ptr), intent(in) :: sflux(*), sedge(*), umac(*), w0mac(*), rho0mac_old(*), rho0mac_new(*)
+     end function mgpu_mk_rhoX_flux_sphr_c
+
+     integer(c_int) function mgpu_mk_rhoh_flux_sphr_c(p, nfabs, sflux, sedge, umac, w0mac, rho0mac_old, &
+          rho0mac_new, h0mac_old, h0mac_new) bind(C, name="mgpu_mk_rhoh_flux_sphr")
+       import :: c_int, c_ptr, mgpu_params
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(c_ptr), intent(in) :: sflux(*), sedge(*), umac(*), w0mac(*), rho0mac_old(*), rho0mac_new(*)
+       type(c_ptr), intent(in) :: h0mac_old(*), h0mac_new(*)
+     end function mgpu_mk_rhoh_flux_sphr_c
+
+     integer(c_int) function mgpu_update_velocity_sphr_c(p, nfabs, uold, unew, umac, uedge, force, sponge, w0mac) &
+          bind(C, name="mgpu_update_velocity_sphr")
+       import :: c_int, c_ptr, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(in) :: uold(*), unew(*), force(*), sponge(*)
+       type(c_ptr), intent(in) :: umac(*), uedge(*), w0mac(*)
+     end function mgpu_update_velocity_sphr_c
+
+     integer(c_int) function mgpu_mkutrans_sphr_c(p, nfabs, utilde, ufull, utrans, w0mac, adv_bc, phys_bc) &
+          bind(C, name="mgpu_mkutrans_sphr")
+       import :: c_int, c_ptr, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(in) :: utilde(*), ufull(*)
+       type(c_ptr), intent(in) :: utrans(*), w0mac(*)
+       integer(c_int), intent(in) :: adv_bc(*), phys_bc(*)
+     end function mgpu_mkutrans_sphr_c
+
+     integer(c_int) function mgpu_velpred_sphr_c(p, nfabs, utilde, ufull, umac, utrans, force, w0mac, adv_bc, &
+          phys_bc) bind(C, name="mgpu_velpred_sphr")
+       import :: c_int, c_ptr, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(in) :: utilde(*), ufull(*), force(*)
+       type(c_ptr), intent(in) :: umac(*), utrans(*), w0mac(*)
+       integer(c_int), intent(in) :: adv_bc(*), phys_bc(*)
+     end function mgpu_velpred_sphr_c
+
+     integer(c_int) function mgpu_modify_scal_force_sphr_c(p, g, nfabs, force, s, umac, s0_cart, w0, comp, &
+          fullform) bind(C, name="mgpu_modify_scal_force_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs, comp, fullform
+       type(mgpu_fab), intent(in) :: force(*), s(*), s0_cart(*)
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: w0(*)
+     end function mgpu_modify_scal_force_sphr_c
+
+     integer(c_int) function mgpu_put_in_pert_form_sphr_c(p, g, nfabs, s, s0, comp, flag) &
+          bind(C, name="mgpu_put_in_pert_form_sphr")
+       import :: c_int, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs, comp, flag
+       type(mgpu_fab), intent(in) :: s(*)
+       real(c_double), intent(in) :: s0(*)
+     end function mgpu_put_in_pert_form_sphr_c
   end interface
 
   public :: mgpu_startup, mgpu_shutdown, mgpu_fill_params, mgpu_describe, mgpu_describe_edges, mgpu_check
   public :: mgpu_make_edge_scal_c, mgpu_bds_c, mgpu_mk_rhoX_flux_c, mgpu_mk_rhoh_flux_c, mgpu_update_scal_c
   public :: mgpu_update_velocity_c, mgpu_addw0_c, mgpu_mkutrans_c, mgpu_velpred_c
+  public :: mgpu_put_1d_array_on_cart_c, mgpu_make_w0mac_c, mgpu_make_s0mac_c, mgpu_addw0_sphr_c
+  public :: mgpu_mk_rhoX_flux_sphr_c, mgpu_mk_rhoh_flux_sphr_c, mgpu_update_velocity_sphr_c
+  public :: mgpu_mkutrans_sphr_c, mgpu_velpred_sphr_c, mgpu_modify_scal_force_sphr_c, mgpu_put_in_pert_form_sphr_c
+  public :: mgpu_fill_geom
   public :: make_edge_scal_gpu
 
 contains
@@ -225,6 +345,23 @@ contains
   end subroutine mgpu_fill_params
 
   ! what dataptr/get_box/nghost give the reference kernels (make_edge_scal.f90:70-76), per local fab
+  ! spherical geometry from the geometry module and probin (Source/geometry.f90, Source/_parameters:632-651)
+  subroutine mgpu_fill_geom(g)
+    use geometry, only: center, dr, nr_fine, r_cc_loc, r_edge_loc
+    use probin_module, only: prob_lo, s0_interp_type, w0_interp_type, s0mac_interp_type, w0mac_interp_type
+    type(mgpu_geom), intent(out) :: g
+    g%center = center(1:3)
+    g%prob_lo = prob_lo(1:3)
+    g%dr = dr(1)
+    g%nr_fine = nr_fine
+    g%r_cc_loc = c_loc(r_cc_loc(1,0))
+    g%r_edge_loc = c_loc(r_edge_loc(1,0))
+    g%s0_interp_type = s0_interp_type
+    g%w0_interp_type = w0_interp_type
+    g%s0mac_interp_type = s0mac_interp_type
+    g%w0mac_interp_type = w0mac_interp_type
+  end subroutine mgpu_fill_geom
+
   subroutine mgpu_describe(mf, d)
     type(multifab), intent(in) :: mf
     type(mgpu_fab), intent(out) :: d(:)

@@ -31,14 +31,15 @@ def main():
     dm = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     bcset = sys.argv[2] if len(sys.argv) > 2 else "periodic"
     ppm_type = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    exact = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     ops = lib.init(local)
     slab.comm_init_from_torch(lib.load(), "cuda:%d" % local)
-    lib.set_option("exact", 1)
+    lib.set_option("exact", exact)  # 0: the FAST kernels (upwind-first fused edge kernel on interior slabs)
     r = dm - 1
-    n = [16, 12, 8 * world] if dm == 3 else [24, 10 * world]
+    n = ([16, 12, 8 * world] if exact else [40, 12, 10 * world]) if dm == 3 else [24, 10 * world]
     walls = [[abi.PERIODIC, abi.PERIODIC]] * (dm - 1) + [[abi.SLIP_WALL, abi.OUTLET]]
     phys = None if bcset == "periodic" else walls
     st = make_state(dm, n, phys_bc=phys, ppm_type=ppm_type)

@@ -420,8 +420,9 @@ def test_density_advance_bds(gpu_ops, oracle, dm, n, spt):
 
 
 # ---- multi-GPU: slab partition + NCCL halo exchange (needs >= 2 GPUs; run with gpurun --gpus 2) -------------
-@pytest.mark.parametrize("dm,bcset,ppm_type", [(3, "periodic", 1), (3, "walls", 2), (2, "walls", 2)])
-def test_multi_gpu_density_advance(gpu_ops, dm, bcset, ppm_type):
+@pytest.mark.parametrize("dm,bcset,ppm_type,exact", [(3, "periodic", 1, 1), (3, "walls", 2, 1), (2, "walls", 2, 1),
+                                                      (3, "periodic", 1, 0), (3, "periodic", 2, 0)])
+def test_multi_gpu_density_advance(gpu_ops, dm, bcset, ppm_type, exact):
     import os
     import subprocess
     import sys
@@ -435,7 +436,7 @@ def test_multi_gpu_density_advance(gpu_ops, dm, bcset, ppm_type):
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(here, "mgpu_rank_parity.py"), str(dm),
-           bcset, str(ppm_type)]
+           bcset, str(ppm_type), str(exact)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" OK ") == world
