@@ -242,7 +242,7 @@ static void fill_flux_args(const mgpu_params& P, FluxArgs& a, const int* lo, con
 // make_edge_scal for one component: fused single-launch kernel when it covers the case, else the staged path
 static void edge_one_comp(const mgpu_params& P, const DV& s, DV* sedge, const DV* umac, const DV& force,
                           const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel,
-                          bool is_cons, int ng_s, int ng_f) {
+                          bool is_cons, int ng_s, int ng_f, bool force_zero = false) {
   for (int d = 0; d < P.dm; ++d) {  // validate BC codes up front (make_edge_scal.f90:853)
     for (int side = 0; side < 2; ++side) {
       const int bc = adv_bc[d + P.dm * (side + 2 * (bccomp - 1))];
@@ -253,7 +253,7 @@ static void edge_one_comp(const mgpu_params& P, const DV& s, DV* sedge, const DV
   }
   if (g_opt_fused && fused_edge_supported(P, is_cons)) {
     fused_edge_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, ng_s, ng_f, g_opt_kchunk,
-                   g_opt_exact != 0);
+                   g_opt_exact != 0, force_zero);
   } else {
     size_t mark = arena_mark();
     make_edge_scal_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, is_cons, ng_s, ng_f);
@@ -285,18 +285,24 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
     fb.run();
   };
 
-  set_dev(scal_force.p, 0.0, scal_force.size());  // :101-103
+  // "lean" episode (FAST arithmetic, fused edge kernel for every component): the forces of the species and tracers
+  // are identically zero (:99-103), so the edge kernels do not read them and only the density component of
+  // scal_force has to be zero before modify_scal_force writes it; scal_force is zeroed once, at the end (:349-351).
+  const bool lean = g_opt_exact == 0 && g_opt_fused && P.bds_type == 0 && fused_edge_supported(P, false) &&
+                    (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X);
+  if (lean) set_dev(scal_force.p + scal_force.cs * (P.rho_comp - 1), 0.0, scal_force.cs);
+  else set_dev(scal_force.p, 0.0, scal_force.size());  // :101-103
   if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {  // :119-128
     modify_scal_force_dev(P, scal_force, sold, umac, rho0_old, rho0_edge_old, w0, P.rho_comp,
-                          spt == MGPU_PREDICT_RHO_AND_X, lo, hi, g_opt_exact == 0);
+                          spt == MGPU_PREDICT_RHO_AND_X, lo, hi, g_opt_exact == 0, lean);
     fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
   }
   addw0_dev(P, umac, w0, 1.0, lo, hi);  // :148
   fill_umac();
   // :160-171.  rhoX -> X and rho -> rho' act on the valid cells of different components, so both run before the two
   // ghost fills, which then share one NCCL group (same values as the reference's convert, fill, perturb, fill)
-  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) convert_rhoX_to_X_dev(P, sold, true, lo, hi);
-  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) put_in_pert_form_dev(P, sold, rho0_old, P.rho_comp, true, lo, hi);
+  species_form_dev(P, sold, rho0_old, spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X,
+                   spt == MGPU_PREDICT_RHOPRIME_AND_X, true, lo, hi);
   {
     FillBatch fb;
     if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X)
@@ -305,7 +311,7 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
       fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
     fb.run();
   }
-  auto edge = [&](int scomp, int ncomp, bool cons) {
+  auto edge = [&](int scomp, int ncomp, bool cons, bool force_zero = false) {
     for (int n = 0; n < ncomp; ++n) {
       if (P.bds_type != 0) {  // density_advance.f90:183-185 etc.
         size_t mark = arena_mark();
@@ -314,19 +320,19 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
         continue;
       }
       edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, scomp - 1 + n, dm + scomp + n, false, cons, ng_s,
-                    ng_f);
+                    ng_f, force_zero);
     }
   };
   if (spt == MGPU_PREDICT_RHOX) edge(P.spec_comp, P.nspec, true);  // :190-198
-  else edge(P.spec_comp, P.nspec, false);                            // :178-186
+  else edge(P.spec_comp, P.nspec, false, lean);                      // :178-186
   if (spt == MGPU_PREDICT_RHOX) {  // :204-213
     for (int d = 0; d < dm; ++d) sum_comps_dev(sedge[d], P.rho_comp - 1, P.spec_comp - 1, P.nspec);
   } else {
     edge(P.rho_comp, 1, false);  // :216-224
   }
   // :229-240: rho' -> rho, then X -> rhoX with the restored rho (valid cells), then both ghost fills as one group
-  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) put_in_pert_form_dev(P, sold, rho0_old, P.rho_comp, false, lo, hi);
-  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) convert_rhoX_to_X_dev(P, sold, false, lo, hi);
+  species_form_dev(P, sold, rho0_old, spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X,
+                   spt == MGPU_PREDICT_RHOPRIME_AND_X, false, lo, hi);
   {
     FillBatch fb;
     if (spt == MGPU_PREDICT_RHOPRIME_AND_X)
@@ -335,7 +341,7 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
       fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
     fb.run();
   }
-  if (P.ntrac >= 1) edge(P.trac_comp, P.ntrac, false);  // :242-252
+  if (P.ntrac >= 1) edge(P.trac_comp, P.ntrac, false, lean);  // :242-252
   addw0_dev(P, umac, w0, -1.0, lo, hi);                 // :258
   fill_umac();
 

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(BX* BY, MGPU_FUSED_MINB) k_fused_edge(FusedArg
     pre_v = pv[o_v];
     if (ty == BY - 1) pre_v1 = pv1[o_v];
     pre_w1 = pw[o_w + w_sz];
-    pre_f = pf[o_f];
+    pre_f = a.force_zero ? 0.0 : pf[o_f];
     o_s += s_sz; o_u += u_sz; o_v += v_sz; o_w += w_sz; o_f += f_sz;
   };
   pre_w = pw[o_w];
@@ -483,12 +483,13 @@ bool fused_edge_supported(const mgpu_params& P, bool is_cons) {
 
 void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
                     const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
-                    int ng_f, int kchunk, bool exact) {
+                    int ng_f, int kchunk, bool exact, bool force_zero) {
   if (P.ppm_type == 2 && ng_s < 4) throw Error("Need 4 ghost cells for ppm_type=2");  // ppm.f90:1864-1866
   if (ng_s < 3) throw Error("make_edge_scal: need at least 3 ghost cells");
   if (ng_f < 1) throw Error("make_edge_scal: force needs at least 1 ghost cell");
   FusedArgs a;
   a.slope_order = P.slope_order;
+  a.force_zero = force_zero;
   a.dt = P.dt;
   a.rel_eps = P.rel_eps;
   bool any_bc = false;

@@ -21,6 +21,7 @@ struct FusedArgs {
   int bclo[3], bchi[3];
   bool velnorm[3];
   int kchunk;  // z planes per CTA
+  bool force_zero;  // the force of this component is identically zero: do not read it (density_advance.f90:99-103)
   double dt, dx[3], rel_eps;
   DV s, force;  // single-component views
   DV umac[3];
@@ -33,7 +34,7 @@ bool fused_edge_supported(const mgpu_params& P, bool is_cons);
 // exact: bit-identical arithmetic (-fmad=false build); otherwise the FAST build (dt/dx folded, FMA)
 void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
                     const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
-                    int ng_f, int kchunk, bool exact);
+                    int ng_f, int kchunk, bool exact, bool force_zero = false);
 void fused_edge_launch_exact(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
 void fused_edge_launch_fast(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
 // second design (mgpu_fused2.cu): upwind-first, all faces INTERIOR, FAST arithmetic only

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     ld_v1 = gv[q_v + v_row];
     ld_w1 = gw[q_w];
     ld_s = gs[q_s];
-    const double f2 = gf[q_f];  // consumed at the end of this cell phase
+    const double f2 = a.force_zero ? 0.0 : gf[q_f];  // consumed at the end of this cell phase
 #pragma unroll
     for (int m = 0; m < SM::NH; ++m) {
       hS[m] = (h_idx[m] >= 0) ? gs[h_off[m]] : 0.0;

@@ -253,14 +253,14 @@ void addw0_dev(const mgpu_params& P, DV* umac, const double* w0_dev, double mult
 template <bool FAST>
 __global__ void k_modify_scal_force(DV force, DV s, DV u, DV v, DV w, Box3 vb, int dm, const double* s0,
                                     const double* s0_edge, const double* w0, double dx0, double dx1, double dx2,
-                                    bool fullform) {
+                                    bool fullform, bool assign) {
   int ix[3];
   if (!decode3(vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
   const int ir = ix[dm - 1];
   // FAST: dx0..dx2 hold 1/dx and the divisions become multiplications (last-bit differences)
 #define MGPU_DIV(x, h) (FAST ? (x) * (h) : (x) / (h))
-  double divu, divs0u, f = force(i, j, k);
+  double divu, divs0u, f = assign ? 0.0 : force(i, j, k);  // assign: the force is known to be zero on entry
   if (dm == 2) {
     divu = MGPU_DIV(u(i + 1, j, k) - u(i, j, k), dx0) + MGPU_DIV(v(i, j + 1, k) - v(i, j, k), dx1);
     divu = divu + MGPU_DIV(w0[ir + 1] - w0[ir], dx1);
@@ -288,16 +288,16 @@ __global__ void k_modify_scal_force(DV force, DV s, DV u, DV v, DV w, Box3 vb, i
 }
 void modify_scal_force_dev(const mgpu_params& P, const DV& force, const DV& s, const DV* umac, const double* s0,
                            const double* s0_edge, const double* w0, int comp, bool fullform, const int* lo,
-                           const int* hi, bool fast) {
+                           const int* hi, bool fast, bool assign) {
   Box3 vb = grown(lo, hi, P.dm, 0);
   if (fast)
     k_modify_scal_force<true><<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(
         force.comp(comp - 1), s.comp(comp - 1), umac[0], umac[1], P.dm == 3 ? umac[2] : umac[1], vb, P.dm, s0, s0_edge,
-        w0, 1.0 / P.dx[0], 1.0 / P.dx[1], 1.0 / P.dx[2], fullform);
+        w0, 1.0 / P.dx[0], 1.0 / P.dx[1], 1.0 / P.dx[2], fullform, assign);
   else
     k_modify_scal_force<false><<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(
         force.comp(comp - 1), s.comp(comp - 1), umac[0], umac[1], P.dm == 3 ? umac[2] : umac[1], vb, P.dm, s0, s0_edge,
-        w0, P.dx[0], P.dx[1], P.dx[2], fullform);
+        w0, P.dx[0], P.dx[1], P.dx[2], fullform, assign);
   MGPU_LAUNCH_CHECK();
 }
 
@@ -412,6 +412,43 @@ void convert_rhoX_to_X_dev(const mgpu_params& P, const DV& s, bool flag, const i
     MGPU_LAUNCH_CHECK();
   }
 }
+// rhoX <-> X of every species and rho <-> rho' in one pass over the valid cells (density_advance.f90:160-171 and
+// :229-240): the same statements as convert_rhoX_to_X_dev + put_in_pert_form_dev, rho read once per zone.
+//   forward : X = rhoX / rho (rho still the full density), then rho' = rho - rho0
+//   backward: rho = rho' + rho0, then rhoX = X * rho (the restored density)
+__global__ void k_species_form(DV s, Box3 vb, int rho, int spec0, int nspec, bool convert, bool pert, bool forward,
+                               int r, const double* base) {
+  int ix[3];
+  if (!decode3(vb, ix)) return;
+  const long o = s.off(ix[0], ix[1], ix[2]);
+  double* pr = s.p + o + s.cs * rho;
+  double rv = *pr;
+  if (forward) {
+    if (convert)
+      for (int n = 0; n < nspec; ++n) {
+        double* px = s.p + o + s.cs * (spec0 + n);
+        *px = *px / rv;
+      }
+    if (pert) *pr = rv + (-1.0) * base[ix[r]];
+  } else {
+    if (pert) {
+      rv = rv + 1.0 * base[ix[r]];
+      *pr = rv;
+    }
+    if (convert)
+      for (int n = 0; n < nspec; ++n) {
+        double* px = s.p + o + s.cs * (spec0 + n);
+        *px = *px * rv;
+      }
+  }
+}
+void species_form_dev(const mgpu_params& P, const DV& s, const double* base_dev, bool convert, bool pert, bool forward,
+                      const int* lo, const int* hi) {
+  if (!convert && !pert) return;
+  Box3 vb = grown(lo, hi, P.dm, 0);
+  MGPU_TIMED(TAG_GLUE, (k_species_form<<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(
+                           s, vb, P.rho_comp - 1, P.spec_comp - 1, P.nspec, convert, pert, forward, P.dm - 1, base_dev)));
+}
 void comp_muldiv_dev(const mgpu_params& P, const DV& a, int ca, const DV& b, int cb, int op, int g, const int* lo,
                      const int* hi) {
   Box3 vb = grown(lo, hi, P.dm, g);
@@ -441,6 +478,35 @@ __global__ void k_wrap(DV a, Box3 tb, int d, int lo, int hi, int ng, int nodal) 
     src = dst + n;
   } else {
     dst = hi + nodal + 1 + (g - ng);
+    src = dst - n;
+  }
+  int id[3] = {ix[0], ix[1], ix[2]}, is[3] = {ix[0], ix[1], ix[2]};
+  id[d] = dst;
+  is[d] = src;
+  a(id[0], id[1], id[2]) = a(is[0], is[1], is[2]);
+}
+
+// the same wrap for up to WRAP_MAX (fab, component) pairs in one launch: blockIdx.y selects the pair
+#define WRAP_MAX 12
+struct WrapMany {
+  int n;
+  DV a[WRAP_MAX];
+  Box3 tb[WRAP_MAX];
+  int lo[WRAP_MAX], hi[WRAP_MAX], ng[WRAP_MAX], nodal[WRAP_MAX];
+};
+__global__ void k_wrap_many(const __grid_constant__ WrapMany w, int d) {
+  const int e = blockIdx.y;
+  const DV& a = w.a[e];
+  int ix[3];
+  if (!decode32(w.tb[e], ix)) return;
+  const int g = ix[d], ng = w.ng[e];
+  const int n = w.hi[e] - w.lo[e] + 1;
+  int dst, src;
+  if (g < ng) {
+    dst = w.lo[e] - 1 - g;
+    src = dst + n;
+  } else {
+    dst = w.hi[e] + w.nodal[e] + 1 + (g - ng);
     src = dst - n;
   }
   int id[3] = {ix[0], ix[1], ix[2]}, is[3] = {ix[0], ix[1], ix[2]};
@@ -495,26 +561,51 @@ bool fill_exchange(const FillReq& r) {
                            ctx().stream);
 }
 
-void fill_local(const FillReq& r, bool slab) {
+// periodic wraps of a set of requests: x, then y, then z (so edges/corners come out right); one launch per
+// direction covers every (fab, component) pair of the set
+void fill_wraps(const FillReq* reqs, const char* slab, size_t nreq) {
+  Context& cx = ctx();
+  for (int d = 0; d < 3; ++d) {
+    WrapMany w;
+    w.n = 0;
+    unsigned maxblocks = 0;
+    auto flush = [&]() {
+      if (w.n == 0) return;
+      k_wrap_many<<<dim3(maxblocks, w.n), 256, 0, cx.stream>>>(w, d);
+      MGPU_LAUNCH_CHECK();
+      w.n = 0;
+      maxblocks = 0;
+    };
+    for (size_t q = 0; q < nreq; ++q) {
+      const FillReq& r = reqs[q];
+      if (d >= r.P.dm || !r.pmask[d]) continue;
+      if (slab[q] && d == r.P.dm - 1) continue;
+      for (int c = 0; c < r.ncomp; ++c) {
+        if (w.n == WRAP_MAX) flush();
+        const int e = w.n++;
+        w.a[e] = r.sfull.comp(r.scomp - 1 + c);
+        for (int t = 0; t < 3; ++t) { w.tb[e].lo[t] = w.a[e].lo[t]; w.tb[e].hi[t] = w.a[e].lo[t] + w.a[e].n[t] - 1; }
+        w.tb[e].lo[d] = 0;
+        w.tb[e].hi[d] = 2 * r.ng - 1;
+        w.lo[e] = r.lo[d];
+        w.hi[e] = r.hi[d];
+        w.ng[e] = r.ng;
+        w.nodal[e] = r.has_nodal ? r.nodal[d] : 0;
+        maxblocks = std::max(maxblocks, nblocks(w.tb[e].npts(), 256));
+      }
+    }
+    flush();
+  }
+}
+
+void fill_physbc(const FillReq& r) {
   Context& cx = ctx();
   const mgpu_params& P = r.P;
   const int dm = P.dm, ng = r.ng, ncomp = r.ncomp, scomp = r.scomp;
-  const int *lo = r.lo, *hi = r.hi, *pmask = r.pmask, *adv_bc = r.adv_bc;
+  const int *lo = r.lo, *hi = r.hi, *adv_bc = r.adv_bc;
   const int* nodal = r.has_nodal ? r.nodal : nullptr;
   const DV& sfull = r.sfull;
   const bool is_nodal = nodal && (nodal[0] || nodal[1] || nodal[2]);
-  // periodic wraps: x, then y, then z (so edges/corners come out right), all components of the call per launch
-  for (int d = 0; d < dm; ++d) {
-    if (!pmask[d]) continue;
-    if (slab && d == dm - 1) continue;
-    DV s = sfull.comp(scomp - 1);
-    Box3 tb;
-    for (int q = 0; q < 3; ++q) { tb.lo[q] = s.lo[q]; tb.hi[q] = s.lo[q] + s.n[q] - 1; }
-    tb.lo[d] = 0;
-    tb.hi[d] = 2 * ng - 1;
-    k_wrap<<<dim3(nblocks(tb.npts(), 256), ncomp), 256, 0, cx.stream>>>(s, tb, d, lo[d], hi[d], ng, nodal ? nodal[d] : 0);
-    MGPU_LAUNCH_CHECK();
-  }
   for (int n = 0; n < ncomp; ++n) {
     DV s = sfull.comp(scomp - 1 + n);
     if (is_nodal) continue;  // multifab_physbc_edgevel (FBoxLib) is left to the caller
@@ -563,7 +654,8 @@ void fill_batch_end() {
   halo_group_begin();
   for (size_t q = 0; q < g_batch.size(); ++q) slab[q] = fill_exchange(g_batch[q]) ? 1 : 0;
   halo_group_end();
-  for (size_t q = 0; q < g_batch.size(); ++q) fill_local(g_batch[q], slab[q] != 0);
+  fill_wraps(g_batch.data(), slab.data(), g_batch.size());
+  for (size_t q = 0; q < g_batch.size(); ++q) fill_physbc(g_batch[q]);
   g_batch.clear();
 }
 void fill_batch_abort() {
@@ -595,7 +687,9 @@ void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, con
     g_batch.push_back(r);
     return;
   }
-  fill_local(r, fill_exchange(r));
+  const char slab = fill_exchange(r) ? 1 : 0;
+  fill_wraps(&r, &slab, 1);
+  fill_physbc(r);
 }
 
 }  // namespace mgpu

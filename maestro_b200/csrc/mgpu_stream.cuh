@@ -66,12 +66,14 @@ void comp_muldiv_dev(const mgpu_params& P, const DV& a, int ca, const DV& b, int
 void addw0_dev(const mgpu_params& P, DV* umac, const double* w0_dev, double mult, const int* lo, const int* hi);
 void modify_scal_force_dev(const mgpu_params& P, const DV& force, const DV& s, const DV* umac, const double* s0,
                            const double* s0_edge, const double* w0, int comp, bool fullform, const int* lo,
-                           const int* hi, bool fast);
+                           const int* hi, bool fast, bool assign = false);
 void convert_rhoX_to_X_dev(const mgpu_params& P, const DV& s, bool flag, const int* lo, const int* hi);
 void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_dev, int comp, bool flag,
                           const int* lo, const int* hi);
 // Batched ghost fills: between begin and end fill_boundary_dev only records; end issues every slab exchange of the
 // batch as ONE NCCL group and then the local wraps / physical BCs in the recorded order (mgpu_stream.cu).
+void species_form_dev(const mgpu_params& P, const DV& s, const double* base_dev, bool convert, bool pert, bool forward,
+                      const int* lo, const int* hi);
 void fill_batch_begin();
 void fill_batch_end();
 void fill_batch_abort();
