@@ -284,8 +284,21 @@ def main():
         # write sedge 24 = 64 B per zone (kernel table); other classes report their own figure
         bytes_per_zone = {"fused_edge": 64.0, "edge_transverse": 64.0, "edge_final": 64.0}.get(name, 64.0)
         achieved = bytes_per_zone * n ** 3 / (ms / nl * 1e-3) / 1e9
+        traffic = None
+        try:  # DRAM bytes per launch of this kernel class from the committed ncu --set full capture (n = 256 only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if n == 256 and name in tj:
+                traffic = tj[name]["bytes_per_launch"]
+        except Exception:
+            traffic = None
+        others = {}
+        if "update" in prof and prof["update"][1] > 0:  # flux + update + density kernel: 360 B per zone
+            ms_u = prof["update"][0] / args.steps
+            others["update"] = {"achieved": 360.0 * n ** 3 / (ms_u * 1e-3) / 1e9, "frac": 360.0 * n ** 3 / (ms_u * 1e-3) / 1e9 / hbm,
+                                "ms_per_step": ms_u, "algorithmic_bytes_per_zone": 360.0,
+                                "note": "k_copy + k_flux_update3_fast, all species/tracers in one launch"}
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src, "other_kernels": others,
                 "kernel_ms_per_launch": ms / nl, "kernel_share_of_step": (ms / args.steps) / (t_dev / args.steps * 1e3),
                 "algorithmic_bytes_per_launch": bytes_per_zone * n ** 3,
                 "episode_algorithmic_GBs": 368.0 * n ** 3 * args.steps / t_dev / 1e9,
