@@ -23,6 +23,7 @@ static Context g_ctx;
 static std::string g_err;
 static int g_opt_fused = 1;    // use the fused 3-D edge kernel when it covers the case
 static int g_opt_kchunk = 32;  // z planes per CTA of the fused kernel
+static int g_opt_leanplus = 1;  // density_advance: on-the-fly input transforms where the upwind-first kernel applies
 static int g_opt_exact = 0;    // 1: bit-identical arithmetic everywhere (fused kernel built with -fmad=false)
 Context& ctx() { return g_ctx; }
 
@@ -242,7 +243,8 @@ static void fill_flux_args(const mgpu_params& P, FluxArgs& a, const int* lo, con
 // make_edge_scal for one component: fused single-launch kernel when it covers the case, else the staged path
 static void edge_one_comp(const mgpu_params& P, const DV& s, DV* sedge, const DV* umac, const DV& force,
                           const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel,
-                          bool is_cons, int ng_s, int ng_f, bool force_zero = false) {
+                          bool is_cons, int ng_s, int ng_f, bool force_zero = false, const double* sdiv = nullptr,
+                          const double* ssub = nullptr, const double* wadd = nullptr) {
   for (int d = 0; d < P.dm; ++d) {  // validate BC codes up front (make_edge_scal.f90:853)
     for (int side = 0; side < 2; ++side) {
       const int bc = adv_bc[d + P.dm * (side + 2 * (bccomp - 1))];
@@ -253,12 +255,101 @@ static void edge_one_comp(const mgpu_params& P, const DV& s, DV* sedge, const DV
   }
   if (g_opt_fused && fused_edge_supported(P, is_cons)) {
     fused_edge_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, ng_s, ng_f, g_opt_kchunk,
-                   g_opt_exact != 0, force_zero);
+                   g_opt_exact != 0, force_zero, sdiv, ssub, wadd);
   } else {
     size_t mark = arena_mark();
     make_edge_scal_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, is_cons, ng_s, ng_f);
     arena_release(mark);
   }
+}
+
+// ---- density_advance, "lean+" device-resident episode (see density_advance_dev) --------------------------------
+static void fill_flux_args(const mgpu_params& P, FluxArgs& a, const int* lo, const int* hi);
+static void density_advance_leanplus(const mgpu_params& P, int which_step, DV& sold, DV& snew, DV* sedge, DV* sflux,
+                                     DV& scal_force, DV* umac, const double* w0_h, const double* w0,
+                                     DV& eta, const double* rho0_old_h, const double* rho0_old,
+                                     const double* rho0_edge_old, const double* rho0_new_eff,
+                                     const double* rho0_edge_new_eff, const double* rho0_pe, const int* lo,
+                                     const int* hi, int ng_s, int ng_f, const int* adv_bc, const int* pmask) {
+  (void)which_step;
+  const int dm = 3, spt = P.species_pred_type, nr = P.nr;
+  const int foextrap_comp = dm + P.nscal + 2;
+  const int r = 2;
+  // base-state values by fab plane: the ghost planes take the value of the plane they are a copy of (periodic wrap
+  // of the global domain; planes of a neighbouring slab keep their own global index)
+  auto wrap_cell = [&](int k) {
+    const int n = P.domhi[r] - P.domlo[r] + 1;
+    while (k < P.domlo[r]) k += n;
+    while (k > P.domhi[r]) k -= n;
+    return k;
+  };
+  std::vector<double> sub(sold.n[r]), wadd(umac[r].n[r]);
+  for (int q = 0; q < sold.n[r]; ++q) sub[q] = rho0_old_h[wrap_cell(sold.lo[r] + q) - 0];
+  for (int q = 0; q < umac[r].n[r]; ++q) {
+    int k = umac[r].lo[r] + q;  // z-face index; faces domlo..domhi+1 are the domain's own, ghost faces wrap
+    const int n = P.domhi[r] - P.domlo[r] + 1;
+    if (k < P.domlo[r]) k += n;
+    else if (k > P.domhi[r] + 1) k -= n;
+    wadd[q] = w0_h[k];
+  }
+  (void)nr;
+  const double* sub_d = upload_small(sub.data(), sub.size());
+  const double* wadd_d = upload_small(wadd.data(), wadd.size());
+  int nodal_d[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+
+  // force of the density component (modify_scal_force, :119-128) from the raw inputs
+  set_dev(scal_force.p + scal_force.cs * (P.rho_comp - 1), 0.0, scal_force.cs);
+  modify_scal_force_dev(P, scal_force, sold, umac, rho0_old, rho0_edge_old, w0, P.rho_comp,
+                        spt == MGPU_PREDICT_RHO_AND_X, lo, hi, true, true);
+  {  // one batch: ghost cells of that force, of umac and of the raw rho / rhoX inputs
+    FillBatch fb;
+    fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
+    for (int d = 0; d < dm; ++d) fill_boundary_dev(P, umac[d], lo, hi, 1, nodal_d[d], 1, 1, 1, adv_bc, pmask, false);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
+    fb.run();
+  }
+  // 1/rho once (whole fab, ghost cells included) so that the edge kernels form X = rhoX * (1/rho) with a multiply
+  double* rinv = arena_alloc((size_t)sold.cs);
+  recip_dev(rinv, sold.p + sold.cs * (P.rho_comp - 1), sold.cs);
+  const double* rho_p = rinv;
+  for (int n = 0; n < P.nspec; ++n)  // X = rhoX / rho, zero force (:178-186)
+    edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, P.spec_comp - 1 + n, dm + P.spec_comp + n, false,
+                  false, ng_s, ng_f, true, rho_p, nullptr, wadd_d);
+  // rho' = rho - rho0 (or rho itself for predict_rho_and_X), with its force (:216-224)
+  edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, P.rho_comp - 1, dm + P.rho_comp, false, false, ng_s,
+                ng_f, false, nullptr, spt == MGPU_PREDICT_RHOPRIME_AND_X ? sub_d : nullptr, wadd_d);
+  for (int n = 0; n < P.ntrac; ++n)  // tracers (:242-252)
+    edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, P.trac_comp - 1 + n, dm + P.trac_comp + n, false,
+                  false, ng_s, ng_f, true, nullptr, nullptr, wadd_d);
+
+  FluxArgs fa;
+  fill_flux_args(P, fa, lo, hi);
+  for (int d = 0; d < dm; ++d) { fa.sflux[d] = sflux[d]; fa.sedge[d] = sedge[d]; fa.umac[d] = umac[d]; }
+  fa.eta = eta;
+  fa.w0 = w0;
+  fa.rho0_old = rho0_old;
+  fa.rho0_edge_old = rho0_edge_old;
+  fa.rho0_new = rho0_new_eff;
+  fa.rho0_edge_new = rho0_edge_new_eff;
+  fa.rho0_predicted_edge = rho0_pe;
+  set_dev(scal_force.p, 0.0, scal_force.size());  // :349-351
+  UpdArgs ua;
+  ua.dm = dm;
+  ua.dt = P.dt;
+  for (int d = 0; d < 3; ++d) ua.dx[d] = P.dx[d];
+  ua.vb = grown(lo, hi, dm, 0);
+  ua.sold = sold;
+  ua.snew = snew;
+  ua.force = scal_force;
+  for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
+  flux_update_all_dev(P, fa, ua, false);
+  FillBatch fb;
+  fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
+  fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
+  if (P.ntrac >= 1)
+    fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.trac_comp, dm + P.trac_comp, P.ntrac, adv_bc, pmask, false);
+  fb.run();
 }
 
 // ---- density_advance on the device (general path) ----------------------------------------------
@@ -290,6 +381,25 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   // scal_force has to be zero before modify_scal_force writes it; scal_force is zeroed once, at the end (:349-351).
   const bool lean = g_opt_exact == 0 && g_opt_fused && P.bds_type == 0 && fused_edge_supported(P, false) &&
                     (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X);
+  // "lean+" (every predicted component runs the upwind-first kernel, i.e. all six faces of the box are INTERIOR for
+  // all of them): rhoX -> X, rho -> rho' and umac + w0 are applied on the fly while the edge kernels stage their
+  // tiles, so sold and umac are never rewritten in HBM: no transform passes, no addw0 passes and only one ghost fill
+  // of the raw inputs.  On return sold and umac hold the caller's values (the reference returns their round trips
+  // (rhoX/rho)*rho and (umac+w0)-w0, one rounding away).
+  // pmask: the decision must be the same on every rank of a slab-partitioned run (it changes the exchange sequence)
+  bool leanp = lean && dm == 3 && g_opt_leanplus != 0 && pmask[0] && pmask[1] && pmask[2];
+  if (leanp) {
+    for (int c : {P.rho_comp, P.spec_comp, P.trac_comp})
+      if (!fused_edge_is_upwind_first(P, adv_bc, dm + c, g_opt_exact != 0)) leanp = false;
+    for (int n = 1; n < P.nspec; ++n)
+      if (!fused_edge_is_upwind_first(P, adv_bc, dm + P.spec_comp + n, false)) leanp = false;
+  }
+  if (leanp) {
+    density_advance_leanplus(P, which_step, sold, snew, sedge, sflux, scal_force, umac, w0_h, w0, eta, rho0_old_h,
+                             rho0_old, rho0_edge_old, (which_step == 1) ? rho0_old : rho0_new,
+                             (which_step == 1) ? rho0_edge_old : rho0_edge_new, rho0_pe, lo, hi, ng_s, ng_f, adv_bc, pmask);
+    return;
+  }
   if (lean) set_dev(scal_force.p + scal_force.cs * (P.rho_comp - 1), 0.0, scal_force.cs);
   else set_dev(scal_force.p, 0.0, scal_force.size());  // :101-103
   if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {  // :119-128
@@ -679,6 +789,7 @@ int mgpu_set_option(const char* key, int value) {
   if (k == "fused") g_opt_fused = value;
   else if (k == "kchunk") g_opt_kchunk = value;
   else if (k == "exact") g_opt_exact = value;
+  else if (k == "leanplus") g_opt_leanplus = value;
   else if (k == "fused_variant") fused_edge_set_variant(value);
   else if (k == "fused_by") fused_edge2_set_by(value);
   else throw Error("mgpu_set_option: unknown key " + k);
@@ -1054,8 +1165,10 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
   MGPU_TRY
   (void)p0_dummy;
   if (p->spherical) throw Error("mgpu_density_advance: spherical geometry not available on the device yet");
-  Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
-             (size_t)(8 * (p->nr + 2)) * sizeof(double) + 8192);
+  size_t one_comp = sizeof(double) + 256;  // the lean+ path keeps 1/rho of the whole fab in the arena
+  for (int d = 0; d < p->dm; ++d) one_comp *= (size_t)(sold->hi[d] - sold->lo[d] + 1 + 2 * sold->ng);
+  Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) + one_comp +
+             (size_t)(12 * (p->nr + 16)) * sizeof(double) + 8192);
   // components the episode reads / writes (density_advance.f90:101-366): rho, the species and the tracers
   const cmask_t adv = crange(p->rho_comp - 1, 1) | crange(p->spec_comp - 1, p->nspec) |
                       (p->ntrac >= 1 ? crange(p->trac_comp - 1, p->ntrac) : 0);

@@ -481,15 +481,27 @@ bool fused_edge_supported(const mgpu_params& P, bool is_cons) {
   return P.dm == 3 && P.bds_type == 0 && P.ppm_trace_forces == 0 && !is_cons;
 }
 
+bool fused_edge_is_upwind_first(const mgpu_params& P, const int* adv_bc, int bccomp, bool exact) {
+  if (exact || g_variant != 1 || P.dm != 3) return false;
+  for (int d = 0; d < 3; ++d)
+    for (int side = 0; side < 2; ++side)
+      if (adv_bc[d + 3 * (side + 2 * (bccomp - 1))] != MGPU_BC_INTERIOR) return false;
+  return true;
+}
+
 void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
                     const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
-                    int ng_f, int kchunk, bool exact, bool force_zero) {
+                    int ng_f, int kchunk, bool exact, bool force_zero, const double* sdiv, const double* ssub,
+                    const double* wadd) {
   if (P.ppm_type == 2 && ng_s < 4) throw Error("Need 4 ghost cells for ppm_type=2");  // ppm.f90:1864-1866
   if (ng_s < 3) throw Error("make_edge_scal: need at least 3 ghost cells");
   if (ng_f < 1) throw Error("make_edge_scal: force needs at least 1 ghost cell");
   FusedArgs a;
   a.slope_order = P.slope_order;
   a.force_zero = force_zero;
+  a.sdiv = sdiv;
+  a.ssub = ssub;
+  a.wadd = wadd;
   a.dt = P.dt;
   a.rel_eps = P.rel_eps;
   bool any_bc = false;
@@ -509,6 +521,9 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
   const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
   a.kchunk = kchunk > 0 ? kchunk : nz;
   if (a.kchunk > nz) a.kchunk = nz;
+  const bool xform = sdiv || ssub || wadd;
+  if (xform && (exact || any_bc || g_variant != 1))
+    throw Error("make_edge_scal: on-the-fly input transforms need the upwind-first kernel (internal error)");
   if (exact)
     fused_edge_launch_exact(a, P.ppm_type, any_bc, nx, ny, nz);
   else if (!any_bc && g_variant == 1)

@@ -22,6 +22,12 @@ struct FusedArgs {
   bool velnorm[3];
   int kchunk;  // z planes per CTA
   bool force_zero;  // the force of this component is identically zero: do not read it (density_advance.f90:99-103)
+  // on-the-fly input transforms of the upwind-first kernel (device-resident lean episode, density_advance.f90:160-171
+  // and :148): the predicted quantity is s*sdiv (X = rhoX * (1/rho), sdiv = the reciprocal density, same layout as s) and/or s - ssub(k) (rho' = rho - rho0(k)), the z
+  // velocity is wmac + wadd(k); ssub / wadd are indexed by the plane index inside the s / wmac fab.  nullptr: none.
+  const double* sdiv;
+  const double* ssub;
+  const double* wadd;
   double dt, dx[3], rel_eps;
   DV s, force;  // single-component views
   DV umac[3];
@@ -34,7 +40,10 @@ bool fused_edge_supported(const mgpu_params& P, bool is_cons);
 // exact: bit-identical arithmetic (-fmad=false build); otherwise the FAST build (dt/dx folded, FMA)
 void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
                     const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
-                    int ng_f, int kchunk, bool exact, bool force_zero = false);
+                    int ng_f, int kchunk, bool exact, bool force_zero = false, const double* sdiv = nullptr,
+                    const double* ssub = nullptr, const double* wadd = nullptr);
+// true when fused_edge_dev would run the upwind-first kernel for this component (FAST build, all faces INTERIOR)
+bool fused_edge_is_upwind_first(const mgpu_params& P, const int* adv_bc, int bccomp, bool exact);
 void fused_edge_launch_exact(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
 void fused_edge_launch_fast(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
 // second design (mgpu_fused2.cu): upwind-first, all faces INTERIOR, FAST arithmetic only

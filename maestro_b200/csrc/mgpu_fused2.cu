@@ -128,7 +128,9 @@ __device__ __forceinline__ LineBC no_wall2() {
   return b;
 }
 
-template <int PPM, int BX, int BY>
+// XF: on-the-fly input transform of s (0 none, 1 multiply by smul (X = rhoX * (1/rho)), 2 subtract ssub(k));
+// WADD: add wadd(k) to the z velocity.  Compile-time so that the plain kernel carries none of it.
+template <int PPM, int BX, int BY, int XF, bool WADD>
 __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_fused_edge2(FusedArgs a) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = Smem2<H, BX, BY>;
@@ -176,6 +178,15 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     if (k < k1) q += sz;
   };
   const double* __restrict__ gs = a.s.p;
+  // on-the-fly input transform of one s element at fab offset `off` in (clamped) fab plane `pk`
+  const double* __restrict__ gmul = a.sdiv;
+  const double* __restrict__ gsub = a.ssub;
+  const double* __restrict__ gwadd = a.wadd;
+  auto xs = [&](double v, int off, int pk) {
+    if constexpr (XF == 1) v = v * gmul[off];
+    if constexpr (XF == 2) v = v - gsub[pk];
+    return v;
+  };
   const double* __restrict__ gf = a.force.p;
   const double* __restrict__ gu = a.umac[0].p;
   const double* __restrict__ gv = a.umac[1].p;
@@ -213,7 +224,10 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
   const int t1 = kz1 + 2 + (top ? 1 : 0);
   double sw[2 * H + 1];  // z window: sw[m] = s(i,j,t-H+m) after the shift at the top of step t
 #pragma unroll
-  for (int m = 1; m <= 2 * H; ++m) sw[m] = gs[o_s + clampk(t0 - 1 - H + m, s_k0, s_k1) * s_sz];
+  for (int m = 1; m <= 2 * H; ++m) {
+    const int pk = clampk(t0 - 1 - H + m, s_k0, s_k1);
+    sw[m] = xs(gs[o_s + pk * s_sz], o_s + pk * s_sz, pk);
+  }
   // running offsets: q_s -> plane t+1+H of s (window), q_h -> plane t+1 (tile halo), q_u/q_v -> plane t+1,
   // q_w -> z-face t+2, q_f -> plane t-2, all for the step t about to start
   int q_s = o_s + clampk(t0 + 1 + H, s_k0, s_k1) * s_sz;
@@ -234,12 +248,21 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     S[sc_idx] = sw[H + 1];
 #pragma unroll
     for (int m = 0; m < SM::NH; ++m)
-      if (h_idx[m] >= 0) S[h_idx[m]] = gs[h_off[m] + clampk(t0, s_k0, s_k1) * s_sz];
+      if (h_idx[m] >= 0) {
+        const int pk = clampk(t0, s_k0, s_k1);
+        S[h_idx[m]] = xs(gs[h_off[m] + pk * s_sz], h_off[m] + pk * s_sz, pk);
+      }
 #pragma unroll
     for (int m = 0; m < SM::NH; ++m) h_off[m] += clampk(t0 + 1, s_k0, s_k1) * s_sz;
   }
   // loads in flight across one step
-  double ld_s = gs[o_s + clampk(t0 + H, s_k0, s_k1) * s_sz];
+  double ld_s;
+  {
+    const int pk = clampk(t0 + H, s_k0, s_k1);
+    ld_s = xs(gs[o_s + pk * s_sz], o_s + pk * s_sz, pk);
+  }
+  int pk_s = clampk(t0 + 1 + H, s_k0, s_k1), pk_h = clampk(t0 + 1, s_k0, s_k1);  // fab planes q_s / h_off address
+  int pk_w = clampk(t0 + 2, w_k0, w_k1);
   double ld_u, ld_u1, ld_v, ld_v1, ld_w1;
   double w0c;  // w on z-face t
   {
@@ -252,6 +275,10 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     ld_v1 = gv[ov + v_row];
     ld_w1 = gw[ow + clampk(t0 + 1, w_k0, w_k1) * w_sz];
     w0c = gw[ow + clampk(t0, w_k0, w_k1) * w_sz];
+    if constexpr (WADD) {
+      ld_w1 += gwadd[clampk(t0 + 1, w_k0, w_k1)];
+      w0c += gwadd[clampk(t0, w_k0, w_k1)];
+    }
   }
 
   // carried state, suffix = age in planes relative to t
@@ -293,17 +320,23 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     ld_v = gv[q_v];
     ld_v1 = gv[q_v + v_row];
     ld_w1 = gw[q_w];
-    ld_s = gs[q_s];
+    if constexpr (WADD) ld_w1 += gwadd[pk_w];
+    ld_s = xs(gs[q_s], q_s, pk_s);
     const double f2 = a.force_zero ? 0.0 : gf[q_f];  // consumed at the end of this cell phase
 #pragma unroll
     for (int m = 0; m < SM::NH; ++m) {
-      hS[m] = (h_idx[m] >= 0) ? gs[h_off[m]] : 0.0;
+      hS[m] = (h_idx[m] >= 0) ? xs(gs[h_off[m]], h_off[m], pk_h) : 0.0;
       adv_hi(h_off[m], t + 1, s_k1, s_sz);
     }
     adv_hi(q_u, t + 1, u_k1, u_sz);
     adv_hi(q_v, t + 1, u_k1, v_sz);
     adv_hi(q_w, t + 2, w_k1, w_sz);
     adv_hi(q_s, t + 1 + H, s_k1, s_sz);
+    if constexpr (XF == 2) {
+      adv_hi(pk_s, t + 1 + H, s_k1, 1);
+      adv_hi(pk_h, t + 1, s_k1, 1);
+    }
+    if constexpr (WADD) adv_hi(pk_w, t + 2, w_k1, 1);
     adv(q_f, t - 2, f_k0, f_k1, f_sz);
 
     __syncthreads();  // A: s tile(t), simhx/simhy(t-1), simhxy..simhyz(t-2) are visible
@@ -448,13 +481,13 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
   }
 }
 
-template <int PPM, int BX, int BY>
+template <int PPM, int BX, int BY, int XF, bool WADD>
 void launch_fused2(const FusedArgs& a, int nx, int ny, int nz) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = Smem2<H, BX, BY>;
   Context& c = ctx();
   static bool configured = false;
-  auto kern = k_fused_edge2<PPM, BX, BY>;
+  auto kern = k_fused_edge2<PPM, BX, BY, XF, WADD>;
   constexpr int bytes = SM::TOTAL * (int)sizeof(double);
   if (!configured) {
     MGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -465,19 +498,35 @@ void launch_fused2(const FusedArgs& a, int nx, int ny, int nz) {
   MGPU_TIMED(TAG_FUSED_EDGE, (kern<<<grid, block, bytes, c.stream>>>(a)));
 }
 
+template <int PPM, int BY>
+void launch_fused2_xf(const FusedArgs& a, int nx, int ny, int nz) {
+  constexpr int BX = MGPU_FUSED_BX;
+  const int xf = a.sdiv ? 1 : (a.ssub ? 2 : 0);
+  if (a.sdiv && a.ssub) throw Error("make_edge_scal: only one on-the-fly transform of s at a time");
+  if constexpr (BY == 8) {
+    if (a.wadd) {
+      if (xf == 0) launch_fused2<PPM, BX, BY, 0, true>(a, nx, ny, nz);
+      else if (xf == 1) launch_fused2<PPM, BX, BY, 1, true>(a, nx, ny, nz);
+      else launch_fused2<PPM, BX, BY, 2, true>(a, nx, ny, nz);
+      return;
+    }
+  }
+  if (xf != 0 || a.wadd) throw Error("make_edge_scal: on-the-fly transforms are built for the 32x8 tile with wadd only");
+  launch_fused2<PPM, BX, BY, 0, false>(a, nx, ny, nz);
+}
+
 }  // namespace
 
 // all six faces INTERIOR, FAST arithmetic.  a.kchunk: z planes per CTA.
 template <int BY>
 static void fused_edge2_launch_by(const FusedArgs& a, int ppm_type, int nx, int ny, int nz) {
-  constexpr int BX = MGPU_FUSED_BX;
   // 32-bit in-plane offsets
   for (const DV* v : {&a.s, &a.force, &a.umac[0], &a.umac[1], &a.umac[2], &a.sedge[0], &a.sedge[1], &a.sedge[2]})
     if (v->cs >= (1L << 31)) throw Error("make_edge_scal: fab too large for the fused kernel's 32-bit offsets");
   switch (ppm_type) {
-    case 0: launch_fused2<0, BX, BY>(a, nx, ny, nz); break;
-    case 1: launch_fused2<1, BX, BY>(a, nx, ny, nz); break;
-    case 2: launch_fused2<2, BX, BY>(a, nx, ny, nz); break;
+    case 0: launch_fused2_xf<0, BY>(a, nx, ny, nz); break;
+    case 1: launch_fused2_xf<1, BY>(a, nx, ny, nz); break;
+    case 2: launch_fused2_xf<2, BY>(a, nx, ny, nz); break;
     default: throw Error("make_edge_scal: invalid ppm_type");
   }
 }
@@ -485,7 +534,7 @@ static void fused_edge2_launch_by(const FusedArgs& a, int ppm_type, int nx, int 
 static int g_by = MGPU_FUSED2_BY;
 void fused_edge2_set_by(int by) { g_by = by; }
 void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz) {
-  if (g_by == 16) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz);
+  if (g_by == 16 && !a.wadd && !a.sdiv && !a.ssub) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz);
   else fused_edge2_launch_by<8>(a, ppm_type, nx, ny, nz);
 }
 

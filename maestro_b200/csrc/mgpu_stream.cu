@@ -390,6 +390,13 @@ __global__ void k_add(double* dst, const double* src, long n) {
   long t = MGPU_TID;
   if (t < n) dst[t] = dst[t] + src[t];
 }
+__global__ void k_recip(double* dst, const double* src, long n) {
+  long t = MGPU_TID;
+  if (t < n) dst[t] = 1.0 / src[t];
+}
+void recip_dev(double* dst, const double* src, long n) {
+  MGPU_TIMED(TAG_GLUE, (k_recip<<<nblocks(n, 256), 256, 0, ctx().stream>>>(dst, src, n)));
+}
 void add_dev(double* dst, const double* src, long n) {
   k_add<<<nblocks(n, 256), 256, 0, ctx().stream>>>(dst, src, n);
   MGPU_LAUNCH_CHECK();

@@ -74,6 +74,7 @@ void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_
 // batch as ONE NCCL group and then the local wraps / physical BCs in the recorded order (mgpu_stream.cu).
 void species_form_dev(const mgpu_params& P, const DV& s, const double* base_dev, bool convert, bool pert, bool forward,
                       const int* lo, const int* hi);
+void recip_dev(double* dst, const double* src, long n);
 void fill_batch_begin();
 void fill_batch_end();
 void fill_batch_abort();
