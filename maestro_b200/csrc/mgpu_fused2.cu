@@ -47,12 +47,19 @@ struct Smem2 {
   static constexpr int SN = (BY + 2 * H) * SP;
   static constexpr int P = BX;             // pitch of every other plane
   static constexpr int PL = (BY + 1) * P;  // doubles per plane (one spare row: reads at row+1 stay inside)
-  enum { AX0 = 0, AX1, AY0, AY1, TX, TY, TZ, GX, GY, SHX, SHY, XY, YX, XZ, YZ, NPL };
-  static constexpr int TOTAL = 2 * SN + NPL * PL;
+  // TX/TY: two planes each (plane t-1 and plane t-2, selected by the parity of t)
+  enum { AX0 = 0, AX1, AY0, AY1, TX, TXB, TY, TYB, TZ, GX, GY, XY, YX, XZ, YZ, NPL };
+  // ring of three slots (planes t, t-1, t-2) of four planes each: simhx, simhy and this thread's own
+  // u(i+1)+u(i), v(j+1)+v(j); aged values are re-read from the ring instead of being carried in registers
+  enum { R_SHX = 0, R_SHY, R_US, R_VS, NRING };
+  static constexpr int RS = NRING * PL;  // doubles per ring slot
+  static constexpr int TOTAL = 2 * SN + (NPL + 3 * NRING) * PL;
   static constexpr int NHALO = SN - BX * BY;  // s-tile elements outside the CTA's own columns
   static constexpr int NH = (NHALO + BX * BY - 1) / (BX * BY);
 };
 #define PLN(A, dy, dx) pl[SM::A * SM::PL + (dy) * SM::P + (dx)]
+// plane A of the ring slot at element offset R (r0: plane t, r1: t-1, r2: t-2)
+#define RNG(R, A, dy, dx) rg[(R) + SM::A * SM::PL + (dy) * SM::P + (dx)]
 
 // one traced state on a face from the parabola (a0=sm, a1=sp) / slope (a0) of its upwind cell.
 // a = u dt/h (signed CFL number), up = (u > 0): the upwind cell is the face's low neighbour.
@@ -285,11 +292,10 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
   double pz0_1 = 0.0, pz1_1 = 0.0;                      // z parabola of cell t-1
   double w1 = 0.0, w2 = 0.0;                            // w on z-faces t-1, t-2
   double shz1 = 0.0, shz2 = 0.0;                        // simhz on z-faces t-1, t-2
-  double tx2 = 0.0, ty2 = 0.0;                          // T_x, T_y of cell t-2
   double zx2 = 0.0, zy2 = 0.0;                          // simhzx, simhzy on z-face t-2
   double gz3 = 0.0;                                     // G_z of cell t-3
-  double us1 = 0.0, us2 = 0.0, vs1 = 0.0, vs2 = 0.0;    // u(i+1)+u(i), v(j+1)+v(j) of planes t-1, t-2
-  double shx1 = 0.0, shx2 = 0.0, shy1 = 0.0, shy2 = 0.0;  // simhx, simhy of this thread's faces, planes t-1, t-2
+  double* const rg = pl + SM::NPL * SM::PL;  // this thread's cell in ring slot 0, plane 0
+  int r0 = 0, r1 = SM::RS, r2 = 2 * SM::RS;  // ring slots of planes t, t-1, t-2
   unsigned selx = 0, sely = 0;  // 2 bits per plane (age 0,1,2): bit0 = upwind is the low cell, bit1 = |u| <= rel_eps
 
   const bool st_x = (tx >= 1) && (tx <= BX - 2 || i == a.hi[0] + 1) && (i <= a.hi[0] + 1) && (ty >= 1) &&
@@ -312,7 +318,8 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     for (int m = 0; m < 2 * H; ++m) sw[m] = sw[m + 1];
     sw[2 * H] = ld_s;
     const double u0 = ld_u, v0 = ld_v;  // face velocities of plane t
-    const double us0 = ld_u1 + ld_u, vs0 = ld_v1 + ld_v;
+    RNG(r0, R_US, 0, 0) = ld_u1 + ld_u;  // own slot: read back by this thread only, at ages 1 and 2
+    RNG(r0, R_VS, 0, 0) = ld_v1 + ld_v;
     const double wn = ld_w1;  // w on z-face t+1
     double hS[SM::NH];  // halo of the s tile of plane t+1, published at the end of this step's face phase
     ld_u = gu[q_u];
@@ -372,11 +379,13 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     if (slz0) shz0 = trace_slow<PPM>(pz0_1, s1, pz0_0, s0, w0c * tdz);
     // C2(t-1): cell-centred transverse terms of plane t-1
     const double ws1 = w0c + w1;
-    const double tx1 = us1 * (PLN(SHX, 0, 1) - shx1);
-    const double ty1 = vs1 * (PLN(SHY, 1, 0) - shy1);
+    const int tq0 = (t & 1) ? SM::PL : 0, tq1 = SM::PL - tq0;  // TX/TY planes of t-1 (written now) and t-2
+    const double tx1 = RNG(r1, R_US, 0, 0) * (RNG(r1, R_SHX, 0, 1) - RNG(r1, R_SHX, 0, 0));
+    const double ty1 = RNG(r1, R_VS, 0, 0) * (RNG(r1, R_SHY, 1, 0) - RNG(r1, R_SHY, 0, 0));
+    const double tx2 = pl[SM::TX * SM::PL + tq1], ty2 = pl[SM::TY * SM::PL + tq1];
     const double tz1 = ws1 * (shz0 - shz1);
-    PLN(TX, 0, 0) = tx1;
-    PLN(TY, 0, 0) = ty1;
+    pl[SM::TX * SM::PL + tq0] = tx1;
+    pl[SM::TY * SM::PL + tq0] = ty1;
     PLN(TZ, 0, 0) = tz1;
     const bool upz1 = w1 > 0.0, slz1 = !(fabs(w1) > rel_eps);
     double txs = upz1 ? tx2 : tx1, tys = upz1 ? ty2 : ty1;
@@ -390,6 +399,7 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     const double ws2 = w1 + w2;
     const double hf = dt2 * f2;
     const double dzy = c4z * ws2 * (zy1 - zy2), dzx = c4z * ws2 * (zx1 - zx2);
+    const double us2 = RNG(r2, R_US, 0, 0), vs2 = RNG(r2, R_VS, 0, 0);
     const double gx2 = fma(c4y * vs2, PLN(YZ, 1, 0) - PLN(YZ, 0, 0), dzy) - hf;
     const double gy2 = fma(c4x * us2, PLN(XZ, 0, 1) - PLN(XZ, 0, 0), dzx) - hf;
     const double gz2 =
@@ -414,7 +424,7 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       shx0 = trace1<PPM>((pl + off)[SM::AX0 * SM::PL], (pl + off)[SM::AX1 * SM::PL], S[off], u0 * tdx, up);
       if (slow) shx0 = trace_slow<PPM>(PLN(AX0, 0, -1), S[-1], PLN(AX0, 0, 0), S[0], u0 * tdx);
       selx = (selx << 2) | (up ? 1u : 0u) | (slow ? 2u : 0u);
-      PLN(SHX, 0, 0) = shx0;
+      RNG(r0, R_SHX, 0, 0) = shx0;
     }
     {
       const bool up = v0 > 0.0, slow = !(fabs(v0) > rel_eps);
@@ -422,26 +432,30 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       shy0 = trace1<PPM>((pl + off)[SM::AY0 * SM::PL], (pl + off)[SM::AY1 * SM::PL], S[up ? -SP : 0], v0 * tdy, up);
       if (slow) shy0 = trace_slow<PPM>(PLN(AY0, -1, 0), S[-SP], PLN(AY0, 0, 0), S[0], v0 * tdy);
       sely = (sely << 2) | (up ? 1u : 0u) | (slow ? 2u : 0u);
-      PLN(SHY, 0, 0) = shy0;
+      RNG(r0, R_SHY, 0, 0) = shy0;
     }
     // F2(t-1): transverse face states of plane t-1
     {
       const int off = (selx & 4u) ? -1 : 0;
-      double tys = (pl + off)[SM::TY * SM::PL], tzs = (pl + off)[SM::TZ * SM::PL];
+      const int tq = (t & 1) ? SM::PL : 0;
+      double tys = (pl + off)[SM::TY * SM::PL + tq], tzs = (pl + off)[SM::TZ * SM::PL];
       if (selx & 8u) {
-        tys = 0.5 * (PLN(TY, 0, -1) + PLN(TY, 0, 0));
+        tys = 0.5 * (pl[SM::TY * SM::PL + tq - 1] + pl[SM::TY * SM::PL + tq]);
         tzs = 0.5 * (PLN(TZ, 0, -1) + PLN(TZ, 0, 0));
       }
+      const double shx1 = RNG(r1, R_SHX, 0, 0);
       PLN(XY, 0, 0) = fma(-c6y, tys, shx1);
       PLN(XZ, 0, 0) = fma(-c6z, tzs, shx1);
     }
     {
       const int off = (sely & 4u) ? -P : 0;
-      double txs2 = (pl + off)[SM::TX * SM::PL], tzs = (pl + off)[SM::TZ * SM::PL];
+      const int tq = (t & 1) ? SM::PL : 0;
+      double txs2 = (pl + off)[SM::TX * SM::PL + tq], tzs = (pl + off)[SM::TZ * SM::PL];
       if (sely & 8u) {
-        txs2 = 0.5 * (PLN(TX, -1, 0) + PLN(TX, 0, 0));
+        txs2 = 0.5 * (pl[SM::TX * SM::PL + tq - P] + pl[SM::TX * SM::PL + tq]);
         tzs = 0.5 * (PLN(TZ, -1, 0) + PLN(TZ, 0, 0));
       }
+      const double shy1 = RNG(r1, R_SHY, 0, 0);
       PLN(YX, 0, 0) = fma(-c6x, txs2, shy1);
       PLN(YZ, 0, 0) = fma(-c6z, tzs, shy1);
     }
@@ -452,12 +466,12 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       if (kin && st_x) {
         double g = (pl + ((selx & 16u) ? -1 : 0))[SM::GX * SM::PL];
         if (selx & 32u) g = 0.5 * (PLN(GX, 0, -1) + PLN(GX, 0, 0));
-        gex[q_ex] = shx2 - g;
+        gex[q_ex] = RNG(r2, R_SHX, 0, 0) - g;
       }
       if (kin && st_y) {
         double g = (pl + ((sely & 16u) ? -P : 0))[SM::GY * SM::PL];
         if (sely & 32u) g = 0.5 * (PLN(GY, -1, 0) + PLN(GY, 0, 0));
-        gey[q_ey] = shy2 - g;
+        gey[q_ey] = RNG(r2, R_SHY, 0, 0) - g;
       }
     }
     // publish the s tile of plane t+1
@@ -473,11 +487,9 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     pz0_1 = pz0_0; pz1_1 = pz1_0;
     w2 = w1; w1 = w0c; w0c = wn;
     shz2 = shz1; shz1 = shz0;
-    tx2 = tx1; ty2 = ty1;
     zx2 = zx1; zy2 = zy1;
     gz3 = gz2;
-    us2 = us1; us1 = us0; vs2 = vs1; vs1 = vs0;
-    shx2 = shx1; shx1 = shx0; shy2 = shy1; shy1 = shy0;
+    { const int rt = r2; r2 = r1; r1 = r0; r0 = rt; }  // the slot of plane t-2 becomes the slot of plane t+1
   }
 }
 
@@ -535,6 +547,8 @@ static int g_by = MGPU_FUSED2_BY;
 void fused_edge2_set_by(int by) { g_by = by; }
 void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz) {
   if (g_by == 16 && !a.wadd && !a.sdiv && !a.ssub) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz);
+  else if (g_by == 10 && !a.wadd && !a.sdiv && !a.ssub) fused_edge2_launch_by<10>(a, ppm_type, nx, ny, nz);
+  else if (g_by == 12 && !a.wadd && !a.sdiv && !a.ssub) fused_edge2_launch_by<12>(a, ppm_type, nx, ny, nz);
   else fused_edge2_launch_by<8>(a, ppm_type, nx, ny, nz);
 }
 
