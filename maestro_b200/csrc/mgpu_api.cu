@@ -343,7 +343,8 @@ static void density_advance_leanplus(const mgpu_params& P, int which_step, DV& s
   ua.snew = snew;
   ua.force = scal_force;
   for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
-  flux_update_all_dev(P, fa, ua, false);
+  // scal_force is zero by construction here and the periodic / slab fills below rewrite every ghost cell of snew
+  flux_update_all_dev(P, fa, ua, false, true, true);
   FillBatch fb;
   fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
   fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);

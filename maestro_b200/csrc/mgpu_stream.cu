@@ -861,6 +861,7 @@ struct FU3 {
   int t_lo[3], t_n0, t_n01;        // etarhoflux
   int lo[3], hi[3];
   int spt, do_eta, rho, spec0, nspec, trac0, ntrac;
+  int force_zero;  // scal_force is identically zero (density_advance.f90:349-351): do not read it
   double dt, rdx[3], half_bcd;
   const double *w0, *rho0_old, *rho0_edge_old, *rho0_new, *rho0_edge_new, *rho0_predicted_edge;
 };
@@ -928,7 +929,7 @@ __global__ void __launch_bounds__(256, 3) k_flux_update3_fast(const __grid_const
       fhi[d] = r0hi[d] * __ldg(pe + se[d]);
     }
     const double so = __ldg(a.sold + os + a.s_cs * c);
-    const double fo = __ldg(a.force + of + a.f_cs * c);
+    const double fo = a.force_zero ? 0.0 : __ldg(a.force + of + a.f_cs * c);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       double* pf = a.sflux[d] + oe[d] + a.e_cs[d] * c;
@@ -987,7 +988,7 @@ static bool same_layout(const DV& x, const DV& y) {
   return x.cs == y.cs;
 }
 // true if the specialised kernel covers this call (and then launches it)
-static bool flux_update3_fast(const mgpu_params& P, const FluxArgs& a, const UpdArgs& u) {
+static bool flux_update3_fast(const mgpu_params& P, const FluxArgs& a, const UpdArgs& u, bool force_zero) {
   if (P.dm != 3) return false;
   const long lim = 1L << 31;
   for (int d = 0; d < 3; ++d)
@@ -1022,6 +1023,7 @@ static bool flux_update3_fast(const mgpu_params& P, const FluxArgs& a, const Upd
   f.spt = a.species_pred_type; f.do_eta = a.evolve_base_state ? 1 : 0;
   f.rho = a.rho; f.spec0 = a.spec0; f.nspec = a.nspec; f.trac0 = P.trac_comp - 1; f.ntrac = P.ntrac;
   f.dt = u.dt; f.half_bcd = 0.5 * P.base_cutoff_density;
+  f.force_zero = force_zero ? 1 : 0;
   f.w0 = a.w0; f.rho0_old = a.rho0_old; f.rho0_edge_old = a.rho0_edge_old; f.rho0_new = a.rho0_new;
   f.rho0_edge_new = a.rho0_edge_new; f.rho0_predicted_edge = a.rho0_predicted_edge;
   const dim3 g = grid3(u.vb, 256);
@@ -1030,14 +1032,20 @@ static bool flux_update3_fast(const mgpu_params& P, const FluxArgs& a, const Upd
   return true;
 }
 
-void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exact) {
+void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exact, bool force_zero, bool skip_rho_copy) {
   Context& cx = ctx();
   const int rho = P.rho_comp - 1;
   if (u.snew.cs != u.sold.cs) throw Error("update_scal: sold and snew must have the same ghost width");
   // snew(:,:,:,rho_comp) = sold(:,:,:,rho_comp) including ghost cells (update_scal.f90:455)
-  MGPU_TIMED(TAG_UPDATE, (k_copy<<<nblocks(u.snew.cs, 256), 256, 0, cx.stream>>>(u.snew.p + u.snew.cs * rho,
-                                                                                 u.sold.p + u.sold.cs * rho, u.snew.cs)));
-  if (!exact && flux_update3_fast(P, a, u)) return;
+  // (skipped when the caller knows that the ghost fill that follows overwrites every ghost cell of the component)
+  auto rho_copy = [&]() {
+    MGPU_TIMED(TAG_UPDATE, (k_copy<<<nblocks(u.snew.cs, 256), 256, 0, cx.stream>>>(u.snew.p + u.snew.cs * rho,
+                                                                                   u.sold.p + u.sold.cs * rho, u.snew.cs)));
+  };
+  if (!skip_rho_copy) rho_copy();
+  if (!exact && flux_update3_fast(P, a, u, force_zero)) return;
+  // general kernel: it reads the force (zero in memory when force_zero) and the copy is always made
+  if (skip_rho_copy) rho_copy();
   const dim3 g = grid3(u.vb, 256);
   const int b = block3(u.vb, 256);
   const int t0 = P.trac_comp - 1;

@@ -25,7 +25,8 @@ struct UpdArgs {
 };
 void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop);
 // mk_rhoX_flux (species + tracers) + update_scal (species + tracers + density) of density_advance in one launch
-void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exact);
+void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exact, bool force_zero = false,
+                         bool skip_rho_copy = false);
 
 struct VelArgs {
   int dm;
