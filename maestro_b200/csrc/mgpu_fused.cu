@@ -482,7 +482,7 @@ bool fused_edge_supported(const mgpu_params& P, bool is_cons) {
 }
 
 bool fused_edge_is_upwind_first(const mgpu_params& P, const int* adv_bc, int bccomp, bool exact) {
-  if (exact || g_variant != 1 || P.dm != 3) return false;
+  if (exact || g_variant == 0 || P.dm != 3) return false;
   for (int d = 0; d < 3; ++d)
     for (int side = 0; side < 2; ++side)
       if (adv_bc[d + 3 * (side + 2 * (bccomp - 1))] != MGPU_BC_INTERIOR) return false;
@@ -522,12 +522,12 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
   a.kchunk = kchunk > 0 ? kchunk : nz;
   if (a.kchunk > nz) a.kchunk = nz;
   const bool xform = sdiv || ssub || wadd;
-  if (xform && (exact || any_bc || g_variant != 1))
+  if (xform && (exact || any_bc || g_variant == 0))
     throw Error("make_edge_scal: on-the-fly input transforms need the upwind-first kernel (internal error)");
   if (exact)
     fused_edge_launch_exact(a, P.ppm_type, any_bc, nx, ny, nz);
-  else if (!any_bc && g_variant == 1)
-    fused_edge2_launch(a, P.ppm_type, nx, ny, nz);
+  else if (g_variant == 1 || (g_variant == 2 && !any_bc))
+    fused_edge2_launch(a, P.ppm_type, nx, ny, nz, any_bc);
   else
     fused_edge_launch_fast(a, P.ppm_type, any_bc, nx, ny, nz);
 }

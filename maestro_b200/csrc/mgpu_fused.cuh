@@ -46,8 +46,8 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
 bool fused_edge_is_upwind_first(const mgpu_params& P, const int* adv_bc, int bccomp, bool exact);
 void fused_edge_launch_exact(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
 void fused_edge_launch_fast(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
-// second design (mgpu_fused2.cu): upwind-first, all faces INTERIOR, FAST arithmetic only
-void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz);
+// second design (mgpu_fused2.cu): upwind-first, FAST arithmetic only; bc: the box has physical boundaries
+void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc);
 // 0: always the literal kernel; 1 (default): the upwind-first kernel wherever it applies
 void fused_edge_set_variant(int v);
 void fused_edge2_set_by(int by);  // rows per CTA of the upwind-first kernel: 8 or 16

@@ -124,6 +124,67 @@ __device__ __forceinline__ void cell_par(const double* q, int st, int slope_orde
   }
 }
 
+
+// Boundary-face rule of one face in upwind-first form.  At a face on a physical boundary the reference overwrites
+// the left/right states so that both are equal (bc_states / final_bc of mgpu_fused.cu restate it literally); the
+// Riemann problem then returns that common value whatever the velocity.  Encoded per face:
+//   FB_NONE  interior face (normal upwinding)
+//   FB_LEFT / FB_RIGHT  the state of the low / high cell is used whatever the sign of u (FOEXTRAP, HOEXTRAP,
+//            REFLECT_EVEN), optionally clamped to inflow-free values (normal velocity component: min/max with 0)
+//   FB_GHOST the value is the s of the ghost cell, no transverse / final correction (EXT_DIR)
+//   FB_ZERO  the value is 0 (REFLECT_ODD)
+enum { FB_NONE = 0, FB_LEFT = 1, FB_RIGHT = 2, FB_GHOST = 3, FB_ZERO = 4 };
+struct FaceRule {
+  int kind;   // FB_*
+  int clamp;  // 0 none, 1 min(.,0) (low boundary), 2 max(.,0) (high boundary)
+  bool low;   // the face is the low boundary of its direction
+};
+__device__ __forceinline__ FaceRule face_rule(int f, int lo, int hi, int bclo, int bchi, bool velnorm) {
+  FaceRule r;
+  r.kind = FB_NONE;
+  r.clamp = 0;
+  r.low = false;
+  int bc = MGPU_BC_INTERIOR;
+  bool low = false;
+  if (f == lo && bclo != MGPU_BC_INTERIOR) { bc = bclo; low = true; r.low = true; }
+  else if (f == hi + 1 && bchi != MGPU_BC_INTERIOR) { bc = bchi; }
+  if (bc == MGPU_BC_EXT_DIR) r.kind = FB_GHOST;
+  else if (bc == MGPU_BC_REFLECT_ODD) r.kind = FB_ZERO;
+  else if (bc == MGPU_BC_FOEXTRAP || bc == MGPU_BC_HOEXTRAP || bc == MGPU_BC_REFLECT_EVEN) {
+    r.kind = low ? FB_RIGHT : FB_LEFT;
+    if (velnorm && bc != MGPU_BC_REFLECT_EVEN) r.clamp = low ? 1 : 2;
+  }
+  return r;
+}
+__device__ __forceinline__ double clamp_rule(double v, int clamp) {
+  if (clamp == 1) return dmin2(v, 0.0);
+  if (clamp == 2) return dmax2(v, 0.0);
+  return v;
+}
+// stage-0 state of a forced face: Ip of the low cell / Im of the high cell exactly as ppm_trace / the slope formula
+// give them (for PPM the parabola is only traced when the velocity exceeds rel_eps in that direction)
+template <int PPM>
+__device__ __forceinline__ double forced_state(bool left, double a0, double a1, double sc, double u, double td,
+                                               double rel_eps) {
+  if constexpr (PPM == 0) return trace1<0>(a0, a1, sc, u * td, left);
+  const bool moving = left ? (u > rel_eps) : (u < -rel_eps);
+  return moving ? trace1<PPM>(a0, a1, sc, u * td, left) : sc;
+}
+
+// limited parabola / slope of one cell with the reference's wall stencils (cell index c on a line with BCs b)
+template <int PPM>
+__device__ __forceinline__ void cell_par_bc(const double* q, int st, int c, int slope_order, const LineBC& b,
+                                            double& a0, double& a1) {
+  if constexpr (PPM == 0) {
+    a0 = slope_cell(q, st, c, b, slope_order);
+    a1 = 0.0;
+  } else if constexpr (PPM == 1) {
+    ppm1_cell(q, st, c, b, a0, a1);
+  } else {
+    ppm2_cell(q, st, c, b, a0, a1);
+  }
+}
+
 __device__ __forceinline__ LineBC no_wall2() {
   LineBC b;
   b.lo = -(1 << 30);
@@ -137,7 +198,9 @@ __device__ __forceinline__ LineBC no_wall2() {
 
 // XF: on-the-fly input transform of s (0 none, 1 multiply by smul (X = rhoX * (1/rho)), 2 subtract ssub(k));
 // WADD: add wadd(k) to the z velocity.  Compile-time so that the plain kernel carries none of it.
-template <int PPM, int BX, int BY, int XF, bool WADD>
+// BC: the box has physical boundaries: wall stencils of the reconstruction and the boundary-face rules of
+// make_edge_scal.f90:900-1000 (stage 0), :1100-1400 (transverse stages) and :1450-1560 (final) in upwind-first form.
+template <int PPM, int BX, int BY, int XF, bool WADD, bool BC>
 __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_fused_edge2(FusedArgs a) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = Smem2<H, BX, BY>;
@@ -156,6 +219,18 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
   const bool top = (kz1 == a.hi[2]);
   const int ic = min(i, a.hi[0] + 1), jc = min(j, a.hi[1] + 1);
   const LineBC nb = no_wall2();
+  const LineBC lbx = BC ? make_linebc(3, 0, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0]) : nb;
+  const LineBC lby = BC ? make_linebc(3, 1, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1]) : nb;
+  const LineBC lbz = BC ? make_linebc(3, 2, a.lo[2], a.hi[2], a.bclo[2], a.bchi[2]) : nb;
+  // rules of this thread's x- and y-face (the same on every plane)
+  FaceRule frx, fry;
+  frx.kind = fry.kind = FB_NONE;
+  frx.clamp = fry.clamp = 0;
+  frx.low = fry.low = false;
+  if constexpr (BC) {
+    frx = face_rule(i, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0], a.velnorm[0]);
+    fry = face_rule(j, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1], a.velnorm[1]);
+  }
 
   const double rel_eps = a.rel_eps;
   const double tdx = a.dt / a.dx[0], tdy = a.dt / a.dx[1], tdz = a.dt / a.dx[2];
@@ -294,6 +369,7 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
   double shz1 = 0.0, shz2 = 0.0;                        // simhz on z-faces t-1, t-2
   double zx2 = 0.0, zy2 = 0.0;                          // simhzx, simhzy on z-face t-2
   double gz3 = 0.0;                                     // G_z of cell t-3
+  double s_m3 = 0.0;                                    // s(i,j,t-3) (BC only: EXT_DIR value of the final z state)
   double* const rg = pl + SM::NPL * SM::PL;  // this thread's cell in ring slot 0, plane 0
   int r0 = 0, r1 = SM::RS, r2 = 2 * SM::RS;  // ring slots of planes t, t-1, t-2
   unsigned selx = 0, sely = 0;  // 2 bits per plane (age 0,1,2): bit0 = upwind is the low cell, bit1 = |u| <= rel_eps
@@ -355,13 +431,17 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     double pz0_0, pz1_0;
     {
       double a0, a1;
-      cell_par<PPM>(S, 1, a.slope_order, nb, a0, a1);
+      if constexpr (BC) cell_par_bc<PPM>(S, 1, i, a.slope_order, lbx, a0, a1);
+      else cell_par<PPM>(S, 1, a.slope_order, nb, a0, a1);
       PLN(AX0, 0, 0) = a0;
       if (PPM != 0) PLN(AX1, 0, 0) = a1;
-      cell_par<PPM>(S, SP, a.slope_order, nb, a0, a1);
+      if constexpr (BC) cell_par_bc<PPM>(S, SP, j, a.slope_order, lby, a0, a1);
+      else cell_par<PPM>(S, SP, a.slope_order, nb, a0, a1);
       PLN(AY0, 0, 0) = a0;
       if (PPM != 0) PLN(AY1, 0, 0) = a1;
-      if constexpr (PPM == 1) {
+      if constexpr (BC) {
+        cell_par_bc<PPM>(&sw[H], 1, t, a.slope_order, lbz, pz0_0, pz1_0);
+      } else if constexpr (PPM == 1) {
         const double dz_n = dsvl_fast(sw[H], sw[H + 1], sw[H + 2]);
         const double e = edge_fast(sw[H], sw[H + 1], dz_c, dz_n);
         pz0_0 = ez_c;
@@ -374,9 +454,31 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       }
     }
     // Z(t): simhz on z-face t (between cells t-1 and t)
-    const bool upz0 = w0c > 0.0, slz0 = !(fabs(w0c) > rel_eps);
-    double shz0 = trace1<PPM>(upz0 ? pz0_1 : pz0_0, upz0 ? pz1_1 : pz1_0, upz0 ? s1 : s0, w0c * tdz, upz0);
-    if (slz0) shz0 = trace_slow<PPM>(pz0_1, s1, pz0_0, s0, w0c * tdz);
+    bool upz0 = w0c > 0.0, slz0 = !(fabs(w0c) > rel_eps);
+    FaceRule fz0, fz1, fz2;  // rules of z-faces t, t-1, t-2 (uniform over the CTA)
+    fz0.kind = fz1.kind = fz2.kind = FB_NONE;
+    fz0.clamp = fz1.clamp = fz2.clamp = 0;
+    fz0.low = fz1.low = fz2.low = false;
+    if constexpr (BC) {
+      fz0 = face_rule(t, a.lo[2], a.hi[2], a.bclo[2], a.bchi[2], a.velnorm[2]);
+      fz1 = face_rule(t - 1, a.lo[2], a.hi[2], a.bclo[2], a.bchi[2], a.velnorm[2]);
+      fz2 = face_rule(t - 2, a.lo[2], a.hi[2], a.bclo[2], a.bchi[2], a.velnorm[2]);
+    }
+    double shz0;
+    if (BC && fz0.kind != FB_NONE) {
+      if (fz0.kind == FB_GHOST) {
+        shz0 = s0;  // QUIRK make_edge_scal.f90:1010-1011: the z-lo EXT_DIR state of this stage is s(lo), not s(lo-1)
+      } else if (fz0.kind == FB_ZERO) {
+        shz0 = 0.0;
+      } else {
+        const bool left = fz0.kind == FB_LEFT;
+        shz0 = clamp_rule(forced_state<PPM>(left, left ? pz0_1 : pz0_0, left ? pz1_1 : pz1_0, left ? s1 : s0, w0c, tdz, rel_eps),
+                          fz0.clamp);
+      }
+    } else {
+      shz0 = trace1<PPM>(upz0 ? pz0_1 : pz0_0, upz0 ? pz1_1 : pz1_0, upz0 ? s1 : s0, w0c * tdz, upz0);
+      if (slz0) shz0 = trace_slow<PPM>(pz0_1, s1, pz0_0, s0, w0c * tdz);
+    }
     // C2(t-1): cell-centred transverse terms of plane t-1
     const double ws1 = w0c + w1;
     const int tq0 = (t & 1) ? SM::PL : 0, tq1 = SM::PL - tq0;  // TX/TY planes of t-1 (written now) and t-2
@@ -387,14 +489,26 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     pl[SM::TX * SM::PL + tq0] = tx1;
     pl[SM::TY * SM::PL + tq0] = ty1;
     PLN(TZ, 0, 0) = tz1;
-    const bool upz1 = w1 > 0.0, slz1 = !(fabs(w1) > rel_eps);
+    bool upz1 = w1 > 0.0, slz1 = !(fabs(w1) > rel_eps);
+    if (BC && fz1.kind != FB_NONE) {
+      upz1 = fz1.kind == FB_LEFT;
+      slz1 = false;
+    }
     double txs = upz1 ? tx2 : tx1, tys = upz1 ? ty2 : ty1;
     if (slz1) {
       txs = 0.5 * (tx2 + tx1);
       tys = 0.5 * (ty2 + ty1);
     }
-    const double zx1 = fma(-c6x, txs, shz1);  // simhzx on z-face t-1
-    const double zy1 = fma(-c6y, tys, shz1);  // simhzy
+    double zx1 = fma(-c6x, txs, shz1);  // simhzx on z-face t-1
+    double zy1 = fma(-c6y, tys, shz1);  // simhzy
+    if (BC && fz1.kind != FB_NONE) {
+      if (fz1.kind == FB_GHOST) zx1 = zy1 = fz1.low ? sw[H - 2] : s1;  // s(lo-1) / s(hi+1) of this stage
+      else if (fz1.kind == FB_ZERO) zx1 = zy1 = 0.0;
+      else {
+        zx1 = clamp_rule(zx1, fz1.clamp);
+        zy1 = clamp_rule(zy1, fz1.clamp);
+      }
+    }
     // C3(t-2): cell-centred final corrections of plane t-2
     const double ws2 = w1 + w2;
     const double hf = dt2 * f2;
@@ -407,11 +521,21 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     PLN(GX, 0, 0) = gx2;
     PLN(GY, 0, 0) = gy2;
     {
-      const bool upz2 = w2 > 0.0, slz2 = !(fabs(w2) > rel_eps);
+      bool upz2 = w2 > 0.0, slz2 = !(fabs(w2) > rel_eps);
+      if (BC && fz2.kind != FB_NONE) {
+        upz2 = fz2.kind == FB_LEFT;
+        slz2 = false;
+      }
       double g = upz2 ? gz3 : gz2;
       if (slz2) g = 0.5 * (gz3 + gz2);
+      double e = shz2 - g;
+      if (BC && fz2.kind != FB_NONE) {
+        if (fz2.kind == FB_GHOST) e = fz2.low ? s_m3 : sw[H - 2];  // s(lo-1) / s(hi+1)
+        else if (fz2.kind == FB_ZERO) e = 0.0;
+        else e = clamp_rule(e, fz2.clamp);
+      }
       const int f = t - 2;  // z-face index
-      if (st_z && f >= kz0 && (f <= kz1 || (top && f == kz1 + 1))) gez[q_ez] = shz2 - g;
+      if (st_z && f >= kz0 && (f <= kz1 || (top && f == kz1 + 1))) gez[q_ez] = e;
     }
 
     __syncthreads();  // B: parabolas(t), T(t-1), G(t-2) are visible
@@ -419,18 +543,40 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     // F1(t): simhx, simhy
     double shx0, shy0;
     {
-      const bool up = u0 > 0.0, slow = !(fabs(u0) > rel_eps);
-      const int off = up ? -1 : 0;
-      shx0 = trace1<PPM>((pl + off)[SM::AX0 * SM::PL], (pl + off)[SM::AX1 * SM::PL], S[off], u0 * tdx, up);
-      if (slow) shx0 = trace_slow<PPM>(PLN(AX0, 0, -1), S[-1], PLN(AX0, 0, 0), S[0], u0 * tdx);
+      bool up = u0 > 0.0, slow = !(fabs(u0) > rel_eps);
+      if (BC && frx.kind != FB_NONE) {
+        up = frx.kind == FB_LEFT;
+        slow = false;
+        const int off = up ? -1 : 0;
+        if (frx.kind == FB_GHOST) shx0 = frx.low ? S[-1] : S[0];
+        else if (frx.kind == FB_ZERO) shx0 = 0.0;
+        else
+          shx0 = clamp_rule(forced_state<PPM>(up, (pl + off)[SM::AX0 * SM::PL], (pl + off)[SM::AX1 * SM::PL], S[off], u0, tdx,
+                                              rel_eps), frx.clamp);
+      } else {
+        const int off = up ? -1 : 0;
+        shx0 = trace1<PPM>((pl + off)[SM::AX0 * SM::PL], (pl + off)[SM::AX1 * SM::PL], S[off], u0 * tdx, up);
+        if (slow) shx0 = trace_slow<PPM>(PLN(AX0, 0, -1), S[-1], PLN(AX0, 0, 0), S[0], u0 * tdx);
+      }
       selx = (selx << 2) | (up ? 1u : 0u) | (slow ? 2u : 0u);
       RNG(r0, R_SHX, 0, 0) = shx0;
     }
     {
-      const bool up = v0 > 0.0, slow = !(fabs(v0) > rel_eps);
-      const int off = up ? -P : 0;
-      shy0 = trace1<PPM>((pl + off)[SM::AY0 * SM::PL], (pl + off)[SM::AY1 * SM::PL], S[up ? -SP : 0], v0 * tdy, up);
-      if (slow) shy0 = trace_slow<PPM>(PLN(AY0, -1, 0), S[-SP], PLN(AY0, 0, 0), S[0], v0 * tdy);
+      bool up = v0 > 0.0, slow = !(fabs(v0) > rel_eps);
+      if (BC && fry.kind != FB_NONE) {
+        up = fry.kind == FB_LEFT;
+        slow = false;
+        const int off = up ? -P : 0;
+        if (fry.kind == FB_GHOST) shy0 = fry.low ? S[-SP] : S[0];
+        else if (fry.kind == FB_ZERO) shy0 = 0.0;
+        else
+          shy0 = clamp_rule(forced_state<PPM>(up, (pl + off)[SM::AY0 * SM::PL], (pl + off)[SM::AY1 * SM::PL], S[up ? -SP : 0], v0,
+                                              tdy, rel_eps), fry.clamp);
+      } else {
+        const int off = up ? -P : 0;
+        shy0 = trace1<PPM>((pl + off)[SM::AY0 * SM::PL], (pl + off)[SM::AY1 * SM::PL], S[up ? -SP : 0], v0 * tdy, up);
+        if (slow) shy0 = trace_slow<PPM>(PLN(AY0, -1, 0), S[-SP], PLN(AY0, 0, 0), S[0], v0 * tdy);
+      }
       sely = (sely << 2) | (up ? 1u : 0u) | (slow ? 2u : 0u);
       RNG(r0, R_SHY, 0, 0) = shy0;
     }
@@ -444,8 +590,16 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
         tzs = 0.5 * (PLN(TZ, 0, -1) + PLN(TZ, 0, 0));
       }
       const double shx1 = RNG(r1, R_SHX, 0, 0);
-      PLN(XY, 0, 0) = fma(-c6y, tys, shx1);
-      PLN(XZ, 0, 0) = fma(-c6z, tzs, shx1);
+      double xy = fma(-c6y, tys, shx1), xz = fma(-c6z, tzs, shx1);
+      if (BC && frx.kind != FB_NONE) {
+        if (frx.kind >= FB_GHOST) xy = xz = shx1;  // EXT_DIR / REFLECT_ODD: the boundary value at every stage
+        else {
+          xy = clamp_rule(xy, frx.clamp);
+          xz = clamp_rule(xz, frx.clamp);
+        }
+      }
+      PLN(XY, 0, 0) = xy;
+      PLN(XZ, 0, 0) = xz;
     }
     {
       const int off = (sely & 4u) ? -P : 0;
@@ -456,8 +610,16 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
         tzs = 0.5 * (PLN(TZ, -1, 0) + PLN(TZ, 0, 0));
       }
       const double shy1 = RNG(r1, R_SHY, 0, 0);
-      PLN(YX, 0, 0) = fma(-c6x, txs2, shy1);
-      PLN(YZ, 0, 0) = fma(-c6z, tzs, shy1);
+      double yx = fma(-c6x, txs2, shy1), yz = fma(-c6z, tzs, shy1);
+      if (BC && fry.kind != FB_NONE) {
+        if (fry.kind >= FB_GHOST) yx = yz = shy1;
+        else {
+          yx = clamp_rule(yx, fry.clamp);
+          yz = clamp_rule(yz, fry.clamp);
+        }
+      }
+      PLN(YX, 0, 0) = yx;
+      PLN(YZ, 0, 0) = yz;
     }
     // F3(t-2): final edge states of plane t-2
     {
@@ -466,12 +628,16 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       if (kin && st_x) {
         double g = (pl + ((selx & 16u) ? -1 : 0))[SM::GX * SM::PL];
         if (selx & 32u) g = 0.5 * (PLN(GX, 0, -1) + PLN(GX, 0, 0));
-        gex[q_ex] = RNG(r2, R_SHX, 0, 0) - g;
+        double e = RNG(r2, R_SHX, 0, 0) - g;
+        if (BC && frx.kind != FB_NONE) e = (frx.kind >= FB_GHOST) ? RNG(r2, R_SHX, 0, 0) : clamp_rule(e, frx.clamp);
+        gex[q_ex] = e;
       }
       if (kin && st_y) {
         double g = (pl + ((sely & 16u) ? -P : 0))[SM::GY * SM::PL];
         if (sely & 32u) g = 0.5 * (PLN(GY, -1, 0) + PLN(GY, 0, 0));
-        gey[q_ey] = RNG(r2, R_SHY, 0, 0) - g;
+        double e = RNG(r2, R_SHY, 0, 0) - g;
+        if (BC && fry.kind != FB_NONE) e = (fry.kind >= FB_GHOST) ? RNG(r2, R_SHY, 0, 0) : clamp_rule(e, fry.clamp);
+        gey[q_ey] = e;
       }
     }
     // publish the s tile of plane t+1
@@ -489,17 +655,18 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     shz2 = shz1; shz1 = shz0;
     zx2 = zx1; zy2 = zy1;
     gz3 = gz2;
+    if constexpr (BC) s_m3 = sw[H - 2];
     { const int rt = r2; r2 = r1; r1 = r0; r0 = rt; }  // the slot of plane t-2 becomes the slot of plane t+1
   }
 }
 
-template <int PPM, int BX, int BY, int XF, bool WADD>
+template <int PPM, int BX, int BY, int XF, bool WADD, bool BC>
 void launch_fused2(const FusedArgs& a, int nx, int ny, int nz) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = Smem2<H, BX, BY>;
   Context& c = ctx();
   static bool configured = false;
-  auto kern = k_fused_edge2<PPM, BX, BY, XF, WADD>;
+  auto kern = k_fused_edge2<PPM, BX, BY, XF, WADD, BC>;
   constexpr int bytes = SM::TOTAL * (int)sizeof(double);
   if (!configured) {
     MGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -511,45 +678,52 @@ void launch_fused2(const FusedArgs& a, int nx, int ny, int nz) {
 }
 
 template <int PPM, int BY>
-void launch_fused2_xf(const FusedArgs& a, int nx, int ny, int nz) {
+void launch_fused2_xf(const FusedArgs& a, int nx, int ny, int nz, bool bc) {
   constexpr int BX = MGPU_FUSED_BX;
   const int xf = a.sdiv ? 1 : (a.ssub ? 2 : 0);
+  if (bc) {  // boxes with physical boundaries: plain inputs, 32x8 tile
+    if (xf != 0 || a.wadd) throw Error("make_edge_scal: on-the-fly transforms are not built for boxes with physical boundaries");
+    if constexpr (BY == 8) launch_fused2<PPM, BX, BY, 0, false, true>(a, nx, ny, nz);
+    else throw Error("make_edge_scal: the boundary variant of the upwind-first kernel is built for the 32x8 tile");
+    return;
+  }
   if (a.sdiv && a.ssub) throw Error("make_edge_scal: only one on-the-fly transform of s at a time");
   if constexpr (BY == 8) {
     if (a.wadd) {
-      if (xf == 0) launch_fused2<PPM, BX, BY, 0, true>(a, nx, ny, nz);
-      else if (xf == 1) launch_fused2<PPM, BX, BY, 1, true>(a, nx, ny, nz);
-      else launch_fused2<PPM, BX, BY, 2, true>(a, nx, ny, nz);
+      if (xf == 0) launch_fused2<PPM, BX, BY, 0, true, false>(a, nx, ny, nz);
+      else if (xf == 1) launch_fused2<PPM, BX, BY, 1, true, false>(a, nx, ny, nz);
+      else launch_fused2<PPM, BX, BY, 2, true, false>(a, nx, ny, nz);
       return;
     }
   }
   if (xf != 0 || a.wadd) throw Error("make_edge_scal: on-the-fly transforms are built for the 32x8 tile with wadd only");
-  launch_fused2<PPM, BX, BY, 0, false>(a, nx, ny, nz);
+  launch_fused2<PPM, BX, BY, 0, false, false>(a, nx, ny, nz);
 }
 
 }  // namespace
 
 // all six faces INTERIOR, FAST arithmetic.  a.kchunk: z planes per CTA.
 template <int BY>
-static void fused_edge2_launch_by(const FusedArgs& a, int ppm_type, int nx, int ny, int nz) {
+static void fused_edge2_launch_by(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc) {
   // 32-bit in-plane offsets
   for (const DV* v : {&a.s, &a.force, &a.umac[0], &a.umac[1], &a.umac[2], &a.sedge[0], &a.sedge[1], &a.sedge[2]})
     if (v->cs >= (1L << 31)) throw Error("make_edge_scal: fab too large for the fused kernel's 32-bit offsets");
   switch (ppm_type) {
-    case 0: launch_fused2_xf<0, BY>(a, nx, ny, nz); break;
-    case 1: launch_fused2_xf<1, BY>(a, nx, ny, nz); break;
-    case 2: launch_fused2_xf<2, BY>(a, nx, ny, nz); break;
+    case 0: launch_fused2_xf<0, BY>(a, nx, ny, nz, bc); break;
+    case 1: launch_fused2_xf<1, BY>(a, nx, ny, nz, bc); break;
+    case 2: launch_fused2_xf<2, BY>(a, nx, ny, nz, bc); break;
     default: throw Error("make_edge_scal: invalid ppm_type");
   }
 }
 
 static int g_by = MGPU_FUSED2_BY;
 void fused_edge2_set_by(int by) { g_by = by; }
-void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz) {
-  if (g_by == 16 && !a.wadd && !a.sdiv && !a.ssub) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz);
-  else if (g_by == 10 && !a.wadd && !a.sdiv && !a.ssub) fused_edge2_launch_by<10>(a, ppm_type, nx, ny, nz);
-  else if (g_by == 12 && !a.wadd && !a.sdiv && !a.ssub) fused_edge2_launch_by<12>(a, ppm_type, nx, ny, nz);
-  else fused_edge2_launch_by<8>(a, ppm_type, nx, ny, nz);
+void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc) {
+  const bool plain = !a.wadd && !a.sdiv && !a.ssub && !bc;
+  if (g_by == 16 && plain) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz, false);
+  else if (g_by == 10 && plain) fused_edge2_launch_by<10>(a, ppm_type, nx, ny, nz, false);
+  else if (g_by == 12 && plain) fused_edge2_launch_by<12>(a, ppm_type, nx, ny, nz, false);
+  else fused_edge2_launch_by<8>(a, ppm_type, nx, ny, nz, bc);
 }
 
 }  // namespace mgpu

@@ -90,14 +90,16 @@ def test_fused_edge_ragged_boxes(gpu_ops, oracle, ppm_type, bcset, shape, kchunk
 @pytest.mark.parametrize("ppm_type", [0, 1, 2])
 @pytest.mark.parametrize("variant", [0, 1], ids=["literal", "upwind-first"])
 @pytest.mark.parametrize("shape,kchunk", [((37, 9, 11), 4), ((30, 6, 40), 16), ((70, 20, 9), 64)])
-def test_fused_edge_slow_faces(gpu_ops, oracle, ppm_type, variant, shape, kchunk):
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
+def test_fused_edge_slow_faces(gpu_ops, oracle, ppm_type, variant, shape, kchunk, bcset):
     """FAST fused kernels on periodic boxes where a large share of the faces has |u| <= rel_eps (the
     reference then averages the left and right states, make_edge_scal.f90:881-883), some faces have u == 0
     exactly, and the velocity changes sign inside warps.  The upwind-first kernel (mgpu_fused2.cu) takes its
     averaged-T/G branch there."""
     from maestro_b200 import lib
 
-    st = make_state(3, shape, ppm_type=ppm_type)
+    phys = {"periodic": None, "walls": WALLS_3D, "inout": INOUT_3D}[bcset]
+    st = make_state(3, shape, phys_bc=phys, ppm_type=ppm_type)
     umax = max(np.abs(u.a).max() for u in st["umac"])
     for u in st["umac"]:
         u.a[np.abs(u.a) < 0.15 * umax] = 0.0
@@ -107,12 +109,14 @@ def test_fused_edge_slow_faces(gpu_ops, oracle, ppm_type, variant, shape, kchunk
     lib.set_option("kchunk", kchunk)
     try:
         g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
+        gv, cv = edge_pair(gpu_ops, oracle, st, (1, 3), is_vel=True, bccomp0=1)
     finally:
         lib.set_option("kchunk", 32)
         lib.set_option("fused_variant", 1)
     for d in range(3):
         for c_ in range(3):
             check(g[d].a[c_], c[d].a[c_], bitwise=False)
+            check(gv[d].a[c_], cv[d].a[c_], bitwise=False)
 
 
 @pytest.mark.parametrize("dm,n", [(2, 24), (3, 16)])
