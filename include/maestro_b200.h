@@ -283,6 +283,14 @@ int mgpu_modify_scal_force_sphr(const mgpu_params* p, const mgpu_geom* g, int nf
 int mgpu_put_in_pert_form_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* s,
                                const double* s0, int comp, int flag);
 
+/* density_advance with spherical == 1 as one device-resident episode (Source/density_advance.f90:20): rho0_old_cart and
+ * the rho0mac arrays are built on the device (put_1d_array_on_cart + ghost fill, make_s0mac); w0mac is the caller's
+ * (make_w0mac); no etarhoflux in spherical geometry.  rho0_old / rho0_new: radial arrays (0:nr_fine-1). */
+int mgpu_density_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int which_step, mgpu_fab* sold, mgpu_fab* snew,
+                              mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
+                              mgpu_fab* const* umac, const double* w0, const mgpu_fab* const* w0mac,
+                              const double* rho0_old, const double* rho0_new, const int* adv_bc, const int* pmask);
+
 /* ---- L4 episode: density_advance (Source/density_advance.f90:20), planar, one level ------
  * Signature mirrors the Fortran argument list; sold is modified in place exactly as the reference
  * does (rhoX->X->rhoX, rho->rho'->rho round trips), umac is (umac+w0)-w0 on return, sedge, sflux,

@@ -507,6 +507,135 @@ static void fill_faces_dev(const mgpu_params& P, DV* u, const int* lo, const int
   for (int d = 0; d < P.dm; ++d) fill_boundary_dev(P, u[d], lo, hi, 1, NODAL_D[d], 1, 1, 1, adv_bc, pmask, false);
   fb.run();
 }
+
+// ---- density_advance, spherical (density_advance.f90:20 with spherical == 1) ---------------------------------------
+static void density_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, int which_step, DV& sold, DV& snew,
+                                     DV* sedge, DV* sflux, DV& scal_force, DV* umac, const double* w0_h, const DV* w0mac,
+                                     const double* rho0_old_h, const double* rho0_new_h, const int* lo, const int* hi,
+                                     int ng_s, int ng_f, const int* adv_bc, const int* pmask) {
+  const int dm = 3, spt = P.species_pred_type;
+  const int foextrap_comp = dm + P.nscal + 2;
+  Geom gd = make_geom(P, g);
+  const double* rho0_old = upload_small(rho0_old_h, (size_t)g.nr_fine);
+  const double* rho0_new = upload_small(rho0_new_h, (size_t)g.nr_fine);
+  const int zero3[3] = {0, 0, 0};
+  auto cart_of = [&](const double* s0_dev, int ng) {  // put_1d_array_on_cart incl. its ghost fill (fill_3d_data.f90:21)
+    DV c = make_view(nullptr, lo, hi, dm, ng, zero3, 1);
+    c.p = arena_alloc((size_t)c.size());
+    put_1d_array_on_cart_dev(P, g, gd, s0_dev, c, false, false, lo, hi);
+    fill_boundary_dev(P, c, lo, hi, ng, nullptr, 1, dm + P.rho_comp, 1, adv_bc, pmask, false);
+    return c;
+  };
+  auto fill_umac = [&]() {
+    FillBatch fb;
+    for (int d = 0; d < dm; ++d) fill_boundary_dev(P, umac[d], lo, hi, 1, NODAL_D[d], 1, 1, 1, adv_bc, pmask, false);
+    fb.run();
+  };
+  set_dev(scal_force.p, 0.0, scal_force.size());
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {
+    DV rho0_old_cart = cart_of(rho0_old, 1);
+    modify_scal_force_sphr_dev(P, g, gd, scal_force, sold, umac, rho0_old_cart, w0_h, P.rho_comp,
+                               spt == MGPU_PREDICT_RHO_AND_X, lo, hi);
+    fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
+  }
+  {
+    DV wm[3] = {w0mac[0], w0mac[1], w0mac[2]};
+    addw0_sphr_dev(umac, wm, 1.0, lo, hi);
+  }
+  fill_umac();
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {
+    convert_rhoX_to_X_dev(P, sold, true, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, foextrap_comp, P.nspec, adv_bc, pmask, true);
+  }
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) {
+    pert_form_sphr_dev(g, gd, sold, rho0_old, P.rho_comp, true, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
+  }
+  auto edge = [&](int scomp, int ncomp, bool cons) {
+    for (int n = 0; n < ncomp; ++n) {
+      if (P.bds_type != 0) {
+        size_t mark = arena_mark();
+        bds_dev(P, sold, sedge, umac, scal_force, lo, hi, scomp - 1 + n, cons, ng_s, ng_f);
+        arena_release(mark);
+        continue;
+      }
+      edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, scomp - 1 + n, dm + scomp + n, false, cons, ng_s,
+                    ng_f);
+    }
+  };
+  edge(P.spec_comp, P.nspec, spt == MGPU_PREDICT_RHOX);
+  if (spt == MGPU_PREDICT_RHOX) {
+    for (int d = 0; d < dm; ++d) sum_comps_dev(sedge[d], P.rho_comp - 1, P.spec_comp - 1, P.nspec);
+  } else {
+    edge(P.rho_comp, 1, false);
+  }
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) {
+    pert_form_sphr_dev(g, gd, sold, rho0_old, P.rho_comp, false, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
+  }
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {
+    convert_rhoX_to_X_dev(P, sold, false, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
+  }
+  if (P.ntrac >= 1) edge(P.trac_comp, P.ntrac, false);
+  {
+    DV wm[3] = {w0mac[0], w0mac[1], w0mac[2]};
+    addw0_sphr_dev(umac, wm, -1.0, lo, hi);
+  }
+  fill_umac();
+  // rho0mac_old / rho0mac_new (make_s0mac, fill_3d_data.f90:942)
+  auto mac_of = [&](const double* s0_dev, DV* mac) {
+    for (int d = 0; d < 3; ++d) {
+      mac[d] = make_view(nullptr, lo, hi, dm, 1, NODAL_D[d], 1);
+      mac[d].p = arena_alloc((size_t)mac[d].size());
+    }
+    if (g.s0mac_interp_type == 1) {
+      DV c = cart_of(s0_dev, 2);
+      make_mac_dev(g, gd, s0_dev, mac, &c, 1, lo, hi);
+    } else {
+      make_mac_dev(g, gd, s0_dev, mac, nullptr, 1, lo, hi);
+    }
+  };
+  SphrFluxArgs fa;
+  fa.spt = spt;
+  fa.rho = P.rho_comp - 1;
+  fa.rhoh = P.rhoh_comp - 1;
+  fa.vb = grown(lo, hi, dm, 0);
+  mac_of(rho0_old, fa.r0o);
+  if (which_step == 2) mac_of(rho0_new, fa.r0n);
+  else for (int d = 0; d < 3; ++d) fa.r0n[d] = fa.r0o[d];
+  for (int d = 0; d < 3; ++d) {
+    fa.sflux[d] = sflux[d];
+    fa.sedge[d] = sedge[d];
+    fa.umac[d] = umac[d];
+    fa.w0mac[d] = w0mac[d];
+    fa.h0o[d] = fa.h0n[d] = fa.r0o[d];
+  }
+  mk_rhoX_flux_sphr_dev(fa, P.spec_comp, P.spec_comp + P.nspec - 1);
+  if (P.ntrac >= 1) mk_rhoX_flux_sphr_dev(fa, P.trac_comp, P.trac_comp + P.ntrac - 1);
+  set_dev(scal_force.p, 0.0, scal_force.size());
+  UpdArgs ua;
+  ua.dm = dm;
+  ua.dt = P.dt;
+  for (int d = 0; d < 3; ++d) ua.dx[d] = P.dx[d];
+  ua.vb = grown(lo, hi, dm, 0);
+  ua.sold = sold;
+  ua.snew = snew;
+  ua.force = scal_force;
+  for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
+  update_scal_dev(P, ua, P.spec_comp, P.spec_comp + P.nspec - 1);
+  {
+    FillBatch fb;
+    fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
+    fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
+    fb.run();
+  }
+  if (P.ntrac >= 1) {
+    update_scal_dev(P, ua, P.trac_comp, P.trac_comp + P.ntrac - 1);
+    fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.trac_comp, dm + P.trac_comp, P.ntrac, adv_bc, pmask, false);
+  }
+}
+
 static DV arena_fab(const int* lo, const int* hi, int dm, int ng, const int* nodal, int nc) {
   DV v = make_view(nullptr, lo, hi, dm, ng, nodal, nc);
   v.p = arena_alloc((size_t)v.size());
@@ -1528,6 +1657,28 @@ int mgpu_put_in_pert_form_sphr(const mgpu_params* p, const mgpu_geom* g, int nfa
     DV sv = c.view(s[i], true, true);
     pert_form_sphr_dev(*g, gd, sv, s0d, comp, flag != 0, s[i].lo, s[i].hi);
   }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_density_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int which_step, mgpu_fab* sold, mgpu_fab* snew,
+                              mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
+                              mgpu_fab* const* umac, const double* w0, const mgpu_fab* const* w0mac,
+                              const double* rho0_old, const double* rho0_new, const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  need_sphr(p, g);
+  size_t cell = 1;
+  for (int d = 0; d < 3; ++d) cell *= (size_t)(sold->hi[d] - sold->lo[d] + 1 + 6);
+  Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
+                10 * (cell * sizeof(double) + 256) + geom_scratch(g) + 8192);
+  DV so = c.view(*sold, true, true), sn = c.view(*snew, true, true), fv = c.view(*scal_force, false, true);
+  DV se[3], sf[3], um[3], wm[3];
+  c.views((const mgpu_fab* const*)sedge, 0, true, true, se);
+  c.views((const mgpu_fab* const*)sflux, 0, true, true, sf);
+  c.views((const mgpu_fab* const*)umac, 0, true, true, um);
+  c.views(w0mac, 0, true, false, wm);
+  density_advance_sphr_dev(*p, *g, which_step, so, sn, se, sf, fv, um, w0, wm, rho0_old, rho0_new, sold->lo, sold->hi,
+                           sold->ng, scal_force->ng, adv_bc, pmask);
   c.finish();
   MGPU_CATCH
 }

@@ -526,7 +526,9 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
     throw Error("make_edge_scal: on-the-fly input transforms need the upwind-first kernel (internal error)");
   if (exact)
     fused_edge_launch_exact(a, P.ppm_type, any_bc, nx, ny, nz);
-  else if (g_variant == 1 || (g_variant == 2 && !any_bc))
+  else if ((g_variant == 1 && !(any_bc && P.ppm_type == 2 && !xform)) || (g_variant == 2 && !any_bc) || g_variant == 3)
+    // (variant 1 leaves ppm_type 2 on boxes with physical boundaries to the literal kernel: measured equal or faster
+    //  there, profiles/r01i_episodes.md; variant 3 forces the upwind-first kernel everywhere, for the tests)
     fused_edge2_launch(a, P.ppm_type, nx, ny, nz, any_bc);
   else
     fused_edge_launch_fast(a, P.ppm_type, any_bc, nx, ny, nz);

@@ -183,6 +183,16 @@ class Operators:
         b, bp = as_double_p(s0)
         self._call("put_in_pert_form_sphr", C.byref(p), C.byref(geom.c), 1, fab_ptr(s), bp, comp, int(flag))
 
+    def density_advance_sphr(self, p, geom, which_step, sold, snew, sedge, sflux, scal_force, umac, w0, w0mac, rho0_old,
+                             rho0_new, adv_bc, pmask):
+        keep = [as_double_p(x) for x in (w0, rho0_old, rho0_new)]
+        bc, bcp = as_int_p(adv_bc)
+        pm, pmp = as_int_p(pmask)
+        ptrs = [fab_pp(x) for x in (sedge, sflux, umac, w0mac)]
+        self._call("density_advance_sphr", C.byref(p), C.byref(geom.c), which_step, fab_ptr(sold), fab_ptr(snew),
+                   ptrs[0][0], ptrs[1][0], fab_ptr(scal_force), ptrs[2][0], keep[0][1], ptrs[3][0], keep[1][1],
+                   keep[2][1], bcp, pmp)
+
     # ---- L4 driver -----------------------------------------------------------------------------
     def density_advance(self, p, which_step, sold, snew, sedge, sflux, scal_force, umac, w0, etarhoflux, rho0_old,
                         rho0_new, p0_dummy, rho0_predicted_edge, adv_bc, pmask):

@@ -323,6 +323,113 @@ void pert_form_sphr(const mgpu_params& P, const mgpu_geom& g, Arr& s, const doub
   for_box(grown(lo, hi, 3, 0), [&](int i, int j, int k) { s(i, j, k) = s(i, j, k) + mult * s0_cart(i, j, k); });
 }
 
+
+// density_advance (Source/density_advance.f90:20) with spherical == 1: rho0_old_cart for the force (:105-111), addw0
+// with w0mac (:148), spherical perturbational form (:166,229), rho0mac_old/new by make_s0mac (:268-311), no etarhoflux.
+void density_advance_sphr_box(const mgpu_params& P, const mgpu_geom& g, int which_step, Arr& sold, Arr& snew, Arr* sedge,
+                              Arr* sflux, Arr& scal_force, Arr* umac, const double* w0, const Arr* w0mac,
+                              const double* rho0_old, const double* rho0_new, const int* lo, const int* hi, int ng_s,
+                              int ng_f, const int* adv_bc, const int* pmask) {
+  const int dm = 3, spt = P.species_pred_type;
+  const int foextrap_comp = dm + P.nscal + 2;
+  auto cart_of = [&](const double* s0, int ng) {  // put_1d_array_on_cart (fill_3d_data.f90:21) incl. its ghost fill
+    Arr c(lo[0] - ng, hi[0] + ng, lo[1] - ng, hi[1] + ng, lo[2] - ng, hi[2] + ng, 1);
+    put_1d_array_on_cart_sphr(P, g, false, false, s0, c, lo, hi);
+    // component 1 of a 1-component array filled with the BCs of the density (bc_comp = dm+rho_comp)
+    fill_boundary_box(P, c, lo, hi, ng, 1, dm + P.rho_comp, 1, adv_bc, pmask);
+    return c;
+  };
+  auto fill_umac = [&]() {
+    for (int d = 0; d < dm; ++d) fill_boundary_face(P, umac[d], lo, hi, 1, d, pmask);
+  };
+  scal_force.fill(0.0);
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {
+    Arr rho0_old_cart = cart_of(rho0_old, 1);
+    Arr fo = scal_force.comp(P.rho_comp - 1), sa = sold.comp(P.rho_comp - 1);
+    modify_scal_force_sphr(P, g, fo, sa, umac, rho0_old_cart, w0, spt == MGPU_PREDICT_RHO_AND_X, lo, hi);
+    fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rho_comp, foextrap_comp, 1, adv_bc, pmask);
+  }
+  addw0_sphr(umac, w0mac, lo, hi, 1.0);
+  fill_umac();
+  Box vb = grown(lo, hi, dm, 0);
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {
+    for (int n = 0; n < P.nspec; ++n) {
+      const int c = P.spec_comp - 1 + n;
+      for_box(vb, [&](int i, int j, int k) { sold(i, j, k, c) = sold(i, j, k, c) / sold(i, j, k, P.rho_comp - 1); });
+      fill_boundary_box(P, sold, lo, hi, ng_s, c + 1, foextrap_comp, 1, adv_bc, pmask);
+    }
+  }
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) {
+    Arr sa = sold.comp(P.rho_comp - 1);
+    pert_form_sphr(P, g, sa, rho0_old, true, lo, hi);
+    fill_boundary_box(P, sold, lo, hi, ng_s, P.rho_comp, foextrap_comp, 1, adv_bc, pmask);
+  }
+  auto edge = [&](int scomp, int ncomp, bool cons) {
+    for (int n = 0; n < ncomp; ++n) {
+      if (P.bds_type == 0)
+        make_edge_scal_box(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, scomp - 1 + n, dm + scomp + n, false, cons, ng_s);
+      else
+        bds_box(P, sold, sedge, umac, scal_force, lo, hi, scomp - 1 + n, cons);
+    }
+  };
+  edge(P.spec_comp, P.nspec, spt == MGPU_PREDICT_RHOX);
+  if (spt == MGPU_PREDICT_RHOX) {
+    for (int d = 0; d < dm; ++d) {
+      Arr r = sedge[d].comp(P.rho_comp - 1), s1 = sedge[d].comp(P.spec_comp - 1);
+      for (size_t q = 0; q < r.size(); ++q) r.p[q] = s1.p[q];
+      for (int n = 1; n < P.nspec; ++n) {
+        Arr sn = sedge[d].comp(P.spec_comp - 1 + n);
+        for (size_t q = 0; q < r.size(); ++q) r.p[q] = r.p[q] + sn.p[q];
+      }
+    }
+  } else {
+    edge(P.rho_comp, 1, false);
+  }
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) {
+    Arr sa = sold.comp(P.rho_comp - 1);
+    pert_form_sphr(P, g, sa, rho0_old, false, lo, hi);
+    fill_boundary_box(P, sold, lo, hi, ng_s, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask);
+  }
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {
+    for (int n = 0; n < P.nspec; ++n) {
+      const int c = P.spec_comp - 1 + n;
+      for_box(vb, [&](int i, int j, int k) { sold(i, j, k, c) = sold(i, j, k, c) * sold(i, j, k, P.rho_comp - 1); });
+    }
+    fill_boundary_box(P, sold, lo, hi, ng_s, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask);
+  }
+  if (P.ntrac >= 1) edge(P.trac_comp, P.ntrac, false);
+  addw0_sphr(umac, w0mac, lo, hi, -1.0);
+  fill_umac();
+  // rho0mac_old / rho0mac_new (make_s0mac, fill_3d_data.f90:942): via cell centres (ng = 2) when s0mac_interp_type = 1
+  auto mac_of = [&](const double* s0, Arr* mac) {
+    for (int d = 0; d < 3; ++d) {
+      Box b;
+      for (int q = 0; q < 3; ++q) { b.lo[q] = lo[q] - 1; b.hi[q] = hi[q] + 1 + (q == d ? 1 : 0); }
+      mac[d].alloc(b.lo[0], b.hi[0], b.lo[1], b.hi[1], b.lo[2], b.hi[2], 1);
+    }
+    if (g.s0mac_interp_type == 1) {
+      Arr c = cart_of(s0, 2);
+      make_s0mac_sphr(P, g, s0, mac, &c, lo, hi);
+    } else {
+      make_s0mac_sphr(P, g, s0, mac, nullptr, lo, hi);
+    }
+  };
+  Arr r0o[3], r0n[3];
+  mac_of(rho0_old, r0o);
+  if (which_step == 2) mac_of(rho0_new, r0n);
+  const Arr* rn = (which_step == 1) ? r0o : r0n;
+  mk_rhoX_flux_sphr(P, sflux, sedge, umac, w0mac, r0o, rn, P.spec_comp, P.spec_comp + P.nspec - 1, lo, hi);
+  if (P.ntrac >= 1) mk_rhoX_flux_sphr(P, sflux, sedge, umac, w0mac, r0o, rn, P.trac_comp, P.trac_comp + P.ntrac - 1, lo, hi);
+  scal_force.fill(0.0);
+  update_scal_box(P, P.spec_comp, P.spec_comp + P.nspec - 1, sold, snew, sflux, scal_force, lo, hi);
+  fill_boundary_box(P, snew, lo, hi, ng_s, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask);
+  fill_boundary_box(P, snew, lo, hi, ng_s, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask);
+  if (P.ntrac >= 1) {
+    update_scal_box(P, P.trac_comp, P.trac_comp + P.ntrac - 1, sold, snew, sflux, scal_force, lo, hi);
+    fill_boundary_box(P, snew, lo, hi, ng_s, P.trac_comp, dm + P.trac_comp, P.ntrac, adv_bc, pmask);
+  }
+}
+
 }  // namespace mo
 
 // ---------------------------------------------------------------------------------------------
@@ -509,6 +616,23 @@ int mo_put_in_pert_form_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs
     Arr sa = Arr::view(s[i], 3).comp(comp - 1);
     pert_form_sphr(*p, *g, sa, s0, flag != 0, s[i].lo, s[i].hi);
   }
+  MO_CATCH
+}
+
+int mo_density_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int which_step, mgpu_fab* sold, mgpu_fab* snew,
+                            mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force, mgpu_fab* const* umac,
+                            const double* w0, const mgpu_fab* const* w0mac, const double* rho0_old,
+                            const double* rho0_new, const int* adv_bc, const int* pmask) {
+  MO_TRY
+  need3(p);
+  Arr so = Arr::view(*sold, 3), sn = Arr::view(*snew, 3), fo = Arr::view(*scal_force, 3);
+  Arr se[3], sf[3], um[3], wm[3];
+  views3((const mgpu_fab* const*)sedge, 0, se);
+  views3((const mgpu_fab* const*)sflux, 0, sf);
+  views3((const mgpu_fab* const*)umac, 0, um);
+  views3(w0mac, 0, wm);
+  density_advance_sphr_box(*p, *g, which_step, so, sn, se, sf, fo, um, w0, wm, rho0_old, rho0_new, sold->lo, sold->hi,
+                           sold->ng, scal_force->ng, adv_bc, pmask);
   MO_CATCH
 }
 

@@ -105,7 +105,7 @@ def test_fused_edge_slow_faces(gpu_ops, oracle, ppm_type, variant, shape, kchunk
         u.a[np.abs(u.a) < 0.15 * umax] = 0.0
     st["p"].rel_eps = 0.3 * umax
     lib.set_option("exact", 0)
-    lib.set_option("fused_variant", variant)
+    lib.set_option("fused_variant", 3 if variant else 0)  # 3: upwind-first kernel for every box and ppm_type
     lib.set_option("kchunk", kchunk)
     try:
         g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
@@ -744,3 +744,35 @@ def test_sphr_mkutrans_velpred(gpu_ops, oracle, ppm_type):
     ut0 = face_fabs(lo, hi, 1, 1, 3)
     oracle.mkutrans(p, vs["utilde"], vs["ufull"], ut0, np.zeros(p.nr + 1), vs["adv_bc"], vs["phys_bc"])
     assert not same(ut0[0].a, res[1][0].a)
+
+
+@pytest.mark.parametrize("spt", [abi.PREDICT_RHOPRIME_AND_X, abi.PREDICT_RHOX, abi.PREDICT_RHO_AND_X])
+@pytest.mark.parametrize("which_step,s0mac_t", [(1, 1), (2, 1), (2, 3)])
+@pytest.mark.parametrize("exact", [1, 0], ids=["exact", "fast"])
+def test_sphr_density_advance(gpu_ops, oracle, spt, which_step, s0mac_t, exact):
+    """density_advance with spherical == 1 (SURVEY config C5 in miniature: outlet on all sides, radial base state):
+    rho0_old_cart, spherical perturbational form, addw0 with w0mac, rho0mac by make_s0mac, spherical fluxes"""
+    from maestro_b200 import lib
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state((14, 12, 10), ops=oracle, s0mac_interp_type=s0mac_t)
+    p, g, lo, hi = st["p"], st["geom"], st["lo"], st["hi"]
+    p.species_pred_type = spt
+    p.rel_eps = 1e-8 * max(np.abs(u.a).max() for u in st["umac"])
+    lib.set_option("exact", exact)
+    res = []
+    for o in (gpu_ops, oracle):
+        sold = st["s"].clone()
+        oracle.fill_boundary(p, sold, 1, 4, p.nscal, st["adv_bc"], st["pmask"])
+        snew = sold.clone()
+        umac = [u.clone() for u in st["umac"]]
+        sedge = face_fabs(lo, hi, 0, p.nscal, 3)
+        sflux = face_fabs(lo, hi, 0, p.nscal, 3)
+        force = st["force"].clone()
+        o.density_advance_sphr(p, g, which_step, sold, snew, sedge, sflux, force, umac, st["rad"]["w0"], st["w0mac"],
+                               st["rad"]["rho0_old"], st["rad"]["rho0_new"], st["adv_bc"], st["pmask"])
+        comps = [p.rho_comp - 1] + list(range(p.spec_comp - 1, p.spec_comp - 1 + p.nspec)) + [p.trac_comp - 1]
+        res.append([sold.a[comps], snew.a[comps], force.a] + [f.a[comps] for f in sedge] +
+                   [f.a[comps[1:]] for f in sflux] + [u.a for u in umac])
+    for a, b in zip(*res):
+        check(a, b, bitwise=bool(exact))
