@@ -263,6 +263,24 @@ static void edge_one_comp(const mgpu_params& P, const DV& s, DV* sedge, const DV
   }
 }
 
+// Which device-resident form of density_advance a call takes ("The density_advance episode").  Only global
+// properties enter (options, parameters, the BC table, pmask): every rank of a slab run takes the same form.
+static bool density_advance_is_lean(const mgpu_params& P) {
+  const int spt = P.species_pred_type;
+  return g_opt_exact == 0 && g_opt_fused && P.bds_type == 0 && fused_edge_supported(P, false) &&
+         (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X);
+}
+static bool density_advance_is_leanplus(const mgpu_params& P, const int* adv_bc, const int* pmask) {
+  if (!density_advance_is_lean(P) || P.dm != 3 || g_opt_leanplus == 0) return false;
+  if (!(pmask[0] && pmask[1] && pmask[2])) return false;
+  const int dm = P.dm;
+  for (int c : {P.rho_comp, P.trac_comp})
+    if (!fused_edge_is_upwind_first(P, adv_bc, dm + c, false)) return false;
+  for (int n = 0; n < P.nspec; ++n)
+    if (!fused_edge_is_upwind_first(P, adv_bc, dm + P.spec_comp + n, false)) return false;
+  return true;
+}
+
 // ---- density_advance, "lean+" device-resident episode (see density_advance_dev) --------------------------------
 static void fill_flux_args(const mgpu_params& P, FluxArgs& a, const int* lo, const int* hi);
 static void density_advance_leanplus(const mgpu_params& P, int which_step, DV& sold, DV& snew, DV* sedge, DV* sflux,
@@ -380,21 +398,8 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
   // "lean" episode (FAST arithmetic, fused edge kernel for every component): the forces of the species and tracers
   // are identically zero (:99-103), so the edge kernels do not read them and only the density component of
   // scal_force has to be zero before modify_scal_force writes it; scal_force is zeroed once, at the end (:349-351).
-  const bool lean = g_opt_exact == 0 && g_opt_fused && P.bds_type == 0 && fused_edge_supported(P, false) &&
-                    (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X);
-  // "lean+" (every predicted component runs the upwind-first kernel, i.e. all six faces of the box are INTERIOR for
-  // all of them): rhoX -> X, rho -> rho' and umac + w0 are applied on the fly while the edge kernels stage their
-  // tiles, so sold and umac are never rewritten in HBM: no transform passes, no addw0 passes and only one ghost fill
-  // of the raw inputs.  On return sold and umac hold the caller's values (the reference returns their round trips
-  // (rhoX/rho)*rho and (umac+w0)-w0, one rounding away).
-  // pmask: the decision must be the same on every rank of a slab-partitioned run (it changes the exchange sequence)
-  bool leanp = lean && dm == 3 && g_opt_leanplus != 0 && pmask[0] && pmask[1] && pmask[2];
-  if (leanp) {
-    for (int c : {P.rho_comp, P.spec_comp, P.trac_comp})
-      if (!fused_edge_is_upwind_first(P, adv_bc, dm + c, g_opt_exact != 0)) leanp = false;
-    for (int n = 1; n < P.nspec; ++n)
-      if (!fused_edge_is_upwind_first(P, adv_bc, dm + P.spec_comp + n, false)) leanp = false;
-  }
+  const bool lean = density_advance_is_lean(P);
+  const bool leanp = density_advance_is_leanplus(P, adv_bc, pmask);
   if (leanp) {
     density_advance_leanplus(P, which_step, sold, snew, sedge, sflux, scal_force, umac, w0_h, w0, eta, rho0_old_h,
                              rho0_old, rho0_edge_old, (which_step == 1) ? rho0_old : rho0_new,
@@ -1304,17 +1309,20 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
                       (p->ntrac >= 1 ? crange(p->trac_comp - 1, p->ntrac) : 0);
   const cmask_t flx = crange(p->spec_comp - 1, p->nspec) | (p->ntrac >= 1 ? crange(p->trac_comp - 1, p->ntrac) : 0);
   const cmask_t edg = p->species_pred_type == MGPU_PREDICT_RHOX ? adv : adv;  // rho edge = sum of rhoX edges or predicted
+  // lean+ form: sold and umac are not rewritten and every ghost cell of the advanced components of snew is refilled,
+  // so neither needs to travel back / in over PCIe
+  const bool leanp = density_advance_is_leanplus(*p, adv_bc, pmask);
   // sold: rho and species are transformed in place and restored (round trips); tracers are read only
-  DV so = c.view(*sold, adv, crange(p->rho_comp - 1, 1) | crange(p->spec_comp - 1, p->nspec));
+  DV so = c.view(*sold, adv, leanp ? (cmask_t)0 : (crange(p->rho_comp - 1, 1) | crange(p->spec_comp - 1, p->nspec)));
   // snew: only the advanced components are written; their ghost corners next to physical walls keep the caller's
   // values (multifab_physbc.f90:165-175), hence copy-in of exactly those components
-  DV sn = c.view(*snew, adv, adv);
+  DV sn = c.view(*snew, leanp ? (cmask_t)0 : adv, adv);
   DV fv = c.view(*scal_force, (cmask_t)0, (cmask_t)0);  // zeroed on entry (:101) and again before the update (:349)
   DV eta = c.view(*etarhoflux, true, true);
   DV se[3], sf[3], um[3];
   c.views((const mgpu_fab* const*)sedge, 0, (cmask_t)0, edg, se);  // every face of the predicted components is written
   c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, flx, sf);
-  c.views((const mgpu_fab* const*)umac, 0, true, true, um);
+  c.views((const mgpu_fab* const*)umac, 0, true, !leanp, um);
   c.zero_on_host(*scal_force);
   density_advance_dev(*p, which_step, so, sn, se, sf, fv, um, w0, eta, rho0_old, rho0_new, rho0_predicted_edge,
                       sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
