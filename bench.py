@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="zones per side of the per-GPU box")
     ap.add_argument("--e2e-steps", type=lambda v: max(1, int(v)), default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (mgpu_set_option), e.g. fused_by=1616")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,6 +215,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
     ops = lib.init(local_rank, use_torch_stream=True)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        lib.set_option(key, int(val))
     n = args.n
     if world > 1:  # NCCL communicator of the library: halo exchange inside every ghost fill of the episode
         from maestro_b200 import slab

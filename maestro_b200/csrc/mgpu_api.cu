@@ -22,7 +22,7 @@ namespace mgpu {
 static Context g_ctx;
 static std::string g_err;
 static int g_opt_fused = 1;    // use the fused 3-D edge kernel when it covers the case
-static int g_opt_kchunk = 32;  // z planes per CTA of the fused kernel
+static int g_opt_kchunk = -1;  // z planes per CTA of the fused kernels; < 0: chosen per launch (fused2_auto_kchunk)
 static int g_opt_leanplus = 1;  // density_advance: on-the-fly input transforms where the upwind-first kernel applies
 static int g_opt_exact = 0;    // 1: bit-identical arithmetic everywhere (fused kernel built with -fmad=false)
 Context& ctx() { return g_ctx; }

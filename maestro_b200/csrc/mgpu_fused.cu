@@ -519,11 +519,16 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
   a.s = s_full.comp(comp);
   a.force = force_full.comp(comp);
   const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
-  a.kchunk = kchunk > 0 ? kchunk : nz;
+  // kchunk < 0: the upwind-first kernel balances the chunk against its resident CTA slots (fused2_auto_kchunk);
+  // the literal kernels keep 32 planes
+  a.kchunk = kchunk > 0 ? kchunk : (kchunk < 0 ? -1 : nz);
   if (a.kchunk > nz) a.kchunk = nz;
   const bool xform = sdiv || ssub || wadd;
   if (xform && (exact || any_bc || g_variant == 0))
     throw Error("make_edge_scal: on-the-fly input transforms need the upwind-first kernel (internal error)");
+  const bool to_fused2 =
+      !exact && ((g_variant == 1 && !(any_bc && P.ppm_type == 2 && !xform)) || (g_variant == 2 && !any_bc) || g_variant == 3);
+  if (a.kchunk < 0 && !to_fused2) a.kchunk = nz < 32 ? nz : 32;
   if (exact)
     fused_edge_launch_exact(a, P.ppm_type, any_bc, nx, ny, nz);
   else if ((g_variant == 1 && !(any_bc && P.ppm_type == 2 && !xform)) || (g_variant == 2 && !any_bc) || g_variant == 3)

@@ -34,6 +34,9 @@
 #include "mgpu_fused.cuh"
 #include "mgpu_recon.cuh"
 
+#include <cmath>
+#include <type_traits>
+
 #ifndef MGPU_FUSED2_MINB
 #define MGPU_FUSED2_MINB 2
 #endif
@@ -201,7 +204,7 @@ __device__ __forceinline__ LineBC no_wall2() {
 // BC: the box has physical boundaries: wall stencils of the reconstruction and the boundary-face rules of
 // make_edge_scal.f90:900-1000 (stage 0), :1100-1400 (transverse stages) and :1450-1560 (final) in upwind-first form.
 template <int PPM, int BX, int BY, int XF, bool WADD, bool BC>
-__global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_fused_edge2(FusedArgs a) {
+__global__ void __launch_bounds__(BX* BY, (BX * BY >= 512 ? 1 : MGPU_FUSED2_MINB)) k_fused_edge2(FusedArgs a) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = Smem2<H, BX, BY>;
   constexpr int SP = SM::SP, P = SM::P;
@@ -338,10 +341,17 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     for (int m = 0; m < SM::NH; ++m) h_off[m] += clampk(t0 + 1, s_k0, s_k1) * s_sz;
   }
   // loads in flight across one step
-  double ld_s;
+  // XF == 2: the plane constant is loaded beside the element and subtracted where the element is consumed (one
+  // step later / at the publish), so that the subtraction does not wait on the global load inside the step
+  double ld_s, ld_sub = 0.0;
   {
     const int pk = clampk(t0 + H, s_k0, s_k1);
-    ld_s = xs(gs[o_s + pk * s_sz], o_s + pk * s_sz, pk);
+    if constexpr (XF == 2) {
+      ld_s = gs[o_s + pk * s_sz];
+      ld_sub = gsub[pk];
+    } else {
+      ld_s = xs(gs[o_s + pk * s_sz], o_s + pk * s_sz, pk);
+    }
   }
   int pk_s = clampk(t0 + 1 + H, s_k0, s_k1), pk_h = clampk(t0 + 1, s_k0, s_k1);  // fab planes q_s / h_off address
   int pk_w = clampk(t0 + 2, w_k0, w_k1);
@@ -392,7 +402,7 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     // ---- rotate in the loads issued one step ago, issue the next ones ----------------------------------------
 #pragma unroll
     for (int m = 0; m < 2 * H; ++m) sw[m] = sw[m + 1];
-    sw[2 * H] = ld_s;
+    sw[2 * H] = (XF == 2) ? ld_s - ld_sub : ld_s;
     const double u0 = ld_u, v0 = ld_v;  // face velocities of plane t
     RNG(r0, R_US, 0, 0) = ld_u1 + ld_u;  // own slot: read back by this thread only, at ages 1 and 2
     RNG(r0, R_VS, 0, 0) = ld_v1 + ld_v;
@@ -404,11 +414,19 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     ld_v1 = gv[q_v + v_row];
     ld_w1 = gw[q_w];
     if constexpr (WADD) ld_w1 += gwadd[pk_w];
-    ld_s = xs(gs[q_s], q_s, pk_s);
+    double h_sub = 0.0;
+    if constexpr (XF == 2) {
+      ld_s = gs[q_s];
+      ld_sub = gsub[pk_s];
+      h_sub = gsub[pk_h];
+    } else {
+      ld_s = xs(gs[q_s], q_s, pk_s);
+    }
     const double f2 = a.force_zero ? 0.0 : gf[q_f];  // consumed at the end of this cell phase
 #pragma unroll
     for (int m = 0; m < SM::NH; ++m) {
-      hS[m] = (h_idx[m] >= 0) ? xs(gs[h_off[m]], h_off[m], pk_h) : 0.0;
+      if constexpr (XF == 2) hS[m] = (h_idx[m] >= 0) ? gs[h_off[m]] : 0.0;
+      else hS[m] = (h_idx[m] >= 0) ? xs(gs[h_off[m]], h_off[m], pk_h) : 0.0;
       adv_hi(h_off[m], t + 1, s_k1, s_sz);
     }
     adv_hi(q_u, t + 1, u_k1, u_sz);
@@ -455,6 +473,16 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     }
     // Z(t): simhz on z-face t (between cells t-1 and t)
     bool upz0 = w0c > 0.0, slz0 = !(fabs(w0c) > rel_eps);
+    bool upz1 = w1 > 0.0, slz1 = !(fabs(w1) > rel_eps);
+    bool upz2 = w2 > 0.0, slz2 = !(fabs(w2) > rel_eps);
+    // faces with |u| <= rel_eps are rare (or fill whole planes): their averaging code sits behind warp-uniform
+    // branches, one vote per phase
+    const bool anyz = __any_sync(0xffffffffu, slz0 || slz1 || slz2);
+    double shz0, zx1, zy1, gz2;  // results of the rest of the cell phase that age into the next steps
+    // the rest of the cell phase, compiled twice: SLOW carries the averaging code of |u| <= rel_eps faces and runs
+    // only in warps (and steps) that have such a face
+    auto cell_rest = [&](auto slow_tag) {
+    constexpr bool SLOW = decltype(slow_tag)::value;
     FaceRule fz0, fz1, fz2;  // rules of z-faces t, t-1, t-2 (uniform over the CTA)
     fz0.kind = fz1.kind = fz2.kind = FB_NONE;
     fz0.clamp = fz1.clamp = fz2.clamp = 0;
@@ -464,7 +492,6 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       fz1 = face_rule(t - 1, a.lo[2], a.hi[2], a.bclo[2], a.bchi[2], a.velnorm[2]);
       fz2 = face_rule(t - 2, a.lo[2], a.hi[2], a.bclo[2], a.bchi[2], a.velnorm[2]);
     }
-    double shz0;
     if (BC && fz0.kind != FB_NONE) {
       if (fz0.kind == FB_GHOST) {
         shz0 = s0;  // QUIRK make_edge_scal.f90:1010-1011: the z-lo EXT_DIR state of this stage is s(lo), not s(lo-1)
@@ -477,7 +504,9 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       }
     } else {
       shz0 = trace1<PPM>(upz0 ? pz0_1 : pz0_0, upz0 ? pz1_1 : pz1_0, upz0 ? s1 : s0, w0c * tdz, upz0);
-      if (slz0) shz0 = trace_slow<PPM>(pz0_1, s1, pz0_0, s0, w0c * tdz);
+      if constexpr (SLOW) {
+        if (slz0) shz0 = trace_slow<PPM>(pz0_1, s1, pz0_0, s0, w0c * tdz);
+      }
     }
     // C2(t-1): cell-centred transverse terms of plane t-1
     const double ws1 = w0c + w1;
@@ -489,18 +518,19 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     pl[SM::TX * SM::PL + tq0] = tx1;
     pl[SM::TY * SM::PL + tq0] = ty1;
     PLN(TZ, 0, 0) = tz1;
-    bool upz1 = w1 > 0.0, slz1 = !(fabs(w1) > rel_eps);
     if (BC && fz1.kind != FB_NONE) {
       upz1 = fz1.kind == FB_LEFT;
       slz1 = false;
     }
     double txs = upz1 ? tx2 : tx1, tys = upz1 ? ty2 : ty1;
-    if (slz1) {
-      txs = 0.5 * (tx2 + tx1);
-      tys = 0.5 * (ty2 + ty1);
+    if constexpr (SLOW) {
+      if (slz1) {
+        txs = 0.5 * (tx2 + tx1);
+        tys = 0.5 * (ty2 + ty1);
+      }
     }
-    double zx1 = fma(-c6x, txs, shz1);  // simhzx on z-face t-1
-    double zy1 = fma(-c6y, tys, shz1);  // simhzy
+    zx1 = fma(-c6x, txs, shz1);  // simhzx on z-face t-1
+    zy1 = fma(-c6y, tys, shz1);  // simhzy
     if (BC && fz1.kind != FB_NONE) {
       if (fz1.kind == FB_GHOST) zx1 = zy1 = fz1.low ? sw[H - 2] : s1;  // s(lo-1) / s(hi+1) of this stage
       else if (fz1.kind == FB_ZERO) zx1 = zy1 = 0.0;
@@ -516,18 +546,19 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
     const double us2 = RNG(r2, R_US, 0, 0), vs2 = RNG(r2, R_VS, 0, 0);
     const double gx2 = fma(c4y * vs2, PLN(YZ, 1, 0) - PLN(YZ, 0, 0), dzy) - hf;
     const double gy2 = fma(c4x * us2, PLN(XZ, 0, 1) - PLN(XZ, 0, 0), dzx) - hf;
-    const double gz2 =
+    gz2 =
         fma(c4x * us2, PLN(XY, 0, 1) - PLN(XY, 0, 0), c4y * vs2 * (PLN(YX, 1, 0) - PLN(YX, 0, 0))) - hf;
     PLN(GX, 0, 0) = gx2;
     PLN(GY, 0, 0) = gy2;
     {
-      bool upz2 = w2 > 0.0, slz2 = !(fabs(w2) > rel_eps);
       if (BC && fz2.kind != FB_NONE) {
         upz2 = fz2.kind == FB_LEFT;
         slz2 = false;
       }
       double g = upz2 ? gz3 : gz2;
-      if (slz2) g = 0.5 * (gz3 + gz2);
+      if constexpr (SLOW) {
+        if (slz2) g = 0.5 * (gz3 + gz2);
+      }
       double e = shz2 - g;
       if (BC && fz2.kind != FB_NONE) {
         if (fz2.kind == FB_GHOST) e = fz2.low ? s_m3 : sw[H - 2];  // s(lo-1) / s(hi+1)
@@ -537,13 +568,34 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       const int f = t - 2;  // z-face index
       if (st_z && f >= kz0 && (f <= kz1 || (top && f == kz1 + 1))) gez[q_ez] = e;
     }
+    };
+    if (anyz) cell_rest(std::true_type{});
+    else cell_rest(std::false_type{});
 
     __syncthreads();  // B: parabolas(t), T(t-1), G(t-2) are visible
     // ==== face phase ============================================================================================
     // F1(t): simhx, simhy
     double shx0, shy0;
+    bool anyf;
     {
-      bool up = u0 > 0.0, slow = !(fabs(u0) > rel_eps);
+      bool upx = u0 > 0.0, slowx = !(fabs(u0) > rel_eps);
+      bool upy = v0 > 0.0, slowy = !(fabs(v0) > rel_eps);
+      if (BC && frx.kind != FB_NONE) {
+        upx = frx.kind == FB_LEFT;
+        slowx = false;
+      }
+      if (BC && fry.kind != FB_NONE) {
+        upy = fry.kind == FB_LEFT;
+        slowy = false;
+      }
+      selx = (selx << 2) | (upx ? 1u : 0u) | (slowx ? 2u : 0u);
+      sely = (sely << 2) | (upy ? 1u : 0u) | (slowy ? 2u : 0u);
+      anyf = __any_sync(0xffffffffu, ((selx | sely) & 0x2au) != 0u);
+    }
+    auto face_rest = [&](auto slow_tag) {
+    constexpr bool SLOW = decltype(slow_tag)::value;
+    {
+      bool up = (selx & 1u) != 0u, slow = (selx & 2u) != 0u;
       if (BC && frx.kind != FB_NONE) {
         up = frx.kind == FB_LEFT;
         slow = false;
@@ -556,13 +608,14 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       } else {
         const int off = up ? -1 : 0;
         shx0 = trace1<PPM>((pl + off)[SM::AX0 * SM::PL], (pl + off)[SM::AX1 * SM::PL], S[off], u0 * tdx, up);
-        if (slow) shx0 = trace_slow<PPM>(PLN(AX0, 0, -1), S[-1], PLN(AX0, 0, 0), S[0], u0 * tdx);
+        if constexpr (SLOW) {
+          if (slow) shx0 = trace_slow<PPM>(PLN(AX0, 0, -1), S[-1], PLN(AX0, 0, 0), S[0], u0 * tdx);
+        }
       }
-      selx = (selx << 2) | (up ? 1u : 0u) | (slow ? 2u : 0u);
       RNG(r0, R_SHX, 0, 0) = shx0;
     }
     {
-      bool up = v0 > 0.0, slow = !(fabs(v0) > rel_eps);
+      bool up = (sely & 1u) != 0u, slow = (sely & 2u) != 0u;
       if (BC && fry.kind != FB_NONE) {
         up = fry.kind == FB_LEFT;
         slow = false;
@@ -575,9 +628,10 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       } else {
         const int off = up ? -P : 0;
         shy0 = trace1<PPM>((pl + off)[SM::AY0 * SM::PL], (pl + off)[SM::AY1 * SM::PL], S[up ? -SP : 0], v0 * tdy, up);
-        if (slow) shy0 = trace_slow<PPM>(PLN(AY0, -1, 0), S[-SP], PLN(AY0, 0, 0), S[0], v0 * tdy);
+        if constexpr (SLOW) {
+          if (slow) shy0 = trace_slow<PPM>(PLN(AY0, -1, 0), S[-SP], PLN(AY0, 0, 0), S[0], v0 * tdy);
+        }
       }
-      sely = (sely << 2) | (up ? 1u : 0u) | (slow ? 2u : 0u);
       RNG(r0, R_SHY, 0, 0) = shy0;
     }
     // F2(t-1): transverse face states of plane t-1
@@ -585,9 +639,11 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       const int off = (selx & 4u) ? -1 : 0;
       const int tq = (t & 1) ? SM::PL : 0;
       double tys = (pl + off)[SM::TY * SM::PL + tq], tzs = (pl + off)[SM::TZ * SM::PL];
-      if (selx & 8u) {
-        tys = 0.5 * (pl[SM::TY * SM::PL + tq - 1] + pl[SM::TY * SM::PL + tq]);
-        tzs = 0.5 * (PLN(TZ, 0, -1) + PLN(TZ, 0, 0));
+      if constexpr (SLOW) {
+        if (selx & 8u) {
+          tys = 0.5 * (pl[SM::TY * SM::PL + tq - 1] + pl[SM::TY * SM::PL + tq]);
+          tzs = 0.5 * (PLN(TZ, 0, -1) + PLN(TZ, 0, 0));
+        }
       }
       const double shx1 = RNG(r1, R_SHX, 0, 0);
       double xy = fma(-c6y, tys, shx1), xz = fma(-c6z, tzs, shx1);
@@ -605,9 +661,11 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       const int off = (sely & 4u) ? -P : 0;
       const int tq = (t & 1) ? SM::PL : 0;
       double txs2 = (pl + off)[SM::TX * SM::PL + tq], tzs = (pl + off)[SM::TZ * SM::PL];
-      if (sely & 8u) {
-        txs2 = 0.5 * (pl[SM::TX * SM::PL + tq - P] + pl[SM::TX * SM::PL + tq]);
-        tzs = 0.5 * (PLN(TZ, -1, 0) + PLN(TZ, 0, 0));
+      if constexpr (SLOW) {
+        if (sely & 8u) {
+          txs2 = 0.5 * (pl[SM::TX * SM::PL + tq - P] + pl[SM::TX * SM::PL + tq]);
+          tzs = 0.5 * (PLN(TZ, -1, 0) + PLN(TZ, 0, 0));
+        }
       }
       const double shy1 = RNG(r1, R_SHY, 0, 0);
       double yx = fma(-c6x, txs2, shy1), yz = fma(-c6z, tzs, shy1);
@@ -627,26 +685,33 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
       const bool kin = (k >= kz0) && (k <= kz1);
       if (kin && st_x) {
         double g = (pl + ((selx & 16u) ? -1 : 0))[SM::GX * SM::PL];
-        if (selx & 32u) g = 0.5 * (PLN(GX, 0, -1) + PLN(GX, 0, 0));
+        if constexpr (SLOW) {
+          if (selx & 32u) g = 0.5 * (PLN(GX, 0, -1) + PLN(GX, 0, 0));
+        }
         double e = RNG(r2, R_SHX, 0, 0) - g;
         if (BC && frx.kind != FB_NONE) e = (frx.kind >= FB_GHOST) ? RNG(r2, R_SHX, 0, 0) : clamp_rule(e, frx.clamp);
         gex[q_ex] = e;
       }
       if (kin && st_y) {
         double g = (pl + ((sely & 16u) ? -P : 0))[SM::GY * SM::PL];
-        if (sely & 32u) g = 0.5 * (PLN(GY, -1, 0) + PLN(GY, 0, 0));
+        if constexpr (SLOW) {
+          if (sely & 32u) g = 0.5 * (PLN(GY, -1, 0) + PLN(GY, 0, 0));
+        }
         double e = RNG(r2, R_SHY, 0, 0) - g;
         if (BC && fry.kind != FB_NONE) e = (fry.kind >= FB_GHOST) ? RNG(r2, R_SHY, 0, 0) : clamp_rule(e, fry.clamp);
         gey[q_ey] = e;
       }
     }
+    };
+    if (anyf) face_rest(std::true_type{});
+    else face_rest(std::false_type{});
     // publish the s tile of plane t+1
     {
       double* Sn = sS + ((t + 1) & 1) * SM::SN;
       Sn[sc_idx] = sw[H + 1];
 #pragma unroll
       for (int m = 0; m < SM::NH; ++m)
-        if (h_idx[m] >= 0) Sn[h_idx[m]] = hS[m];
+        if (h_idx[m] >= 0) Sn[h_idx[m]] = (XF == 2) ? hS[m] - h_sub : hS[m];
     }
     q_ex += ex_sz; q_ey += ey_sz; q_ez += ez_sz;
     // ---- age the carried state -----------------------------------------------------------------------------------
@@ -660,26 +725,54 @@ __global__ void __launch_bounds__(BX* BY, (BY >= 16 ? 1 : MGPU_FUSED2_MINB)) k_f
   }
 }
 
+// z planes per CTA.  Every chunk repeats 4 pipeline steps (warm-up / drain), and the CTAs of a launch run in waves
+// over the resident slots (SMs x CTAs per SM): pick the chunk count whose last wave is fullest for the least
+// repeated work.  256^3, 32x8 tiles, 296 slots: 3 chunks of 86 planes = 1161 CTAs = 3.92 waves (was 8 chunks of 32:
+// 10.46 waves and 12 % repeated planes).
+int fused2_auto_kchunk(int ncols, int nz, int slots) {
+  double best = 0.0;
+  int bk = nz;
+  for (int kz = 1; kz <= (nz + 7) / 8; ++kz) {
+    const int c = (nz + kz - 1) / kz;
+    const int nkz = (nz + c - 1) / c;
+    const double waves = double(ncols) * nkz / slots;
+    const double eff = waves / std::ceil(waves) * nz / (double(nkz) * (c + 4));
+    if (eff > best * 1.0001) {
+      best = eff;
+      bk = c;
+    }
+  }
+  return bk;
+}
+
 template <int PPM, int BX, int BY, int XF, bool WADD, bool BC>
-void launch_fused2(const FusedArgs& a, int nx, int ny, int nz) {
+void launch_fused2(const FusedArgs& a0, int nx, int ny, int nz) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = Smem2<H, BX, BY>;
   Context& c = ctx();
   static bool configured = false;
+  static int slots = 0;
   auto kern = k_fused_edge2<PPM, BX, BY, XF, WADD, BC>;
   constexpr int bytes = SM::TOTAL * (int)sizeof(double);
   if (!configured) {
     MGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    int dev = 0, sms = 0, per_sm = 0;
+    MGPU_CUDA(cudaGetDevice(&dev));
+    MGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BX * BY, bytes));
+    slots = sms * (per_sm > 0 ? per_sm : 1);
     configured = true;
   }
+  FusedArgs a = a0;
+  const int gx = (nx + BX - 3) / (BX - 2), gy = (ny + BY - 3) / (BY - 2);
+  if (a.kchunk <= 0) a.kchunk = fused2_auto_kchunk(gx * gy, nz, slots);
   dim3 block(BX, BY, 1);
-  dim3 grid((nx + BX - 3) / (BX - 2), (ny + BY - 3) / (BY - 2), (nz + a.kchunk - 1) / a.kchunk);
+  dim3 grid(gx, gy, (nz + a.kchunk - 1) / a.kchunk);
   MGPU_TIMED(TAG_FUSED_EDGE, (kern<<<grid, block, bytes, c.stream>>>(a)));
 }
 
-template <int PPM, int BY>
+template <int PPM, int BY, int BX = MGPU_FUSED_BX>
 void launch_fused2_xf(const FusedArgs& a, int nx, int ny, int nz, bool bc) {
-  constexpr int BX = MGPU_FUSED_BX;
   const int xf = a.sdiv ? 1 : (a.ssub ? 2 : 0);
   if (bc) {  // boxes with physical boundaries: plain inputs, 32x8 tile
     if (xf != 0 || a.wadd) throw Error("make_edge_scal: on-the-fly transforms are not built for boxes with physical boundaries");
@@ -688,7 +781,7 @@ void launch_fused2_xf(const FusedArgs& a, int nx, int ny, int nz, bool bc) {
     return;
   }
   if (a.sdiv && a.ssub) throw Error("make_edge_scal: only one on-the-fly transform of s at a time");
-  if constexpr (BY == 8) {
+  if constexpr (BY == 8 || (BX == 16 && BY == 16)) {
     if (a.wadd) {
       if (xf == 0) launch_fused2<PPM, BX, BY, 0, true, false>(a, nx, ny, nz);
       else if (xf == 1) launch_fused2<PPM, BX, BY, 1, true, false>(a, nx, ny, nz);
@@ -696,22 +789,22 @@ void launch_fused2_xf(const FusedArgs& a, int nx, int ny, int nz, bool bc) {
       return;
     }
   }
-  if (xf != 0 || a.wadd) throw Error("make_edge_scal: on-the-fly transforms are built for the 32x8 tile with wadd only");
+  if (xf != 0 || a.wadd) throw Error("make_edge_scal: on-the-fly transforms are built for the 32x8 and 16x16 tiles with wadd only");
   launch_fused2<PPM, BX, BY, 0, false, false>(a, nx, ny, nz);
 }
 
 }  // namespace
 
 // all six faces INTERIOR, FAST arithmetic.  a.kchunk: z planes per CTA.
-template <int BY>
+template <int BY, int BX = MGPU_FUSED_BX>
 static void fused_edge2_launch_by(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc) {
   // 32-bit in-plane offsets
   for (const DV* v : {&a.s, &a.force, &a.umac[0], &a.umac[1], &a.umac[2], &a.sedge[0], &a.sedge[1], &a.sedge[2]})
     if (v->cs >= (1L << 31)) throw Error("make_edge_scal: fab too large for the fused kernel's 32-bit offsets");
   switch (ppm_type) {
-    case 0: launch_fused2_xf<0, BY>(a, nx, ny, nz, bc); break;
-    case 1: launch_fused2_xf<1, BY>(a, nx, ny, nz, bc); break;
-    case 2: launch_fused2_xf<2, BY>(a, nx, ny, nz, bc); break;
+    case 0: launch_fused2_xf<0, BY, BX>(a, nx, ny, nz, bc); break;
+    case 1: launch_fused2_xf<1, BY, BX>(a, nx, ny, nz, bc); break;
+    case 2: launch_fused2_xf<2, BY, BX>(a, nx, ny, nz, bc); break;
     default: throw Error("make_edge_scal: invalid ppm_type");
   }
 }
@@ -720,7 +813,8 @@ static int g_by = MGPU_FUSED2_BY;
 void fused_edge2_set_by(int by) { g_by = by; }
 void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc) {
   const bool plain = !a.wadd && !a.sdiv && !a.ssub && !bc;
-  if (g_by == 16 && plain) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz, false);
+  if (g_by == 1616 && !bc) fused_edge2_launch_by<16, 16>(a, ppm_type, nx, ny, nz, false);
+  else if (g_by == 16 && plain) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz, false);
   else if (g_by == 10 && plain) fused_edge2_launch_by<10>(a, ppm_type, nx, ny, nz, false);
   else if (g_by == 12 && plain) fused_edge2_launch_by<12>(a, ppm_type, nx, ny, nz, false);
   else fused_edge2_launch_by<8>(a, ppm_type, nx, ny, nz, bc);

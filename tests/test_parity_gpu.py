@@ -9,6 +9,7 @@ from synth import make_state, relerr, same
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
+FUSED_BY_DEFAULT = 1616  # rows per CTA of the upwind-first kernel the library starts with (1616: the 16x16 tile)
 
 WALLS_3D = [[abi.PERIODIC, abi.PERIODIC], [abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]
 INOUT_3D = [[abi.INLET, abi.OUTLET], [abi.NO_SLIP_WALL, abi.SLIP_WALL], [abi.SYMMETRY, abi.SYMMETRY]]
@@ -38,7 +39,7 @@ def exact_arithmetic(gpu_ops):
     yield
     lib.set_option("exact", 0)
     lib.set_option("fused", 1)
-    lib.set_option("kchunk", 32)
+    lib.set_option("kchunk", -1)
 
 
 def check(g, c, bitwise=True):
@@ -62,8 +63,8 @@ def fused(request):
 
 @pytest.mark.parametrize("ppm_type", [0, 1, 2])
 @pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
-@pytest.mark.parametrize("shape,kchunk", [((37, 9, 11), 4), ((8, 33, 5), 64), ((64, 16, 7), 3)])
-@pytest.mark.parametrize("exact", [1, 0], ids=["exact", "fast"])
+@pytest.mark.parametrize("shape,kchunk", [((37, 9, 11), 4), ((8, 33, 5), 64), ((64, 16, 7), 3), ((33, 47, 40), -1)])
+@pytest.mark.parametrize("exact", [1, 0, -1], ids=["exact", "fast", "fast-16x16"])
 def test_fused_edge_ragged_boxes(gpu_ops, oracle, ppm_type, bcset, shape, kchunk, exact):
     """Fused kernel on boxes that are not multiples of the CTA tile, several CTAs in x/y and several
     z-chunks per column: tile seams, the last face hi+1 and chunk seams must be written exactly once
@@ -71,7 +72,8 @@ def test_fused_edge_ragged_boxes(gpu_ops, oracle, ppm_type, bcset, shape, kchunk
     from maestro_b200 import lib
 
     lib.set_option("fused", 1)
-    lib.set_option("exact", exact)
+    lib.set_option("exact", max(exact, 0))
+    lib.set_option("fused_by", 1616 if exact < 0 else 8)
     lib.set_option("kchunk", kchunk)
     phys = {"periodic": None, "walls": WALLS_3D, "inout": INOUT_3D}[bcset]
     st = make_state(3, shape, phys_bc=phys, ppm_type=ppm_type)
@@ -80,16 +82,17 @@ def test_fused_edge_ragged_boxes(gpu_ops, oracle, ppm_type, bcset, shape, kchunk
         g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
         gv, cv = edge_pair(gpu_ops, oracle, st, (1, 3), is_vel=True, bccomp0=1)
     finally:
-        lib.set_option("kchunk", 32)
+        lib.set_option("kchunk", -1)
+        lib.set_option("fused_by", FUSED_BY_DEFAULT)
     for d in range(3):
         for c_ in range(3):
-            check(g[d].a[c_], c[d].a[c_], bitwise=bool(exact))
-            check(gv[d].a[c_], cv[d].a[c_], bitwise=bool(exact))
+            check(g[d].a[c_], c[d].a[c_], bitwise=exact == 1)
+            check(gv[d].a[c_], cv[d].a[c_], bitwise=exact == 1)
 
 
 @pytest.mark.parametrize("ppm_type", [0, 1, 2])
-@pytest.mark.parametrize("variant", [0, 1], ids=["literal", "upwind-first"])
-@pytest.mark.parametrize("shape,kchunk", [((37, 9, 11), 4), ((30, 6, 40), 16), ((70, 20, 9), 64)])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["literal", "upwind-first", "upwind-first-16x16"])
+@pytest.mark.parametrize("shape,kchunk", [((37, 9, 11), 4), ((30, 6, 40), 16), ((70, 20, 9), 64), ((45, 33, 70), -1)])
 @pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
 def test_fused_edge_slow_faces(gpu_ops, oracle, ppm_type, variant, shape, kchunk, bcset):
     """FAST fused kernels on periodic boxes where a large share of the faces has |u| <= rel_eps (the
@@ -106,13 +109,15 @@ def test_fused_edge_slow_faces(gpu_ops, oracle, ppm_type, variant, shape, kchunk
     st["p"].rel_eps = 0.3 * umax
     lib.set_option("exact", 0)
     lib.set_option("fused_variant", 3 if variant else 0)  # 3: upwind-first kernel for every box and ppm_type
-    lib.set_option("kchunk", kchunk)
+    lib.set_option("fused_by", 1616 if variant == 2 else 8)  # 16x16 tile (boxes without physical boundaries)
+    lib.set_option("kchunk", kchunk)  # -1: chosen per launch from the resident CTA slots
     try:
         g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
         gv, cv = edge_pair(gpu_ops, oracle, st, (1, 3), is_vel=True, bccomp0=1)
     finally:
-        lib.set_option("kchunk", 32)
+        lib.set_option("kchunk", -1)
         lib.set_option("fused_variant", 1)
+        lib.set_option("fused_by", FUSED_BY_DEFAULT)
     for d in range(3):
         for c_ in range(3):
             check(g[d].a[c_], c[d].a[c_], bitwise=False)
