@@ -181,6 +181,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (mgpu_set_option), e.g. fused_by=1616")
     args = ap.parse_args()
+    if os.environ.get("BENCH_WATCHDOG"):  # debugging aid: dump every thread's Python stack if the run stalls
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -250,10 +254,18 @@ def main():
     for _ in range(W):
         reset_inputs()
         run_episode(ops, st, e)
+    # keep the GPU under the same load for about a second, until the sampler is running.  Every rank must run the
+    # SAME number of episodes (each one exchanges halos with its neighbours): the count is agreed on first
+    torch.cuda.synchronize()
     t_spin = time.time()
-    while time.time() - t_spin < 1.0:  # keep the GPU under the same load until the sampler is running
+    run_episode(ops, st, e)
+    torch.cuda.synchronize()
+    n_spin = torch.tensor([max(1, int(1.0 / max(time.time() - t_spin, 1e-4)))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_spin, op=dist.ReduceOp.MAX)
+    for _ in range(min(int(n_spin.item()), 2000)):
         run_episode(ops, st, e)
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
     sampler.lines.clear()
     barrier()
     lib.launch_count(reset=True)

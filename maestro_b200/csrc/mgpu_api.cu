@@ -23,6 +23,7 @@ static Context g_ctx;
 static std::string g_err;
 static int g_opt_fused = 1;    // use the fused 3-D edge kernel when it covers the case
 static int g_opt_kchunk = -1;  // z planes per CTA of the fused kernels; < 0: chosen per launch (fused2_auto_kchunk)
+static int g_opt_overlap = 1;   // slab runs: exchange the updated boundary planes while the interior is updated
 static int g_opt_leanplus = 1;  // density_advance: on-the-fly input transforms where the upwind-first kernel applies
 static int g_opt_exact = 0;    // 1: bit-identical arithmetic everywhere (fused kernel built with -fmad=false)
 Context& ctx() { return g_ctx; }
@@ -315,17 +316,19 @@ static void density_advance_leanplus(const mgpu_params& P, int which_step, DV& s
   const double* wadd_d = upload_small(wadd.data(), wadd.size());
   int nodal_d[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
 
-  // force of the density component (modify_scal_force, :119-128) from the raw inputs
-  set_dev(scal_force.p + scal_force.cs * (P.rho_comp - 1), 0.0, scal_force.cs);
-  modify_scal_force_dev(P, scal_force, sold, umac, rho0_old, rho0_edge_old, w0, P.rho_comp,
-                        spt == MGPU_PREDICT_RHO_AND_X, lo, hi, true, true);
-  {  // one batch: ghost cells of that force, of umac and of the raw rho / rhoX inputs
+  {  // one batch: ghost cells of umac, of the raw rho / rhoX inputs and of the density force.  The inputs travel
+     // (communication stream) while the force is built from the valid cells (modify_scal_force, :119-128)
     FillBatch fb;
-    fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
     for (int d = 0; d < dm; ++d) fill_boundary_dev(P, umac[d], lo, hi, 1, nodal_d[d], 1, 1, 1, adv_bc, pmask, false);
     fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
     fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
-    fb.run();
+    if (g_opt_overlap) fb.start_exchange();
+    set_dev(scal_force.p + scal_force.cs * (P.rho_comp - 1), 0.0, scal_force.cs);
+    modify_scal_force_dev(P, scal_force, sold, umac, rho0_old, rho0_edge_old, w0, P.rho_comp,
+                          spt == MGPU_PREDICT_RHO_AND_X, lo, hi, true, true);
+    fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
+    fb.start_exchange();
+    fb.finish();
   }
   // 1/rho once (whole fab, ghost cells included) so that the edge kernels form X = rhoX * (1/rho) with a multiply
   double* rinv = arena_alloc((size_t)sold.cs);
@@ -362,12 +365,28 @@ static void density_advance_leanplus(const mgpu_params& P, int which_step, DV& s
   ua.force = scal_force;
   for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
   // scal_force is zero by construction here and the periodic / slab fills below rewrite every ghost cell of snew
+  auto fill_snew = [&]() {
+    fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
+    fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
+    if (P.ntrac >= 1)
+      fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.trac_comp, dm + P.trac_comp, P.ntrac, adv_bc, pmask, false);
+  };
+  const int nz = hi[r] - lo[r] + 1;
+  if (comm_size() > 1 && g_opt_overlap && nz >= 4 * ng_s && flux_update_range_supported(P, fa, ua)) {
+    // slab run: update the ng_s planes next to each slab face first, send them to the neighbours on the
+    // communication stream, and update the interior planes while they travel
+    flux_update_range_dev(P, fa, ua, true, lo[r], lo[r] + ng_s - 1);
+    flux_update_range_dev(P, fa, ua, true, hi[r] - ng_s + 1, hi[r]);
+    FillBatch fb;
+    fill_snew();
+    fb.start_exchange();
+    flux_update_range_dev(P, fa, ua, true, lo[r] + ng_s, hi[r] - ng_s);
+    fb.finish();
+    return;
+  }
   flux_update_all_dev(P, fa, ua, false, true, true);
   FillBatch fb;
-  fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
-  fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
-  if (P.ntrac >= 1)
-    fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.trac_comp, dm + P.trac_comp, P.ntrac, adv_bc, pmask, false);
+  fill_snew();
   fb.run();
 }
 
@@ -925,6 +944,7 @@ int mgpu_set_option(const char* key, int value) {
   else if (k == "kchunk") g_opt_kchunk = value;
   else if (k == "exact") g_opt_exact = value;
   else if (k == "leanplus") g_opt_leanplus = value;
+  else if (k == "overlap") g_opt_overlap = value;
   else if (k == "fused_variant") fused_edge_set_variant(value);
   else if (k == "fused_by") fused_edge2_set_by(value);
   else throw Error("mgpu_set_option: unknown key " + k);

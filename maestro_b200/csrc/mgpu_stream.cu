@@ -562,10 +562,11 @@ struct FillReq {
 };
 bool g_batching = false;
 std::vector<FillReq> g_batch;
+cudaStream_t g_fill_stream = nullptr;  // non-null: the exchanges go to this stream (fill_batch_exchange_async)
 
 bool fill_exchange(const FillReq& r) {
   return halo_exchange_dev(r.P, r.sfull, r.lo, r.hi, r.ng, r.has_nodal ? r.nodal : nullptr, r.scomp - 1, r.ncomp, r.pmask,
-                           ctx().stream);
+                           g_fill_stream ? g_fill_stream : ctx().stream);
 }
 
 // periodic wraps of a set of requests: x, then y, then z (so edges/corners come out right); one launch per
@@ -647,10 +648,48 @@ void fill_physbc(const FillReq& r) {
 }
 }  // namespace
 
+static std::vector<char> g_batch_slab;
 void fill_batch_begin() {
   if (g_batching) throw Error("mgpu: nested ghost-fill batch");
   g_batching = true;
   g_batch.clear();
+  g_batch_slab.clear();
+}
+// Overlapped form of fill_batch_end: the exchanges of the batch go to the communication stream behind everything
+// already enqueued on the compute stream (the kernels that produced the planes to send), the caller then enqueues
+// work that touches neither the sent nor the received planes, and fill_batch_finish() makes the compute stream
+// wait for the exchange before the in-box wraps / physical BCs.
+// It may be called several times while a batch is open: each call sends the requests recorded since the last one.
+void fill_batch_exchange_async() {
+  if (!g_batching) throw Error("mgpu: no ghost-fill batch open");
+  const size_t first = g_batch_slab.size();
+  g_batch_slab.resize(g_batch.size(), 0);
+  if (comm_size() > 1 && first < g_batch.size()) {
+    cudaStream_t cs = comm_stream();
+    MGPU_CUDA(cudaEventRecord(comm_event(0), ctx().stream));
+    MGPU_CUDA(cudaStreamWaitEvent(cs, comm_event(0), 0));
+    g_fill_stream = cs;
+    halo_group_begin();
+    try {
+      for (size_t q = first; q < g_batch.size(); ++q) g_batch_slab[q] = fill_exchange(g_batch[q]) ? 1 : 0;
+    } catch (...) {
+      g_fill_stream = nullptr;
+      throw;
+    }
+    halo_group_end();
+    g_fill_stream = nullptr;
+    MGPU_CUDA(cudaEventRecord(comm_event(1), cs));
+  }
+}
+void fill_batch_finish() {
+  if (!g_batching) return;
+  g_batching = false;
+  if (g_batch_slab.size() != g_batch.size()) throw Error("mgpu: ghost-fill batch finished with unsent requests");
+  if (comm_size() > 1) MGPU_CUDA(cudaStreamWaitEvent(ctx().stream, comm_event(1), 0));
+  fill_wraps(g_batch.data(), g_batch_slab.data(), g_batch.size());
+  for (size_t q = 0; q < g_batch.size(); ++q) fill_physbc(g_batch[q]);
+  g_batch.clear();
+  g_batch_slab.clear();
 }
 void fill_batch_end() {
   if (!g_batching) return;
@@ -667,6 +706,7 @@ void fill_batch_end() {
 }
 void fill_batch_abort() {
   g_batching = false;
+  g_batch_slab.clear();
   g_batch.clear();
 }
 
@@ -860,6 +900,7 @@ struct FU3 {
   int f_lo[3], f_n0, f_n01, f_cs;  // force
   int t_lo[3], t_n0, t_n01;        // etarhoflux
   int lo[3], hi[3];
+  int kb;  // first z plane of this launch (a launch may cover a sub-range of planes; `hi` stays the box's)
   int spt, do_eta, rho, spec0, nspec, trac0, ntrac;
   int force_zero;  // scal_force is identically zero (density_advance.f90:349-351): do not read it
   double dt, rdx[3], half_bcd;
@@ -868,7 +909,7 @@ struct FU3 {
 
 __global__ void __launch_bounds__(256, 3) k_flux_update3_fast(const __grid_constant__ FU3 a) {
   const int i = a.lo[0] + (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  const int j = a.lo[1] + (int)blockIdx.y, k = a.lo[2] + (int)blockIdx.z;
+  const int j = a.lo[1] + (int)blockIdx.y, k = a.kb + (int)blockIdx.z;
   if (i > a.hi[0]) return;
   int oe[3], se[3];
   double vlo[3], vhi[3], r0lo[3], r0hi[3];
@@ -988,7 +1029,10 @@ static bool same_layout(const DV& x, const DV& y) {
   return x.cs == y.cs;
 }
 // true if the specialised kernel covers this call (and then launches it)
-static bool flux_update3_fast(const mgpu_params& P, const FluxArgs& a, const UpdArgs& u, bool force_zero) {
+// k0 <= k1: only the z planes [k0, k1] of the box (the slab episodes update the planes next to the slab faces first
+// and exchange them while the interior planes are updated); dry: only answer whether the kernel covers the call
+static bool flux_update3_fast(const mgpu_params& P, const FluxArgs& a, const UpdArgs& u, bool force_zero, int k0 = 1,
+                              int k1 = 0, bool dry = false) {
   if (P.dm != 3) return false;
   const long lim = 1L << 31;
   for (int d = 0; d < 3; ++d)
@@ -1026,10 +1070,23 @@ static bool flux_update3_fast(const mgpu_params& P, const FluxArgs& a, const Upd
   f.force_zero = force_zero ? 1 : 0;
   f.w0 = a.w0; f.rho0_old = a.rho0_old; f.rho0_edge_old = a.rho0_edge_old; f.rho0_new = a.rho0_new;
   f.rho0_edge_new = a.rho0_edge_new; f.rho0_predicted_edge = a.rho0_predicted_edge;
-  const dim3 g = grid3(u.vb, 256);
+  if (dry) return true;
+  dim3 g = grid3(u.vb, 256);
   const int b = block3(u.vb, 256);
+  f.kb = f.lo[2];
+  if (k0 <= k1) {
+    f.kb = k0;
+    g.z = (unsigned)(k1 - k0 + 1);
+  }
   MGPU_TIMED(TAG_UPDATE, (k_flux_update3_fast<<<g, b, 0, ctx().stream>>>(f)));
   return true;
+}
+bool flux_update_range_supported(const mgpu_params& P, const FluxArgs& a, const UpdArgs& u) {
+  return flux_update3_fast(P, a, u, true, 1, 0, true);
+}
+void flux_update_range_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool force_zero, int k0, int k1) {
+  if (k0 > k1) return;
+  if (!flux_update3_fast(P, a, u, force_zero, k0, k1)) throw Error("update_scal: plane ranges need the lean kernel");
 }
 
 void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exact, bool force_zero, bool skip_rho_copy) {

@@ -27,6 +27,10 @@ void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop);
 // mk_rhoX_flux (species + tracers) + update_scal (species + tracers + density) of density_advance in one launch
 void flux_update_all_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool exact, bool force_zero = false,
                          bool skip_rho_copy = false);
+// the same for the z planes [k0, k1] of the box only (lean 3-D kernel; no density pre-copy: the caller refills every
+// ghost cell of snew afterwards)
+bool flux_update_range_supported(const mgpu_params& P, const FluxArgs& a, const UpdArgs& u);
+void flux_update_range_dev(const mgpu_params& P, FluxArgs& a, UpdArgs& u, bool force_zero, int k0, int k1);
 
 struct VelArgs {
   int dm;
@@ -78,11 +82,15 @@ void species_form_dev(const mgpu_params& P, const DV& s, const double* base_dev,
 void recip_dev(double* dst, const double* src, long n);
 void fill_batch_begin();
 void fill_batch_end();
+void fill_batch_exchange_async();  // exchanges on the communication stream, behind the compute stream's work so far
+void fill_batch_finish();          // compute stream waits for them; in-box wraps and physical BCs
 void fill_batch_abort();
 struct FillBatch {  // RAII: a throw inside the batch drops the recorded requests
   bool done = false;
   FillBatch() { fill_batch_begin(); }
   void run() { done = true; fill_batch_end(); }
+  void start_exchange() { fill_batch_exchange_async(); }
+  void finish() { done = true; fill_batch_finish(); }
   ~FillBatch() { if (!done) fill_batch_abort(); }
 };
 void fill_boundary_dev(const mgpu_params& P, const DV& s, const int* lo, const int* hi, int ng, const int* nodal,
