@@ -341,6 +341,25 @@ int mgpu_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, 
                           const double* p0_old, const double* p0_new, const double* psi, const double* grav_old,
                           const double* grav_nph, const int* adv_bc, const int* pmask);
 
+/* ---- consumers / producers next to the path, planar ---------------------------
+ * estdt (Source/estdt.f90:29; per box _2d :348, _3d_cart :467): the time-step limits of one level from the advective
+ * speeds (u, w0), the velocity force (the caller builds it with mgpu_mk_vel_force, estdt.f90:117-120), the divU
+ * and the dS/dt constraints.  All reductions are max / min, so the result is bit-identical to the reference's
+ * whatever the order.  The boxes of this rank are reduced like the reference's loop over fabs (:148-200), then
+ * across the ranks of the slab run (NCCL min/max, the reference's parallel_reduce :202-203), then the
+ * "protect against huge time steps" rule (:209-217).  On return *dt = min(*dt, dt_lev), *umax = max(*umax,
+ * umax_lev); the caller sets rel_eps = 1.d-8*umax (:229).  rho_min = 1.d-20 (:80) is passed explicitly. */
+int mgpu_estdt(const mgpu_params* p, int nfabs, const mgpu_fab* u, const mgpu_fab* s, const mgpu_fab* force,
+               const mgpu_fab* divU, const mgpu_fab* dSdt, const double* w0, const double* p0,
+               const double* gamma1bar, double rho_min, double cflfac, double* dt, double* umax);
+/* make_etarho_planar (Source/make_eta.f90:36; sum_etarho_2d :176, _3d :213): plane averages of etarhoflux,
+ * etarho_ec(0:nr) on edges and etarho_cc(0:nr-1) = their two-point means.  The sums of one rank's planes are
+ * combined over the ranks (NCCL sum, the reference's parallel_reduce :101); ncell = cells per plane of the whole
+ * domain (p->domlo/domhi).  Floating-point sums: the order differs from the reference's loop, parity is 1e-12
+ * relative (the reference's own MPI reduction order is not fixed either). */
+int mgpu_make_etarho_planar(const mgpu_params* p, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
+                            double* etarho_cc);
+
 #ifdef __cplusplus
 }
 #endif

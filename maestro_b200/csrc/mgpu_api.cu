@@ -7,12 +7,14 @@
 // There is no CPU fallback anywhere: without a CUDA device every entry point fails.
 #include <algorithm>
 #include <cstring>
+#include <limits>
 #include <map>
 
 #include "mgpu_bds.cuh"
 #include "mgpu_edge.cuh"
 #include "mgpu_fused.cuh"
 #include "mgpu_halo.cuh"
+#include "mgpu_reduce.cuh"
 #include "mgpu_sphr.cuh"
 #include "mgpu_stream.cuh"
 #include "mgpu_velpred.cuh"
@@ -1710,5 +1712,83 @@ int mgpu_density_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int whic
   c.finish();
   MGPU_CATCH
 }
+
+// ---- estdt and make_etarho_planar ----------------------------------------------------------
+int mgpu_estdt(const mgpu_params* p, int nfabs, const mgpu_fab* u, const mgpu_fab* s, const mgpu_fab* force,
+               const mgpu_fab* divU, const mgpu_fab* dSdt, const double* w0, const double* p0,
+               const double* gamma1bar, double rho_min, double cflfac, double* dt, double* umax) {
+  MGPU_TRY
+  if (p->spherical) throw Error("mgpu_estdt: spherical geometry not available on the device yet");
+  const int nr = p->nr, dm = p->dm;
+  Call c(p, (size_t)(4 * (nr + 2) + 148 * 8 * 8 + 64) * sizeof(double) + 8192);
+  const double* w0_d = upload_small(w0, nr + 1);
+  const double* p0_d = upload_small(p0, nr);
+  const double* g1_d = upload_small(gamma1bar, nr);
+  const double dt_start = 1.e99;  // estdt.f90:144-146
+  double dt_proc = 1.e99, umax_proc = 0.0;
+  for (int i = 0; i < nfabs; ++i) {
+    DV uv = c.view(u[i], true, false);
+    DV sv = c.view(s[i], crange(p->rho_comp - 1, 1), (cmask_t)0);
+    DV fv = c.view(force[i], true, false);
+    DV dUv = c.view(divU[i], true, false), dSv = c.view(dSdt[i], true, false);
+    double dt_grid = std::numeric_limits<double>::max(), umax_grid = 0.0;  // HUGE(dt_grid), :158-159
+    estdt_box_dev(*p, uv, sv, fv, dUv, dSv, w0_d, w0, p0_d, g1_d, u[i].lo, u[i].hi, rho_min, cflfac, &dt_grid,
+                  &umax_grid);
+    dt_proc = std::min(dt_proc, dt_grid);
+    umax_proc = std::max(umax_proc, umax_grid);
+  }
+  double dt_lev = dt_proc, umax_lev = umax_proc;
+  if (comm_size() > 1) {  // parallel_reduce MPI_MIN / MPI_MAX, :202-203: one MIN over (dt, -umax)
+    double h[2] = {dt_proc, -umax_proc};
+    double* d = arena_alloc(2);
+    MGPU_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, g_ctx.stream));
+    allreduce_dev(d, 2, 1);
+    MGPU_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, g_ctx.stream));
+    MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    dt_lev = h[0];
+    umax_lev = -h[1];
+  }
+  *umax = std::max(*umax, umax_lev);  // :206
+  if (dt_lev == dt_start) {           // protect against huge time steps, :209-217
+    dt_lev = p->dx[0];
+    for (int d = 1; d < dm; ++d) dt_lev = std::min(dt_lev, p->dx[d]);
+  }
+  *dt = std::min(*dt, dt_lev);  // :220
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_make_etarho_planar(const mgpu_params* p, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
+                            double* etarho_cc) {
+  MGPU_TRY
+  if (p->spherical) throw Error("ERROR: make_eta should not be called for spherical");  // make_eta.f90:73-75
+  const int nr = p->nr, dm = p->dm, r = dm - 1;
+  Call c(p, (size_t)(4 * (nr + 2)) * sizeof(double) + 8192);
+  std::vector<double> sum(nr + 1, 0.0);
+  for (int i = 0; i < nfabs; ++i) {
+    const mgpu_fab& f = etarhoflux[i];
+    DV ev = c.view(f, true, false);
+    // the top edge only where the box touches the top of the domain (no double counting), :230-247
+    const int k1 = f.hi[r] + (f.hi[r] == nr - 1 ? 1 : 0);
+    if (f.lo[r] < 0 || k1 > nr) throw Error("make_etarho_planar: box outside the base-state range 0:nr");
+    std::vector<double> part(k1 - f.lo[r] + 1);
+    plane_sums_dev(*p, ev.comp(0), f.lo, f.hi, f.lo[r], k1, part.data());
+    for (int k = f.lo[r]; k <= k1; ++k) sum[k] = sum[k] + part[k - f.lo[r]];
+  }
+  if (comm_size() > 1) {  // parallel_reduce MPI_SUM, :101
+    double* d = arena_alloc((size_t)nr + 1);
+    MGPU_CUDA(cudaMemcpyAsync(d, sum.data(), (nr + 1) * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
+    allreduce_dev(d, nr + 1, 0);
+    MGPU_CUDA(cudaMemcpyAsync(sum.data(), d, (nr + 1) * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+    MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  }
+  double ncell = 1.0;  // :80-86
+  for (int d = 0; d < r; ++d) ncell *= (double)(p->domhi[d] - p->domlo[d] + 1);
+  for (int k = 0; k <= nr; ++k) etarho_ec[k] = sum[k] / ncell;                            // :103-107
+  for (int k = 0; k < nr; ++k) etarho_cc[k] = 0.5 * (etarho_ec[k] + etarho_ec[k + 1]);  // :117-123
+  c.finish();
+  MGPU_CATCH
+}
+
 
 }  // extern "C"

@@ -183,4 +183,11 @@ void allreduce_minmax_dev(double* d_minmax2) {
   MGPU_NCCL(g_nccl.AllReduce(d_minmax2, d_minmax2, 2, ncclDouble, ncclMin, g_comm.comm, ctx().stream));
 }
 
+// in-place all-reduce of n doubles over the ranks of the slab run (op: 0 sum, 1 min, 2 max); no-op on one rank
+void allreduce_dev(double* d, int n, int op) {
+  if (!g_comm.on || g_comm.nranks == 1) return;
+  const ncclRedOp_t o = op == 0 ? ncclSum : (op == 1 ? ncclMin : ncclMax);
+  MGPU_NCCL(g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, o, g_comm.comm, ctx().stream));
+}
+
 }  // namespace mgpu

@@ -22,5 +22,6 @@ bool halo_exchange_dev(const mgpu_params& P, const DV& s, const int* lo, const i
 void halo_group_begin();
 void halo_group_end();
 void allreduce_minmax_dev(double* d_minmax2);
+void allreduce_dev(double* d, int n, int op);  // op: 0 sum, 1 min, 2 max
 
 }  // namespace mgpu

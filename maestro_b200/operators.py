@@ -222,6 +222,23 @@ class Operators:
                    keep[0][1], fab_ptr(gpi), fab_ptr(s), index_rho, keep[1][1], keep[2][1], keep[3][1],
                    int(do_add_utilde_force))
 
+    # ---- reductions next to the path -------------------------------------------------
+    def estdt(self, p, u, s, force, divU, dSdt, w0, p0, gamma1bar, cflfac, dt, umax=0.0, rho_min=1.0e-20):
+        """Source/estdt.f90:29 for one level: returns (min(dt, dt_lev), max(umax, umax_lev)); `force` is the
+        velocity force the caller built with mk_vel_force (:117-120); rel_eps = 1e-8 * umax is the caller's (:229)."""
+        keep = [as_double_p(x) for x in (w0, p0, gamma1bar)]
+        dt_c, um_c = C.c_double(dt), C.c_double(umax)
+        self._call("estdt", C.byref(p), 1, fab_ptr(u), fab_ptr(s), fab_ptr(force), fab_ptr(divU), fab_ptr(dSdt),
+                   keep[0][1], keep[1][1], keep[2][1], float(rho_min), float(cflfac), C.byref(dt_c), C.byref(um_c))
+        return dt_c.value, um_c.value
+
+    def make_etarho_planar(self, p, etarhoflux):
+        """Source/make_eta.f90:36: returns (etarho_ec(0:nr), etarho_cc(0:nr-1))."""
+        ec, cc = np.zeros(p.nr + 1), np.zeros(p.nr)
+        k1, k2 = as_double_p(ec), as_double_p(cc)
+        self._call("make_etarho_planar", C.byref(p), 1, fab_ptr(etarhoflux), k1[1], k2[1])
+        return k1[0].copy(), k2[0].copy()
+
     # ---- the other L4 drivers ---------------------------------------------------------------------------
     def advance_premac(self, p, uold, sold, umac, gpi, w0, w0_force, rho0_old, grav_cell_old, adv_bc, phys_bc, pmask):
         keep = [as_double_p(x) for x in (w0, w0_force, rho0_old, grav_cell_old)]

@@ -327,4 +327,19 @@ int mo_test_advect(int dm, int n, int ppm_type, int bds_type, int itest_dir, dou
   MO_CATCH
 }
 
+int mo_estdt(const mgpu_params* p, int nfabs, const mgpu_fab* u, const mgpu_fab* s, const mgpu_fab* force,
+             const mgpu_fab* divU, const mgpu_fab* dSdt, const double* w0, const double* p0, const double* gamma1bar,
+             double rho_min, double cflfac, double* dt, double* umax) {
+  MO_TRY
+  estdt_level(*p, nfabs, u, s, force, divU, dSdt, w0, p0, gamma1bar, rho_min, cflfac, *dt, *umax);
+  MO_CATCH
+}
+
+int mo_make_etarho_planar(const mgpu_params* p, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
+                          double* etarho_cc) {
+  MO_TRY
+  make_etarho_planar(*p, nfabs, etarhoflux, etarho_ec, etarho_cc);
+  MO_CATCH
+}
+
 }  // extern "C"

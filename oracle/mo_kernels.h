@@ -118,4 +118,11 @@ void fill_boundary_box(const mgpu_params& P, Arr& s, const int* lo, const int* h
 void fill_boundary_face(const mgpu_params& P, Arr& u, const int* lo, const int* hi, int ng, int dir,
                         const int* pmask);
 
+// reductions next to the path (mo_reduce.cpp): estdt.f90:142-220 for one level, make_eta.f90:36
+void estdt_level(const mgpu_params& P, int nfabs, const mgpu_fab* u, const mgpu_fab* s, const mgpu_fab* force,
+                 const mgpu_fab* divU, const mgpu_fab* dSdt, const double* w0, const double* p0,
+                 const double* gamma1bar, double rho_min, double cfl, double& dt, double& umax);
+void make_etarho_planar(const mgpu_params& P, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
+                        double* etarho_cc);
+
 }  // namespace mo

@@ -1,0 +1,126 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (see mo_array.h).
+// Restatement of the reductions next to the advective path:
+//   estdt_2d        Source/estdt.f90:348      estdt_3d_cart   Source/estdt.f90:467
+//   sum_etarho_2d   Source/make_eta.f90:176   sum_etarho_3d   Source/make_eta.f90:213
+//   make_etarho_planar Source/make_eta.f90:36 (single level, one chunk: r_end_coord = nr-1)
+// Same loops, same order, same expressions.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "mo_kernels.h"
+
+namespace mo {
+
+// dt inout, umax out (estdt.f90:364-465 / :483-616)
+void estdt_box(const mgpu_params& P, const Arr& u, const Arr& s, const Arr& force, const Arr& divU, const Arr& dSdt,
+               const double* w0, const double* p0, const double* gamma1bar, const int* lo, const int* hi,
+               double rho_min, double cfl, double& dt, double& umax) {
+  const int dm = P.dm, r = dm - 1, nr = P.nr, rho = P.rho_comp - 1;
+  const double eps = 1.0e-8;
+  const int k0 = dm == 3 ? lo[2] : 0, k1 = dm == 3 ? hi[2] : 0;
+  double spd[3] = {0.0, 0.0, 0.0}, spdr = 0.0;
+  umax = 0.0;
+  // Limit dt based on velocity terms
+  for (int d = 0; d < dm; ++d)
+    for (int k = k0; k <= k1; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+          const int kr = dm == 3 ? k : j;
+          if (d == r) spd[d] = std::max(spd[d], std::fabs(u(i, j, k, d) + 0.5 * (w0[kr] + w0[kr + 1])));
+          else spd[d] = std::max(spd[d], std::fabs(u(i, j, k, d)));
+        }
+  for (int k = lo[r]; k <= hi[r]; ++k) spdr = std::max(spdr, std::fabs(w0[k]));
+  for (int d = 0; d < dm; ++d) umax = std::max(umax, spd[d]);
+  umax = std::max(umax, spdr);
+  for (int d = 0; d < dm; ++d)
+    if (spd[d] > eps) dt = std::min(dt, P.dx[d] / spd[d]);
+  if (spdr > eps) dt = std::min(dt, P.dx[r] / spdr);
+  dt = dt * cfl;
+  // Limit dt based on forcing terms
+  double f[3] = {0.0, 0.0, 0.0};
+  for (int d = 0; d < dm; ++d)
+    for (int k = k0; k <= k1; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) f[d] = std::max(f[d], std::fabs(force(i, j, k, d)));
+  for (int d = 0; d < dm; ++d)
+    if (f[d] > eps) dt = std::min(dt, std::sqrt(2.0 * P.dx[d] / f[d]));
+  // divU constraint
+  for (int k = k0; k <= k1; ++k)
+    for (int j = lo[1]; j <= hi[1]; ++j) {
+      const int kr = dm == 3 ? k : j;
+      double gradp0;
+      if (kr == 0) gradp0 = (p0[kr + 1] - p0[kr]) / P.dx[r];
+      else if (kr == nr - 1) gradp0 = (p0[kr] - p0[kr - 1]) / P.dx[r];
+      else gradp0 = 0.5 * (p0[kr + 1] - p0[kr - 1]) / P.dx[r];
+      for (int i = lo[0]; i <= hi[0]; ++i) {
+        const double denom = divU(i, j, k) - u(i, j, k, r) * gradp0 / (gamma1bar[kr] * p0[kr]);
+        if (denom > 0.0) dt = std::min(dt, 0.4 * (1.0 - rho_min / s(i, j, k, rho)) / denom);
+      }
+    }
+  // dS/dt constraint
+  for (int k = k0; k <= k1; ++k)
+    for (int j = lo[1]; j <= hi[1]; ++j)
+      for (int i = lo[0]; i <= hi[0]; ++i)
+        if (dSdt(i, j, k) > 1.e-20) {
+          const double a = 0.5 * s(i, j, k, rho) * dSdt(i, j, k);
+          const double b = s(i, j, k, rho) * divU(i, j, k);
+          const double c = rho_min - s(i, j, k, rho);
+          dt = std::min(dt, 0.4 * 2.0 * c / (-b - std::sqrt(b * b - 4.0 * a * c)));
+        }
+}
+
+// estdt.f90:142-220 for one level on one rank
+void estdt_level(const mgpu_params& P, int nfabs, const mgpu_fab* u, const mgpu_fab* s, const mgpu_fab* force,
+                 const mgpu_fab* divU, const mgpu_fab* dSdt, const double* w0, const double* p0,
+                 const double* gamma1bar, double rho_min, double cfl, double& dt, double& umax) {
+  const double dt_start = 1.e99;
+  double dt_proc = 1.e99, umax_proc = 0.0;
+  for (int i = 0; i < nfabs; ++i) {
+    Arr ua = Arr::view(u[i], P.dm), sa = Arr::view(s[i], P.dm), fa = Arr::view(force[i], P.dm);
+    Arr dU = Arr::view(divU[i], P.dm), dS = Arr::view(dSdt[i], P.dm);
+    double dt_grid = std::numeric_limits<double>::max(), umax_grid = 0.0;
+    estdt_box(P, ua, sa, fa, dU, dS, w0, p0, gamma1bar, u[i].lo, u[i].hi, rho_min, cfl, dt_grid, umax_grid);
+    dt_proc = std::min(dt_proc, dt_grid);
+    umax_proc = std::max(umax_proc, umax_grid);
+  }
+  double dt_lev = dt_proc;
+  umax = std::max(umax, umax_proc);
+  if (dt_lev == dt_start) {
+    dt_lev = P.dx[0];
+    for (int d = 1; d < P.dm; ++d) dt_lev = std::min(dt_lev, P.dx[d]);
+  }
+  dt = std::min(dt, dt_lev);
+}
+
+// make_eta.f90:176-250: the reference's summation order (i fastest, then j, then k)
+void sum_etarho_box(const mgpu_params& P, const Arr& e, const int* lo, const int* hi, double* etarhosum) {
+  const int dm = P.dm, r = dm - 1;
+  auto plane = [&](int kk) {
+    if (dm == 3) {
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) etarhosum[kk] = etarhosum[kk] + e(i, j, kk);
+    } else {
+      for (int i = lo[0]; i <= hi[0]; ++i) etarhosum[kk] = etarhosum[kk] + e(i, kk, 0);
+    }
+  };
+  for (int kk = lo[r]; kk <= hi[r]; ++kk) plane(kk);
+  if (hi[r] == P.nr - 1) plane(hi[r] + 1);  // top edge only at the top of the domain
+}
+
+void make_etarho_planar(const mgpu_params& P, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
+                        double* etarho_cc) {
+  if (P.spherical) fail("ERROR: make_eta should not be called for spherical");
+  const int nr = P.nr, r = P.dm - 1;
+  std::vector<double> sum(nr + 1, 0.0);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr e = Arr::view(etarhoflux[i], P.dm);
+    sum_etarho_box(P, e, etarhoflux[i].lo, etarhoflux[i].hi, sum.data());
+  }
+  double ncell = 1.0;
+  for (int d = 0; d < r; ++d) ncell *= (double)(P.domhi[d] - P.domlo[d] + 1);
+  for (int k = 0; k <= nr; ++k) etarho_ec[k] = sum[k] / ncell;
+  for (int k = 0; k < nr; ++k) etarho_cc[k] = 0.5 * (etarho_ec[k] + etarho_ec[k + 1]);
+}
+
+}  // namespace mo

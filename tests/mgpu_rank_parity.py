@@ -99,7 +99,7 @@ def main():
     r = dm - 1
     if bcset == "sphr":
         return sphr_main(rank, world, local, ops, exact)
-    n = ([16, 12, 8 * world] if exact else [40, 12, 10 * world]) if dm == 3 else [24, 10 * world]
+    n = ([16, 12, 8 * world] if exact else [40, 12, 20 * world]) if dm == 3 else [24, 10 * world]  # FAST: >= 4 ng planes per slab, so the overlapped exchange of the updated boundary planes runs
     walls = [[abi.PERIODIC, abi.PERIODIC]] * (dm - 1) + [[abi.SLIP_WALL, abi.OUTLET]]
     phys = None if bcset == "periodic" else walls
     st = make_state(dm, n, phys_bc=phys, ppm_type=ppm_type)

@@ -169,3 +169,30 @@ def make_episode_extras(st, seed=97):
                 psi=0.1 * np.cos(2 * np.pi * zr), grav_old=-1.0 - 0.2 * zr, grav_nph=-1.02 - 0.2 * zr,
                 p0_old=2.0 * np.exp(-zr), p0_new=2.05 * np.exp(-zr), w0_force=0.03 * np.sin(2 * np.pi * zr),
                 rho0_nph=1.0 + 0.51 * np.exp(-zr / 0.5))
+
+
+def make_estdt_inputs(dm, n, seed=97, speed=1.0, force_amp=1.0, divu_amp=1.0, dsdt_amp=1.0):
+    """Inputs of estdt (Source/estdt.f90:29) on one periodic box: u (ng 3), s (ng 3; density > 0), the velocity
+    force (ng 1), divU, dSdt (ng 1), w0 on edges, p0 and gamma1bar on cells.  Host fabs, all random but smooth
+    enough that every constraint (velocity, force, divU, dS/dt) is active somewhere."""
+    rng = np.random.default_rng(seed)
+    nn = [n] * dm if np.isscalar(n) else list(n)
+    p = make_params(dm, n=nn + [1] * (3 - dm))
+    lo, hi = [0, 0, 0], [nn[d] - 1 if d < dm else 0 for d in range(3)]
+    u = Fab(lo, hi, 3, dm, dm=dm)
+    u.a[...] = speed * rng.uniform(-1.0, 1.0, size=u.shape)
+    s = Fab(lo, hi, 3, p.nscal, dm=dm)
+    s.a[...] = rng.uniform(0.5, 2.0, size=s.shape)
+    force = Fab(lo, hi, 1, dm, dm=dm)
+    force.a[...] = force_amp * rng.uniform(-40.0, 40.0, size=force.shape)
+    divU = Fab(lo, hi, 1, 1, dm=dm)
+    divU.a[...] = divu_amp * rng.uniform(-30.0, 30.0, size=divU.shape)
+    dSdt = Fab(lo, hi, 1, 1, dm=dm)
+    dSdt.a[...] = dsdt_amp * rng.uniform(-50.0, 50.0, size=dSdt.shape)
+    nr = p.nr
+    zc = (np.arange(nr) + 0.5) * p.dx[dm - 1]
+    w0 = 0.3 * speed * np.sin(2 * np.pi * np.arange(nr + 1) * p.dx[dm - 1])
+    p0 = 10.0 * np.exp(-zc / 0.4)
+    gamma1bar = 1.4 + 0.2 * np.cos(2 * np.pi * zc)
+    return dict(p=p, lo=lo, hi=hi, dm=dm, u=u, s=s, force=force, divU=divU, dSdt=dSdt, w0=w0, p0=p0,
+                gamma1bar=gamma1bar)

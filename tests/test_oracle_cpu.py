@@ -507,3 +507,63 @@ def test_sphr_velpred_runs_and_reduces_to_planar_riemann(oracle):
     p.spherical = 0
     for d in range(3):
         assert np.array_equal(out[0][d].a, out[1][d].a)
+
+
+# ---- reductions next to the path: analytic known answers ---------------------------------
+@pytest.mark.parametrize("dm,n", [(2, (12, 10)), (3, (8, 6, 10))])
+def test_estdt_known_answers(oracle, dm, n):
+    """estdt.f90:348 / :467 on states whose limits are known in closed form: the CFL limit of a uniform flow, the
+    force limit sqrt(2 dx / f), the divU limit 0.4 (1 - rho_min/rho) / divU, and the 'huge time step' guard."""
+    from synth import make_estdt_inputs
+
+    e = make_estdt_inputs(dm, n)
+    p = e["p"]
+    vel = [0.5, -2.0, 1.25][:dm]
+    for d in range(dm):
+        e["u"].a[d] = vel[d]
+    e["s"].a[...] = 2.0
+    for f in (e["force"], e["divU"], e["dSdt"]):
+        f.a[...] = 0.0
+    w0 = np.zeros(p.nr + 1)
+    cfl = 0.7
+    dt, umax = oracle.estdt(p, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0, e["p0"], e["gamma1bar"], cfl, 1e30)
+    assert umax == 2.0
+    assert dt == min(p.dx[d] / abs(vel[d]) for d in range(dm)) * cfl
+    # a force of 50 in x: sqrt(2 dx / 50) is below the CFL limit
+    e["force"].a[0] = -50.0
+    dt2, _ = oracle.estdt(p, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0, e["p0"], e["gamma1bar"], cfl, 1e30)
+    assert dt2 == min(dt, np.sqrt(2.0 * p.dx[0] / 50.0))
+    # divU = 40 everywhere, no radial velocity: 0.4 (1 - rho_min/rho) / 40
+    e["force"].a[...] = 0.0
+    e["u"].a[dm - 1] = 0.0
+    e["divU"].a[...] = 40.0
+    dt3, _ = oracle.estdt(p, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0, e["p0"], e["gamma1bar"], cfl, 1e30)
+    assert dt3 == 0.4 * (1.0 - 1e-20 / 2.0) / 40.0
+    # nothing moves: the level falls back to min(dx) (estdt.f90:209-217); the caller's dt wins if smaller
+    e["u"].a[...] = 0.0
+    e["divU"].a[...] = 0.0
+    dt4, um4 = oracle.estdt(p, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0, e["p0"], e["gamma1bar"], cfl, 1e30)
+    assert dt4 == min(p.dx[d] for d in range(dm)) and um4 == 0.0
+    dt5, _ = oracle.estdt(p, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0, e["p0"], e["gamma1bar"], cfl, 1e-5)
+    assert dt5 == 1e-5
+
+
+@pytest.mark.parametrize("dm,n", [(2, (12, 10)), (3, (8, 6, 10))])
+def test_make_etarho_planar_known_answer(oracle, dm, n):
+    """make_eta.f90:36: a flux that only depends on the radial face index averages to itself; etarho_cc is the
+    two-point mean; a transverse modulation with zero mean drops out."""
+    from synth import make_estdt_inputs
+
+    e = make_estdt_inputs(dm, n)
+    p = e["p"]
+    nod = [0] * 3
+    nod[dm - 1] = 1
+    eta = Fab(e["lo"], e["hi"], 0, 1, nodal=nod, dm=dm)
+    g = 1.0 + np.arange(p.nr + 1) ** 2 / 7.0
+    shape = [1, 1, 1, 1]
+    shape[3 - (dm - 1)] = p.nr + 1
+    x = np.arange(n[0])
+    eta.a[...] = g.reshape(shape) + np.cos(2 * np.pi * (x + 0.5) / n[0]).reshape(1, 1, 1, -1) * 3.0
+    ec, cc = oracle.make_etarho_planar(p, eta)
+    assert np.abs(ec - g).max() <= 1e-13 * np.abs(g).max()
+    assert np.abs(cc - 0.5 * (g[:-1] + g[1:])).max() <= 1e-13 * np.abs(g).max()

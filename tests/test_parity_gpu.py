@@ -782,3 +782,57 @@ def test_sphr_density_advance(gpu_ops, oracle, spt, which_step, s0mac_t, exact):
                    [f.a[comps[1:]] for f in sflux] + [u.a for u in umac])
     for a, b in zip(*res):
         check(a, b, bitwise=bool(exact))
+
+
+# ---- reductions next to the path ---------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("dm,n", [(2, (70, 45)), (3, (33, 20, 27)), (3, (64, 64, 48))])
+@pytest.mark.parametrize("active", ["all", "velocity", "force", "divU", "dSdt", "none"])
+@pytest.mark.parametrize("space", ["host", "device"])
+def test_estdt(gpu_ops, oracle, dm, n, active, space):
+    """estdt.f90:29: max / min reductions are exact, so dt and umax are bit-identical to the restated reference
+    whichever constraint decides (each is made the binding one in turn)."""
+    import torch
+    from synth import make_estdt_inputs
+
+    amp = dict(speed=1.0, force_amp=1.0, divu_amp=1.0, dsdt_amp=1.0)
+    if active != "all":
+        amp = dict(speed=1e-3, force_amp=1e-6, divu_amp=1e-6, dsdt_amp=1e-30)
+        key = {"velocity": "speed", "force": "force_amp", "divU": "divu_amp", "dSdt": "dsdt_amp"}.get(active)
+        if key:
+            amp[key] = 1.0
+        if active == "dSdt":
+            amp["divu_amp"] = 1e-3
+        if active == "none":
+            amp = dict(speed=0.0, force_amp=0.0, divu_amp=0.0, dsdt_amp=0.0)
+    e = make_estdt_inputs(dm, n, **amp)
+    p = e["p"]
+    w0 = e["w0"] if active != "none" else np.zeros_like(e["w0"])
+    want = oracle.estdt(p, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0, e["p0"], e["gamma1bar"], 0.7, 1e30)
+    fabs = [e[k] for k in ("u", "s", "force", "divU", "dSdt")]
+    if space == "device":
+        fabs = [f.to("cuda:0") for f in fabs]
+        p.mem_space = abi.DEVICE
+    try:
+        got = gpu_ops.estdt(p, *fabs, w0, e["p0"], e["gamma1bar"], 0.7, 1e30)
+    finally:
+        p.mem_space = abi.HOST
+    assert got == want, (got, want)
+    assert np.isfinite(got[0]) and got[0] > 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dm,n", [(2, (70, 45)), (3, (33, 20, 27)), (3, (128, 96, 40))])
+def test_make_etarho_planar(gpu_ops, oracle, dm, n):
+    """make_eta.f90:36: plane averages of etarhoflux (floating-point sums in a different order: 1e-12 relative)."""
+    from synth import make_estdt_inputs
+
+    e = make_estdt_inputs(dm, n)
+    p = e["p"]
+    nod = [0] * 3
+    nod[dm - 1] = 1
+    eta = Fab(e["lo"], e["hi"], 0, 1, nodal=nod, dm=dm)
+    eta.a[...] = np.random.default_rng(5).uniform(-1.0, 3.0, size=eta.shape)
+    ec_w, cc_w = oracle.make_etarho_planar(p, eta)
+    ec_g, cc_g = gpu_ops.make_etarho_planar(p, eta)
+    assert relerr(ec_g, ec_w) <= TOL and relerr(cc_g, cc_w) <= TOL
