@@ -256,7 +256,9 @@ static void edge_one_comp(const mgpu_params& P, const DV& s, DV* sedge, const DV
         throw Error("make_edge_scal: invalid boundary type adv_bc");
     }
   }
-  if (g_opt_fused && fused_edge_supported(P, is_cons)) {
+  if (g_opt_fused && !sdiv && !ssub && !wadd && fused_edge2d_supported(P, is_cons, adv_bc, bccomp, g_opt_exact != 0)) {
+    fused_edge2d_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, ng_s, ng_f, force_zero);
+  } else if (g_opt_fused && fused_edge_supported(P, is_cons)) {
     fused_edge_dev(P, s, sedge, umac, force, lo, hi, adv_bc, comp, bccomp, is_vel, ng_s, ng_f, g_opt_kchunk,
                    g_opt_exact != 0, force_zero, sdiv, ssub, wadd);
   } else {

@@ -29,6 +29,8 @@
 //          true  -> (mgpu_fused_fast.cu, built with -fmad=true) dt/dx is folded into one factor (no fp64
 //                   division in the loop) and FMA contraction is allowed: differs from the reference in
 //                   the last bits only (tests: <= 1e-12 relative, the north-star tolerance).
+#include <cstring>
+
 #include "mgpu_fused.cuh"
 #include "mgpu_recon.cuh"
 
@@ -487,6 +489,43 @@ bool fused_edge_is_upwind_first(const mgpu_params& P, const int* adv_bc, int bcc
     for (int side = 0; side < 2; ++side)
       if (adv_bc[d + 3 * (side + 2 * (bccomp - 1))] != MGPU_BC_INTERIOR) return false;
   return true;
+}
+
+bool fused_edge2d_supported(const mgpu_params& P, bool is_cons, const int* adv_bc, int bccomp, bool exact) {
+  if (exact || g_variant == 0 || P.dm != 2 || P.bds_type != 0 || P.ppm_trace_forces != 0 || is_cons) return false;
+  for (int d = 0; d < 2; ++d)
+    for (int side = 0; side < 2; ++side)
+      if (adv_bc[d + 2 * (side + 2 * (bccomp - 1))] == MGPU_BC_REFLECT_ODD) return false;
+  return true;
+}
+
+void fused_edge2d_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
+                      const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
+                      int ng_f, bool force_zero) {
+  if (P.ppm_type == 2 && ng_s < 4) throw Error("Need 4 ghost cells for ppm_type=2");  // ppm.f90:576-578
+  if (ng_s < 3) throw Error("make_edge_scal: need at least 3 ghost cells");
+  if (ng_f < 1) throw Error("make_edge_scal: force needs at least 1 ghost cell");
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.slope_order = P.slope_order;
+  a.force_zero = force_zero;
+  a.dt = P.dt;
+  a.rel_eps = P.rel_eps;
+  bool any_bc = false;
+  for (int d = 0; d < 2; ++d) {
+    a.lo[d] = lo[d];
+    a.hi[d] = hi[d];
+    a.dx[d] = P.dx[d];
+    a.bclo[d] = adv_bc[d + 2 * (0 + 2 * (bccomp - 1))];
+    a.bchi[d] = adv_bc[d + 2 * (1 + 2 * (bccomp - 1))];
+    if (a.bclo[d] != MGPU_BC_INTERIOR || a.bchi[d] != MGPU_BC_INTERIOR) any_bc = true;
+    a.velnorm[d] = is_vel && (comp == d);
+    a.umac[d] = umac[d];
+    a.sedge[d] = sedge_full[d].comp(comp);
+  }
+  a.s = s_full.comp(comp);
+  a.force = force_full.comp(comp);
+  fused_edge2d_launch(a, P.ppm_type, hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, any_bc);
 }
 
 void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,

@@ -48,6 +48,12 @@ void fused_edge_launch_exact(const FusedArgs& a, int ppm_type, bool bc, int nx, 
 void fused_edge_launch_fast(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
 // second design (mgpu_fused2.cu): upwind-first, FAST arithmetic only; bc: the box has physical boundaries
 void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc);
+// 2-D (mgpu_fused2.cu, k_fused_edge2d): FAST arithmetic only, non-conservative, ppm_trace_forces = 0, no REFLECT_ODD
+bool fused_edge2d_supported(const mgpu_params& P, bool is_cons, const int* adv_bc, int bccomp, bool exact);
+void fused_edge2d_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
+                      const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
+                      int ng_f, bool force_zero = false);
+void fused_edge2d_launch(const FusedArgs& a, int ppm_type, int nx, int ny, bool bc);
 // 0: always the literal kernel; 1 (default): the upwind-first kernel wherever it applies
 void fused_edge_set_variant(int v);
 void fused_edge2_set_by(int by);  // rows per CTA of the upwind-first kernel: 8 or 16

@@ -793,6 +793,145 @@ void launch_fused2_xf(const FusedArgs& a, int nx, int ny, int nz, bool bc) {
   launch_fused2<PPM, BX, BY, 0, false, false>(a, nx, ny, nz);
 }
 
+
+// ---- 2-D: the whole of make_edge_scal_2d (Source/make_edge_scal.f90:290-676) for one component in one launch --------
+// Same upwind-first form as the 3-D kernel, without the march: a CTA owns a BX x BY tile of cells with a one-cell halo
+// (the interior (BX-2) x (BY-2) cells store their low faces), four phases separated by barriers:
+//   C1  limited parabolas / slopes of every cell in x and y        (ppm_2d, slopex_2d / slopey_2d)
+//   F1  simhx, simhy: one traced state per face from its upwind cell (:380-524)
+//   C2  cell-centred corrections G_x = dt/(4 hy) (v(j+1)+v(j)) (simhy(j+1)-simhy(j)) - dt/2 f,  G_y likewise (:531-549)
+//   F3  sedgex = simhx - G_x(upwind cell) (mean of both cells when |u| <= rel_eps), sedgey likewise (:551-556)
+// Boundary faces take the per-face rules of the 3-D kernel (both one-sided states are made equal by the reference,
+// :392-436 and :560-596).  REFLECT_ODD is left to the staged path (QUIRK :403-405: the x-lo branch zeroes ie+1).
+template <int PPM, int BX, int BY, bool BC>
+__global__ void __launch_bounds__(BX* BY) k_fused_edge2d(FusedArgs a) {
+  constexpr int H = (PPM == 2) ? 3 : 2;
+  constexpr int SP = BX + 2 * H, SN = (BY + 2 * H) * SP, P = BX, PL = (BY + 1) * P;
+  enum { AX0 = 0, AX1, AY0, AY1, SHX, SHY, GX, GY, NPL };
+  __shared__ double sS[SN];
+  __shared__ double planes[NPL * PL];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * BX + tx;
+  const int ibase = a.lo[0] - 1 + blockIdx.x * (BX - 2);
+  const int jbase = a.lo[1] - 1 + blockIdx.y * (BY - 2);
+  const int i = ibase + tx, j = jbase + ty;
+  const int ic = min(i, a.hi[0] + 1), jc = min(j, a.hi[1] + 1);
+  // loads of this thread's faces and cell, issued before the tile is staged
+  const double* __restrict__ gu = a.umac[0].p;
+  const double* __restrict__ gv = a.umac[1].p;
+  const long ou = a.umac[0].off(ic, jc, 0), ov = a.umac[1].off(ic, jc, 0);
+  const double u0 = gu[ou], u1 = gu[ou + 1];
+  const double v0 = gv[ov], v1 = gv[ov + a.umac[1].n[0]];
+  const double f0 = a.force_zero ? 0.0 : a.force.p[a.force.off(ic, jc, 0)];
+  {
+    const double* __restrict__ gs = a.s.p;
+    const int x0 = a.s.lo[0], x1 = a.s.lo[0] + a.s.n[0] - 1, y0 = a.s.lo[1], y1 = a.s.lo[1] + a.s.n[1] - 1;
+    for (int h = tid; h < SN; h += BX * BY) {
+      const int yy = h / SP, xx = h - yy * SP;
+      const int ii = max(x0, min(ibase - H + xx, x1)), jj = max(y0, min(jbase - H + yy, y1));
+      sS[h] = gs[a.s.off(ii, jj, 0)];
+    }
+  }
+  const LineBC nb = no_wall2();
+  const LineBC lbx = BC ? make_linebc(2, 0, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0]) : nb;
+  const LineBC lby = BC ? make_linebc(2, 1, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1]) : nb;
+  FaceRule frx, fry;
+  frx.kind = fry.kind = FB_NONE;
+  frx.clamp = fry.clamp = 0;
+  frx.low = fry.low = false;
+  if constexpr (BC) {
+    frx = face_rule(i, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0], a.velnorm[0]);
+    fry = face_rule(j, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1], a.velnorm[1]);
+  }
+  const double rel_eps = a.rel_eps;
+  const double tdx = a.dt / a.dx[0], tdy = a.dt / a.dx[1];
+  const double c4x = tdx * 0.25, c4y = tdy * 0.25, dt2 = 0.5 * a.dt;
+  double* const pl = planes + ty * P + tx;
+  const double* const S = sS + (ty + H) * SP + tx + H;
+#define PL2(A, dy, dx) pl[(A)*PL + (dy)*P + (dx)]
+  __syncthreads();
+  // C1
+  {
+    double a0, a1;
+    if constexpr (BC) cell_par_bc<PPM>(S, 1, i, a.slope_order, lbx, a0, a1);
+    else cell_par<PPM>(S, 1, a.slope_order, nb, a0, a1);
+    PL2(AX0, 0, 0) = a0;
+    if (PPM != 0) PL2(AX1, 0, 0) = a1;
+    if constexpr (BC) cell_par_bc<PPM>(S, SP, j, a.slope_order, lby, a0, a1);
+    else cell_par<PPM>(S, SP, a.slope_order, nb, a0, a1);
+    PL2(AY0, 0, 0) = a0;
+    if (PPM != 0) PL2(AY1, 0, 0) = a1;
+  }
+  __syncthreads();
+  // F1
+  bool upx = u0 > 0.0, slowx = !(fabs(u0) > rel_eps);
+  bool upy = v0 > 0.0, slowy = !(fabs(v0) > rel_eps);
+  double shx0, shy0;
+  if (BC && frx.kind != FB_NONE) {
+    upx = frx.kind == FB_LEFT;
+    slowx = false;
+    const int off = upx ? -1 : 0;
+    if (frx.kind == FB_GHOST) shx0 = frx.low ? S[-1] : S[0];
+    else if (frx.kind == FB_ZERO) shx0 = 0.0;
+    else shx0 = clamp_rule(forced_state<PPM>(upx, (pl + off)[AX0 * PL], (pl + off)[AX1 * PL], S[off], u0, tdx, rel_eps),
+                           frx.clamp);
+  } else {
+    const int off = upx ? -1 : 0;
+    shx0 = trace1<PPM>((pl + off)[AX0 * PL], (pl + off)[AX1 * PL], S[off], u0 * tdx, upx);
+    if (slowx) shx0 = trace_slow<PPM>(PL2(AX0, 0, -1), S[-1], PL2(AX0, 0, 0), S[0], u0 * tdx);
+  }
+  if (BC && fry.kind != FB_NONE) {
+    upy = fry.kind == FB_LEFT;
+    slowy = false;
+    const int off = upy ? -P : 0;
+    if (fry.kind == FB_GHOST) shy0 = fry.low ? S[-SP] : S[0];
+    else if (fry.kind == FB_ZERO) shy0 = 0.0;
+    else shy0 = clamp_rule(forced_state<PPM>(upy, (pl + off)[AY0 * PL], (pl + off)[AY1 * PL], S[upy ? -SP : 0], v0, tdy,
+                                             rel_eps), fry.clamp);
+  } else {
+    const int off = upy ? -P : 0;
+    shy0 = trace1<PPM>((pl + off)[AY0 * PL], (pl + off)[AY1 * PL], S[upy ? -SP : 0], v0 * tdy, upy);
+    if (slowy) shy0 = trace_slow<PPM>(PL2(AY0, -1, 0), S[-SP], PL2(AY0, 0, 0), S[0], v0 * tdy);
+  }
+  PL2(SHX, 0, 0) = shx0;
+  PL2(SHY, 0, 0) = shy0;
+  __syncthreads();
+  // C2
+  {
+    const double hf = dt2 * f0;
+    PL2(GX, 0, 0) = c4y * (v1 + v0) * (PL2(SHY, 1, 0) - shy0) - hf;
+    PL2(GY, 0, 0) = c4x * (u1 + u0) * (PL2(SHX, 0, 1) - shx0) - hf;
+  }
+  __syncthreads();
+  // F3
+  const bool st_x = (tx >= 1) && (tx <= BX - 2 || i == a.hi[0] + 1) && (i <= a.hi[0] + 1) && (ty >= 1) &&
+                    (ty <= BY - 2) && (j <= a.hi[1]);
+  const bool st_y = (ty >= 1) && (ty <= BY - 2 || j == a.hi[1] + 1) && (j <= a.hi[1] + 1) && (tx >= 1) &&
+                    (tx <= BX - 2) && (i <= a.hi[0]);
+  if (st_x) {
+    double g = (pl + (upx ? -1 : 0))[GX * PL];
+    if (slowx) g = 0.5 * (PL2(GX, 0, -1) + PL2(GX, 0, 0));
+    double e = shx0 - g;
+    if (BC && frx.kind != FB_NONE) e = (frx.kind >= FB_GHOST) ? shx0 : clamp_rule(e, frx.clamp);
+    a.sedge[0].p[a.sedge[0].off(i, j, 0)] = e;
+  }
+  if (st_y) {
+    double g = (pl + (upy ? -P : 0))[GY * PL];
+    if (slowy) g = 0.5 * (PL2(GY, -1, 0) + PL2(GY, 0, 0));
+    double e = shy0 - g;
+    if (BC && fry.kind != FB_NONE) e = (fry.kind >= FB_GHOST) ? shy0 : clamp_rule(e, fry.clamp);
+    a.sedge[1].p[a.sedge[1].off(i, j, 0)] = e;
+  }
+#undef PL2
+}
+
+template <int PPM, bool BC>
+void launch_fused2d(const FusedArgs& a, int nx, int ny) {
+  constexpr int BX = 32, BY = 8;
+  dim3 block(BX, BY, 1);
+  dim3 grid((nx + BX - 3) / (BX - 2), (ny + BY - 3) / (BY - 2), 1);
+  MGPU_TIMED(TAG_FUSED_EDGE, (k_fused_edge2d<PPM, BX, BY, BC><<<grid, block, 0, ctx().stream>>>(a)));
+}
+
 }  // namespace
 
 // all six faces INTERIOR, FAST arithmetic.  a.kchunk: z planes per CTA.
@@ -818,6 +957,19 @@ void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz
   else if (g_by == 10 && plain) fused_edge2_launch_by<10>(a, ppm_type, nx, ny, nz, false);
   else if (g_by == 12 && plain) fused_edge2_launch_by<12>(a, ppm_type, nx, ny, nz, false);
   else fused_edge2_launch_by<8>(a, ppm_type, nx, ny, nz, bc);
+}
+
+// 2-D, FAST arithmetic; bc: the box has physical boundaries (none of them REFLECT_ODD)
+void fused_edge2d_launch(const FusedArgs& a, int ppm_type, int nx, int ny, bool bc) {
+  switch (ppm_type * 2 + (bc ? 1 : 0)) {
+    case 0: launch_fused2d<0, false>(a, nx, ny); break;
+    case 1: launch_fused2d<0, true>(a, nx, ny); break;
+    case 2: launch_fused2d<1, false>(a, nx, ny); break;
+    case 3: launch_fused2d<1, true>(a, nx, ny); break;
+    case 4: launch_fused2d<2, false>(a, nx, ny); break;
+    case 5: launch_fused2d<2, true>(a, nx, ny); break;
+    default: throw Error("make_edge_scal: invalid ppm_type");
+  }
 }
 
 }  // namespace mgpu

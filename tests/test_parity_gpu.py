@@ -124,12 +124,38 @@ def test_fused_edge_slow_faces(gpu_ops, oracle, ppm_type, variant, shape, kchunk
             check(gv[d].a[c_], cv[d].a[c_], bitwise=False)
 
 
+@pytest.mark.parametrize("ppm_type", [0, 1, 2])
+@pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
+@pytest.mark.parametrize("shape", [(37, 9), (8, 33), (64, 16), (95, 70)])
+@pytest.mark.parametrize("slow", [False, True], ids=["moving", "slow-faces"])
+def test_fused_edge_2d(gpu_ops, oracle, ppm_type, bcset, shape, slow):
+    """FAST fused 2-D kernel (k_fused_edge2d, the whole of make_edge_scal_2d in one launch) on boxes that are not
+    multiples of the CTA tile, scalar and velocity components, periodic / wall / inflow-outflow boxes, with and
+    without faces whose velocity is below rel_eps (or exactly zero)."""
+    from maestro_b200 import lib
+
+    phys = {"periodic": None, "walls": WALLS_2D, "inout": INOUT_2D}[bcset]
+    st = make_state(2, shape, phys_bc=phys, ppm_type=ppm_type)
+    umax = max(np.abs(u.a).max() for u in st["umac"])
+    st["p"].rel_eps = 1e-8 * umax
+    if slow:
+        for u in st["umac"]:
+            u.a[np.abs(u.a) < 0.15 * umax] = 0.0
+        st["p"].rel_eps = 0.3 * umax
+    lib.set_option("exact", 0)
+    g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
+    gv, cv = edge_pair(gpu_ops, oracle, st, (1, 2), is_vel=True, bccomp0=1)
+    for d in range(2):
+        check(g[d].a[:3], c[d].a[:3], bitwise=False)
+        check(gv[d].a[:2], cv[d].a[:2], bitwise=False)
+
+
 @pytest.mark.parametrize("dm,n", [(2, 24), (3, 16)])
 @pytest.mark.parametrize("ppm_type", [0, 1, 2])
 @pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
 @pytest.mark.parametrize("cons", [False, True])
 def test_make_edge_scal(gpu_ops, oracle, fused, dm, n, ppm_type, bcset, cons):
-    if fused != "fused-exact" and (dm == 2 or cons):
+    if fused != "fused-exact" and (cons or (dm == 2 and fused == "staged")):
         pytest.skip("only one device path for this case")
     phys = {"periodic": None, "walls": WALLS_3D if dm == 3 else WALLS_2D,
             "inout": INOUT_3D if dm == 3 else INOUT_2D}[bcset]
@@ -297,8 +323,6 @@ def test_density_advance(gpu_ops, oracle, dm, n, ppm_type, spt, which_step, bcse
     st = make_state(dm, n, phys_bc=phys, ppm_type=ppm_type, species_pred_type=spt)
     p, b = st["p"], st["base"]
     p.rel_eps = 1e-8 * max(np.abs(u.a).max() for u in st["umac"])
-    if exact == 0 and dm == 2:
-        pytest.skip("2-D has no FAST variant")
     from maestro_b200 import lib
 
     lib.set_option("exact", exact)
