@@ -1,6 +1,6 @@
 #!/bin/bash
-# scratch job run on the GPU box by gpurun (edited per experiment)
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -12
 timeout 120 python scripts/perf_2d.py 4096 > gpurun_out/q_perf_2d.log 2>&1
-tail -3 gpurun_out/q_perf_2d.log
+tail -5 gpurun_out/q_perf_2d.log
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/q_launches_2d.csv python scripts/perf_2d.py 4096 > /dev/null 2>&1
+python scripts/ncu_summary.py launches gpurun_out/q_launches_2d.csv 39

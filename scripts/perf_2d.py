@@ -40,5 +40,11 @@ for ppm in (1, 2):
         if it:
             tot += e0.elapsed_time(e1)
     t = tot / 3
+    lib.profile(True)
+    run()
+    torch.cuda.synchronize()
+    prof = lib.profile_get()
+    lib.profile(False)
+    print("   kernel classes (ms, launches) of one profiled episode:", {k: (round(v[0], 3), v[1]) for k, v in prof.items()})
     print("2-D walls ppm%d n=%d density_advance %8.3f ms  %.2e zone-updates/s (4 comps), launches %d"
           % (ppm, n, t, 4 * n * n / t * 1e3, lib.launch_count(reset=True) // 4), flush=True)
