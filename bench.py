@@ -179,9 +179,14 @@ def ncomp_advanced(p):
 
 def cpu_reference(n_sample, steps, warmup):
     """restated reference algorithm (oracle) on the host cores over an n_sample^3 box of the workload"""
+    import ctypes
+
     import oracle_lib
 
     oracle = oracle_lib.load()
+    # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+    gomp = ctypes.CDLL("libgomp.so.1", mode=ctypes.RTLD_GLOBAL)
+    gomp.omp_set_num_threads(len(os.sched_getaffinity(0)))
     st = test_advect_state(n_sample)
     e = alloc_episode(st, None)
     for _ in range(warmup):
@@ -212,7 +217,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1
     W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":

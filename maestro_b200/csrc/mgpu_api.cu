@@ -951,6 +951,7 @@ int mgpu_set_option(const char* key, int value) {
   else if (k == "overlap") g_opt_overlap = value;
   else if (k == "fused_variant") fused_edge_set_variant(value);
   else if (k == "fused_by") fused_edge2_set_by(value);
+  else if (k == "tile2d") fused_edge2d_set_tile(value);
   else throw Error("mgpu_set_option: unknown key " + k);
   MGPU_CATCH
 }

@@ -924,12 +924,22 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge2d(FusedArgs a) {
 #undef PL2
 }
 
-template <int PPM, bool BC>
-void launch_fused2d(const FusedArgs& a, int nx, int ny) {
-  constexpr int BX = 32, BY = 8;
+// tile of the 2-D kernel: 0: 32x8, 1: 16x16, 2: 32x16.  Measured at 4096^2 (profiles/r01k_final.md): 32x16 is the
+// fastest for ppm_type 2 (3.66 ms for 4 components; 32x8: 4.84) and within 1 % of the best for ppm_type 1.  A variant
+// that loops over several tiles per CTA with the next tile's inputs prefetched into registers was slower (it needs
+// 100+ registers, one 512-thread CTA per SM).
+int g_tile2d = 2;
+template <int PPM, bool BC, int BX, int BY>
+void launch_fused2d_t(const FusedArgs& a, int nx, int ny) {
   dim3 block(BX, BY, 1);
   dim3 grid((nx + BX - 3) / (BX - 2), (ny + BY - 3) / (BY - 2), 1);
   MGPU_TIMED(TAG_FUSED_EDGE, (k_fused_edge2d<PPM, BX, BY, BC><<<grid, block, 0, ctx().stream>>>(a)));
+}
+template <int PPM, bool BC>
+void launch_fused2d(const FusedArgs& a, int nx, int ny) {
+  if (g_tile2d == 1) launch_fused2d_t<PPM, BC, 16, 16>(a, nx, ny);
+  else if (g_tile2d == 2) launch_fused2d_t<PPM, BC, 32, 16>(a, nx, ny);
+  else launch_fused2d_t<PPM, BC, 32, 8>(a, nx, ny);
 }
 
 }  // namespace
@@ -950,6 +960,7 @@ static void fused_edge2_launch_by(const FusedArgs& a, int ppm_type, int nx, int 
 
 static int g_by = MGPU_FUSED2_BY;
 void fused_edge2_set_by(int by) { g_by = by; }
+void fused_edge2d_set_tile(int t) { g_tile2d = t; }
 void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc) {
   const bool plain = !a.wadd && !a.sdiv && !a.ssub && !bc;
   if (g_by == 1616 && !bc) fused_edge2_launch_by<16, 16>(a, ppm_type, nx, ny, nz, false);

@@ -13,6 +13,8 @@ from synth import make_state
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 ops = lib.init(0, use_torch_stream=True)
+if len(sys.argv) > 2:
+    lib.set_option("tile2d", int(sys.argv[2]))
 dev = "cuda:0"
 WALLS = [[abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]
 for ppm in (1, 2):

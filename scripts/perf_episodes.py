@@ -18,8 +18,13 @@ dev = "cuda:0"
 WALLS = [[abi.PERIODIC, abi.PERIODIC], [abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]
 
 
+ONLY = os.environ.get("PERF_ONLY")  # e.g. "periodic,1": one configuration only (for ncu launch lists)
+
+
 def timeit(fn, reset, reps=3):
+    lib.launch_count(reset=True)
     reset(); fn(); torch.cuda.synchronize()
+    print("   (%d launches per call)" % lib.launch_count(reset=True), flush=True)
     tot = 0.0
     for _ in range(reps):
         reset()
@@ -35,6 +40,8 @@ def dv(f):
 
 for bcname, phys in (("periodic", None), ("walls", WALLS)):
     for ppm in (1, 2):
+        if ONLY and ONLY != "%s,%d" % (bcname, ppm):
+            continue
         st = make_state(3, n, phys_bc=phys, ppm_type=ppm, noise=0.0)
         vs = make_vel_state(3, n, phys_bc=phys, ppm_type=ppm, noise=0.0)
         p, b = st["p"], st["base"]

@@ -128,7 +128,8 @@ def test_fused_edge_slow_faces(gpu_ops, oracle, ppm_type, variant, shape, kchunk
 @pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
 @pytest.mark.parametrize("shape", [(37, 9), (8, 33), (64, 16), (95, 70)])
 @pytest.mark.parametrize("slow", [False, True], ids=["moving", "slow-faces"])
-def test_fused_edge_2d(gpu_ops, oracle, ppm_type, bcset, shape, slow):
+@pytest.mark.parametrize("tile", [2, 0, 1], ids=["32x16", "32x8", "16x16"])
+def test_fused_edge_2d(gpu_ops, oracle, ppm_type, bcset, shape, slow, tile):
     """FAST fused 2-D kernel (k_fused_edge2d, the whole of make_edge_scal_2d in one launch) on boxes that are not
     multiples of the CTA tile, scalar and velocity components, periodic / wall / inflow-outflow boxes, with and
     without faces whose velocity is below rel_eps (or exactly zero)."""
@@ -143,8 +144,12 @@ def test_fused_edge_2d(gpu_ops, oracle, ppm_type, bcset, shape, slow):
             u.a[np.abs(u.a) < 0.15 * umax] = 0.0
         st["p"].rel_eps = 0.3 * umax
     lib.set_option("exact", 0)
-    g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
-    gv, cv = edge_pair(gpu_ops, oracle, st, (1, 2), is_vel=True, bccomp0=1)
+    lib.set_option("tile2d", tile)
+    try:
+        g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
+        gv, cv = edge_pair(gpu_ops, oracle, st, (1, 2), is_vel=True, bccomp0=1)
+    finally:
+        lib.set_option("tile2d", 2)
     for d in range(2):
         check(g[d].a[:3], c[d].a[:3], bitwise=False)
         check(gv[d].a[:2], cv[d].a[:2], bitwise=False)
