@@ -34,30 +34,6 @@ METRIC = "advective zone-updates/sec (3D PPM)"
 UNIT = "zone-updates/s"
 
 
-def bind_to_gpu_numa_node(gpu):
-    """Run this rank on the CPU cores next to its GPU (NVML's ideal affinity), so that the pinned host buffers of
-    the e2e leg are first-touched on the GPU's own NUMA node and its PCIe traffic does not cross sockets."""
-    try:
-        import pynvml
-
-        pynvml.nvmlInit()
-        import torch
-
-        pr = torch.cuda.get_device_properties(gpu)  # CUDA_VISIBLE_DEVICES may renumber: go through the PCI address
-        h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id,
-                                                                         pr.pci_device_id)).encode())
-        ncpu = os.cpu_count() or 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
-        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
-        allowed = os.sched_getaffinity(0)
-        cpus = [c for c in cpus if c in allowed]
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-        return len(cpus)
-    except Exception:
-        return 0
-
-
 def peaks():
     try:
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -246,8 +222,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        bind_to_gpu_numa_node(local_rank)
     dev = "cuda:%d" % local_rank
     ops = lib.init(local_rank, use_torch_stream=True)
     for kv in args.opt:
