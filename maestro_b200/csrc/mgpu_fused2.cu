@@ -774,10 +774,10 @@ void launch_fused2(const FusedArgs& a0, int nx, int ny, int nz) {
 template <int PPM, int BY, int BX = MGPU_FUSED_BX>
 void launch_fused2_xf(const FusedArgs& a, int nx, int ny, int nz, bool bc) {
   const int xf = a.sdiv ? 1 : (a.ssub ? 2 : 0);
-  if (bc) {  // boxes with physical boundaries: plain inputs, 32x8 tile
+  if (bc) {  // boxes with physical boundaries: plain inputs, 32x8 and 16x16 tiles
     if (xf != 0 || a.wadd) throw Error("make_edge_scal: on-the-fly transforms are not built for boxes with physical boundaries");
-    if constexpr (BY == 8) launch_fused2<PPM, BX, BY, 0, false, true>(a, nx, ny, nz);
-    else throw Error("make_edge_scal: the boundary variant of the upwind-first kernel is built for the 32x8 tile");
+    if constexpr (BY == 8 || (BX == 16 && BY == 16)) launch_fused2<PPM, BX, BY, 0, false, true>(a, nx, ny, nz);
+    else throw Error("make_edge_scal: the boundary variant of the upwind-first kernel is built for the 32x8 and 16x16 tiles");
     return;
   }
   if (a.sdiv && a.ssub) throw Error("make_edge_scal: only one on-the-fly transform of s at a time");
@@ -963,7 +963,7 @@ void fused_edge2_set_by(int by) { g_by = by; }
 void fused_edge2d_set_tile(int t) { g_tile2d = t; }
 void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc) {
   const bool plain = !a.wadd && !a.sdiv && !a.ssub && !bc;
-  if (g_by == 1616 && !bc) fused_edge2_launch_by<16, 16>(a, ppm_type, nx, ny, nz, false);
+  if (g_by == 1616) fused_edge2_launch_by<16, 16>(a, ppm_type, nx, ny, nz, bc);
   else if (g_by == 16 && plain) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz, false);
   else if (g_by == 10 && plain) fused_edge2_launch_by<10>(a, ppm_type, nx, ny, nz, false);
   else if (g_by == 12 && plain) fused_edge2_launch_by<12>(a, ppm_type, nx, ny, nz, false);

@@ -18,6 +18,8 @@ dev = "cuda:0"
 WALLS = [[abi.PERIODIC, abi.PERIODIC], [abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]
 
 
+if os.environ.get("PERF_VARIANT"):  # 3: upwind-first kernel for every box and ppm_type, 0: literal kernel everywhere
+    lib.set_option("fused_variant", int(os.environ["PERF_VARIANT"]))
 ONLY = os.environ.get("PERF_ONLY")  # e.g. "periodic,1": one configuration only (for ncu launch lists)
 
 
