@@ -1,4 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for o in walls,1 walls,2; do PERF_ONLY=$o timeout 200 python scripts/perf_episodes.py 128 2>&1 | grep advance | cut -c1-100; done
+(time python -m pytest tests/test_full_size_gpu.py -x -q 2>&1 | tail -8) 2>&1
+python -m pytest tests/test_full_size_gpu.py -x -q 2>&1 | tail -2
