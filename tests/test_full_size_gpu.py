@@ -162,3 +162,129 @@ def test_c2_uniform_state_in_divergence_free_flow_is_preserved(gpu_ops, c2_state
             if p.spec_comp - 1 <= c < p.spec_comp - 1 + p.nspec:
                 want = v0 / 1.5  # the species are predicted as X = rhoX / rho
             assert float((e["sedge"][d].a[c] - want).abs().max()) <= 1e-13 * abs(want), (c, d)
+
+
+def _max_rel(a, b):
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-300)
+
+
+def test_c2_fast_build_agrees_with_the_bit_identical_build(gpu_ops, c2_state, c2_run):
+    """The FAST episode (upwind-first kernels, FMA, on-the-fly transforms) against the exact build (literal kernels,
+    bit-identical to the oracle in the small-size parity tests) at 256^3: 1e-12 relative, max-norm per field."""
+    from maestro_b200 import lib
+
+    lib.set_option("exact", 1)
+    try:
+        ex = _episode(gpu_ops, c2_state, "cuda:0")
+    finally:
+        lib.set_option("exact", 0)
+    p = c2_state["p"]
+    comps = _comps(p) + [p.rho_comp - 1]
+    for c in comps:
+        assert _max_rel(c2_run["snew"].a[c], ex["snew"].a[c]) <= TOL, ("snew", c)
+        for d in range(3):
+            assert _max_rel(c2_run["sedge"][d].a[c], ex["sedge"][d].a[c]) <= TOL, ("sedge", d, c)
+    for c in _comps(p):
+        for d in range(3):
+            assert _max_rel(c2_run["sflux"][d].a[c], ex["sflux"][d].a[c]) <= TOL, ("sflux", d, c)
+    assert _max_rel(c2_run["eta"].a, ex["eta"].a) <= TOL
+
+
+# ---- config C4: rt, 2-D 4096^2, ppm_type 2, periodic x, slip wall / outlet in y, nspec = 2 -----------------------
+N4 = 4096
+
+
+@pytest.fixture(scope="module")
+def c4_state():
+    from maestro_b200 import abi
+    from synth import make_state
+
+    walls = [[abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]]
+    return make_state(2, N4, phys_bc=walls, ppm_type=2, nspec=2, noise=0.0)
+
+
+def _episode_2d(gpu_ops, st, exact, shift_x=0):
+    import torch
+
+    from maestro_b200 import Fab, abi, face_fabs, lib
+
+    dev = "cuda:0"
+    p, b = st["p"], st["base"]
+    sold, snew = st["s"].to(dev), st["s"].to(dev)
+    umac = [u.to(dev) for u in st["umac"]]
+    if shift_x:
+        g = sold.ng
+        v = sold.a[:, :, g:-g, g:-g]
+        v.copy_(torch.roll(v, shifts=shift_x, dims=3))
+        u = umac[0].a[:, :, 1:-1, 1:1 + N4]  # periodic x-faces
+        u.copy_(torch.roll(u, shifts=shift_x, dims=3))
+        w = umac[1].a[:, :, 1:-1, 1:-1]
+        w.copy_(torch.roll(w, shifts=shift_x, dims=3))
+    umac[0].a[:, :, 1:-1, 1 + N4] = umac[0].a[:, :, 1:-1, 1]  # periodic in x: face hi+1 is face lo (always)
+    sedge = face_fabs(st["lo"], st["hi"], 0, p.nscal, 2, device=dev)
+    sflux = face_fabs(st["lo"], st["hi"], 0, p.nscal, 2, device=dev)
+    force = st["force"].to(dev)
+    eta = Fab(st["lo"], st["hi"], 0, 1, nodal=[0, 1, 0], dm=2, device=dev)
+    torch.cuda.synchronize()  # the library runs on its own stream
+    p.mem_space = abi.DEVICE
+    lib.set_option("exact", exact)
+    try:
+        gpu_ops.fill_boundary(p, sold, 1, 2 + 1, p.nscal, st["adv_bc"], st["pmask"])
+        for d in range(2):
+            gpu_ops.fill_boundary(p, umac[d], 1, 1, 1, st["adv_bc"], st["pmask"])
+        sold0 = sold.a.clone()
+        gpu_ops.density_advance(p, 1, sold, snew, sedge, sflux, force, umac, b["w0"], eta, b["rho0_old"], b["rho0_new"],
+                                b["p0"], b["rho0_predicted_edge"], st["adv_bc"], st["pmask"])
+        torch.cuda.synchronize()
+    finally:
+        p.mem_space = abi.HOST
+        lib.set_option("exact", 0)
+    return dict(sold0=sold0, snew=snew, sedge=sedge, sflux=sflux, eta=eta)
+
+
+@pytest.fixture(scope="module")
+def c4_run(gpu_ops, c4_state):
+    return _episode_2d(gpu_ops, c4_state, exact=0)
+
+
+def test_c4_fused_2d_kernel_agrees_with_the_bit_identical_build(gpu_ops, c4_state, c4_run):
+    """config C4 at full size: the FAST episode (fused 2-D kernel) against the exact build (staged path,
+    bit-identical to the oracle in the small-size parity tests): 1e-12 relative, max-norm per field."""
+    ex = _episode_2d(gpu_ops, c4_state, exact=1)
+    p = c4_state["p"]
+    comps = _comps(p) + [p.rho_comp - 1]
+    for c in comps:
+        assert _max_rel(c4_run["snew"].a[c], ex["snew"].a[c]) <= TOL, ("snew", c)
+        for d in range(2):
+            assert _max_rel(c4_run["sedge"][d].a[c], ex["sedge"][d].a[c]) <= TOL, ("sedge", d, c)
+    for c in _comps(p):
+        for d in range(2):
+            assert _max_rel(c4_run["sflux"][d].a[c], ex["sflux"][d].a[c]) <= TOL, ("sflux", d, c)
+
+
+def test_c4_update_is_the_divergence_of_the_returned_fluxes(c4_state, c4_run):
+    """walls and an outlet: the boundary fluxes are part of the returned arrays, so the identity holds cell by cell"""
+    p = c4_state["p"]
+    g = 4
+    so = c4_run["sold0"][:, 0, g:-g, g:-g]
+    sn = c4_run["snew"].a[:, 0, g:-g, g:-g]
+    fx, fy = (f.a[:, 0] for f in c4_run["sflux"])
+    for c in _comps(p):
+        div = (fx[c][:, 1:] - fx[c][:, :-1]) / p.dx[0] + (fy[c][1:, :] - fy[c][:-1, :]) / p.dx[1]
+        want = so[c] - p.dt * div
+        assert float((sn[c] - want).abs().max()) <= TOL * float(so[c].abs().max()), c
+
+
+def test_c4_translation_symmetry_in_x_is_bitwise(gpu_ops, c4_state, c4_run):
+    import torch
+
+    sh = 45  # not a multiple of the 30-cell tile interior
+    e2 = _episode_2d(gpu_ops, c4_state, exact=0, shift_x=sh)
+    p = c4_state["p"]
+    g = 4
+    for c in _comps(p) + [p.rho_comp - 1]:
+        a = torch.roll(c4_run["snew"].a[c, 0, g:-g, g:-g], shifts=sh, dims=1)
+        assert torch.equal(a, e2["snew"].a[c, 0, g:-g, g:-g]), ("snew", c)
+        for d in range(2):
+            a = torch.roll(c4_run["sedge"][d].a[c, 0, :, :N4], shifts=sh, dims=1)
+            assert torch.equal(a, e2["sedge"][d].a[c, 0, :, :N4]), ("sedge", d, c)
