@@ -965,8 +965,6 @@ void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz
   const bool plain = !a.wadd && !a.sdiv && !a.ssub && !bc;
   if (g_by == 1616) fused_edge2_launch_by<16, 16>(a, ppm_type, nx, ny, nz, bc);
   else if (g_by == 16 && plain) fused_edge2_launch_by<16>(a, ppm_type, nx, ny, nz, false);
-  else if (g_by == 10 && plain) fused_edge2_launch_by<10>(a, ppm_type, nx, ny, nz, false);
-  else if (g_by == 12 && plain) fused_edge2_launch_by<12>(a, ppm_type, nx, ny, nz, false);
   else fused_edge2_launch_by<8>(a, ppm_type, nx, ny, nz, bc);
 }
 

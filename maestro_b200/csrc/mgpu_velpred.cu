@@ -65,7 +65,9 @@ __device__ __forceinline__ double upwind_trans(double l, double r, double ut, do
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_mkutrans(VpArgs a, int d) {
+template <int D>
+__global__ void k_mkutrans(VpArgs a) {
+  constexpr int d = D;
   int ix[3];
   Box3 fb = a.vb;
   fb.hi[d] += 1;
@@ -98,7 +100,9 @@ __global__ void k_mkutrans(VpArgs a, int d) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_vp_face(VpArgs a, int d) {
+template <int D>
+__global__ void k_vp_face(VpArgs a) {
+  constexpr int d = D;
   int ix[3];
   Box3 fb = a.tb;
   fb.lo[d] = a.lo[d];  // faces lo..hi+1 in d, lo-1..hi+1 transverse
@@ -110,7 +114,7 @@ __global__ void k_vp_face(VpArgs a, int d) {
   const long uo = a.utilde.off(ix[0], ix[1], ix[2]);
   const long st = a.utilde.stride(d);
   double ul[3], ur[3];
-  for (int c = 0; c < dm; ++c) {
+  _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) {
     const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[c][d], a.bchi[c][d]);
     const double* q = a.utilde.p + uo + a.utilde.cs * c;
     double dummy;
@@ -121,43 +125,43 @@ __global__ void k_vp_face(VpArgs a, int d) {
   if (ix[d] == a.lo[d]) {
     const int p = a.plo[d];
     if (p == MGPU_BC_INLET) {
-      for (int c = 0; c < dm; ++c) ul[c] = ur[c] = a.utilde.p[uo - st + a.utilde.cs * c];
+      _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ul[c] = ur[c] = a.utilde.p[uo - st + a.utilde.cs * c];
     } else if (p == MGPU_BC_SLIP_WALL || p == MGPU_BC_SYMMETRY) {
-      for (int c = 0; c < dm; ++c) {
+      _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) {
         if (c == d) ul[c] = ur[c] = 0.0;
         else ul[c] = ur[c];
       }
     } else if (p == MGPU_BC_NO_SLIP_WALL) {
-      for (int c = 0; c < dm; ++c) ul[c] = ur[c] = 0.0;
+      _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ul[c] = ur[c] = 0.0;
     } else if (p == MGPU_BC_OUTLET) {
       ur[d] = dmin2(ur[d], 0.0);
       if (d == 0 && dm == 2) {  // QUIRK velpred.f90:415-417: copies the wrong way (urx = ulx)
-        for (int c = 0; c < dm; ++c) ur[c] = ul[c];
+        _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ur[c] = ul[c];
       } else if (d == 0 && dm == 3) {  // QUIRK velpred.f90:861-862: self-assignment
       } else {
-        for (int c = 0; c < dm; ++c) ul[c] = ur[c];
+        _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ul[c] = ur[c];
       }
     }
   }
   if (ix[d] == a.hi[d] + 1) {
     const int p = a.phi[d];
     if (p == MGPU_BC_INLET) {
-      for (int c = 0; c < dm; ++c) ul[c] = ur[c] = a.utilde.p[uo + a.utilde.cs * c];
+      _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ul[c] = ur[c] = a.utilde.p[uo + a.utilde.cs * c];
     } else if (p == MGPU_BC_SLIP_WALL || p == MGPU_BC_SYMMETRY) {
-      for (int c = 0; c < dm; ++c) {
+      _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) {
         if (c == d) ul[c] = ur[c] = 0.0;
         else ur[c] = ul[c];
       }
     } else if (p == MGPU_BC_NO_SLIP_WALL) {
-      for (int c = 0; c < dm; ++c) ul[c] = ur[c] = 0.0;
+      _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ul[c] = ur[c] = 0.0;
     } else if (p == MGPU_BC_OUTLET) {
       ul[d] = dmax2(ul[d], 0.0);
-      for (int c = 0; c < dm; ++c) ur[c] = ul[c];
+      _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ur[c] = ul[c];
     }
   }
   const double ut = a.utrans[d](ix[0], ix[1], ix[2]);
   const long to = a.UL[d].off(ix[0], ix[1], ix[2]);
-  for (int c = 0; c < dm; ++c) {
+  _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) {
     a.UL[d].p[to + a.UL[d].cs * c] = ul[c];
     a.UR[d].p[to + a.UR[d].cs * c] = ur[c];
     if (c != d) a.UIMH[d].p[to + a.UIMH[d].cs * c] = upwind_trans(ul[c], ur[c], ut, a.rel_eps);
@@ -175,7 +179,9 @@ __global__ void k_vp_trans(VpArgs a) {
   int ix[3];
   if (!decode3(a.tb, ix)) return;
   const double dt6 = a.dt / 6.0;
+#pragma unroll
   for (int c = 0; c < 3; ++c)
+#pragma unroll
     for (int d = 0; d < 3; ++d) {
       if (d == c) continue;
       const int t = 3 - c - d;
@@ -202,7 +208,9 @@ __global__ void k_vp_trans(VpArgs a) {
     }
 }
 
-__global__ void k_vp_final(VpArgs a, int d) {
+template <int D>
+__global__ void k_vp_final(VpArgs a) {
+  constexpr int d = D;
   int ix[3];
   Box3 fb = a.vb;
   fb.hi[d] += 1;
@@ -321,7 +329,9 @@ void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* u
   for (int d = 0; d < P.dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    MGPU_TIMED(TAG_VELPRED, (k_mkutrans<<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a, d)));
+    if (d == 0) MGPU_TIMED(TAG_VELPRED, (k_mkutrans<0><<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a)));
+    else if (d == 1) MGPU_TIMED(TAG_VELPRED, (k_mkutrans<1><<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a)));
+    else MGPU_TIMED(TAG_VELPRED, (k_mkutrans<2><<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a)));
   }
 }
 
@@ -361,13 +371,17 @@ void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* um
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.tb;
     fb.lo[d] = a.lo[d];
-    MGPU_TIMED(TAG_VELPRED, (k_vp_face<<<grid3(fb, 128), block3(fb, 128), 0, s>>>(a, d)));
+    if (d == 0) MGPU_TIMED(TAG_VELPRED, (k_vp_face<0><<<grid3(fb, 128), block3(fb, 128), 0, s>>>(a)));
+    else if (d == 1) MGPU_TIMED(TAG_VELPRED, (k_vp_face<1><<<grid3(fb, 128), block3(fb, 128), 0, s>>>(a)));
+    else MGPU_TIMED(TAG_VELPRED, (k_vp_face<2><<<grid3(fb, 128), block3(fb, 128), 0, s>>>(a)));
   }
   if (dm == 3) MGPU_TIMED(TAG_VELPRED, (k_vp_trans<<<grid3(a.tb, 256), block3(a.tb, 256), 0, s>>>(a)));
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    MGPU_TIMED(TAG_VELPRED, (k_vp_final<<<grid3(fb, 256), block3(fb, 256), 0, s>>>(a, d)));
+    if (d == 0) MGPU_TIMED(TAG_VELPRED, (k_vp_final<0><<<grid3(fb, 256), block3(fb, 256), 0, s>>>(a)));
+    else if (d == 1) MGPU_TIMED(TAG_VELPRED, (k_vp_final<1><<<grid3(fb, 256), block3(fb, 256), 0, s>>>(a)));
+    else MGPU_TIMED(TAG_VELPRED, (k_vp_final<2><<<grid3(fb, 256), block3(fb, 256), 0, s>>>(a)));
   }
 }
 

@@ -1,2 +1,3 @@
 #!/bin/bash
-(time python -m pytest tests/test_full_size_gpu.py -x -q -k c3 2>&1 | tail -12) 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+PERF_ONLY=periodic,1 timeout 200 python scripts/perf_episodes.py 128 2>&1 | grep advance | cut -c1-100
