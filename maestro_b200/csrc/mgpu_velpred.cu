@@ -65,7 +65,7 @@ __device__ __forceinline__ double upwind_trans(double l, double r, double ut, do
 }
 
 // ------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int PPM>
 __global__ void k_mkutrans(VpArgs a) {
   constexpr int d = D;
   int ix[3];
@@ -79,9 +79,9 @@ __global__ void k_mkutrans(VpArgs a) {
   const double* qf = uf.p + uf.off(ix[0], ix[1], ix[2]);
   const long fst = uf.stride(d);
   double ul, ur, dummy;
-  vel_cell_states(a.ppm_type, a.slope_order, false, q - st, st, ix[d] - 1, b, qf[-fst], a.dt, a.dx[d], a.rel_eps, ul,
+  vel_cell_states(PPM, a.slope_order, false, q - st, st, ix[d] - 1, b, qf[-fst], a.dt, a.dx[d], a.rel_eps, ul,
                   dummy);
-  vel_cell_states(a.ppm_type, a.slope_order, false, q, st, ix[d], b, qf[0], a.dt, a.dx[d], a.rel_eps, dummy, ur);
+  vel_cell_states(PPM, a.slope_order, false, q, st, ix[d], b, qf[0], a.dt, a.dx[d], a.rel_eps, dummy, ur);
   if (ix[d] == a.lo[d]) {
     const int p = a.plo[d];
     if (p == MGPU_BC_INLET) { ul = q[-st]; ur = q[-st]; }
@@ -100,7 +100,7 @@ __global__ void k_mkutrans(VpArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int PPM>
 __global__ void k_vp_face(VpArgs a) {
   constexpr int d = D;
   int ix[3];
@@ -118,9 +118,9 @@ __global__ void k_vp_face(VpArgs a) {
     const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[c][d], a.bchi[c][d]);
     const double* q = a.utilde.p + uo + a.utilde.cs * c;
     double dummy;
-    vel_cell_states(a.ppm_type, a.slope_order, dm == 3, q - st, st, ix[d] - 1, b, ucl, a.dt, a.dx[d], a.rel_eps, ul[c],
+    vel_cell_states(PPM, a.slope_order, dm == 3, q - st, st, ix[d] - 1, b, ucl, a.dt, a.dx[d], a.rel_eps, ul[c],
                     dummy);
-    vel_cell_states(a.ppm_type, a.slope_order, dm == 3, q, st, ix[d], b, ucr, a.dt, a.dx[d], a.rel_eps, dummy, ur[c]);
+    vel_cell_states(PPM, a.slope_order, dm == 3, q, st, ix[d], b, ucr, a.dt, a.dx[d], a.rel_eps, dummy, ur[c]);
   }
   if (ix[d] == a.lo[d]) {
     const int p = a.plo[d];
@@ -208,7 +208,7 @@ __global__ void k_vp_trans(VpArgs a) {
     }
 }
 
-template <int D>
+template <int D, int PPM>
 __global__ void k_vp_final(VpArgs a) {
   constexpr int d = D;
   int ix[3];
@@ -229,9 +229,9 @@ __global__ void k_vp_final(VpArgs a) {
       const long uo = ufd.off(ix[0], ix[1], ix[2]);
       const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[d][d], a.bchi[d][d]);
       double dummy;
-      vel_cell_states(a.ppm_type, a.slope_order, dm == 3, f.p + fo - fst, fst, ix[d] - 1, b, ufd.p[uo - ufd.stride(d)],
+      vel_cell_states(PPM, a.slope_order, dm == 3, f.p + fo - fst, fst, ix[d] - 1, b, ufd.p[uo - ufd.stride(d)],
                       a.dt, a.dx[d], a.rel_eps, fl, dummy);
-      vel_cell_states(a.ppm_type, a.slope_order, dm == 3, f.p + fo, fst, ix[d], b, ufd.p[uo], a.dt, a.dx[d], a.rel_eps,
+      vel_cell_states(PPM, a.slope_order, dm == 3, f.p + fo, fst, ix[d], b, ufd.p[uo], a.dt, a.dx[d], a.rel_eps,
                       dummy, fr);
     } else {
       fl = f.p[fo - fst];
@@ -269,6 +269,23 @@ __global__ void k_vp_final(VpArgs a) {
   }
   a.umac[d](ix[0], ix[1], ix[2]) = e;
 }
+
+// launches kern<D, PPM> for the runtime (d, ppm_type)
+#define VP_LAUNCH(kern, d, ppm, grid, block, stream, args)                                            \
+  do {                                                                                                \
+    switch ((d)*3 + (ppm)) {                                                                          \
+      case 0: MGPU_TIMED(TAG_VELPRED, (kern<0, 0><<<grid, block, 0, stream>>>(args))); break;         \
+      case 1: MGPU_TIMED(TAG_VELPRED, (kern<0, 1><<<grid, block, 0, stream>>>(args))); break;         \
+      case 2: MGPU_TIMED(TAG_VELPRED, (kern<0, 2><<<grid, block, 0, stream>>>(args))); break;         \
+      case 3: MGPU_TIMED(TAG_VELPRED, (kern<1, 0><<<grid, block, 0, stream>>>(args))); break;         \
+      case 4: MGPU_TIMED(TAG_VELPRED, (kern<1, 1><<<grid, block, 0, stream>>>(args))); break;         \
+      case 5: MGPU_TIMED(TAG_VELPRED, (kern<1, 2><<<grid, block, 0, stream>>>(args))); break;         \
+      case 6: MGPU_TIMED(TAG_VELPRED, (kern<2, 0><<<grid, block, 0, stream>>>(args))); break;         \
+      case 7: MGPU_TIMED(TAG_VELPRED, (kern<2, 1><<<grid, block, 0, stream>>>(args))); break;         \
+      case 8: MGPU_TIMED(TAG_VELPRED, (kern<2, 2><<<grid, block, 0, stream>>>(args))); break;         \
+      default: throw Error("velpred: invalid ppm_type");                                              \
+    }                                                                                                 \
+  } while (0)
 
 void check_phys(int bc, const char* who) {
   switch (bc) {
@@ -329,9 +346,7 @@ void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* u
   for (int d = 0; d < P.dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    if (d == 0) MGPU_TIMED(TAG_VELPRED, (k_mkutrans<0><<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a)));
-    else if (d == 1) MGPU_TIMED(TAG_VELPRED, (k_mkutrans<1><<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a)));
-    else MGPU_TIMED(TAG_VELPRED, (k_mkutrans<2><<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a)));
+    VP_LAUNCH(k_mkutrans, d, a.ppm_type, grid3(fb, 256), block3(fb, 256), ctx().stream, a);
   }
 }
 
@@ -371,17 +386,13 @@ void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* um
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.tb;
     fb.lo[d] = a.lo[d];
-    if (d == 0) MGPU_TIMED(TAG_VELPRED, (k_vp_face<0><<<grid3(fb, 128), block3(fb, 128), 0, s>>>(a)));
-    else if (d == 1) MGPU_TIMED(TAG_VELPRED, (k_vp_face<1><<<grid3(fb, 128), block3(fb, 128), 0, s>>>(a)));
-    else MGPU_TIMED(TAG_VELPRED, (k_vp_face<2><<<grid3(fb, 128), block3(fb, 128), 0, s>>>(a)));
+    VP_LAUNCH(k_vp_face, d, a.ppm_type, grid3(fb, 128), block3(fb, 128), s, a);
   }
   if (dm == 3) MGPU_TIMED(TAG_VELPRED, (k_vp_trans<<<grid3(a.tb, 256), block3(a.tb, 256), 0, s>>>(a)));
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    if (d == 0) MGPU_TIMED(TAG_VELPRED, (k_vp_final<0><<<grid3(fb, 256), block3(fb, 256), 0, s>>>(a)));
-    else if (d == 1) MGPU_TIMED(TAG_VELPRED, (k_vp_final<1><<<grid3(fb, 256), block3(fb, 256), 0, s>>>(a)));
-    else MGPU_TIMED(TAG_VELPRED, (k_vp_final<2><<<grid3(fb, 256), block3(fb, 256), 0, s>>>(a)));
+    VP_LAUNCH(k_vp_final, d, a.ppm_type, grid3(fb, 256), block3(fb, 256), s, a);
   }
 }
 
