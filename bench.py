@@ -306,10 +306,12 @@ def main():
         bytes_per_zone = {"fused_edge": 64.0, "edge_transverse": 64.0, "edge_final": 64.0}.get(name, 64.0)
         achieved = bytes_per_zone * n ** 3 / (ms / nl * 1e-3) / 1e9
         traffic = None
+        ncu_static = None
         try:  # DRAM bytes per launch of this kernel class from the committed ncu --set full capture (n = 256 only)
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             if n == 256 and name in tj:
                 traffic = tj[name]["bytes_per_launch"]
+                ncu_static = tj[name].get("ncu")  # issue / fp64-pipe / DRAM utilisation of the same capture
         except Exception:
             traffic = None
         others = {}
@@ -324,7 +326,8 @@ def main():
                 "algorithmic_bytes_per_launch": bytes_per_zone * n ** 3,
                 "episode_algorithmic_GBs": 368.0 * n ** 3 * args.steps / t_dev / 1e9,
                 "episode_frac": 368.0 * n ** 3 * args.steps / t_dev / 1e9 / hbm,
-                "kernel_classes_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+                "kernel_classes_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+                "ncu_capture": ncu_static}
     del flush
 
     # ---------------- end to end through the C ABI with host buffers (e2e) ------------------------
