@@ -352,6 +352,12 @@ int mgpu_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, 
 int mgpu_estdt(const mgpu_params* p, int nfabs, const mgpu_fab* u, const mgpu_fab* s, const mgpu_fab* force,
                const mgpu_fab* divU, const mgpu_fab* dSdt, const double* w0, const double* p0,
                const double* gamma1bar, double rho_min, double cflfac, double* dt, double* umax);
+/* estdt for spherical geometry (estdt_3d_sphr, Source/estdt.f90:620): w0mac = make_w0mac's face fabs (zero when
+ * evolve_base_state is off, :100-110); gp0 (:734-739) and its put_1d_array_on_cart (:741) happen inside. */
+int mgpu_estdt_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* u, const mgpu_fab* s,
+                    const mgpu_fab* force, const mgpu_fab* divU, const mgpu_fab* dSdt,
+                    const mgpu_fab* const* w0mac, const double* w0, const double* p0, const double* gamma1bar,
+                    double rho_min, double cflfac, double* dt, double* umax);
 /* make_etarho_planar (Source/make_eta.f90:36; sum_etarho_2d :176, _3d :213): plane averages of etarhoflux,
  * etarho_ec(0:nr) on edges and etarho_cc(0:nr-1) = their two-point means.  The sums of one rank's planes are
  * combined over the ranks (NCCL sum, the reference's parallel_reduce :101); ncell = cells per plane of the whole

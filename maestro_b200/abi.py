@@ -126,6 +126,8 @@ OPERATORS = {
     "enthalpy_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_] + [c_double_p] * 10 + [c_int_p] * 2),
     "estdt": (C.c_int, [P_, C.c_int, F_, F_, F_, F_, F_] + [c_double_p] * 3 + [C.c_double] * 2 + [c_double_p] * 2),
     "make_etarho_planar": (C.c_int, [P_, C.c_int, F_, c_double_p, c_double_p]),
+    "estdt_sphr": (C.c_int, [P_, G_, C.c_int, F_, F_, F_, F_, F_, FF_] + [c_double_p] * 3 + [C.c_double] * 2
+                   + [c_double_p] * 2),
     # spherical geometry
     "put_1d_array_on_cart": (C.c_int, [P_, G_, C.c_int, c_double_p, F_, C.c_int, C.c_int]),
     "make_w0mac": (C.c_int, [P_, G_, C.c_int, c_double_p, FF_, F_]),

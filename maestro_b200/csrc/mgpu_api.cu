@@ -1794,4 +1794,68 @@ int mgpu_make_etarho_planar(const mgpu_params* p, int nfabs, const mgpu_fab* eta
 }
 
 
+int mgpu_estdt_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* u, const mgpu_fab* s,
+                    const mgpu_fab* force, const mgpu_fab* divU, const mgpu_fab* dSdt, const mgpu_fab* const* w0mac,
+                    const double* w0, const double* p0, const double* gamma1bar, double rho_min, double cflfac,
+                    double* dt, double* umax) {
+  MGPU_TRY
+  need_sphr(p, g);
+  const int nr = g->nr_fine;
+  size_t cells = 0;
+  for (int i = 0; i < nfabs; ++i) {
+    size_t c1 = 1;
+    for (int d = 0; d < 3; ++d) c1 *= (size_t)(u[i].hi[d] - u[i].lo[d] + 1);
+    cells = std::max(cells, c1);
+  }
+  Call c(p, geom_scratch(g) + (3 * cells + 148 * 8 * 8 + 64) * sizeof(double) + 8192);
+  Geom gd = make_geom(*p, *g);
+  // gp0 on the radial edges (estdt.f90:734-739)
+  std::vector<double> gp0(nr + 1);
+  for (int r = 1; r <= nr - 1; ++r) {
+    const double gamma1bar_p_avg = 0.5 * (gamma1bar[r] * p0[r] + gamma1bar[r - 1] * p0[r - 1]);
+    gp0[r] = ((p0[r] - p0[r - 1]) / g->dr) / gamma1bar_p_avg;
+  }
+  gp0[nr] = gp0[nr - 1];
+  gp0[0] = gp0[1];
+  const double* gp0_d = upload_small(gp0.data(), (size_t)nr + 1);
+  const double* w0_d = upload_small(w0, (size_t)nr + 1);
+  const double dt_start = 1.e99;
+  double dt_proc = 1.e99, umax_proc = 0.0;
+  for (int i = 0; i < nfabs; ++i) {
+    DV uv = c.view(u[i], true, false);
+    DV sv = c.view(s[i], crange(p->rho_comp - 1, 1), (cmask_t)0);
+    DV fv = c.view(force[i], true, false);
+    DV dUv = c.view(divU[i], true, false), dSv = c.view(dSdt[i], true, false);
+    DV wm[3];
+    c.views(w0mac, i, true, false, wm);
+    const size_t mark = arena_mark();
+    size_t c1 = 1;
+    for (int d = 0; d < 3; ++d) c1 *= (size_t)(u[i].hi[d] - u[i].lo[d] + 1);
+    DV gc = make_view(arena_alloc(3 * c1), u[i].lo, u[i].hi, 3, 0, nullptr, 3);
+    put_1d_array_on_cart_dev(*p, *g, gd, gp0_d, gc, true, true, u[i].lo, u[i].hi);  // :741
+    double dt_grid = std::numeric_limits<double>::max(), umax_grid = 0.0;
+    estdt_box_dev(*p, uv, sv, fv, dUv, dSv, w0_d, w0, nullptr, nullptr, u[i].lo, u[i].hi, rho_min, cflfac, &dt_grid,
+                  &umax_grid, wm, &gc, g->dr, nr);
+    arena_release(mark);
+    dt_proc = std::min(dt_proc, dt_grid);
+    umax_proc = std::max(umax_proc, umax_grid);
+  }
+  double dt_lev = dt_proc, umax_lev = umax_proc;
+  if (comm_size() > 1) {
+    double h[2] = {dt_proc, -umax_proc};
+    double* d = arena_alloc(2);
+    MGPU_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, g_ctx.stream));
+    allreduce_dev(d, 2, 1);
+    MGPU_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, g_ctx.stream));
+    MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    dt_lev = h[0];
+    umax_lev = -h[1];
+  }
+  *umax = std::max(*umax, umax_lev);
+  if (dt_lev == dt_start) dt_lev = std::min(p->dx[0], std::min(p->dx[1], p->dx[2]));
+  *dt = std::min(*dt, dt_lev);
+  c.finish();
+  MGPU_CATCH
+}
+
 }  // extern "C"

@@ -30,11 +30,14 @@ struct EstdtArgs {
   double dx_r;  // dx of the radial (last) direction
   double rho_min;
   double* part;  // E_N doubles per CTA
+  // spherical (estdt_3d_sphr, estdt.f90:620): w0 on the faces of every direction, grad(p0)/(gamma1bar p0) as a
+  // Cartesian vector field on the valid cells (put_1d_array_on_cart of gp0, :741)
+  DV w0mac[3], gp0c;
 };
 
 // One pass over the valid cells; every thread keeps the eight running extrema of estdt_2d / estdt_3d_cart.
 // The expressions are the reference's (estdt.f90:503-515 speeds, :538-552 forces, :566-585 divU, :600-606 dS/dt).
-template <int DM>
+template <int DM, bool SPHR>
 __global__ void __launch_bounds__(256) k_estdt(EstdtArgs a) {
   const int nx = a.vb.hi[0] - a.vb.lo[0] + 1, ny = a.vb.hi[1] - a.vb.lo[1] + 1;
   const long npts = a.vb.npts();
@@ -53,17 +56,30 @@ __global__ void __launch_bounds__(256) k_estdt(EstdtArgs a) {
 #pragma unroll
     for (int d = 0; d < DM; ++d) {
       double v = a.u.p[ou + a.u.cs * d];
-      if (d == r) v = v + 0.5 * (a.w0[kr] + a.w0[kr + 1]);
+      if constexpr (SPHR) {  // :664-680
+        const long ow = a.w0mac[d].off(i, j, k);
+        v = v + 0.5 * (a.w0mac[d].p[ow] + a.w0mac[d].p[ow + a.w0mac[d].stride(d)]);
+      } else if (d == r) {
+        v = v + 0.5 * (a.w0[kr] + a.w0[kr + 1]);
+      }
       m[E_SPD0 + d] = fmax(m[E_SPD0 + d], fabs(v));
       m[E_F0 + d] = fmax(m[E_F0 + d], fabs(a.force.p[of + a.force.cs * d]));
     }
-    double gradp0;
-    if (kr == 0) gradp0 = (a.p0[kr + 1] - a.p0[kr]) / a.dx_r;
-    else if (kr == a.nr - 1) gradp0 = (a.p0[kr] - a.p0[kr - 1]) / a.dx_r;
-    else gradp0 = 0.5 * (a.p0[kr + 1] - a.p0[kr - 1]) / a.dx_r;
     const double rho = a.s(i, j, k, a.rho);
     const double dU = a.divU(i, j, k);
-    const double denom = dU - ur * gradp0 / (a.gamma1bar[kr] * a.p0[kr]);
+    double denom;
+    if constexpr (SPHR) {  // :747-751
+      const long og = a.gp0c.off(i, j, k);
+      const double gp_dot_u = a.u.p[ou] * a.gp0c.p[og] + a.u.p[ou + a.u.cs] * a.gp0c.p[og + a.gp0c.cs] +
+                              a.u.p[ou + 2 * a.u.cs] * a.gp0c.p[og + 2 * a.gp0c.cs];
+      denom = dU - gp_dot_u;
+    } else {
+      double gradp0;
+      if (kr == 0) gradp0 = (a.p0[kr + 1] - a.p0[kr]) / a.dx_r;
+      else if (kr == a.nr - 1) gradp0 = (a.p0[kr] - a.p0[kr - 1]) / a.dx_r;
+      else gradp0 = 0.5 * (a.p0[kr + 1] - a.p0[kr - 1]) / a.dx_r;
+      denom = dU - ur * gradp0 / (a.gamma1bar[kr] * a.p0[kr]);
+    }
     if (denom > 0.0) m[E_DT_DIVU] = fmin(m[E_DT_DIVU], 0.4 * (1.0 - a.rho_min / rho) / denom);
     const double dS = a.dSdt(i, j, k);
     if (dS > 1.e-20) {
@@ -114,7 +130,8 @@ __global__ void __launch_bounds__(256) k_plane_sums(DV f, Box3 vb, int dm, int k
 
 void estdt_box_dev(const mgpu_params& P, const DV& u, const DV& s, const DV& force, const DV& divU, const DV& dSdt,
                    const double* w0, const double* w0_h, const double* p0, const double* gamma1bar, const int* lo,
-                   const int* hi, double rho_min, double cfl, double* dt, double* umax) {
+                   const int* hi, double rho_min, double cfl, double* dt, double* umax, const DV* w0mac,
+                   const DV* gp0_cart, double dr, int nr_fine) {
   Context& cx = ctx();
   const int dm = P.dm, r = dm - 1;
   EstdtArgs a;
@@ -128,8 +145,16 @@ void estdt_box_dev(const mgpu_params& P, const DV& u, const DV& s, const DV& for
   a.rho_min = rho_min;
   const unsigned nb = std::min<unsigned>(nblocks(a.vb.npts(), 256), 148u * 8u);
   a.part = arena_alloc((size_t)nb * E_N);
-  if (dm == 3) k_estdt<3><<<nb, 256, 0, cx.stream>>>(a);
-  else k_estdt<2><<<nb, 256, 0, cx.stream>>>(a);
+  const bool sphr = w0mac != nullptr;
+  if (sphr) {
+    for (int d = 0; d < 3; ++d) a.w0mac[d] = w0mac[d];
+    a.gp0c = *gp0_cart;
+    k_estdt<3, true><<<nb, 256, 0, cx.stream>>>(a);
+  } else if (dm == 3) {
+    k_estdt<3, false><<<nb, 256, 0, cx.stream>>>(a);
+  } else {
+    k_estdt<2, false><<<nb, 256, 0, cx.stream>>>(a);
+  }
   MGPU_LAUNCH_CHECK();
   std::vector<double> part((size_t)nb * E_N);
   MGPU_CUDA(cudaMemcpyAsync(part.data(), a.part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, cx.stream));
@@ -142,14 +167,18 @@ void estdt_box_dev(const mgpu_params& P, const DV& u, const DV& s, const DV& for
   // the scalar tail of estdt_2d / estdt_3d_cart, statement by statement
   const double eps = 1.0e-8;
   double spdr = 0.0;
-  for (int k = lo[r]; k <= hi[r]; ++k) spdr = std::max(spdr, std::fabs(w0_h[k]));  // :517-519
+  if (sphr) {
+    for (int k = 0; k <= nr_fine; ++k) spdr = std::max(spdr, std::fabs(w0_h[k]));  // :682-684
+  } else {
+    for (int k = lo[r]; k <= hi[r]; ++k) spdr = std::max(spdr, std::fabs(w0_h[k]));  // :517-519
+  }
   double um = 0.0;
   for (int d = 0; d < dm; ++d) um = std::max(um, m[E_SPD0 + d]);
   *umax = std::max(um, spdr);  // :521
   double t = *dt;
   for (int d = 0; d < dm; ++d)
     if (m[E_SPD0 + d] > eps) t = std::min(t, P.dx[d] / m[E_SPD0 + d]);  // :523-525
-  if (spdr > eps) t = std::min(t, P.dx[r] / spdr);                     // :526
+  if (spdr > eps) t = std::min(t, (sphr ? dr : P.dx[r]) / spdr);       // :526 / :691
   t = t * cfl;                                                          // :528
   for (int d = 0; d < dm; ++d)
     if (m[E_F0 + d] > eps) t = std::min(t, std::sqrt(2.0 * P.dx[d] / m[E_F0 + d]));  // :554-561

@@ -232,6 +232,17 @@ class Operators:
                    keep[0][1], keep[1][1], keep[2][1], float(rho_min), float(cflfac), C.byref(dt_c), C.byref(um_c))
         return dt_c.value, um_c.value
 
+    def estdt_sphr(self, p, geom, u, s, force, divU, dSdt, w0mac, w0, p0, gamma1bar, cflfac, dt, umax=0.0,
+                   rho_min=1.0e-20):
+        """estdt_3d_sphr (Source/estdt.f90:620) for one level: returns (min(dt, dt_lev), max(umax, umax_lev))."""
+        keep = [as_double_p(x) for x in (w0, p0, gamma1bar)]
+        wm, k1 = fab_pp(w0mac)
+        dt_c, um_c = C.c_double(dt), C.c_double(umax)
+        self._call("estdt_sphr", C.byref(p), C.byref(geom.c), 1, fab_ptr(u), fab_ptr(s), fab_ptr(force), fab_ptr(divU),
+                   fab_ptr(dSdt), wm, keep[0][1], keep[1][1], keep[2][1], float(rho_min), float(cflfac),
+                   C.byref(dt_c), C.byref(um_c))
+        return dt_c.value, um_c.value
+
     def make_etarho_planar(self, p, etarhoflux):
         """Source/make_eta.f90:36: returns (etarho_ec(0:nr), etarho_cc(0:nr-1))."""
         ec, cc = np.zeros(p.nr + 1), np.zeros(p.nr)

@@ -342,4 +342,13 @@ int mo_make_etarho_planar(const mgpu_params* p, int nfabs, const mgpu_fab* etarh
   MO_CATCH
 }
 
+int mo_estdt_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* u, const mgpu_fab* s,
+                  const mgpu_fab* force, const mgpu_fab* divU, const mgpu_fab* dSdt, const mgpu_fab* const* w0mac,
+                  const double* w0, const double* p0, const double* gamma1bar, double rho_min, double cflfac, double* dt,
+                  double* umax) {
+  MO_TRY
+  estdt_sphr_level(*p, *g, nfabs, u, s, force, divU, dSdt, w0mac, w0, p0, gamma1bar, rho_min, cflfac, *dt, *umax);
+  MO_CATCH
+}
+
 }  // extern "C"

@@ -122,6 +122,13 @@ void fill_boundary_face(const mgpu_params& P, Arr& u, const int* lo, const int* 
 void estdt_level(const mgpu_params& P, int nfabs, const mgpu_fab* u, const mgpu_fab* s, const mgpu_fab* force,
                  const mgpu_fab* divU, const mgpu_fab* dSdt, const double* w0, const double* p0,
                  const double* gamma1bar, double rho_min, double cfl, double& dt, double& umax);
+// put_1d_array_on_cart_3d_sphr (mo_sphr.cpp, fill_3d_data.f90:269)
+void put_1d_array_on_cart_sphr(const mgpu_params& P, const mgpu_geom& g, bool edge_in, bool vec, const double* s0,
+                               Arr& cart, const int* lo, const int* hi);
+void estdt_sphr_level(const mgpu_params& P, const mgpu_geom& g, int nfabs, const mgpu_fab* u, const mgpu_fab* s,
+                      const mgpu_fab* force, const mgpu_fab* divU, const mgpu_fab* dSdt, const mgpu_fab* const* w0mac,
+                      const double* w0, const double* p0, const double* gamma1bar, double rho_min, double cfl,
+                      double& dt, double& umax);
 void make_etarho_planar(const mgpu_params& P, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
                         double* etarho_cc);
 

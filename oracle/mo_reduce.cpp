@@ -2,6 +2,7 @@
 // Restatement of the reductions next to the advective path:
 //   estdt_2d        Source/estdt.f90:348      estdt_3d_cart   Source/estdt.f90:467
 //   sum_etarho_2d   Source/make_eta.f90:176   sum_etarho_3d   Source/make_eta.f90:213
+//   estdt_3d_sphr   Source/estdt.f90:620
 //   make_etarho_planar Source/make_eta.f90:36 (single level, one chunk: r_end_coord = nr-1)
 // Same loops, same order, same expressions.
 #include <algorithm>
@@ -90,6 +91,82 @@ void estdt_level(const mgpu_params& P, int nfabs, const mgpu_fab* u, const mgpu_
     dt_lev = P.dx[0];
     for (int d = 1; d < P.dm; ++d) dt_lev = std::min(dt_lev, P.dx[d]);
   }
+  dt = std::min(dt, dt_lev);
+}
+
+// estdt_3d_sphr, estdt.f90:620-773 (dt inout, umax out)
+void estdt_sphr_box(const mgpu_params& P, const mgpu_geom& g, const Arr& u, const Arr& s, const Arr& force,
+                    const Arr& divU, const Arr& dSdt, const Arr* w0mac, const double* w0, const double* p0,
+                    const double* gamma1bar, const int* lo, const int* hi, double rho_min, double cfl, double& dt,
+                    double& umax) {
+  const int nr_fine = g.nr_fine, rho = P.rho_comp - 1;
+  const double eps = 1.0e-8;
+  double spd[3] = {0.0, 0.0, 0.0}, spdr = 0.0;
+  umax = 0.0;
+  for (int d = 0; d < 3; ++d)
+    for (int k = lo[2]; k <= hi[2]; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+          const double whi = w0mac[d](i + (d == 0), j + (d == 1), k + (d == 2));
+          spd[d] = std::max(spd[d], std::fabs(u(i, j, k, d) + 0.5 * (w0mac[d](i, j, k) + whi)));
+        }
+  for (int k = 0; k <= nr_fine; ++k) spdr = std::max(spdr, std::fabs(w0[k]));
+  for (int d = 0; d < 3; ++d) umax = std::max(umax, spd[d]);
+  umax = std::max(umax, spdr);
+  for (int d = 0; d < 3; ++d)
+    if (spd[d] > eps) dt = std::min(dt, P.dx[d] / spd[d]);
+  if (spdr > eps) dt = std::min(dt, g.dr / spdr);
+  dt = dt * cfl;
+  double f[3] = {0.0, 0.0, 0.0};
+  for (int d = 0; d < 3; ++d)
+    for (int k = lo[2]; k <= hi[2]; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) f[d] = std::max(f[d], std::fabs(force(i, j, k, d)));
+  for (int d = 0; d < 3; ++d)
+    if (f[d] > eps) dt = std::min(dt, std::sqrt(2.0 * P.dx[d] / f[d]));
+  std::vector<double> gp0(nr_fine + 1);
+  for (int r = 1; r <= nr_fine - 1; ++r) {
+    const double gamma1bar_p_avg = 0.5 * (gamma1bar[r] * p0[r] + gamma1bar[r - 1] * p0[r - 1]);
+    gp0[r] = ((p0[r] - p0[r - 1]) / g.dr) / gamma1bar_p_avg;
+  }
+  gp0[nr_fine] = gp0[nr_fine - 1];
+  gp0[0] = gp0[1];
+  Arr gp0_cart(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 3);
+  put_1d_array_on_cart_sphr(P, g, true, true, gp0.data(), gp0_cart, lo, hi);
+  for (int k = lo[2]; k <= hi[2]; ++k)
+    for (int j = lo[1]; j <= hi[1]; ++j)
+      for (int i = lo[0]; i <= hi[0]; ++i) {
+        const double gp_dot_u =
+            u(i, j, k, 0) * gp0_cart(i, j, k, 0) + u(i, j, k, 1) * gp0_cart(i, j, k, 1) + u(i, j, k, 2) * gp0_cart(i, j, k, 2);
+        const double denom = divU(i, j, k) - gp_dot_u;
+        if (denom > 0.0) dt = std::min(dt, 0.4 * (1.0 - rho_min / s(i, j, k, rho)) / denom);
+        if (dSdt(i, j, k) > 1.e-20) {
+          const double a = 0.5 * s(i, j, k, rho) * dSdt(i, j, k);
+          const double b = s(i, j, k, rho) * divU(i, j, k);
+          const double c = rho_min - s(i, j, k, rho);
+          dt = std::min(dt, 0.4 * 2.0 * c / (-b - std::sqrt(b * b - 4.0 * a * c)));
+        }
+      }
+}
+
+void estdt_sphr_level(const mgpu_params& P, const mgpu_geom& g, int nfabs, const mgpu_fab* u, const mgpu_fab* s,
+                      const mgpu_fab* force, const mgpu_fab* divU, const mgpu_fab* dSdt, const mgpu_fab* const* w0mac,
+                      const double* w0, const double* p0, const double* gamma1bar, double rho_min, double cfl,
+                      double& dt, double& umax) {
+  const double dt_start = 1.e99;
+  double dt_proc = 1.e99, umax_proc = 0.0;
+  for (int i = 0; i < nfabs; ++i) {
+    Arr ua = Arr::view(u[i], 3), sa = Arr::view(s[i], 3), fa = Arr::view(force[i], 3);
+    Arr dU = Arr::view(divU[i], 3), dS = Arr::view(dSdt[i], 3);
+    Arr wm[3] = {Arr::view(w0mac[0][i], 3), Arr::view(w0mac[1][i], 3), Arr::view(w0mac[2][i], 3)};
+    double dt_grid = std::numeric_limits<double>::max(), umax_grid = 0.0;
+    estdt_sphr_box(P, g, ua, sa, fa, dU, dS, wm, w0, p0, gamma1bar, u[i].lo, u[i].hi, rho_min, cfl, dt_grid, umax_grid);
+    dt_proc = std::min(dt_proc, dt_grid);
+    umax_proc = std::max(umax_proc, umax_grid);
+  }
+  double dt_lev = dt_proc;
+  umax = std::max(umax, umax_proc);
+  if (dt_lev == dt_start) dt_lev = std::min(P.dx[0], std::min(P.dx[1], P.dx[2]));
   dt = std::min(dt, dt_lev);
 }
 

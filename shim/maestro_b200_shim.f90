@@ -284,6 +284,20 @@ module maestro_b200_shim
        real(c_double), intent(inout) :: dt, umax
      end function mgpu_estdt_c
 
+     ! estdt_3d_sphr (Source/estdt.f90:620) for one level; w0mac: the three face multifabs of make_w0mac
+     integer(c_int) function mgpu_estdt_sphr_c(p, g, nfabs, u, s, force, divU, dSdt, w0mac, w0, p0, gamma1bar, &
+          rho_min, cflfac, dt, umax) bind(C, name="mgpu_estdt_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(in) :: u(*), s(*), force(*), divU(*), dSdt(*)
+       type(c_ptr), intent(in) :: w0mac(*)
+       real(c_double), intent(in) :: w0(*), p0(*), gamma1bar(*)
+       real(c_double), value :: rho_min, cflfac
+       real(c_double), intent(inout) :: dt, umax
+     end function mgpu_estdt_sphr_c
+
      ! make_etarho_planar (Source/make_eta.f90:36): etarho_ec(0:nr), etarho_cc(0:nr-1) of one level
      integer(c_int) function mgpu_make_etarho_planar_c(p, nfabs, etarhoflux, etarho_ec, etarho_cc) &
           bind(C, name="mgpu_make_etarho_planar")
@@ -301,7 +315,7 @@ module maestro_b200_shim
   public :: mgpu_put_1d_array_on_cart_c, mgpu_make_w0mac_c, mgpu_make_s0mac_c, mgpu_addw0_sphr_c
   public :: mgpu_mk_rhoX_flux_sphr_c, mgpu_mk_rhoh_flux_sphr_c, mgpu_update_velocity_sphr_c
   public :: mgpu_mkutrans_sphr_c, mgpu_velpred_sphr_c, mgpu_modify_scal_force_sphr_c, mgpu_put_in_pert_form_sphr_c
-  public :: mgpu_fill_geom, mgpu_estdt_c, mgpu_make_etarho_planar_c
+  public :: mgpu_fill_geom, mgpu_estdt_c, mgpu_estdt_sphr_c, mgpu_make_etarho_planar_c
   public :: make_edge_scal_gpu
 
 contains

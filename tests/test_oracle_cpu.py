@@ -567,3 +567,53 @@ def test_make_etarho_planar_known_answer(oracle, dm, n):
     ec, cc = oracle.make_etarho_planar(p, eta)
     assert np.abs(ec - g).max() <= 1e-13 * np.abs(g).max()
     assert np.abs(cc - 0.5 * (g[:-1] + g[1:])).max() <= 1e-13 * np.abs(g).max()
+
+
+def test_estdt_sphr_known_answers(oracle):
+    """estdt_3d_sphr (estdt.f90:620): with w0 = 0, no forces and no expansion the limit is the CFL limit of the
+    velocity; with a hydrostatic-like p0(r) and a purely radial outflow u = c * rhat the divU constraint sees
+    denom = divU - u . grad(p0)/(gamma1bar p0), checked against the same expression built from the path's own
+    put_1d_array_on_cart."""
+    from sphr_common import make_sphr_state
+    from synth import make_estdt_inputs
+
+    st = make_sphr_state(n=12, ops=oracle)
+    p, g = st["p"], st["geom"]
+    e = make_estdt_inputs(3, 12)
+    nr = g.nr_fine
+    vel = [0.5, -2.0, 1.25]
+    for d in range(3):
+        e["u"].a[d] = vel[d]
+    e["s"].a[...] = 2.0
+    for f in (e["force"], e["divU"], e["dSdt"]):
+        f.a[...] = 0.0
+    w0mac0 = face_fabs(st["lo"], st["hi"], 1, 1, 3)
+    p0 = np.full(nr, 3.0)
+    g1 = np.full(nr, 1.5)
+    dt, umax = oracle.estdt_sphr(p, g, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0mac0, np.zeros(nr + 1), p0, g1,
+                                 0.7, 1e30)
+    assert umax == 2.0 and dt == min(p.dx[d] / abs(vel[d]) for d in range(3)) * 0.7
+    # w0 only: the radial speed limit uses dr, not dx (estdt.f90:691)
+    e["u"].a[...] = 0.0
+    w0 = np.zeros(nr + 1)
+    w0[3] = -4.0
+    dt2, um2 = oracle.estdt_sphr(p, g, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0mac0, w0, p0, g1, 0.7, 1e30)
+    assert um2 == 4.0 and dt2 == (g.dr / 4.0) * 0.7
+    # divU constraint with a pressure gradient: rebuild denom from put_1d_array_on_cart of gp0
+    rc = g.r_cc_loc
+    p0 = 10.0 * np.exp(-rc / 0.4)
+    gp0 = np.zeros(nr + 1)
+    for r in range(1, nr):
+        gp0[r] = ((p0[r] - p0[r - 1]) / g.dr) / (0.5 * (g1[r] * p0[r] + g1[r - 1] * p0[r - 1]))
+    gp0[nr], gp0[0] = gp0[nr - 1], gp0[1]
+    cart = Fab(st["lo"], st["hi"], 0, 3, dm=3)
+    oracle.put_1d_array_on_cart(p, g, gp0, cart, True, True)
+    rng = np.random.default_rng(3)
+    e["u"].a[...] = 1e-3 * rng.uniform(-1, 1, size=e["u"].shape)
+    e["divU"].a[...] = 50.0
+    uv = e["u"].valid()
+    denom = 50.0 - (uv[0] * cart.a[0] + uv[1] * cart.a[1] + uv[2] * cart.a[2])
+    want = (0.4 * (1.0 - 1e-20 / 2.0) / denom[denom > 0]).min()
+    dt3, _ = oracle.estdt_sphr(p, g, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0mac0, np.zeros(nr + 1), p0, g1,
+                               0.7, 1e30)
+    assert dt3 == want

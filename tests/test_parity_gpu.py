@@ -865,3 +865,35 @@ def test_make_etarho_planar(gpu_ops, oracle, dm, n):
     ec_w, cc_w = oracle.make_etarho_planar(p, eta)
     ec_g, cc_g = gpu_ops.make_etarho_planar(p, eta)
     assert relerr(ec_g, ec_w) <= TOL and relerr(cc_g, cc_w) <= TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [12, (20, 14, 17)])
+@pytest.mark.parametrize("active", ["all", "velocity", "divU", "dSdt"])
+@pytest.mark.parametrize("w0_interp_type", [1, 2, 3])
+def test_estdt_sphr(gpu_ops, oracle, n, active, w0_interp_type):
+    """estdt_3d_sphr (estdt.f90:620): w0 on the faces (make_w0mac), grad p0 through put_1d_array_on_cart; max / min
+    reductions of bit-identical operands, so dt and umax are bit-identical to the restated reference."""
+    from sphr_common import make_sphr_state
+    from synth import make_estdt_inputs
+
+    st = make_sphr_state(n=n, ops=oracle, w0_interp_type=w0_interp_type)
+    p, g = st["p"], st["geom"]
+    shape = (n, n, n) if np.isscalar(n) else n
+    amp = dict(speed=1.0, force_amp=1.0, divu_amp=1.0, dsdt_amp=1.0)
+    if active != "all":
+        amp = dict(speed=1e-3, force_amp=1e-6, divu_amp=1e-6, dsdt_amp=1e-30)
+        amp[{"velocity": "speed", "divU": "divu_amp", "dSdt": "dsdt_amp"}[active]] = 1.0
+        if active == "dSdt":
+            amp["divu_amp"] = 1e-3
+    e = make_estdt_inputs(3, list(shape), **amp)
+    nr = g.nr_fine
+    rc = g.r_cc_loc
+    p0 = 10.0 * np.exp(-rc / 0.4)
+    g1 = 1.4 + 0.2 * np.cos(2 * np.pi * rc)
+    w0 = st["rad"]["w0"] * (1.0 if active in ("all", "velocity") else 1e-4)
+    args = (p, g, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], st["w0mac"], w0, p0, g1, 0.7, 1e30)
+    want = oracle.estdt_sphr(*args)
+    got = gpu_ops.estdt_sphr(*args)
+    assert got == want, (got, want)
+    assert np.isfinite(got[0]) and got[0] > 0.0
