@@ -752,7 +752,7 @@ namespace mgpu {
 
 // DM: dimensionality; FAST: multiply by 1/dx instead of dividing (last-bit differences, <= 1e-12 relative)
 template <int DM, bool FAST>
-__global__ void __launch_bounds__(256, 4) k_flux_update_all(FluxArgs a, UpdArgs u, int t0, int ntrac, int rho, double bcd) {
+__global__ void __launch_bounds__(256, 3) k_flux_update_all(FluxArgs a, UpdArgs u, int t0, int ntrac, int rho, double bcd) {
   int ix[3];
   if (!decode3(u.vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
