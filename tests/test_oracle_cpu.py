@@ -617,3 +617,31 @@ def test_estdt_sphr_known_answers(oracle):
     dt3, _ = oracle.estdt_sphr(p, g, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], w0mac0, np.zeros(nr + 1), p0, g1,
                                0.7, 1e30)
     assert dt3 == want
+
+
+@pytest.mark.parametrize("dm,n", [(2, (14, 11)), (3, (9, 7, 10))])
+def test_reductions_bounds_checked_build_agrees(oracle, dm, n):
+    """estdt / make_etarho_planar (and estdt_sphr in 3-D): every restated loop stays inside the reference's array
+    bounds (the MO_BOUNDS build aborts otherwise) and gives the same bits as the optimised build."""
+    from synth import make_estdt_inputs
+
+    dbg = oracle_lib.load(debug=True)
+    e = make_estdt_inputs(dm, list(n))
+    p = e["p"]
+    args = (p, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], e["w0"], e["p0"], e["gamma1bar"], 0.7, 1e30)
+    assert oracle.estdt(*args) == dbg.estdt(*args)
+    nod = [0] * 3
+    nod[dm - 1] = 1
+    eta = Fab(e["lo"], e["hi"], 0, 1, nodal=nod, dm=dm)
+    eta.a[...] = np.random.default_rng(11).uniform(-1.0, 2.0, size=eta.shape)
+    for a, b in zip(oracle.make_etarho_planar(p, eta), dbg.make_etarho_planar(p, eta)):
+        assert np.array_equal(a, b)
+    if dm == 3:
+        from sphr_common import make_sphr_state
+
+        st = make_sphr_state(n=list(n), ops=oracle)
+        g = st["geom"]
+        rc = g.r_cc_loc
+        sargs = (st["p"], g, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], st["w0mac"], st["rad"]["w0"],
+                 10.0 * np.exp(-rc / 0.4), 1.4 + 0.2 * np.cos(2 * np.pi * rc), 0.7, 1e30)
+        assert oracle.estdt_sphr(*sargs) == dbg.estdt_sphr(*sargs)
