@@ -88,7 +88,7 @@ void halo_plan_make(int dm, const int* domlo, const int* domhi, const int* lo, c
   const bool per = pmask[r] != 0;
   pl->dn_rank = at_lo ? (per ? nranks - 1 : -1) : rank - 1;
   pl->up_rank = at_hi ? (per ? 0 : -1) : rank + 1;
-  if (nranks == 1) pl->dn_rank = pl->up_rank = -1;  // a single slab wraps inside the box (k_wrap)
+  if (nranks == 1) pl->dn_rank = pl->up_rank = -1;  // a single slab wraps inside the box (k_wrap_all)
   // planes are addressed by their index in the slab direction (the reference's global k or j)
   pl->send_up_k0 = hi[r] + 1 - ng;       // -> up neighbour's low ghosts   lo_up-ng .. lo_up-1
   pl->send_dn_k0 = lo[r] + nod;          // -> down neighbour's high ghosts hi_dn+nod+1 .. hi_dn+nod+ng

@@ -471,55 +471,59 @@ void put_in_pert_form_dev(const mgpu_params& P, const DV& s, const double* base_
 }
 
 // ------------------------------------------------------------------------------------------
-// ghost fill.  Periodic wrap in direction d over the full allocated transverse extent (done for
-// d = x, y, z in turn, so edges/corners come out right), then physbc in the reference's order.
-__global__ void k_wrap(DV a, Box3 tb, int d, int lo, int hi, int ng, int nodal) {
-  int ix[3];
-  if (!decode32(tb, ix)) return;  // tb: d collapsed to [0, 2*ng-1] = ghost slot
-  a.p += a.cs * blockIdx.y;       // one grid row per component
-  const int g = ix[d];                    // 0..ng-1: lo side, ng..2ng-1: hi side
-  const int n = hi - lo + 1;
-  int dst, src;
-  if (g < ng) {
-    dst = lo - 1 - g;
-    src = dst + n;
-  } else {
-    dst = hi + nodal + 1 + (g - ng);
-    src = dst - n;
-  }
-  int id[3] = {ix[0], ix[1], ix[2]}, is[3] = {ix[0], ix[1], ix[2]};
-  id[d] = dst;
-  is[d] = src;
-  a(id[0], id[1], id[2]) = a(is[0], is[1], is[2]);
-}
+// ghost fill: periodic wraps (k_wrap_all), then physbc in the reference's order.
+#define WRAP_MAX 12  // (fab, component) pairs per wrap launch: blockIdx.y selects the pair
 
-// the same wrap for up to WRAP_MAX (fab, component) pairs in one launch: blockIdx.y selects the pair
-#define WRAP_MAX 12
-struct WrapMany {
+// All periodic directions in ONE launch: a ghost cell takes the value of the cell obtained by wrapping every periodic
+// coordinate that lies in its ghost range -- the same values as wrapping x, then y, then z (edges and corners
+// included), without the ordering.  The ghost shell is split into disjoint regions (blockIdx.z): region r holds the
+// cells that are ghost in direction r and not ghost in any periodic direction before r.
+struct WrapAll {
   int n;
   DV a[WRAP_MAX];
-  Box3 tb[WRAP_MAX];
-  int lo[WRAP_MAX], hi[WRAP_MAX], ng[WRAP_MAX], nodal[WRAP_MAX];
+  int lo[WRAP_MAX][3], hi[WRAP_MAX][3], nodal[WRAP_MAX][3], ng[WRAP_MAX];
+  int per[3];  // wrap in this direction (periodic and not the slab direction of a multi-rank run)
 };
-__global__ void k_wrap_many(const __grid_constant__ WrapMany w, int d) {
-  const int e = blockIdx.y;
+__global__ void k_wrap_all(const __grid_constant__ WrapAll w) {
+  const int e = blockIdx.y, reg = blockIdx.z;
+  if (!w.per[reg]) return;
   const DV& a = w.a[e];
-  int ix[3];
-  if (!decode32(w.tb[e], ix)) return;
-  const int g = ix[d], ng = w.ng[e];
-  const int n = w.hi[e] - w.lo[e] + 1;
-  int dst, src;
-  if (g < ng) {
-    dst = w.lo[e] - 1 - g;
-    src = dst + n;
-  } else {
-    dst = w.hi[e] + w.nodal[e] + 1 + (g - ng);
-    src = dst - n;
+  const int ng = w.ng[e];
+  int cnt[3], base[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (d == reg) {
+      cnt[d] = 2 * ng;
+      base[d] = 0;
+    } else if (d < reg && w.per[d]) {  // valid range only (its ghost cells belong to region d)
+      base[d] = w.lo[e][d];
+      cnt[d] = w.hi[e][d] + w.nodal[e][d] - w.lo[e][d] + 1;
+    } else {  // the whole allocated extent
+      base[d] = a.lo[d];
+      cnt[d] = a.n[d];
+    }
   }
-  int id[3] = {ix[0], ix[1], ix[2]}, is[3] = {ix[0], ix[1], ix[2]};
-  id[d] = dst;
-  is[d] = src;
-  a(id[0], id[1], id[2]) = a(is[0], is[1], is[2]);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)cnt[0] * (unsigned)cnt[1] * (unsigned)cnt[2]) return;
+  const unsigned q1 = t / (unsigned)cnt[0];
+  int c[3];
+  c[0] = (int)(t - q1 * (unsigned)cnt[0]);
+  const unsigned q2 = q1 / (unsigned)cnt[1];
+  c[1] = (int)(q1 - q2 * (unsigned)cnt[1]);
+  c[2] = (int)q2;
+  int dst[3], src[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int lo = w.lo[e][d], top = w.hi[e][d] + w.nodal[e][d], n = w.hi[e][d] - w.lo[e][d] + 1;
+    if (d == reg) dst[d] = (c[d] < ng) ? lo - 1 - c[d] : top + 1 + (c[d] - ng);
+    else dst[d] = base[d] + c[d];
+    src[d] = dst[d];
+    if (w.per[d]) {
+      if (dst[d] < lo) src[d] = dst[d] + n;
+      else if (dst[d] > top) src[d] = dst[d] - n;
+    }
+  }
+  a(dst[0], dst[1], dst[2]) = a(src[0], src[1], src[2]);
 }
 
 __global__ void k_physbc(DV s, Box3 tb, int d, int side, int bc, int lo, int hi, int ng) {
@@ -569,37 +573,47 @@ bool fill_exchange(const FillReq& r) {
                            g_fill_stream ? g_fill_stream : ctx().stream);
 }
 
-// periodic wraps of a set of requests: x, then y, then z (so edges/corners come out right); one launch per
-// direction covers every (fab, component) pair of the set
+// periodic wraps of a set of requests: every periodic direction in one launch (k_wrap_all) for all the (fab,
+// component) pairs that wrap in the same directions
 void fill_wraps(const FillReq* reqs, const char* slab, size_t nreq) {
   Context& cx = ctx();
-  for (int d = 0; d < 3; ++d) {
-    WrapMany w;
+  for (int sig = 1; sig < 8; ++sig) {  // bit d: wrap in direction d
+    WrapAll w;
     w.n = 0;
+    for (int d = 0; d < 3; ++d) w.per[d] = (sig >> d) & 1;
     unsigned maxblocks = 0;
     auto flush = [&]() {
       if (w.n == 0) return;
-      k_wrap_many<<<dim3(maxblocks, w.n), 256, 0, cx.stream>>>(w, d);
+      k_wrap_all<<<dim3(maxblocks, w.n, 3), 256, 0, cx.stream>>>(w);
       MGPU_LAUNCH_CHECK();
       w.n = 0;
       maxblocks = 0;
     };
     for (size_t q = 0; q < nreq; ++q) {
       const FillReq& r = reqs[q];
-      if (d >= r.P.dm || !r.pmask[d]) continue;
-      if (slab[q] && d == r.P.dm - 1) continue;
+      int mine = 0;
+      for (int d = 0; d < r.P.dm; ++d)
+        if (r.pmask[d] && !(slab[q] && d == r.P.dm - 1)) mine |= 1 << d;
+      if (mine != sig) continue;
       for (int c = 0; c < r.ncomp; ++c) {
         if (w.n == WRAP_MAX) flush();
         const int e = w.n++;
         w.a[e] = r.sfull.comp(r.scomp - 1 + c);
-        for (int t = 0; t < 3; ++t) { w.tb[e].lo[t] = w.a[e].lo[t]; w.tb[e].hi[t] = w.a[e].lo[t] + w.a[e].n[t] - 1; }
-        w.tb[e].lo[d] = 0;
-        w.tb[e].hi[d] = 2 * r.ng - 1;
-        w.lo[e] = r.lo[d];
-        w.hi[e] = r.hi[d];
         w.ng[e] = r.ng;
-        w.nodal[e] = r.has_nodal ? r.nodal[d] : 0;
-        maxblocks = std::max(maxblocks, nblocks(w.tb[e].npts(), 256));
+        long big = 0;
+        for (int d = 0; d < 3; ++d) {
+          w.lo[e][d] = r.lo[d];
+          w.hi[e][d] = r.hi[d];
+          w.nodal[e][d] = r.has_nodal ? r.nodal[d] : 0;
+        }
+        for (int reg = 0; reg < 3; ++reg) {  // the largest region decides the grid
+          if (!w.per[reg]) continue;
+          long npts = 2L * r.ng;
+          for (int d = 0; d < 3; ++d)
+            if (d != reg) npts *= w.a[e].n[d];
+          big = std::max(big, npts);
+        }
+        maxblocks = std::max(maxblocks, nblocks(big, 256));
       }
     }
     flush();
