@@ -57,6 +57,6 @@ void fused_edge2d_launch(const FusedArgs& a, int ppm_type, int nx, int ny, bool 
 // 0: always the literal kernel; 1 (default): the upwind-first kernel wherever it applies
 void fused_edge_set_variant(int v);
 void fused_edge2d_set_tile(int t);  // 2-D kernel tile: 0 32x8, 1 16x16, 2 32x16
-void fused_edge2_set_by(int by);  // rows per CTA of the upwind-first kernel: 8 or 16
+void fused_edge2_set_by(int by);  // tile of the upwind-first kernel: 1616 (16x16, default), 8 (32x8), 16 (32x16, plain inputs only)
 
 }  // namespace mgpu

@@ -727,7 +727,8 @@ __global__ void __launch_bounds__(BX* BY, (BX * BY >= 512 ? 1 : MGPU_FUSED2_MINB
 
 // z planes per CTA.  Every chunk repeats 4 pipeline steps (warm-up / drain), and the CTAs of a launch run in waves
 // over the resident slots (SMs x CTAs per SM): pick the chunk count whose last wave is fullest for the least
-// repeated work.  256^3, 32x8 tiles, 296 slots: 3 chunks of 86 planes = 1161 CTAs = 3.92 waves (was 8 chunks of 32:
+// repeated work.  256^3, 296 slots: 16x16 tiles -> 4 chunks of 64 planes = 1444 CTAs = 4.88 waves; 32x8 tiles -> 3
+// chunks of 86 planes = 1161 CTAs = 3.92 waves (the fixed 32-plane chunks before: 8 chunks,
 // 10.46 waves and 12 % repeated planes).
 int fused2_auto_kchunk(int ncols, int nz, int slots) {
   double best = 0.0;
