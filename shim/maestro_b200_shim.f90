@@ -65,6 +65,44 @@ module maestro_b200_shim
      type(c_ptr) function mgpu_last_error() bind(C, name="mgpu_last_error")
        import :: c_ptr
      end function mgpu_last_error
+     ! slab runs: rank 0 makes the NCCL id, every rank joins (INTEGRATION.md, section 2)
+     integer(c_int) function mgpu_comm_unique_id(id128) bind(C, name="mgpu_comm_unique_id")
+       import :: c_int, c_char
+       character(kind=c_char), intent(out) :: id128(128)
+     end function mgpu_comm_unique_id
+     integer(c_int) function mgpu_comm_init(rank, nranks, id128) bind(C, name="mgpu_comm_init")
+       import :: c_int, c_char
+       integer(c_int), value :: rank, nranks
+       character(kind=c_char), intent(in) :: id128(128)
+     end function mgpu_comm_init
+     integer(c_int) function mgpu_comm_finalize() bind(C, name="mgpu_comm_finalize")
+       import :: c_int
+     end function mgpu_comm_finalize
+     integer(c_int) function mgpu_set_option(key, value) bind(C, name="mgpu_set_option")
+       import :: c_int, c_char
+       character(kind=c_char), intent(in) :: key(*)   ! null-terminated, e.g. "overlap"//c_null_char
+       integer(c_int), value :: value
+     end function mgpu_set_option
+     ! device residency (params%mem_space = MGPU_DEVICE): device buffers of n doubles and copies
+     integer(c_int) function mgpu_malloc(dptr, n) bind(C, name="mgpu_malloc")
+       import :: c_int, c_long, c_ptr
+       type(c_ptr), intent(out) :: dptr
+       integer(c_long), value :: n
+     end function mgpu_malloc
+     integer(c_int) function mgpu_free(dptr) bind(C, name="mgpu_free")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: dptr
+     end function mgpu_free
+     integer(c_int) function mgpu_memcpy_h2d(dst, src, n) bind(C, name="mgpu_memcpy_h2d")
+       import :: c_int, c_long, c_ptr
+       type(c_ptr), value :: dst, src
+       integer(c_long), value :: n
+     end function mgpu_memcpy_h2d
+     integer(c_int) function mgpu_memcpy_d2h(dst, src, n) bind(C, name="mgpu_memcpy_d2h")
+       import :: c_int, c_long, c_ptr
+       type(c_ptr), value :: dst, src
+       integer(c_long), value :: n
+     end function mgpu_memcpy_d2h
      integer(c_int) function mgpu_host_register(hptr, n) bind(C, name="mgpu_host_register")
        import :: c_int, c_long, c_ptr
        type(c_ptr), value :: hptr
@@ -315,6 +353,8 @@ module maestro_b200_shim
   public :: mgpu_put_1d_array_on_cart_c, mgpu_make_w0mac_c, mgpu_make_s0mac_c, mgpu_addw0_sphr_c
   public :: mgpu_mk_rhoX_flux_sphr_c, mgpu_mk_rhoh_flux_sphr_c, mgpu_update_velocity_sphr_c
   public :: mgpu_mkutrans_sphr_c, mgpu_velpred_sphr_c, mgpu_modify_scal_force_sphr_c, mgpu_put_in_pert_form_sphr_c
+  public :: mgpu_comm_unique_id, mgpu_comm_init, mgpu_comm_finalize, mgpu_set_option
+  public :: mgpu_malloc, mgpu_free, mgpu_memcpy_h2d, mgpu_memcpy_d2h
   public :: mgpu_fill_geom, mgpu_estdt_c, mgpu_estdt_sphr_c, mgpu_make_etarho_planar_c
   public :: make_edge_scal_gpu
 
