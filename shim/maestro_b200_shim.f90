@@ -310,6 +310,214 @@ module maestro_b200_shim
        real(c_double), intent(in) :: s0(*)
      end function mgpu_put_in_pert_form_sphr_c
 
+     ! multifab_fill_boundary + multifab_physbc (multifab_physbc.f90:16)
+     integer(c_int) function mgpu_fill_boundary_c(p, s, scomp, bccomp, ncomp, adv_bc, pmask) &
+          bind(C, name="mgpu_fill_boundary")
+       import :: c_int, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_fab), intent(inout) :: s(*)
+       integer(c_int), value :: scomp
+       integer(c_int), value :: bccomp
+       integer(c_int), value :: ncomp
+       integer(c_int), intent(in) :: adv_bc(*)
+       integer(c_int), intent(in) :: pmask(*)
+     end function mgpu_fill_boundary_c
+
+     ! convert_rhoX_to_X.f90:20
+     integer(c_int) function mgpu_convert_rhoX_to_X_c(p, nfabs, s, flag) &
+          bind(C, name="mgpu_convert_rhoX_to_X")
+       import :: c_int, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(inout) :: s(*)
+       integer(c_int), value :: flag
+     end function mgpu_convert_rhoX_to_X_c
+
+     ! modify_scal_force.f90:15
+     integer(c_int) function mgpu_modify_scal_force_c(p, nfabs, force, s, umac, s0, s0_edge, w0, comp, &
+          fullform) &
+          bind(C, name="mgpu_modify_scal_force")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(inout) :: force(*)
+       type(mgpu_fab), intent(in) :: s(*)
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: s0(*)
+       real(c_double), intent(in) :: s0_edge(*)
+       real(c_double), intent(in) :: w0(*)
+       integer(c_int), value :: comp
+       integer(c_int), value :: fullform
+     end function mgpu_modify_scal_force_c
+
+     ! put_in_pert_form.f90:22
+     integer(c_int) function mgpu_put_in_pert_form_c(p, nfabs, s, base, comp, flag) &
+          bind(C, name="mgpu_put_in_pert_form")
+       import :: c_int, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(inout) :: s(*)
+       real(c_double), intent(in) :: base(*)
+       integer(c_int), value :: comp
+       integer(c_int), value :: flag
+     end function mgpu_put_in_pert_form_c
+
+     ! mkscalforce.f90:31
+     integer(c_int) function mgpu_mkrhohforce_c(p, nfabs, scal_force, is_prediction, thermal, umac, p0_1, p0_2, &
+          rho0_1, rho0_2, grav, psi, add_thermal) &
+          bind(C, name="mgpu_mkrhohforce")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(inout) :: scal_force(*)
+       integer(c_int), value :: is_prediction
+       type(mgpu_fab), intent(in) :: thermal(*)
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: p0_1(*)
+       real(c_double), intent(in) :: p0_2(*)
+       real(c_double), intent(in) :: rho0_1(*)
+       real(c_double), intent(in) :: rho0_2(*)
+       real(c_double), intent(in) :: grav(*)
+       real(c_double), intent(in) :: psi(*)
+       integer(c_int), value :: add_thermal
+     end function mgpu_mkrhohforce_c
+
+     ! mkforce.f90:22
+     integer(c_int) function mgpu_mk_vel_force_c(p, nfabs, vel_force, is_final_update, uold, uedge, w0, gpi, s, &
+          index_rho, rho0, grav, w0_force, do_add_utilde_force) &
+          bind(C, name="mgpu_mk_vel_force")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(inout) :: vel_force(*)
+       integer(c_int), value :: is_final_update
+       type(mgpu_fab), intent(in) :: uold(*)
+       type(c_ptr), intent(in) :: uedge(*)
+       real(c_double), intent(in) :: w0(*)
+       type(mgpu_fab), intent(in) :: gpi(*)
+       type(mgpu_fab), intent(in) :: s(*)
+       integer(c_int), value :: index_rho
+       real(c_double), intent(in) :: rho0(*)
+       real(c_double), intent(in) :: grav(*)
+       real(c_double), intent(in) :: w0_force(*)
+       integer(c_int), value :: do_add_utilde_force
+     end function mgpu_mk_vel_force_c
+
+     ! density_advance.f90:20, the whole episode on the device
+     integer(c_int) function mgpu_density_advance_c(p, which_step, sold, snew, sedge, sflux, scal_force, umac, &
+          w0, etarhoflux, rho0_old, rho0_new, p0_dummy, rho0_predicted_edge, adv_bc, pmask) &
+          bind(C, name="mgpu_density_advance")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: which_step
+       type(mgpu_fab), intent(inout) :: sold(*)
+       type(mgpu_fab), intent(inout) :: snew(*)
+       type(c_ptr), intent(in) :: sedge(*)
+       type(c_ptr), intent(in) :: sflux(*)
+       type(mgpu_fab), intent(inout) :: scal_force(*)
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: w0(*)
+       type(mgpu_fab), intent(inout) :: etarhoflux(*)
+       real(c_double), intent(in) :: rho0_old(*)
+       real(c_double), intent(in) :: rho0_new(*)
+       real(c_double), intent(in) :: p0_dummy(*)
+       real(c_double), intent(in) :: rho0_predicted_edge(*)
+       integer(c_int), intent(in) :: adv_bc(*)
+       integer(c_int), intent(in) :: pmask(*)
+     end function mgpu_density_advance_c
+
+     ! density_advance.f90:20, spherical
+     integer(c_int) function mgpu_density_advance_sphr_c(p, g, which_step, sold, snew, sedge, sflux, &
+          scal_force, umac, w0, w0mac, rho0_old, rho0_new, adv_bc, pmask) &
+          bind(C, name="mgpu_density_advance_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: which_step
+       type(mgpu_fab), intent(inout) :: sold(*)
+       type(mgpu_fab), intent(inout) :: snew(*)
+       type(c_ptr), intent(in) :: sedge(*)
+       type(c_ptr), intent(in) :: sflux(*)
+       type(mgpu_fab), intent(inout) :: scal_force(*)
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: w0(*)
+       type(c_ptr), intent(in) :: w0mac(*)
+       real(c_double), intent(in) :: rho0_old(*)
+       real(c_double), intent(in) :: rho0_new(*)
+       integer(c_int), intent(in) :: adv_bc(*)
+       integer(c_int), intent(in) :: pmask(*)
+     end function mgpu_density_advance_sphr_c
+
+     ! enthalpy_advance.f90:16
+     integer(c_int) function mgpu_enthalpy_advance_c(p, which_step, sold, snew, sedge, sflux, scal_force, &
+          thermal, umac, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old, grav_nph, &
+          adv_bc, pmask) &
+          bind(C, name="mgpu_enthalpy_advance")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: which_step
+       type(mgpu_fab), intent(inout) :: sold(*)
+       type(mgpu_fab), intent(inout) :: snew(*)
+       type(c_ptr), intent(in) :: sedge(*)
+       type(c_ptr), intent(in) :: sflux(*)
+       type(mgpu_fab), intent(inout) :: scal_force(*)
+       type(mgpu_fab), intent(in) :: thermal(*)
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: w0(*)
+       real(c_double), intent(in) :: rho0_old(*)
+       real(c_double), intent(in) :: rhoh0_old(*)
+       real(c_double), intent(in) :: rho0_new(*)
+       real(c_double), intent(in) :: rhoh0_new(*)
+       real(c_double), intent(in) :: p0_old(*)
+       real(c_double), intent(in) :: p0_new(*)
+       real(c_double), intent(in) :: psi(*)
+       real(c_double), intent(in) :: grav_old(*)
+       real(c_double), intent(in) :: grav_nph(*)
+       integer(c_int), intent(in) :: adv_bc(*)
+       integer(c_int), intent(in) :: pmask(*)
+     end function mgpu_enthalpy_advance_c
+
+     ! velocity_advance.f90:16
+     integer(c_int) function mgpu_velocity_advance_c(p, uold, unew, sold, rhohalf, umac, gpi, w0, w0_force, &
+          rho0_old, rho0_nph, grav_cell_old, grav_cell_nph, sponge, adv_bc, pmask) &
+          bind(C, name="mgpu_velocity_advance")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_fab), intent(in) :: uold(*)
+       type(mgpu_fab), intent(inout) :: unew(*)
+       type(mgpu_fab), intent(in) :: sold(*)
+       type(mgpu_fab), intent(in) :: rhohalf(*)
+       type(c_ptr), intent(in) :: umac(*)
+       type(mgpu_fab), intent(in) :: gpi(*)
+       real(c_double), intent(in) :: w0(*)
+       real(c_double), intent(in) :: w0_force(*)
+       real(c_double), intent(in) :: rho0_old(*)
+       real(c_double), intent(in) :: rho0_nph(*)
+       real(c_double), intent(in) :: grav_cell_old(*)
+       real(c_double), intent(in) :: grav_cell_nph(*)
+       type(mgpu_fab), intent(in) :: sponge(*)
+       integer(c_int), intent(in) :: adv_bc(*)
+       integer(c_int), intent(in) :: pmask(*)
+     end function mgpu_velocity_advance_c
+
+     ! advance_premac.f90:21
+     integer(c_int) function mgpu_advance_premac_c(p, uold, sold, umac, gpi, w0, w0_force, rho0_old, &
+          grav_cell_old, adv_bc, phys_bc, pmask) &
+          bind(C, name="mgpu_advance_premac")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_fab), intent(in) :: uold(*)
+       type(mgpu_fab), intent(in) :: sold(*)
+       type(c_ptr), intent(in) :: umac(*)
+       type(mgpu_fab), intent(in) :: gpi(*)
+       real(c_double), intent(in) :: w0(*)
+       real(c_double), intent(in) :: w0_force(*)
+       real(c_double), intent(in) :: rho0_old(*)
+       real(c_double), intent(in) :: grav_cell_old(*)
+       integer(c_int), intent(in) :: adv_bc(*)
+       integer(c_int), intent(in) :: phys_bc(*)
+       integer(c_int), intent(in) :: pmask(*)
+     end function mgpu_advance_premac_c
      ! estdt (Source/estdt.f90:29) for one level: force is the multifab mk_vel_force filled (:117-120)
      integer(c_int) function mgpu_estdt_c(p, nfabs, u, s, force, divU, dSdt, w0, p0, gamma1bar, rho_min, cflfac, &
           dt, umax) bind(C, name="mgpu_estdt")
@@ -353,6 +561,8 @@ module maestro_b200_shim
   public :: mgpu_put_1d_array_on_cart_c, mgpu_make_w0mac_c, mgpu_make_s0mac_c, mgpu_addw0_sphr_c
   public :: mgpu_mk_rhoX_flux_sphr_c, mgpu_mk_rhoh_flux_sphr_c, mgpu_update_velocity_sphr_c
   public :: mgpu_mkutrans_sphr_c, mgpu_velpred_sphr_c, mgpu_modify_scal_force_sphr_c, mgpu_put_in_pert_form_sphr_c
+  public :: mgpu_fill_boundary_c, mgpu_convert_rhoX_to_X_c, mgpu_modify_scal_force_c, mgpu_put_in_pert_form_c, mgpu_mkrhohforce_c, mgpu_mk_vel_force_c
+  public :: mgpu_density_advance_c, mgpu_density_advance_sphr_c, mgpu_enthalpy_advance_c, mgpu_velocity_advance_c, mgpu_advance_premac_c
   public :: mgpu_comm_unique_id, mgpu_comm_init, mgpu_comm_finalize, mgpu_set_option
   public :: mgpu_malloc, mgpu_free, mgpu_memcpy_h2d, mgpu_memcpy_d2h
   public :: mgpu_fill_geom, mgpu_estdt_c, mgpu_estdt_sphr_c, mgpu_make_etarho_planar_c

@@ -35,7 +35,8 @@ def test_struct_layout_matches_c(tmp_path):
 
     src = tmp_path / "layout.c"
     fields = {"mgpu_fab": [f[0] for f in abi.mgpu_fab._fields_], "mgpu_params": [f[0] for f in abi.mgpu_params._fields_],
-              "mgpu_halo_plan": [f[0] for f in abi.mgpu_halo_plan._fields_]}
+              "mgpu_halo_plan": [f[0] for f in abi.mgpu_halo_plan._fields_],
+              "mgpu_geom": [f[0] for f in abi.mgpu_geom._fields_]}
     body = ['#include <stdio.h>', '#include <stddef.h>', '#include "maestro_b200.h"', 'int main(void) {']
     for st, fs in fields.items():
         body.append('printf("%s %%zu\\n", sizeof(%s));' % (st, st))
@@ -51,6 +52,21 @@ def test_struct_layout_matches_c(tmp_path):
         assert C.sizeof(cls) == int(out[st]), st
         for f in fs:
             assert getattr(cls, f).offset == int(out["%s.%s" % (st, f)]), (st, f)
+
+
+def test_fortran_shim_binds_only_declared_symbols():
+    """every bind(C, name="...") of shim/maestro_b200_shim.f90 is an entry point the header declares (and the library
+    exports), and every operator entry point of the header has a binding in the shim"""
+    txt = open(os.path.join(ROOT, "shim", "maestro_b200_shim.f90")).read()
+    bound = set(re.findall(r'bind\(C,\s*name="(mgpu_[A-Za-z0-9_]+)"\)', txt))
+    declared = set(header_symbols())
+    assert bound, "no bindings found"
+    assert bound <= declared, sorted(bound - declared)
+    # operators (not the test / profiling helpers) must all be reachable from Fortran
+    helpers = {s for s in declared if any(k in s for k in ("profile", "launch_count", "copy_bytes", "version", "stream",
+                                                           "halo_plan", "synchronize", "host_unregister"))}
+    missing = declared - bound - helpers
+    assert not missing, sorted(missing)
 
 
 def test_no_cpu_fallback():
