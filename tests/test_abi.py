@@ -69,6 +69,33 @@ def test_fortran_shim_binds_only_declared_symbols():
     assert not missing, sorted(missing)
 
 
+def test_fortran_shim_struct_mirrors_match():
+    """the bind(C) derived types of the shim list the same fields, in the same order and with the same kinds and
+    extents, as the C structs (through the ctypes mirror, itself checked against gcc's layout above)"""
+    txt = open(os.path.join(ROOT, "shim", "maestro_b200_shim.f90")).read()
+    kinds = {"integer(c_int)": C.c_int, "real(c_double)": C.c_double, "type(c_ptr)": None}
+    for st in ("mgpu_fab", "mgpu_params", "mgpu_geom"):
+        body = re.search(r"type, bind\(C\), public :: %s\n(.*?)end type %s" % (st, st), txt, flags=re.S).group(1)
+        got = []
+        for line in body.splitlines():
+            line = line.split("!")[0].strip()
+            if not line:
+                continue
+            kind, names = [x.strip() for x in line.split("::")]
+            for nm in re.findall(r"([A-Za-z_0-9]+)(?:\((\d+)\))?", names):
+                got.append((nm[0], kind, int(nm[1]) if nm[1] else 1))
+        want = getattr(abi, st)._fields_
+        assert [g[0] for g in got] == [w[0] for w in want], st
+        for (name, kind, ext), (wname, wtype) in zip(got, want):
+            n = getattr(wtype, "_length_", 1)
+            base = getattr(wtype, "_type_", wtype) if n > 1 else wtype
+            assert ext == n, (st, name)
+            if kinds[kind] is None:
+                assert C.sizeof(base) == C.sizeof(C.c_void_p), (st, name)
+            else:
+                assert base is kinds[kind], (st, name)
+
+
 def test_no_cpu_fallback():
     import torch
 
