@@ -196,3 +196,72 @@ def make_estdt_inputs(dm, n, seed=97, speed=1.0, force_amp=1.0, divu_amp=1.0, ds
     gamma1bar = 1.4 + 0.2 * np.cos(2 * np.pi * zc)
     return dict(p=p, lo=lo, hi=hi, dm=dm, u=u, s=s, force=force, divU=divU, dSdt=dSdt, w0=w0, p0=p0,
                 gamma1bar=gamma1bar)
+
+
+def python_test_advect(ops, dm, n, ppm_type, direction, cfl=0.7, stop_time=1.0, device=None, fill_ops=None):
+    """The reference's unit test Exec/UNIT_TESTS/test_advect/varden.f90:16 driven through the operator interface:
+    Gaussian density (test_advect.f90:58), unit velocity along `direction` (+-1, +-2, +-3), dt = cfl dx, repeated
+    density_advance until stop_time, then |rho_final - rho_init|_2 and the relative norm (varden.f90:509-524).
+    Returns (abs_norm, rel_norm, rho_final valid cells as numpy).  `ops` runs the episodes (device fabs when
+    `device` is given); `fill_ops` fills the initial ghost cells (defaults to ops)."""
+    import math
+
+    p = make_params(dm, n=[n] * dm + [1] * (3 - dm), ppm_type=ppm_type)
+    lo, hi = [0, 0, 0], [n - 1 if d < dm else 0 for d in range(3)]
+    adv_bc = make_adv_bc(p, [[abi.PERIODIC, abi.PERIODIC]] * dm)
+    pmask = [1] * dm + [0] * (3 - dm)
+    W = float(np.float32(0.05))  # test_advect.f90:11: a dp parameter initialised from a single-precision literal
+    x = (np.arange(n) + 0.5) * p.dx[0]
+    if dm == 3:
+        d2 = (x[None, None, :] - 0.5) ** 2 + (x[None, :, None] - 0.5) ** 2 + (x[:, None, None] - 0.5) ** 2
+    else:
+        d2 = ((x[None, :] - 0.5) ** 2 + (x[:, None] - 0.5) ** 2)[None]
+    dist = np.sqrt(d2)
+    # libm's exp, element by element: numpy's vectorised exp differs from it in the last bit for some arguments
+    arg = -(dist * dist) / (W * W)
+    rho = np.array([math.exp(v) for v in arg.ravel().tolist()]).reshape(arg.shape)
+    rho = np.maximum(rho, p.base_cutoff_density)
+    sold = Fab(lo, hi, 4, p.nscal, dm=dm)
+    sold.valid()[p.rho_comp - 1] = rho
+    sold.valid()[p.spec_comp - 1] = rho
+    (fill_ops or ops).fill_boundary(p, sold, p.rho_comp, dm + p.rho_comp, p.nscal, adv_bc, pmask)
+    dens_orig = sold.valid()[p.rho_comp - 1].copy()
+    umac = face_fabs(lo, hi, 1, 1, dm)
+    idim = abs(direction) - 1
+    for d, u in enumerate(umac):
+        u.a[...] = (1.0 if direction > 0 else -1.0) if d == idim else 0.0
+    snew = Fab(lo, hi, 4, p.nscal, dm=dm)
+    force = Fab(lo, hi, 1, p.nscal, dm=dm)
+    sedge = face_fabs(lo, hi, 0, p.nscal, dm)
+    sflux = face_fabs(lo, hi, 0, p.nscal, dm)
+    nod = [0] * 3
+    nod[dm - 1] = 1
+    eta = Fab(lo, hi, 0, 1, nodal=nod, dm=dm)
+    if device is not None:
+        sold, snew, force, eta = sold.to(device), snew.to(device), force.to(device), eta.to(device)
+        umac, sedge, sflux = [u.to(device) for u in umac], [f.to(device) for f in sedge], [f.to(device) for f in sflux]
+        p.mem_space = abi.DEVICE
+    zc, ze = np.zeros(n), np.zeros(n + 1)
+    dt = cfl * p.dx[0] / 1.0
+    t = 0.0
+    try:
+        while t < stop_time:
+            p.dt = dt
+            ops.density_advance(p, 1, sold, snew, sedge, sflux, force, umac, ze, eta, zc, zc, zc, ze, adv_bc, pmask)
+            if device is None:
+                sold.a[...] = snew.a
+            else:
+                sold.a.copy_(snew.a)
+            t = t + dt
+            if t + dt > stop_time:
+                dt = stop_time - t
+    finally:
+        p.mem_space = abi.HOST
+    final = snew.valid()[p.rho_comp - 1]
+    final = final if device is None else final.cpu().numpy()
+    e = (final - dens_orig).ravel()
+    sa = sr = 0.0
+    for v, r0 in zip(e.tolist(), dens_orig.ravel().tolist()):  # the reference's summation order
+        sa += v * v
+        sr += (v / r0) * (v / r0)
+    return math.sqrt(sa), math.sqrt(sr), np.array(final)

@@ -645,3 +645,23 @@ def test_reductions_bounds_checked_build_agrees(oracle, dm, n):
         sargs = (st["p"], g, e["u"], e["s"], e["force"], e["divU"], e["dSdt"], st["w0mac"], st["rad"]["w0"],
                  10.0 * np.exp(-rc / 0.4), 1.4 + 0.2 * np.cos(2 * np.pi * rc), 0.7, 1e30)
         assert oracle.estdt_sphr(*sargs) == dbg.estdt_sphr(*sargs)
+
+
+@pytest.mark.parametrize("dm,n,ppm_type,direction,stop", [(2, 32, 1, 1, 0.3), (2, 24, 2, -2, 0.2), (3, 12, 0, 3, 0.2)])
+def test_python_driven_test_advect_is_the_oracle_driver(oracle, dm, n, ppm_type, direction, stop):
+    """tests/synth.python_test_advect (the reference's unit test varden.f90 through the operator interface, the loop
+    the GPU test runs) gives bit for bit what the oracle's own restatement of the driver (mo_test_advect) gives."""
+    from synth import python_test_advect
+
+    a, r, rho = python_test_advect(oracle, dm, n, ppm_type, direction, stop_time=stop)
+    a0, r0, rho0 = oracle_lib.test_advect(oracle, dm, n, ppm_type, 0, direction, stop_time=stop, want_rho=True)
+    assert np.array_equal(rho.reshape(rho0.shape), rho0)
+    assert a == a0 and r == r0
+
+
+def test_python_driven_test_advect_reproduces_a_golden_case(oracle):
+    from synth import python_test_advect
+
+    c = GOLD["cases"]["dm2_n64_ppm1_dir+1"]
+    a, r, _ = python_test_advect(oracle, c["dm"], c["n"], c["ppm_type"], c["dir"], stop_time=c["stop_time"])
+    assert abs(a - c["abs"]) <= 1e-13 * c["abs"] and abs(r - c["rel"]) <= 1e-13 * c["rel"]

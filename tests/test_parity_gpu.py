@@ -897,3 +897,26 @@ def test_estdt_sphr(gpu_ops, oracle, n, active, w0_interp_type):
     got = gpu_ops.estdt_sphr(*args)
     assert got == want, (got, want)
     assert np.isfinite(got[0]) and got[0] > 0.0
+
+
+# ---- the reference's own unit test through the CUDA path ------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["dm2_n64_ppm0_dir-2", "dm2_n64_ppm1_dir+1", "dm2_n64_ppm2_dir+1", "dm3_n24_ppm1_dir-3"])
+def test_reference_unit_test_through_the_cuda_path(gpu_ops, oracle, key):
+    """Exec/UNIT_TESTS/test_advect/varden.f90 (Gaussian advected by a unit velocity, repeated density_advance with host
+    multifabs, error norms at the end) with the CUDA library doing every step, exact build: the final density is bit
+    for bit the oracle driver's, and the norms are the committed golden values (tests/golden/test_advect_norms.json)."""
+    import json
+    import os
+
+    import oracle_lib
+    from synth import python_test_advect
+
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "test_advect_norms.json")))
+    c = gold["cases"][key]
+    a, r, rho = python_test_advect(gpu_ops, c["dm"], c["n"], c["ppm_type"], c["dir"], stop_time=c["stop_time"])
+    a0, r0, rho0 = oracle_lib.test_advect(oracle, c["dm"], c["n"], c["ppm_type"], 0, c["dir"], stop_time=c["stop_time"],
+                                          want_rho=True)
+    assert np.array_equal(rho.reshape(rho0.shape), rho0)
+    assert a == a0 and r == r0
+    assert abs(a - c["abs"]) <= 1e-13 * c["abs"] and abs(r - c["rel"]) <= 1e-13 * c["rel"]
