@@ -14,6 +14,11 @@ void density_advance_box(const mgpu_params& P, int which_step, Arr& sold, Arr& s
                          const int* hi, int ng_s, int ng_f, const int* adv_bc, const int* pmask);
 void test_advect_run(int dm, int n, int ppm_type, int bds_type, int itest_dir, double cflfac, double stop_time,
                      double* abs_norm, double* rel_norm, double* rho_final_out);
+void test_advect_run_ex(int dm, int n, int ppm_type, int bds_type, int itest_dir, double cflfac, double stop_time,
+                        const double* opt, double* abs_norm, double* rel_norm, double* rho_final_out,
+                        double* rho_init_out);
+extern bool g_ppm1_no_edge_clip;
+extern int g_ppm1_variant;
 }  // namespace mo
 
 using namespace mo;
@@ -324,6 +329,17 @@ int mo_test_advect(int dm, int n, int ppm_type, int bds_type, int itest_dir, dou
                    double* abs_norm, double* rel_norm, double* rho_final) {
   MO_TRY
   test_advect_run(dm, n, ppm_type, bds_type, itest_dir, cflfac, stop_time, abs_norm, rel_norm, rho_final);
+  MO_CATCH
+}
+
+void mo_set_ppm1_no_edge_clip(int on) { mo::g_ppm1_no_edge_clip = on != 0; }
+void mo_set_ppm1_variant(int v) { mo::g_ppm1_variant = v; }
+
+int mo_test_advect_ex(int dm, int n, int ppm_type, int bds_type, int itest_dir, double cflfac, double stop_time,
+                      const double* opt, double* abs_norm, double* rel_norm, double* rho_final, double* rho_init) {
+  MO_TRY
+  test_advect_run_ex(dm, n, ppm_type, bds_type, itest_dir, cflfac, stop_time, opt, abs_norm, rel_norm, rho_final,
+                     rho_init);
   MO_CATCH
 }
 

@@ -129,16 +129,30 @@ void density_advance_box(const mgpu_params& P, int which_step, Arr& sold, Arr& s
 // Exec/UNIT_TESTS/test_advect: n^dm periodic unit box, Gaussian density, unit velocity along one axis,
 // dt = cfl*dx, density_advance(which_step=1) repeated to stop_time.  Returns |rho_f - rho_i|_2 and
 // |(rho_f - rho_i)/rho_i|_2 as plain sqrt(sum of squares) over valid cells (FBoxLib multifab_norm_l2).
+// opt (all optional, used by oracle/pin_sweep.py to look for the archived report's configuration):
+//   opt[0] W  gaussian width (<= 0: the reference's single-precision 0.05)      opt[1] floor of the initial density
+//   (< 0: none)   opt[2] base_cutoff_density   opt[3] species_pred_type   opt[4] 1: keep dt fixed on the last step
+//   opt[5] slope_order
+void test_advect_run_ex(int dm, int n, int ppm_type, int bds_type, int itest_dir, double cflfac, double stop_time,
+                        const double* opt, double* abs_norm, double* rel_norm, double* rho_final_out,
+                        double* rho_init_out);
 void test_advect_run(int dm, int n, int ppm_type, int bds_type, int itest_dir, double cflfac, double stop_time,
                      double* abs_norm, double* rel_norm, double* rho_final_out) {
+  const double opt[6] = {-1.0, 1.e-10, 1.e-10, (double)MGPU_PREDICT_RHOPRIME_AND_X, 0.0, 4.0};
+  test_advect_run_ex(dm, n, ppm_type, bds_type, itest_dir, cflfac, stop_time, opt, abs_norm, rel_norm, rho_final_out,
+                     nullptr);
+}
+void test_advect_run_ex(int dm, int n, int ppm_type, int bds_type, int itest_dir, double cflfac, double stop_time,
+                        const double* opt, double* abs_norm, double* rel_norm, double* rho_final_out,
+                        double* rho_init_out) {
   mgpu_params P;
   memset(&P, 0, sizeof(P));
   P.dm = dm;
   P.ppm_type = ppm_type;
   P.bds_type = bds_type;
-  P.slope_order = 4;
+  P.slope_order = (int)opt[5];
   P.ppm_trace_forces = 0;
-  P.species_pred_type = MGPU_PREDICT_RHOPRIME_AND_X;
+  P.species_pred_type = (int)opt[3];
   P.enthalpy_pred_type = MGPU_PREDICT_RHOHPRIME;
   P.spherical = 0;
   P.evolve_base_state = 1;
@@ -147,7 +161,7 @@ void test_advect_run(int dm, int n, int ppm_type, int bds_type, int itest_dir, d
   P.rho_comp = 1; P.rhoh_comp = 2; P.spec_comp = 3; P.temp_comp = 6; P.pi_comp = 7; P.trac_comp = 8;
   P.nscal = 8;
   P.rel_eps = 0.0;  // never set in test_advect (estdt is not called): static zero
-  P.base_cutoff_density = 1.e-10;
+  P.base_cutoff_density = opt[2];
   P.nr = n;
   int lo[3] = {0, 0, 0}, hi[3] = {n - 1, n - 1, dm == 3 ? n - 1 : 0};
   for (int d = 0; d < 3; ++d) { P.domlo[d] = lo[d]; P.domhi[d] = hi[d]; P.dx[d] = 1.0 / n; }
@@ -178,7 +192,7 @@ void test_advect_run(int dm, int n, int ppm_type, int bds_type, int itest_dir, d
   std::vector<double> rho0_old(n, 0.0), rho0_new(n, 0.0), w0(n + 1, 0.0), rho0_pe(n + 1, 0.0);
 
   // test_advect.f90:11 -- W is declared dp but initialised from the single-precision literal 0.05
-  const double W = (double)0.05f;
+  const double W = opt[0] > 0.0 ? opt[0] : (double)0.05f;
   Box vb = grown(lo, hi, dm, 0);
   for_box(vb, [&](int i, int j, int k) {
     double x = ((double)i + 0.5) * P.dx[0], y = ((double)j + 0.5) * P.dx[1];
@@ -190,7 +204,8 @@ void test_advect_run(int dm, int n, int ppm_type, int bds_type, int itest_dir, d
     } else {
       dist = std::sqrt((x - xc) * (x - xc) + (y - yc) * (y - yc));
     }
-    double rho = dmax(std::exp(-(dist * dist) / (W * W)), P.base_cutoff_density);
+    double rho = std::exp(-(dist * dist) / (W * W));
+    if (opt[1] >= 0.0) rho = dmax(rho, opt[1]);
     sold(i, j, k, P.rho_comp - 1) = rho;
     sold(i, j, k, P.spec_comp - 1) = rho;
   });
@@ -206,7 +221,7 @@ void test_advect_run(int dm, int n, int ppm_type, int bds_type, int itest_dir, d
                         rho0_new.data(), rho0_pe.data(), lo, hi, ng_s, ng_f, adv_bc.data(), pmask);
     for (size_t q = 0; q < sold.size(); ++q) sold.p[q] = snew.p[q];
     t = t + dt;
-    if (t + dt > stop_time) dt = stop_time - t;
+    if (opt[4] == 0.0 && t + dt > stop_time) dt = stop_time - t;
   }
   double sa = 0.0, sr = 0.0;
   for (int k = vb.lo[2]; k <= vb.hi[2]; ++k)
@@ -217,6 +232,7 @@ void test_advect_run(int dm, int n, int ppm_type, int bds_type, int itest_dir, d
         double r = e / dens_orig(i, j, k);
         sr += r * r;
         if (rho_final_out) rho_final_out[dens_orig.idx(i, j, k)] = snew(i, j, k, P.rho_comp - 1);
+        if (rho_init_out) rho_init_out[dens_orig.idx(i, j, k)] = dens_orig(i, j, k);
       }
   *abs_norm = std::sqrt(sa);
   *rel_norm = std::sqrt(sr);

@@ -9,6 +9,11 @@
 #include "mo_kernels.h"
 
 namespace mo {
+// pin_sweep.py only: evaluate ppm_type 1 WITHOUT the "make sure sedge lies in between adjacent cell-centered values"
+// clip of ppm.f90:1723-1727 (the variant that reproduces the ppm_type 1 line of the archived report)
+bool g_ppm1_no_edge_clip = false;
+int g_ppm1_variant = 0;  // pin_sweep.py only: historical ppm_type 1 candidates (0 = the source in the tree)
+
 
 static const double C_CS = 1.25;  // ppm.f90:1656
 
@@ -139,6 +144,16 @@ void ppm(const Arr& s, const Arr* vel, Arr& Ip, Arr& Im, const int* lo, const in
       double sc = s(i, j, k);
       double& P = sp(i, j, k);
       double& M = sm(i, j, k);
+      if (g_ppm1_variant == 2) return;
+      if (g_ppm1_variant == 4) {  // Colella & Woodward 1984 eq. 1.10 as printed
+        if ((P - sc) * (sc - M) <= 0.0) { P = sc; M = sc; }
+        else {
+          const double dq = P - M, q6 = 6.0 * (sc - 0.5 * (M + P));
+          if (dq * q6 > dq * dq) M = 3.0 * sc - 2.0 * P;
+          else if (-(dq * dq) > dq * q6) P = 3.0 * sc - 2.0 * M;
+        }
+        return;
+      }
       if ((P - sc) * (sc - M) <= 0.0) {
         P = sc;
         M = sc;
@@ -160,12 +175,16 @@ void ppm(const Arr& s, const Arr* vel, Arr& Ip, Arr& Im, const int* lo, const in
         double dsl = 2.0 * (s(i, j, k) - s.at(i, j, k, d, -1));
         double dsr = 2.0 * (s.at(i, j, k, d, 1) - s(i, j, k));
         if (dsl * dsr > 0.0) dsvl(i, j, k) = sign1(dsc) * dmin(dmin(dabs(dsc), dabs(dsl)), dabs(dsr));
+        if (g_ppm1_variant == 1) dsvl(i, j, k) = dsc;
+        if (g_ppm1_variant == 3) dsvl(i, j, k) = (dsl * dsr > 0.0) ? sign1(dsc) * dmin(dmin(dabs(dsc), 0.5 * dabs(dsl)), 0.5 * dabs(dsr)) : 0.0;
       });
       for_box(eb, [&](int i, int j, int k) {  // ppm.f90:1713-1727
         double sl = s.at(i, j, k, d, -1), sc = s(i, j, k);
         double e = 0.5 * (sc + sl) - (1.0 / 6.0) * (dsvl(i, j, k) - dsvl.at(i, j, k, d, -1));
-        e = dmax(e, dmin(sc, sl));
-        e = dmin(e, dmax(sc, sl));
+        if (!g_ppm1_no_edge_clip) {
+          e = dmax(e, dmin(sc, sl));
+          e = dmin(e, dmax(sc, sl));
+        }
         sedge(i, j, k) = e;
       });
       for_box(tb, [&](int i, int j, int k) {  // ppm.f90:1731-1752

@@ -28,11 +28,19 @@ if "--full" in sys.argv:  # the reference's own configuration: 64^3, cfl 0.7, t 
 else:
     old = json.load(open(os.path.join(HERE, "test_advect_norms.json")))
     full = old.get("oracle_3d_64", {})
+old = json.load(open(os.path.join(HERE, "test_advect_norms.json")))
+maxnorm = old.get("oracle_3d_64_maxnorm", {})
+if "--full" in sys.argv:
+    import numpy as np
+    for t in (0, 1, 2):
+        ri, rf = oracle_lib.test_advect_fields(ops, 3, 64, t, 1)
+        maxnorm["ppm%d" % t] = float(np.abs(rf - ri).max())
 out = dict(
     cases=cases,
+    oracle_3d_64_maxnorm=maxnorm,
     oracle_3d_64=full,
     archived_3d_64=dict(ppm0=0.135411700899960, ppm1=0.105604113268602, ppm2=4.140496304475560e-2,
-                        source="Exec/UNIT_TESTS/test_advect/advect_3d_report_example.out (older driver; soft)"),
+                        source="Exec/UNIT_TESTS/test_advect/advect_3d_report_example.out: fcompare max-norm of rho_final - rho_init; ppm0 and ppm2 reproduced to 1e-10 (tests/test_oracle_cpu.py), ppm1 is from an older reconstruction"),
 )
 json.dump(out, open(os.path.join(HERE, "test_advect_norms.json"), "w"), indent=1, sort_keys=True)
 print("wrote", len(cases), "cases")
