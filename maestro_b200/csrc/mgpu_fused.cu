@@ -565,7 +565,7 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
   const bool xform = sdiv || ssub || wadd;
   if (xform && (exact || any_bc || g_variant == 0))
     throw Error("make_edge_scal: on-the-fly input transforms need the upwind-first kernel (internal error)");
-  const bool to_fused2 = !exact && (g_variant == 1 || (g_variant == 2 && !any_bc) || g_variant == 3);
+  const bool to_fused2 = !exact && (g_variant == 1 || (g_variant == 2 && !any_bc) || g_variant == 3 || g_variant == 4);
   if (a.kchunk < 0 && !to_fused2) a.kchunk = nz < 32 ? nz : 32;
   if (exact)
     fused_edge_launch_exact(a, P.ppm_type, any_bc, nx, ny, nz);
@@ -573,7 +573,8 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
     // (variant 1, the default: the upwind-first kernel for every FAST prediction -- since the warp-uniform slow-face
     //  branches it also wins for ppm_type 2 on boxes with physical boundaries, profiles/r01k_final.md; variant 2
     //  keeps the literal kernel on such boxes, variant 0 everywhere)
-    fused_edge2_launch(a, P.ppm_type, nx, ny, nz, any_bc);
+    if (g_variant != 4 && fused_edge3_supported(a, any_bc)) fused_edge3_launch(a, P.ppm_type, nx, ny, nz, any_bc);
+    else fused_edge2_launch(a, P.ppm_type, nx, ny, nz, any_bc);
   else
     fused_edge_launch_fast(a, P.ppm_type, any_bc, nx, ny, nz);
 }

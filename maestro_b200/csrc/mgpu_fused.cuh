@@ -29,6 +29,8 @@ struct FusedArgs {
   const double* ssub;
   const double* wadd;
   double dt, dx[3], rel_eps;
+  // dt/dx, dt/(6 dx), dt/(4 dx) and dt/2, filled by fused_edge3_launch: read as constant-bank operands, no registers
+  double td[3], c6[3], c4[3], dt2;
   DV s, force;  // single-component views
   DV umac[3];
   DV sedge[3];  // single-component views of the output
@@ -48,13 +50,17 @@ void fused_edge_launch_exact(const FusedArgs& a, int ppm_type, bool bc, int nx, 
 void fused_edge_launch_fast(const FusedArgs& a, int ppm_type, bool bc, int nx, int ny, int nz);
 // second design (mgpu_fused2.cu): upwind-first, FAST arithmetic only; bc: the box has physical boundaries
 void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc);
+// third design (mgpu_fused3.cu): the upwind-first algorithm with TMA-staged tiles and a register-renamed plane loop
+bool fused_edge3_supported(const FusedArgs& a, bool bc);
+void fused_edge3_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc);
 // 2-D (mgpu_fused2.cu, k_fused_edge2d): FAST arithmetic only, non-conservative, ppm_trace_forces = 0, no REFLECT_ODD
 bool fused_edge2d_supported(const mgpu_params& P, bool is_cons, const int* adv_bc, int bccomp, bool exact);
 void fused_edge2d_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
                       const int* lo, const int* hi, const int* adv_bc, int comp, int bccomp, bool is_vel, int ng_s,
                       int ng_f, bool force_zero = false);
 void fused_edge2d_launch(const FusedArgs& a, int ppm_type, int nx, int ny, bool bc);
-// 0: always the literal kernel; 1 (default): the upwind-first kernel wherever it applies
+// 0: always the literal kernel; 1 (default): the upwind-first kernels wherever they apply (the TMA design where its
+// stride rules hold, else the second design); 4: the second design only
 void fused_edge_set_variant(int v);
 void fused_edge2d_set_tile(int t);  // 2-D kernel tile: 0 32x8, 1 16x16, 2 32x16
 void fused_edge2_set_by(int by);  // tile of the upwind-first kernel: 1616 (16x16, default), 8 (32x8), 16 (32x16, plain inputs only)
