@@ -44,6 +44,7 @@ struct Smem3 {
   static constexpr int SN = TXW * TYW;                 // doubles per tile (the TMA box)
   static constexpr int SLOT = (SN + 15) / 16 * 16;     // slot pitch: a multiple of 128 B
   static constexpr int NS = H + 3;                     // tile slots
+  static constexpr int KCAP = 128;                     // capacity of the per-plane constant arrays (kchunk + 16 <= KCAP)
   static constexpr int P = BX;                         // pitch of every exchange plane
   static constexpr int PL = (BY + 1) * P;              // doubles per plane (one spare row: reads at row+1 stay inside)
   enum { AX0 = 0, AX1, AY0, AY1, TZ, GX, GY, XY, YX, XZ, YZ, TXA, TXB, TYA, TYB, NPL };
@@ -52,7 +53,7 @@ struct Smem3 {
   static constexpr int RS = NRING * PL;
   static constexpr int NTILE = NS * SLOT * (DIV ? 2 : 1);
   static constexpr int NPLANES = NPL + 4 * NRING;
-  static constexpr int BYTES = (NTILE + NPLANES * PL) * 8 + 64;  // + mbarriers
+  static constexpr int BYTES = (NTILE + NPLANES * PL) * 8 + 64 + 2 * KCAP * 8;  // + mbarriers + per-plane constants
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,10 +103,10 @@ __global__ void __launch_bounds__(BX* BY, 2)
   double* const dtiles = tiles + NS * SM::SLOT;
   double* const planes = tiles + SM::NTILE;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(planes + SM::NPLANES * SM::PL);
-  // per-plane constants of the on-the-fly transforms, staged once per CTA (kchunk + 16 doubles each):
+  // per-plane constants of the on-the-fly transforms, staged once per CTA (KCAP doubles each, kchunk + 16 <= KCAP):
   // sWadd[m] = wadd of z-face t0 + m, sSub[m] = ssub of plane t0 + m
   double* const sWadd = reinterpret_cast<double*>(bars + 8);
-  double* const sSub = sWadd + (a.kchunk + 16);
+  double* const sSub = sWadd + SM::KCAP;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * BX + tx;
   double* const pl = planes + ty * P + tx;       // this thread's cell in plane 0
   double* const rg = pl + SM::NPL * SM::PL;      // this thread's cell in ring slot 0, plane 0
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(BX* BY, 2)
     for (int n = 0; n <= H + 1; ++n) issue(t0 + n, n);
   }
   if constexpr (WADD || XF == 2) {
-    for (int m = tid; m < a.kchunk + 16; m += NT) {
+    for (int m = tid; m < SM::KCAP; m += NT) {
       if constexpr (WADD) sWadd[m] = gwadd[clampk(t0 + m, w_k0, w_k1)];
       if constexpr (XF == 2) sSub[m] = gsub[clampk(t0 + m, s_k0, s_k1)];
     }
@@ -690,9 +691,9 @@ void launch_fused3(const FusedArgs& a0, int nx, int ny, int nz) {
   static int slots = 0;
   auto kern = k_fused_edge3<PPM, BX, BY, XF, WADD, BC>;
   constexpr int bytes = SM::BYTES;
-  constexpr int KMAX = 1024;  // z planes per CTA at most (the per-plane constants are staged in shared memory)
+  constexpr int KMAX = SM::KCAP - 16;  // z planes per CTA at most (the per-plane constants are staged in shared memory)
   if (!configured) {
-    MGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 2 * (KMAX + 16) * 8));
+    MGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     int dev = 0, sms = 0, per_sm = 0;
     MGPU_CUDA(cudaGetDevice(&dev));
     MGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -710,7 +711,7 @@ void launch_fused3(const FusedArgs& a0, int nx, int ny, int nz) {
   const int gx = (nx + BX - 3) / (BX - 2), gy = (ny + BY - 3) / (BY - 2);
   if (a.kchunk <= 0) a.kchunk = fused3_auto_kchunk(gx * gy, nz, slots);
   if (a.kchunk > KMAX) a.kchunk = KMAX;
-  const int smem = bytes + ((WADD || XF == 2) ? 2 * (a.kchunk + 16) * 8 : 0);
+  const int smem = bytes;
   const CUtensorMap tm_s = make_tmap(a.s.p, a.s, SM::TXW, SM::TYW);
   const CUtensorMap tm_d = (XF == 1) ? make_tmap(a.sdiv, a.s, SM::TXW, SM::TYW) : tm_s;
   dim3 block(BX, BY, 1);

@@ -13,6 +13,9 @@ from maestro_b200 import abi, lib
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 ops = lib.init(0, use_torch_stream=True)
+for kv in sys.argv[3:]:
+    k, v = kv.split("=")
+    lib.set_option(k, int(v))
 st = bench.test_advect_state(n)
 st["p"].mem_space = abi.DEVICE
 e = bench.alloc_episode(st, "cuda:0")
