@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(BX* BY, 2)
   double dzc[4] = {0.0, 0.0, 0.0, 0.0};     // ZROT: age 0 = van Leer slope of cell t+1, age 1 = of cell t
   double ezc[4] = {0.0, 0.0, 0.0, 0.0};     // ZROT: age 0 = edge value on z-face t+1, age 1 = on z-face t
   double sw[2 * H + 1];                     // !ZROT: sw[m] = s(i,j,t-H+m) after the shift at the top of step t
+  double ez2[4] = {0.0, 0.0, 0.0, 0.0};     // ppm_type 2, no BC: limited edge value on z-face t+2-age
 #pragma unroll
   for (int m = 0; m <= 2 * H; ++m) sw[m] = 0.0;
   if constexpr (ZROT) {
@@ -239,6 +240,11 @@ __global__ void __launch_bounds__(BX* BY, 2)
   } else {
 #pragma unroll
     for (int m = 1; m <= 2 * H; ++m) sw[m] = gload_s(t0 - 1 - H + m);
+    if constexpr (PPM == 2 && !BC) {  // edge values on z-faces t0+1, t0, t0-1 (ages 1, 2, 3 of the first step)
+      ez2[3] = sedge2_of(&sw[H + 2], 1);  // s(t0+1) sits at sw[H+2] before the first shift
+      ez2[2] = sedge2_of(&sw[H + 1], 1);
+      ez2[1] = sedge2_of(&sw[H], 1);
+    }
   }
   // running offsets for the step t about to start: q_u/q_v -> plane t+1, q_w -> z-face t+1, q_f -> plane t-2
   int q_u = (int)a.umac[0].off(ic, jc, a.umac[0].lo[2]) + clampk(t0 + 1, u_k0, u_k1) * u_sz;
@@ -341,8 +347,16 @@ __global__ void __launch_bounds__(BX* BY, 2)
         s0 = sw[H];
         s1 = sw[H - 1];
         double p0, p1;
-        if constexpr (BC) cell_par_bc<PPM>(&sw[H], 1, t, a.slope_order, lbz, p0, p1);
-        else cell_par<PPM>(&sw[H], 1, a.slope_order, nb, p0, p1);
+        if constexpr (BC) {
+          cell_par_bc<PPM>(&sw[H], 1, t, a.slope_order, lbz, p0, p1);
+        } else if constexpr (PPM == 2) {
+          // the limiter of cell t reads the edge values on z-faces t-1 .. t+2: one new edge per step, three carried
+          ez2[AGE(0)] = sedge2_of(&sw[H + 2], 1);
+          cs_limit_fast(&sw[H], 1, [&](int o) { return o == -1 ? ez2[AGE(3)] : (o == 0 ? ez2[AGE(2)] : (o == 1 ? ez2[AGE(1)] : ez2[AGE(0)])); },
+                        p0, p1);
+        } else {
+          cell_par<PPM>(&sw[H], 1, a.slope_order, nb, p0, p1);
+        }
         pz0[AGE(0)] = p0;
         pz1[AGE(0)] = p1;
       }

@@ -62,6 +62,59 @@ __device__ __forceinline__ double edge_fast(double sl, double sr, double dl, dou
 #endif
 }
 
+// FAST form of the Colella 2008 limiter (cs_limit, ppm.f90:1905-1974): same branches and values, except that
+//   * the two one-sided blocks (|alphap| > 2 |alpham| / |alpham| > 2 |alphap|) are mutually exclusive, so one code path
+//     with the roles swapped serves both (one division and one square root instead of two of each when a warp diverges);
+//   * at an extremum both ends are scaled by ONE quotient D2LIM / D2ABS (the reference divides twice: last-bit difference).
+template <class EdgeFn>
+__device__ __forceinline__ void cs_limit_fast(const double* q, long st, EdgeFn E, double& sm, double& sp) {
+  const double sc = q[0], qm = q[-st], qp = q[st];
+  const double e0 = E(0), e1 = E(1);
+  double alphap = e1 - sc;
+  double alpham = e0 - sc;
+  const bool bigp = fabs(alphap) > 2.0 * fabs(alpham);
+  const bool bigm = fabs(alpham) > 2.0 * fabs(alphap);
+  bool extremum = false;
+  if (alpham * alphap >= 0.0) {
+    extremum = true;
+  } else if (bigp || bigm) {
+    const double dafacem = e0 - E(-1);
+    const double dafacep = E(2) - e1;
+    const double dabarm = sc - qm;
+    const double dabarp = qp - sc;
+    const bool face = dmin2(fabs(dafacem), fabs(dafacep)) >= dmin2(fabs(dabarm), fabs(dabarp));
+    const double dachkm = face ? dafacem : dabarm, dachkp = face ? dafacep : dabarp;
+    extremum = (dachkm * dachkp <= 0.0);
+  }
+  if (extremum) {
+    const double D2 = 6.0 * (alpham + alphap);
+    const double D2L = q[-2 * st] - 2.0 * qm + sc;
+    const double D2R = sc - 2.0 * qp + q[2 * st];
+    const double D2C = qm - 2.0 * sc + qp;
+    const double sgn = sign1(D2);
+    const double D2LIM =
+        dmax2(dmin2(dmin2(dmin2(sgn * D2, MGPU_CS_C * sgn * D2L), MGPU_CS_C * sgn * D2R), MGPU_CS_C * sgn * D2C), 0.0);
+    const double r = D2LIM / dmax2(fabs(D2), 1.e-10);
+    alpham = alpham * r;
+    alphap = alphap * r;
+  } else if (bigp || bigm) {
+    const double a_s = bigp ? alpham : alphap;  // the small end, kept
+    const double a_b = bigp ? alphap : alpham;  // the big end, limited
+    const double del = (bigp ? qm : qp) - sc;
+    const double sgn = sign1(a_s);
+    const double amax = -(a_b * a_b) / (4 * (alpham + alphap));
+    double nb = a_b;
+    if (sgn * amax >= sgn * del) {
+      if (sgn * (del - a_s) >= 1.e-10) nb = (-2.0 * del - 2.0 * sgn * sqrt(del * del - del * a_s));
+      else nb = -2.0 * a_s;
+    }
+    alphap = bigp ? nb : alphap;
+    alpham = bigp ? alpham : nb;
+  }
+  sm = sc + alpham;
+  sp = sc + alphap;
+}
+
 // limited parabola (PPM>=1: a0 = sm, a1 = sp) or slope (PPM==0: a0) of one cell along a line in memory
 template <int PPM>
 __device__ __forceinline__ void cell_par(const double* q, int st, int slope_order, const LineBC& nb, double& a0,
@@ -76,7 +129,7 @@ __device__ __forceinline__ void cell_par(const double* q, int st, int slope_orde
     a1 = edge_fast(c0, p1, d0, dp);
     cw_limit(c0, a0, a1);
   } else {
-    ppm2_cell(q, st, 0, nb, a0, a1);
+    cs_limit_fast(q, st, [&](int o) { return sedge2_of(q + o * st, st); }, a0, a1);
   }
 }
 
@@ -137,8 +190,18 @@ __device__ __forceinline__ void cell_par_bc(const double* q, int st, int c, int 
     a1 = 0.0;
   } else if constexpr (PPM == 1) {
     ppm1_cell(q, st, c, b, a0, a1);
-  } else {
-    ppm2_cell(q, st, c, b, a0, a1);
+  } else {  // ppm2_cell (mgpu_recon.cuh) with the FAST limiter
+    if (b.wlo && c == b.lo) {  // ppm.f90:1987, 2010
+      a0 = q[-st];
+      a1 = sedge_wall(q, st, +1);
+    } else if (b.whi && c == b.hi) {  // :2103, 2127
+      a1 = q[st];
+      a0 = sedge_wall(q, st, -1);
+    } else {
+      const bool eff = (b.wlo && c >= b.lo + 1 && c <= b.relimit_last) || (b.whi && c >= b.hi - 2 && c <= b.hi - 1);
+      if (eff) cs_limit_fast(q, st, [&](int o) { return sedge2_eff(q + o * st, st, c + o, b); }, a0, a1);
+      else cs_limit_fast(q, st, [&](int o) { return sedge2_of(q + o * st, st); }, a0, a1);
+    }
   }
 }
 
