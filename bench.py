@@ -91,43 +91,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def test_advect_state(n, device=None, seed=67890, rank=0, world=1):
-    """test_advect initial data + velocity set B/C of SURVEY 8d on this rank's n^3 slab of the periodic
-    n x n x (n*world) domain (world = 1: the n^3 unit box of the reference test)."""
-    from maestro_b200 import Fab, abi, face_fabs, make_adv_bc, make_params
+def build_workload(config, n, device, rank=0, world=1):
+    from maestro_b200 import workloads
 
-    p = make_params(3, n=[n, n, n * world], ppm_type=1)
-    p.base_cutoff_density = 1e-10
-    lo, hi = [0, 0, rank * n], [n - 1, n - 1, rank * n + n - 1]
-    W = float(np.float32(0.05))
-    x = (np.arange(-4, n + 4) + 0.5) / n
-    xp = ((x % 1.0) - 0.5) ** 2
-    r2 = xp[None, None, :] + xp[None, :, None] + xp[:, None, None]
-    rho = np.maximum(np.exp(-r2 / W ** 2), 1e-10)
-    sold = Fab(lo, hi, 4, p.nscal, dm=3)
-    sold.a[p.rho_comp - 1] = rho
-    sold.a[p.spec_comp - 1] = 0.6 * rho
-    sold.a[p.spec_comp] = 0.3 * rho
-    sold.a[p.spec_comp + 1] = 0.1 * rho
-    sold.a[p.trac_comp - 1] = np.sin(2 * np.pi * x)[None, None, :] * np.ones_like(rho)
-    rng = np.random.default_rng(seed)
-    umac = face_fabs(lo, hi, 1, 1, 3)
-    for d, u in enumerate(umac):
-        c = [(np.arange(-1, u.shape[3 - q] - 1) + (0.0 if q == d else 0.5)) / n for q in range(3)]
-        # the fields are 1-periodic, so every slab of the taller domain sees the same (globally periodic) data
-        X, Y, Z = c[0][None, None, :], c[1][None, :, None], c[2][:, None, None]
-        o = [X, Y, Z]
-        a, b = o[(d + 1) % 3], o[(d + 2) % 3]
-        u.a[0] = np.sin(2 * np.pi * b) + np.cos(2 * np.pi * a)
-        u.a[0] += rng.uniform(-0.1, 0.1, size=u.a[0].shape) * 0.0 + 0.05 * np.sin(2 * np.pi * 7 * (a + b))
-    umax = max(np.abs(u.a).max() for u in umac)
-    p.dt = 0.7 * p.dx[0] / umax
-    p.rel_eps = 1e-8 * umax
-    adv_bc = make_adv_bc(p, [[abi.PERIODIC, abi.PERIODIC]] * 3)
-    zero_c, zero_e = np.zeros(n * world), np.zeros(n * world + 1)
-    st = dict(p=p, lo=lo, hi=hi, sold=sold, umac=umac, adv_bc=adv_bc, pmask=[1, 1, 1],
-              base=dict(w0=zero_e, rho0_old=zero_c, rho0_new=zero_c, p0=zero_c, rho0_predicted_edge=zero_e))
-    return st
+    return workloads.BUILDERS[config](n=n or workloads.DEFAULT_N[config], device=device, rank=rank, world=world)
+
+
+# ---- the c2 state as plain dicts (tests/test_full_size_gpu.py drives the episode on rolled / modified inputs) ---------
+def test_advect_state(n, rank=0, world=1):
+    import numpy as np
+
+    w = build_workload("c2", n, None, rank=rank, world=world)
+    e, p = w.extra["e"], w.p
+    nz = n * world
+    zero_c, zero_e = np.zeros(nz), np.zeros(nz + 1)
+    return dict(p=p, lo=e["sold"].lo, hi=e["sold"].hi, sold=e["sold"], umac=e["umac"], adv_bc=w.extra["adv_bc"],
+                pmask=[1, 1, 1], base=dict(w0=zero_e, rho0_old=zero_c, rho0_new=zero_c, p0=zero_c,
+                                           rho0_predicted_edge=zero_e))
 
 
 def alloc_episode(st, device):
@@ -135,12 +115,10 @@ def alloc_episode(st, device):
     from maestro_b200 import Fab, face_fabs
 
     p, lo, hi = st["p"], st["lo"], st["hi"]
-    e = dict(sold=st["sold"].to(device), snew=Fab(lo, hi, 4, p.nscal, dm=3, device=device),
-             umac=[u.to(device) for u in st["umac"]], sedge=face_fabs(lo, hi, 0, p.nscal, 3, device=device),
-             sflux=face_fabs(lo, hi, 0, p.nscal, 3, device=device),
-             force=Fab(lo, hi, 1, p.nscal, dm=3, device=device),
-             eta=Fab(lo, hi, 0, 1, nodal=[0, 0, 1], dm=3, device=device))
-    return e
+    return dict(sold=st["sold"].to(device), snew=Fab(lo, hi, 4, p.nscal, dm=3, device=device),
+                umac=[u.to(device) for u in st["umac"]], sedge=face_fabs(lo, hi, 0, p.nscal, 3, device=device),
+                sflux=face_fabs(lo, hi, 0, p.nscal, 3, device=device), force=Fab(lo, hi, 1, p.nscal, dm=3, device=device),
+                eta=Fab(lo, hi, 0, 1, nodal=[0, 0, 1], dm=3, device=device))
 
 
 def run_episode(ops, st, e):
@@ -149,12 +127,8 @@ def run_episode(ops, st, e):
                         b["rho0_old"], b["rho0_new"], b["p0"], b["rho0_predicted_edge"], st["adv_bc"], st["pmask"])
 
 
-def ncomp_advanced(p):
-    return p.nspec + 1 + p.ntrac  # species + density + tracers are predicted to edges and updated
-
-
-def cpu_reference(n_sample, steps, warmup):
-    """restated reference algorithm (oracle) on the host cores over an n_sample^3 box of the workload"""
+def cpu_reference(config, n_sample, steps, warmup):
+    """restated reference algorithm (oracle) on the host cores over an n_sample box of the workload"""
     import ctypes
 
     import oracle_lib
@@ -163,16 +137,38 @@ def cpu_reference(n_sample, steps, warmup):
     # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
     gomp = ctypes.CDLL("libgomp.so.1", mode=ctypes.RTLD_GLOBAL)
     gomp.omp_set_num_threads(len(os.sched_getaffinity(0)))
-    st = test_advect_state(n_sample)
-    e = alloc_episode(st, None)
+    if config == "c5":  # built with torch on the host for the CPU arm
+        w = build_workload(config, n_sample, "cpu")
+        for f in [w.extra["e"][k] for k in ("sold", "snew", "force")] + sum((w.extra["e"][k] for k in ("umac", "w0mac", "sedge", "sflux")), []):
+            f.device, f.a = None, f.a.numpy()  # same memory, numpy view: the oracle takes host pointers
+    else:
+        w = build_workload(config, n_sample, None)
     for _ in range(warmup):
-        run_episode(oracle, st, e)
-    t0 = time.perf_counter()
+        w.reset()
+        w.step(oracle)
+    t = 0.0
     for _ in range(steps):
-        run_episode(oracle, st, e)
-    dt = (time.perf_counter() - t0) / steps
-    zu = n_sample ** 3 * ncomp_advanced(st["p"])
-    return zu / dt, dt
+        w.reset()
+        t0 = time.perf_counter()
+        w.step(oracle)
+        t += time.perf_counter() - t0
+    dt = t / steps
+    return w.zone_updates / dt, dt, w
+
+
+def per_zone_parity(ref, got):
+    """max over zones of |got - ref| / max(|ref|, floor), floor = 1e-10 x the field's max-norm, per output field"""
+    import torch
+
+    out = {}
+    for k in ref:
+        a, b = got[k].double(), ref[k].double()
+        fl = 1e-10 * float(b.abs().max())
+        if fl == 0.0:
+            out[k] = float((a - b).abs().max())
+            continue
+        out[k] = float(((a - b).abs() / torch.clamp(b.abs(), min=fl)).max())
+    return out
 
 
 def main():
@@ -181,10 +177,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="zones per side of the per-GPU box")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configuration (maestro_b200/workloads.py); c2 carries the headline metric")
+    ap.add_argument("--n", type=int, default=0, help="zones per side (default: the configuration's own size)")
     ap.add_argument("--e2e-steps", type=lambda v: max(1, int(v)), default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--opt", action="append", default=[], help="library option key=value (mgpu_set_option), e.g. fused_by=1616")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--selftest", action="store_true",
+                    help="multi-rank parity of the NCCL path against the single-box oracle instead of the timing run")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (mgpu_set_option), e.g. exact=1")
     args = ap.parse_args()
     if os.environ.get("BENCH_WATCHDOG"):  # debugging aid: dump every thread's Python stack if the run stalls
         import faulthandler
@@ -195,21 +196,35 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = len(os.sched_getaffinity(0)) or 1
     W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    from maestro_b200 import workloads
+
+    n = args.n or workloads.DEFAULT_N[args.config]
+    L2_NOTE = "256 MB flush between timed iterations"
+
+    def config_of(w, nworld):
+        multi = "single box"
+        if nworld > 1:
+            multi = ("one slab per rank (%s scaling), NCCL send/recv halo exchange in every ghost fill (timed)" % w.scaling)
+        c = dict(w.desc)
+        c.update({"l2": L2_NOTE, "multi_gpu": multi})
+        return c
 
     if args.impl == "reference":
         # the reference's own CPU implementation of the path cannot be built here (no Fortran compiler,
-        # FBoxLib not vendored): the arm times the restated algorithm (oracle/), OpenMP over all host cores.
+        # FBoxLib not vendored): the arm times the restated algorithm (oracle/), OpenMP over all host cores, on the
+        # SAME box as the GPU arm (c5: a bounded 96^3 sample -- 512^3 of oracle temporaries do not fit the host).
         if rank != 0:
             return
-        n_s = 96
-        zups, dt = cpu_reference(n_s, max(args.steps, 1), max(args.warmup, 1))
+        n_s = 96 if args.config == "c5" else n
+        zups, dt, w = cpu_reference(args.config, n_s, max(args.steps, 1), max(args.warmup, 0))
+        sample = "the full %s box, every step" % args.config if n_s == n else "%d^3 box of the same workload per step" % n_s
+        cfg = config_of(build_desc_only(args.config, n, args.gpus) if n_s != n else w, args.gpus)
         line = {"metric": METRIC, "value": zups, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "test_advect 3D %d^3 per GPU, ppm_type=1, density_advance episode" % args.n,
-                           "sample": "%d^3 box of the same workload per step" % n_s},
+                "scaling": w.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": zups, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": "density_advance on a %d^3 box, OpenMP over %d threads" % (n_s, cores)},
+                                 "sample": "%s, OpenMP over %d threads (restated reference algorithm, oracle pinned on the "
+                                           "reference's test_advect figures)" % (sample, cores)},
                 "e2e": {"value": zups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -227,15 +242,15 @@ def main():
     for kv in args.opt:
         key, val = kv.split("=")
         lib.set_option(key, int(val))
-    n = args.n
     if world > 1:  # NCCL communicator of the library: halo exchange inside every ghost fill of the episode
         from maestro_b200 import slab
 
         slab.comm_init_from_torch(lib.load(), dev)
-    st = test_advect_state(n, rank=rank, world=world)
-    p = st["p"]
-    ncomp = ncomp_advanced(p)
-    zone_updates = n ** 3 * ncomp
+    if args.selftest:
+        return selftest(ops, rank, world, local_rank, dev)
+    w = build_workload(args.config, n, dev, rank=rank, world=world)
+    p = w.p
+    zone_updates = w.zone_updates
 
     def barrier():
         if world > 1:
@@ -244,32 +259,26 @@ def main():
 
     # ---------------- device-resident episode (value) --------------------------------------------
     p.mem_space = abi.DEVICE
-    e = alloc_episode(st, dev)
-    sold0 = e["sold"].a.clone()
-    umac0 = [u.a.clone() for u in e["umac"]]
+    for q in w.extra.get("params", []):
+        q.mem_space = abi.DEVICE
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MB > 126 MB L2
-
-    def reset_inputs():
-        e["sold"].a.copy_(sold0)
-        for u, u0 in zip(e["umac"], umac0):
-            u.a.copy_(u0)
 
     sampler = ClockSampler(local_rank)
     sampler.start()  # nvidia-smi needs ~0.5 s to produce its first sample: start it before the warm-up
     for _ in range(W):
-        reset_inputs()
-        run_episode(ops, st, e)
+        w.reset()
+        w.step(ops)
     # keep the GPU under the same load for about a second, until the sampler is running.  Every rank must run the
     # SAME number of episodes (each one exchanges halos with its neighbours): the count is agreed on first
     torch.cuda.synchronize()
     t_spin = time.time()
-    run_episode(ops, st, e)
+    w.step(ops)
     torch.cuda.synchronize()
     n_spin = torch.tensor([max(1, int(1.0 / max(time.time() - t_spin, 1e-4)))], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(n_spin, op=dist.ReduceOp.MAX)
     for _ in range(min(int(n_spin.item()), 2000)):
-        run_episode(ops, st, e)
+        w.step(ops)
     torch.cuda.synchronize()
     sampler.lines.clear()
     barrier()
@@ -278,10 +287,10 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for k in range(args.steps):
-        reset_inputs()      # untimed: restores the in-place-modified inputs
+        w.reset()           # untimed: restores the in-place-modified inputs
         flush.zero_()       # untimed: evicts L2 between timed iterations
         ev[k][0].record()
-        run_episode(ops, st, e)
+        w.step(ops)
         ev[k][1].record()
     barrier()
     clocks = sampler.stop()
@@ -290,10 +299,12 @@ def main():
     lib.profile(False)
     t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3  # seconds for K steps on this rank
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    zz = torch.tensor([float(zone_updates)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(zz, op=dist.ReduceOp.SUM)
     t_max = float(tt.item())
-    value = world * zone_updates * args.steps / t_max
+    value = float(zz.item()) * args.steps / t_max
 
     # roofline of the dominant kernel class
     hbm, peak_src = peaks()
@@ -301,92 +312,158 @@ def main():
     roof = None
     if dom[0] is not None and dom[1][1] > 0:
         name, (ms, nl) = dom
-        # algorithmic bytes per launch of one make_edge_scal component (3-D): read s 8 + force 8 + umac 24,
-        # write sedge 24 = 64 B per zone (kernel table); other classes report their own figure
-        bytes_per_zone = {"fused_edge": 64.0, "edge_transverse": 64.0, "edge_final": 64.0}.get(name, 64.0)
-        achieved = bytes_per_zone * n ** 3 / (ms / nl * 1e-3) / 1e9
+        # algorithmic bytes per launch of one make_edge_scal component: 3-D read s 8 + force 8 + umac 24, write
+        # sedge 24 = 64 B per zone; 2-D 8 + 8 + 16 + 16 = 48 B per zone (kernel table)
+        bytes_per_zone = 48.0 if p.dm == 2 else 64.0
+        achieved = bytes_per_zone * w.zones / (ms / nl * 1e-3) / 1e9
         traffic = None
         ncu_static = None
-        try:  # DRAM bytes per launch of this kernel class from the committed ncu --set full capture (n = 256 only)
+        try:  # DRAM bytes per launch of this kernel class from the committed ncu --set full capture (c2, n = 256 only)
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if n == 256 and name in tj:
+            if args.config == "c2" and n == 256 and name in tj:
                 traffic = tj[name]["bytes_per_launch"]
                 ncu_static = tj[name].get("ncu")  # issue / fp64-pipe / DRAM utilisation of the same capture
         except Exception:
             traffic = None
         others = {}
-        if "update" in prof and prof["update"][1] > 0:  # flux + update + density kernel: 360 B per zone
+        if args.config == "c2" and "update" in prof and prof["update"][1] > 0:  # flux + update + density kernel: 360 B per zone
             ms_u = prof["update"][0] / args.steps
-            others["update"] = {"achieved": 360.0 * n ** 3 / (ms_u * 1e-3) / 1e9, "frac": 360.0 * n ** 3 / (ms_u * 1e-3) / 1e9 / hbm,
+            others["update"] = {"achieved": 360.0 * w.zones / (ms_u * 1e-3) / 1e9, "frac": 360.0 * w.zones / (ms_u * 1e-3) / 1e9 / hbm,
                                 "ms_per_step": ms_u, "algorithmic_bytes_per_zone": 360.0,
-                                "note": "k_copy + k_flux_update3_fast, all species/tracers in one launch"}
+                                "note": "k_flux_update3_fast, all species/tracers in one launch"}
+        ep_gbs = w.bytes_per_zone * w.zones * args.steps / t_dev / 1e9
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src, "other_kernels": others,
                 "kernel_ms_per_launch": ms / nl, "kernel_share_of_step": (ms / args.steps) / (t_dev / args.steps * 1e3),
-                "algorithmic_bytes_per_launch": bytes_per_zone * n ** 3,
-                "episode_algorithmic_GBs": 368.0 * n ** 3 * args.steps / t_dev / 1e9,
-                "episode_frac": 368.0 * n ** 3 * args.steps / t_dev / 1e9 / hbm,
+                "algorithmic_bytes_per_launch": bytes_per_zone * w.zones,
+                "episode_algorithmic_bytes_per_zone": w.bytes_per_zone,
+                "episode_algorithmic_GBs": ep_gbs, "episode_frac": ep_gbs / hbm,
                 "kernel_classes_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
                 "ncu_capture": ncu_static}
     del flush
 
+    # ---------------- the bit-identical build beside it, and the per-zone distance between the two ------------------
+    parity = None
+    exact_line = None
+    if world == 1 and not args.no_parity and args.config in ("c2", "c3", "c4"):
+        w.reset()
+        w.step(ops)
+        fast = {k: v.clone() for k, v in w.outputs().items()}
+        lib.set_option("exact", 1)
+        te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w.reset(); w.step(ops)  # warm-up (first launch of the exact kernels)
+        ms_exact = 0.0
+        for _ in range(3):
+            w.reset()
+            te0.record(); w.step(ops); te1.record()
+            torch.cuda.synchronize()
+            ms_exact += te0.elapsed_time(te1) / 3
+        parity = {"what": "FAST build (timed above) against the exact build (bit-identical to the oracle), max over zones of "
+                          "|a-b| / max(|b|, 1e-10 max|b|) per output field", "per_zone_rel": per_zone_parity(w.outputs(), fast)}
+        parity["worst"] = max(parity["per_zone_rel"].values())
+        exact_line = {"ms_per_step": ms_exact, "value": zone_updates / (ms_exact * 1e-3),
+                      "note": "exact build (--opt exact=1): no FMA contraction, reference expression order, bit-identical to the oracle"}
+        lib.set_option("exact", 0)
+        del fast
+
     # ---------------- end to end through the C ABI with host buffers (e2e) ------------------------
-    p.mem_space = abi.HOST
-    del e
-    torch.cuda.empty_cache()
-    eh = alloc_episode(st, None)
-    import ctypes as C
+    e2e = None
+    if args.config == "c2":
+        p.mem_space = abi.HOST
+        del w
+        torch.cuda.empty_cache()
+        wh = build_workload(args.config, n, None, rank=rank, world=world)
+        wh.p.dt, wh.p.rel_eps = p.dt, p.rel_eps
+        eh = wh.extra["e"]
+        import ctypes as C
 
-    def pin(f):  # pinned host memory so the copies run at full PCIe rate
-        t = torch.from_numpy(f.a)
-        lib.load().mgpu_host_register(C.c_void_p(f.ptr), f.a.size)
-        return t
+        def pin(f):  # pinned host memory so the copies run at full PCIe rate
+            t = torch.from_numpy(f.a)
+            lib.load().mgpu_host_register(C.c_void_p(f.ptr), f.a.size)
+            return t
 
-    keep = [pin(f) for f in [eh["sold"], eh["snew"], eh["force"], eh["eta"]] + eh["umac"] + eh["sedge"] + eh["sflux"]]
-    sold_h0 = eh["sold"].a.copy()
-    umac_h0 = [u.a.copy() for u in eh["umac"]]
-    run_episode(ops, st, eh)  # warm-up (allocates the staging pool)
-    barrier()
-    lib.copy_bytes(reset=True)  # the library counts the bytes of every cudaMemcpyAsync it issues
-    t_e2e = 0.0
-    for _ in range(args.e2e_steps):
-        eh["sold"].a[...] = sold_h0  # untimed: restore the in-place-modified host inputs
-        for u, u0 in zip(eh["umac"], umac_h0):
-            u.a[...] = u0
+        keep = [pin(f) for f in [eh["sold"], eh["snew"], eh["force"], eh["eta"]] + eh["umac"] + eh["sedge"] + eh["sflux"]]
+        wh.step(ops)  # warm-up (allocates the staging pool)
         barrier()
-        t0 = time.perf_counter()
-        run_episode(ops, st, eh)  # synchronous: H2D of inputs, kernels, D2H of outputs, stream sync
-        t_e2e += time.perf_counter() - t0
-    in_bytes, out_bytes = [b // args.e2e_steps for b in lib.copy_bytes()]
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * zone_updates * args.e2e_steps / float(te.item())
-    snew_sum = float(eh["snew"].valid(0).sum())
+        lib.copy_bytes(reset=True)  # the library counts the bytes of every cudaMemcpyAsync it issues
+        t_e2e = 0.0
+        for _ in range(args.e2e_steps):
+            wh.reset()  # untimed: restore the in-place-modified host inputs
+            barrier()
+            t0 = time.perf_counter()
+            wh.step(ops)  # synchronous: H2D of inputs, kernels, D2H of outputs, stream sync
+            t_e2e += time.perf_counter() - t0
+        in_bytes, out_bytes = [b // args.e2e_steps for b in lib.copy_bytes()]
+        te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * zone_updates * args.e2e_steps / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "steps": args.e2e_steps,
+               "check_sum_rho_new": float(eh["snew"].valid(0).sum())}
+        w = wh
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "test_advect 3D %d^3 per GPU, ppm_type=1, density_advance episode "
-                                   "(%d comps: %d species + rho' + %d tracer), ng_s=4, periodic" % (n, ncomp, p.nspec,
-                                                                                                  p.ntrac),
-                       "zones_per_gpu": n ** 3, "components": ncomp, "l2": "256 MB flush between timed iterations",
-                       "multi_gpu": ("periodic %d x %d x %d domain, one %d^3 slab per rank, NCCL send/recv halo exchange "
-                                     "in every ghost fill (timed)" % (n, n, n * world, n)) if world > 1 else "single box"},
-            "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                    "steps": args.e2e_steps, "check_sum_rho_new": snew_sum},
-            "roofline": roof}
+            "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": w.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(w, world),
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof}
+    if parity is not None:
+        line["parity"] = parity
+        line["exact_build"] = exact_line
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        zups, dt = cpu_reference(96, 2, 1)
+        n_s = {"c2": 128, "c3": 96, "c4": 1024, "c5": 64}[args.config]
+        zups, dt, _ = cpu_reference(args.config, n_s, 2, 1)
         line["cpu_baseline"] = {"value": zups, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "density_advance on a 96^3 box of the same workload, 2 steps, OpenMP over "
-                                          "%d threads (restated reference algorithm; gfortran+FBoxLib build "
-                                          "impossible here)" % cores}
+                                "sample": "the same episode(s) on a %d-zone-per-side box of the same workload, 2 steps, "
+                                          "OpenMP over %d threads (restated reference algorithm, oracle pinned on the "
+                                          "reference's test_advect figures; gfortran+FBoxLib build impossible here); "
+                                          "`--impl reference` times the full-size box" % (n_s, cores)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def build_desc_only(config, n, world):
+    """the configuration text of the full-size workload without building it (reference arm on a sample box)"""
+    class D:
+        pass
+
+    d = D()
+    w = None
+    from maestro_b200 import workloads
+
+    # a tiny build of the same configuration gives the text; sizes are patched to the full ones
+    w = workloads.BUILDERS[config](n=16 if config != "c4" else 32, device="cpu" if config == "c5" else None)
+    w.desc["workload"] = w.desc["workload"].replace("16^3", "%d^3" % n).replace("32^2", "%d^2" % n)
+    w.desc["zones_per_gpu"] = n ** w.p.dm // max(1, world if w.scaling == "strong" else 1)
+    return w
+
+
+def selftest(ops, rank, world, local_rank, dev):
+    """`bench.py --gpus N --selftest` (under torchrun): the multi-rank parity cases of tests/mgpu_rank_parity.py, run
+    inside the same launch the driver uses for the scaling bench, so that the NCCL halo path is checked on the
+    driver's hardware.  Prints one JSON line; exits nonzero on mismatch."""
+    import subprocess
+
+    import torch.distributed as dist
+
+    dist.destroy_process_group()
+    if rank != 0:
+        return
+    cases = [("3", "periodic", "1", "1"), ("3", "walls", "2", "1"), ("2", "walls", "1", "1"), ("3", "periodic", "1", "0"),
+             ("3", "walls", "2", "0"), ("2", "periodic", "2", "0"), ("3", "sphr", "1", "1")]
+    res = {}
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_PORT", "TORCHELASTIC_RUN_ID")}
+    for i, c in enumerate(cases):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(29730 + i), os.path.join(ROOT, "tests", "mgpu_rank_parity.py")] + list(c)
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+        oks = [ln for ln in r.stdout.splitlines() if ln.startswith("RANK")]
+        res["dm%s_%s_ppm%s_%s" % (c[0], c[1], c[2], "exact" if c[3] == "1" else "fast")] = {"rc": r.returncode, "ranks": oks}
+    ok = all(v["rc"] == 0 for v in res.values())
+    print(json.dumps({"selftest": "multi-rank density_advance against the single-box oracle, NCCL halo exchange in "
+                                  "every ghost fill", "n_gpus": world, "ok": ok, "cases": res}))
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

@@ -948,6 +948,7 @@ int mgpu_set_option(const char* key, int value) {
   else if (k == "kchunk") g_opt_kchunk = value;
   else if (k == "exact") g_opt_exact = value;
   else if (k == "leanplus") g_opt_leanplus = value;
+  else if (k == "split_tiles") fused_edge3_set_split(value);
   else if (k == "overlap") g_opt_overlap = value;
   else if (k == "fused_variant") fused_edge_set_variant(value);
   else if (k == "fused_by") fused_edge2_set_by(value);

@@ -536,6 +536,7 @@ void fused_edge_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, cons
   if (ng_s < 3) throw Error("make_edge_scal: need at least 3 ghost cells");
   if (ng_f < 1) throw Error("make_edge_scal: force needs at least 1 ghost cell");
   FusedArgs a;
+  memset(&a, 0, sizeof(a));
   a.slope_order = P.slope_order;
   a.force_zero = force_zero;
   a.sdiv = sdiv;

@@ -31,6 +31,9 @@ struct FusedArgs {
   double dt, dx[3], rel_eps;
   // dt/dx, dt/(6 dx), dt/(4 dx) and dt/2, filled by fused_edge3_launch: read as constant-bank operands, no registers
   double td[3], c6[3], c4[3], dt2;
+  // third design, boxes with physical boundaries: 0 every tile; 1 only the tiles no boundary rule can reach (run by the
+  // plain kernel), 2 only the others (run by the boundary kernel) -- see fused_edge3_launch
+  int tile_mode;
   DV s, force;  // single-component views
   DV umac[3];
   DV sedge[3];  // single-component views of the output
@@ -53,6 +56,7 @@ void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz
 // third design (mgpu_fused3.cu): the upwind-first algorithm with TMA-staged tiles and a register-renamed plane loop
 bool fused_edge3_supported(const FusedArgs& a, bool bc);
 void fused_edge3_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc);
+void fused_edge3_set_split(int on);  // boundary boxes: interior tiles through the plain kernel (default on)
 // 2-D (mgpu_fused2.cu, k_fused_edge2d): FAST arithmetic only, non-conservative, ppm_trace_forces = 0, no REFLECT_ODD
 bool fused_edge2d_supported(const mgpu_params& P, bool is_cons, const int* adv_bc, int bccomp, bool exact);
 void fused_edge2d_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,

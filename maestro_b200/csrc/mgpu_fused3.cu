@@ -118,6 +118,20 @@ __global__ void __launch_bounds__(BX* BY, 2)
   const int kz1 = min(kz0 + a.kchunk - 1, a.hi[2]);
   const bool top = (kz1 == a.hi[2]);
   const int ic = min(i, a.hi[0] + 1), jc = min(j, a.hi[1] + 1);
+  if (a.tile_mode != 0) {
+    // A tile is "interior" when none of the cells it reconstructs (columns ibase .. ibase+BX-1, rows likewise, planes
+    // kz0-1 .. kz1+3) lies within two cells of a physical boundary and none of its faces is a boundary face: the wall
+    // stencils (ppm.f90:1758-1856, :1983-2216, slope.f90:245-285) and the boundary-face rules cannot reach it, and the
+    // plain kernel gives what the boundary kernel would.  CTA-uniform.
+    const int c0[3] = {ibase, jbase, kz0 - 1}, c1[3] = {ibase + BX - 1, jbase + BY - 1, kz1 + 3};
+    bool interior = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (a.bclo[d] != MGPU_BC_INTERIOR && c0[d] <= a.lo[d] + 2) interior = false;
+      if (a.bchi[d] != MGPU_BC_INTERIOR && c1[d] >= a.hi[d] - 2) interior = false;
+    }
+    if ((a.tile_mode == 1) != interior) return;
+  }
   const LineBC nb = no_wall2();
   const LineBC lbx = BC ? make_linebc(3, 0, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0]) : nb;
   const LineBC lby = BC ? make_linebc(3, 1, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1]) : nb;
@@ -668,6 +682,8 @@ int fused3_auto_kchunk(int ncols, int nz, int slots) {
   return bk;
 }
 
+bool g_split_tiles = true;  // boundary boxes: interior tiles through the plain kernel (mgpu_set_option "split_tiles")
+
 typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -734,12 +750,27 @@ void launch_fused3(const FusedArgs& a0, int nx, int ny, int nz) {
 }
 
 template <int PPM>
-void launch_fused3_xf(const FusedArgs& a, int nx, int ny, int nz, bool bc) {
-  const int xf = a.sdiv ? 1 : (a.ssub ? 2 : 0);
+void launch_fused3_xf(const FusedArgs& a0, int nx, int ny, int nz, bool bc) {
+  const int xf = a0.sdiv ? 1 : (a0.ssub ? 2 : 0);
   if (bc) {
+    // Most tiles of a box with physical boundaries are out of reach of every boundary rule: those run the plain
+    // kernel (incremental z reconstruction, no per-face rule tests), the shell next to the boundaries runs the boundary
+    // kernel.  Two launches over the same grid; a CTA of the wrong kind exits at once.  Shorter z chunks keep the
+    // boundary shell thin when the box has a boundary in z.
+    FusedArgs a = a0;
+    const bool zbc = a.bclo[2] != MGPU_BC_INTERIOR || a.bchi[2] != MGPU_BC_INTERIOR;
+    if (a.kchunk <= 0 && zbc && nz >= 128) a.kchunk = 32;
+    const bool split = g_split_tiles && nx >= 3 * 14 && ny >= 3 * 14 && nz >= 24;
+    if (split) {
+      if (a.kchunk <= 0) a.kchunk = nz >= 128 ? 64 : nz;  // both launches must cut the same chunks
+      a.tile_mode = 1;
+      launch_fused3<PPM, 16, 16, 0, false, false>(a, nx, ny, nz);
+      a.tile_mode = 2;
+    }
     launch_fused3<PPM, 16, 16, 0, false, true>(a, nx, ny, nz);
     return;
   }
+  const FusedArgs& a = a0;
   if (a.wadd) {
     if (xf == 0) launch_fused3<PPM, 16, 16, 0, true, false>(a, nx, ny, nz);
     else if (xf == 1) launch_fused3<PPM, 16, 16, 1, true, false>(a, nx, ny, nz);
@@ -762,6 +793,8 @@ bool fused_edge3_supported(const FusedArgs& a, bool bc) {
   if (a.sdiv && (reinterpret_cast<uintptr_t>(a.sdiv) & 15u)) return false;
   return true;
 }
+
+void fused_edge3_set_split(int on) { g_split_tiles = on != 0; }
 
 void fused_edge3_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc) {
   switch (ppm_type) {

@@ -12,14 +12,20 @@ from maestro_b200 import abi, lib
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+config = "c2"
 ops = lib.init(0, use_torch_stream=True)
 for kv in sys.argv[3:]:
     k, v = kv.split("=")
-    lib.set_option(k, int(v))
-st = bench.test_advect_state(n)
-st["p"].mem_space = abi.DEVICE
-e = bench.alloc_episode(st, "cuda:0")
+    if k == "config":
+        config = v
+    else:
+        lib.set_option(k, int(v))
+w = bench.build_workload(config, n, "cuda:0")
+w.p.mem_space = abi.DEVICE
+for q in w.extra.get("params", []):
+    q.mem_space = abi.DEVICE
 for _ in range(reps):
-    bench.run_episode(ops, st, e)
+    w.reset()
+    w.step(ops)
 torch.cuda.synchronize()
-print("launches per episode:", lib.launch_count() // reps)
+print("launches per step:", lib.launch_count() // reps)
