@@ -130,6 +130,19 @@ int mgpu_set_stream(void* stream);
 int mgpu_host_register(double* hptr, long n);
 int mgpu_host_unregister(double* hptr);
 
+/* ---- residency registry (the multifabs of a MAESTRO step stay on the device between episodes) ----
+ * A registered host fab (hptr = its first element, n = doubles, ghost cells and all components included) keeps one
+ * device mirror.  Host-pointer calls then upload only the components whose host copy is newer and leave their
+ * results on the device; mgpu_download brings the components a call wrote back to the host, mgpu_invalidate tells the
+ * library that the host changed them (0-based comp0, ncomp < 0: every component).  Replaces what FBoxLib does
+ * implicitly by owning the data: the Fortran driver calls mgpu_invalidate after it writes a multifab on the host and
+ * mgpu_download before it reads one the device wrote.  pin != 0 also page-locks the host memory. */
+int mgpu_register(double* hptr, long n, int pin);
+int mgpu_unregister(double* hptr);
+int mgpu_invalidate(double* hptr, int comp0, int ncomp);
+int mgpu_download(double* hptr, int comp0, int ncomp);
+int mgpu_upload(double* hptr, int comp0, int ncomp);
+
 /* device memory helpers for device-resident episodes (tests/bench own their buffers) */
 int mgpu_malloc(double** dptr, long n);
 int mgpu_free(double* dptr);

@@ -162,6 +162,11 @@ LIFECYCLE = {
     "mgpu_set_stream": (C.c_int, [C.c_void_p]),
     "mgpu_host_register": (C.c_int, [C.c_void_p, C.c_long]),
     "mgpu_host_unregister": (C.c_int, [C.c_void_p]),
+    "mgpu_register": (C.c_int, [C.c_void_p, C.c_long, C.c_int]),
+    "mgpu_unregister": (C.c_int, [C.c_void_p]),
+    "mgpu_invalidate": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mgpu_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mgpu_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mgpu_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_long]),
     "mgpu_free": (C.c_int, [C.c_void_p]),
     "mgpu_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long]),

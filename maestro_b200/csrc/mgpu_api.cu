@@ -142,10 +142,27 @@ static inline cmask_t crange(int c0, int nc) {  // components c0 .. c0+nc-1 (0-b
   for (int c = c0; c < c0 + nc; ++c) m |= (1ull << c);
   return m;
 }
+// ---- residency registry (lifecycle) ---------------------------------------------------------
+// A host fab registered with mgpu_register keeps ONE device mirror for as long as it is registered.  Per component
+// the registry knows which side holds the truth:
+//   host_dirty  the host copy is newer: the next call that reads the component uploads it first
+//   dev_dirty   the device copy is newer (a call wrote it): the host sees it after mgpu_download
+// Calls with host pointers then move only what is stale, and outputs stay on the device until someone asks for them:
+// the episodes of one MAESTRO step hand sedge / sflux / scal_force / umac to each other without crossing PCIe.
+struct Resident {
+  double* d = nullptr;
+  size_t n = 0;  // doubles
+  cmask_t host_dirty = ALLC, dev_dirty = 0;
+  size_t cs = 0;  // component stride, known from the first call that views the fab
+  int nc = 0;
+  bool pinned = false;
+};
+static std::map<const double*, Resident> g_res;
+
 struct Call {
   const mgpu_params& P;
   bool host;
-  struct Item { double* h; double* d; size_t cs; int nc; cmask_t out; cmask_t zero; };
+  struct Item { double* h; double* d; size_t cs; int nc; cmask_t out; cmask_t zero; cmask_t in_done; Resident* res; };
   std::vector<Item> items;
   explicit Call(const mgpu_params* p, size_t scratch_bytes) : P(*p), host(p->mem_space == MGPU_HOST) {
     require_init();
@@ -154,7 +171,8 @@ struct Call {
     arena_reset();
   }
   ~Call() {
-    for (auto& it : items) g_pool.put(it.d);
+    for (auto& it : items)
+      if (!it.res) g_pool.put(it.d);
   }
   // runs of set bits of m (restricted to nc components) -> one cudaMemcpyAsync each
   template <class F>
@@ -172,19 +190,43 @@ struct Call {
     if (!f.ptr) throw Error("mgpu: null fab pointer");
     if (!host) return make_view(f, P.dm);
     if (f.nc > 64) in = out = (in || out) ? ALLC : 0;
+    DV v = make_view(f, P.dm);
+    auto upload = [&](double* d, cmask_t comps) {
+      for_runs(comps, f.nc, [&](int c0, int n) {
+        MGPU_CUDA(cudaMemcpyAsync(d + v.cs * c0, f.ptr + v.cs * c0, (size_t)v.cs * n * sizeof(double),
+                                  cudaMemcpyHostToDevice, g_ctx.stream));
+        g_h2d_bytes += (long)v.cs * n * (long)sizeof(double);
+      });
+    };
+    const cmask_t all = f.nc >= 64 ? ALLC : ((cmask_t(1) << f.nc) - 1);
     for (auto& it : items)  // the same host fab passed twice maps to one device buffer
       if (it.h == f.ptr) {
+        cmask_t more = in & all & ~it.in_done;  // components this view reads that the first one did not bring in
+        if (it.res) {
+          more &= it.res->host_dirty;
+          it.res->host_dirty &= ~more;
+        }
+        upload(it.d, more);
+        it.in_done |= in & all;
         it.out |= out;
         return make_view(f, P.dm, it.d);
       }
-    DV v = make_view(f, P.dm);
+    auto rit = g_res.find(f.ptr);
+    if (rit != g_res.end()) {  // registered: the persistent mirror, only the stale components travel
+      Resident& r = rit->second;
+      if ((size_t)v.size() > r.n) throw Error("mgpu: the fab is larger than the region registered for it");
+      if (r.cs != 0 && (r.cs != (size_t)v.cs || r.nc != f.nc)) throw Error("mgpu: a registered fab changed its shape (unregister it first)");
+      r.cs = (size_t)v.cs;
+      r.nc = f.nc;
+      const cmask_t need = in & all & r.host_dirty;
+      upload(r.d, need);
+      r.host_dirty &= ~need;
+      items.push_back({f.ptr, r.d, (size_t)v.cs, f.nc, out, (cmask_t)0, in & all, &r});
+      return make_view(f, P.dm, r.d);
+    }
     double* d = g_pool.get((size_t)v.size());
-    for_runs(in, f.nc, [&](int c0, int n) {
-      MGPU_CUDA(cudaMemcpyAsync(d + v.cs * c0, f.ptr + v.cs * c0, (size_t)v.cs * n * sizeof(double),
-                                cudaMemcpyHostToDevice, g_ctx.stream));
-      g_h2d_bytes += (long)v.cs * n * (long)sizeof(double);
-    });
-    items.push_back({f.ptr, d, (size_t)v.cs, f.nc, out, (cmask_t)0});
+    upload(d, in & all);
+    items.push_back({f.ptr, d, (size_t)v.cs, f.nc, out, (cmask_t)0, in & all, nullptr});
     return make_view(f, P.dm, d);
   }
   DV view(const mgpu_fab& f, bool copy_in, bool copy_out) { return view(f, copy_in ? ALLC : 0, copy_out ? ALLC : 0); }
@@ -202,14 +244,30 @@ struct Call {
   }
   void finish() {
     if (!host) return;
-    for (auto& it : items)
+    for (auto& it : items) {
+      if (it.res) {  // registered: the results stay on the device until mgpu_download
+        const cmask_t all = it.nc >= 64 ? ALLC : ((cmask_t(1) << it.nc) - 1);
+        it.res->dev_dirty |= it.out & all;
+        it.res->host_dirty &= ~(it.out & all);
+        continue;
+      }
       for_runs(it.out, it.nc, [&](int c0, int n) {
         MGPU_CUDA(cudaMemcpyAsync(it.h + it.cs * c0, it.d + it.cs * c0, it.cs * n * sizeof(double),
                                   cudaMemcpyDeviceToHost, g_ctx.stream));
         g_d2h_bytes += (long)(it.cs * n * sizeof(double));
       });
+    }
     for (auto& it : items)  // overlaps the asynchronous device-to-host copies
-      for_runs(it.zero, it.nc, [&](int c0, int n) { memset(it.h + it.cs * c0, 0, it.cs * n * sizeof(double)); });
+      for_runs(it.zero, it.nc, [&](int c0, int n) {
+        if (it.res) {  // registered: the zeros are produced in the mirror and reach the host with mgpu_download
+          MGPU_CUDA(cudaMemsetAsync(it.d + it.cs * c0, 0, it.cs * n * sizeof(double), g_ctx.stream));
+          const cmask_t m = ((n >= 64 ? ALLC : ((cmask_t(1) << n) - 1)) << c0);
+          it.res->dev_dirty |= m;
+          it.res->host_dirty &= ~m;
+          return;
+        }
+        memset(it.h + it.cs * c0, 0, it.cs * n * sizeof(double));
+      });
     MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
   }
 };
@@ -932,6 +990,11 @@ int mgpu_finalize(void) {
   cudaStreamSynchronize(g_ctx.stream);
   comm_finalize();
   g_pool.clear();
+  for (auto& kv : g_res) {
+    if (kv.second.pinned) cudaHostUnregister(const_cast<double*>(kv.first));
+    cudaFree(kv.second.d);
+  }
+  g_res.clear();
   if (g_ctx.arena) cudaFree(g_ctx.arena);
   g_ctx.arena = nullptr;
   g_ctx.arena_bytes = 0;
@@ -1036,6 +1099,87 @@ int mgpu_host_register(double* hptr, long n) {
 int mgpu_host_unregister(double* hptr) {
   MGPU_TRY
   MGPU_CUDA(cudaHostUnregister(hptr));
+  MGPU_CATCH
+}
+
+/* ---- residency registry -------------------------------------------------------------------------------------- */
+int mgpu_register(double* hptr, long n, int pin) {
+  MGPU_TRY
+  require_init();
+  if (!hptr || n <= 0) throw Error("mgpu_register: null pointer or empty region");
+  if (g_res.count(hptr)) throw Error("mgpu_register: the fab is already registered");
+  Resident r;
+  r.n = (size_t)n;
+  MGPU_CUDA(cudaMalloc((void**)&r.d, r.n * sizeof(double)));
+  if (pin) {
+    cudaError_t e = cudaHostRegister(hptr, r.n * sizeof(double), cudaHostRegisterDefault);
+    if (e == cudaSuccess) r.pinned = true;
+    else if (e == cudaErrorHostMemoryAlreadyRegistered) cudaGetLastError();
+    else { cudaFree(r.d); MGPU_CUDA(e); }
+  }
+  g_res[hptr] = r;
+  MGPU_CATCH
+}
+static Resident& resident_of(const double* hptr, const char* who) {
+  auto it = g_res.find(hptr);
+  if (it == g_res.end()) throw Error(std::string(who) + ": the fab is not registered");
+  return it->second;
+}
+static cmask_t comp_mask(const Resident& r, int comp0, int ncomp, const char* who) {
+  if (ncomp < 0) return ALLC;  // every component
+  if (comp0 < 0 || comp0 + ncomp > 64) throw Error(std::string(who) + ": component range outside 0..63");
+  (void)r;
+  return ncomp == 0 ? 0 : ((ncomp >= 64 ? ALLC : ((cmask_t(1) << ncomp) - 1)) << comp0);
+}
+/* the host changed components comp0 .. comp0+ncomp-1 (0-based; ncomp < 0: all): the mirror is stale */
+int mgpu_invalidate(double* hptr, int comp0, int ncomp) {
+  MGPU_TRY
+  Resident& r = resident_of(hptr, "mgpu_invalidate");
+  const cmask_t m = comp_mask(r, comp0, ncomp, "mgpu_invalidate");
+  r.host_dirty |= m;
+  r.dev_dirty &= ~m;
+  MGPU_CATCH
+}
+/* bring the host copy of the components up to date (copies only what a call wrote since the last download) */
+int mgpu_download(double* hptr, int comp0, int ncomp) {
+  MGPU_TRY
+  require_init();
+  Resident& r = resident_of(hptr, "mgpu_download");
+  const cmask_t m = comp_mask(r, comp0, ncomp, "mgpu_download") & r.dev_dirty;
+  if (m && r.cs == 0) throw Error("mgpu_download: no call has used this fab yet");
+  Call::for_runs(m, r.nc, [&](int c0, int n) {
+    MGPU_CUDA(cudaMemcpyAsync(hptr + r.cs * c0, r.d + r.cs * c0, r.cs * n * sizeof(double), cudaMemcpyDeviceToHost,
+                              g_ctx.stream));
+    g_d2h_bytes += (long)(r.cs * n * sizeof(double));
+  });
+  MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  r.dev_dirty &= ~m;
+  MGPU_CATCH
+}
+/* eager upload of the stale components (optional: calls upload what they read on their own) */
+int mgpu_upload(double* hptr, int comp0, int ncomp) {
+  MGPU_TRY
+  require_init();
+  Resident& r = resident_of(hptr, "mgpu_upload");
+  if (r.cs == 0) throw Error("mgpu_upload: the shape of the fab is known after the first call that uses it");
+  const cmask_t m = comp_mask(r, comp0, ncomp, "mgpu_upload") & r.host_dirty;
+  Call::for_runs(m, r.nc, [&](int c0, int n) {
+    MGPU_CUDA(cudaMemcpyAsync(r.d + r.cs * c0, hptr + r.cs * c0, r.cs * n * sizeof(double), cudaMemcpyHostToDevice,
+                              g_ctx.stream));
+    g_h2d_bytes += (long)(r.cs * n * sizeof(double));
+  });
+  r.host_dirty &= ~m;
+  MGPU_CATCH
+}
+/* downloads nothing: call mgpu_download first if the host needs the device's results */
+int mgpu_unregister(double* hptr) {
+  MGPU_TRY
+  auto it = g_res.find(hptr);
+  if (it == g_res.end()) throw Error("mgpu_unregister: the fab is not registered");
+  MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  if (it->second.pinned) cudaHostUnregister(hptr);
+  cudaFree(it->second.d);
+  g_res.erase(it);
   MGPU_CATCH
 }
 

@@ -140,11 +140,20 @@ bool halo_exchange_dev(const mgpu_params& P, const DV& s, const int* lo, const i
   long ext[3] = {s.n[0], s.n[1], s.n[2]};
   halo_plan_make(P.dm, P.domlo, P.domhi, lo, hi, ng, nodal, ext, pmask, g_comm.rank, g_comm.nranks, &pl);
   const int r = pl.dir;
+  // a slab thinner than the ghost width would send planes that are its own (stale) ghost planes: FBoxLib copies from
+  // the box that owns the zones, two slabs away -- not built; fail instead of exchanging wrong planes
+  if (hi[r] - lo[r] + 1 < ng && (pl.up_rank >= 0 || pl.dn_rank >= 0))
+    throw Error("halo exchange: a slab of " + std::to_string(hi[r] - lo[r] + 1) + " plane(s) is thinner than the ghost width " +
+                std::to_string(ng) + " (use fewer ranks or a taller domain)");
   const size_t cnt = (size_t)pl.plane_doubles * pl.nplanes;
   auto plane = [&](int c, int k) { return s.p + s.cs * (long)c + (long)(k - s.lo[r]) * pl.plane_doubles; };
   const bool outer = g_group_depth > 0;
   if (!outer) prof_begin(TAG_HALO);
   MGPU_NCCL(g_nccl.GroupStart());
+  struct CloseGroup {  // an exception below must not leave the NCCL group open
+    bool armed = true;
+    ~CloseGroup() { if (armed) g_nccl.GroupEnd(); }
+  } closer;
   for (int c = c0; c < c0 + nc; ++c) {
     // order per peer must be the same on both sides: (send up, recv from down, send down, recv from up)
     if (pl.up_rank >= 0) MGPU_NCCL(g_nccl.Send(plane(c, pl.send_up_k0), cnt, ncclDouble, pl.up_rank, g_comm.comm, stream));
@@ -152,6 +161,7 @@ bool halo_exchange_dev(const mgpu_params& P, const DV& s, const int* lo, const i
     if (pl.dn_rank >= 0) MGPU_NCCL(g_nccl.Send(plane(c, pl.send_dn_k0), cnt, ncclDouble, pl.dn_rank, g_comm.comm, stream));
     if (pl.up_rank >= 0) MGPU_NCCL(g_nccl.Recv(plane(c, pl.recv_hi_k0), cnt, ncclDouble, pl.up_rank, g_comm.comm, stream));
   }
+  closer.armed = false;
   MGPU_NCCL(g_nccl.GroupEnd());
   if (!outer) {
     count_launch();  // one grouped NCCL kernel
@@ -164,6 +174,14 @@ void halo_group_begin() {
   if (!(g_comm.on && g_comm.nranks > 1)) return;
   if (g_group_depth++ == 0) prof_begin(TAG_HALO);
   MGPU_NCCL(g_nccl.GroupStart());
+}
+// closes a batch that an exception interrupted: the NCCL group ends and the depth returns to zero (FillBatch's destructor)
+void halo_group_abort() {
+  if (!(g_comm.on && g_comm.nranks > 1)) return;
+  while (g_group_depth > 0) {
+    g_nccl.GroupEnd();
+    --g_group_depth;
+  }
 }
 void halo_group_end() {
   if (!(g_comm.on && g_comm.nranks > 1)) return;

@@ -21,6 +21,7 @@ bool halo_exchange_dev(const mgpu_params& P, const DV& s, const int* lo, const i
 // one NCCL group around several halo_exchange_dev calls (NCCL groups nest): a single launch for all fields
 void halo_group_begin();
 void halo_group_end();
+void halo_group_abort();  // after an exception inside a group: end the NCCL group(s), depth back to zero
 void allreduce_minmax_dev(double* d_minmax2);
 void allreduce_dev(double* d, int n, int op);  // op: 0 sum, 1 min, 2 max
 

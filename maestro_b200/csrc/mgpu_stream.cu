@@ -162,8 +162,32 @@ __global__ void k_update_rho(UpdArgs a, int c0, int c1, int rho, double bcd) {
   }
 }
 
+// zones of the valid box with rho <= cutoff (update_scal.f90:421: the zones whose rhoh the reference resets with the EOS)
+__global__ void k_count_below(DV s, Box3 vb, int rho, double cutoff, unsigned long long* count) {
+  int ix[3];
+  bool hit = decode3(vb, ix) && s(ix[0], ix[1], ix[2], rho) <= cutoff;
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
 void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop) {
   Context& cx = ctx();
+  if (P.do_eos_h_above_cutoff && nstart == P.rhoh_comp) {
+    // The reference recomputes rhoh from the EOS at (rho, p0, X) wherever rho <= base_cutoff_density
+    // (update_scal.f90:421-447, default do_eos_h_above_cutoff = T).  The EOS is not on the device: if any
+    // zone of this box would take that branch the call fails instead of returning a different rhoh.
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(arena_alloc(1));
+    MGPU_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), cx.stream));
+    k_count_below<<<grid3(a.vb, 256), block3(a.vb, 256), 0, cx.stream>>>(a.snew, a.vb, P.rho_comp - 1, P.base_cutoff_density, cnt);
+    MGPU_LAUNCH_CHECK();
+    unsigned long long h = 0;
+    MGPU_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, cx.stream));
+    MGPU_CUDA(cudaStreamSynchronize(cx.stream));
+    if (h > 0)
+      throw Error("update_scal: " + std::to_string(h) + " zone(s) have rho <= base_cutoff_density: the EOS reset of rhoh "
+                  "(update_scal.f90:421-447) is not available on the device -- set do_eos_h_above_cutoff = F and apply "
+                  "it on the host (INTEGRATION.md), or keep the density above the cutoff");
+  }
   const long nv = a.vb.npts();
   for (int comp = nstart; comp <= nstop; ++comp) {
     k_update_scal<<<grid3(a.vb, 256), block3(a.vb, 256), 0, cx.stream>>>(a, comp - 1);
@@ -688,6 +712,7 @@ void fill_batch_exchange_async() {
       for (size_t q = first; q < g_batch.size(); ++q) g_batch_slab[q] = fill_exchange(g_batch[q]) ? 1 : 0;
     } catch (...) {
       g_fill_stream = nullptr;
+      halo_group_abort();
       throw;
     }
     halo_group_end();
@@ -712,13 +737,20 @@ void fill_batch_end() {
   // slab-partitioned domain: the slab-direction ghost planes come from the neighbouring ranks (NCCL), first, so
   // that the in-box wraps and physical BCs below also cover the received planes (corners come out right)
   halo_group_begin();
-  for (size_t q = 0; q < g_batch.size(); ++q) slab[q] = fill_exchange(g_batch[q]) ? 1 : 0;
+  try {
+    for (size_t q = 0; q < g_batch.size(); ++q) slab[q] = fill_exchange(g_batch[q]) ? 1 : 0;
+  } catch (...) {
+    halo_group_abort();
+    g_batch.clear();
+    throw;
+  }
   halo_group_end();
   fill_wraps(g_batch.data(), slab.data(), g_batch.size());
   for (size_t q = 0; q < g_batch.size(); ++q) fill_physbc(g_batch[q]);
   g_batch.clear();
 }
 void fill_batch_abort() {
+  halo_group_abort();
   g_batching = false;
   g_batch_slab.clear();
   g_batch.clear();

@@ -100,3 +100,32 @@ def copy_bytes(reset=False):
 def finalize():
     if _lib is not None:
         _lib.mgpu_finalize()
+
+
+# ---- residency registry (include/maestro_b200.h): host fabs that keep a device mirror between calls -------------------
+def _chk(rc):
+    if rc != 0:
+        raise RuntimeError(load().mgpu_last_error().decode())
+
+
+def register(fab, pin=True):
+    """keep a device mirror of a host Fab; host-pointer calls then move only its stale components"""
+    _chk(load().mgpu_register(C.c_void_p(fab.ptr), fab.a.size, 1 if pin else 0))
+
+
+def unregister(fab):
+    _chk(load().mgpu_unregister(C.c_void_p(fab.ptr)))
+
+
+def invalidate(fab, comp0=0, ncomp=-1):
+    """the host wrote components comp0 .. comp0+ncomp-1 (0-based; all by default)"""
+    _chk(load().mgpu_invalidate(C.c_void_p(fab.ptr), comp0, ncomp))
+
+
+def download(fab, comp0=0, ncomp=-1):
+    """bring the host copy up to date with what the device wrote"""
+    _chk(load().mgpu_download(C.c_void_p(fab.ptr), comp0, ncomp))
+
+
+def upload(fab, comp0=0, ncomp=-1):
+    _chk(load().mgpu_upload(C.c_void_p(fab.ptr), comp0, ncomp))

@@ -108,6 +108,32 @@ module maestro_b200_shim
        type(c_ptr), value :: hptr
        integer(c_long), value :: n
      end function mgpu_host_register
+     ! residency registry: the multifabs of a step stay on the device between episodes (maestro_b200.h)
+     integer(c_int) function mgpu_register(hptr, n, pin) bind(C, name="mgpu_register")
+       import :: c_int, c_long, c_ptr
+       type(c_ptr), value :: hptr
+       integer(c_long), value :: n
+       integer(c_int), value :: pin
+     end function mgpu_register
+     integer(c_int) function mgpu_unregister(hptr) bind(C, name="mgpu_unregister")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: hptr
+     end function mgpu_unregister
+     integer(c_int) function mgpu_invalidate(hptr, comp0, ncomp) bind(C, name="mgpu_invalidate")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: hptr
+       integer(c_int), value :: comp0, ncomp
+     end function mgpu_invalidate
+     integer(c_int) function mgpu_download(hptr, comp0, ncomp) bind(C, name="mgpu_download")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: hptr
+       integer(c_int), value :: comp0, ncomp
+     end function mgpu_download
+     integer(c_int) function mgpu_upload(hptr, comp0, ncomp) bind(C, name="mgpu_upload")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: hptr
+       integer(c_int), value :: comp0, ncomp
+     end function mgpu_upload
 
      integer(c_int) function mgpu_make_edge_scal_c(p, nfabs, s, sedge, umac, force, adv_bc, is_vel, &
           start_scomp, start_bccomp, num_comp, is_conservative) bind(C, name="mgpu_make_edge_scal")
