@@ -154,6 +154,11 @@ int mgpu_memcpy_d2h(double* dst, const double* src, long n);
  * BCs per adv_bc (physbc_2d :150, physbc_3d :329) for comps scomp..scomp+ncomp-1. */
 int mgpu_fill_boundary(const mgpu_params* p, mgpu_fab* s, int scomp, int bccomp, int ncomp,
                        const int* adv_bc, const int* pmask);
+/* The same for a multifab of nfabs boxes on this rank (FBoxLib multifab_fill_boundary: same-level box-to-box copies,
+ * periodic images included, then multifab_physbc on each box where it touches the domain boundary).  adv_bc is the
+ * DOMAIN's table (bc_level index 0, define_bc_tower.f90:150-197); the per-box tables are derived from it. */
+int mgpu_fill_boundary_mf(const mgpu_params* p, int nfabs, mgpu_fab* s, int scomp, int bccomp, int ncomp,
+                          const int* adv_bc, const int* pmask);
 
 /* ---- multi-GPU: one slab per rank along the slowest index (z in 3-D, y in 2-D); replaces the MPI ghost
  * exchange inside FBoxLib's multifab_fill_boundary (call sites: SURVEY.md section 2d) by NCCL send/recv between
@@ -314,6 +319,14 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
                          mgpu_fab* const* umac, const double* w0, mgpu_fab* etarhoflux,
                          const double* rho0_old, const double* rho0_new, const double* p0_dummy,
                          const double* rho0_predicted_edge, const int* adv_bc, const int* pmask);
+/* density_advance over a multifab of nfabs boxes on this rank (the reference's test_advect lays 64^3 out as 8 x 32^3,
+ * Exec/UNIT_TESTS/test_advect/gr0_3d): arrays of nfabs fabs, sedge / sflux / umac dm arrays of nfabs fabs, adv_bc the
+ * domain's table.  General path of density_advance.f90:20, every ghost fill through the multifab fill above. */
+int mgpu_density_advance_mf(const mgpu_params* p, int which_step, int nfabs, mgpu_fab* sold, mgpu_fab* snew,
+                            mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force, mgpu_fab* const* umac,
+                            const double* w0, mgpu_fab* etarhoflux, const double* rho0_old, const double* rho0_new,
+                            const double* p0_dummy, const double* rho0_predicted_edge, const int* adv_bc,
+                            const int* pmask);
 
 /* ---- force builders inside the L4 drivers ----------------------------------------
  * mkrhohforce (Source/mkscalforce.f90:31; _2d :249, _3d :310), planar: writes comp rhoh_comp of scal_force on the

@@ -146,6 +146,13 @@ OPERATORS = {
                         + [c_int_p] * 2),
 }
 
+# several boxes per rank: the CUDA library only (the oracle's multifab is one box covering the domain)
+MULTIBOX = {
+    "mgpu_fill_boundary_mf": (C.c_int, [P_, C.c_int, F_, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p]),
+    "mgpu_density_advance_mf": (C.c_int, [P_, C.c_int, C.c_int, F_, F_, FF_, FF_, F_, FF_, c_double_p, F_]
+                                + [c_double_p] * 4 + [c_int_p] * 2),
+}
+
 # symbols only the library has
 LIFECYCLE = {
     "mgpu_init": (C.c_int, [C.c_int]),
@@ -188,4 +195,4 @@ def declare(lib, prefix):
 
 
 def all_symbols():
-    return ["mgpu_" + n for n in OPERATORS] + list(LIFECYCLE)
+    return ["mgpu_" + n for n in OPERATORS] + list(LIFECYCLE) + list(MULTIBOX)

@@ -158,6 +158,7 @@ struct Resident {
   bool pinned = false;
 };
 static std::map<const double*, Resident> g_res;
+static const int NODAL_OF[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
 
 struct Call {
   const mgpu_params& P;
@@ -585,8 +586,128 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
 }
 
 
+// ---- density_advance over several boxes of one rank (general path, statement by statement) ------------------------
+// What density_advance.f90:20 does with a multifab of nfabs boxes: every stage runs box by box, every ghost fill is
+// the multifab fill (box-to-box copies with the periodic images, then the physical BCs of each box).  The reference's
+// unit test lays 64^3 out as 8 boxes of 32^3 (Exec/UNIT_TESTS/test_advect/gr0_3d).
+struct BoxSet {
+  int n;
+  std::vector<const int*> lo, hi, bc;  // per box: valid range and its own adv_bc table
+};
+static void fill_mf(const mgpu_params& P, const BoxSet& B, std::vector<DV>& f, int ng, const int* nodal, int scomp, int bccomp,
+                    int ncomp, const int* pmask, bool same_boundary = false) {
+  fill_boundary_mf_dev(P, B.n, f.data(), B.lo.data(), B.hi.data(), ng, nodal, scomp, bccomp, ncomp, B.bc.data(), pmask,
+                       same_boundary);
+}
+static void density_advance_mf_dev(const mgpu_params& P, int which_step, const BoxSet& B, std::vector<DV>& sold,
+                                   std::vector<DV>& snew, std::vector<DV>* sedge, std::vector<DV>* sflux,
+                                   std::vector<DV>& scal_force, std::vector<DV>* umac, const double* w0_h,
+                                   std::vector<DV>& eta, const double* rho0_old_h, const double* rho0_new_h,
+                                   const double* rho0_pe_h, int ng_s, int ng_f, const int* pmask) {
+  const int dm = P.dm, nr = P.nr, nf = B.n;
+  const int spt = P.species_pred_type;
+  const int foextrap_comp = dm + P.nscal + 2;  // variables.f90:119-121
+  std::vector<double> e_old(nr + 1), e_new(nr + 1);
+  cell_to_edge_host(rho0_old_h, e_old.data(), nr);  // density_advance.f90:90-91
+  cell_to_edge_host(rho0_new_h, e_new.data(), nr);
+  const double* w0 = upload_small(w0_h, nr + 1);
+  const double* rho0_old = upload_small(rho0_old_h, nr);
+  const double* rho0_new = upload_small(rho0_new_h, nr);
+  const double* rho0_pe = upload_small(rho0_pe_h, nr + 1);
+  const double* rho0_edge_old = upload_small(e_old.data(), nr + 1);
+  const double* rho0_edge_new = upload_small(e_new.data(), nr + 1);
+  const bool rx = spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X;
+  auto box_umac = [&](int i, DV* u) { for (int d = 0; d < dm; ++d) u[d] = umac[d][i]; };
+  auto box_faces = [&](std::vector<DV>* f, int i, DV* out) { for (int d = 0; d < dm; ++d) out[d] = f[d][i]; };
+  auto fill_umac = [&]() {  // addw0.f90:85-93
+    for (int d = 0; d < dm; ++d) fill_mf(P, B, umac[d], 1, NODAL_OF[d], 1, 1, 1, pmask);
+  };
+  for (int i = 0; i < nf; ++i) set_dev(scal_force[i].p, 0.0, scal_force[i].size());  // :101-103
+  if (rx) {  // :119-128
+    for (int i = 0; i < nf; ++i) {
+      DV u[3];
+      box_umac(i, u);
+      modify_scal_force_dev(P, scal_force[i], sold[i], u, rho0_old, rho0_edge_old, w0, P.rho_comp,
+                            spt == MGPU_PREDICT_RHO_AND_X, B.lo[i], B.hi[i], g_opt_exact == 0, false);
+    }
+    fill_mf(P, B, scal_force, ng_f, nullptr, P.rho_comp, foextrap_comp, 1, pmask);
+  }
+  for (int i = 0; i < nf; ++i) {  // :148
+    DV u[3];
+    box_umac(i, u);
+    addw0_dev(P, u, w0, 1.0, B.lo[i], B.hi[i]);
+  }
+  fill_umac();
+  for (int i = 0; i < nf; ++i)  // :160-171
+    species_form_dev(P, sold[i], rho0_old, rx, spt == MGPU_PREDICT_RHOPRIME_AND_X, true, B.lo[i], B.hi[i]);
+  if (rx) fill_mf(P, B, sold, ng_s, nullptr, P.spec_comp, foextrap_comp, P.nspec, pmask, true);
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) fill_mf(P, B, sold, ng_s, nullptr, P.rho_comp, foextrap_comp, 1, pmask);
+  auto edge = [&](int scomp, int ncomp, bool cons) {
+    for (int i = 0; i < nf; ++i) {
+      DV u[3], se[3];
+      box_umac(i, u);
+      box_faces(sedge, i, se);
+      for (int n = 0; n < ncomp; ++n) {
+        if (P.bds_type != 0) {  // density_advance.f90:183-185 etc.
+          size_t mark = arena_mark();
+          bds_dev(P, sold[i], se, u, scal_force[i], B.lo[i], B.hi[i], scomp - 1 + n, cons, ng_s, ng_f);
+          arena_release(mark);
+          continue;
+        }
+        edge_one_comp(P, sold[i], se, u, scal_force[i], B.lo[i], B.hi[i], B.bc[i], scomp - 1 + n, dm + scomp + n, false,
+                      cons, ng_s, ng_f);
+      }
+    }
+  };
+  if (spt == MGPU_PREDICT_RHOX) edge(P.spec_comp, P.nspec, true);  // :190-198
+  else edge(P.spec_comp, P.nspec, false);                            // :178-186
+  if (spt == MGPU_PREDICT_RHOX) {  // :204-213
+    for (int i = 0; i < nf; ++i)
+      for (int d = 0; d < dm; ++d) sum_comps_dev(sedge[d][i], P.rho_comp - 1, P.spec_comp - 1, P.nspec);
+  } else {
+    edge(P.rho_comp, 1, false);  // :216-224
+  }
+  for (int i = 0; i < nf; ++i)  // :229-240
+    species_form_dev(P, sold[i], rho0_old, rx, spt == MGPU_PREDICT_RHOPRIME_AND_X, false, B.lo[i], B.hi[i]);
+  if (spt == MGPU_PREDICT_RHOPRIME_AND_X) fill_mf(P, B, sold, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, pmask);
+  if (rx) fill_mf(P, B, sold, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, pmask);
+  if (P.ntrac >= 1) edge(P.trac_comp, P.ntrac, false);  // :242-252
+  for (int i = 0; i < nf; ++i) {                        // :258
+    DV u[3];
+    box_umac(i, u);
+    addw0_dev(P, u, w0, -1.0, B.lo[i], B.hi[i]);
+  }
+  fill_umac();
+  for (int i = 0; i < nf; ++i) {  // :280-366
+    FluxArgs fa;
+    fill_flux_args(P, fa, B.lo[i], B.hi[i]);
+    for (int d = 0; d < dm; ++d) { fa.sflux[d] = sflux[d][i]; fa.sedge[d] = sedge[d][i]; fa.umac[d] = umac[d][i]; }
+    fa.eta = eta[i];
+    fa.w0 = w0;
+    fa.rho0_old = rho0_old;
+    fa.rho0_edge_old = rho0_edge_old;
+    fa.rho0_new = (which_step == 1) ? rho0_old : rho0_new;
+    fa.rho0_edge_new = (which_step == 1) ? rho0_edge_old : rho0_edge_new;
+    fa.rho0_predicted_edge = rho0_pe;
+    set_dev(scal_force[i].p, 0.0, scal_force[i].size());  // :349-351
+    UpdArgs ua;
+    ua.dm = dm;
+    ua.dt = P.dt;
+    for (int d = 0; d < 3; ++d) ua.dx[d] = P.dx[d];
+    ua.vb = grown(B.lo[i], B.hi[i], dm, 0);
+    ua.sold = sold[i];
+    ua.snew = snew[i];
+    ua.force = scal_force[i];
+    for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d][i];
+    flux_update_all_dev(P, fa, ua, g_opt_exact != 0);
+  }
+  fill_mf(P, B, snew, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, pmask);
+  fill_mf(P, B, snew, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, pmask);
+  if (P.ntrac >= 1) fill_mf(P, B, snew, ng_s, nullptr, P.trac_comp, dm + P.trac_comp, P.ntrac, pmask);
+}
+
 // ---- shared pieces of the other L4 episodes ---------------------------------------------------------
-static const int NODAL_D[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+static const int (&NODAL_D)[3][3] = NODAL_OF;
 static void fill_faces_dev(const mgpu_params& P, DV* u, const int* lo, const int* hi, const int* adv_bc,
                            const int* pmask) {  // addw0.f90:85-93 / mkutrans.f90:105-115
   FillBatch fb;
@@ -1496,6 +1617,81 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
   c.zero_on_host(*scal_force);
   density_advance_dev(*p, which_step, so, sn, se, sf, fv, um, w0, eta, rho0_old, rho0_new, rho0_predicted_edge,
                       sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+// per-box adv_bc tables from the domain's (define_bc_tower.f90:150-197, 199-294: a face that does not lie on the
+// domain boundary is INTERIOR for every component)
+static void box_bc_tables(const mgpu_params& P, int nfabs, const mgpu_fab* f, const int* adv_bc, std::vector<std::vector<int>>& out) {
+  const int dm = P.dm, nbc = dm + P.nscal + 3;
+  out.assign(nfabs, std::vector<int>(adv_bc, adv_bc + dm * 2 * nbc));
+  for (int i = 0; i < nfabs; ++i)
+    for (int d = 0; d < dm; ++d) {
+      const bool at[2] = {f[i].lo[d] == P.domlo[d], f[i].hi[d] == P.domhi[d]};
+      for (int side = 0; side < 2; ++side)
+        if (!at[side])
+          for (int c = 0; c < nbc; ++c) out[i][d + dm * (side + 2 * c)] = MGPU_BC_INTERIOR;
+    }
+}
+
+int mgpu_fill_boundary_mf(const mgpu_params* p, int nfabs, mgpu_fab* s, int scomp, int bccomp, int ncomp,
+                          const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  if (nfabs < 1) throw Error("mgpu_fill_boundary_mf: nfabs must be at least 1");
+  Call c(p, (size_t)nfabs * nfabs * 27 * 256 + 65536);
+  std::vector<DV> v(nfabs);
+  std::vector<std::vector<int>> bcs;
+  box_bc_tables(*p, nfabs, s, adv_bc, bcs);
+  BoxSet B;
+  B.n = nfabs;
+  for (int i = 0; i < nfabs; ++i) {
+    v[i] = c.view(s[i], true, true);
+    B.lo.push_back(s[i].lo); B.hi.push_back(s[i].hi); B.bc.push_back(bcs[i].data());
+    if (s[i].ng != s[0].ng || s[i].nc != s[0].nc) throw Error("mgpu_fill_boundary_mf: the boxes of a multifab share ng and nc");
+  }
+  const bool nod = s[0].nodal[0] || s[0].nodal[1] || s[0].nodal[2];
+  fill_mf(*p, B, v, s[0].ng, nod ? s[0].nodal : nullptr, scomp, bccomp, ncomp, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+/* density_advance for a multifab of nfabs boxes on this rank (one level); arguments as mgpu_density_advance with
+ * arrays of nfabs fabs (sedge / sflux / umac: dm arrays of nfabs fabs).  adv_bc is the DOMAIN's table. */
+int mgpu_density_advance_mf(const mgpu_params* p, int which_step, int nfabs, mgpu_fab* sold, mgpu_fab* snew,
+                            mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force, mgpu_fab* const* umac,
+                            const double* w0, mgpu_fab* etarhoflux, const double* rho0_old, const double* rho0_new,
+                            const double* p0_dummy, const double* rho0_predicted_edge, const int* adv_bc,
+                            const int* pmask) {
+  MGPU_TRY
+  (void)p0_dummy;
+  if (p->spherical) throw Error("mgpu_density_advance_mf: spherical geometry not available on the device yet");
+  if (nfabs < 1) throw Error("mgpu_density_advance_mf: nfabs must be at least 1");
+  size_t scratch = 0;
+  for (int i = 0; i < nfabs; ++i)
+    scratch = std::max(scratch, std::max(make_edge_scal_scratch(*p, sold[i].lo, sold[i].hi), bds_scratch(*p, sold[i].lo, sold[i].hi)));
+  Call c(p, scratch + (size_t)(12 * (p->nr + 16)) * sizeof(double) + (size_t)nfabs * nfabs * 27 * 256 * 16 + 65536);
+  const int dm = p->dm;
+  std::vector<std::vector<int>> bcs;
+  box_bc_tables(*p, nfabs, sold, adv_bc, bcs);
+  BoxSet B;
+  B.n = nfabs;
+  std::vector<DV> so(nfabs), sn(nfabs), fv(nfabs), et(nfabs), se[3], sf[3], um[3];
+  for (int d = 0; d < dm; ++d) { se[d].resize(nfabs); sf[d].resize(nfabs); um[d].resize(nfabs); }
+  for (int i = 0; i < nfabs; ++i) {
+    B.lo.push_back(sold[i].lo); B.hi.push_back(sold[i].hi); B.bc.push_back(bcs[i].data());
+    so[i] = c.view(sold[i], true, true);
+    sn[i] = c.view(snew[i], true, true);
+    fv[i] = c.view(scal_force[i], false, true);
+    et[i] = c.view(etarhoflux[i], true, true);
+    for (int d = 0; d < dm; ++d) {
+      se[d][i] = c.view(sedge[d][i], true, true);
+      sf[d][i] = c.view(sflux[d][i], true, true);
+      um[d][i] = c.view(umac[d][i], true, true);
+    }
+  }
+  density_advance_mf_dev(*p, which_step, B, so, sn, se, sf, fv, um, w0, et, rho0_old, rho0_new, rho0_predicted_edge,
+                         sold[0].ng, scal_force[0].ng, pmask);
   c.finish();
   MGPU_CATCH
 }

@@ -9,6 +9,8 @@
 //   ghost fill     FBoxLib multifab_fill_boundary (periodic wrap) + Source/multifab_physbc.f90:150,329
 // All are HBM-bound: one thread per zone/face, x-contiguous so every warp reads/writes whole lines.
 #include "mgpu_halo.cuh"
+#include <algorithm>
+
 #include "mgpu_stream.cuh"
 
 namespace mgpu {
@@ -754,6 +756,129 @@ void fill_batch_abort() {
   g_batching = false;
   g_batch_slab.clear();
   g_batch.clear();
+}
+
+// ---- several boxes per rank: FBoxLib multifab_fill_boundary + multifab_physbc for a list of fabs -----------------------
+// Every ghost cell of box i that lies inside the valid region of a box j (j = i included) shifted by a periodic image
+// of the domain takes that box's value; then the physical BCs of each box on the faces where it touches the domain
+// boundary.  One launch copies every (destination, source, image) intersection of a component range.
+struct BoxCopy {
+  double* dst;
+  const double* src;
+  int lo[3], n[3];      // intersection in destination indices
+  int dlo[3], dn[2];    // destination fab origin and extents (x, y)
+  int slo[3], sn[2];    // source fab origin and extents
+  int shift[3];         // source index = destination index - shift
+  int vlo[3], vhi[3];   // destination valid region (skipped: only ghost cells are written)
+  long dcs, scs;
+  int ncomp;
+};
+__global__ void k_box_copies(const BoxCopy* __restrict__ cs, int ncopies) {
+  const BoxCopy c = cs[blockIdx.y];
+  const long npts = (long)c.n[0] * c.n[1] * c.n[2];
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < npts; t += (long)gridDim.x * blockDim.x) {
+    const int ix = c.lo[0] + (int)(t % c.n[0]);
+    const long r = t / c.n[0];
+    const int iy = c.lo[1] + (int)(r % c.n[1]), iz = c.lo[2] + (int)(r / c.n[1]);
+    if (ix >= c.vlo[0] && ix <= c.vhi[0] && iy >= c.vlo[1] && iy <= c.vhi[1] && iz >= c.vlo[2] && iz <= c.vhi[2]) continue;
+    const long od = (ix - c.dlo[0]) + (long)c.dn[0] * ((iy - c.dlo[1]) + (long)c.dn[1] * (iz - c.dlo[2]));
+    const long os = (ix - c.shift[0] - c.slo[0]) +
+                    (long)c.sn[0] * ((iy - c.shift[1] - c.slo[1]) + (long)c.sn[1] * (iz - c.shift[2] - c.slo[2]));
+    for (int q = 0; q < c.ncomp; ++q) c.dst[od + c.dcs * q] = c.src[os + c.scs * q];
+  }
+}
+
+void fill_boundary_mf_dev(const mgpu_params& P, int nfabs, const DV* fabs, const int* const* lo, const int* const* hi, int ng,
+                          const int* nodal, int scomp, int bccomp, int ncomp, const int* const* adv_bc, const int* pmask,
+                          bool same_boundary) {
+  if (ng == 0) return;
+  if (comm_size() > 1) throw Error("fill_boundary: several boxes per rank and several ranks at once are not built");
+  const int dm = P.dm;
+  std::vector<BoxCopy> copies;
+  int nshift[3] = {0, 0, 0};
+  for (int d = 0; d < dm; ++d) nshift[d] = pmask[d] ? 1 : 0;
+  for (int i = 0; i < nfabs; ++i) {
+    int glo[3] = {0, 0, 0}, ghi[3] = {0, 0, 0}, vlo[3] = {0, 0, 0}, vhi[3] = {0, 0, 0};
+    for (int d = 0; d < dm; ++d) {
+      vlo[d] = lo[i][d];
+      vhi[d] = hi[i][d] + (nodal ? nodal[d] : 0);
+      glo[d] = vlo[d] - ng;
+      ghi[d] = vhi[d] + ng;
+    }
+    for (int j = 0; j < nfabs; ++j)
+      for (int sz = -nshift[2]; sz <= nshift[2]; ++sz)
+        for (int sy = -nshift[1]; sy <= nshift[1]; ++sy)
+          for (int sx = -nshift[0]; sx <= nshift[0]; ++sx) {
+            if (i == j && sx == 0 && sy == 0 && sz == 0) continue;
+            const int sh[3] = {sx * (P.domhi[0] - P.domlo[0] + 1), sy * (P.domhi[1] - P.domlo[1] + 1),
+                               sz * (P.domhi[2] - P.domlo[2] + 1)};
+            BoxCopy c;
+            bool empty = false;
+            for (int d = 0; d < 3; ++d) {
+              if (d >= dm) { c.lo[d] = 0; c.n[d] = 1; c.shift[d] = 0; continue; }
+              const int slo = lo[j][d] + sh[d], shi = hi[j][d] + (nodal ? nodal[d] : 0) + sh[d];
+              const int a = std::max(glo[d], slo), b = std::min(ghi[d], shi);
+              if (a > b) { empty = true; break; }
+              c.lo[d] = a;
+              c.n[d] = b - a + 1;
+              c.shift[d] = sh[d];
+            }
+            if (empty) continue;
+            c.dst = fabs[i].p + fabs[i].cs * (scomp - 1);
+            c.src = fabs[j].p + fabs[j].cs * (scomp - 1);
+            for (int d = 0; d < 3; ++d) {
+              c.dlo[d] = fabs[i].lo[d];
+              c.slo[d] = fabs[j].lo[d];
+              c.vlo[d] = d < dm ? vlo[d] : 0;
+              c.vhi[d] = d < dm ? vhi[d] : 0;
+            }
+            c.dn[0] = fabs[i].n[0]; c.dn[1] = fabs[i].n[1];
+            c.sn[0] = fabs[j].n[0]; c.sn[1] = fabs[j].n[1];
+            c.dcs = fabs[i].cs; c.scs = fabs[j].cs;
+            c.ncomp = ncomp;
+            copies.push_back(c);
+          }
+  }
+  // Face-centred data on a periodic domain stores the face on the domain boundary twice (lo and hi+1), so a ghost
+  // face can have two images.  They hold the same value in MAESTRO's data; to be deterministic whatever the data, the
+  // image reached with the fewest periodic shifts is written last (a ghost face that exists unshifted in direction d
+  // takes that one: the same-index rule of a single box wrapping onto itself).
+  auto nsh = [](const BoxCopy& c) { return (c.shift[0] != 0) + (c.shift[1] != 0) + (c.shift[2] != 0); };
+  std::stable_sort(copies.begin(), copies.end(), [&](const BoxCopy& a, const BoxCopy& b) { return nsh(a) > nsh(b); });
+  if (!copies.empty()) {
+    if (copies.size() > 65535) throw Error("fill_boundary: too many box intersections");
+    const BoxCopy* d_c = reinterpret_cast<const BoxCopy*>(upload_small(reinterpret_cast<const double*>(copies.data()),
+                                                                      (copies.size() * sizeof(BoxCopy) + 7) / 8));
+    size_t first = 0;
+    while (first < copies.size()) {  // one launch per number of shifted directions, most-shifted first
+      size_t last = first;
+      long mx = 1;
+      while (last < copies.size() && nsh(copies[last]) == nsh(copies[first])) {
+        mx = std::max(mx, (long)copies[last].n[0] * copies[last].n[1] * copies[last].n[2]);
+        ++last;
+      }
+      dim3 g((unsigned)std::min<long>((mx + 255) / 256, 64), (unsigned)(last - first));
+      MGPU_TIMED(TAG_FILL, (k_box_copies<<<g, 256, 0, ctx().stream>>>(d_c + first, (int)(last - first))));
+      first = last;
+    }
+  }
+  for (int i = 0; i < nfabs; ++i) {  // physical BCs where the box touches the domain boundary (per-box table)
+    FillReq r;
+    r.P = P;
+    r.sfull = fabs[i];
+    for (int d = 0; d < 3; ++d) {
+      r.lo[d] = d < dm ? lo[i][d] : 0;
+      r.hi[d] = d < dm ? hi[i][d] : 0;
+      r.nodal[d] = nodal ? nodal[d] : 0;
+      r.pmask[d] = pmask[d];
+    }
+    r.ng = ng;
+    r.has_nodal = nodal != nullptr;
+    r.scomp = scomp; r.bccomp = bccomp; r.ncomp = ncomp;
+    r.adv_bc = adv_bc[i];
+    r.same_boundary = same_boundary;
+    fill_physbc(r);
+  }
 }
 
 void fill_boundary_dev(const mgpu_params& P, const DV& sfull, const int* lo, const int* hi, int ng,

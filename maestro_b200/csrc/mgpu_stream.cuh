@@ -93,6 +93,10 @@ struct FillBatch {  // RAII: a throw inside the batch drops the recorded request
   void finish() { done = true; fill_batch_finish(); }
   ~FillBatch() { if (!done) fill_batch_abort(); }
 };
+// several boxes on this rank: box-to-box ghost copies (periodic images included) + per-box physical BCs
+void fill_boundary_mf_dev(const mgpu_params& P, int nfabs, const DV* fabs, const int* const* lo, const int* const* hi, int ng,
+                          const int* nodal, int scomp, int bccomp, int ncomp, const int* const* adv_bc, const int* pmask,
+                          bool same_boundary);
 void fill_boundary_dev(const mgpu_params& P, const DV& s, const int* lo, const int* hi, int ng, const int* nodal,
                        int scomp, int bccomp, int ncomp, const int* adv_bc, const int* pmask, bool same_boundary);
 void sum_comps_dev(const DV& a, int dst, int c0, int ncomp);

@@ -26,7 +26,7 @@ def load():
                 "(there is no CPU fallback)" % LIB_PATH)
         _lib = C.CDLL(LIB_PATH)
         abi.declare(_lib, "mgpu_")
-        for name, (res, args) in abi.LIFECYCLE.items():
+        for name, (res, args) in list(abi.LIFECYCLE.items()) + list(abi.MULTIBOX.items()):
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
@@ -129,3 +129,38 @@ def download(fab, comp0=0, ncomp=-1):
 
 def upload(fab, comp0=0, ncomp=-1):
     _chk(load().mgpu_upload(C.c_void_p(fab.ptr), comp0, ncomp))
+
+
+# ---- several boxes per rank (multifab of nfabs boxes): the CUDA library's own entry points -----------------------------
+def _fab_array(fabs):
+    return (abi.mgpu_fab * len(fabs))(*[f.cfab() for f in fabs])
+
+
+def _fab_arrays(per_dir):
+    keep = [_fab_array(fs) for fs in per_dir]
+    return (abi.F_ * len(per_dir))(*[C.cast(k, abi.F_) for k in keep]), keep
+
+
+def fill_boundary_mf(p, fabs, scomp, bccomp, ncomp, adv_bc, pmask):
+    """multifab_fill_boundary + multifab_physbc over the boxes `fabs` of one rank; adv_bc = the domain's table"""
+    from .fab import as_int_p
+
+    bc, bcp = as_int_p(adv_bc)
+    pm, pmp = as_int_p(pmask)
+    _chk(load().mgpu_fill_boundary_mf(C.byref(p), len(fabs), _fab_array(fabs), scomp, bccomp, ncomp, bcp, pmp))
+
+
+def density_advance_mf(p, which_step, sold, snew, sedge, sflux, scal_force, umac, w0, etarhoflux, rho0_old, rho0_new,
+                       p0_dummy, rho0_predicted_edge, adv_bc, pmask):
+    """density_advance over lists of boxes (sedge / sflux / umac: dm lists of boxes); adv_bc = the domain's table"""
+    from .fab import as_double_p, as_int_p
+
+    keep = [as_double_p(x) for x in (w0, rho0_old, rho0_new, p0_dummy, rho0_predicted_edge)]
+    bc, bcp = as_int_p(adv_bc)
+    pm, pmp = as_int_p(pmask)
+    se, k1 = _fab_arrays(sedge)
+    sf, k2 = _fab_arrays(sflux)
+    um, k3 = _fab_arrays(umac)
+    _chk(load().mgpu_density_advance_mf(C.byref(p), which_step, len(sold), _fab_array(sold), _fab_array(snew), se, sf,
+                                        _fab_array(scal_force), um, keep[0][1], _fab_array(etarhoflux), keep[1][1],
+                                        keep[2][1], keep[3][1], keep[4][1], bcp, pmp))

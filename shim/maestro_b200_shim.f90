@@ -452,6 +452,29 @@ module maestro_b200_shim
        integer(c_int), intent(in) :: pmask(*)
      end function mgpu_density_advance_c
 
+     ! density_advance.f90:20 over the nfabs boxes of this rank's multifab (adv_bc: the domain's table)
+     integer(c_int) function mgpu_density_advance_mf_c(p, which_step, nfabs, sold, snew, sedge, sflux, scal_force, &
+          umac, w0, etarhoflux, rho0_old, rho0_new, p0_dummy, rho0_predicted_edge, adv_bc, pmask) &
+          bind(C, name="mgpu_density_advance_mf")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: which_step, nfabs
+       type(mgpu_fab), intent(inout) :: sold(*), snew(*), scal_force(*), etarhoflux(*)
+       type(c_ptr), intent(in) :: sedge(*), sflux(*), umac(*)
+       real(c_double), intent(in) :: w0(*), rho0_old(*), rho0_new(*), p0_dummy(*), rho0_predicted_edge(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_density_advance_mf_c
+
+     ! multifab_fill_boundary + multifab_physbc over the nfabs boxes of this rank's multifab
+     integer(c_int) function mgpu_fill_boundary_mf_c(p, nfabs, s, scomp, bccomp, ncomp, adv_bc, pmask) &
+          bind(C, name="mgpu_fill_boundary_mf")
+       import :: c_int, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs, scomp, bccomp, ncomp
+       type(mgpu_fab), intent(inout) :: s(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_fill_boundary_mf_c
+
      ! density_advance.f90:20, spherical
      integer(c_int) function mgpu_density_advance_sphr_c(p, g, which_step, sold, snew, sedge, sflux, &
           scal_force, umac, w0, w0mac, rho0_old, rho0_new, adv_bc, pmask) &
@@ -588,6 +611,7 @@ module maestro_b200_shim
   public :: mgpu_mk_rhoX_flux_sphr_c, mgpu_mk_rhoh_flux_sphr_c, mgpu_update_velocity_sphr_c
   public :: mgpu_mkutrans_sphr_c, mgpu_velpred_sphr_c, mgpu_modify_scal_force_sphr_c, mgpu_put_in_pert_form_sphr_c
   public :: mgpu_fill_boundary_c, mgpu_convert_rhoX_to_X_c, mgpu_modify_scal_force_c, mgpu_put_in_pert_form_c, mgpu_mkrhohforce_c, mgpu_mk_vel_force_c
+  public :: mgpu_density_advance_mf_c, mgpu_fill_boundary_mf_c
   public :: mgpu_density_advance_c, mgpu_density_advance_sphr_c, mgpu_enthalpy_advance_c, mgpu_velocity_advance_c, mgpu_advance_premac_c
   public :: mgpu_comm_unique_id, mgpu_comm_init, mgpu_comm_finalize, mgpu_set_option
   public :: mgpu_malloc, mgpu_free, mgpu_memcpy_h2d, mgpu_memcpy_d2h
