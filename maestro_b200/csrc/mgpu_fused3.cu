@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(BX* BY, 2)
         if constexpr (XF == 1) T[e] = T[e] * D[e];
         else T[e] = T[e] - sub;
       }
+      __syncwarp();  // the last pass runs in a partly active warp: reconverge before the shared-memory reads that follow
     }
   };
 
