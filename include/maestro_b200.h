@@ -309,6 +309,32 @@ int mgpu_density_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int whic
                               mgpu_fab* const* umac, const double* w0, const mgpu_fab* const* w0mac,
                               const double* rho0_old, const double* rho0_new, const int* adv_bc, const int* pmask);
 
+/* make_normal (fill_3d_data.f90:1280): the unit radial vector on the cell centres, ghost cells included. */
+int mgpu_make_normal(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* normal);
+
+/* mk_vel_force with spherical == 1 (mkforce.f90:22 -> mk_vel_force_3d_sphr :484), valid cells; the caller fills the
+ * ghost cells (mkforce.f90:209: bc comps 1..dm).  w0 is the radial array (0:nr_fine); w0_cart and grad w0 on the cell
+ * centres are built inside, as the reference's wrapper does (:92-127).  s(index_rho) is the density, normal and
+ * w0_force_cart the cell-centred fabs of make_normal / put_1d_array_on_cart(w0_force, vector). */
+int mgpu_mk_vel_force_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* vel_force, int is_final_update,
+                           const mgpu_fab* uold, const mgpu_fab* const* uedge, const double* w0,
+                           const mgpu_fab* const* w0mac, const mgpu_fab* gpi, const mgpu_fab* s, int index_rho,
+                           const mgpu_fab* normal, const double* rho0, const double* grav, const mgpu_fab* w0_force_cart,
+                           int do_add_utilde_force);
+
+/* advance_premac (advance_premac.f90:21) and velocity_advance (velocity_advance.f90:16) with spherical == 1 as
+ * device-resident episodes; argument lists of the Fortran drivers (normal, w0mac, w0_force_cart included). */
+int mgpu_advance_premac_sphr(const mgpu_params* p, const mgpu_geom* g, const mgpu_fab* uold, const mgpu_fab* sold,
+                             mgpu_fab* const* umac, const mgpu_fab* gpi, const mgpu_fab* normal, const double* w0,
+                             const mgpu_fab* const* w0mac, const mgpu_fab* w0_force_cart, const double* rho0_old,
+                             const double* grav_cell_old, const int* adv_bc, const int* phys_bc, const int* pmask);
+int mgpu_velocity_advance_sphr(const mgpu_params* p, const mgpu_geom* g, const mgpu_fab* uold, mgpu_fab* unew,
+                               const mgpu_fab* sold, const mgpu_fab* rhohalf, mgpu_fab* const* umac, const mgpu_fab* gpi,
+                               const mgpu_fab* normal, const double* w0, const mgpu_fab* const* w0mac,
+                               const mgpu_fab* w0_force_cart, const double* rho0_old, const double* rho0_nph,
+                               const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
+                               const int* adv_bc, const int* pmask);
+
 /* ---- L4 episode: density_advance (Source/density_advance.f90:20), planar, one level ------
  * Signature mirrors the Fortran argument list; sold is modified in place exactly as the reference
  * does (rhoX->X->rhoX, rho->rho'->rho round trips), umac is (umac+w0)-w0 on return, sedge, sflux,

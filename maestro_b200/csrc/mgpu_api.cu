@@ -958,6 +958,86 @@ static void velocity_advance_dev(const mgpu_params& P, const DV& uold, DV& unew,
   fill_boundary_dev(P, unew, lo, hi, ng_u, nullptr, 1, 1, dm, adv_bc, pmask, false);  // update_vel.f90:121
 }
 
+// ---- advance_premac and velocity_advance with spherical == 1 ------------------------------------------------------
+// The planar episodes above with the spherical operators: w0 reaches the cells and faces through w0_cart / w0mac, the
+// force is mk_vel_force_3d_sphr (mkforce.f90:484), the update is the spherical branch of update_velocity_3d.
+static void vel_force_sphr_full(const mgpu_params& P, const mgpu_geom& g, const Geom& gd, DV& force, bool is_final,
+                                const DV& uold, const DV* uedge, const double* w0_h, const DV* w0mac, const DV& gpi,
+                                const DV& rho1, const DV& normal, const double* rho0_h, const double* grav_h,
+                                const DV& w0fc, const int* lo, const int* hi, int ng_f, const int* adv_bc,
+                                const int* pmask) {
+  size_t mark = arena_mark();
+  mk_vel_force_sphr_dev(P, g, gd, force, is_final, uold, uedge, w0_h, w0mac, gpi, rho1, normal, rho0_h, grav_h, w0fc, lo,
+                        hi, true);
+  arena_release(mark);
+  fill_boundary_dev(P, force, lo, hi, ng_f, nullptr, 1, 1, 3, adv_bc, pmask, false);  // mkforce.f90:209
+}
+static size_t sphr_force_scratch(const int* lo, const int* hi) { return 4 * fab_bytes(lo, hi, 3, 0, 0, 3); }
+
+static void advance_premac_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const DV& uold, const DV& sold, DV* umac,
+                                    const DV& gpi, const DV& normal, const double* w0_h, const DV* w0mac, const DV& w0fc,
+                                    const double* rho0_old_h, const double* grav_h, const int* lo, const int* hi, int ng_u,
+                                    const int* adv_bc, const int* phys_bc, const int* pmask) {
+  const int dm = 3;
+  const int ng_f = P.ppm_trace_forces == 1 ? ng_u : 1;  // advance_premac.f90:62-66
+  Geom gd = make_geom(P, g);
+  int z3[3] = {0, 0, 0};
+  DV ufull = arena_fab(lo, hi, dm, ng_u, z3, dm), force = arena_fab(lo, hi, dm, ng_f, z3, dm);
+  DV utrans[3];
+  for (int d = 0; d < dm; ++d) utrans[d] = arena_fab(lo, hi, dm, 1, NODAL_D[d], 1);
+  set_dev(ufull.p, 0.0, ufull.size());
+  put_1d_array_on_cart_dev(P, g, gd, upload_small(w0_h, (size_t)g.nr_fine + 1), ufull, true, true, lo, hi);  // :75
+  fill_boundary_dev(P, ufull, lo, hi, ng_u, nullptr, 1, 1, dm, adv_bc, pmask, false);
+  if (ufull.size() != uold.size()) throw Error("advance_premac: internal size mismatch");
+  add_dev(ufull.p, uold.p, ufull.size());  // :76-78
+  mkutrans_dev(P, uold, ufull, utrans, nullptr, lo, hi, adv_bc, phys_bc, ng_u, w0mac);  // :90
+  fill_faces_dev(P, utrans, lo, hi, adv_bc, pmask);
+  vel_force_sphr_full(P, g, gd, force, false, uold, utrans, w0_h, w0mac, gpi, sold.comp(P.rho_comp - 1), normal, rho0_old_h,
+                      grav_h, w0fc, lo, hi, ng_f, adv_bc, pmask);  // :98
+  addw0_sphr_dev(utrans, w0mac, 1.0, lo, hi);  // :109
+  fill_faces_dev(P, utrans, lo, hi, adv_bc, pmask);
+  velpred_dev(P, uold, ufull, umac, utrans, force, nullptr, lo, hi, adv_bc, phys_bc, ng_u, ng_f, w0mac);  // :116
+}
+
+static void velocity_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const DV& uold, DV& unew, const DV& sold,
+                                      const DV& rhohalf, DV* umac, const DV& gpi, const DV& normal, const double* w0_h,
+                                      const DV* w0mac, const DV& w0fc, const double* rho0_old_h, const double* rho0_nph_h,
+                                      const double* grav_old_h, const double* grav_nph_h, const DV& sponge, const int* lo,
+                                      const int* hi, int ng_u, const int* adv_bc, const int* pmask) {
+  const int dm = 3;
+  const int ng_f = P.ppm_trace_forces == 0 ? 1 : ng_u;  // velocity_advance.f90:69-75
+  Geom gd = make_geom(P, g);
+  int z3[3] = {0, 0, 0};
+  DV force = arena_fab(lo, hi, dm, ng_f, z3, dm);
+  DV uedge[3];
+  for (int d = 0; d < dm; ++d) uedge[d] = arena_fab(lo, hi, dm, 0, NODAL_D[d], dm);
+  vel_force_sphr_full(P, g, gd, force, false, uold, umac, w0_h, w0mac, gpi, sold.comp(P.rho_comp - 1), normal, rho0_old_h,
+                      grav_old_h, w0fc, lo, hi, ng_f, adv_bc, pmask);  // :80
+  addw0_sphr_dev(umac, w0mac, 1.0, lo, hi);  // :90
+  fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
+  for (int c = 0; c < dm; ++c) {  // :102-109
+    size_t mark = arena_mark();
+    if (P.bds_type != 0) bds_dev(P, uold, uedge, umac, force, lo, hi, c, false, ng_u, ng_f);
+    else edge_one_comp(P, uold, uedge, umac, force, lo, hi, adv_bc, c, 1 + c, true, false, ng_u, ng_f);
+    arena_release(mark);
+  }
+  addw0_sphr_dev(umac, w0mac, -1.0, lo, hi);  // :115
+  fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
+  vel_force_sphr_full(P, g, gd, force, true, uold, umac, w0_h, w0mac, gpi, rhohalf.comp(0), normal, rho0_nph_h, grav_nph_h,
+                      w0fc, lo, hi, ng_f, adv_bc, pmask);  // :122
+  VelArgs a;
+  a.dm = dm;
+  a.do_sponge = P.do_sponge != 0;
+  a.dt = P.dt;
+  for (int d = 0; d < 3; ++d) a.dx[d] = P.dx[d];
+  a.vb = grown(lo, hi, dm, 0);
+  a.uold = uold; a.unew = unew; a.force = force; a.sponge = sponge;
+  for (int d = 0; d < dm; ++d) { a.umac[d] = umac[d]; a.uedge[d] = uedge[d]; }
+  a.w0 = nullptr;
+  update_velocity_sphr_dev(a, w0mac);  // :132
+  fill_boundary_dev(P, unew, lo, hi, ng_u, nullptr, 1, 1, dm, adv_bc, pmask, false);  // update_vel.f90:121
+}
+
 // enthalpy_advance (Source/enthalpy_advance.f90:16)
 static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold, DV& snew, DV* sedge, DV* sflux,
                                  DV& scal_force, const DV& thermal, DV* umac, const double* w0_h,
@@ -2053,6 +2133,91 @@ int mgpu_density_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int whic
   c.views(w0mac, 0, true, false, wm);
   density_advance_sphr_dev(*p, *g, which_step, so, sn, se, sf, fv, um, w0, wm, rho0_old, rho0_new, sold->lo, sold->hi,
                            sold->ng, scal_force->ng, adv_bc, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_make_normal(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* normal) {
+  MGPU_TRY
+  need_sphr(p, g);
+  Call c(p, geom_scratch(g));
+  Geom gd = make_geom(*p, *g);
+  for (int i = 0; i < nfabs; ++i) {
+    if (normal[i].nc < 3) throw Error("make_normal: normal needs three components");
+    DV nv = c.view(normal[i], false, true);
+    make_normal_dev(gd, nv, normal[i].lo, normal[i].hi, normal[i].ng);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_mk_vel_force_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* vel_force, int is_final_update,
+                           const mgpu_fab* uold, const mgpu_fab* const* uedge, const double* w0,
+                           const mgpu_fab* const* w0mac, const mgpu_fab* gpi, const mgpu_fab* s, int index_rho,
+                           const mgpu_fab* normal, const double* rho0, const double* grav, const mgpu_fab* w0_force_cart,
+                           int do_add_utilde_force) {
+  MGPU_TRY
+  need_sphr(p, g);
+  if (!p->spherical) throw Error("mk_vel_force_sphr: params.spherical must be 1");
+  size_t need = 0;
+  for (int i = 0; i < nfabs; ++i) need = std::max(need, sphr_force_scratch(vel_force[i].lo, vel_force[i].hi));
+  Call c(p, need + geom_scratch(g) + (size_t)(4 * (g->nr_fine + 4)) * sizeof(double));
+  Geom gd = make_geom(*p, *g);
+  for (int i = 0; i < nfabs; ++i) {
+    DV fv = c.view(vel_force[i], false, true), uo = c.view(uold[i], true, false), gp = c.view(gpi[i], true, false);
+    DV sv = c.view(s[i], crange(index_rho - 1, 1), (cmask_t)0), nm = c.view(normal[i], true, false);
+    DV wf = c.view(w0_force_cart[i], true, false);
+    DV ue[3], wm[3];
+    c.views(uedge, i, true, false, ue);
+    c.views(w0mac, i, true, false, wm);
+    size_t mark = arena_mark();
+    mk_vel_force_sphr_dev(*p, *g, gd, fv, is_final_update != 0, uo, ue, w0, wm, gp, sv.comp(index_rho - 1), nm, rho0, grav, wf,
+                          vel_force[i].lo, vel_force[i].hi, do_add_utilde_force != 0);
+    arena_release(mark);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_advance_premac_sphr(const mgpu_params* p, const mgpu_geom* g, const mgpu_fab* uold, const mgpu_fab* sold,
+                             mgpu_fab* const* umac, const mgpu_fab* gpi, const mgpu_fab* normal, const double* w0,
+                             const mgpu_fab* const* w0mac, const mgpu_fab* w0_force_cart, const double* rho0_old,
+                             const double* grav_cell_old, const int* adv_bc, const int* phys_bc, const int* pmask) {
+  MGPU_TRY
+  need_sphr(p, g);
+  if (!p->spherical) throw Error("advance_premac_sphr: params.spherical must be 1");
+  Call c(p, advance_premac_scratch(*p, uold->lo, uold->hi, uold->ng) + sphr_force_scratch(uold->lo, uold->hi) +
+                geom_scratch(g) + (size_t)(6 * (g->nr_fine + 4)) * sizeof(double));
+  DV uo = c.view(*uold, true, false), so = c.view(*sold, crange(p->rho_comp - 1, 1), (cmask_t)0);
+  DV gp = c.view(*gpi, true, false), nm = c.view(*normal, true, false), wf = c.view(*w0_force_cart, true, false);
+  DV um[3], wm[3];
+  c.views((const mgpu_fab* const*)umac, 0, true, true, um);
+  c.views(w0mac, 0, true, false, wm);
+  advance_premac_sphr_dev(*p, *g, uo, so, um, gp, nm, w0, wm, wf, rho0_old, grav_cell_old, uold->lo, uold->hi, uold->ng,
+                          adv_bc, phys_bc, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_velocity_advance_sphr(const mgpu_params* p, const mgpu_geom* g, const mgpu_fab* uold, mgpu_fab* unew,
+                               const mgpu_fab* sold, const mgpu_fab* rhohalf, mgpu_fab* const* umac, const mgpu_fab* gpi,
+                               const mgpu_fab* normal, const double* w0, const mgpu_fab* const* w0mac,
+                               const mgpu_fab* w0_force_cart, const double* rho0_old, const double* rho0_nph,
+                               const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
+                               const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  need_sphr(p, g);
+  if (!p->spherical) throw Error("velocity_advance_sphr: params.spherical must be 1");
+  Call c(p, velocity_advance_scratch(*p, uold->lo, uold->hi, uold->ng) + sphr_force_scratch(uold->lo, uold->hi) +
+                geom_scratch(g) + (size_t)(6 * (g->nr_fine + 4)) * sizeof(double));
+  DV uo = c.view(*uold, true, false), un = c.view(*unew, true, true), gp = c.view(*gpi, true, false);
+  DV so = c.view(*sold, crange(p->rho_comp - 1, 1), (cmask_t)0), rh = c.view(*rhohalf, true, false);
+  DV sp = c.view(*sponge, true, false), nm = c.view(*normal, true, false), wf = c.view(*w0_force_cart, true, false);
+  DV um[3], wm[3];
+  c.views((const mgpu_fab* const*)umac, 0, true, true, um);
+  c.views(w0mac, 0, true, false, wm);
+  velocity_advance_sphr_dev(*p, *g, uo, un, so, rh, um, gp, nm, w0, wm, wf, rho0_old, rho0_nph, grav_cell_old,
+                            grav_cell_nph, sp, uold->lo, uold->hi, uold->ng, adv_bc, pmask);
   c.finish();
   MGPU_CATCH
 }

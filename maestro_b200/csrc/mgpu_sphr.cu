@@ -249,6 +249,65 @@ __global__ void k_pert_form_sphr(Geom g, DV s, Box3 vb, const double* s0, int ty
   s(ix[0], ix[1], ix[2]) = s(ix[0], ix[1], ix[2]) + mult * v;
 }
 
+// make_normal_3d_sphr (fill_3d_data.f90:1308)
+__global__ void k_make_normal(Geom g, DV n, Box3 gb) {
+  int ix[3];
+  if (!decode3(gb, ix)) return;
+  const double x = pos(g, 0, ix[0], true), y = pos(g, 1, ix[1], true), z = pos(g, 2, ix[2], true);
+  const double radius = sqrt(x * x + y * y + z * z);
+  n(ix[0], ix[1], ix[2], 0) = x * (1.0 / radius);
+  n(ix[0], ix[1], ix[2], 1) = y * (1.0 / radius);
+  n(ix[0], ix[1], ix[2], 2) = z * (1.0 / radius);
+}
+
+// mk_vel_force_3d_sphr (mkforce.f90:484): buoyancy with the radial gravity vector, pressure gradient, Coriolis and
+// centrifugal terms about the z axis, w0 force, and the utilde . grad w0 term (:617-640); expression order of the source
+struct VelForceSphr {
+  Geom g;
+  DV force, uold, gpi, rho, normal, w0_cart, gradw0, w0f, rho0c, gravc, ue[3], w0m[2];
+  Box3 vb;
+  bool is_final, add_utilde;
+  double omega, rho_cut;
+};
+__global__ void k_vel_force_sphr(VelForceSphr a) {
+  int ix[3];
+  if (!decode3(a.vb, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  const double yy = a.g.prob_lo[1] + ((double)j + 0.5) * a.g.dx[1] - a.g.center[1];
+  const double xx = a.g.prob_lo[0] + ((double)i + 0.5) * a.g.dx[0] - a.g.center[0];
+  const double rho = a.rho(i, j, k);
+  double rhopert = rho - a.rho0c(i, j, k, 0);
+  const bool outside = rho < a.rho_cut;
+  if (outside) rhopert = 0.0;
+  const double omega = a.omega;
+  double cen[3] = {-omega * omega * xx, -omega * omega * yy, 0.0};
+  if (outside) cen[0] = cen[1] = cen[2] = 0.0;
+  double cor[3];
+  if (a.is_final) {
+    cor[0] = -(2.0 * omega * 0.5 * (a.ue[1](i, j, k) + a.w0m[1](i, j, k) + a.ue[1](i, j + 1, k) + a.w0m[1](i, j + 1, k)));
+    cor[1] = 2.0 * omega * 0.5 * (a.ue[0](i, j, k) + a.w0m[0](i, j, k) + a.ue[0](i + 1, j, k) + a.w0m[0](i + 1, j, k));
+    cor[2] = 0.0;
+  } else {
+    cor[0] = -(2.0 * omega * (a.uold(i, j, k, 1) + a.w0_cart(i, j, k, 1)));
+    cor[1] = 2.0 * omega * (a.uold(i, j, k, 0) + a.w0_cart(i, j, k, 0));
+    cor[2] = 0.0;
+  }
+  double f[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    f[c] = -cor[c] - cen[c] + (rhopert * a.gravc(i, j, k, c) - a.gpi(i, j, k, c)) / rho - a.w0f(i, j, k, c);
+  if (a.add_utilde) {
+    const double ut = 0.5 * (a.ue[0](i, j, k) + a.ue[0](i + 1, j, k)) * a.normal(i, j, k, 0) +
+                      0.5 * (a.ue[1](i, j, k) + a.ue[1](i, j + 1, k)) * a.normal(i, j, k, 1) +
+                      0.5 * (a.ue[2](i, j, k) + a.ue[2](i, j, k + 1)) * a.normal(i, j, k, 2);
+    const double gw = a.gradw0(i, j, k, 0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f[c] = f[c] - ut * gw * a.normal(i, j, k, c);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) a.force(i, j, k, c) = f[c];
+}
+
 Box3 mac_box(const int* lo, const int* hi, int d) {
   Box3 b;
   for (int q = 0; q < 3; ++q) {
@@ -360,6 +419,51 @@ void pert_form_sphr_dev(const mgpu_geom& g, const Geom& gd, const DV& s, const d
   Box3 vb = grown(lo, hi, 3, 0);
   MGPU_TIMED(TAG_GLUE, (k_pert_form_sphr<<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(gd, s.comp(comp - 1), vb, s0_dev, type,
                                                                                            flag ? -1 : 1)));
+}
+
+void make_normal_dev(const Geom& gd, const DV& normal, const int* lo, const int* hi, int ng) {
+  Box3 gb = grown(lo, hi, 3, ng);
+  MGPU_TIMED(TAG_GLUE, (k_make_normal<<<grid3(gb, 256), block3(gb, 256), 0, ctx().stream>>>(gd, normal, gb)));
+}
+
+// the spherical branch of mk_vel_force (mkforce.f90:22): w0 and grad w0 on the cell centres (:92-127), rho0 and the
+// gravity vector on the cell centres (:529-530), then the force on the valid cells.  Temporaries from the arena.
+void mk_vel_force_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const Geom& gd, const DV& force, bool is_final,
+                           const DV& uold, const DV* uedge, const double* w0_h, const DV* w0mac, const DV& gpi,
+                           const DV& rho1, const DV& normal, const double* rho0_h, const double* grav_h,
+                           const DV& w0_force_cart, const int* lo, const int* hi, bool add_utilde) {
+  const int nr = g.nr_fine;
+  const int z3[3] = {0, 0, 0};
+  auto tmp = [&](int nc) {
+    DV v = make_view(nullptr, lo, hi, 3, 0, z3, nc);
+    v.p = arena_alloc((size_t)v.size());
+    return v;
+  };
+  DV w0_cart = tmp(3), gradw0 = tmp(1), rho0c = tmp(1), gravc = tmp(3);
+  set_dev(w0_cart.p, 0.0, w0_cart.size());
+  set_dev(gradw0.p, 0.0, gradw0.size());
+  if (P.evolve_base_state) {
+    put_1d_array_on_cart_dev(P, g, gd, upload_small(w0_h, (size_t)nr + 1), w0_cart, true, true, lo, hi);
+    if (add_utilde) {
+      std::vector<double> gr(nr);
+      for (int r = 0; r < nr; ++r) gr[r] = (w0_h[r + 1] - w0_h[r]) / g.dr;
+      put_1d_array_on_cart_dev(P, g, gd, upload_small(gr.data(), (size_t)nr), gradw0, false, false, lo, hi);
+    }
+  }
+  set_dev(force.p, 0.0, force.size());
+  put_1d_array_on_cart_dev(P, g, gd, upload_small(rho0_h, (size_t)nr), rho0c, false, false, lo, hi);
+  put_1d_array_on_cart_dev(P, g, gd, upload_small(grav_h, (size_t)nr), gravc, false, true, lo, hi);
+  VelForceSphr a;
+  a.g = gd;
+  a.force = force; a.uold = uold; a.gpi = gpi; a.rho = rho1; a.normal = normal; a.w0_cart = w0_cart; a.gradw0 = gradw0;
+  a.w0f = w0_force_cart; a.rho0c = rho0c; a.gravc = gravc;
+  for (int d = 0; d < 3; ++d) a.ue[d] = uedge[d];
+  a.w0m[0] = w0mac[0]; a.w0m[1] = w0mac[1];
+  a.vb = grown(lo, hi, 3, 0);
+  a.is_final = is_final; a.add_utilde = add_utilde;
+  a.omega = P.omega;
+  a.rho_cut = P.buoyancy_cutoff_factor * P.base_cutoff_density;
+  MGPU_TIMED(TAG_GLUE, (k_vel_force_sphr<<<grid3(a.vb, 256), block3(a.vb, 256), 0, ctx().stream>>>(a)));
 }
 
 }  // namespace mgpu

@@ -36,4 +36,10 @@ void modify_scal_force_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const 
 void pert_form_sphr_dev(const mgpu_geom& g, const Geom& gd, const DV& s, const double* s0_dev, int comp, bool flag,
                         const int* lo, const int* hi);
 
+void make_normal_dev(const Geom& gd, const DV& normal, const int* lo, const int* hi, int ng);
+void mk_vel_force_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const Geom& gd, const DV& force, bool is_final,
+                           const DV& uold, const DV* uedge, const double* w0_h, const DV* w0mac, const DV& gpi,
+                           const DV& rho1, const DV& normal, const double* rho0_h, const double* grav_h,
+                           const DV& w0_force_cart, const int* lo, const int* hi, bool add_utilde);
+
 }  // namespace mgpu

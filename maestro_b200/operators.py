@@ -193,6 +193,40 @@ class Operators:
                    ptrs[0][0], ptrs[1][0], fab_ptr(scal_force), ptrs[2][0], keep[0][1], ptrs[3][0], keep[1][1],
                    keep[2][1], bcp, pmp)
 
+    def make_normal(self, p, geom, normal):
+        self._call("make_normal", C.byref(p), C.byref(geom.c), 1, fab_ptr(normal))
+
+    def mk_vel_force_sphr(self, p, geom, vel_force, is_final_update, uold, uedge, w0, w0mac, gpi, s, index_rho, normal,
+                          rho0, grav, w0_force_cart, do_add_utilde_force):
+        keep = [as_double_p(x) for x in (w0, rho0, grav)]
+        ue, k1 = fab_pp(uedge)
+        wm, k2 = fab_pp(w0mac)
+        self._call("mk_vel_force_sphr", C.byref(p), C.byref(geom.c), 1, fab_ptr(vel_force), int(is_final_update),
+                   fab_ptr(uold), ue, keep[0][1], wm, fab_ptr(gpi), fab_ptr(s), index_rho, fab_ptr(normal), keep[1][1],
+                   keep[2][1], fab_ptr(w0_force_cart), int(do_add_utilde_force))
+
+    def advance_premac_sphr(self, p, geom, uold, sold, umac, gpi, normal, w0, w0mac, w0_force_cart, rho0_old,
+                            grav_cell_old, adv_bc, phys_bc, pmask):
+        keep = [as_double_p(x) for x in (w0, rho0_old, grav_cell_old)]
+        bc, bcp = as_int_p(adv_bc)
+        pb, pbp = as_int_p(phys_bc)
+        pm, pmp = as_int_p(pmask)
+        um, k1 = fab_pp(umac)
+        wm, k2 = fab_pp(w0mac)
+        self._call("advance_premac_sphr", C.byref(p), C.byref(geom.c), fab_ptr(uold), fab_ptr(sold), um, fab_ptr(gpi),
+                   fab_ptr(normal), keep[0][1], wm, fab_ptr(w0_force_cart), keep[1][1], keep[2][1], bcp, pbp, pmp)
+
+    def velocity_advance_sphr(self, p, geom, uold, unew, sold, rhohalf, umac, gpi, normal, w0, w0mac, w0_force_cart,
+                              rho0_old, rho0_nph, grav_cell_old, grav_cell_nph, sponge, adv_bc, pmask):
+        keep = [as_double_p(x) for x in (w0, rho0_old, rho0_nph, grav_cell_old, grav_cell_nph)]
+        bc, bcp = as_int_p(adv_bc)
+        pm, pmp = as_int_p(pmask)
+        um, k1 = fab_pp(umac)
+        wm, k2 = fab_pp(w0mac)
+        self._call("velocity_advance_sphr", C.byref(p), C.byref(geom.c), fab_ptr(uold), fab_ptr(unew), fab_ptr(sold),
+                   fab_ptr(rhohalf), um, fab_ptr(gpi), fab_ptr(normal), keep[0][1], wm, fab_ptr(w0_force_cart),
+                   keep[1][1], keep[2][1], keep[3][1], keep[4][1], fab_ptr(sponge), bcp, pmp)
+
     # ---- L4 driver -----------------------------------------------------------------------------
     def density_advance(self, p, which_step, sold, snew, sedge, sflux, scal_force, umac, w0, etarhoflux, rho0_old,
                         rho0_new, p0_dummy, rho0_predicted_edge, adv_bc, pmask):

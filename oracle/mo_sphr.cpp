@@ -444,6 +444,145 @@ extern std::string mo_g_err;
   }                                      \
   return 0;
 
+// make_normal_3d_sphr (fill_3d_data.f90:1308): unit radial vector at the cell centres, ghost cells included
+void make_normal_sphr(const mgpu_params& P, const mgpu_geom& g, Arr& normal, const int* lo, const int* hi, int ng) {
+  for_box(grown(lo, hi, 3, ng), [&](int i, int j, int k) {
+    const double x = pos(g, P, 0, i, true), y = pos(g, P, 1, j, true), z = pos(g, P, 2, k, true);
+    const double radius = std::sqrt(x * x + y * y + z * z);
+    normal(i, j, k, 0) = x * (1.0 / radius);
+    normal(i, j, k, 1) = y * (1.0 / radius);
+    normal(i, j, k, 2) = z * (1.0 / radius);
+  });
+}
+
+// mk_vel_force_3d_sphr (mkforce.f90:484) with the spherical preparation of its wrapper (mkforce.f90:92-127: w0 on the
+// cell centres as a vector, the radial gradient of w0 on the cell centres).  rho is a single-component view.
+void mk_vel_force_sphr_box(const mgpu_params& P, const mgpu_geom& g, Arr& vel_force, bool is_final_update, const Arr& uold,
+                           const Arr* uedge, const double* w0, const Arr* w0mac, const Arr& gpi, const Arr& rho,
+                           const Arr& normal, const double* rho0, const double* grav, const Arr& w0_force_cart,
+                           const int* lo, const int* hi, bool do_add_utilde_force) {
+  const int nr = g.nr_fine;
+  Box vb = grown(lo, hi, 3, 0);
+  auto cart = [&](int nc) { return Arr(vb.lo[0], vb.hi[0], vb.lo[1], vb.hi[1], vb.lo[2], vb.hi[2], nc); };
+  Arr w0_cart = cart(3), gradw0_cart = cart(1), rho0_cart = cart(1), grav_cart = cart(3);
+  w0_cart.fill(0.0);
+  gradw0_cart.fill(0.0);
+  if (P.evolve_base_state) {  // :109-126
+    put_1d_array_on_cart_sphr(P, g, true, true, w0, w0_cart, lo, hi);
+    if (do_add_utilde_force) {
+      std::vector<double> gradw0_rad(nr);
+      for (int r = 0; r < nr; ++r) gradw0_rad[r] = (w0[r + 1] - w0[r]) / g.dr;
+      put_1d_array_on_cart_sphr(P, g, false, false, gradw0_rad.data(), gradw0_cart, lo, hi);
+    }
+  }
+  vel_force.fill(0.0);  // :527
+  put_1d_array_on_cart_sphr(P, g, false, false, rho0, rho0_cart, lo, hi);
+  put_1d_array_on_cart_sphr(P, g, false, true, grav, grav_cart, lo, hi);
+  const double omega = P.omega;
+  const Arr &ue = uedge[0], &ve = uedge[1], &we = uedge[2];
+  for_box(vb, [&](int i, int j, int k) {
+    const double zz = g.prob_lo[2] + ((double)k + 0.5) * P.dx[2] - g.center[2];
+    const double yy = g.prob_lo[1] + ((double)j + 0.5) * P.dx[1] - g.center[1];
+    const double xx = g.prob_lo[0] + ((double)i + 0.5) * P.dx[0] - g.center[0];
+    (void)zz;
+    double rhopert = rho(i, j, k) - rho0_cart(i, j, k, 0);
+    const bool outside = rho(i, j, k) < P.buoyancy_cutoff_factor * P.base_cutoff_density;
+    if (outside) rhopert = 0.0;
+    double cen[3] = {-omega * omega * xx, -omega * omega * yy, 0.0};
+    if (outside) cen[0] = cen[1] = cen[2] = 0.0;
+    double cor[3];
+    if (is_final_update) {
+      cor[0] = -(2.0 * omega * 0.5 * (ve(i, j, k) + w0mac[1](i, j, k) + ve(i, j + 1, k) + w0mac[1](i, j + 1, k)));
+      cor[1] = 2.0 * omega * 0.5 * (ue(i, j, k) + w0mac[0](i, j, k) + ue(i + 1, j, k) + w0mac[0](i + 1, j, k));
+      cor[2] = 0.0;
+    } else {
+      cor[0] = -(2.0 * omega * (uold(i, j, k, 1) + w0_cart(i, j, k, 1)));
+      cor[1] = 2.0 * omega * (uold(i, j, k, 0) + w0_cart(i, j, k, 0));
+      cor[2] = 0.0;
+    }
+    for (int c = 0; c < 3; ++c)
+      vel_force(i, j, k, c) = -cor[c] - cen[c] + (rhopert * grav_cart(i, j, k, c) - gpi(i, j, k, c)) / rho(i, j, k) -
+                              w0_force_cart(i, j, k, c);
+  });
+  if (do_add_utilde_force) {  // :617-640
+    for_box(vb, [&](int i, int j, int k) {
+      const double Ut_dot_er = 0.5 * (ue(i, j, k) + ue(i + 1, j, k)) * normal(i, j, k, 0) +
+                               0.5 * (ve(i, j, k) + ve(i, j + 1, k)) * normal(i, j, k, 1) +
+                               0.5 * (we(i, j, k) + we(i, j, k + 1)) * normal(i, j, k, 2);
+      for (int c = 0; c < 3; ++c)
+        vel_force(i, j, k, c) = vel_force(i, j, k, c) - Ut_dot_er * gradw0_cart(i, j, k, 0) * normal(i, j, k, c);
+    });
+  }
+}
+
+static void fill_faces3(const mgpu_params& P, Arr* u, const int* lo, const int* hi, const int* pmask) {
+  for (int d = 0; d < 3; ++d) fill_boundary_face(P, u[d], lo, hi, 1, d, pmask);
+}
+
+// advance_premac (advance_premac.f90:21) with spherical == 1
+void advance_premac_sphr_box(const mgpu_params& P, const mgpu_geom& g, const Arr& uold, const Arr& sold, Arr* umac,
+                             const Arr& gpi, const Arr& normal, const double* w0, const Arr* w0mac,
+                             const Arr& w0_force_cart, const double* rho0_old, const double* grav_cell_old, const int* lo,
+                             const int* hi, int ng_u, const int* adv_bc, const int* phys_bc, const int* pmask) {
+  const int dm = 3;
+  const int ng_f = (P.ppm_trace_forces == 1) ? ng_u : 1;  // :62-66
+  Box gb = grown(lo, hi, dm, ng_u), fb = grown(lo, hi, dm, ng_f);
+  Arr ufull(gb.lo[0], gb.hi[0], gb.lo[1], gb.hi[1], gb.lo[2], gb.hi[2], dm);
+  Arr force(fb.lo[0], fb.hi[0], fb.lo[1], fb.hi[1], fb.lo[2], fb.hi[2], dm);
+  ufull.fill(0.0);
+  put_1d_array_on_cart_sphr(P, g, true, true, w0, ufull, lo, hi);  // :75, then its ghost fill (fill_3d_data.f90:110-128)
+  fill_boundary_box(P, ufull, lo, hi, ng_u, 1, 1, dm, adv_bc, pmask);
+  for (size_t q = 0; q < ufull.size(); ++q) ufull.p[q] = ufull.p[q] + uold.p[q];  // :76-78
+  std::vector<Arr> utrans(dm);
+  for (int d = 0; d < dm; ++d) {
+    Box b = grown(lo, hi, dm, 1);
+    b.hi[d] += 1;
+    utrans[d].alloc(b.lo[0], b.hi[0], b.lo[1], b.hi[1], b.lo[2], b.hi[2], 1);
+  }
+  mkutrans_box(P, uold, ufull, utrans.data(), nullptr, lo, hi, adv_bc, phys_bc, ng_u, w0mac);  // :90
+  fill_faces3(P, utrans.data(), lo, hi, pmask);
+  mk_vel_force_sphr_box(P, g, force, false, uold, utrans.data(), w0, w0mac, gpi, sold.comp(P.rho_comp - 1), normal,
+                        rho0_old, grav_cell_old, w0_force_cart, lo, hi, true);  // :98
+  fill_boundary_box(P, force, lo, hi, ng_f, 1, 1, dm, adv_bc, pmask);
+  addw0_sphr(utrans.data(), w0mac, lo, hi, 1.0);  // :109
+  fill_faces3(P, utrans.data(), lo, hi, pmask);
+  velpred_box(P, uold, ufull, umac, utrans.data(), force, nullptr, lo, hi, adv_bc, phys_bc, ng_u, w0mac);  // :116
+}
+
+// velocity_advance (velocity_advance.f90:16) with spherical == 1
+void velocity_advance_sphr_box(const mgpu_params& P, const mgpu_geom& g, const Arr& uold, Arr& unew, const Arr& sold,
+                               const Arr& rhohalf, Arr* umac, const Arr& gpi, const Arr& normal, const double* w0,
+                               const Arr* w0mac, const Arr& w0_force_cart, const double* rho0_old, const double* rho0_nph,
+                               const double* grav_cell_old, const double* grav_cell_nph, const Arr& sponge, const int* lo,
+                               const int* hi, int ng_u, const int* adv_bc, const int* pmask) {
+  const int dm = 3;
+  const int ng_f = (P.ppm_trace_forces == 0) ? 1 : ng_u;  // :69-75
+  Box fb = grown(lo, hi, dm, ng_f);
+  Arr force(fb.lo[0], fb.hi[0], fb.lo[1], fb.hi[1], fb.lo[2], fb.hi[2], dm);
+  mk_vel_force_sphr_box(P, g, force, false, uold, umac, w0, w0mac, gpi, sold.comp(P.rho_comp - 1), normal, rho0_old,
+                        grav_cell_old, w0_force_cart, lo, hi, true);  // :80
+  fill_boundary_box(P, force, lo, hi, ng_f, 1, 1, dm, adv_bc, pmask);
+  addw0_sphr(umac, w0mac, lo, hi, 1.0);  // :90
+  fill_faces3(P, umac, lo, hi, pmask);
+  std::vector<Arr> uedge(dm);
+  for (int d = 0; d < dm; ++d) {
+    Box b = grown(lo, hi, dm, 0);
+    b.hi[d] += 1;
+    uedge[d].alloc(b.lo[0], b.hi[0], b.lo[1], b.hi[1], b.lo[2], b.hi[2], dm);
+  }
+  for (int c = 0; c < dm; ++c) {  // :102-109
+    if (P.bds_type == 0) make_edge_scal_box(P, uold, uedge.data(), umac, force, lo, hi, adv_bc, c, 1 + c, true, false, ng_u);
+    else bds_box(P, uold, uedge.data(), umac, force, lo, hi, c, false);
+  }
+  addw0_sphr(umac, w0mac, lo, hi, -1.0);  // :115
+  fill_faces3(P, umac, lo, hi, pmask);
+  mk_vel_force_sphr_box(P, g, force, true, uold, umac, w0, w0mac, gpi, rhohalf.comp(0), normal, rho0_nph, grav_cell_nph,
+                        w0_force_cart, lo, hi, true);  // :122
+  fill_boundary_box(P, force, lo, hi, ng_f, 1, 1, dm, adv_bc, pmask);
+  update_velocity_sphr(P, uold, unew, umac, uedge.data(), force, sponge, w0mac, lo, hi);  // :132
+  fill_boundary_box(P, unew, lo, hi, ng_u, 1, 1, dm, adv_bc, pmask);  // update_vel.f90:121
+}
+
 static void need3(const mgpu_params* p) {
   if (p->dm != 3) fail("spherical geometry is 3-D only");
 }
@@ -633,6 +772,68 @@ int mo_density_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int which_
   views3(w0mac, 0, wm);
   density_advance_sphr_box(*p, *g, which_step, so, sn, se, sf, fo, um, w0, wm, rho0_old, rho0_new, sold->lo, sold->hi,
                            sold->ng, scal_force->ng, adv_bc, pmask);
+  MO_CATCH
+}
+
+int mo_make_normal(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* normal) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr n = Arr::view(normal[i], 3);
+    make_normal_sphr(*p, *g, n, normal[i].lo, normal[i].hi, normal[i].ng);
+  }
+  MO_CATCH
+}
+
+int mo_mk_vel_force_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* vel_force, int is_final_update,
+                         const mgpu_fab* uold, const mgpu_fab* const* uedge, const double* w0, const mgpu_fab* const* w0mac,
+                         const mgpu_fab* gpi, const mgpu_fab* s, int index_rho, const mgpu_fab* normal, const double* rho0,
+                         const double* grav, const mgpu_fab* w0_force_cart, int do_add_utilde_force) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr f = Arr::view(vel_force[i], 3), uo = Arr::view(uold[i], 3), gp = Arr::view(gpi[i], 3), sv = Arr::view(s[i], 3);
+    Arr nm = Arr::view(normal[i], 3), wf = Arr::view(w0_force_cart[i], 3);
+    Arr ue[3], wm[3];
+    views3(uedge, i, ue);
+    views3(w0mac, i, wm);
+    mk_vel_force_sphr_box(*p, *g, f, is_final_update != 0, uo, ue, w0, wm, gp, sv.comp(index_rho - 1), nm, rho0, grav, wf,
+                          vel_force[i].lo, vel_force[i].hi, do_add_utilde_force != 0);
+  }
+  MO_CATCH
+}
+
+int mo_advance_premac_sphr(const mgpu_params* p, const mgpu_geom* g, const mgpu_fab* uold, const mgpu_fab* sold,
+                           mgpu_fab* const* umac, const mgpu_fab* gpi, const mgpu_fab* normal, const double* w0,
+                           const mgpu_fab* const* w0mac, const mgpu_fab* w0_force_cart, const double* rho0_old,
+                           const double* grav_cell_old, const int* adv_bc, const int* phys_bc, const int* pmask) {
+  MO_TRY
+  need3(p);
+  Arr uo = Arr::view(*uold, 3), so = Arr::view(*sold, 3), gp = Arr::view(*gpi, 3), nm = Arr::view(*normal, 3);
+  Arr wf = Arr::view(*w0_force_cart, 3);
+  Arr um[3], wm[3];
+  views3((const mgpu_fab* const*)umac, 0, um);
+  views3(w0mac, 0, wm);
+  advance_premac_sphr_box(*p, *g, uo, so, um, gp, nm, w0, wm, wf, rho0_old, grav_cell_old, uold->lo, uold->hi, uold->ng,
+                          adv_bc, phys_bc, pmask);
+  MO_CATCH
+}
+
+int mo_velocity_advance_sphr(const mgpu_params* p, const mgpu_geom* g, const mgpu_fab* uold, mgpu_fab* unew,
+                             const mgpu_fab* sold, const mgpu_fab* rhohalf, mgpu_fab* const* umac, const mgpu_fab* gpi,
+                             const mgpu_fab* normal, const double* w0, const mgpu_fab* const* w0mac,
+                             const mgpu_fab* w0_force_cart, const double* rho0_old, const double* rho0_nph,
+                             const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
+                             const int* adv_bc, const int* pmask) {
+  MO_TRY
+  need3(p);
+  Arr uo = Arr::view(*uold, 3), un = Arr::view(*unew, 3), so = Arr::view(*sold, 3), rh = Arr::view(*rhohalf, 3);
+  Arr gp = Arr::view(*gpi, 3), nm = Arr::view(*normal, 3), wf = Arr::view(*w0_force_cart, 3), sp = Arr::view(*sponge, 3);
+  Arr um[3], wm[3];
+  views3((const mgpu_fab* const*)umac, 0, um);
+  views3(w0mac, 0, wm);
+  velocity_advance_sphr_box(*p, *g, uo, un, so, rh, um, gp, nm, w0, wm, wf, rho0_old, rho0_nph, grav_cell_old,
+                            grav_cell_nph, sp, uold->lo, uold->hi, uold->ng, adv_bc, pmask);
   MO_CATCH
 }
 

@@ -475,6 +475,55 @@ module maestro_b200_shim
        integer(c_int), intent(in) :: adv_bc(*), pmask(*)
      end function mgpu_fill_boundary_mf_c
 
+     ! fill_3d_data.f90:1280
+     integer(c_int) function mgpu_make_normal_c(p, g, nfabs, normal) bind(C, name="mgpu_make_normal")
+       import :: c_int, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(inout) :: normal(*)
+     end function mgpu_make_normal_c
+
+     ! mkforce.f90:22 with spherical == 1 (mk_vel_force_3d_sphr :484)
+     integer(c_int) function mgpu_mk_vel_force_sphr_c(p, g, nfabs, vel_force, is_final_update, uold, uedge, w0, w0mac, &
+          gpi, s, index_rho, normal, rho0, grav, w0_force_cart, do_add_utilde_force) &
+          bind(C, name="mgpu_mk_vel_force_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs, is_final_update, index_rho, do_add_utilde_force
+       type(mgpu_fab), intent(inout) :: vel_force(*)
+       type(mgpu_fab), intent(in) :: uold(*), gpi(*), s(*), normal(*), w0_force_cart(*)
+       type(c_ptr), intent(in) :: uedge(*), w0mac(*)
+       real(c_double), intent(in) :: w0(*), rho0(*), grav(*)
+     end function mgpu_mk_vel_force_sphr_c
+
+     ! advance_premac.f90:21, spherical
+     integer(c_int) function mgpu_advance_premac_sphr_c(p, g, uold, sold, umac, gpi, normal, w0, w0mac, w0_force_cart, &
+          rho0_old, grav_cell_old, adv_bc, phys_bc, pmask) bind(C, name="mgpu_advance_premac_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       type(mgpu_fab), intent(in) :: uold(*), sold(*), gpi(*), normal(*), w0_force_cart(*)
+       type(c_ptr), intent(in) :: umac(*), w0mac(*)
+       real(c_double), intent(in) :: w0(*), rho0_old(*), grav_cell_old(*)
+       integer(c_int), intent(in) :: adv_bc(*), phys_bc(*), pmask(*)
+     end function mgpu_advance_premac_sphr_c
+
+     ! velocity_advance.f90:16, spherical
+     integer(c_int) function mgpu_velocity_advance_sphr_c(p, g, uold, unew, sold, rhohalf, umac, gpi, normal, w0, w0mac, &
+          w0_force_cart, rho0_old, rho0_nph, grav_cell_old, grav_cell_nph, sponge, adv_bc, pmask) &
+          bind(C, name="mgpu_velocity_advance_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       type(mgpu_fab), intent(in) :: uold(*), sold(*), rhohalf(*), gpi(*), normal(*), w0_force_cart(*), sponge(*)
+       type(mgpu_fab), intent(inout) :: unew(*)
+       type(c_ptr), intent(in) :: umac(*), w0mac(*)
+       real(c_double), intent(in) :: w0(*), rho0_old(*), rho0_nph(*), grav_cell_old(*), grav_cell_nph(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_velocity_advance_sphr_c
+
      ! density_advance.f90:20, spherical
      integer(c_int) function mgpu_density_advance_sphr_c(p, g, which_step, sold, snew, sedge, sflux, &
           scal_force, umac, w0, w0mac, rho0_old, rho0_new, adv_bc, pmask) &
@@ -612,6 +661,7 @@ module maestro_b200_shim
   public :: mgpu_mkutrans_sphr_c, mgpu_velpred_sphr_c, mgpu_modify_scal_force_sphr_c, mgpu_put_in_pert_form_sphr_c
   public :: mgpu_fill_boundary_c, mgpu_convert_rhoX_to_X_c, mgpu_modify_scal_force_c, mgpu_put_in_pert_form_c, mgpu_mkrhohforce_c, mgpu_mk_vel_force_c
   public :: mgpu_density_advance_mf_c, mgpu_fill_boundary_mf_c
+  public :: mgpu_make_normal_c, mgpu_mk_vel_force_sphr_c, mgpu_advance_premac_sphr_c, mgpu_velocity_advance_sphr_c
   public :: mgpu_density_advance_c, mgpu_density_advance_sphr_c, mgpu_enthalpy_advance_c, mgpu_velocity_advance_c, mgpu_advance_premac_c
   public :: mgpu_comm_unique_id, mgpu_comm_init, mgpu_comm_finalize, mgpu_set_option
   public :: mgpu_malloc, mgpu_free, mgpu_memcpy_h2d, mgpu_memcpy_d2h
