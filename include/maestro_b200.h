@@ -335,6 +335,21 @@ int mgpu_velocity_advance_sphr(const mgpu_params* p, const mgpu_geom* g, const m
                                const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
                                const int* adv_bc, const int* pmask);
 
+/* mkrhohforce with spherical == 1 (mkscalforce.f90:31 -> mkrhohforce_3d_sphr :388): p0 = (p0_1 + p0_2)/2 is put on the
+ * cell centres and on the faces inside (put_1d_array_on_cart, make_s0mac), psi on the cell centres; writes the rhoh
+ * component of scal_force, ghost cells included (:177-181). */
+int mgpu_mkrhohforce_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* scal_force, int is_prediction,
+                          const mgpu_fab* thermal, const mgpu_fab* const* umac, const double* p0_1, const double* p0_2,
+                          const double* psi, int add_thermal, const int* adv_bc, const int* pmask);
+/* enthalpy_advance (enthalpy_advance.f90:16) with spherical == 1 as a device-resident episode: rhoh0_old_cart, the
+ * rho0mac / h0mac arrays and p0 on cells and faces are built on the device; radial arrays are (0:nr_fine-1). */
+int mgpu_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int which_step, mgpu_fab* sold, mgpu_fab* snew,
+                               mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
+                               const mgpu_fab* thermal, mgpu_fab* const* umac, const double* w0,
+                               const mgpu_fab* const* w0mac, const double* rho0_old, const double* rhoh0_old,
+                               const double* rho0_new, const double* rhoh0_new, const double* p0_old, const double* p0_new,
+                               const double* psi, const int* adv_bc, const int* pmask);
+
 /* ---- L4 episode: density_advance (Source/density_advance.f90:20), planar, one level ------
  * Signature mirrors the Fortran argument list; sold is modified in place exactly as the reference
  * does (rhoX->X->rhoX, rho->rho'->rho round trips), umac is (umac+w0)-w0 on return, sedge, sflux,

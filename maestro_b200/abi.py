@@ -140,6 +140,10 @@ OPERATORS = {
     "velpred_sphr": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, FF_, c_int_p, c_int_p]),
     "modify_scal_force_sphr": (C.c_int, [P_, G_, C.c_int, F_, F_, FF_, F_, c_double_p, C.c_int, C.c_int]),
     "put_in_pert_form_sphr": (C.c_int, [P_, G_, C.c_int, F_, c_double_p, C.c_int, C.c_int]),
+    "mkrhohforce_sphr": (C.c_int, [P_, G_, C.c_int, F_, C.c_int, F_, FF_, c_double_p, c_double_p, c_double_p, C.c_int,
+                                   c_int_p, c_int_p]),
+    "enthalpy_advance_sphr": (C.c_int, [P_, G_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_, c_double_p, FF_] + [c_double_p] * 7
+                              + [c_int_p] * 2),
     "make_normal": (C.c_int, [P_, G_, C.c_int, F_]),
     "mk_vel_force_sphr": (C.c_int, [P_, G_, C.c_int, F_, C.c_int, F_, FF_, c_double_p, FF_, F_, F_, C.c_int, F_, c_double_p,
                                     c_double_p, F_, C.c_int]),

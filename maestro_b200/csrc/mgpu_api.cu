@@ -1038,6 +1038,148 @@ static void velocity_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
   fill_boundary_dev(P, unew, lo, hi, ng_u, nullptr, 1, 1, dm, adv_bc, pmask, false);  // update_vel.f90:121
 }
 
+// ---- enthalpy_advance with spherical == 1 --------------------------------------------------------------------------
+struct SphrCtx {  // what the spherical helpers of one episode share
+  const mgpu_params& P;
+  const mgpu_geom& g;
+  Geom gd;
+  const int *lo, *hi, *adv_bc, *pmask;
+};
+// put_1d_array_on_cart of a bin-centred array incl. its ghost fill with the BCs of component bccomp (fill_3d_data.f90:21)
+static DV sphr_cart(const SphrCtx& X, const double* s0_dev, int ng, int bccomp) {
+  const int z3[3] = {0, 0, 0};
+  DV c = make_view(nullptr, X.lo, X.hi, 3, ng, z3, 1);
+  c.p = arena_alloc((size_t)c.size());
+  put_1d_array_on_cart_dev(X.P, X.g, X.gd, s0_dev, c, false, false, X.lo, X.hi);
+  fill_boundary_dev(X.P, c, X.lo, X.hi, ng, nullptr, 1, bccomp, 1, X.adv_bc, X.pmask, false);
+  return c;
+}
+// make_s0mac (fill_3d_data.f90:942): through the cell centres (two ghost cells) when s0mac_interp_type = 1
+static void sphr_s0mac(const SphrCtx& X, const double* s0_dev, DV* mac, int bccomp) {
+  for (int d = 0; d < 3; ++d) {
+    mac[d] = make_view(nullptr, X.lo, X.hi, 3, 1, NODAL_D[d], 1);
+    mac[d].p = arena_alloc((size_t)mac[d].size());
+  }
+  if (X.g.s0mac_interp_type == 1) {
+    DV c = sphr_cart(X, s0_dev, 2, bccomp);
+    make_mac_dev(X.g, X.gd, s0_dev, mac, &c, 1, X.lo, X.hi);
+  } else {
+    make_mac_dev(X.g, X.gd, s0_dev, mac, nullptr, 1, X.lo, X.hi);
+  }
+}
+// the spherical branch of mkrhohforce (mkscalforce.f90:31): p0 = (p0_1 + p0_2)/2 on cells and faces, then the kernel,
+// then the ghost fill of the rhoh component (:177-181)
+static void rhoh_force_sphr_full(const SphrCtx& X, DV& scal_force, bool is_prediction, const DV& thermal, const DV* umac,
+                                 const double* p0_1, const double* p0_2, const double* psi_h, bool add_thermal, int ng_f) {
+  const mgpu_params& P = X.P;
+  const int nr = X.g.nr_fine, foextrap_comp = 3 + P.nscal + 2;
+  std::vector<double> p0(nr);
+  for (int r = 0; r < nr; ++r) p0[r] = 0.5 * (p0_1[r] + p0_2[r]);
+  size_t mark = arena_mark();
+  const double* p0d = upload_small(p0.data(), (size_t)nr);
+  DV p0c = sphr_cart(X, p0d, 1, foextrap_comp);
+  DV p0m[3];
+  sphr_s0mac(X, p0d, p0m, foextrap_comp);
+  mkrhohforce_sphr_dev(P, X.g, X.gd, scal_force.comp(P.rhoh_comp - 1), is_prediction, thermal, umac, p0c, p0m, psi_h,
+                       add_thermal, X.lo, X.hi);
+  arena_release(mark);
+  fill_boundary_dev(P, scal_force, X.lo, X.hi, ng_f, nullptr, P.rhoh_comp, foextrap_comp, 1, X.adv_bc, X.pmask, false);
+}
+
+static void enthalpy_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, int which_step, DV& sold, DV& snew,
+                                      DV* sedge, DV* sflux, DV& scal_force, const DV& thermal, DV* umac, const double* w0_h,
+                                      const DV* w0mac, const double* rho0_old_h, const double* rhoh0_old_h,
+                                      const double* rho0_new_h, const double* rhoh0_new_h, const double* p0_old_h,
+                                      const double* p0_new_h, const double* psi_h, const int* lo, const int* hi, int ng_s,
+                                      int ng_f, const int* adv_bc, const int* pmask) {
+  const int dm = 3, nr = g.nr_fine;
+  const int ept = P.enthalpy_pred_type;
+  const int foextrap_comp = dm + P.nscal + 2;
+  const int rhoh = P.rhoh_comp - 1, rho = P.rho_comp - 1;
+  if (ept == MGPU_PREDICT_HPRIME) throw Error("mk_rhoh_flux : predict_hprime not coded yet");  // mkflux.f90:1167
+  if (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H)
+    throw Error("enthalpy_advance: temperature-based prediction needs the EOS (makeHfromRhoT_edge): not on the device");
+  SphrCtx X{P, g, make_geom(P, g), lo, hi, adv_bc, pmask};
+  const double* rho0_old = upload_small(rho0_old_h, (size_t)nr);
+  const double* rho0_new = upload_small(rho0_new_h, (size_t)nr);
+  const double* rhoh0_old = upload_small(rhoh0_old_h, (size_t)nr);
+  std::vector<double> h0o(nr), h0n(nr);
+  for (int r = 0; r < nr; ++r) {
+    h0o[r] = rhoh0_old_h[r] / rho0_old_h[r];
+    h0n[r] = rhoh0_new_h[r] / rho0_new_h[r];
+  }
+  const double* h0_old = upload_small(h0o.data(), (size_t)nr);
+  const double* h0_new = upload_small(h0n.data(), (size_t)nr);
+  auto fill_umac = [&]() { fill_faces_dev(P, umac, lo, hi, adv_bc, pmask); };
+  auto rhoh_to_h = [&](bool flag) {  // convert_rhoh_to_h, convert_rhoX_to_X.f90:80
+    comp_muldiv_dev(P, sold, rhoh, sold, rho, flag ? 0 : 1, 0, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc,
+                      pmask, false);
+  };
+  auto pert = [&](bool flag) {
+    pert_form_sphr_dev(g, X.gd, sold, rhoh0_old, P.rhoh_comp, flag, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc,
+                      pmask, false);
+  };
+  if (ept == MGPU_PREDICT_H) rhoh_to_h(true);     // :122-126
+  set_dev(scal_force.p, 0.0, scal_force.size());  // :132-134
+  rhoh_force_sphr_full(X, scal_force, true, thermal, umac, p0_old_h, p0_old_h, psi_h, true, ng_f);
+  if (ept == MGPU_PREDICT_RHOHPRIME) {  // :141-156
+    size_t mark = arena_mark();
+    DV rhoh0_old_cart = sphr_cart(X, rhoh0_old, 1, dm + P.rhoh_comp);
+    modify_scal_force_sphr_dev(P, g, X.gd, scal_force, sold, umac, rhoh0_old_cart, w0_h, P.rhoh_comp, false, lo, hi);
+    arena_release(mark);
+    fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask, false);
+  } else if (ept == MGPU_PREDICT_H) {  // :173-178
+    comp_muldiv_dev(P, scal_force, rhoh, sold, rho, 0, 1, lo, hi);
+  }
+  addw0_sphr_dev(umac, w0mac, 1.0, lo, hi);  // :201
+  fill_umac();
+  if (ept == MGPU_PREDICT_RHOHPRIME) pert(true);  // :204-208
+  {
+    const bool cons = (ept == MGPU_PREDICT_RHOH);  // :232-254
+    size_t mark = arena_mark();
+    if (P.bds_type != 0) bds_dev(P, sold, sedge, umac, scal_force, lo, hi, rhoh, cons, ng_s, ng_f);
+    else edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, rhoh, dm + P.rhoh_comp, false, cons, ng_s, ng_f);
+    arena_release(mark);
+  }
+  if (ept == MGPU_PREDICT_RHOHPRIME) pert(false);  // :257-261
+  if (ept == MGPU_PREDICT_H) rhoh_to_h(false);     // :272-276
+  addw0_sphr_dev(umac, w0mac, -1.0, lo, hi);       // :293
+  fill_umac();
+  const bool s1 = (which_step == 1);
+  {
+    size_t mark = arena_mark();
+    SphrFluxArgs fa;
+    fa.spt = P.species_pred_type;
+    fa.rho = rho;
+    fa.rhoh = rhoh;
+    fa.vb = grown(lo, hi, dm, 0);
+    sphr_s0mac(X, rho0_old, fa.r0o, dm + P.rho_comp);  // :301-399
+    sphr_s0mac(X, h0_old, fa.h0o, foextrap_comp);
+    if (s1) {
+      for (int d = 0; d < 3; ++d) { fa.r0n[d] = fa.r0o[d]; fa.h0n[d] = fa.h0o[d]; }
+    } else {
+      sphr_s0mac(X, rho0_new, fa.r0n, dm + P.rho_comp);
+      sphr_s0mac(X, h0_new, fa.h0n, foextrap_comp);
+    }
+    for (int d = 0; d < 3; ++d) { fa.sflux[d] = sflux[d]; fa.sedge[d] = sedge[d]; fa.umac[d] = umac[d]; fa.w0mac[d] = w0mac[d]; }
+    mk_rhoh_flux_sphr_dev(P, fa);
+    arena_release(mark);
+  }
+  set_dev(scal_force.p, 0.0, scal_force.size());  // :401-403
+  rhoh_force_sphr_full(X, scal_force, false, thermal, umac, p0_old_h, s1 ? p0_old_h : p0_new_h, psi_h, false, ng_f);  // :405-416
+  UpdArgs ua;
+  ua.dm = dm;
+  ua.dt = P.dt;
+  for (int d = 0; d < 3; ++d) ua.dx[d] = P.dx[d];
+  ua.vb = grown(lo, hi, dm, 0);
+  ua.sold = sold; ua.snew = snew; ua.force = scal_force;
+  for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
+  update_scal_dev(P, ua, P.rhoh_comp, P.rhoh_comp);  // :431
+  fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rhoh_comp, dm + P.rhoh_comp, 1, adv_bc, pmask, false);
+}
+
 // enthalpy_advance (Source/enthalpy_advance.f90:16)
 static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold, DV& snew, DV* sedge, DV* sflux,
                                  DV& scal_force, const DV& thermal, DV* umac, const double* w0_h,
@@ -2218,6 +2360,55 @@ int mgpu_velocity_advance_sphr(const mgpu_params* p, const mgpu_geom* g, const m
   c.views(w0mac, 0, true, false, wm);
   velocity_advance_sphr_dev(*p, *g, uo, un, so, rh, um, gp, nm, w0, wm, wf, rho0_old, rho0_nph, grav_cell_old,
                             grav_cell_nph, sp, uold->lo, uold->hi, uold->ng, adv_bc, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_mkrhohforce_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* scal_force, int is_prediction,
+                          const mgpu_fab* thermal, const mgpu_fab* const* umac, const double* p0_1, const double* p0_2,
+                          const double* psi, int add_thermal, const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  need_sphr(p, g);
+  if (!p->spherical) throw Error("mkrhohforce_sphr: params.spherical must be 1");
+  size_t need = 0;
+  for (int i = 0; i < nfabs; ++i)
+    need = std::max(need, 6 * fab_bytes(scal_force[i].lo, scal_force[i].hi, 3, 2, 1, 1));
+  Call c(p, need + geom_scratch(g) + (size_t)(4 * (g->nr_fine + 4)) * sizeof(double));
+  const cmask_t mrhoh = crange(p->rhoh_comp - 1, 1);
+  for (int i = 0; i < nfabs; ++i) {
+    DV fv = c.view(scal_force[i], mrhoh, mrhoh), th = c.view(thermal[i], true, false);
+    DV um[3];
+    c.views(umac, i, true, false, um);
+    SphrCtx X{*p, *g, make_geom(*p, *g), scal_force[i].lo, scal_force[i].hi, adv_bc, pmask};
+    rhoh_force_sphr_full(X, fv, is_prediction != 0, th, um, p0_1, p0_2, psi, add_thermal != 0, scal_force[i].ng);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int which_step, mgpu_fab* sold, mgpu_fab* snew,
+                               mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
+                               const mgpu_fab* thermal, mgpu_fab* const* umac, const double* w0,
+                               const mgpu_fab* const* w0mac, const double* rho0_old, const double* rhoh0_old,
+                               const double* rho0_new, const double* rhoh0_new, const double* p0_old, const double* p0_new,
+                               const double* psi, const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  need_sphr(p, g);
+  if (!p->spherical) throw Error("enthalpy_advance_sphr: params.spherical must be 1");
+  Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
+                14 * fab_bytes(sold->lo, sold->hi, 3, 2, 1, 1) + geom_scratch(g) +
+                (size_t)(16 * (g->nr_fine + 4)) * sizeof(double) + 16384);
+  const cmask_t mrho = crange(p->rho_comp - 1, 1), mrhoh = crange(p->rhoh_comp - 1, 1);
+  DV so = c.view(*sold, mrho | mrhoh, mrhoh), sn = c.view(*snew, mrhoh, mrhoh);
+  DV fv = c.view(*scal_force, (cmask_t)0, mrhoh);
+  DV th = c.view(*thermal, true, false);
+  DV se[3], sf[3], um[3], wm[3];
+  c.views((const mgpu_fab* const*)sedge, 0, mrho, mrhoh, se);
+  c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, mrhoh, sf);
+  c.views((const mgpu_fab* const*)umac, 0, true, true, um);
+  c.views(w0mac, 0, true, false, wm);
+  enthalpy_advance_sphr_dev(*p, *g, which_step, so, sn, se, sf, fv, th, um, w0, wm, rho0_old, rhoh0_old, rho0_new, rhoh0_new,
+                            p0_old, p0_new, psi, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
   c.finish();
   MGPU_CATCH
 }

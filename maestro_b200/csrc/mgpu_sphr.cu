@@ -308,6 +308,29 @@ __global__ void k_vel_force_sphr(VelForceSphr a) {
   for (int c = 0; c < 3; ++c) a.force(i, j, k, c) = f[c];
 }
 
+// mkrhohforce_3d_sphr (mkscalforce.f90:388): u.grad p0 = div(u p0) - p0 div(u) with p0 on the faces and on the cell
+// centres, + psi (cell centres) where the reference adds it, + thermal
+struct RhohForceSphr {
+  DV force, um, vm, wm, thermal, p0c, p0m[3], psic;
+  Box3 vb;
+  double dx[3];
+  bool add_psi, add_thermal;
+};
+__global__ void k_rhoh_force_sphr(RhohForceSphr a) {
+  int ix[3];
+  if (!decode3(a.vb, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  const double divup = (a.um(i + 1, j, k) * a.p0m[0](i + 1, j, k) - a.um(i, j, k) * a.p0m[0](i, j, k)) / a.dx[0] +
+                       (a.vm(i, j + 1, k) * a.p0m[1](i, j + 1, k) - a.vm(i, j, k) * a.p0m[1](i, j, k)) / a.dx[1] +
+                       (a.wm(i, j, k + 1) * a.p0m[2](i, j, k + 1) - a.wm(i, j, k) * a.p0m[2](i, j, k)) / a.dx[2];
+  const double p0divu = ((a.um(i + 1, j, k) - a.um(i, j, k)) / a.dx[0] + (a.vm(i, j + 1, k) - a.vm(i, j, k)) / a.dx[1] +
+                         (a.wm(i, j, k + 1) - a.wm(i, j, k)) / a.dx[2]) * a.p0c(i, j, k);
+  double f = divup - p0divu;
+  if (a.add_psi) f = f + a.psic(i, j, k);
+  if (a.add_thermal) f = f + a.thermal(i, j, k);
+  a.force(i, j, k) = f;
+}
+
 Box3 mac_box(const int* lo, const int* hi, int d) {
   Box3 b;
   for (int q = 0; q < 3; ++q) {
@@ -464,6 +487,30 @@ void mk_vel_force_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const Geom&
   a.omega = P.omega;
   a.rho_cut = P.buoyancy_cutoff_factor * P.base_cutoff_density;
   MGPU_TIMED(TAG_GLUE, (k_vel_force_sphr<<<grid3(a.vb, 256), block3(a.vb, 256), 0, ctx().stream>>>(a)));
+}
+
+// force: single-component view of scal_force(rhoh_comp); p0c (one ghost cell, filled) and p0mac from the caller
+void mkrhohforce_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const Geom& gd, const DV& force, bool is_prediction,
+                          const DV& thermal, const DV* umac, const DV& p0c, const DV* p0mac, const double* psi_h,
+                          bool add_thermal, const int* lo, const int* hi) {
+  const int ept = P.enthalpy_pred_type;
+  if (is_prediction && !(ept == MGPU_PREDICT_RHOHPRIME || ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_RHOH))
+    throw Error("ERROR: should only call mkrhohforce when predicting rhoh', h, or rhoh");  // mkscalforce.f90:87-92
+  RhohForceSphr a;
+  a.force = force; a.um = umac[0]; a.vm = umac[1]; a.wm = umac[2]; a.thermal = thermal; a.p0c = p0c;
+  for (int d = 0; d < 3; ++d) { a.p0m[d] = p0mac[d]; a.dx[d] = P.dx[d]; }
+  a.vb = grown(lo, hi, 3, 0);
+  a.add_psi = (is_prediction && ept == MGPU_PREDICT_H) || (is_prediction && ept == MGPU_PREDICT_RHOH) || !is_prediction;
+  a.add_thermal = add_thermal;
+  a.psic = p0c;
+  if (a.add_psi) {
+    const int z3[3] = {0, 0, 0};
+    DV psic = make_view(nullptr, lo, hi, 3, 0, z3, 1);
+    psic.p = arena_alloc((size_t)psic.size());
+    put_1d_array_on_cart_dev(P, g, gd, upload_small(psi_h, (size_t)g.nr_fine), psic, false, false, lo, hi);
+    a.psic = psic;
+  }
+  MGPU_TIMED(TAG_GLUE, (k_rhoh_force_sphr<<<grid3(a.vb, 256), block3(a.vb, 256), 0, ctx().stream>>>(a)));
 }
 
 }  // namespace mgpu

@@ -36,6 +36,9 @@ void modify_scal_force_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const 
 void pert_form_sphr_dev(const mgpu_geom& g, const Geom& gd, const DV& s, const double* s0_dev, int comp, bool flag,
                         const int* lo, const int* hi);
 
+void mkrhohforce_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const Geom& gd, const DV& force, bool is_prediction,
+                          const DV& thermal, const DV* umac, const DV& p0c, const DV* p0mac, const double* psi_h,
+                          bool add_thermal, const int* lo, const int* hi);
 void make_normal_dev(const Geom& gd, const DV& normal, const int* lo, const int* hi, int ng);
 void mk_vel_force_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const Geom& gd, const DV& force, bool is_final,
                            const DV& uold, const DV* uedge, const double* w0_h, const DV* w0mac, const DV& gpi,

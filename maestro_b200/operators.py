@@ -193,6 +193,27 @@ class Operators:
                    ptrs[0][0], ptrs[1][0], fab_ptr(scal_force), ptrs[2][0], keep[0][1], ptrs[3][0], keep[1][1],
                    keep[2][1], bcp, pmp)
 
+    def mkrhohforce_sphr(self, p, geom, scal_force, is_prediction, thermal, umac, p0_1, p0_2, psi, add_thermal, adv_bc,
+                         pmask):
+        keep = [as_double_p(x) for x in (p0_1, p0_2, psi)]
+        bc, bcp = as_int_p(adv_bc)
+        pm, pmp = as_int_p(pmask)
+        um, k1 = fab_pp(umac)
+        self._call("mkrhohforce_sphr", C.byref(p), C.byref(geom.c), 1, fab_ptr(scal_force), int(is_prediction),
+                   fab_ptr(thermal), um, keep[0][1], keep[1][1], keep[2][1], int(add_thermal), bcp, pmp)
+
+    def enthalpy_advance_sphr(self, p, geom, which_step, sold, snew, sedge, sflux, scal_force, thermal, umac, w0, w0mac,
+                              rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, adv_bc, pmask):
+        keep = [as_double_p(x) for x in (w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi)]
+        bc, bcp = as_int_p(adv_bc)
+        pm, pmp = as_int_p(pmask)
+        se, k1 = fab_pp(sedge)
+        sf, k2 = fab_pp(sflux)
+        um, k3 = fab_pp(umac)
+        wm, k4 = fab_pp(w0mac)
+        self._call("enthalpy_advance_sphr", C.byref(p), C.byref(geom.c), which_step, fab_ptr(sold), fab_ptr(snew), se, sf,
+                   fab_ptr(scal_force), fab_ptr(thermal), um, keep[0][1], wm, *[k[1] for k in keep[1:]], bcp, pmp)
+
     def make_normal(self, p, geom, normal):
         self._call("make_normal", C.byref(p), C.byref(geom.c), 1, fab_ptr(normal))
 

@@ -583,6 +583,143 @@ void velocity_advance_sphr_box(const mgpu_params& P, const mgpu_geom& g, const A
   fill_boundary_box(P, unew, lo, hi, ng_u, 1, 1, dm, adv_bc, pmask);  // update_vel.f90:121
 }
 
+// ---- enthalpy path, spherical ------------------------------------------------------------------------------------
+// put_1d_array_on_cart of a bin-centred array incl. its ghost fill with the BCs of component bccomp (fill_3d_data.f90:21)
+static Arr cart_with_ghosts(const mgpu_params& P, const mgpu_geom& g, const double* s0, int ng, int bccomp, const int* lo,
+                            const int* hi, const int* adv_bc, const int* pmask) {
+  Arr c(lo[0] - ng, hi[0] + ng, lo[1] - ng, hi[1] + ng, lo[2] - ng, hi[2] + ng, 1);
+  put_1d_array_on_cart_sphr(P, g, false, false, s0, c, lo, hi);
+  fill_boundary_box(P, c, lo, hi, ng, 1, bccomp, 1, adv_bc, pmask);
+  return c;
+}
+// make_s0mac (fill_3d_data.f90:942): through the cell centres (two ghost cells) when s0mac_interp_type = 1
+static void s0mac_of(const mgpu_params& P, const mgpu_geom& g, const double* s0, Arr* mac, int bccomp, const int* lo,
+                     const int* hi, const int* adv_bc, const int* pmask) {
+  for (int d = 0; d < 3; ++d) {
+    Box b;
+    for (int q = 0; q < 3; ++q) { b.lo[q] = lo[q] - 1; b.hi[q] = hi[q] + 1 + (q == d ? 1 : 0); }
+    mac[d].alloc(b.lo[0], b.hi[0], b.lo[1], b.hi[1], b.lo[2], b.hi[2], 1);
+  }
+  if (g.s0mac_interp_type == 1) {
+    Arr c = cart_with_ghosts(P, g, s0, 2, bccomp, lo, hi, adv_bc, pmask);
+    make_s0mac_sphr(P, g, s0, mac, &c, lo, hi);
+  } else {
+    make_s0mac_sphr(P, g, s0, mac, nullptr, lo, hi);
+  }
+}
+
+// mkrhohforce with spherical == 1 (mkscalforce.f90:31 -> mkrhohforce_3d_sphr :388): p0 = (p0_1 + p0_2)/2 on the cell
+// centres and on the faces (make_s0mac), u.grad p0 = div(u p0) - p0 div u, psi where the reference adds it, thermal.
+// Writes the rhoh component of scal_force on the valid cells.
+void mkrhohforce_sphr_box(const mgpu_params& P, const mgpu_geom& g, Arr& scal_force, bool is_prediction, const Arr& thermal,
+                          const Arr* umac, const double* p0_1, const double* p0_2, const double* psi, bool add_thermal,
+                          const int* lo, const int* hi, const int* adv_bc, const int* pmask) {
+  const int ept = P.enthalpy_pred_type, nr = g.nr_fine;
+  const int foextrap_comp = 3 + P.nscal + 2;
+  if (is_prediction && !(ept == MGPU_PREDICT_RHOHPRIME || ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_RHOH))
+    fail("ERROR: should only call mkrhohforce when predicting rhoh', h, or rhoh");  // mkscalforce.f90:87-92
+  std::vector<double> p0(nr);
+  for (int r = 0; r < nr; ++r) p0[r] = 0.5 * (p0_1[r] + p0_2[r]);
+  Arr p0_cart = cart_with_ghosts(P, g, p0.data(), 1, foextrap_comp, lo, hi, adv_bc, pmask);
+  Arr p0mac[3];
+  s0mac_of(P, g, p0.data(), p0mac, foextrap_comp, lo, hi, adv_bc, pmask);
+  const int rhoh = P.rhoh_comp - 1;
+  const double* dx = P.dx;
+  Box vb = grown(lo, hi, 3, 0);
+  const Arr &um = umac[0], &vm = umac[1], &wm = umac[2];
+  for_box(vb, [&](int i, int j, int k) {
+    const double divup = (um(i + 1, j, k) * p0mac[0](i + 1, j, k) - um(i, j, k) * p0mac[0](i, j, k)) / dx[0] +
+                         (vm(i, j + 1, k) * p0mac[1](i, j + 1, k) - vm(i, j, k) * p0mac[1](i, j, k)) / dx[1] +
+                         (wm(i, j, k + 1) * p0mac[2](i, j, k + 1) - wm(i, j, k) * p0mac[2](i, j, k)) / dx[2];
+    const double p0divu = ((um(i + 1, j, k) - um(i, j, k)) / dx[0] + (vm(i, j + 1, k) - vm(i, j, k)) / dx[1] +
+                           (wm(i, j, k + 1) - wm(i, j, k)) / dx[2]) * p0_cart(i, j, k);
+    scal_force(i, j, k, rhoh) = divup - p0divu;
+  });
+  if ((is_prediction && ept == MGPU_PREDICT_H) || (is_prediction && ept == MGPU_PREDICT_RHOH) || !is_prediction) {
+    Arr psi_cart(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 1);
+    put_1d_array_on_cart_sphr(P, g, false, false, psi, psi_cart, lo, hi);
+    for_box(vb, [&](int i, int j, int k) { scal_force(i, j, k, rhoh) = scal_force(i, j, k, rhoh) + psi_cart(i, j, k); });
+  }
+  if (add_thermal)
+    for_box(vb, [&](int i, int j, int k) { scal_force(i, j, k, rhoh) = scal_force(i, j, k, rhoh) + thermal(i, j, k); });
+}
+
+// enthalpy_advance (enthalpy_advance.f90:16) with spherical == 1
+void enthalpy_advance_sphr_box(const mgpu_params& P, const mgpu_geom& g, int which_step, Arr& sold, Arr& snew, Arr* sedge,
+                               Arr* sflux, Arr& scal_force, const Arr& thermal, Arr* umac, const double* w0,
+                               const Arr* w0mac, const double* rho0_old, const double* rhoh0_old, const double* rho0_new,
+                               const double* rhoh0_new, const double* p0_old, const double* p0_new, const double* psi,
+                               const int* lo, const int* hi, int ng_s, int ng_f, const int* adv_bc, const int* pmask) {
+  const int dm = 3, nr = g.nr_fine;
+  const int ept = P.enthalpy_pred_type;
+  const int foextrap_comp = dm + P.nscal + 2;
+  const int rhoh = P.rhoh_comp - 1, rho = P.rho_comp - 1;
+  if (ept == MGPU_PREDICT_HPRIME) fail("mk_rhoh_flux : predict_hprime not coded yet");
+  if (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H)
+    fail("oracle: temperature-based enthalpy prediction needs the EOS (makeHfromRhoT_edge): not restated");
+  Box vb = grown(lo, hi, dm, 0);
+  auto fill_umac = [&]() {
+    for (int d = 0; d < dm; ++d) fill_boundary_face(P, umac[d], lo, hi, 1, d, pmask);
+  };
+  auto rhoh_to_h = [&](bool flag) {  // convert_rhoh_to_h, convert_rhoX_to_X.f90:80
+    for_box(vb, [&](int i, int j, int k) {
+      if (flag) sold(i, j, k, rhoh) = sold(i, j, k, rhoh) / sold(i, j, k, rho);
+      else sold(i, j, k, rhoh) = sold(i, j, k, rhoh) * sold(i, j, k, rho);
+    });
+    fill_boundary_box(P, sold, lo, hi, ng_s, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc, pmask);
+  };
+  if (ept == MGPU_PREDICT_H) rhoh_to_h(true);  // :122-126
+  scal_force.fill(0.0);                         // :132-134
+  mkrhohforce_sphr_box(P, g, scal_force, true, thermal, umac, p0_old, p0_old, psi, true, lo, hi, adv_bc, pmask);
+  fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
+  if (ept == MGPU_PREDICT_RHOHPRIME) {  // :141-156
+    Arr rhoh0_old_cart = cart_with_ghosts(P, g, rhoh0_old, 1, dm + P.rhoh_comp, lo, hi, adv_bc, pmask);
+    Arr fo = scal_force.comp(rhoh), sa = sold.comp(rhoh);
+    modify_scal_force_sphr(P, g, fo, sa, umac, rhoh0_old_cart, w0, false, lo, hi);
+    fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
+  } else if (ept == MGPU_PREDICT_H) {  // :173-178
+    Box g1 = grown(lo, hi, dm, 1);
+    for_box(g1, [&](int i, int j, int k) { scal_force(i, j, k, rhoh) = scal_force(i, j, k, rhoh) / sold(i, j, k, rho); });
+  }
+  addw0_sphr(umac, w0mac, lo, hi, 1.0);  // :201
+  fill_umac();
+  auto pert = [&](bool flag) {  // put_in_pert_form on the rhoh component with rhoh0_old
+    Arr sa = sold.comp(rhoh);
+    pert_form_sphr(P, g, sa, rhoh0_old, flag, lo, hi);
+    fill_boundary_box(P, sold, lo, hi, ng_s, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc, pmask);
+  };
+  if (ept == MGPU_PREDICT_RHOHPRIME) pert(true);  // :204-208
+  const bool cons = (ept == MGPU_PREDICT_RHOH);     // :232-254
+  if (P.bds_type == 0) make_edge_scal_box(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, rhoh, dm + P.rhoh_comp, false, cons, ng_s);
+  else bds_box(P, sold, sedge, umac, scal_force, lo, hi, rhoh, cons);
+  if (ept == MGPU_PREDICT_RHOHPRIME) pert(false);  // :257-261
+  if (ept == MGPU_PREDICT_H) rhoh_to_h(false);     // :272-276
+  addw0_sphr(umac, w0mac, lo, hi, -1.0);           // :293
+  fill_umac();
+  // :301-399: rho0mac and h0mac of the old (and, for which_step 2, the new) base state; rhoh0mac is built by the
+  // reference too but mk_rhoh_flux_3d_sphr (mkflux.f90:1289) does not read it
+  std::vector<double> h0_old(nr), h0_new(nr);
+  for (int r = 0; r < nr; ++r) {
+    h0_old[r] = rhoh0_old[r] / rho0_old[r];
+    h0_new[r] = rhoh0_new[r] / rho0_new[r];
+  }
+  Arr r0o[3], r0n[3], h0o[3], h0n[3];
+  s0mac_of(P, g, rho0_old, r0o, dm + P.rho_comp, lo, hi, adv_bc, pmask);
+  s0mac_of(P, g, h0_old.data(), h0o, foextrap_comp, lo, hi, adv_bc, pmask);
+  const bool s1 = (which_step == 1);
+  if (!s1) {
+    s0mac_of(P, g, rho0_new, r0n, dm + P.rho_comp, lo, hi, adv_bc, pmask);
+    s0mac_of(P, g, h0_new.data(), h0n, foextrap_comp, lo, hi, adv_bc, pmask);
+  }
+  mk_rhoh_flux_sphr(P, sflux, sedge, umac, w0mac, r0o, s1 ? r0o : r0n, h0o, s1 ? h0o : h0n, lo, hi);
+  scal_force.fill(0.0);  // :401-403
+  mkrhohforce_sphr_box(P, g, scal_force, false, thermal, umac, p0_old, s1 ? p0_old : p0_new, psi, false, lo, hi, adv_bc,
+                       pmask);  // :405-416
+  fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
+  update_scal_box(P, P.rhoh_comp, P.rhoh_comp, sold, snew, sflux, scal_force, lo, hi);  // :431 (no EOS below the cutoff here)
+  fill_boundary_box(P, snew, lo, hi, ng_s, P.rhoh_comp, dm + P.rhoh_comp, 1, adv_bc, pmask);
+}
+
 static void need3(const mgpu_params* p) {
   if (p->dm != 3) fail("spherical geometry is 3-D only");
 }
@@ -834,6 +971,43 @@ int mo_velocity_advance_sphr(const mgpu_params* p, const mgpu_geom* g, const mgp
   views3(w0mac, 0, wm);
   velocity_advance_sphr_box(*p, *g, uo, un, so, rh, um, gp, nm, w0, wm, wf, rho0_old, rho0_nph, grav_cell_old,
                             grav_cell_nph, sp, uold->lo, uold->hi, uold->ng, adv_bc, pmask);
+  MO_CATCH
+}
+
+int mo_mkrhohforce_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* scal_force, int is_prediction,
+                        const mgpu_fab* thermal, const mgpu_fab* const* umac, const double* p0_1, const double* p0_2,
+                        const double* psi, int add_thermal, const int* adv_bc, const int* pmask) {
+  MO_TRY
+  need3(p);
+  for (int i = 0; i < nfabs; ++i) {
+    Arr f = Arr::view(scal_force[i], 3), th = Arr::view(thermal[i], 3);
+    Arr um[3];
+    views3(umac, i, um);
+    mkrhohforce_sphr_box(*p, *g, f, is_prediction != 0, th, um, p0_1, p0_2, psi, add_thermal != 0, scal_force[i].lo,
+                         scal_force[i].hi, adv_bc, pmask);
+    // ml_restrict_and_fill of the rhoh component (mkscalforce.f90:177-181)
+    fill_boundary_box(*p, f, scal_force[i].lo, scal_force[i].hi, scal_force[i].ng, p->rhoh_comp, 3 + p->nscal + 2, 1, adv_bc,
+                      pmask);
+  }
+  MO_CATCH
+}
+
+int mo_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int which_step, mgpu_fab* sold, mgpu_fab* snew,
+                             mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force, const mgpu_fab* thermal,
+                             mgpu_fab* const* umac, const double* w0, const mgpu_fab* const* w0mac, const double* rho0_old,
+                             const double* rhoh0_old, const double* rho0_new, const double* rhoh0_new,
+                             const double* p0_old, const double* p0_new, const double* psi, const int* adv_bc,
+                             const int* pmask) {
+  MO_TRY
+  need3(p);
+  Arr so = Arr::view(*sold, 3), sn = Arr::view(*snew, 3), fa = Arr::view(*scal_force, 3), th = Arr::view(*thermal, 3);
+  Arr se[3], sf[3], um[3], wm[3];
+  views3((const mgpu_fab* const*)sedge, 0, se);
+  views3((const mgpu_fab* const*)sflux, 0, sf);
+  views3((const mgpu_fab* const*)umac, 0, um);
+  views3(w0mac, 0, wm);
+  enthalpy_advance_sphr_box(*p, *g, which_step, so, sn, se, sf, fa, th, um, w0, wm, rho0_old, rhoh0_old, rho0_new, rhoh0_new,
+                            p0_old, p0_new, psi, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
   MO_CATCH
 }
 

@@ -475,6 +475,35 @@ module maestro_b200_shim
        integer(c_int), intent(in) :: adv_bc(*), pmask(*)
      end function mgpu_fill_boundary_mf_c
 
+     ! mkscalforce.f90:31 with spherical == 1 (mkrhohforce_3d_sphr :388)
+     integer(c_int) function mgpu_mkrhohforce_sphr_c(p, g, nfabs, scal_force, is_prediction, thermal, umac, p0_1, p0_2, &
+          psi, add_thermal, adv_bc, pmask) bind(C, name="mgpu_mkrhohforce_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs, is_prediction, add_thermal
+       type(mgpu_fab), intent(inout) :: scal_force(*)
+       type(mgpu_fab), intent(in) :: thermal(*)
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: p0_1(*), p0_2(*), psi(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_mkrhohforce_sphr_c
+
+     ! enthalpy_advance.f90:16, spherical
+     integer(c_int) function mgpu_enthalpy_advance_sphr_c(p, g, which_step, sold, snew, sedge, sflux, scal_force, thermal, &
+          umac, w0, w0mac, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, adv_bc, pmask) &
+          bind(C, name="mgpu_enthalpy_advance_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: which_step
+       type(mgpu_fab), intent(inout) :: sold(*), snew(*), scal_force(*)
+       type(mgpu_fab), intent(in) :: thermal(*)
+       type(c_ptr), intent(in) :: sedge(*), sflux(*), umac(*), w0mac(*)
+       real(c_double), intent(in) :: w0(*), rho0_old(*), rhoh0_old(*), rho0_new(*), rhoh0_new(*), p0_old(*), p0_new(*), psi(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_enthalpy_advance_sphr_c
+
      ! fill_3d_data.f90:1280
      integer(c_int) function mgpu_make_normal_c(p, g, nfabs, normal) bind(C, name="mgpu_make_normal")
        import :: c_int, mgpu_params, mgpu_geom, mgpu_fab
@@ -661,6 +690,7 @@ module maestro_b200_shim
   public :: mgpu_mkutrans_sphr_c, mgpu_velpred_sphr_c, mgpu_modify_scal_force_sphr_c, mgpu_put_in_pert_form_sphr_c
   public :: mgpu_fill_boundary_c, mgpu_convert_rhoX_to_X_c, mgpu_modify_scal_force_c, mgpu_put_in_pert_form_c, mgpu_mkrhohforce_c, mgpu_mk_vel_force_c
   public :: mgpu_density_advance_mf_c, mgpu_fill_boundary_mf_c
+  public :: mgpu_mkrhohforce_sphr_c, mgpu_enthalpy_advance_sphr_c
   public :: mgpu_make_normal_c, mgpu_mk_vel_force_sphr_c, mgpu_advance_premac_sphr_c, mgpu_velocity_advance_sphr_c
   public :: mgpu_density_advance_c, mgpu_density_advance_sphr_c, mgpu_enthalpy_advance_c, mgpu_velocity_advance_c, mgpu_advance_premac_c
   public :: mgpu_comm_unique_id, mgpu_comm_init, mgpu_comm_finalize, mgpu_set_option

@@ -137,3 +137,79 @@ def test_velocity_advance_sphr(gpu_ops, oracle, ppm_type, do_sponge, exact):
             assert relerr(a, b) <= 1e-12
     finally:
         lib.set_option("exact", 0)
+
+
+# ---- enthalpy path, spherical: mkrhohforce_3d_sphr (mkscalforce.f90:388) and the enthalpy_advance episode -----------
+def sphr_enthalpy_state(oracle, ept, ppm_type=1):
+    from sphr_common import make_sphr_state
+
+    st = make_sphr_state((14, 12, 10), ops=oracle)
+    p, g = st["p"], st["geom"]
+    p.enthalpy_pred_type = ept
+    p.ppm_type = ppm_type
+    p.rel_eps = 1e-8 * max(np.abs(u.a).max() for u in st["umac"])
+    rc = g.r_cc_loc
+    rad = dict(st["rad"])
+    rad.update(p0_old=5.0 * np.exp(-(rc / 0.5) ** 2) + 0.3, p0_new=5.05 * np.exp(-(rc / 0.5) ** 2) + 0.3,
+               psi=0.2 * np.sin(3.0 * rc))
+    ex = make_episode_extras(st)
+    sold = st["s"].clone()
+    sold.a[p.rho_comp - 1] = np.abs(sold.a[p.rho_comp - 1]) + 0.5
+    oracle.fill_boundary(p, sold, 1, 4, p.nscal, st["adv_bc"], st["pmask"])
+    return st, p, g, rad, ex, sold
+
+
+@pytest.mark.parametrize("is_prediction,ept,add_thermal", [(True, abi.PREDICT_RHOHPRIME, True), (True, abi.PREDICT_H, False),
+                                                           (False, abi.PREDICT_RHOHPRIME, False)])
+def test_mkrhohforce_sphr(gpu_ops, oracle, is_prediction, ept, add_thermal):
+    st, p, g, rad, ex, sold = sphr_enthalpy_state(oracle, ept)
+    res = []
+    for o in (gpu_ops, oracle):
+        f = st["force"].clone()
+        o.mkrhohforce_sphr(p, g, f, is_prediction, ex["thermal"], st["umac"], rad["p0_old"], rad["p0_new"], rad["psi"],
+                           add_thermal, st["adv_bc"], st["pmask"])
+        res.append(f.a[p.rhoh_comp - 1])
+    assert same(res[0], res[1])
+    assert np.abs(res[1]).max() > 0.0
+
+
+def test_mkrhohforce_sphr_error(gpu_ops, oracle):
+    st, p, g, rad, ex, sold = sphr_enthalpy_state(oracle, abi.PREDICT_T_THEN_H)
+    for o in (gpu_ops, oracle):
+        with pytest.raises(Exception, match="should only call mkrhohforce"):
+            o.mkrhohforce_sphr(p, g, st["force"].clone(), True, ex["thermal"], st["umac"], rad["p0_old"], rad["p0_new"],
+                               rad["psi"], True, st["adv_bc"], st["pmask"])
+
+
+@pytest.mark.parametrize("ept,which_step,ppm_type", [(abi.PREDICT_RHOHPRIME, 1, 1), (abi.PREDICT_RHOHPRIME, 2, 2),
+                                                     (abi.PREDICT_H, 2, 1), (abi.PREDICT_RHOH, 1, 1)])
+@pytest.mark.parametrize("exact", [1, 0], ids=["exact", "fast"])
+def test_enthalpy_advance_sphr(gpu_ops, oracle, ept, which_step, ppm_type, exact):
+    from maestro_b200 import lib
+
+    st, p, g, rad, ex, sold0 = sphr_enthalpy_state(oracle, ept, ppm_type)
+    lo, hi = st["lo"], st["hi"]
+    lib.set_option("exact", exact)
+    try:
+        res = []
+        for o in (gpu_ops, oracle):
+            sold = sold0.clone()
+            snew = sold.clone()
+            umac = [u.clone() for u in st["umac"]]
+            sedge = face_fabs(lo, hi, 0, p.nscal, 3)
+            for d in range(3):  # the density edge states density_advance leaves behind
+                sedge[d].a[p.rho_comp - 1] = 0.4 + 0.1 * np.cos(np.arange(sedge[d].a[0].size).reshape(sedge[d].a[0].shape) * 0.01)
+            sflux = face_fabs(lo, hi, 0, p.nscal, 3)
+            force = st["force"].clone()
+            o.enthalpy_advance_sphr(p, g, which_step, sold, snew, sedge, sflux, force, ex["thermal"], umac, rad["w0"],
+                                    st["w0mac"], rad["rho0_old"], rad["rhoh0_old"], rad["rho0_new"], rad["rhoh0_new"],
+                                    rad["p0_old"], rad["p0_new"], rad["psi"], st["adv_bc"], st["pmask"])
+            c = p.rhoh_comp - 1
+            res.append([sold.a[c], snew.a[c], force.a[c]] + [f.a[c] for f in sedge] + [f.a[c] for f in sflux] +
+                       [u.a for u in umac])
+        for a, b in zip(*res):
+            if exact:
+                assert same(a, b)
+            assert relerr(a, b) <= 1e-12
+    finally:
+        lib.set_option("exact", 0)
