@@ -139,7 +139,8 @@ def cpu_reference(config, n_sample, steps, warmup):
     gomp.omp_set_num_threads(len(os.sched_getaffinity(0)))
     if config == "c5":  # built with torch on the host for the CPU arm
         w = build_workload(config, n_sample, "cpu")
-        for f in [w.extra["e"][k] for k in ("sold", "snew", "force")] + sum((w.extra["e"][k] for k in ("umac", "w0mac", "sedge", "sflux")), []):
+        ee = w.extra["e"]
+        for f in [v for v in ee.values() if not isinstance(v, list)] + sum((v for v in ee.values() if isinstance(v, list)), []):
             f.device, f.a = None, f.a.numpy()  # same memory, numpy view: the oracle takes host pointers
     else:
         w = build_workload(config, n_sample, None)

@@ -274,6 +274,34 @@ def c5(n=512, device="cuda:0", rank=0, world=1, seed=4242):
     e = dict(sold=sold, snew=Fab(lo, hi, 4, p.nscal, dm=3, device=device), umac=umac, w0mac=w0mac,
              sedge=face_fabs(lo, hi, 0, p.nscal, 3, device=device), sflux=face_fabs(lo, hi, 0, p.nscal, 3, device=device),
              force=Fab(lo, hi, 1, p.nscal, dm=3, device=device))
+    # the enthalpy and velocity episodes: thermal, grad(pi), rho at the half time, sponge, the velocity itself, the
+    # unit radial vector and the w0 force on the cell centres
+    rad.update(rhoh0_old=rad["rho0_old"] * (1.5 + 0.1 * np.cos(4.0 * rc)), rhoh0_new=rad["rho0_new"] * (1.5 + 0.1 * np.cos(4.0 * rc)),
+               p0_old=5.0 * np.exp(-(rc / 0.5) ** 2) + 0.3, p0_new=5.05 * np.exp(-(rc / 0.5) ** 2) + 0.3,
+               psi=0.2 * np.sin(3.0 * rc), grav=-3.0 * rc / (0.05 + rc ** 2), grav_nph=-3.1 * rc / (0.05 + rc ** 2))
+    for k in ("rho0_old", "rho0_new"):
+        rad[k + "_nph"] = rad[k]
+    e["thermal"] = Fab(lo, hi, 1, 1, dm=3, device=device)
+    e["gpi"] = Fab(lo, hi, 1, 3, dm=3, device=device)
+    e["rhohalf"] = Fab(lo, hi, 1, 1, dm=3, device=device)
+    e["sponge"] = Fab(lo, hi, 0, 1, dm=3, device=device, fill=1.0)
+    e["ut"] = Fab(lo, hi, 4, 3, dm=3, device=device)
+    e["unew"] = Fab(lo, hi, 4, 3, dm=3, device=device)
+    e["normal"] = Fab(lo, hi, 1, 3, dm=3, device=device)
+    e["w0fc"] = Fab(lo, hi, 1, 3, dm=3, device=device)
+    Xc, Yc, Zc = coords(e["gpi"])
+    rr = torch.sqrt(Xc * Xc + Yc * Yc + Zc * Zc)
+    e["thermal"].a[0] = 0.05 * torch.cos(5.0 * Xc) * torch.sin(4.0 * Yc) + 0.0 * Zc
+    for d, Cd in enumerate((Xc, Yc, Zc)):
+        e["gpi"].a[d] = 0.1 * torch.sin(3.0 * Cd) + 0.0 * rr
+        e["normal"].a[d] = Cd / rr
+        e["w0fc"].a[d] = 0.02 * torch.exp(-(rr / 0.3) ** 2) * Cd
+    e["rhohalf"].a[0] = 2.01 * torch.exp(-(rr / 0.35) ** 2) + 0.1
+    del rr
+    Xu, Yu, Zu = coords(e["ut"])
+    e["ut"].a[0] = 0.5 * (torch.sin(2 * np.pi * Zu) + torch.cos(2 * np.pi * Yu)) + 0.0 * Xu
+    e["ut"].a[1] = 0.5 * (torch.sin(2 * np.pi * Xu) + torch.cos(2 * np.pi * Zu)) + 0.0 * Yu
+    e["ut"].a[2] = 0.5 * (torch.sin(2 * np.pi * Yu) + torch.cos(2 * np.pi * Xu)) + 0.0 * Zu
     sold0, umac0 = e["sold"].a.clone(), [u.a.clone() for u in umac]
 
     def reset():
@@ -284,18 +312,25 @@ def c5(n=512, device="cuda:0", rank=0, world=1, seed=4242):
     def step(ops):
         ops.density_advance_sphr(p, g, 1, e["sold"], e["snew"], e["sedge"], e["sflux"], e["force"], e["umac"], rad["w0"],
                                  e["w0mac"], rad["rho0_old"], rad["rho0_new"], adv_bc, pmask)
+        ops.enthalpy_advance_sphr(p, g, 1, e["sold"], e["snew"], e["sedge"], e["sflux"], e["force"], e["thermal"], e["umac"],
+                                  rad["w0"], e["w0mac"], rad["rho0_old"], rad["rhoh0_old"], rad["rho0_new"], rad["rhoh0_new"],
+                                  rad["p0_old"], rad["p0_new"], rad["psi"], adv_bc, pmask)
+        ops.velocity_advance_sphr(p, g, e["ut"], e["unew"], e["sold"], e["rhohalf"], e["umac"], e["gpi"], e["normal"],
+                                  rad["w0"], e["w0mac"], e["w0fc"], rad["rho0_old"], rad["rho0_old_nph"], rad["grav"],
+                                  rad["grav_nph"], e["sponge"], adv_bc, pmask)
 
     def outputs():
-        return {"snew": e["snew"].valid()}
+        return {"snew": e["snew"].valid(), "unew": e["unew"].valid()}
 
     zones = n * n * (khi - klo + 1)
-    ncomp = p.nspec + 1 + p.ntrac
+    ncomp = (p.nspec + 1 + p.ntrac) + 1 + 3
     desc = {"workload": "wdconvect-like spherical 3D %d^3 (drdxfac 5), outlets, ppm_type=1, slab-partitioned in z over %d "
-                        "GPU(s), density_advance episode with the spherical base state (%d comps)" % (n, world, ncomp),
+                        "GPU(s), advective step with the spherical base state: density_advance (5 comps) + "
+                        "enthalpy_advance (1) + velocity_advance (3)" % (n, world),
             "zones_per_gpu": zones, "components": ncomp}
-    # density_advance 368 B + w0mac 24 B read per zone
-    return Workload("c5", desc, p, zones, ncomp, 392.0, step, reset, outputs, "strong" if world > 1 else "weak",
-                    extra=dict(e=e, geom=g))
+    # density 368 + enthalpy 96 + velocity 176 B per zone + w0mac 24 B read by each episode
+    return Workload("c5", desc, p, zones, ncomp, 368.0 + 96.0 + 176.0 + 72.0, step, reset, outputs,
+                    "strong" if world > 1 else "weak", extra=dict(e=e, geom=g))
 
 
 BUILDERS = {"c2": c2, "c3": c3, "c4": c4, "c5": c5}
