@@ -158,18 +158,19 @@ def cpu_reference(config, n_sample, steps, warmup):
 
 
 def per_zone_parity(ref, got):
-    """max over zones of |got - ref| / max(|ref|, floor), floor = 1e-10 x the field's max-norm, per output field"""
+    """per output field: max over zones of |got - ref| / max(|ref|, floor) with floor = 1e-10 x the field's max-norm
+    (per-zone relative error; sign-changing fields reach it at their zero crossings), and the max-norm relative error
+    max|got - ref| / max|ref| the tests assert"""
     import torch
 
-    out = {}
+    zone, norm = {}, {}
     for k in ref:
         a, b = got[k].double(), ref[k].double()
-        fl = 1e-10 * float(b.abs().max())
-        if fl == 0.0:
-            out[k] = float((a - b).abs().max())
-            continue
-        out[k] = float(((a - b).abs() / torch.clamp(b.abs(), min=fl)).max())
-    return out
+        mx = float(b.abs().max())
+        err = (a - b).abs()
+        norm[k] = float(err.max()) / mx if mx > 0.0 else float(err.max())
+        zone[k] = float((err / torch.clamp(b.abs(), min=1e-10 * mx)).max()) if mx > 0.0 else float(err.max())
+    return zone, norm
 
 
 def main():
@@ -359,9 +360,11 @@ def main():
             te0.record(); w.step(ops); te1.record()
             torch.cuda.synchronize()
             ms_exact += te0.elapsed_time(te1) / 3
-        parity = {"what": "FAST build (timed above) against the exact build (bit-identical to the oracle), max over zones of "
-                          "|a-b| / max(|b|, 1e-10 max|b|) per output field", "per_zone_rel": per_zone_parity(w.outputs(), fast)}
-        parity["worst"] = max(parity["per_zone_rel"].values())
+        zone, norm = per_zone_parity(w.outputs(), fast)
+        parity = {"what": "FAST build (timed above) against the exact build (bit-identical to the oracle) per output field: "
+                          "per_zone_rel = max over zones of |a-b| / max(|b|, 1e-10 max|b|), max_norm_rel = max|a-b| / max|b|",
+                  "per_zone_rel": zone, "max_norm_rel": norm, "worst_per_zone": max(zone.values()),
+                  "worst_max_norm": max(norm.values())}
         exact_line = {"ms_per_step": ms_exact, "value": zone_updates / (ms_exact * 1e-3),
                       "note": "exact build (--opt exact=1): no FMA contraction, reference expression order, bit-identical to the oracle"}
         lib.set_option("exact", 0)
