@@ -209,11 +209,15 @@ int mgpu_mk_rhoh_flux(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux,
                       const double* rhoh0_edge_old, const double* rhoh0_new,
                       const double* rhoh0_edge_new);
 
-/* update_scal (Source/update_scal.f90:16), planar (_2d :246, _3d_cart :370); valid cells only, the
- * caller follows with mgpu_fill_boundary (update_scal.f90:110-122). EOS-below-cutoff zones
- * (:421-447) are left to the caller. */
+/* update_scal (Source/update_scal.f90:16), planar (_2d :246, _3d_cart :370) and spherical (_3d_sphr :508); valid
+ * cells only, the caller follows with mgpu_fill_boundary (update_scal.f90:110-122).  With do_eos_h_above_cutoff and
+ * nstart == rhoh_comp the zones with rho <= base_cutoff_density get rhoh from the EOS at (rho, p0_new, X)
+ * (:421-447): p0_new is the level's 1-D array (planar) or p0_new_cart the fabs of put_1d_array_on_cart (spherical);
+ * needs mgpu_set_eos -- without an EOS the call FAILS when a zone is below the cutoff (it never skips the reset
+ * silently).  Both may be NULL for the other component ranges. */
 int mgpu_update_scal(const mgpu_params* p, int nfabs, int nstart, int nstop, const mgpu_fab* sold,
-                     mgpu_fab* snew, const mgpu_fab* const* sflux, const mgpu_fab* force);
+                     mgpu_fab* snew, const mgpu_fab* const* sflux, const mgpu_fab* force, const double* p0_new,
+                     const mgpu_fab* p0_new_cart);
 
 /* update_velocity (Source/update_vel.f90:15), planar (_2d :174, _3d :227). */
 int mgpu_update_velocity(const mgpu_params* p, int nfabs, const mgpu_fab* uold, mgpu_fab* unew,
@@ -348,7 +352,7 @@ int mgpu_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int whi
                                const mgpu_fab* thermal, mgpu_fab* const* umac, const double* w0,
                                const mgpu_fab* const* w0mac, const double* rho0_old, const double* rhoh0_old,
                                const double* rho0_new, const double* rhoh0_new, const double* p0_old, const double* p0_new,
-                               const double* psi, const int* adv_bc, const int* pmask);
+                               const double* tempbar, const double* psi, const int* adv_bc, const int* pmask);
 
 /* ---- L4 episode: density_advance (Source/density_advance.f90:20), planar, one level ------
  * Signature mirrors the Fortran argument list; sold is modified in place exactly as the reference
@@ -397,16 +401,19 @@ int mgpu_velocity_advance(const mgpu_params* p, const mgpu_fab* uold, mgpu_fab* 
                           const double* w0_force, const double* rho0_old, const double* rho0_nph,
                           const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
                           const int* adv_bc, const int* pmask);
-/* enthalpy_advance (Source/enthalpy_advance.f90:16), enthalpy_pred_type in {predict_rhoh, predict_rhohprime,
- * predict_h} (the temperature-based types need the EOS).  grav_old / grav_nph: make_grav_cell of
- * rho0_old / (rho0_old+rho0_new)/2.  sedge(rho_comp) must hold the density edge states left by density_advance
- * (mkflux.f90:1126).  EOS-below-cutoff zones of update_scal (:421-447) are left to the caller. */
+/* enthalpy_advance (Source/enthalpy_advance.f90:16), every enthalpy_pred_type the reference codes (predict_hprime
+ * raises, mkflux.f90:1167).  The temperature-based types (predict_T_then_rhohprime, predict_T_then_h,
+ * predict_Tprime_then_h: mktempforce, T or T' edge states, makeHfromRhoT_edge) and the reset of rhoh below the cutoff
+ * (update_scal.f90:421-447, do_eos_h_above_cutoff) call the EOS: they need mgpu_set_eos and fail without it.  tempbar:
+ * the level's 1-D array (may be NULL for the other types).  grav_old / grav_nph: make_grav_cell of rho0_old /
+ * (rho0_old+rho0_new)/2.  sedge(rho_comp) and the species edge states must hold what density_advance left
+ * (mkflux.f90:1126, rhoh_vs_t.f90:437-461). */
 int mgpu_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgpu_fab* snew,
                           mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
                           const mgpu_fab* thermal, mgpu_fab* const* umac, const double* w0, const double* rho0_old,
                           const double* rhoh0_old, const double* rho0_new, const double* rhoh0_new,
-                          const double* p0_old, const double* p0_new, const double* psi, const double* grav_old,
-                          const double* grav_nph, const int* adv_bc, const int* pmask);
+                          const double* p0_old, const double* p0_new, const double* tempbar, const double* psi,
+                          const double* grav_old, const double* grav_nph, const int* adv_bc, const int* pmask);
 
 /* ---- consumers / producers next to the path, planar ---------------------------
  * estdt (Source/estdt.f90:29; per box _2d :348, _3d_cart :467): the time-step limits of one level from the advective
@@ -432,6 +439,80 @@ int mgpu_estdt_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, const m
  * relative (the reference's own MPI reduction order is not fixed either). */
 int mgpu_make_etarho_planar(const mgpu_params* p, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
                             double* etarho_cc);
+
+
+/* ---- EOS -----------------------------------------------------------------------------
+ * The generic front end of Microphysics/EOS/eos.F90:99 (composition eos_type.f90:157, reset_inputs eos.F90:129,
+ * eos_reset :291) over gamma_law_general (Microphysics/EOS/gamma_law_general/gamma_law_general.f90:60).  Like the
+ * reference's eos_init (eos.F90:26) the EOS is process state, set once; mgpu_set_eos(NULL) unsets it.  The network's
+ * aion / zion are not part of MAESTRO's tree (they come with the problem's network), so the caller passes them; k_B
+ * and n_A are the values of Source/constants_cgs.f90:15,24.  The entropy of gamma_law_general (Sackur-Tetrode, :177)
+ * is not evaluated -- nothing on the advective path reads it -- so eos_input_ps raises, like eos_input_ph / _th do in
+ * the reference (:147-160).  A tabulated EOS (helmeos) is out of scope. */
+#define MGPU_EOS_MAXSPEC 32
+enum { MGPU_EOS_NONE = 0, MGPU_EOS_GAMMA_LAW = 1 };
+enum { /* eos_type.f90:8-15 */
+  MGPU_EOS_INPUT_RT = 1, MGPU_EOS_INPUT_RH = 2, MGPU_EOS_INPUT_TP = 3, MGPU_EOS_INPUT_RP = 4, MGPU_EOS_INPUT_RE = 5,
+  MGPU_EOS_INPUT_PS = 6, MGPU_EOS_INPUT_PH = 7, MGPU_EOS_INPUT_TH = 8
+};
+typedef struct {
+  int kind;           /* MGPU_EOS_GAMMA_LAW */
+  int assume_neutral; /* eos_assume_neutral (gamma_law_general/_parameters) */
+  int nspec;
+  int pad_;
+  double gamma;       /* eos_gamma */
+  double k_B, n_A;    /* constants_cgs.f90:15,24: 1.3806488e-16, 6.02214129e23 */
+  double mintemp, maxtemp, mindens, maxdens, mine, maxe, minp, maxp, minh, maxh; /* eos_type.f90:42-57 */
+  double small_temp;  /* probin small_temp (rhoh_vs_t.f90:431) */
+  double aion[MGPU_EOS_MAXSPEC], zion[MGPU_EOS_MAXSPEC]; /* network */
+} mgpu_eos;
+int mgpu_set_eos(const mgpu_eos* e);
+/* eos(input, state) at n points, host arrays.  state is (n, MGPU_EOS_NQ) point-fastest: state[q*n + i]; xn is
+ * (n, nspec) point-fastest.  Inputs are read from the columns the input mode names, every column is written. */
+enum {
+  MGPU_EOS_Q_RHO = 0, MGPU_EOS_Q_T, MGPU_EOS_Q_P, MGPU_EOS_Q_E, MGPU_EOS_Q_H, MGPU_EOS_Q_CV, MGPU_EOS_Q_CP,
+  MGPU_EOS_Q_CS, MGPU_EOS_Q_DPDT, MGPU_EOS_Q_DPDR, MGPU_EOS_Q_DEDT, MGPU_EOS_Q_DEDR, MGPU_EOS_Q_DHDT, MGPU_EOS_Q_MU,
+  MGPU_EOS_Q_ABAR, MGPU_EOS_Q_ZBAR, MGPU_EOS_NQ
+};
+int mgpu_eos_eval(int input, long n, double* state, const double* xn);
+
+/* makeHfromRhoT_edge (Source/rhoh_vs_t.f90:20; _2d :252, _3d_cart :392): the rhoh component of the edge states from
+ * the predicted T (or T') and the density / species edge states, per enthalpy_pred_type and species_pred_type.  The
+ * base-state arrays are the level's 1-D slices (cell (0:nr-1), edge (0:nr)).  QUIRK kept: the 3-D Cartesian y and z
+ * faces read T' from the x-face array (:487, :543). */
+int mgpu_make_h_from_rhot_edge(const mgpu_params* p, int nfabs, mgpu_fab* const* sedge, const double* rho0_old,
+                               const double* rhoh0_old, const double* t0_old, const double* rho0_edge_old,
+                               const double* rhoh0_edge_old, const double* t0_edge_old, const double* rho0_new,
+                               const double* rhoh0_new, const double* t0_new, const double* rho0_edge_new,
+                               const double* rhoh0_edge_new, const double* t0_edge_new);
+/* the same with spherical == 1 (wrapper :84-105 + _3d_sphr :596): the half-time base state is put on the cell centres
+ * (2 ghost cells, put_1d_array_on_cart with its boundary fill) inside. */
+int mgpu_make_h_from_rhot_edge_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* const* sedge,
+                                    const double* rho0_old, const double* rhoh0_old, const double* t0_old,
+                                    const double* rho0_new, const double* rhoh0_new, const double* t0_new,
+                                    const int* adv_bc, const int* pmask);
+/* mktempforce (Source/mkscalforce.f90:719; _2d :896, _3d :954, _3d_sphr :1026): comp temp_comp of temp_force on the
+ * valid cells, then its ghost cells (foextrap_comp, :833-837).  g may be NULL for planar geometry. */
+int mgpu_mktempforce(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* temp_force,
+                     const mgpu_fab* const* umac, const mgpu_fab* s, const mgpu_fab* thermal, const double* p0_old,
+                     const double* psi, const int* adv_bc, const int* pmask);
+/* firstdt (Source/firstdt.f90:25; _2d :330, _3d :460, _3d_sphr :599) for one level: the velocity force is built inside
+ * like the reference does (:96-100, mk_vel_force with zero w0 and no utilde force); on return *dt = min(*dt,
+ * dt_lev*init_shrink) and *umax = max(*umax, umax_lev) (:171-190); the small_dt / max_dt / fixed_dt rules (:199-216)
+ * stay with the caller.  g may be NULL for planar geometry. */
+int mgpu_firstdt(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* u, const mgpu_fab* gpi,
+                 const mgpu_fab* s, const mgpu_fab* divU, const double* rho0, const double* p0, const double* grav,
+                 const double* gamma1bar, double cflfac, double init_shrink, int use_soundspeed_firstdt,
+                 int use_divu_firstdt, double* dt, double* umax);
+/* makeTfromRhoH / makeTfromRhoP (Source/rhoh_vs_t.f90:800, :1165), planar and spherical: the temperature component
+ * of the state on the valid cells from (rho, h, X) or (rho, p0, X), then its ghost cells (:846-852, :1224-1230).
+ * use_eos_e_instead_of_h / use_pprime_in_tfromp: the probin switches of the same names.  p0: the level's 1-D array;
+ * with spherical == 1 it is put on the cell centres inside (:1097, :1410).  update_rhoh (makeTfromRhoP only): also reset
+ * rhoh = rho * h(rho, p0, X). */
+int mgpu_make_t_from_rhoh(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* state, const double* p0,
+                          int use_eos_e_instead_of_h, const int* adv_bc, const int* pmask);
+int mgpu_make_t_from_rhop(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* state, const double* p0,
+                          int update_rhoh, int use_pprime_in_tfromp, const int* adv_bc, const int* pmask);
 
 #ifdef __cplusplus
 }

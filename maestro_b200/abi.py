@@ -110,7 +110,7 @@ OPERATORS = {
     "bds": (C.c_int, [P_, C.c_int, F_, FF_, FF_, F_, c_int_p] + [C.c_int] * 5),
     "mk_rhoX_flux": (C.c_int, [P_, C.c_int, FF_, F_, FF_, FF_] + [c_double_p] * 6 + [C.c_int] * 2),
     "mk_rhoh_flux": (C.c_int, [P_, C.c_int, FF_, FF_, FF_] + [c_double_p] * 9),
-    "update_scal": (C.c_int, [P_, C.c_int, C.c_int, C.c_int, F_, F_, FF_, F_]),
+    "update_scal": (C.c_int, [P_, C.c_int, C.c_int, C.c_int, F_, F_, FF_, F_, c_double_p, F_]),
     "update_velocity": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, F_, c_double_p]),
     "addw0": (C.c_int, [P_, C.c_int, FF_, c_double_p, C.c_double]),
     "mkutrans": (C.c_int, [P_, C.c_int, F_, F_, FF_, c_double_p, c_int_p, c_int_p]),
@@ -123,7 +123,7 @@ OPERATORS = {
                      + [C.c_int]),
     "advance_premac": (C.c_int, [P_, F_, F_, FF_, F_] + [c_double_p] * 4 + [c_int_p] * 3),
     "velocity_advance": (C.c_int, [P_, F_, F_, F_, F_, FF_, F_] + [c_double_p] * 6 + [F_] + [c_int_p] * 2),
-    "enthalpy_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_] + [c_double_p] * 10 + [c_int_p] * 2),
+    "enthalpy_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_] + [c_double_p] * 11 + [c_int_p] * 2),
     "estdt": (C.c_int, [P_, C.c_int, F_, F_, F_, F_, F_] + [c_double_p] * 3 + [C.c_double] * 2 + [c_double_p] * 2),
     "make_etarho_planar": (C.c_int, [P_, C.c_int, F_, c_double_p, c_double_p]),
     "estdt_sphr": (C.c_int, [P_, G_, C.c_int, F_, F_, F_, F_, F_, FF_] + [c_double_p] * 3 + [C.c_double] * 2
@@ -142,7 +142,7 @@ OPERATORS = {
     "put_in_pert_form_sphr": (C.c_int, [P_, G_, C.c_int, F_, c_double_p, C.c_int, C.c_int]),
     "mkrhohforce_sphr": (C.c_int, [P_, G_, C.c_int, F_, C.c_int, F_, FF_, c_double_p, c_double_p, c_double_p, C.c_int,
                                    c_int_p, c_int_p]),
-    "enthalpy_advance_sphr": (C.c_int, [P_, G_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_, c_double_p, FF_] + [c_double_p] * 7
+    "enthalpy_advance_sphr": (C.c_int, [P_, G_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_, c_double_p, FF_] + [c_double_p] * 8
                               + [c_int_p] * 2),
     "make_normal": (C.c_int, [P_, G_, C.c_int, F_]),
     "mk_vel_force_sphr": (C.c_int, [P_, G_, C.c_int, F_, C.c_int, F_, FF_, c_double_p, FF_, F_, F_, C.c_int, F_, c_double_p,
@@ -156,6 +156,46 @@ OPERATORS = {
     "density_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, FF_, c_double_p, F_] + [c_double_p] * 4
                         + [c_int_p] * 2),
 }
+
+# the EOS and the pieces of the path that call it
+E_ = None  # set below (POINTER(mgpu_eos))
+
+
+class mgpu_eos(C.Structure):
+    """gamma_law_general + the generic front end's limits (include/maestro_b200.h)"""
+    MAXSPEC = 32
+    _fields_ = [
+        ("kind", C.c_int),
+        ("assume_neutral", C.c_int),
+        ("nspec", C.c_int),
+        ("pad_", C.c_int),
+        ("gamma", C.c_double),
+        ("k_B", C.c_double),
+        ("n_A", C.c_double),
+        ("mintemp", C.c_double), ("maxtemp", C.c_double), ("mindens", C.c_double), ("maxdens", C.c_double),
+        ("mine", C.c_double), ("maxe", C.c_double), ("minp", C.c_double), ("maxp", C.c_double),
+        ("minh", C.c_double), ("maxh", C.c_double),
+        ("small_temp", C.c_double),
+        ("aion", C.c_double * 32),
+        ("zion", C.c_double * 32),
+    ]
+
+
+E_ = C.POINTER(mgpu_eos)
+EOS_NONE, EOS_GAMMA_LAW = 0, 1
+EOS_INPUT_RT, EOS_INPUT_RH, EOS_INPUT_TP, EOS_INPUT_RP, EOS_INPUT_RE, EOS_INPUT_PS, EOS_INPUT_PH, EOS_INPUT_TH = range(1, 9)
+EOS_Q = ["rho", "T", "p", "e", "h", "cv", "cp", "cs", "dpdT", "dpdr", "dedT", "dedr", "dhdT", "mu", "abar", "zbar"]
+OPERATORS.update({
+    "set_eos": (C.c_int, [E_]),
+    "eos_eval": (C.c_int, [C.c_int, C.c_long, c_double_p, c_double_p]),
+    "make_h_from_rhot_edge": (C.c_int, [P_, C.c_int, FF_] + [c_double_p] * 12),
+    "make_h_from_rhot_edge_sphr": (C.c_int, [P_, G_, C.c_int, FF_] + [c_double_p] * 6 + [c_int_p] * 2),
+    "mktempforce": (C.c_int, [P_, G_, C.c_int, F_, FF_, F_, F_, c_double_p, c_double_p, c_int_p, c_int_p]),
+    "firstdt": (C.c_int, [P_, G_, C.c_int, F_, F_, F_, F_] + [c_double_p] * 4 + [C.c_double] * 2 + [C.c_int] * 2
+                + [c_double_p] * 2),
+    "make_t_from_rhoh": (C.c_int, [P_, G_, C.c_int, F_, c_double_p, C.c_int, c_int_p, c_int_p]),
+    "make_t_from_rhop": (C.c_int, [P_, G_, C.c_int, F_, c_double_p, C.c_int, C.c_int, c_int_p, c_int_p]),
+})
 
 # several boxes per rank: the CUDA library only (the oracle's multifab is one box covering the domain)
 MULTIBOX = {

@@ -12,6 +12,7 @@
 
 #include "mgpu_bds.cuh"
 #include "mgpu_edge.cuh"
+#include "mgpu_eos.cuh"
 #include "mgpu_fused.cuh"
 #include "mgpu_halo.cuh"
 #include "mgpu_reduce.cuh"
@@ -856,12 +857,12 @@ static size_t fab_bytes(const int* lo, const int* hi, int dm, int ng, int nodal_
 static void vel_force_dev(const mgpu_params& P, DV& force, bool is_final, const DV& uold, const DV* uedge,
                           const double* w0, const DV& gpi, const DV& rho1, const double* rho0, const double* grav,
                           const double* w0_force, const int* lo, const int* hi, int ng_f, const int* adv_bc,
-                          const int* pmask) {
+                          const int* pmask, bool add_utilde = true) {
   VelForceArgs a;
   a.dm = P.dm;
   a.nr = P.nr;
   a.is_final_update = is_final;
-  a.add_utilde = true;
+  a.add_utilde = add_utilde;
   a.dr = P.dx[P.dm - 1];
   a.rho_cut = P.buoyancy_cutoff_factor * P.base_cutoff_density;
   a.omega = P.omega; a.sin_theta = P.sin_theta; a.cos_theta = P.cos_theta; a.rotation_radius = P.rotation_radius;
@@ -1090,16 +1091,22 @@ static void enthalpy_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
                                       DV* sedge, DV* sflux, DV& scal_force, const DV& thermal, DV* umac, const double* w0_h,
                                       const DV* w0mac, const double* rho0_old_h, const double* rhoh0_old_h,
                                       const double* rho0_new_h, const double* rhoh0_new_h, const double* p0_old_h,
-                                      const double* p0_new_h, const double* psi_h, const int* lo, const int* hi, int ng_s,
-                                      int ng_f, const int* adv_bc, const int* pmask) {
+                                      const double* p0_new_h, const double* tempbar_h, const double* psi_h, const int* lo,
+                                      const int* hi, int ng_s, int ng_f, const int* adv_bc, const int* pmask) {
   const int dm = 3, nr = g.nr_fine;
   const int ept = P.enthalpy_pred_type;
   const int foextrap_comp = dm + P.nscal + 2;
   const int rhoh = P.rhoh_comp - 1, rho = P.rho_comp - 1;
   if (ept == MGPU_PREDICT_HPRIME) throw Error("mk_rhoh_flux : predict_hprime not coded yet");  // mkflux.f90:1167
-  if (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H)
-    throw Error("enthalpy_advance: temperature-based prediction needs the EOS (makeHfromRhoT_edge): not on the device");
+  const bool pred_T =
+      (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H);
+  if (pred_T) {
+    the_eos("enthalpy_advance (temperature-based prediction: mktempforce, makeHfromRhoT_edge)");
+    if (!tempbar_h) throw Error("enthalpy_advance: the temperature-based predictions need tempbar");
+  }
+  const int temp = P.temp_comp - 1;
   SphrCtx X{P, g, make_geom(P, g), lo, hi, adv_bc, pmask};
+  const double* tempbar = pred_T ? upload_small(tempbar_h, (size_t)nr) : nullptr;
   const double* rho0_old = upload_small(rho0_old_h, (size_t)nr);
   const double* rho0_new = upload_small(rho0_new_h, (size_t)nr);
   const double* rhoh0_old = upload_small(rhoh0_old_h, (size_t)nr);
@@ -1121,9 +1128,33 @@ static void enthalpy_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
     fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc,
                       pmask, false);
   };
+  auto pert_T = [&](bool flag) {  // :214-217, :268-272
+    pert_form_sphr_dev(g, X.gd, sold, tempbar, P.temp_comp, flag, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.temp_comp, flag ? foextrap_comp : dm + P.temp_comp, 1, adv_bc,
+                      pmask, false);
+  };
   if (ept == MGPU_PREDICT_H) rhoh_to_h(true);     // :122-126
   set_dev(scal_force.p, 0.0, scal_force.size());  // :132-134
-  rhoh_force_sphr_full(X, scal_force, true, thermal, umac, p0_old_h, p0_old_h, psi_h, true, ng_f);
+  if (pred_T) {  // :190-195: mktempforce with spherical == 1 (mkscalforce.f90:770-776, _3d_sphr :1026)
+    size_t mark = arena_mark();
+    TempForceArgs ta;
+    ta.dm = dm; ta.nr = nr; ta.rho = rho; ta.temp = temp; ta.spec0 = P.spec_comp - 1;
+    ta.sphr = true;
+    ta.dr = g.dr;
+    for (int d = 0; d < 3; ++d) ta.dx[d] = P.dx[d];
+    ta.vb = grown(lo, hi, dm, 0);
+    ta.f = scal_force.comp(temp); ta.s = sold; ta.thermal = thermal;
+    for (int d = 0; d < dm; ++d) ta.umac[d] = umac[d];
+    ta.p0_old = ta.psi = nullptr;
+    ta.p0_cart = sphr_cart(X, upload_small(p0_old_h, (size_t)nr), 1, foextrap_comp);
+    ta.psi_cart = arena_fab(lo, hi, 3, 0, nullptr, 1);
+    put_1d_array_on_cart_dev(P, g, X.gd, upload_small(psi_h, (size_t)nr), ta.psi_cart, false, false, lo, hi);
+    mktempforce_dev(ta);
+    arena_release(mark);
+    fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.temp_comp, foextrap_comp, 1, adv_bc, pmask, false);
+  } else {
+    rhoh_force_sphr_full(X, scal_force, true, thermal, umac, p0_old_h, p0_old_h, psi_h, true, ng_f);
+  }
   if (ept == MGPU_PREDICT_RHOHPRIME) {  // :141-156
     size_t mark = arena_mark();
     DV rhoh0_old_cart = sphr_cart(X, rhoh0_old, 1, dm + P.rhoh_comp);
@@ -1136,15 +1167,38 @@ static void enthalpy_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
   addw0_sphr_dev(umac, w0mac, 1.0, lo, hi);  // :201
   fill_umac();
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(true);  // :204-208
+  if (ept == MGPU_PREDICT_TPRIME_THEN_H) pert_T(true);
   {
     const bool cons = (ept == MGPU_PREDICT_RHOH);  // :232-254
+    const int pc = pred_T ? temp : rhoh;           // :220-226
     size_t mark = arena_mark();
-    if (P.bds_type != 0) bds_dev(P, sold, sedge, umac, scal_force, lo, hi, rhoh, cons, ng_s, ng_f);
-    else edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, rhoh, dm + P.rhoh_comp, false, cons, ng_s, ng_f);
+    if (P.bds_type != 0) bds_dev(P, sold, sedge, umac, scal_force, lo, hi, pc, cons, ng_s, ng_f);
+    else edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, pc, dm + pc + 1, false, cons, ng_s, ng_f);
     arena_release(mark);
   }
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(false);  // :257-261
+  if (ept == MGPU_PREDICT_TPRIME_THEN_H) pert_T(false);
   if (ept == MGPU_PREDICT_H) rhoh_to_h(false);     // :272-276
+  if (pred_T) {  // :280-286: makeHfromRhoT_edge with spherical == 1 (rhoh_vs_t.f90:84-105, _3d_sphr :596)
+    size_t mark = arena_mark();
+    std::vector<double> r0h(nr), rh0h(nr), t0h(nr);
+    for (int r = 0; r < nr; ++r) {
+      r0h[r] = 0.5 * (rho0_old_h[r] + rho0_new_h[r]);
+      rh0h[r] = 0.5 * (rhoh0_old_h[r] + rhoh0_new_h[r]);
+      t0h[r] = 0.5 * (tempbar_h[r] + tempbar_h[r]);
+    }
+    HEdgeArgs ha{};
+    ha.dm = dm; ha.ept = ept; ha.spt = P.species_pred_type;
+    ha.rho = rho; ha.rhoh = rhoh; ha.temp = temp; ha.spec0 = P.spec_comp - 1;
+    ha.sphr = true;
+    ha.vb = grown(lo, hi, dm, 0);
+    for (int d = 0; d < dm; ++d) ha.sedge[d] = sedge[d];
+    ha.rho0_cart = sphr_cart(X, upload_small(r0h.data(), (size_t)nr), 2, dm + P.rho_comp);
+    ha.rhoh0_cart = sphr_cart(X, upload_small(rh0h.data(), (size_t)nr), 2, dm + P.rhoh_comp);
+    ha.t0_cart = sphr_cart(X, upload_small(t0h.data(), (size_t)nr), 2, dm + P.temp_comp);
+    h_from_rhot_edge_dev(ha);
+    arena_release(mark);
+  }
   addw0_sphr_dev(umac, w0mac, -1.0, lo, hi);       // :293
   fill_umac();
   const bool s1 = (which_step == 1);
@@ -1176,7 +1230,13 @@ static void enthalpy_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
   ua.vb = grown(lo, hi, dm, 0);
   ua.sold = sold; ua.snew = snew; ua.force = scal_force;
   for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
+  size_t mark_p0 = arena_mark();
+  if (P.do_eos_h_above_cutoff && have_eos()) {  // :418-424: p0_new on the cell centres (only the EOS reset reads it)
+    ua.p0_new_cart = sphr_cart(X, upload_small(p0_new_h, (size_t)nr), 1, foextrap_comp);
+    ua.have_p0_new_cart = true;
+  }
   update_scal_dev(P, ua, P.rhoh_comp, P.rhoh_comp);  // :431
+  arena_release(mark_p0);
   fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rhoh_comp, dm + P.rhoh_comp, 1, adv_bc, pmask, false);
 }
 
@@ -1185,16 +1245,26 @@ static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold,
                                  DV& scal_force, const DV& thermal, DV* umac, const double* w0_h,
                                  const double* rho0_old_h, const double* rhoh0_old_h, const double* rho0_new_h,
                                  const double* rhoh0_new_h, const double* p0_old_h, const double* p0_new_h,
-                                 const double* psi_h, const double* grav_old_h, const double* grav_nph_h, const int* lo,
-                                 const int* hi, int ng_s, int ng_f, const int* adv_bc, const int* pmask) {
+                                 const double* tempbar_h, const double* psi_h, const double* grav_old_h,
+                                 const double* grav_nph_h, const int* lo, const int* hi, int ng_s, int ng_f,
+                                 const int* adv_bc, const int* pmask) {
   const int dm = P.dm, nr = P.nr;
   const int ept = P.enthalpy_pred_type;
   const int foextrap_comp = dm + P.nscal + 2;
   if (ept == MGPU_PREDICT_HPRIME) throw Error("mk_rhoh_flux : predict_hprime not coded yet");  // mkflux.f90:1167
-  if (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H)
-    throw Error("enthalpy_advance: temperature-based prediction needs the EOS (makeHfromRhoT_edge): not on the device");
+  const bool pred_T =
+      (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H);
+  if (pred_T) {
+    the_eos("enthalpy_advance (temperature-based prediction: mktempforce, makeHfromRhoT_edge)");
+    if (!tempbar_h) throw Error("enthalpy_advance: the temperature-based predictions need tempbar");
+  }
   std::vector<double> e[4] = {std::vector<double>(nr + 1), std::vector<double>(nr + 1), std::vector<double>(nr + 1),
                               std::vector<double>(nr + 1)};
+  std::vector<double> t0e(nr + 1);
+  if (pred_T) cell_to_edge_host(tempbar_h, t0e.data(), nr);  // :118-119 (old and new are both tempbar)
+  const double* tempbar = pred_T ? upload_small(tempbar_h, nr) : nullptr;
+  const double* t0_edge = pred_T ? upload_small(t0e.data(), nr + 1) : nullptr;
+  const int temp = P.temp_comp - 1;
   cell_to_edge_host(rho0_old_h, e[0].data(), nr);  // enthalpy_advance.f90:114-117
   cell_to_edge_host(rho0_new_h, e[1].data(), nr);
   cell_to_edge_host(rhoh0_old_h, e[2].data(), nr);
@@ -1238,9 +1308,28 @@ static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold,
     fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc,
                       pmask, false);
   };
+  auto pert_T = [&](bool flag) {  // put_in_pert_form on the temperature with tempbar (:214-217, :268-272)
+    put_in_pert_form_dev(P, sold, tempbar, P.temp_comp, flag, lo, hi);
+    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.temp_comp, flag ? foextrap_comp : dm + P.temp_comp, 1, adv_bc,
+                      pmask, false);
+  };
   if (ept == MGPU_PREDICT_H) rhoh_to_h(true);  // :122-126
   set_dev(scal_force.p, 0.0, scal_force.size());  // :132-134
-  rhoh_force(true, p0_old, rho0_old, grav_old, true);
+  if (pred_T) {  // :190-195: mktempforce (mkscalforce.f90:719) and its ghost fill (:833-837)
+    TempForceArgs ta;
+    ta.dm = dm; ta.nr = nr; ta.rho = rho; ta.temp = temp; ta.spec0 = P.spec_comp - 1;
+    ta.sphr = false;
+    ta.dr = P.dx[dm - 1];
+    for (int d = 0; d < 3; ++d) ta.dx[d] = P.dx[d];
+    ta.vb = grown(lo, hi, dm, 0);
+    ta.f = scal_force.comp(temp); ta.s = sold; ta.thermal = thermal;
+    for (int d = 0; d < dm; ++d) ta.umac[d] = umac[d];
+    ta.p0_old = p0_old; ta.psi = psi;
+    mktempforce_dev(ta);
+    fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.temp_comp, foextrap_comp, 1, adv_bc, pmask, false);
+  } else {
+    rhoh_force(true, p0_old, rho0_old, grav_old, true);
+  }
   if (ept == MGPU_PREDICT_RHOHPRIME) {  // :153-156
     modify_scal_force_dev(P, scal_force, sold, umac, rhoh0_old, rh0e_old, w0, P.rhoh_comp, false, lo, hi, g_opt_exact == 0);
     fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask, false);
@@ -1250,15 +1339,32 @@ static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold,
   addw0_dev(P, umac, w0, 1.0, lo, hi);  // :201
   fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(true);  // :204-208
+  if (ept == MGPU_PREDICT_TPRIME_THEN_H) pert_T(true);
   {
     const bool cons = (ept == MGPU_PREDICT_RHOH);  // :232-254
+    const int pc = pred_T ? temp : rhoh;           // :220-226
     size_t mark = arena_mark();
-    if (P.bds_type != 0) bds_dev(P, sold, sedge, umac, scal_force, lo, hi, rhoh, cons, ng_s, ng_f);
-    else edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, rhoh, dm + P.rhoh_comp, false, cons, ng_s, ng_f);
+    if (P.bds_type != 0) bds_dev(P, sold, sedge, umac, scal_force, lo, hi, pc, cons, ng_s, ng_f);
+    else edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, pc, dm + pc + 1, false, cons, ng_s, ng_f);
     arena_release(mark);
   }
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(false);  // :257-261
+  if (ept == MGPU_PREDICT_TPRIME_THEN_H) pert_T(false);
   if (ept == MGPU_PREDICT_H) rhoh_to_h(false);     // :272-276
+  if (pred_T) {                                    // :280-286: makeHfromRhoT_edge (rhoh_vs_t.f90:20)
+    HEdgeArgs ha;
+    ha.dm = dm; ha.ept = ept; ha.spt = P.species_pred_type;
+    ha.rho = rho; ha.rhoh = rhoh; ha.temp = temp; ha.spec0 = P.spec_comp - 1;
+    ha.sphr = false;
+    ha.vb = grown(lo, hi, dm, 0);
+    for (int d = 0; d < dm; ++d) ha.sedge[d] = sedge[d];
+    ha.rho0_old = rho0_old; ha.rhoh0_old = rhoh0_old; ha.t0_old = tempbar;
+    ha.rho0_edge_old = r0e_old; ha.rhoh0_edge_old = rh0e_old; ha.t0_edge_old = t0_edge;
+    ha.rho0_new = rho0_new; ha.rhoh0_new = rhoh0_new; ha.t0_new = tempbar;
+    ha.rho0_edge_new = r0e_new; ha.rhoh0_edge_new = rh0e_new; ha.t0_edge_new = t0_edge;
+    ha.rho0_cart = ha.rhoh0_cart = ha.t0_cart = sold;
+    h_from_rhot_edge_dev(ha);
+  }
   addw0_dev(P, umac, w0, -1.0, lo, hi);             // :293
   fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
   const bool s1 = (which_step == 1);
@@ -1280,8 +1386,31 @@ static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold,
   ua.vb = grown(lo, hi, dm, 0);
   ua.sold = sold; ua.snew = snew; ua.force = scal_force;
   for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d];
+  ua.p0_new = p0_new;
   update_scal_dev(P, ua, P.rhoh_comp, P.rhoh_comp);  // :431
   fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rhoh_comp, dm + P.rhoh_comp, 1, adv_bc, pmask, false);
+}
+
+// which components of the caller's fabs an enthalpy_advance episode reads / writes (host-pointer calls copy only these)
+struct EnthalpyMasks {
+  cmask_t mrhoh, sold_in, sold_out, snew_in, sedge_in, sedge_out, force_out;
+};
+static EnthalpyMasks enthalpy_masks(const mgpu_params& P) {
+  const int ept = P.enthalpy_pred_type;
+  const bool pred_T =
+      (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H);
+  const cmask_t mrho = crange(P.rho_comp - 1, 1), mrhoh = crange(P.rhoh_comp - 1, 1), mtemp = crange(P.temp_comp - 1, 1);
+  const cmask_t mspec = crange(P.spec_comp - 1, P.nspec);
+  const bool eos_reset = P.do_eos_h_above_cutoff != 0;  // reads rho, X of snew and the temperature of sold
+  EnthalpyMasks m;
+  m.mrhoh = mrhoh;
+  m.sold_in = mrho | mrhoh | ((pred_T || eos_reset) ? (mtemp | mspec) : 0);
+  m.sold_out = mrhoh | (pred_T ? mtemp : 0);
+  m.snew_in = mrhoh | (eos_reset ? (mrho | mspec) : 0);
+  m.sedge_in = mrho | (pred_T ? (mspec | mtemp) : 0);  // the x-face T' is read by the other faces (QUIRK) after it is written
+  m.sedge_out = mrhoh | (pred_T ? mtemp : 0);
+  m.force_out = pred_T ? mtemp : mrhoh;
+  return m;
 }
 
 }  // namespace mgpu
@@ -1667,9 +1796,12 @@ int mgpu_mk_rhoh_flux(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, c
 }
 
 int mgpu_update_scal(const mgpu_params* p, int nfabs, int nstart, int nstop, const mgpu_fab* sold, mgpu_fab* snew,
-                     const mgpu_fab* const* sflux, const mgpu_fab* force) {
+                     const mgpu_fab* const* sflux, const mgpu_fab* force, const double* p0_new,
+                     const mgpu_fab* p0_new_cart) {
   MGPU_TRY
-  Call c(p, 0);
+  Call c(p, (size_t)(p->nr + 8) * sizeof(double) + 4096);
+  const bool eos_reset = p->do_eos_h_above_cutoff && nstart == p->rhoh_comp && have_eos();
+  const double* p0_d = (eos_reset && !p->spherical && p0_new) ? upload_small(p0_new, (size_t)p->nr) : nullptr;
   for (int i = 0; i < nfabs; ++i) {
     UpdArgs a;
     a.dm = p->dm;
@@ -1680,6 +1812,11 @@ int mgpu_update_scal(const mgpu_params* p, int nfabs, int nstart, int nstop, con
     a.snew = c.view(snew[i], true, true);
     a.force = c.view(force[i], true, false);
     c.views(sflux, i, true, false, a.sflux);
+    a.p0_new = p0_d;
+    if (eos_reset && p->spherical && p0_new_cart) {
+      a.p0_new_cart = c.view(p0_new_cart[i], true, false);
+      a.have_p0_new_cart = true;
+    }
     update_scal_dev(*p, a, nstart, nstop);
   }
   c.finish();
@@ -2019,25 +2156,27 @@ int mgpu_velocity_advance(const mgpu_params* p, const mgpu_fab* uold, mgpu_fab* 
 int mgpu_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgpu_fab* snew, mgpu_fab* const* sedge,
                           mgpu_fab* const* sflux, mgpu_fab* scal_force, const mgpu_fab* thermal, mgpu_fab* const* umac,
                           const double* w0, const double* rho0_old, const double* rhoh0_old, const double* rho0_new,
-                          const double* rhoh0_new, const double* p0_old, const double* p0_new, const double* psi,
-                          const double* grav_old, const double* grav_nph, const int* adv_bc, const int* pmask) {
+                          const double* rhoh0_new, const double* p0_old, const double* p0_new, const double* tempbar,
+                          const double* psi, const double* grav_old, const double* grav_nph, const int* adv_bc,
+                          const int* pmask) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_enthalpy_advance: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_enthalpy_advance: use mgpu_enthalpy_advance_sphr with spherical == 1");
   Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
                 (size_t)(16 * (p->nr + 2)) * sizeof(double) + 16384);
   // the episode reads rho and rhoh of sold (rhoh is transformed in place and restored), writes rhoh of snew, of the
   // edge states and of the fluxes, and reads the density edge states density_advance left in sedge(rho_comp)
-  const cmask_t mrho = crange(p->rho_comp - 1, 1), mrhoh = crange(p->rhoh_comp - 1, 1);
-  DV so = c.view(*sold, mrho | mrhoh, mrhoh), sn = c.view(*snew, mrhoh, mrhoh);
-  DV fv = c.view(*scal_force, (cmask_t)0, mrhoh);  // zeroed on entry; only the rhoh component is non-zero on return
-  c.zero_on_host(*scal_force, ~mrhoh);
+  const EnthalpyMasks m = enthalpy_masks(*p);
+  DV so = c.view(*sold, m.sold_in, m.sold_out), sn = c.view(*snew, m.snew_in, m.mrhoh);
+  DV fv = c.view(*scal_force, (cmask_t)0, m.force_out);  // zeroed on entry; only the predicted component is non-zero on return
+  c.zero_on_host(*scal_force, ~m.force_out);
   DV th = c.view(*thermal, true, false);
   DV se[3], sf[3], um[3];
-  c.views((const mgpu_fab* const*)sedge, 0, mrho, mrhoh, se);
-  c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, mrhoh, sf);
+  c.views((const mgpu_fab* const*)sedge, 0, m.sedge_in, m.sedge_out, se);
+  c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, m.mrhoh, sf);
   c.views((const mgpu_fab* const*)umac, 0, true, true, um);
   enthalpy_advance_dev(*p, which_step, so, sn, se, sf, fv, th, um, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old,
-                       p0_new, psi, grav_old, grav_nph, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
+                       p0_new, tempbar, psi, grav_old, grav_nph, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc,
+                       pmask);
   c.finish();
   MGPU_CATCH
 }
@@ -2391,24 +2530,24 @@ int mgpu_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int whi
                                const mgpu_fab* thermal, mgpu_fab* const* umac, const double* w0,
                                const mgpu_fab* const* w0mac, const double* rho0_old, const double* rhoh0_old,
                                const double* rho0_new, const double* rhoh0_new, const double* p0_old, const double* p0_new,
-                               const double* psi, const int* adv_bc, const int* pmask) {
+                               const double* tempbar, const double* psi, const int* adv_bc, const int* pmask) {
   MGPU_TRY
   need_sphr(p, g);
   if (!p->spherical) throw Error("enthalpy_advance_sphr: params.spherical must be 1");
   Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
                 14 * fab_bytes(sold->lo, sold->hi, 3, 2, 1, 1) + geom_scratch(g) +
                 (size_t)(16 * (g->nr_fine + 4)) * sizeof(double) + 16384);
-  const cmask_t mrho = crange(p->rho_comp - 1, 1), mrhoh = crange(p->rhoh_comp - 1, 1);
-  DV so = c.view(*sold, mrho | mrhoh, mrhoh), sn = c.view(*snew, mrhoh, mrhoh);
-  DV fv = c.view(*scal_force, (cmask_t)0, mrhoh);
+  const EnthalpyMasks m = enthalpy_masks(*p);
+  DV so = c.view(*sold, m.sold_in, m.sold_out), sn = c.view(*snew, m.snew_in, m.mrhoh);
+  DV fv = c.view(*scal_force, (cmask_t)0, m.force_out);
   DV th = c.view(*thermal, true, false);
   DV se[3], sf[3], um[3], wm[3];
-  c.views((const mgpu_fab* const*)sedge, 0, mrho, mrhoh, se);
-  c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, mrhoh, sf);
+  c.views((const mgpu_fab* const*)sedge, 0, m.sedge_in, m.sedge_out, se);
+  c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, m.mrhoh, sf);
   c.views((const mgpu_fab* const*)umac, 0, true, true, um);
   c.views(w0mac, 0, true, false, wm);
   enthalpy_advance_sphr_dev(*p, *g, which_step, so, sn, se, sf, fv, th, um, w0, wm, rho0_old, rhoh0_old, rho0_new, rhoh0_new,
-                            p0_old, p0_new, psi, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
+                            p0_old, p0_new, tempbar, psi, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
   c.finish();
   MGPU_CATCH
 }
@@ -2552,6 +2691,312 @@ int mgpu_estdt_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, const m
   if (dt_lev == dt_start) dt_lev = std::min(p->dx[0], std::min(p->dx[1], p->dx[2]));
   *dt = std::min(*dt, dt_lev);
   c.finish();
+  MGPU_CATCH
+}
+
+// ---- the EOS and the pieces of the path that call it (mgpu_eos.cu) ---------------------------
+int mgpu_set_eos(const mgpu_eos* e) {
+  MGPU_TRY
+  set_eos(e);
+  MGPU_CATCH
+}
+
+int mgpu_eos_eval(int input, long n, double* state, const double* xn) {
+  MGPU_TRY
+  require_init();
+  const EosDev& E = the_eos("eos");
+  if (n < 0) throw Error("mgpu_eos_eval: n < 0");
+  arena_reserve((size_t)n * (MGPU_EOS_NQ + E.nspec) * sizeof(double) + (1u << 20));
+  arena_reset();
+  double* sd = arena_alloc((size_t)n * MGPU_EOS_NQ);
+  double* xd = arena_alloc((size_t)n * E.nspec);
+  MGPU_CUDA(cudaMemcpyAsync(sd, state, (size_t)n * MGPU_EOS_NQ * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
+  MGPU_CUDA(cudaMemcpyAsync(xd, xn, (size_t)n * E.nspec * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
+  eos_points_dev(input, n, sd, xd);
+  MGPU_CUDA(cudaMemcpyAsync(state, sd, (size_t)n * MGPU_EOS_NQ * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+  MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  MGPU_CATCH
+}
+
+static void h_edge_common(const mgpu_params* p, HEdgeArgs& a, const mgpu_fab& f0) {
+  a.dm = p->dm;
+  a.ept = p->enthalpy_pred_type;
+  a.spt = p->species_pred_type;
+  a.rho = p->rho_comp - 1; a.rhoh = p->rhoh_comp - 1; a.temp = p->temp_comp - 1; a.spec0 = p->spec_comp - 1;
+  a.vb = grown(f0.lo, f0.hi, p->dm, 0);
+  if (!(a.ept == MGPU_PREDICT_T_THEN_RHOHPRIME || a.ept == MGPU_PREDICT_T_THEN_H || a.ept == MGPU_PREDICT_TPRIME_THEN_H))
+    throw Error("makeHfromRhoT_edge: enthalpy_pred_type must be one of the temperature-based predictions");
+}
+static cmask_t h_edge_in(const mgpu_params* p) {
+  return crange(p->rho_comp - 1, 1) | crange(p->temp_comp - 1, 1) | crange(p->spec_comp - 1, p->nspec);
+}
+
+int mgpu_make_h_from_rhot_edge(const mgpu_params* p, int nfabs, mgpu_fab* const* sedge, const double* rho0_old,
+                               const double* rhoh0_old, const double* t0_old, const double* rho0_edge_old,
+                               const double* rhoh0_edge_old, const double* t0_edge_old, const double* rho0_new,
+                               const double* rhoh0_new, const double* t0_new, const double* rho0_edge_new,
+                               const double* rhoh0_edge_new, const double* t0_edge_new) {
+  MGPU_TRY
+  if (p->spherical) throw Error("make_h_from_rhot_edge: use the _sphr entry point with spherical == 1");
+  const int nr = p->nr;
+  Call c(p, (size_t)(12 * (nr + 4)) * sizeof(double) + 16384);
+  HEdgeArgs a{};
+  a.sphr = false;
+  a.rho0_old = upload_small(rho0_old, (size_t)nr); a.rhoh0_old = upload_small(rhoh0_old, (size_t)nr);
+  a.t0_old = upload_small(t0_old, (size_t)nr);
+  a.rho0_new = upload_small(rho0_new, (size_t)nr); a.rhoh0_new = upload_small(rhoh0_new, (size_t)nr);
+  a.t0_new = upload_small(t0_new, (size_t)nr);
+  a.rho0_edge_old = upload_small(rho0_edge_old, (size_t)nr + 1); a.rhoh0_edge_old = upload_small(rhoh0_edge_old, (size_t)nr + 1);
+  a.t0_edge_old = upload_small(t0_edge_old, (size_t)nr + 1);
+  a.rho0_edge_new = upload_small(rho0_edge_new, (size_t)nr + 1); a.rhoh0_edge_new = upload_small(rhoh0_edge_new, (size_t)nr + 1);
+  a.t0_edge_new = upload_small(t0_edge_new, (size_t)nr + 1);
+  for (int i = 0; i < nfabs; ++i) {
+    h_edge_common(p, a, sedge[0][i]);
+    c.views((const mgpu_fab* const*)sedge, i, h_edge_in(p), crange(p->rhoh_comp - 1, 1), a.sedge);
+    a.rho0_cart = a.rhoh0_cart = a.t0_cart = a.sedge[0];
+    h_from_rhot_edge_dev(a);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_make_h_from_rhot_edge_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* const* sedge,
+                                    const double* rho0_old, const double* rhoh0_old, const double* t0_old,
+                                    const double* rho0_new, const double* rhoh0_new, const double* t0_new,
+                                    const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  need_sphr(p, g);
+  if (!p->spherical) throw Error("make_h_from_rhot_edge_sphr: params.spherical must be 1");
+  const int nr = g->nr_fine, dm = 3;
+  size_t need = 0;
+  for (int i = 0; i < nfabs; ++i) need = std::max(need, 3 * fab_bytes(sedge[0][i].lo, sedge[0][i].hi, 3, 2, 0, 1));
+  Call c(p, need + geom_scratch(g) + (size_t)(4 * (nr + 4)) * sizeof(double) + 16384);
+  std::vector<double> r0h(nr), rh0h(nr), t0h(nr);
+  for (int r = 0; r < nr; ++r) {  // rhoh_vs_t.f90:91-95
+    r0h[r] = 0.5 * (rho0_old[r] + rho0_new[r]);
+    rh0h[r] = 0.5 * (rhoh0_old[r] + rhoh0_new[r]);
+    t0h[r] = 0.5 * (t0_old[r] + t0_new[r]);
+  }
+  const double* r0d = upload_small(r0h.data(), (size_t)nr);
+  const double* rh0d = upload_small(rh0h.data(), (size_t)nr);
+  const double* t0d = upload_small(t0h.data(), (size_t)nr);
+  for (int i = 0; i < nfabs; ++i) {
+    HEdgeArgs a{};
+    a.sphr = true;
+    h_edge_common(p, a, sedge[0][i]);
+    c.views((const mgpu_fab* const*)sedge, i, h_edge_in(p), crange(p->rhoh_comp - 1, 1), a.sedge);
+    SphrCtx X{*p, *g, make_geom(*p, *g), sedge[0][i].lo, sedge[0][i].hi, adv_bc, pmask};
+    const size_t mark = arena_mark();
+    a.rho0_cart = sphr_cart(X, r0d, 2, dm + p->rho_comp);
+    a.rhoh0_cart = sphr_cart(X, rh0d, 2, dm + p->rhoh_comp);
+    a.t0_cart = sphr_cart(X, t0d, 2, dm + p->temp_comp);
+    h_from_rhot_edge_dev(a);
+    arena_release(mark);
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_mktempforce(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* temp_force,
+                     const mgpu_fab* const* umac, const mgpu_fab* s, const mgpu_fab* thermal, const double* p0_old,
+                     const double* psi, const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  if (p->spherical) need_sphr(p, g);
+  const int ept = p->enthalpy_pred_type;
+  if (!(ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H))
+    throw Error("ERROR: should only call mkrhohforce when predicting T or T'");  // mkscalforce.f90:756 (the reference's wording)
+  const int dm = p->dm, foextrap_comp = dm + p->nscal + 2;
+  const int nr = p->spherical ? g->nr_fine : p->nr;
+  size_t need = 0;
+  if (p->spherical)
+    for (int i = 0; i < nfabs; ++i) need = std::max(need, 2 * fab_bytes(s[i].lo, s[i].hi, 3, 1, 0, 1));
+  Call c(p, need + (p->spherical ? geom_scratch(g) : 0) + (size_t)(4 * (nr + 4)) * sizeof(double) + 16384);
+  const double* p0d = upload_small(p0_old, (size_t)nr);
+  const double* psid = upload_small(psi, (size_t)nr);
+  const cmask_t mtemp = crange(p->temp_comp - 1, 1);
+  const cmask_t sin = crange(p->rho_comp - 1, 1) | mtemp | crange(p->spec_comp - 1, p->nspec);
+  for (int i = 0; i < nfabs; ++i) {
+    const int* lo = s[i].lo;
+    const int* hi = s[i].hi;
+    DV fv = c.view(temp_force[i], mtemp, mtemp), sv = c.view(s[i], sin, (cmask_t)0), th = c.view(thermal[i], true, false);
+    TempForceArgs a;
+    a.dm = dm; a.nr = nr; a.rho = p->rho_comp - 1; a.temp = p->temp_comp - 1; a.spec0 = p->spec_comp - 1;
+    a.sphr = p->spherical != 0;
+    a.dr = p->spherical ? g->dr : p->dx[dm - 1];
+    for (int d = 0; d < 3; ++d) a.dx[d] = p->dx[d];
+    a.vb = grown(lo, hi, dm, 0);
+    a.f = fv.comp(a.temp); a.s = sv; a.thermal = th;
+    c.views(umac, i, true, false, a.umac);
+    a.p0_old = p0d; a.psi = psid;
+    a.p0_cart = a.psi_cart = sv;
+    const size_t mark = arena_mark();
+    if (p->spherical) {  // mkscalforce.f90:770-776, :1059-1061
+      SphrCtx X{*p, *g, make_geom(*p, *g), lo, hi, adv_bc, pmask};
+      a.p0_cart = sphr_cart(X, p0d, 1, foextrap_comp);
+      a.psi_cart = arena_fab(lo, hi, 3, 0, nullptr, 1);
+      put_1d_array_on_cart_dev(*p, *g, X.gd, psid, a.psi_cart, false, false, lo, hi);
+    }
+    mktempforce_dev(a);
+    arena_release(mark);
+    fill_boundary_dev(*p, fv, lo, hi, temp_force[i].ng, nullptr, p->temp_comp, foextrap_comp, 1, adv_bc, pmask, false);  // :833-837
+  }
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_firstdt(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* u, const mgpu_fab* gpi,
+                 const mgpu_fab* s, const mgpu_fab* divU, const double* rho0, const double* p0, const double* grav,
+                 const double* gamma1bar, double cflfac, double init_shrink, int use_soundspeed_firstdt,
+                 int use_divu_firstdt, double* dt, double* umax) {
+  MGPU_TRY
+  if (p->spherical) need_sphr(p, g);
+  the_eos("firstdt");
+  const int dm = p->dm;
+  const bool sphr = p->spherical != 0;
+  const int nr = sphr ? g->nr_fine : p->nr;
+  size_t need = 0;
+  for (int i = 0; i < nfabs; ++i)
+    need = std::max(need, (size_t)(2 * dm + 2 * dm + 3) * fab_bytes(u[i].lo, u[i].hi, dm, 1, 1, 1) +
+                              (sphr ? 8 * fab_bytes(u[i].lo, u[i].hi, 3, 1, 0, 3) : 0));
+  Call c(p, need + (sphr ? geom_scratch(g) : 0) + (size_t)(8 * (nr + 4) + 148 * 8 * 8 + 64) * sizeof(double) + 16384);
+  std::vector<double> zeros((size_t)nr + 1, 0.0);
+  const double* w0_dummy = upload_small(zeros.data(), (size_t)nr + 1);        // firstdt.f90:74-77
+  const double* w0_force_dummy = upload_small(zeros.data(), (size_t)nr);
+  const double* rho0_d = upload_small(rho0, (size_t)nr);
+  const double* grav_d = upload_small(grav, (size_t)nr);
+  const double* p0_d = upload_small(p0, (size_t)nr);
+  const double* g1_d = upload_small(gamma1bar, (size_t)nr);
+  const double* gp0_d = nullptr;
+  if (sphr) {  // gp0 on the radial edges (:708-719)
+    std::vector<double> gp0(nr + 1);
+    for (int r = 1; r <= nr - 1; ++r) {
+      const double gamma1bar_p_avg = 0.5 * (gamma1bar[r] * p0[r] + gamma1bar[r - 1] * p0[r - 1]);
+      gp0[r] = ((p0[r] - p0[r - 1]) / g->dr) / gamma1bar_p_avg;
+    }
+    gp0[nr] = gp0[nr - 1];
+    gp0[0] = gp0[1];
+    gp0_d = upload_small(gp0.data(), (size_t)nr + 1);
+  }
+  // the force of firstdt.f90:96-100 needs no boundary data: adv_bc / pmask of an all-interior box keep the ghost fill
+  // of mk_vel_force away from anything the reductions read (they run over the valid cells only)
+  double dt_proc = 1.e99, umax_proc = 0.0;  // :134-137
+  const cmask_t sin = crange(p->rho_comp - 1, 1) | crange(p->temp_comp - 1, 1) | crange(p->spec_comp - 1, p->nspec);
+  for (int i = 0; i < nfabs; ++i) {
+    const int* lo = u[i].lo;
+    const int* hi = u[i].hi;
+    DV uv = c.view(u[i], true, false), gp = c.view(gpi[i], true, false), sv = c.view(s[i], sin, (cmask_t)0);
+    DV dUv = c.view(divU[i], true, false);
+    const size_t mark = arena_mark();
+    DV force = arena_fab(lo, hi, dm, 1, nullptr, dm);
+    DV umd[3];
+    for (int d = 0; d < dm; ++d) {  // umac_dummy: zero, one ghost layer (:84-88)
+      umd[d] = arena_fab(lo, hi, dm, 1, NODAL_D[d], 1);
+      set_dev(umd[d].p, 0.0, umd[d].size());
+    }
+    double dt_grid, umax_grid;
+    if (sphr) {
+      Geom gd = make_geom(*p, *g);
+      DV w0md[3];
+      for (int d = 0; d < 3; ++d) {
+        w0md[d] = arena_fab(lo, hi, 3, 1, NODAL_D[d], 1);
+        set_dev(w0md[d].p, 0.0, w0md[d].size());
+      }
+      DV normal_dummy = arena_fab(lo, hi, 3, 1, nullptr, 3), w0fc = arena_fab(lo, hi, 3, 1, nullptr, 3);
+      set_dev(normal_dummy.p, 0.0, normal_dummy.size());
+      set_dev(w0fc.p, 0.0, w0fc.size());
+      mk_vel_force_sphr_dev(*p, *g, gd, force, false, uv, umd, zeros.data(), w0md, gp, sv.comp(p->rho_comp - 1),
+                            normal_dummy, rho0, grav, w0fc, lo, hi, false);
+      DV gc = arena_fab(lo, hi, 3, 0, nullptr, 3);
+      put_1d_array_on_cart_dev(*p, *g, gd, gp0_d, gc, true, true, lo, hi);  // :721
+      firstdt_box_dev(*p, uv, sv, force, dUv, p0_d, g1_d, &gc, lo, hi, cflfac, use_soundspeed_firstdt != 0,
+                      use_divu_firstdt != 0, &dt_grid, &umax_grid);
+    } else {
+      VelForceArgs a;
+      a.dm = dm;
+      a.nr = nr;
+      a.is_final_update = false;
+      a.add_utilde = false;
+      a.dr = p->dx[dm - 1];
+      a.rho_cut = p->buoyancy_cutoff_factor * p->base_cutoff_density;
+      a.omega = p->omega; a.sin_theta = p->sin_theta; a.cos_theta = p->cos_theta; a.rotation_radius = p->rotation_radius;
+      a.vb = grown(lo, hi, dm, 0);
+      a.force = force; a.uold = uv; a.gpi = gp; a.rho = sv.comp(p->rho_comp - 1);
+      for (int d = 0; d < dm; ++d) a.uedge[d] = umd[d];
+      a.w0 = w0_dummy; a.rho0 = rho0_d; a.grav = grav_d; a.w0_force = w0_force_dummy;
+      mk_vel_force_dev(a);
+      firstdt_box_dev(*p, uv, sv, force, dUv, p0_d, g1_d, nullptr, lo, hi, cflfac, use_soundspeed_firstdt != 0,
+                      use_divu_firstdt != 0, &dt_grid, &umax_grid);
+    }
+    arena_release(mark);
+    dt_proc = std::min(dt_proc, dt_grid);
+    umax_proc = std::max(umax_proc, umax_grid);
+  }
+  double dt_lev = dt_proc, umax_lev = umax_proc;
+  if (comm_size() > 1) {  // parallel_reduce MPI_MIN / MPI_MAX, :169-170: one MIN over (dt, -umax)
+    double h[2] = {dt_proc, -umax_proc};
+    double* d = arena_alloc(2);
+    MGPU_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, g_ctx.stream));
+    allreduce_dev(d, 2, 1);
+    MGPU_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, g_ctx.stream));
+    MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    dt_lev = h[0];
+    umax_lev = -h[1];
+  }
+  *umax = std::max(*umax, umax_lev);  // :173
+  dt_lev = dt_lev * init_shrink;      // :180
+  *dt = std::min(*dt, dt_lev);        // :187
+  c.finish();
+  MGPU_CATCH
+}
+
+static void make_t_api(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* state, const double* p0, bool from_p,
+                       bool flag, bool update_rhoh, const int* adv_bc, const int* pmask) {
+  if (p->spherical) need_sphr(p, g);
+  the_eos(from_p ? "makeTfromRhoP" : "makeTfromRhoH");
+  const int dm = p->dm;
+  const bool sphr = p->spherical != 0;
+  const int nr = sphr ? g->nr_fine : p->nr;
+  size_t need = 0;
+  if (sphr)
+    for (int i = 0; i < nfabs; ++i) need = std::max(need, fab_bytes(state[i].lo, state[i].hi, 3, 0, 0, 1));
+  Call c(p, need + (sphr ? geom_scratch(g) : 0) + (size_t)(2 * (nr + 4)) * sizeof(double) + 16384);
+  const double* p0d = upload_small(p0, (size_t)nr);
+  const cmask_t mtemp = crange(p->temp_comp - 1, 1), mrhoh = crange(p->rhoh_comp - 1, 1);
+  cmask_t in = crange(p->rho_comp - 1, 1) | mtemp | crange(p->spec_comp - 1, p->nspec);
+  if (!from_p) in |= mrhoh;
+  if (from_p && flag) in |= crange(p->pi_comp - 1, 1);
+  const cmask_t out = mtemp | ((from_p && update_rhoh) ? mrhoh : 0);
+  for (int i = 0; i < nfabs; ++i) {
+    const int* lo = state[i].lo;
+    const int* hi = state[i].hi;
+    DV sv = c.view(state[i], in | out, out);
+    const size_t mark = arena_mark();
+    DV p0c;
+    if (sphr) {  // rhoh_vs_t.f90:1097, :1410
+      Geom gd = make_geom(*p, *g);
+      p0c = arena_fab(lo, hi, 3, 0, nullptr, 1);
+      put_1d_array_on_cart_dev(*p, *g, gd, p0d, p0c, false, false, lo, hi);
+    }
+    make_t_dev(*p, sv, p0d, sphr ? &p0c : nullptr, from_p, flag, update_rhoh, grown(lo, hi, dm, 0));
+    arena_release(mark);
+    fill_boundary_dev(*p, sv, lo, hi, state[i].ng, nullptr, p->temp_comp, dm + p->temp_comp, 1, adv_bc, pmask, false);
+    if (from_p && update_rhoh)
+      fill_boundary_dev(*p, sv, lo, hi, state[i].ng, nullptr, p->rhoh_comp, dm + p->rhoh_comp, 1, adv_bc, pmask, false);
+  }
+  c.finish();
+}
+
+int mgpu_make_t_from_rhoh(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* state, const double* p0,
+                          int use_eos_e_instead_of_h, const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  make_t_api(p, g, nfabs, state, p0, false, use_eos_e_instead_of_h != 0, false, adv_bc, pmask);
+  MGPU_CATCH
+}
+
+int mgpu_make_t_from_rhop(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgpu_fab* state, const double* p0,
+                          int update_rhoh, int use_pprime_in_tfromp, const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  make_t_api(p, g, nfabs, state, p0, true, use_pprime_in_tfromp != 0, update_rhoh != 0, adv_bc, pmask);
   MGPU_CATCH
 }
 

@@ -11,6 +11,7 @@
 #include "mgpu_halo.cuh"
 #include <algorithm>
 
+#include "mgpu_eos.cuh"
 #include "mgpu_stream.cuh"
 
 namespace mgpu {
@@ -174,10 +175,11 @@ __global__ void k_count_below(DV s, Box3 vb, int rho, double cutoff, unsigned lo
 
 void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop) {
   Context& cx = ctx();
-  if (P.do_eos_h_above_cutoff && nstart == P.rhoh_comp) {
+  const bool eos_reset = P.do_eos_h_above_cutoff && nstart == P.rhoh_comp;
+  if (eos_reset && !have_eos()) {
     // The reference recomputes rhoh from the EOS at (rho, p0, X) wherever rho <= base_cutoff_density
-    // (update_scal.f90:421-447, default do_eos_h_above_cutoff = T).  The EOS is not on the device: if any
-    // zone of this box would take that branch the call fails instead of returning a different rhoh.
+    // (update_scal.f90:421-447, default do_eos_h_above_cutoff = T).  Without an EOS (mgpu_set_eos): if any zone of this
+    // box would take that branch the call fails instead of returning a different rhoh.
     unsigned long long* cnt = reinterpret_cast<unsigned long long*>(arena_alloc(1));
     MGPU_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), cx.stream));
     k_count_below<<<grid3(a.vb, 256), block3(a.vb, 256), 0, cx.stream>>>(a.snew, a.vb, P.rho_comp - 1, P.base_cutoff_density, cnt);
@@ -187,14 +189,16 @@ void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop) {
     MGPU_CUDA(cudaStreamSynchronize(cx.stream));
     if (h > 0)
       throw Error("update_scal: " + std::to_string(h) + " zone(s) have rho <= base_cutoff_density: the EOS reset of rhoh "
-                  "(update_scal.f90:421-447) is not available on the device -- set do_eos_h_above_cutoff = F and apply "
-                  "it on the host (INTEGRATION.md), or keep the density above the cutoff");
+                  "(update_scal.f90:421-447) needs an EOS -- call mgpu_set_eos (gamma_law_general), or set "
+                  "do_eos_h_above_cutoff = F and apply the reset on the host (INTEGRATION.md)");
   }
   const long nv = a.vb.npts();
   for (int comp = nstart; comp <= nstop; ++comp) {
     k_update_scal<<<grid3(a.vb, 256), block3(a.vb, 256), 0, cx.stream>>>(a, comp - 1);
     MGPU_LAUNCH_CHECK();
   }
+  if (eos_reset && have_eos())
+    update_scal_eos_dev(P, a.sold, a.snew, a.p0_new, a.have_p0_new_cart ? &a.p0_new_cart : nullptr, a.vb);
   if (nstart == P.spec_comp && nstop == P.spec_comp + P.nspec - 1) {
     const int rho = P.rho_comp - 1;
     if (a.snew.cs != a.sold.cs) throw Error("update_scal: sold and snew must have the same ghost width");

@@ -22,6 +22,11 @@ struct UpdArgs {
   double dt, dx[3];
   Box3 vb;
   DV sold, snew, force, sflux[3];
+  // the EOS reset below the cutoff (update_scal.f90:421-447): p0_new on the radial cells (planar, device pointer) or on
+  // the cell centres (spherical); nullptr / false when the caller did not pass them
+  const double* p0_new = nullptr;
+  DV p0_new_cart;
+  bool have_p0_new_cart = false;
 };
 void update_scal_dev(const mgpu_params& P, UpdArgs& a, int nstart, int nstop);
 // mk_rhoX_flux (species + tracers) + update_scal (species + tracers + density) of density_advance in one launch

@@ -78,9 +78,12 @@ class Operators:
         self._call("mk_rhoh_flux", C.byref(p), 1, sf, se, um, *[k[1] for k in keep])
 
     # ---- updates -------------------------------------------------------------------------------
-    def update_scal(self, p, nstart, nstop, sold, snew, sflux, scal_force):
+    def update_scal(self, p, nstart, nstop, sold, snew, sflux, scal_force, p0_new=None, p0_new_cart=None):
+        """Source/update_scal.f90:16; p0_new (planar) / p0_new_cart (spherical) feed the EOS reset below the cutoff."""
         sf, k1 = fab_pp(sflux)
-        self._call("update_scal", C.byref(p), 1, nstart, nstop, fab_ptr(sold), fab_ptr(snew), sf, fab_ptr(scal_force))
+        pk, pp = as_double_p(p0_new) if p0_new is not None else (None, None)
+        self._call("update_scal", C.byref(p), 1, nstart, nstop, fab_ptr(sold), fab_ptr(snew), sf, fab_ptr(scal_force),
+                   pp, fab_ptr(p0_new_cart) if p0_new_cart is not None else None)
 
     def update_velocity(self, p, uold, unew, umac, uedge, force, sponge, w0):
         w, wp = as_double_p(w0)
@@ -203,8 +206,10 @@ class Operators:
                    fab_ptr(thermal), um, keep[0][1], keep[1][1], keep[2][1], int(add_thermal), bcp, pmp)
 
     def enthalpy_advance_sphr(self, p, geom, which_step, sold, snew, sedge, sflux, scal_force, thermal, umac, w0, w0mac,
-                              rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, adv_bc, pmask):
-        keep = [as_double_p(x) for x in (w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi)]
+                              rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, adv_bc, pmask, tempbar=None):
+        if tempbar is None:
+            tempbar = np.zeros(geom.c.nr_fine)
+        keep = [as_double_p(x) for x in (w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, tempbar, psi)]
         bc, bcp = as_int_p(adv_bc)
         pm, pmp = as_int_p(pmask)
         se, k1 = fab_pp(sedge)
@@ -322,12 +327,85 @@ class Operators:
                    fab_ptr(gpi), *[k[1] for k in keep], fab_ptr(sponge), *[k[1] for k in ints])
 
     def enthalpy_advance(self, p, which_step, sold, snew, sedge, sflux, scal_force, thermal, umac, w0, rho0_old,
-                         rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old, grav_nph, adv_bc, pmask):
-        keep = [as_double_p(x) for x in (w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old,
-                                         grav_nph)]
+                         rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old, grav_nph, adv_bc, pmask,
+                         tempbar=None):
+        """Source/enthalpy_advance.f90:16; tempbar (the reference passes it after p0_new) is only read by the
+        temperature-based predictions."""
+        if tempbar is None:
+            tempbar = np.zeros(p.nr)
+        keep = [as_double_p(x) for x in (w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, tempbar, psi,
+                                         grav_old, grav_nph)]
         ints = [as_int_p(x) for x in (adv_bc, pmask)]
         se, k1 = fab_pp(sedge)
         sf, k2 = fab_pp(sflux)
         um, k3 = fab_pp(umac)
         self._call("enthalpy_advance", C.byref(p), which_step, fab_ptr(sold), fab_ptr(snew), se, sf,
                    fab_ptr(scal_force), fab_ptr(thermal), um, *[k[1] for k in keep], *[k[1] for k in ints])
+
+    # ---- the EOS and the pieces of the path that call it (SURVEY 8 f4 / f1 / f3) ----------------------------------
+    def set_eos(self, eos):
+        """eos_init (Microphysics/EOS/eos.F90:26): process state; None unsets it."""
+        self._call("set_eos", C.byref(eos) if eos is not None else None)
+
+    def eos_eval(self, eos_input, state, xn):
+        """eos(input, state) (eos.F90:99) at n points: `state` a dict of 1-D arrays (rho, T, p, e, h: the ones the input
+        mode names are read), `xn` (n, nspec); returns a dict with every column of abi.EOS_Q."""
+        from .abi import EOS_Q
+        xn = np.ascontiguousarray(np.asarray(xn, dtype=np.float64))
+        n = xn.shape[0]
+        buf = np.zeros((len(EOS_Q), n))
+        for q, name in enumerate(EOS_Q):
+            if name in state:
+                buf[q] = state[name]
+        xt = np.ascontiguousarray(xn.T)  # point-fastest
+        self._call("eos_eval", int(eos_input), n, buf.ctypes.data_as(C.POINTER(C.c_double)),
+                   xt.ctypes.data_as(C.POINTER(C.c_double)))
+        return {name: buf[q].copy() for q, name in enumerate(EOS_Q)}
+
+    def make_h_from_rhot_edge(self, p, sedge, rho0_old, rhoh0_old, t0_old, rho0_edge_old, rhoh0_edge_old, t0_edge_old,
+                              rho0_new, rhoh0_new, t0_new, rho0_edge_new, rhoh0_edge_new, t0_edge_new):
+        """makeHfromRhoT_edge (Source/rhoh_vs_t.f90:20), planar."""
+        keep = [as_double_p(x) for x in (rho0_old, rhoh0_old, t0_old, rho0_edge_old, rhoh0_edge_old, t0_edge_old, rho0_new,
+                                         rhoh0_new, t0_new, rho0_edge_new, rhoh0_edge_new, t0_edge_new)]
+        se, k1 = fab_pp(sedge)
+        self._call("make_h_from_rhot_edge", C.byref(p), 1, se, *[k[1] for k in keep])
+
+    def make_h_from_rhot_edge_sphr(self, p, geom, sedge, rho0_old, rhoh0_old, t0_old, rho0_new, rhoh0_new, t0_new, adv_bc,
+                                   pmask):
+        keep = [as_double_p(x) for x in (rho0_old, rhoh0_old, t0_old, rho0_new, rhoh0_new, t0_new)]
+        ints = [as_int_p(x) for x in (adv_bc, pmask)]
+        se, k1 = fab_pp(sedge)
+        self._call("make_h_from_rhot_edge_sphr", C.byref(p), C.byref(geom.c), 1, se, *[k[1] for k in keep],
+                   *[k[1] for k in ints])
+
+    def mktempforce(self, p, temp_force, umac, s, thermal, p0_old, psi, adv_bc, pmask, geom=None):
+        """mktempforce (Source/mkscalforce.f90:719)."""
+        keep = [as_double_p(x) for x in (p0_old, psi)]
+        ints = [as_int_p(x) for x in (adv_bc, pmask)]
+        um, k1 = fab_pp(umac)
+        self._call("mktempforce", C.byref(p), C.byref(geom.c) if geom is not None else None, 1, fab_ptr(temp_force), um,
+                   fab_ptr(s), fab_ptr(thermal), keep[0][1], keep[1][1], ints[0][1], ints[1][1])
+
+    def firstdt(self, p, u, gpi, s, divU, rho0, p0, grav, gamma1bar, cflfac, init_shrink, dt, umax=0.0,
+                use_soundspeed_firstdt=False, use_divu_firstdt=False, geom=None):
+        """firstdt (Source/firstdt.f90:25) for one level: returns (min(dt, dt_lev*init_shrink), max(umax, umax_lev))."""
+        keep = [as_double_p(x) for x in (rho0, p0, grav, gamma1bar)]
+        dt_c, um_c = C.c_double(dt), C.c_double(umax)
+        self._call("firstdt", C.byref(p), C.byref(geom.c) if geom is not None else None, 1, fab_ptr(u), fab_ptr(gpi),
+                   fab_ptr(s), fab_ptr(divU), *[k[1] for k in keep], float(cflfac), float(init_shrink),
+                   int(use_soundspeed_firstdt), int(use_divu_firstdt), C.byref(dt_c), C.byref(um_c))
+        return dt_c.value, um_c.value
+
+    def make_t_from_rhoh(self, p, state, p0, adv_bc, pmask, use_eos_e_instead_of_h=False, geom=None):
+        """makeTfromRhoH (Source/rhoh_vs_t.f90:800)."""
+        pk, pp = as_double_p(p0)
+        ints = [as_int_p(x) for x in (adv_bc, pmask)]
+        self._call("make_t_from_rhoh", C.byref(p), C.byref(geom.c) if geom is not None else None, 1, fab_ptr(state), pp,
+                   int(use_eos_e_instead_of_h), ints[0][1], ints[1][1])
+
+    def make_t_from_rhop(self, p, state, p0, adv_bc, pmask, update_rhoh=False, use_pprime_in_tfromp=False, geom=None):
+        """makeTfromRhoP (Source/rhoh_vs_t.f90:1165)."""
+        pk, pp = as_double_p(p0)
+        ints = [as_int_p(x) for x in (adv_bc, pmask)]
+        self._call("make_t_from_rhop", C.byref(p), C.byref(geom.c) if geom is not None else None, 1, fab_ptr(state), pp,
+                   int(update_rhoh), int(use_pprime_in_tfromp), ints[0][1], ints[1][1])

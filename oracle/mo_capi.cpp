@@ -125,13 +125,16 @@ int mo_mk_rhoh_flux(const mgpu_params* p, int nfabs, mgpu_fab* const* sflux, con
 }
 
 int mo_update_scal(const mgpu_params* p, int nfabs, int nstart, int nstop, const mgpu_fab* sold, mgpu_fab* snew,
-                   const mgpu_fab* const* sflux, const mgpu_fab* force) {
+                   const mgpu_fab* const* sflux, const mgpu_fab* force, const double* p0_new,
+                   const mgpu_fab* p0_new_cart) {
   MO_TRY
   for (int i = 0; i < nfabs; ++i) {
     Arr so = Arr::view(sold[i], p->dm), sn = Arr::view(snew[i], p->dm), fa = Arr::view(force[i], p->dm);
     Arr sf[3];
     views(p, sflux, i, sf);
-    update_scal_box(*p, nstart, nstop, so, sn, sf, fa, sold[i].lo, sold[i].hi);
+    Arr pc;
+    if (p0_new_cart) pc = Arr::view(p0_new_cart[i], p->dm);
+    update_scal_box(*p, nstart, nstop, so, sn, sf, fa, sold[i].lo, sold[i].hi, p0_new, p0_new_cart ? &pc : nullptr);
   }
   MO_CATCH
 }
@@ -310,8 +313,9 @@ int mo_velocity_advance(const mgpu_params* p, const mgpu_fab* uold, mgpu_fab* un
 int mo_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgpu_fab* snew, mgpu_fab* const* sedge,
                         mgpu_fab* const* sflux, mgpu_fab* scal_force, const mgpu_fab* thermal, mgpu_fab* const* umac,
                         const double* w0, const double* rho0_old, const double* rhoh0_old, const double* rho0_new,
-                        const double* rhoh0_new, const double* p0_old, const double* p0_new, const double* psi,
-                        const double* grav_old, const double* grav_nph, const int* adv_bc, const int* pmask) {
+                        const double* rhoh0_new, const double* p0_old, const double* p0_new, const double* tempbar,
+                        const double* psi, const double* grav_old, const double* grav_nph, const int* adv_bc,
+                        const int* pmask) {
   MO_TRY
   Arr so = Arr::view(*sold, p->dm), sn = Arr::view(*snew, p->dm), fa = Arr::view(*scal_force, p->dm);
   Arr th = Arr::view(*thermal, p->dm);
@@ -320,8 +324,8 @@ int mo_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mg
   views(p, (const mgpu_fab* const*)sflux, 0, sf);
   views(p, (const mgpu_fab* const*)umac, 0, um);
   enthalpy_advance_box(*p, which_step, so, sn, se, sf, fa, th, um, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new,
-                       p0_old, p0_new, psi, grav_old, grav_nph, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc,
-                       pmask);
+                       p0_old, p0_new, tempbar, psi, grav_old, grav_nph, sold->lo, sold->hi, sold->ng, scal_force->ng,
+                       adv_bc, pmask);
   MO_CATCH
 }
 

@@ -168,17 +168,20 @@ void velocity_advance_box(const mgpu_params& P, const Arr& uold, Arr& unew, cons
 void enthalpy_advance_box(const mgpu_params& P, int which_step, Arr& sold, Arr& snew, Arr* sedge, Arr* sflux,
                           Arr& scal_force, const Arr& thermal, Arr* umac, const double* w0, const double* rho0_old,
                           const double* rhoh0_old, const double* rho0_new, const double* rhoh0_new,
-                          const double* p0_old, const double* p0_new, const double* psi, const double* grav_old,
-                          const double* grav_nph, const int* lo, const int* hi, int ng_s, int ng_f, const int* adv_bc,
-                          const int* pmask) {
+                          const double* p0_old, const double* p0_new, const double* tempbar, const double* psi,
+                          const double* grav_old, const double* grav_nph, const int* lo, const int* hi, int ng_s, int ng_f,
+                          const int* adv_bc, const int* pmask) {
   const int dm = P.dm, nr = P.nr, r = dm - 1;
   const int ept = P.enthalpy_pred_type;
   const int foextrap_comp = dm + P.nscal + 2;
   const int rhoh = P.rhoh_comp - 1, rho = P.rho_comp - 1;
   if (ept == MGPU_PREDICT_HPRIME) fail("mk_rhoh_flux : predict_hprime not coded yet");
-  if (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H)
-    fail("oracle: temperature-based enthalpy prediction needs the EOS (makeHfromRhoT_edge): not restated");
-  std::vector<double> r0e_old(nr + 1), r0e_new(nr + 1), rh0e_old(nr + 1), rh0e_new(nr + 1);
+  const bool pred_T =
+      (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H);
+  const int temp = P.temp_comp - 1;
+  if (pred_T && !tempbar) fail("enthalpy_advance: the temperature-based predictions need tempbar");
+  std::vector<double> r0e_old(nr + 1), r0e_new(nr + 1), rh0e_old(nr + 1), rh0e_new(nr + 1), t0e(nr + 1);
+  if (pred_T) cell_to_edge(tempbar, t0e.data(), nr);  // :118-119 (old and new are both tempbar)
   cell_to_edge(rho0_old, r0e_old.data(), nr);  // enthalpy_advance.f90:114-117
   cell_to_edge(rho0_new, r0e_new.data(), nr);
   cell_to_edge(rhoh0_old, rh0e_old.data(), nr);
@@ -194,8 +197,13 @@ void enthalpy_advance_box(const mgpu_params& P, int which_step, Arr& sold, Arr& 
   if (ept == MGPU_PREDICT_H) rhoh_to_h(true);  // :122-126
 
   scal_force.fill(0.0);  // :132-134
-  mkrhohforce_box(P, scal_force, true, thermal, umac, p0_old, p0_old, rho0_old, rho0_old, grav_old, psi, true, lo, hi);
-  fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
+  if (pred_T) {  // :190-195
+    mktempforce_box(P, scal_force, sold, umac, thermal, p0_old, psi, lo, hi);
+    fill_boundary_box(P, scal_force, lo, hi, ng_f, P.temp_comp, foextrap_comp, 1, adv_bc, pmask);
+  } else {
+    mkrhohforce_box(P, scal_force, true, thermal, umac, p0_old, p0_old, rho0_old, rho0_old, grav_old, psi, true, lo, hi);
+    fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
+  }
   if (ept == MGPU_PREDICT_RHOHPRIME) {  // :153-156
     modify_scal_force_box(P, scal_force, sold, umac, rhoh0_old, rh0e_old.data(), w0, P.rhoh_comp, false, lo, hi);
     fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
@@ -211,12 +219,24 @@ void enthalpy_advance_box(const mgpu_params& P, int which_step, Arr& sold, Arr& 
     });
     fill_boundary_box(P, sold, lo, hi, ng_s, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc, pmask);
   };
+  auto pert_T = [&](bool flag) {  // put_in_pert_form on the temperature with tempbar (:214-217, :268-272)
+    for_box(vb, [&](int i, int j, int k) {
+      sold(i, j, k, temp) = sold(i, j, k, temp) + (flag ? -1.0 : 1.0) * tempbar[r == 1 ? j : k];
+    });
+    fill_boundary_box(P, sold, lo, hi, ng_s, P.temp_comp, flag ? foextrap_comp : dm + P.temp_comp, 1, adv_bc, pmask);
+  };
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(true);  // :204-208
+  if (ept == MGPU_PREDICT_TPRIME_THEN_H) pert_T(true);
   const bool cons = (ept == MGPU_PREDICT_RHOH);     // :232-254
-  if (P.bds_type == 0) make_edge_scal_box(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, rhoh, dm + P.rhoh_comp, false, cons, ng_s);
-  else bds_box(P, sold, sedge, umac, scal_force, lo, hi, rhoh, cons);
+  const int pc = pred_T ? temp : rhoh;              // :220-226
+  if (P.bds_type == 0) make_edge_scal_box(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, pc, dm + pc + 1, false, cons, ng_s);
+  else bds_box(P, sold, sedge, umac, scal_force, lo, hi, pc, cons);
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(false);  // :257-261
+  if (ept == MGPU_PREDICT_TPRIME_THEN_H) pert_T(false);
   if (ept == MGPU_PREDICT_H) rhoh_to_h(false);     // :272-276
+  if (pred_T)                                      // :280-286
+    h_from_rhot_edge_box(P, sedge, rho0_old, rhoh0_old, tempbar, r0e_old.data(), rh0e_old.data(), t0e.data(), rho0_new,
+                         rhoh0_new, tempbar, r0e_new.data(), rh0e_new.data(), t0e.data(), lo, hi);
   addw0_box(P, umac, w0, -1.0, lo, hi);             // :293
   fill_faces(P, umac, lo, hi, pmask);
   const bool s1 = (which_step == 1);  // :326 / :375
@@ -227,7 +247,7 @@ void enthalpy_advance_box(const mgpu_params& P, int which_step, Arr& sold, Arr& 
   mkrhohforce_box(P, scal_force, false, thermal, umac, p0_old, s1 ? p0_old : p0_new, rho0_old, s1 ? rho0_old : rho0_new,
                   s1 ? grav_old : grav_nph, psi, false, lo, hi);  // :405-416
   fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
-  update_scal_box(P, P.rhoh_comp, P.rhoh_comp, sold, snew, sflux, scal_force, lo, hi);  // :431
+  update_scal_box(P, P.rhoh_comp, P.rhoh_comp, sold, snew, sflux, scal_force, lo, hi, p0_new);  // :431
   fill_boundary_box(P, snew, lo, hi, ng_s, P.rhoh_comp, dm + P.rhoh_comp, 1, adv_bc, pmask);
 }
 

@@ -100,7 +100,7 @@ void mk_rhoh_flux_box(const mgpu_params& P, Arr* sflux, const Arr* sedge, const 
 }
 
 void update_scal_box(const mgpu_params& P, int nstart, int nstop, const Arr& sold, Arr& snew, const Arr* sflux,
-                     const Arr& force, const int* lo, const int* hi) {
+                     const Arr& force, const int* lo, const int* hi, const double* p0_new, const Arr* p0_new_cart) {
   const int dm = P.dm;
   const double dt = P.dt;
   const double* dx = P.dx;
@@ -114,7 +114,18 @@ void update_scal_box(const mgpu_params& P, int nstart, int nstop, const Arr& sol
       snew(i, j, k, c) = sold(i, j, k, c) + dt * (-divterm + force(i, j, k, c));
     });
   }
-  // EOS call below cutoff (update_scal.f90:421-447) stays with the Fortran caller: not restated.
+  if (P.do_eos_h_above_cutoff && nstart == P.rhoh_comp) {  // update_scal.f90:421-447
+    if (have_eos()) {
+      update_scal_eos_box(P, sold, snew, p0_new, p0_new_cart, lo, hi);
+    } else {  // like the product: never skip the reset silently
+      long below = 0;
+      for (int k = vb.lo[2]; k <= vb.hi[2]; ++k)
+        for (int j = vb.lo[1]; j <= vb.hi[1]; ++j)
+          for (int i = vb.lo[0]; i <= vb.hi[0]; ++i)
+            if (snew(i, j, k, P.rho_comp - 1) <= P.base_cutoff_density) ++below;
+      if (below > 0) fail("update_scal: zones below base_cutoff_density need the EOS (mo_set_eos)");
+    }
+  }
   if (nstart == P.spec_comp && nstop == P.spec_comp + P.nspec - 1) {
     const int rho = P.rho_comp - 1;
     {  // snew(:,:,:,rho_comp) = sold(:,:,:,rho_comp), ghost cells included

@@ -66,7 +66,8 @@ void mk_rhoh_flux_box(const mgpu_params& P, Arr* sflux, const Arr* sedge, const 
                       const double* rhoh0_new, const double* rhoh0_edge_new, const int* lo, const int* hi);
 
 void update_scal_box(const mgpu_params& P, int nstart, int nstop, const Arr& sold, Arr& snew, const Arr* sflux,
-                     const Arr& force, const int* lo, const int* hi);
+                     const Arr& force, const int* lo, const int* hi, const double* p0_new = nullptr,
+                     const Arr* p0_new_cart = nullptr);
 
 void update_velocity_box(const mgpu_params& P, const Arr& uold, Arr& unew, const Arr* umac, const Arr* uedge,
                          const Arr& force, const Arr& sponge, const double* w0, const int* lo, const int* hi);
@@ -107,9 +108,9 @@ void velocity_advance_box(const mgpu_params& P, const Arr& uold, Arr& unew, cons
 void enthalpy_advance_box(const mgpu_params& P, int which_step, Arr& sold, Arr& snew, Arr* sedge, Arr* sflux,
                           Arr& scal_force, const Arr& thermal, Arr* umac, const double* w0, const double* rho0_old,
                           const double* rhoh0_old, const double* rho0_new, const double* rhoh0_new,
-                          const double* p0_old, const double* p0_new, const double* psi, const double* grav_old,
-                          const double* grav_nph, const int* lo, const int* hi, int ng_s, int ng_f, const int* adv_bc,
-                          const int* pmask);
+                          const double* p0_old, const double* p0_new, const double* tempbar, const double* psi,
+                          const double* grav_old, const double* grav_nph, const int* lo, const int* hi, int ng_s, int ng_f,
+                          const int* adv_bc, const int* pmask);
 
 // ghost fill of a single box covering the whole domain: periodic wrap + multifab_physbc
 void fill_boundary_box(const mgpu_params& P, Arr& s, const int* lo, const int* hi, int ng, int scomp, int bccomp,
@@ -132,4 +133,38 @@ void estdt_sphr_level(const mgpu_params& P, const mgpu_geom& g, int nfabs, const
 void make_etarho_planar(const mgpu_params& P, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
                         double* etarho_cc);
 
+// ---- EOS pieces (mo_eos.cpp) ----
+struct EosState {  // the fields of eos_t (eos_type.f90:102) the advective path reads
+  double rho, T, p, e, h, cv, cp, cs, dpdT, dpdr, dedT, dedr, dhdT, mu, mu_e, abar, zbar;
+};
+void set_eos(const mgpu_eos* e);
+bool have_eos();
+const mgpu_eos& the_eos(const char* who);
+void eos_call(int input, EosState& s, const double* xn);
+void update_scal_eos_box(const mgpu_params& P, const Arr& sold, Arr& snew, const double* p0_new, const Arr* p0_new_cart,
+                         const int* lo, const int* hi);
+void h_from_rhot_edge_box(const mgpu_params& P, Arr* sedge, const double* rho0_old, const double* rhoh0_old,
+                          const double* t0_old, const double* rho0_edge_old, const double* rhoh0_edge_old,
+                          const double* t0_edge_old, const double* rho0_new, const double* rhoh0_new,
+                          const double* t0_new, const double* rho0_edge_new, const double* rhoh0_edge_new,
+                          const double* t0_edge_new, const int* lo, const int* hi);
+void h_from_rhot_edge_sphr_box(const mgpu_params& P, Arr* sedge, const Arr& rho0_cart, const Arr& rhoh0_cart,
+                               const Arr& t0_cart, const int* lo, const int* hi);
+void mktempforce_box(const mgpu_params& P, Arr& temp_force, const Arr& s, const Arr* umac, const Arr& thermal,
+                     const double* p0_old, const double* psi, const int* lo, const int* hi);
+void mktempforce_sphr_box(const mgpu_params& P, Arr& temp_force, const Arr& s, const Arr* umac, const Arr& thermal,
+                          const Arr& p0_cart, const Arr& psi_cart, const int* lo, const int* hi);
+void firstdt_box(const mgpu_params& P, const Arr& u, const Arr& s, const Arr& force, const Arr& divU, const double* p0,
+                 const double* gamma1bar, const Arr* gp0_cart, const int* lo, const int* hi, double cfl,
+                 bool use_soundspeed_firstdt, bool use_divu_firstdt, double& dt, double& umax);
+void make_t_box(const mgpu_params& P, Arr& state, const double* p0, const Arr* p0_cart, bool from_p, bool flag,
+                bool update_rhoh, const int* lo, const int* hi);
 }  // namespace mo
+
+// spherical helpers of mo_sphr.cpp used by the EOS entry points (they live outside namespace mo there)
+mo::Arr cart_with_ghosts(const mgpu_params& P, const mgpu_geom& g, const double* s0, int ng, int bccomp, const int* lo,
+                     const int* hi, const int* adv_bc, const int* pmask);
+void mk_vel_force_sphr_box(const mgpu_params& P, const mgpu_geom& g, mo::Arr& vel_force, bool is_final_update, const mo::Arr& uold,
+                           const mo::Arr* uedge, const double* w0, const mo::Arr* w0mac, const mo::Arr& gpi, const mo::Arr& rho,
+                           const mo::Arr& normal, const double* rho0, const double* grav, const mo::Arr& w0_force_cart,
+                           const int* lo, const int* hi, bool do_add_utilde_force);

@@ -585,7 +585,7 @@ void velocity_advance_sphr_box(const mgpu_params& P, const mgpu_geom& g, const A
 
 // ---- enthalpy path, spherical ------------------------------------------------------------------------------------
 // put_1d_array_on_cart of a bin-centred array incl. its ghost fill with the BCs of component bccomp (fill_3d_data.f90:21)
-static Arr cart_with_ghosts(const mgpu_params& P, const mgpu_geom& g, const double* s0, int ng, int bccomp, const int* lo,
+Arr cart_with_ghosts(const mgpu_params& P, const mgpu_geom& g, const double* s0, int ng, int bccomp, const int* lo,
                             const int* hi, const int* adv_bc, const int* pmask) {
   Arr c(lo[0] - ng, hi[0] + ng, lo[1] - ng, hi[1] + ng, lo[2] - ng, hi[2] + ng, 1);
   put_1d_array_on_cart_sphr(P, g, false, false, s0, c, lo, hi);
@@ -648,15 +648,18 @@ void mkrhohforce_sphr_box(const mgpu_params& P, const mgpu_geom& g, Arr& scal_fo
 void enthalpy_advance_sphr_box(const mgpu_params& P, const mgpu_geom& g, int which_step, Arr& sold, Arr& snew, Arr* sedge,
                                Arr* sflux, Arr& scal_force, const Arr& thermal, Arr* umac, const double* w0,
                                const Arr* w0mac, const double* rho0_old, const double* rhoh0_old, const double* rho0_new,
-                               const double* rhoh0_new, const double* p0_old, const double* p0_new, const double* psi,
-                               const int* lo, const int* hi, int ng_s, int ng_f, const int* adv_bc, const int* pmask) {
+                               const double* rhoh0_new, const double* p0_old, const double* p0_new, const double* tempbar,
+                               const double* psi, const int* lo, const int* hi, int ng_s, int ng_f, const int* adv_bc,
+                               const int* pmask) {
   const int dm = 3, nr = g.nr_fine;
   const int ept = P.enthalpy_pred_type;
   const int foextrap_comp = dm + P.nscal + 2;
   const int rhoh = P.rhoh_comp - 1, rho = P.rho_comp - 1;
   if (ept == MGPU_PREDICT_HPRIME) fail("mk_rhoh_flux : predict_hprime not coded yet");
-  if (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H)
-    fail("oracle: temperature-based enthalpy prediction needs the EOS (makeHfromRhoT_edge): not restated");
+  const bool pred_T =
+      (ept == MGPU_PREDICT_T_THEN_RHOHPRIME || ept == MGPU_PREDICT_T_THEN_H || ept == MGPU_PREDICT_TPRIME_THEN_H);
+  const int temp = P.temp_comp - 1;
+  if (pred_T && !tempbar) fail("enthalpy_advance: the temperature-based predictions need tempbar");
   Box vb = grown(lo, hi, dm, 0);
   auto fill_umac = [&]() {
     for (int d = 0; d < dm; ++d) fill_boundary_face(P, umac[d], lo, hi, 1, d, pmask);
@@ -670,8 +673,16 @@ void enthalpy_advance_sphr_box(const mgpu_params& P, const mgpu_geom& g, int whi
   };
   if (ept == MGPU_PREDICT_H) rhoh_to_h(true);  // :122-126
   scal_force.fill(0.0);                         // :132-134
-  mkrhohforce_sphr_box(P, g, scal_force, true, thermal, umac, p0_old, p0_old, psi, true, lo, hi, adv_bc, pmask);
-  fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
+  if (pred_T) {  // :190-195, mkscalforce.f90:770-776
+    Arr p0_cart = cart_with_ghosts(P, g, p0_old, 1, foextrap_comp, lo, hi, adv_bc, pmask);
+    Arr psi_cart(vb.lo[0], vb.hi[0], vb.lo[1], vb.hi[1], vb.lo[2], vb.hi[2], 1);
+    put_1d_array_on_cart_sphr(P, g, false, false, psi, psi_cart, lo, hi);
+    mktempforce_sphr_box(P, scal_force, sold, umac, thermal, p0_cart, psi_cart, lo, hi);
+    fill_boundary_box(P, scal_force, lo, hi, ng_f, P.temp_comp, foextrap_comp, 1, adv_bc, pmask);
+  } else {
+    mkrhohforce_sphr_box(P, g, scal_force, true, thermal, umac, p0_old, p0_old, psi, true, lo, hi, adv_bc, pmask);
+    fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
+  }
   if (ept == MGPU_PREDICT_RHOHPRIME) {  // :141-156
     Arr rhoh0_old_cart = cart_with_ghosts(P, g, rhoh0_old, 1, dm + P.rhoh_comp, lo, hi, adv_bc, pmask);
     Arr fo = scal_force.comp(rhoh), sa = sold.comp(rhoh);
@@ -688,12 +699,32 @@ void enthalpy_advance_sphr_box(const mgpu_params& P, const mgpu_geom& g, int whi
     pert_form_sphr(P, g, sa, rhoh0_old, flag, lo, hi);
     fill_boundary_box(P, sold, lo, hi, ng_s, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc, pmask);
   };
+  auto pert_T = [&](bool flag) {  // :214-217, :268-272
+    Arr sa = sold.comp(temp);
+    pert_form_sphr(P, g, sa, tempbar, flag, lo, hi);
+    fill_boundary_box(P, sold, lo, hi, ng_s, P.temp_comp, flag ? foextrap_comp : dm + P.temp_comp, 1, adv_bc, pmask);
+  };
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(true);  // :204-208
+  if (ept == MGPU_PREDICT_TPRIME_THEN_H) pert_T(true);
   const bool cons = (ept == MGPU_PREDICT_RHOH);     // :232-254
-  if (P.bds_type == 0) make_edge_scal_box(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, rhoh, dm + P.rhoh_comp, false, cons, ng_s);
-  else bds_box(P, sold, sedge, umac, scal_force, lo, hi, rhoh, cons);
+  const int pc = pred_T ? temp : rhoh;              // :220-226
+  if (P.bds_type == 0) make_edge_scal_box(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, pc, dm + pc + 1, false, cons, ng_s);
+  else bds_box(P, sold, sedge, umac, scal_force, lo, hi, pc, cons);
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(false);  // :257-261
+  if (ept == MGPU_PREDICT_TPRIME_THEN_H) pert_T(false);
   if (ept == MGPU_PREDICT_H) rhoh_to_h(false);     // :272-276
+  if (pred_T) {                                    // :280-286, rhoh_vs_t.f90:84-105
+    std::vector<double> r0h(nr), rh0h(nr), t0h(nr);
+    for (int r = 0; r < nr; ++r) {
+      r0h[r] = 0.5 * (rho0_old[r] + rho0_new[r]);
+      rh0h[r] = 0.5 * (rhoh0_old[r] + rhoh0_new[r]);
+      t0h[r] = 0.5 * (tempbar[r] + tempbar[r]);
+    }
+    Arr r0c = cart_with_ghosts(P, g, r0h.data(), 2, dm + P.rho_comp, lo, hi, adv_bc, pmask);
+    Arr rh0c = cart_with_ghosts(P, g, rh0h.data(), 2, dm + P.rhoh_comp, lo, hi, adv_bc, pmask);
+    Arr t0c = cart_with_ghosts(P, g, t0h.data(), 2, dm + P.temp_comp, lo, hi, adv_bc, pmask);
+    h_from_rhot_edge_sphr_box(P, sedge, r0c, rh0c, t0c, lo, hi);
+  }
   addw0_sphr(umac, w0mac, lo, hi, -1.0);           // :293
   fill_umac();
   // :301-399: rho0mac and h0mac of the old (and, for which_step 2, the new) base state; rhoh0mac is built by the
@@ -716,7 +747,10 @@ void enthalpy_advance_sphr_box(const mgpu_params& P, const mgpu_geom& g, int whi
   mkrhohforce_sphr_box(P, g, scal_force, false, thermal, umac, p0_old, s1 ? p0_old : p0_new, psi, false, lo, hi, adv_bc,
                        pmask);  // :405-416
   fill_boundary_box(P, scal_force, lo, hi, ng_f, P.rhoh_comp, foextrap_comp, 1, adv_bc, pmask);
-  update_scal_box(P, P.rhoh_comp, P.rhoh_comp, sold, snew, sflux, scal_force, lo, hi);  // :431 (no EOS below the cutoff here)
+  {  // :418-431
+    Arr p0_new_cart = cart_with_ghosts(P, g, p0_new, 1, foextrap_comp, lo, hi, adv_bc, pmask);
+    update_scal_box(P, P.rhoh_comp, P.rhoh_comp, sold, snew, sflux, scal_force, lo, hi, nullptr, &p0_new_cart);
+  }
   fill_boundary_box(P, snew, lo, hi, ng_s, P.rhoh_comp, dm + P.rhoh_comp, 1, adv_bc, pmask);
 }
 
@@ -996,8 +1030,8 @@ int mo_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int which
                              mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force, const mgpu_fab* thermal,
                              mgpu_fab* const* umac, const double* w0, const mgpu_fab* const* w0mac, const double* rho0_old,
                              const double* rhoh0_old, const double* rho0_new, const double* rhoh0_new,
-                             const double* p0_old, const double* p0_new, const double* psi, const int* adv_bc,
-                             const int* pmask) {
+                             const double* p0_old, const double* p0_new, const double* tempbar, const double* psi,
+                             const int* adv_bc, const int* pmask) {
   MO_TRY
   need3(p);
   Arr so = Arr::view(*sold, 3), sn = Arr::view(*snew, 3), fa = Arr::view(*scal_force, 3), th = Arr::view(*thermal, 3);
@@ -1007,7 +1041,7 @@ int mo_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int which
   views3((const mgpu_fab* const*)umac, 0, um);
   views3(w0mac, 0, wm);
   enthalpy_advance_sphr_box(*p, *g, which_step, so, sn, se, sf, fa, th, um, w0, wm, rho0_old, rhoh0_old, rho0_new, rhoh0_new,
-                            p0_old, p0_new, psi, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
+                            p0_old, p0_new, tempbar, psi, sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
   MO_CATCH
 }
 

@@ -52,6 +52,16 @@ module maestro_b200_shim
      integer(c_int) :: s0_interp_type, w0_interp_type, s0mac_interp_type, w0mac_interp_type
   end type mgpu_geom
 
+  ! the EOS state of the library (include/maestro_b200.h mgpu_eos): what eos_init leaves in the module variables of
+  ! eos_type_module / actual_eos_module, plus the network's aion / zion and the constants of constants_cgs.f90
+  type, bind(C), public :: mgpu_eos
+     integer(c_int) :: kind, assume_neutral, nspec, pad_
+     real(c_double) :: gamma, k_B, n_A
+     real(c_double) :: mintemp, maxtemp, mindens, maxdens, mine, maxe, minp, maxp, minh, maxh
+     real(c_double) :: small_temp
+     real(c_double) :: aion(32), zion(32)
+  end type mgpu_eos
+
   integer(c_int), parameter :: MGPU_HOST = 0
 
   interface
@@ -178,13 +188,15 @@ module maestro_b200_shim
                                      rhoh0_old(*), rhoh0_edge_old(*), rhoh0_new(*), rhoh0_edge_new(*)
      end function mgpu_mk_rhoh_flux_c
 
-     integer(c_int) function mgpu_update_scal_c(p, nfabs, nstart, nstop, sold, snew, sflux, force) &
+     ! p0_new / p0_new_cart: c_loc of the level's 1-D array / of an array of nfabs mgpu_fab (c_null_ptr when unused)
+     integer(c_int) function mgpu_update_scal_c(p, nfabs, nstart, nstop, sold, snew, sflux, force, p0_new, p0_new_cart) &
           bind(C, name="mgpu_update_scal")
        import :: c_int, c_ptr, mgpu_params, mgpu_fab
        type(mgpu_params), intent(in) :: p
        integer(c_int), value :: nfabs, nstart, nstop
        type(mgpu_fab), intent(in) :: sold(*), snew(*), force(*)
        type(c_ptr), intent(in) :: sflux(*)
+       type(c_ptr), value :: p0_new, p0_new_cart
      end function mgpu_update_scal_c
 
      integer(c_int) function mgpu_update_velocity_c(p, nfabs, uold, unew, umac, uedge, force, sponge, w0) &
@@ -491,7 +503,7 @@ module maestro_b200_shim
 
      ! enthalpy_advance.f90:16, spherical
      integer(c_int) function mgpu_enthalpy_advance_sphr_c(p, g, which_step, sold, snew, sedge, sflux, scal_force, thermal, &
-          umac, w0, w0mac, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, adv_bc, pmask) &
+          umac, w0, w0mac, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, tempbar, psi, adv_bc, pmask) &
           bind(C, name="mgpu_enthalpy_advance_sphr")
        import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
        type(mgpu_params), intent(in) :: p
@@ -500,7 +512,8 @@ module maestro_b200_shim
        type(mgpu_fab), intent(inout) :: sold(*), snew(*), scal_force(*)
        type(mgpu_fab), intent(in) :: thermal(*)
        type(c_ptr), intent(in) :: sedge(*), sflux(*), umac(*), w0mac(*)
-       real(c_double), intent(in) :: w0(*), rho0_old(*), rhoh0_old(*), rho0_new(*), rhoh0_new(*), p0_old(*), p0_new(*), psi(*)
+       real(c_double), intent(in) :: w0(*), rho0_old(*), rhoh0_old(*), rho0_new(*), rhoh0_new(*), p0_old(*), p0_new(*)
+       real(c_double), intent(in) :: tempbar(*), psi(*)
        integer(c_int), intent(in) :: adv_bc(*), pmask(*)
      end function mgpu_enthalpy_advance_sphr_c
 
@@ -577,8 +590,8 @@ module maestro_b200_shim
 
      ! enthalpy_advance.f90:16
      integer(c_int) function mgpu_enthalpy_advance_c(p, which_step, sold, snew, sedge, sflux, scal_force, &
-          thermal, umac, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old, grav_nph, &
-          adv_bc, pmask) &
+          thermal, umac, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, tempbar, psi, grav_old, &
+          grav_nph, adv_bc, pmask) &
           bind(C, name="mgpu_enthalpy_advance")
        import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
        type(mgpu_params), intent(in) :: p
@@ -597,6 +610,7 @@ module maestro_b200_shim
        real(c_double), intent(in) :: rhoh0_new(*)
        real(c_double), intent(in) :: p0_old(*)
        real(c_double), intent(in) :: p0_new(*)
+       real(c_double), intent(in) :: tempbar(*)
        real(c_double), intent(in) :: psi(*)
        real(c_double), intent(in) :: grav_old(*)
        real(c_double), intent(in) :: grav_nph(*)
@@ -680,8 +694,100 @@ module maestro_b200_shim
        type(mgpu_fab), intent(in) :: etarhoflux(*)
        real(c_double), intent(out) :: etarho_ec(*), etarho_cc(*)
      end function mgpu_make_etarho_planar_c
+     ! ---- the EOS and the pieces of the path that call it (SURVEY 8 f4 / f1 / f3) ----
+     ! eos_init (Microphysics/EOS/eos.F90:26): called once after eos_init / network_init with their values
+     integer(c_int) function mgpu_set_eos_c(e) bind(C, name="mgpu_set_eos")
+       import :: c_int, mgpu_eos
+       type(mgpu_eos), intent(in) :: e
+     end function mgpu_set_eos_c
+
+     ! eos(input, state) at n points: state(n, MGPU_EOS_NQ), xn(n, nspec), Fortran order
+     integer(c_int) function mgpu_eos_eval_c(input, n, state, xn) bind(C, name="mgpu_eos_eval")
+       import :: c_int, c_long, c_double
+       integer(c_int), value :: input
+       integer(c_long), value :: n
+       real(c_double), intent(inout) :: state(*)
+       real(c_double), intent(in) :: xn(*)
+     end function mgpu_eos_eval_c
+
+     ! rhoh_vs_t.f90:20 (planar)
+     integer(c_int) function mgpu_make_h_from_rhot_edge_c(p, nfabs, sedge, rho0_old, rhoh0_old, t0_old, rho0_edge_old, &
+          rhoh0_edge_old, t0_edge_old, rho0_new, rhoh0_new, t0_new, rho0_edge_new, rhoh0_edge_new, t0_edge_new) &
+          bind(C, name="mgpu_make_h_from_rhot_edge")
+       import :: c_int, c_ptr, c_double, mgpu_params
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(c_ptr), intent(in) :: sedge(*)
+       real(c_double), intent(in) :: rho0_old(*), rhoh0_old(*), t0_old(*), rho0_edge_old(*), rhoh0_edge_old(*), t0_edge_old(*)
+       real(c_double), intent(in) :: rho0_new(*), rhoh0_new(*), t0_new(*), rho0_edge_new(*), rhoh0_edge_new(*), t0_edge_new(*)
+     end function mgpu_make_h_from_rhot_edge_c
+
+     ! rhoh_vs_t.f90:20 with spherical == 1
+     integer(c_int) function mgpu_make_h_from_rhot_edge_sphr_c(p, g, nfabs, sedge, rho0_old, rhoh0_old, t0_old, rho0_new, &
+          rhoh0_new, t0_new, adv_bc, pmask) bind(C, name="mgpu_make_h_from_rhot_edge_sphr")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs
+       type(c_ptr), intent(in) :: sedge(*)
+       real(c_double), intent(in) :: rho0_old(*), rhoh0_old(*), t0_old(*), rho0_new(*), rhoh0_new(*), t0_new(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_make_h_from_rhot_edge_sphr_c
+
+     ! mkscalforce.f90:719; g: c_loc of an mgpu_geom, c_null_ptr for planar geometry
+     integer(c_int) function mgpu_mktempforce_c(p, g, nfabs, temp_force, umac, s, thermal, p0_old, psi, adv_bc, pmask) &
+          bind(C, name="mgpu_mktempforce")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(c_ptr), value :: g
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(inout) :: temp_force(*)
+       type(c_ptr), intent(in) :: umac(*)
+       type(mgpu_fab), intent(in) :: s(*), thermal(*)
+       real(c_double), intent(in) :: p0_old(*), psi(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_mktempforce_c
+
+     ! firstdt.f90:25
+     integer(c_int) function mgpu_firstdt_c(p, g, nfabs, u, gpi, s, divU, rho0, p0, grav, gamma1bar, cflfac, init_shrink, &
+          use_soundspeed_firstdt, use_divu_firstdt, dt, umax) bind(C, name="mgpu_firstdt")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(c_ptr), value :: g
+       integer(c_int), value :: nfabs, use_soundspeed_firstdt, use_divu_firstdt
+       type(mgpu_fab), intent(in) :: u(*), gpi(*), s(*), divU(*)
+       real(c_double), intent(in) :: rho0(*), p0(*), grav(*), gamma1bar(*)
+       real(c_double), value :: cflfac, init_shrink
+       real(c_double), intent(inout) :: dt, umax
+     end function mgpu_firstdt_c
+
+     ! rhoh_vs_t.f90:800
+     integer(c_int) function mgpu_make_t_from_rhoh_c(p, g, nfabs, state, p0, use_eos_e_instead_of_h, adv_bc, pmask) &
+          bind(C, name="mgpu_make_t_from_rhoh")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(c_ptr), value :: g
+       integer(c_int), value :: nfabs, use_eos_e_instead_of_h
+       type(mgpu_fab), intent(inout) :: state(*)
+       real(c_double), intent(in) :: p0(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_make_t_from_rhoh_c
+
+     ! rhoh_vs_t.f90:1165
+     integer(c_int) function mgpu_make_t_from_rhop_c(p, g, nfabs, state, p0, update_rhoh, use_pprime_in_tfromp, adv_bc, &
+          pmask) bind(C, name="mgpu_make_t_from_rhop")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(c_ptr), value :: g
+       integer(c_int), value :: nfabs, update_rhoh, use_pprime_in_tfromp
+       type(mgpu_fab), intent(inout) :: state(*)
+       real(c_double), intent(in) :: p0(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_make_t_from_rhop_c
   end interface
 
+  public :: mgpu_set_eos_c, mgpu_eos_eval_c, mgpu_make_h_from_rhot_edge_c, mgpu_make_h_from_rhot_edge_sphr_c
+  public :: mgpu_mktempforce_c, mgpu_firstdt_c, mgpu_make_t_from_rhoh_c, mgpu_make_t_from_rhop_c
   public :: mgpu_startup, mgpu_shutdown, mgpu_fill_params, mgpu_describe, mgpu_describe_edges, mgpu_check
   public :: mgpu_make_edge_scal_c, mgpu_bds_c, mgpu_mk_rhoX_flux_c, mgpu_mk_rhoh_flux_c, mgpu_update_scal_c
   public :: mgpu_update_velocity_c, mgpu_addw0_c, mgpu_mkutrans_c, mgpu_velpred_c

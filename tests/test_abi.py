@@ -36,7 +36,7 @@ def test_struct_layout_matches_c(tmp_path):
     src = tmp_path / "layout.c"
     fields = {"mgpu_fab": [f[0] for f in abi.mgpu_fab._fields_], "mgpu_params": [f[0] for f in abi.mgpu_params._fields_],
               "mgpu_halo_plan": [f[0] for f in abi.mgpu_halo_plan._fields_],
-              "mgpu_geom": [f[0] for f in abi.mgpu_geom._fields_]}
+              "mgpu_geom": [f[0] for f in abi.mgpu_geom._fields_], "mgpu_eos": [f[0] for f in abi.mgpu_eos._fields_]}
     body = ['#include <stdio.h>', '#include <stddef.h>', '#include "maestro_b200.h"', 'int main(void) {']
     for st, fs in fields.items():
         body.append('printf("%s %%zu\\n", sizeof(%s));' % (st, st))
@@ -74,7 +74,7 @@ def test_fortran_shim_struct_mirrors_match():
     extents, as the C structs (through the ctypes mirror, itself checked against gcc's layout above)"""
     txt = open(os.path.join(ROOT, "shim", "maestro_b200_shim.f90")).read()
     kinds = {"integer(c_int)": C.c_int, "real(c_double)": C.c_double, "type(c_ptr)": None}
-    for st in ("mgpu_fab", "mgpu_params", "mgpu_geom"):
+    for st in ("mgpu_fab", "mgpu_params", "mgpu_geom", "mgpu_eos"):
         body = re.search(r"type, bind\(C\), public :: %s\n(.*?)end type %s" % (st, st), txt, flags=re.S).group(1)
         got = []
         for line in body.splitlines():
