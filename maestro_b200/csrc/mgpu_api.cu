@@ -1409,7 +1409,7 @@ static EnthalpyMasks enthalpy_masks(const mgpu_params& P) {
   m.snew_in = mrhoh | (eos_reset ? (mrho | mspec) : 0);
   m.sedge_in = mrho | (pred_T ? (mspec | mtemp) : 0);  // the x-face T' is read by the other faces (QUIRK) after it is written
   m.sedge_out = mrhoh | (pred_T ? mtemp : 0);
-  m.force_out = pred_T ? mtemp : mrhoh;
+  m.force_out = mrhoh;  // zeroed again at :401-403: only the force of the final update survives the episode
   return m;
 }
 
@@ -2171,7 +2171,8 @@ int mgpu_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, 
   c.zero_on_host(*scal_force, ~m.force_out);
   DV th = c.view(*thermal, true, false);
   DV se[3], sf[3], um[3];
-  c.views((const mgpu_fab* const*)sedge, 0, m.sedge_in, m.sedge_out, se);
+  // edge-state fabs with ghost cells: the episode writes the valid faces only, so what it writes is read first
+  c.views((const mgpu_fab* const*)sedge, 0, m.sedge_in | (sedge[0]->ng > 0 ? m.sedge_out : (cmask_t)0), m.sedge_out, se);
   c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, m.mrhoh, sf);
   c.views((const mgpu_fab* const*)umac, 0, true, true, um);
   enthalpy_advance_dev(*p, which_step, so, sn, se, sf, fv, th, um, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old,
@@ -2540,9 +2541,11 @@ int mgpu_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int whi
   const EnthalpyMasks m = enthalpy_masks(*p);
   DV so = c.view(*sold, m.sold_in, m.sold_out), sn = c.view(*snew, m.snew_in, m.mrhoh);
   DV fv = c.view(*scal_force, (cmask_t)0, m.force_out);
+  c.zero_on_host(*scal_force, ~m.force_out);
   DV th = c.view(*thermal, true, false);
   DV se[3], sf[3], um[3], wm[3];
-  c.views((const mgpu_fab* const*)sedge, 0, m.sedge_in, m.sedge_out, se);
+  // edge-state fabs with ghost cells: the episode writes the valid faces only, so what it writes is read first
+  c.views((const mgpu_fab* const*)sedge, 0, m.sedge_in | (sedge[0]->ng > 0 ? m.sedge_out : (cmask_t)0), m.sedge_out, se);
   c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, m.mrhoh, sf);
   c.views((const mgpu_fab* const*)umac, 0, true, true, um);
   c.views(w0mac, 0, true, false, wm);
@@ -2752,7 +2755,8 @@ int mgpu_make_h_from_rhot_edge(const mgpu_params* p, int nfabs, mgpu_fab* const*
   a.t0_edge_new = upload_small(t0_edge_new, (size_t)nr + 1);
   for (int i = 0; i < nfabs; ++i) {
     h_edge_common(p, a, sedge[0][i]);
-    c.views((const mgpu_fab* const*)sedge, i, h_edge_in(p), crange(p->rhoh_comp - 1, 1), a.sedge);
+    c.views((const mgpu_fab* const*)sedge, i, h_edge_in(p) | (sedge[0][i].ng > 0 ? crange(p->rhoh_comp - 1, 1) : (cmask_t)0),
+            crange(p->rhoh_comp - 1, 1), a.sedge);
     a.rho0_cart = a.rhoh0_cart = a.t0_cart = a.sedge[0];
     h_from_rhot_edge_dev(a);
   }
@@ -2784,7 +2788,8 @@ int mgpu_make_h_from_rhot_edge_sphr(const mgpu_params* p, const mgpu_geom* g, in
     HEdgeArgs a{};
     a.sphr = true;
     h_edge_common(p, a, sedge[0][i]);
-    c.views((const mgpu_fab* const*)sedge, i, h_edge_in(p), crange(p->rhoh_comp - 1, 1), a.sedge);
+    c.views((const mgpu_fab* const*)sedge, i, h_edge_in(p) | (sedge[0][i].ng > 0 ? crange(p->rhoh_comp - 1, 1) : (cmask_t)0),
+            crange(p->rhoh_comp - 1, 1), a.sedge);
     SphrCtx X{*p, *g, make_geom(*p, *g), sedge[0][i].lo, sedge[0][i].hi, adv_bc, pmask};
     const size_t mark = arena_mark();
     a.rho0_cart = sphr_cart(X, r0d, 2, dm + p->rho_comp);

@@ -374,10 +374,12 @@ def test_enthalpy_advance_temperature_predictions(gpu_ops, oracle, eos_on, dm, n
                                b["rhoh0_old"], b["rho0_new"], b["rhoh0_new"], p0_old, p0_new, ex["psi"], ex["grav_old"],
                                ex["grav_nph"], st["adv_bc"], st["pmask"], tempbar=tempbar)
             out.append([sold, snew, force] + sedge + sflux + umac)
-        for g, c in zip(*out):
+        names = ["sold", "snew", "force"] + ["sedge%d" % d for d in range(dm)] + ["sflux%d" % d for d in range(dm)] + \
+                ["umac%d" % d for d in range(dm)]
+        for nm, g, c in zip(names, *out):
             if exact:
-                assert same(g.a, c.a)
-            assert relerr(g.a, c.a) <= 1e-12
+                assert same(g.a, c.a), nm
+            assert relerr(g.a, c.a) <= 1e-12, nm
         snew_v = out[1][1].valid()
         assert (snew_v[p.rho_comp - 1] <= p.base_cutoff_density).any()
     finally:
@@ -495,9 +497,11 @@ def test_enthalpy_advance_sphr_temperature_predictions(gpu_ops, oracle, eos_on, 
                                     rad["p0_old"], rad["p0_new"], rad["psi"], st["adv_bc"], st["pmask"],
                                     tempbar=rad["tempbar"])
             res.append([sold.a, snew.a, force.a] + [f.a for f in sedge] + [f.a for f in sflux] + [u.a for u in umac])
-        for a, b in zip(*res):
+        names = ["sold", "snew", "force"] + ["sedge%d" % d for d in range(3)] + ["sflux%d" % d for d in range(3)] + \
+                ["umac%d" % d for d in range(3)]
+        for nm, a, b in zip(names, *res):
             if exact:
-                assert same(a, b)
-            assert relerr(a, b) <= 1e-12
+                assert same(a, b), nm
+            assert relerr(a, b) <= 1e-12, nm
     finally:
         lib.set_option("exact", 0)
