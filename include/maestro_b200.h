@@ -440,6 +440,19 @@ int mgpu_estdt_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, const m
 int mgpu_make_etarho_planar(const mgpu_params* p, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
                             double* etarho_cc);
 
+/* average (Source/average.f90:24) of component incomp (1-based) of one level's fabs into phibar(0:nr-1).  Planar: the
+ * mean of every plane (sums over the ranks, NCCL).  Spherical (g != NULL): the reference's binning by the exact set of
+ * radii a cell centre can have (sum_phi_3d_sphr :564), then quadratic interpolation onto the base-state radii (:312-352),
+ * for one level (max_levs = 1); nr_irreg (geometry, initialize.f90:1272) and drdxfac (probin) are passed explicitly.
+ * Floating-point sums in a different order than the reference's loops: parity is 1e-12 relative. */
+int mgpu_average(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* phi, int incomp, int nr_irreg,
+                 int drdxfac, double* phibar);
+/* make_etarho_spherical (Source/make_eta.f90:256): eta_cart = [rho' (U . e_r)] at the half time (construct_eta_cart
+ * :345), its average -> etarho_cc(0:nr_fine-1), and etarho_ec(0:nr_fine) on the edges (:337-343). */
+int mgpu_make_etarho_spherical(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* sold,
+                               const mgpu_fab* snew, const mgpu_fab* const* umac, const mgpu_fab* const* w0mac,
+                               const double* rho0_old, const double* rho0_new, const mgpu_fab* normal, int nr_irreg,
+                               int drdxfac, double* etarho_ec, double* etarho_cc);
 
 /* ---- EOS -----------------------------------------------------------------------------
  * The generic front end of Microphysics/EOS/eos.F90:99 (composition eos_type.f90:157, reset_inputs eos.F90:129,

@@ -195,6 +195,9 @@ OPERATORS.update({
                 + [c_double_p] * 2),
     "make_t_from_rhoh": (C.c_int, [P_, G_, C.c_int, F_, c_double_p, C.c_int, c_int_p, c_int_p]),
     "make_t_from_rhop": (C.c_int, [P_, G_, C.c_int, F_, c_double_p, C.c_int, C.c_int, c_int_p, c_int_p]),
+    "average": (C.c_int, [P_, G_, C.c_int, F_, C.c_int, C.c_int, C.c_int, c_double_p]),
+    "make_etarho_spherical": (C.c_int, [P_, G_, C.c_int, F_, F_, FF_, FF_, c_double_p, c_double_p, F_, C.c_int, C.c_int,
+                                        c_double_p, c_double_p]),
 })
 
 # several boxes per rank: the CUDA library only (the oracle's multifab is one box covering the domain)

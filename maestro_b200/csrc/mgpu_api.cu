@@ -3006,3 +3006,128 @@ int mgpu_make_t_from_rhop(const mgpu_params* p, const mgpu_geom* g, int nfabs, m
 }
 
 }  // extern "C"
+
+// ---- average and make_etarho_spherical ------------------------------------------------------------------
+// average (average.f90:24) of component incomp of one level's fabs (device views) into phibar(0:nr-1)
+static void average_views(const mgpu_params* p, const mgpu_geom* g, int nfabs, const DV* phi1, const mgpu_fab* boxes,
+                          int nr_irreg, int drdxfac, double* phibar) {
+  const int dm = p->dm;
+  if (!p->spherical) {  // :114-163: plane sums over the ranks / cells of the domain's plane
+    const int nr = p->nr, r = dm - 1;
+    std::vector<double> sum(nr, 0.0);
+    for (int i = 0; i < nfabs; ++i) {
+      const mgpu_fab& f = boxes[i];
+      if (f.lo[r] < 0 || f.hi[r] > nr - 1) throw Error("average: box outside the base-state range 0:nr-1");
+      std::vector<double> part(f.hi[r] - f.lo[r] + 1);
+      plane_sums_dev(*p, phi1[i], f.lo, f.hi, f.lo[r], f.hi[r], part.data());
+      for (int k = f.lo[r]; k <= f.hi[r]; ++k) sum[k] = sum[k] + part[k - f.lo[r]];
+    }
+    if (comm_size() > 1) {  // parallel_reduce MPI_SUM, :152
+      double* d = arena_alloc((size_t)nr);
+      MGPU_CUDA(cudaMemcpyAsync(d, sum.data(), nr * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
+      allreduce_dev(d, nr, 0);
+      MGPU_CUDA(cudaMemcpyAsync(sum.data(), d, nr * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+      MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    }
+    double ncell = 1.0;  // :127-135
+    for (int d = 0; d < r; ++d) ncell *= (double)(p->domhi[d] - p->domlo[d] + 1);
+    for (int k = 0; k < nr; ++k) phibar[k] = sum[k] / ncell;  // :155-159
+    return;
+  }
+  if (nr_irreg < 2) throw Error("average: nr_irreg (geometry) must be passed for spherical geometry");
+  for (int i = 0; i < nfabs; ++i) {  // the reference would write past phisum(nr_irreg) for such a box: refuse instead
+    double far2 = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      const double a = g->prob_lo[d] + ((double)boxes[i].lo[d] + 0.5) * p->dx[d] - g->center[d];
+      const double b = g->prob_lo[d] + ((double)boxes[i].hi[d] + 0.5) * p->dx[d] - g->center[d];
+      far2 += std::max(a * a, b * b);
+    }
+    if ((int)((far2 / (p->dx[0] * p->dx[0]) - 0.75) / 2.0) > nr_irreg) throw Error("average: a cell maps beyond nr_irreg");
+  }
+  const int nb = nr_irreg + 1;
+  std::vector<double> radii(nr_irreg + 3), phisum(nr_irreg + 2, 0.0);
+  std::vector<long> ncell(nr_irreg + 2, 0);
+  for (int r = 0; r <= nr_irreg; ++r) radii[r + 1] = std::sqrt(0.75 + 2.0 * r) * p->dx[0];  // :92
+  radii[nr_irreg + 2] = 1.e99;                                                               // :98
+  const double* radii_d = upload_small(radii.data() + 1, (size_t)nr_irreg + 2);
+  double* ps_d = arena_alloc((size_t)2 * nb);  // sums, then counts (as doubles for the reduction over the ranks)
+  unsigned long long* nc_d = reinterpret_cast<unsigned long long*>(arena_alloc((size_t)nb));
+  MGPU_CUDA(cudaMemsetAsync(ps_d, 0, (size_t)2 * nb * sizeof(double), g_ctx.stream));
+  MGPU_CUDA(cudaMemsetAsync(nc_d, 0, (size_t)nb * sizeof(unsigned long long), g_ctx.stream));
+  for (int i = 0; i < nfabs; ++i) sum_phi_sphr_dev(*p, *g, phi1[i], boxes[i].lo, boxes[i].hi, radii_d, nr_irreg, ps_d, nc_d);
+  std::vector<unsigned long long> nc_h(nb);
+  MGPU_CUDA(cudaMemcpyAsync(nc_h.data(), nc_d, nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_ctx.stream));
+  MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  if (comm_size() > 1) {  // parallel_reduce of ncell and phisum, :197-198 (counts are exact in fp64)
+    std::vector<double> cnt(nb);
+    for (int r = 0; r < nb; ++r) cnt[r] = (double)nc_h[r];
+    MGPU_CUDA(cudaMemcpyAsync(ps_d + nb, cnt.data(), nb * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
+    allreduce_dev(ps_d, 2 * nb, 0);
+    MGPU_CUDA(cudaMemcpyAsync(cnt.data(), ps_d + nb, nb * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+    MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    for (int r = 0; r < nb; ++r) nc_h[r] = (unsigned long long)cnt[r];
+  }
+  MGPU_CUDA(cudaMemcpyAsync(phisum.data() + 1, ps_d, nb * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+  MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  for (int r = 0; r < nb; ++r) ncell[r + 1] = (long)nc_h[r];
+  average_sphr_tail(g->dr, g->nr_fine, nr_irreg, drdxfac, phisum, ncell, radii, phibar);
+}
+
+extern "C" {
+
+int mgpu_average(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* phi, int incomp, int nr_irreg,
+                 int drdxfac, double* phibar) {
+  MGPU_TRY
+  if (p->spherical) need_sphr(p, g);
+  const int nr = p->spherical ? g->nr_fine : p->nr;
+  Call c(p, (size_t)(4 * (nr + 4) + 4 * (std::max(nr_irreg, 0) + 8)) * sizeof(double) + 16384);
+  std::vector<DV> v(nfabs);
+  for (int i = 0; i < nfabs; ++i) {
+    if (incomp < 1 || incomp > phi[i].nc) throw Error("average: incomp out of range");
+    v[i] = c.view(phi[i], crange(incomp - 1, 1), (cmask_t)0).comp(incomp - 1);
+  }
+  average_views(p, g, nfabs, v.data(), phi, nr_irreg, drdxfac, phibar);
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_make_etarho_spherical(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* sold,
+                               const mgpu_fab* snew, const mgpu_fab* const* umac, const mgpu_fab* const* w0mac,
+                               const double* rho0_old, const double* rho0_new, const mgpu_fab* normal, int nr_irreg,
+                               int drdxfac, double* etarho_ec, double* etarho_cc) {
+  MGPU_TRY
+  if (!p->spherical) throw Error("ERROR: make_eta_spherical should not be called for plane-parallel");  // make_eta.f90:289
+  need_sphr(p, g);
+  const int nr = g->nr_fine;
+  size_t need = 0;
+  for (int i = 0; i < nfabs; ++i) need += 2 * fab_bytes(sold[i].lo, sold[i].hi, 3, 0, 0, 1);
+  Call c(p, need + geom_scratch(g) + (size_t)(4 * (nr + 4) + 4 * (std::max(nr_irreg, 0) + 8)) * sizeof(double) + 16384);
+  Geom gd = make_geom(*p, *g);
+  std::vector<double> nph(nr);
+  for (int r = 0; r < nr; ++r) nph[r] = 0.5 * (rho0_old[r] + rho0_new[r]);  // :376-378
+  const double* nph_d = upload_small(nph.data(), (size_t)nr);
+  const cmask_t mrho = crange(p->rho_comp - 1, 1);
+  std::vector<DV> eta(nfabs);
+  for (int i = 0; i < nfabs; ++i) {  // construct_eta_cart, :345-408 (its ghost fill :322 feeds nothing: average reads valid cells)
+    const int* lo = sold[i].lo;
+    const int* hi = sold[i].hi;
+    DV so = c.view(sold[i], mrho, (cmask_t)0), sn = c.view(snew[i], mrho, (cmask_t)0), nm = c.view(normal[i], true, false);
+    DV um[3], wm[3];
+    c.views(umac, i, true, false, um);
+    c.views(w0mac, i, true, false, wm);
+    eta[i] = arena_fab(lo, hi, 3, 0, nullptr, 1);
+    const size_t mark = arena_mark();
+    DV nc = arena_fab(lo, hi, 3, 0, nullptr, 1);
+    put_1d_array_on_cart_dev(*p, *g, gd, nph_d, nc, false, false, lo, hi);
+    eta_cart_dev(eta[i], so.comp(p->rho_comp - 1), sn.comp(p->rho_comp - 1), um, wm, nm, nc, lo, hi);
+    arena_release(mark);
+  }
+  average_views(p, g, nfabs, eta.data(), sold, nr_irreg, drdxfac, etarho_cc);  // :327
+  etarho_ec[0] = 0.0;                                                          // :337-343
+  for (int r = 1; r < nr; ++r) etarho_ec[r] = 0.5 * (etarho_cc[r] + etarho_cc[r - 1]);
+  etarho_ec[nr] = etarho_cc[nr - 1];
+  c.finish();
+  MGPU_CATCH
+}
+
+}  // extern "C"

@@ -126,7 +126,114 @@ __global__ void __launch_bounds__(256) k_plane_sums(DV f, Box3 vb, int dm, int k
   }
 }
 
+// sum_phi_3d_sphr (average.f90:564-618, no mask: one level): every cell adds its value and a count to the radial bin its
+// centre maps into.  Floating-point atomics: the order of the additions inside a bin differs from the reference's loop
+// (and from run to run), parity is 1e-12 relative like the plane sums.
+__global__ void __launch_bounds__(256) k_sum_phi_sphr(DV phi, Box3 vb, double cx, double cy, double cz, double plx,
+                                                      double ply, double plz, double dx0, double dx1, double dx2,
+                                                      const double* radii, int nr_irreg, double* phisum,
+                                                      unsigned long long* ncell) {
+  int ix[3];
+  if (!decode3(vb, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  const double z = plz + ((double)k + 0.5) * dx2 - cz;
+  const double y = ply + ((double)j + 0.5) * dx1 - cy;
+  const double x = plx + ((double)i + 0.5) * dx0 - cx;
+  const double radius = sqrt(x * x + y * y + z * z);
+  const double q = radius / dx0;
+  int index = (int)((q * q - 0.75) / 2.0);
+  if (index < nr_irreg) {
+    if (fabs(radius - radii[index]) > fabs(radius - radii[index + 1])) index = index + 1;
+  }
+  atomicAdd(&phisum[index], phi(i, j, k));
+  atomicAdd(&ncell[index], 1ull);
+}
+
+// construct_eta_cart (make_eta.f90:345-408): [rho' (U . e_r)] at the half time on the valid cells
+__global__ void k_eta_cart(DV eta, Box3 vb, DV rho_old, DV rho_new, DV um, DV vm, DV wm, DV wx, DV wy, DV wz, DV normal,
+                           DV nph) {
+  int ix[3];
+  if (!decode3(vb, ix)) return;
+  const int i = ix[0], j = ix[1], k = ix[2];
+  const double U_dot_er = 0.5 * (um(i, j, k) + um(i + 1, j, k) + wx(i, j, k) + wx(i + 1, j, k)) * normal(i, j, k, 0) +
+                          0.5 * (vm(i, j, k) + vm(i, j + 1, k) + wy(i, j, k) + wy(i, j + 1, k)) * normal(i, j, k, 1) +
+                          0.5 * (wm(i, j, k) + wm(i, j, k + 1) + wz(i, j, k) + wz(i, j, k + 1)) * normal(i, j, k, 2);
+  eta(i, j, k) = (0.5 * (rho_old(i, j, k) + rho_new(i, j, k)) - nph(i, j, k)) * U_dot_er;
+}
+
+// quad_interp, average.f90:386-401
+double avg_quad_interp(double x, double x0, double x1, double x2, double y0, double y1, double y2, bool limit) {
+  double y = y0 + (y1 - y0) / (x1 - x0) * (x - x0) +
+             ((y2 - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0)) / (x2 - x0) * (x - x0) * (x - x1);
+  if (limit) {
+    const double hi = std::max(std::max(y0, y1), y2), lo = std::min(std::min(y0, y1), y2);
+    if (y > hi) y = hi;
+    if (y < lo) y = lo;
+  }
+  return y;
+}
+
 }  // namespace
+
+void sum_phi_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const DV& phi1, const int* lo, const int* hi,
+                      const double* radii_dev, int nr_irreg, double* phisum_dev, unsigned long long* ncell_dev) {
+  const Box3 vb = grown(lo, hi, 3, 0);
+  MGPU_TIMED(TAG_GLUE, (k_sum_phi_sphr<<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(
+                           phi1, vb, g.center[0], g.center[1], g.center[2], g.prob_lo[0], g.prob_lo[1], g.prob_lo[2],
+                           P.dx[0], P.dx[1], P.dx[2], radii_dev, nr_irreg, phisum_dev, ncell_dev)));
+}
+
+void eta_cart_dev(const DV& eta, const DV& rho_old, const DV& rho_new, const DV* umac, const DV* w0mac, const DV& normal,
+                  const DV& rho0_nph_cart, const int* lo, const int* hi) {
+  const Box3 vb = grown(lo, hi, 3, 0);
+  MGPU_TIMED(TAG_GLUE, (k_eta_cart<<<grid3(vb, 256), block3(vb, 256), 0, ctx().stream>>>(
+                           eta, vb, rho_old, rho_new, umac[0], umac[1], umac[2], w0mac[0], w0mac[1], w0mac[2], normal,
+                           rho0_nph_cart)));
+}
+
+// the part of average() after the sums for spherical == 1 and one level (average.f90:204-362); the three arrays are
+// indexed -1.. in the reference: element [r + 1] here
+void average_sphr_tail(double dr, int nr_fine, int nr_irreg, int drdxfac, std::vector<double>& phisum,
+                       std::vector<long>& ncell, std::vector<double>& radii, double* phibar) {
+  double* PS = phisum.data() + 1;
+  long* NC = ncell.data() + 1;
+  double* RD = radii.data() + 1;
+  for (int r = 0; r <= nr_irreg; ++r)
+    if (NC[r] != 0) PS[r] = PS[r] / (double)NC[r];      // :204-210
+  PS[-1] = (11.0 / 8.0) * PS[0] - (3.0 / 8.0) * PS[1];  // :213-215
+  RD[-1] = 0.0;
+  NC[-1] = 1;
+  int max_rcoord = nr_irreg;  // :286-309: drop the radii no cell maps into (one level: which_lev = 1 everywhere)
+  for (int r = 0, j = 0; r <= nr_irreg; ++r) {
+    while (j <= nr_irreg && NC[j] == 0) ++j;
+    if (j > nr_irreg) {
+      for (int q = r; q <= nr_irreg; ++q) PS[q] = 1.e99;
+      for (int q = r; q <= nr_irreg + 1; ++q) RD[q] = 1.e99;
+      max_rcoord = r - 1;
+      break;
+    }
+    PS[r] = PS[j];
+    RD[r] = RD[j];
+    NC[r] = NC[j];
+    ++j;
+    if (j > nr_irreg) {
+      max_rcoord = r;
+      break;
+    }
+  }
+  int sc = 0;  // :312-352
+  for (int r = 0; r < nr_fine; ++r) {
+    const double radius = ((double)r + 0.5) * dr;
+    for (int j = sc; j <= max_rcoord; ++j)
+      if (std::fabs(radius - RD[j]) < std::fabs(radius - RD[j + 1])) {
+        sc = j;
+        break;
+      }
+    sc = std::min(sc, max_rcoord - 1);
+    const bool limit = !((double)r > (double)(nr_fine - 1) - (double)drdxfac);
+    phibar[r] = avg_quad_interp(radius, RD[sc - 1], RD[sc], RD[sc + 1], PS[sc - 1], PS[sc], PS[sc + 1], limit);
+  }
+}
 
 void estdt_box_dev(const mgpu_params& P, const DV& u, const DV& s, const DV& force, const DV& divU, const DV& dSdt,
                    const double* w0, const double* w0_h, const double* p0, const double* gamma1bar, const int* lo,

@@ -17,4 +17,14 @@ void estdt_box_dev(const mgpu_params& P, const DV& u, const DV& s, const DV& for
 // sums of the slab-direction planes k0..k1 of a single-component fab over the valid transverse cells -> host
 void plane_sums_dev(const mgpu_params& P, const DV& f, const int* lo, const int* hi, int k0, int k1, double* sums_h);
 
+// average() with spherical == 1 (average.f90:168-362), one level: the binning of one box (atomics into phisum / ncell,
+// nr_irreg + 1 bins, radii(0:nr_irreg+1) on the device) and the host tail (normalise, drop the empty radii, interpolate)
+void sum_phi_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const DV& phi1, const int* lo, const int* hi,
+                      const double* radii_dev, int nr_irreg, double* phisum_dev, unsigned long long* ncell_dev);
+void average_sphr_tail(double dr, int nr_fine, int nr_irreg, int drdxfac, std::vector<double>& phisum,
+                       std::vector<long>& ncell, std::vector<double>& radii, double* phibar);
+// construct_eta_cart (make_eta.f90:345): eta and rho0_nph_cart cover the valid cells
+void eta_cart_dev(const DV& eta, const DV& rho_old, const DV& rho_new, const DV* umac, const DV* w0mac, const DV& normal,
+                  const DV& rho0_nph_cart, const int* lo, const int* hi);
+
 }  // namespace mgpu

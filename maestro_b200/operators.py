@@ -409,3 +409,24 @@ class Operators:
         ints = [as_int_p(x) for x in (adv_bc, pmask)]
         self._call("make_t_from_rhop", C.byref(p), C.byref(geom.c) if geom is not None else None, 1, fab_ptr(state), pp,
                    int(update_rhoh), int(use_pprime_in_tfromp), ints[0][1], ints[1][1])
+
+    # ---- averages -----------------------------------------------------------------------------------
+    def average(self, p, phi, incomp, geom=None, nr_irreg=0, drdxfac=1):
+        """average (Source/average.f90:24) of one level: returns phibar(0:nr-1)."""
+        nr = geom.c.nr_fine if geom is not None else p.nr
+        out = np.zeros(nr)
+        self._call("average", C.byref(p), C.byref(geom.c) if geom is not None else None, 1, fab_ptr(phi), int(incomp),
+                   int(nr_irreg), int(drdxfac), out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def make_etarho_spherical(self, p, geom, sold, snew, umac, w0mac, rho0_old, rho0_new, normal, nr_irreg, drdxfac=1):
+        """make_etarho_spherical (Source/make_eta.f90:256): returns (etarho_ec(0:nr_fine), etarho_cc(0:nr_fine-1))."""
+        nr = geom.c.nr_fine
+        ec, cc = np.zeros(nr + 1), np.zeros(nr)
+        keep = [as_double_p(x) for x in (rho0_old, rho0_new)]
+        um, k1 = fab_pp(umac)
+        wm, k2 = fab_pp(w0mac)
+        self._call("make_etarho_spherical", C.byref(p), C.byref(geom.c), 1, fab_ptr(sold), fab_ptr(snew), um, wm,
+                   keep[0][1], keep[1][1], fab_ptr(normal), int(nr_irreg), int(drdxfac),
+                   ec.ctypes.data_as(C.POINTER(C.c_double)), cc.ctypes.data_as(C.POINTER(C.c_double)))
+        return ec, cc

@@ -219,4 +219,54 @@ int mo_make_t_from_rhop(const mgpu_params* p, const mgpu_geom* g, int nfabs, mgp
   MO_CATCH
 }
 
+// ---- average / make_etarho_spherical (average.f90:24, make_eta.f90:256) -----------------------------------------------
+int mo_average(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* phi, int incomp, int nr_irreg,
+               int drdxfac, double* phibar) {
+  MO_TRY
+  average_level(*p, g, nfabs, phi, incomp, nr_irreg, drdxfac, phibar);
+  MO_CATCH
+}
+
+int mo_make_etarho_spherical(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* sold,
+                             const mgpu_fab* snew, const mgpu_fab* const* umac, const mgpu_fab* const* w0mac,
+                             const double* rho0_old, const double* rho0_new, const mgpu_fab* normal, int nr_irreg,
+                             int drdxfac, double* etarho_ec, double* etarho_cc) {
+  MO_TRY
+  if (!p->spherical) fail("ERROR: make_eta_spherical should not be called for plane-parallel");  // make_eta.f90:289
+  need_geom(p, g, "make_etarho_spherical");
+  const int nr = g->nr_fine, rho = p->rho_comp - 1;
+  std::vector<double> rho0_nph(nr);
+  for (int r = 0; r < nr; ++r) rho0_nph[r] = 0.5 * (rho0_old[r] + rho0_new[r]);  // :376-378
+  std::vector<Arr> eta(nfabs);
+  std::vector<mgpu_fab> ef(nfabs);
+  for (int i = 0; i < nfabs; ++i) {  // construct_eta_cart, :345-408
+    const int* lo = sold[i].lo;
+    const int* hi = sold[i].hi;
+    Arr so = Arr::view(sold[i], 3), sn = Arr::view(snew[i], 3), nm = Arr::view(normal[i], 3);
+    Arr um[3], wm[3];
+    views(p, umac, i, um);
+    views(p, w0mac, i, wm);
+    Arr nph(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 1);
+    put_1d_array_on_cart_sphr(*p, *g, false, false, rho0_nph.data(), nph, lo, hi);
+    eta[i].alloc(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 1);
+    Arr& e = eta[i];
+    for_box(grown(lo, hi, 3, 0), [&](int ii, int j, int k) {
+      const double U_dot_er =
+          0.5 * (um[0](ii, j, k) + um[0](ii + 1, j, k) + wm[0](ii, j, k) + wm[0](ii + 1, j, k)) * nm(ii, j, k, 0) +
+          0.5 * (um[1](ii, j, k) + um[1](ii, j + 1, k) + wm[1](ii, j, k) + wm[1](ii, j + 1, k)) * nm(ii, j, k, 1) +
+          0.5 * (um[2](ii, j, k) + um[2](ii, j, k + 1) + wm[2](ii, j, k) + wm[2](ii, j, k + 1)) * nm(ii, j, k, 2);
+      e(ii, j, k) = (0.5 * (so(ii, j, k, rho) + sn(ii, j, k, rho)) - nph(ii, j, k)) * U_dot_er;
+    });
+    ef[i] = sold[i];
+    ef[i].ptr = e.p;
+    ef[i].ng = 0;
+    ef[i].nc = 1;
+  }
+  average_level(*p, g, nfabs, ef.data(), 1, nr_irreg, drdxfac, etarho_cc);  // :327
+  etarho_ec[0] = 0.0;                                                       // :337-343
+  for (int r = 1; r < nr; ++r) etarho_ec[r] = 0.5 * (etarho_cc[r] + etarho_cc[r - 1]);
+  etarho_ec[nr] = etarho_cc[nr - 1];
+  MO_CATCH
+}
+
 }  // extern "C"

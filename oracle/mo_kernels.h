@@ -133,6 +133,10 @@ void estdt_sphr_level(const mgpu_params& P, const mgpu_geom& g, int nfabs, const
 void make_etarho_planar(const mgpu_params& P, int nfabs, const mgpu_fab* etarhoflux, double* etarho_ec,
                         double* etarho_cc);
 
+// average (average.f90:24) of one level: phibar(0:nr-1); g == nullptr for planar geometry
+void average_level(const mgpu_params& P, const mgpu_geom* g, int nfabs, const mgpu_fab* phi, int incomp, int nr_irreg,
+                   int drdxfac, double* phibar);
+
 // ---- EOS pieces (mo_eos.cpp) ----
 struct EosState {  // the fields of eos_t (eos_type.f90:102) the advective path reads
   double rho, T, p, e, h, cv, cp, cs, dpdT, dpdr, dedT, dedr, dhdT, mu, mu_e, abar, zbar;

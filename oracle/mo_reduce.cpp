@@ -200,4 +200,139 @@ void make_etarho_planar(const mgpu_params& P, int nfabs, const mgpu_fab* etarhof
   for (int k = 0; k < nr; ++k) etarho_cc[k] = 0.5 * (etarho_ec[k] + etarho_ec[k + 1]);
 }
 
+// ---- average (Source/average.f90:24), one level -------------------------------------------------------------------
+namespace {
+// quad_interp, average.f90:386-401
+double avg_quad_interp(double x, double x0, double x1, double x2, double y0, double y1, double y2, bool limit) {
+  double y = y0 + (y1 - y0) / (x1 - x0) * (x - x0) +
+             ((y2 - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0)) / (x2 - x0) * (x - x0) * (x - x1);
+  if (limit) {
+    if (y > dmax(dmax(y0, y1), y2)) y = dmax(dmax(y0, y1), y2);
+    if (y < dmin(dmin(y0, y1), y2)) y = dmin(dmin(y0, y1), y2);
+  }
+  return y;
+}
+}  // namespace
+
+// sum_phi_3d_sphr, average.f90:564-618 (no mask: one level); radii(0:nr_irreg+1)
+void sum_phi_sphr_box(const mgpu_params& P, const mgpu_geom& g, const double* radii, int nr_irreg, const Arr& phi, int comp,
+                      const int* lo, const int* hi, double* phisum, long* ncell) {
+  for (int k = lo[2]; k <= hi[2]; ++k) {
+    const double z = g.prob_lo[2] + ((double)k + 0.5) * P.dx[2] - g.center[2];
+    for (int j = lo[1]; j <= hi[1]; ++j) {
+      const double y = g.prob_lo[1] + ((double)j + 0.5) * P.dx[1] - g.center[1];
+      for (int i = lo[0]; i <= hi[0]; ++i) {
+        const double x = g.prob_lo[0] + ((double)i + 0.5) * P.dx[0] - g.center[0];
+        const double radius = std::sqrt(x * x + y * y + z * z);
+        const double q = radius / P.dx[0];
+        int index = (int)((q * q - 0.75) / 2.0);
+        if (index < nr_irreg) {
+          if (dabs(radius - radii[index]) > dabs(radius - radii[index + 1])) index = index + 1;
+        }
+        phisum[index] = phisum[index] + phi(i, j, k, comp);
+        ncell[index] = ncell[index] + 1;
+      }
+    }
+  }
+}
+
+// the part of average() after the sums for spherical == 1 and nlevs = max_levs = 1 (average.f90:204-362):
+// phisum / ncell / radii are indexed -1..nr_irreg(+1) in the reference -> offset 1 here
+void average_sphr_tail(const mgpu_geom& g, int nr_irreg, int drdxfac, std::vector<double>& phisum,
+                       std::vector<long>& ncell, std::vector<double>& radii, double* phibar) {
+  auto PS = [&](int r) -> double& { return phisum[r + 1]; };
+  auto NC = [&](int r) -> long& { return ncell[r + 1]; };
+  auto RD = [&](int r) -> double& { return radii[r + 1]; };
+  for (int r = 0; r <= nr_irreg; ++r)
+    if (NC(r) != 0) PS(r) = PS(r) / (double)NC(r);  // :204-210
+  PS(-1) = (11.0 / 8.0) * PS(0) - (3.0 / 8.0) * PS(1);  // :213-215
+  RD(-1) = 0.0;
+  NC(-1) = 1;
+  // :217-283 choose the level to interpolate from: one level, which_lev(r) = 1
+  int max_rcoord = nr_irreg;
+  {  // :286-309 squish the list down to the radii that received a cell
+    int j = 0;
+    for (int r = 0; r <= nr_irreg; ++r) {
+      while (NC(j) == 0) {
+        j = j + 1;
+        if (j > nr_irreg) break;
+      }
+      if (j > nr_irreg) {
+        for (int q = r; q <= nr_irreg; ++q) PS(q) = 1.e99;
+        for (int q = r; q <= nr_irreg + 1; ++q) RD(q) = 1.e99;
+        max_rcoord = r - 1;
+        break;
+      }
+      PS(r) = PS(j);
+      RD(r) = RD(j);
+      NC(r) = NC(j);
+      j = j + 1;
+      if (j > nr_irreg) {
+        max_rcoord = r;
+        break;
+      }
+    }
+  }
+  int stencil_coord = 0;  // :312-352
+  for (int r = 0; r < g.nr_fine; ++r) {
+    const double radius = ((double)r + 0.5) * g.dr;
+    for (int j = stencil_coord; j <= max_rcoord; ++j)
+      if (dabs(radius - RD(j)) < dabs(radius - RD(j + 1))) {
+        stencil_coord = j;
+        break;
+      }
+    stencil_coord = std::min(stencil_coord, max_rcoord - 1);
+    const bool limit = !((double)r > (double)(g.nr_fine - 1) - (double)drdxfac * 1.0);  // 2.d0**(max_levs-1) = 1
+    phibar[r] = avg_quad_interp(radius, RD(stencil_coord - 1), RD(stencil_coord), RD(stencil_coord + 1),
+                                PS(stencil_coord - 1), PS(stencil_coord), PS(stencil_coord + 1), limit);
+  }
+}
+
+void average_level(const mgpu_params& P, const mgpu_geom* g, int nfabs, const mgpu_fab* phi, int incomp, int nr_irreg,
+                   int drdxfac, double* phibar) {
+  const int dm = P.dm, comp = incomp - 1;
+  for (int f = 0; f < nfabs; ++f)
+    if (incomp < 1 || incomp > phi[f].nc) fail("average: incomp out of range");
+  if (!P.spherical) {  // :114-163: every cell of a plane, divided by the cells of the domain's plane
+    const int nr = P.nr, r = dm - 1;
+    std::vector<double> sum(nr, 0.0);
+    for (int f = 0; f < nfabs; ++f) {  // sum_phi_2d / _3d (:520-560): k outermost, i innermost
+      Arr a = Arr::view(phi[f], dm);
+      const int* lo = phi[f].lo;
+      const int* hi = phi[f].hi;
+      if (dm == 3) {
+        for (int k = lo[2]; k <= hi[2]; ++k)
+          for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i) sum[k] = sum[k] + a(i, j, k, comp);
+      } else {
+        for (int j = lo[1]; j <= hi[1]; ++j)
+          for (int i = lo[0]; i <= hi[0]; ++i) sum[j] = sum[j] + a(i, j, 0, comp);
+      }
+    }
+    double ncell = 1.0;
+    for (int d = 0; d < r; ++d) ncell *= (double)(P.domhi[d] - P.domlo[d] + 1);
+    for (int k = 0; k < nr; ++k) phibar[k] = sum[k] / ncell;
+    return;
+  }
+  if (!g || dm != 3) fail("average: spherical geometry needs mgpu_geom (3-D)");
+  std::vector<double> radii(nr_irreg + 3), phisum(nr_irreg + 2, 0.0);
+  std::vector<long> ncell(nr_irreg + 2, 0);
+  for (int r = 0; r <= nr_irreg; ++r) radii[r + 1] = std::sqrt(0.75 + 2.0 * r) * P.dx[0];  // :92
+  radii[nr_irreg + 2] = 1.e99;
+  for (int f = 0; f < nfabs; ++f) {  // the reference would write past phisum(nr_irreg) here: refuse instead
+    double far2 = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      const double a = g->prob_lo[d] + ((double)phi[f].lo[d] + 0.5) * P.dx[d] - g->center[d];
+      const double b = g->prob_lo[d] + ((double)phi[f].hi[d] + 0.5) * P.dx[d] - g->center[d];
+      far2 += dmax(a * a, b * b);
+    }
+    if ((int)((far2 / (P.dx[0] * P.dx[0]) - 0.75) / 2.0) > nr_irreg) fail("average: a cell maps beyond nr_irreg");
+  }
+  for (int f = 0; f < nfabs; ++f) {
+    Arr a = Arr::view(phi[f], dm);
+    sum_phi_sphr_box(P, *g, radii.data() + 1, nr_irreg, a, comp, phi[f].lo, phi[f].hi, phisum.data() + 1, ncell.data() + 1);
+  }
+  average_sphr_tail(*g, nr_irreg, drdxfac, phisum, ncell, radii, phibar);
+}
+
 }  // namespace mo

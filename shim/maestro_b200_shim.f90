@@ -784,8 +784,33 @@ module maestro_b200_shim
        real(c_double), intent(in) :: p0(*)
        integer(c_int), intent(in) :: adv_bc(*), pmask(*)
      end function mgpu_make_t_from_rhop_c
+
+     ! average.f90:24 (g: c_loc of an mgpu_geom, c_null_ptr for planar geometry)
+     integer(c_int) function mgpu_average_c(p, g, nfabs, phi, incomp, nr_irreg, drdxfac, phibar) &
+          bind(C, name="mgpu_average")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(c_ptr), value :: g
+       integer(c_int), value :: nfabs, incomp, nr_irreg, drdxfac
+       type(mgpu_fab), intent(in) :: phi(*)
+       real(c_double), intent(inout) :: phibar(*)
+     end function mgpu_average_c
+
+     ! make_eta.f90:256
+     integer(c_int) function mgpu_make_etarho_spherical_c(p, g, nfabs, sold, snew, umac, w0mac, rho0_old, rho0_new, &
+          normal, nr_irreg, drdxfac, etarho_ec, etarho_cc) bind(C, name="mgpu_make_etarho_spherical")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_geom, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       type(mgpu_geom), intent(in) :: g
+       integer(c_int), value :: nfabs, nr_irreg, drdxfac
+       type(mgpu_fab), intent(in) :: sold(*), snew(*), normal(*)
+       type(c_ptr), intent(in) :: umac(*), w0mac(*)
+       real(c_double), intent(in) :: rho0_old(*), rho0_new(*)
+       real(c_double), intent(inout) :: etarho_ec(*), etarho_cc(*)
+     end function mgpu_make_etarho_spherical_c
   end interface
 
+  public :: mgpu_average_c, mgpu_make_etarho_spherical_c
   public :: mgpu_set_eos_c, mgpu_eos_eval_c, mgpu_make_h_from_rhot_edge_c, mgpu_make_h_from_rhot_edge_sphr_c
   public :: mgpu_mktempforce_c, mgpu_firstdt_c, mgpu_make_t_from_rhoh_c, mgpu_make_t_from_rhop_c
   public :: mgpu_startup, mgpu_shutdown, mgpu_fill_params, mgpu_describe, mgpu_describe_edges, mgpu_check
