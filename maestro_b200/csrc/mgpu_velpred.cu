@@ -6,6 +6,9 @@
 //   k_mkutrans   : one launch per direction: 1-D extrapolation of the normal component, BCs, Riemann with w0
 //   k_vp_face    : per face direction d: u_L^d, u_R^d of every component (+BCs) and the transverse
 //                  components upwinded by utrans                                 (velpred.f90:803-1129)
+// Both are fp64-compute bound (a PPM reconstruction per component), so they are CELL-centred: a thread reconstructs
+// its own cell once (Ip and Im together), hands Ip to the thread of the next cell through shared memory, and that
+// thread finishes the face between them.  Blocks overlap by one cell along d (1/128 resp. 1/8 of the threads).
 //   k_vp_trans   : 3-D only, the six corner-coupled states                      (:1139-1558)
 //   k_vp_final   : umac_L/R, Riemann with w0, BCs                               (:1562-1851, 2-D :528-630)
 #include "mgpu_recon.cuh"
@@ -65,23 +68,64 @@ __device__ __forceinline__ double upwind_trans(double l, double r, double ut, do
 }
 
 // ------------------------------------------------------------------------------------------
+// thread -> cell of a block that overlaps its neighbour by one cell along D: x blocks of VP_NX threads for D = 0,
+// (32, VP_ND) blocks otherwise.  ix: the cell; first: the block's first cell along D (it only feeds its neighbour);
+// returns false for threads past the face box fb (hi + 1 along D included as a cell: the right cell of the last face)
+constexpr int VP_NX = 128, VP_ND = 8;
+template <int D>
+__device__ __forceinline__ bool vp_cell(const Box3& fb, int* ix, bool& first, int& slot) {
+  if (D == 0) {
+    ix[0] = fb.lo[0] - 1 + (int)blockIdx.x * (VP_NX - 1) + (int)threadIdx.x;
+    ix[1] = fb.lo[1] + (int)blockIdx.y;
+    ix[2] = fb.lo[2] + (int)blockIdx.z;
+    first = threadIdx.x == 0;
+    slot = threadIdx.x;
+    return ix[0] <= fb.hi[0];
+  }
+  constexpr int T = (D == 1) ? 2 : 1;  // the other transverse direction
+  ix[0] = fb.lo[0] + (int)blockIdx.x * 32 + (int)threadIdx.x;
+  ix[D] = fb.lo[D] - 1 + (int)blockIdx.y * (VP_ND - 1) + (int)threadIdx.y;
+  ix[T] = fb.lo[T] + (int)blockIdx.z;
+  first = threadIdx.y == 0;
+  slot = threadIdx.y * 32 + threadIdx.x;
+  return ix[0] <= fb.hi[0] && ix[D] <= fb.hi[D];
+}
+template <int D>
+__device__ __forceinline__ int vp_left(int slot) { return D == 0 ? slot - 1 : slot - 32; }
+template <int D>
+inline dim3 vp_grid(const Box3& fb) {
+  const int n0 = fb.hi[0] - fb.lo[0] + 1, nd = fb.hi[D] - fb.lo[D] + 1;
+  if (D == 0) return dim3((unsigned)((n0 + VP_NX - 2) / (VP_NX - 1)), (unsigned)(fb.hi[1] - fb.lo[1] + 1), (unsigned)(fb.hi[2] - fb.lo[2] + 1));
+  constexpr int T = (D == 1) ? 2 : 1;
+  return dim3((unsigned)((n0 + 31) / 32), (unsigned)((nd + VP_ND - 2) / (VP_ND - 1)), (unsigned)(fb.hi[T] - fb.lo[T] + 1));
+}
+template <int D>
+inline dim3 vp_block() { return D == 0 ? dim3(VP_NX, 1, 1) : dim3(32, VP_ND, 1); }
+
 template <int D, int PPM>
-__global__ void k_mkutrans(VpArgs a) {
+__global__ void __launch_bounds__(256) k_mkutrans(VpArgs a) {
   constexpr int d = D;
-  int ix[3];
+  __shared__ double sh_ip[256];
+  int ix[3], slot;
+  bool first;
   Box3 fb = a.vb;
   fb.hi[d] += 1;
-  if (!decode3(fb, ix)) return;
+  const bool in = vp_cell<D>(fb, ix, first, slot);
   const DV u = a.utilde.comp(d), uf = a.ufull.comp(d);
   const long st = u.stride(d);
-  const LineBC b = make_linebc(a.dm, d, a.lo[d], a.hi[d], a.bclo[d][d], a.bchi[d][d]);
-  const double* q = u.p + u.off(ix[0], ix[1], ix[2]);
-  const double* qf = uf.p + uf.off(ix[0], ix[1], ix[2]);
-  const long fst = uf.stride(d);
-  double ul, ur, dummy;
-  vel_cell_states(PPM, a.slope_order, false, q - st, st, ix[d] - 1, b, qf[-fst], a.dt, a.dx[d], a.rel_eps, ul,
-                  dummy);
-  vel_cell_states(PPM, a.slope_order, false, q, st, ix[d], b, qf[0], a.dt, a.dx[d], a.rel_eps, dummy, ur);
+  double ul = 0.0, ur = 0.0;
+  const double* q = nullptr;
+  if (in) {  // this cell's two extrapolated states: Ip feeds the face above, Im the face below (this thread's face)
+    const LineBC b = make_linebc(a.dm, d, a.lo[d], a.hi[d], a.bclo[d][d], a.bchi[d][d]);
+    q = u.p + u.off(ix[0], ix[1], ix[2]);
+    double ip;
+    vel_cell_states(PPM, a.slope_order, false, q, st, ix[d], b, uf.p[uf.off(ix[0], ix[1], ix[2])], a.dt, a.dx[d],
+                    a.rel_eps, ip, ur);
+    sh_ip[slot] = ip;
+  }
+  __syncthreads();
+  if (!in || first) return;
+  ul = sh_ip[vp_left<D>(slot)];
   if (ix[d] == a.lo[d]) {
     const int p = a.plo[d];
     if (p == MGPU_BC_INLET) { ul = q[-st]; ur = q[-st]; }
@@ -101,27 +145,32 @@ __global__ void k_mkutrans(VpArgs a) {
 
 // ------------------------------------------------------------------------------------------
 template <int D, int PPM>
-__global__ void k_vp_face(VpArgs a) {
+__global__ void __launch_bounds__(256) k_vp_face(VpArgs a) {
   constexpr int d = D;
-  int ix[3];
+  __shared__ double sh_ip[3][256];
+  int ix[3], slot;
+  bool first;
   Box3 fb = a.tb;
   fb.lo[d] = a.lo[d];  // faces lo..hi+1 in d, lo-1..hi+1 transverse
-  if (!decode3(fb, ix)) return;
+  const bool in = vp_cell<D>(fb, ix, first, slot);
   const int dm = a.dm;
-  const DV ufd = a.ufull.comp(d);
-  const long fo = ufd.off(ix[0], ix[1], ix[2]);
-  const double ucl = ufd.p[fo - ufd.stride(d)], ucr = ufd.p[fo];
   const long uo = a.utilde.off(ix[0], ix[1], ix[2]);
   const long st = a.utilde.stride(d);
   double ul[3], ur[3];
-  _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) {
-    const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[c][d], a.bchi[c][d]);
-    const double* q = a.utilde.p + uo + a.utilde.cs * c;
-    double dummy;
-    vel_cell_states(PPM, a.slope_order, dm == 3, q - st, st, ix[d] - 1, b, ucl, a.dt, a.dx[d], a.rel_eps, ul[c],
-                    dummy);
-    vel_cell_states(PPM, a.slope_order, dm == 3, q, st, ix[d], b, ucr, a.dt, a.dx[d], a.rel_eps, dummy, ur[c]);
+  if (in) {  // this cell's states in direction d, every component: Ip feeds the face above, Im this thread's face
+    const DV ufd = a.ufull.comp(d);
+    const double uc = ufd.p[ufd.off(ix[0], ix[1], ix[2])];
+    _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) {
+      const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[c][d], a.bchi[c][d]);
+      const double* q = a.utilde.p + uo + a.utilde.cs * c;
+      double ip;
+      vel_cell_states(PPM, a.slope_order, dm == 3, q, st, ix[d], b, uc, a.dt, a.dx[d], a.rel_eps, ip, ur[c]);
+      sh_ip[c][slot] = ip;
+    }
   }
+  __syncthreads();
+  if (!in || first) return;
+  _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ul[c] = sh_ip[c][vp_left<D>(slot)];
   if (ix[d] == a.lo[d]) {
     const int p = a.plo[d];
     if (p == MGPU_BC_INLET) {
@@ -287,6 +336,25 @@ __global__ void k_vp_final(VpArgs a) {
     }                                                                                                 \
   } while (0)
 
+// the cell-centred kernels (k_mkutrans, k_vp_face): grid and block follow from the direction
+#define VPC_CASE(kern, D, PPM, fb, stream, args) \
+  MGPU_TIMED(TAG_VELPRED, (kern<D, PPM><<<vp_grid<D>(fb), vp_block<D>(), 0, stream>>>(args)))
+#define VPC_LAUNCH(kern, d, ppm, fb, stream, args)                       \
+  do {                                                                   \
+    switch ((d)*3 + (ppm)) {                                             \
+      case 0: VPC_CASE(kern, 0, 0, fb, stream, args); break;             \
+      case 1: VPC_CASE(kern, 0, 1, fb, stream, args); break;             \
+      case 2: VPC_CASE(kern, 0, 2, fb, stream, args); break;             \
+      case 3: VPC_CASE(kern, 1, 0, fb, stream, args); break;             \
+      case 4: VPC_CASE(kern, 1, 1, fb, stream, args); break;             \
+      case 5: VPC_CASE(kern, 1, 2, fb, stream, args); break;             \
+      case 6: VPC_CASE(kern, 2, 0, fb, stream, args); break;             \
+      case 7: VPC_CASE(kern, 2, 1, fb, stream, args); break;             \
+      case 8: VPC_CASE(kern, 2, 2, fb, stream, args); break;             \
+      default: throw Error("velpred: invalid ppm_type");                 \
+    }                                                                    \
+  } while (0)
+
 void check_phys(int bc, const char* who) {
   switch (bc) {
     case MGPU_BC_INLET: case MGPU_BC_OUTLET: case MGPU_BC_SYMMETRY: case MGPU_BC_SLIP_WALL: case MGPU_BC_NO_SLIP_WALL:
@@ -346,7 +414,7 @@ void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* u
   for (int d = 0; d < P.dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    VP_LAUNCH(k_mkutrans, d, a.ppm_type, grid3(fb, 256), block3(fb, 256), ctx().stream, a);
+    VPC_LAUNCH(k_mkutrans, d, a.ppm_type, fb, ctx().stream, a);
   }
 }
 
@@ -386,7 +454,7 @@ void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* um
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.tb;
     fb.lo[d] = a.lo[d];
-    VP_LAUNCH(k_vp_face, d, a.ppm_type, grid3(fb, 128), block3(fb, 128), s, a);
+    VPC_LAUNCH(k_vp_face, d, a.ppm_type, fb, s, a);
   }
   if (dm == 3) MGPU_TIMED(TAG_VELPRED, (k_vp_trans<<<grid3(a.tb, 256), block3(a.tb, 256), 0, s>>>(a)));
   for (int d = 0; d < dm; ++d) {
