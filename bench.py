@@ -236,6 +236,7 @@ def main():
 
     from maestro_b200 import abi, lib
 
+    host_affinity = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -444,7 +445,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": w.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(w, world),
-            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof}
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "host_affinity": host_affinity}
     if parity is not None:
         line["parity"] = parity
         line["exact_build"] = exact_line
@@ -476,6 +477,29 @@ def build_desc_only(config, n, world):
     w.desc["workload"] = w.desc["workload"].replace("16^3", "%d^3" % n).replace("32^2", "%d^2" % n)
     w.desc["zones_per_gpu"] = n ** w.p.dm // max(1, world if w.scaling == "strong" else 1)
     return w
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs next to its GPU (NVML's CPU affinity of the device, restricted to the CPUs the
+    container allows) before any host buffer is allocated, so that the pinned staging memory of the e2e leg is
+    first-touched on the GPU's NUMA node and the ranks of an 8-GPU run do not all stream through one socket.
+    Best effort: returns what was done for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = near & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return {"cpus": len(use), "of_allowed": len(allowed), "bound": True}
+        return {"cpus": len(allowed), "of_allowed": len(allowed), "bound": False}
+    except Exception as e:  # no NVML, no permission: run unbound
+        return {"bound": False, "why": str(e)[:80]}
 
 
 def selftest(ops, rank, world, local_rank, dev):

@@ -1221,7 +1221,8 @@ static void enthalpy_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
     mk_rhoh_flux_sphr_dev(P, fa);
     arena_release(mark);
   }
-  set_dev(scal_force.p, 0.0, scal_force.size());  // :401-403
+  // :401-403 setval(scal_force, ZERO, all): every component but the predicted one is still zero from :132-134
+  set_dev(scal_force.p + scal_force.cs * (pred_T ? temp : rhoh), 0.0, scal_force.cs);
   rhoh_force_sphr_full(X, scal_force, false, thermal, umac, p0_old_h, s1 ? p0_old_h : p0_new_h, psi_h, false, ng_f);  // :405-416
   UpdArgs ua;
   ua.dm = dm;
@@ -1377,7 +1378,8 @@ static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold,
   fa.rhoh0_old = rhoh0_old; fa.rhoh0_edge_old = rh0e_old;
   fa.rhoh0_new = s1 ? rhoh0_old : rhoh0_new; fa.rhoh0_edge_new = s1 ? rh0e_old : rh0e_new;
   mk_rhoh_flux_dev(P, fa);  // :326 / :375
-  set_dev(scal_force.p, 0.0, scal_force.size());  // :401-403
+  // :401-403 setval(scal_force, ZERO, all): every component but the predicted one is still zero from :132-134
+  set_dev(scal_force.p + scal_force.cs * (pred_T ? temp : rhoh), 0.0, scal_force.cs);
   rhoh_force(false, s1 ? p0_old : p0_new, s1 ? rho0_old : rho0_new, s1 ? grav_old : grav_nph, false);  // :405-416
   UpdArgs ua;
   ua.dm = dm;
