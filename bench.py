@@ -91,10 +91,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+PARAM_OVERRIDES = {}  # --bds: every leg (device, e2e, CPU arm) runs the same variant of the workload
+
+
 def build_workload(config, n, device, rank=0, world=1):
     from maestro_b200 import workloads
 
-    return workloads.BUILDERS[config](n=n or workloads.DEFAULT_N[config], device=device, rank=rank, world=world)
+    w = workloads.BUILDERS[config](n=n or workloads.DEFAULT_N[config], device=device, rank=rank, world=world)
+    for k, v in PARAM_OVERRIDES.items():
+        setattr(w.p, k, v)
+    if PARAM_OVERRIDES.get("bds_type") == 1:
+        w.desc["workload"] = w.desc["workload"].replace("ppm_type=1", "bds_type=1 (BDS edge states, Source/bds.f90)")
+    return w
 
 
 # ---- the c2 state as plain dicts (tests/test_full_size_gpu.py drives the episode on rolled / modified inputs) ---------
@@ -183,12 +191,18 @@ def main():
                     help="BASELINE.json configuration (maestro_b200/workloads.py); c2 carries the headline metric")
     ap.add_argument("--n", type=int, default=0, help="zones per side (default: the configuration's own size)")
     ap.add_argument("--e2e-steps", type=lambda v: max(1, int(v)), default=2)
+    ap.add_argument("--bds", action="store_true",
+                    help="bds_type = 1: the second half of BASELINE configs[1] (BDS edge states instead of PPM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--selftest", action="store_true",
                     help="multi-rank parity of the NCCL path against the single-box oracle instead of the timing run")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (mgpu_set_option), e.g. exact=1")
     args = ap.parse_args()
+    if args.bds:
+        if args.config != "c2":
+            ap.error("--bds applies to the test_advect configuration (c2)")
+        PARAM_OVERRIDES["bds_type"] = 1
     if os.environ.get("BENCH_WATCHDOG"):  # debugging aid: dump every thread's Python stack if the run stalls
         import faulthandler
 
@@ -319,6 +333,8 @@ def main():
         # sedge 24 = 64 B per zone; 2-D 8 + 8 + 16 + 16 = 48 B per zone (kernel table)
         bytes_per_zone = 48.0 if p.dm == 2 else 64.0
         achieved = bytes_per_zone * w.zones / (ms / nl * 1e-3) / 1e9
+        if name == "bds":  # staged: several launches per component -> per component, not per launch
+            achieved = bytes_per_zone * w.zones * w.ncomp / (ms / args.steps * 1e-3) / 1e9
         traffic = None
         ncu_static = None
         try:  # DRAM bytes per launch of this kernel class from the committed ncu --set full capture (c2, n = 256 only)

@@ -7,8 +7,19 @@
 // bdsconc's face blocks are index permutations of one another, written once over (d, t, r) = (normal, transverse,
 // corner) with every vector kept in (x,y,z) order; QUIRK: the z-face block samples the transverse velocity of p3
 // in the corner tetrahedra at (face + corner offset), bds.f90:2842,2916,3051,3125,3261,3335,3470,3544.
+// Two builds of this file (like mgpu_fused.cu): the exact one (-fmad=false, every division the reference writes: bit-
+// identical) and the FAST one (mgpu_bds_fast.cu: FMA contraction, divisions by dx, 3, 3h, 2h as multiplications by
+// reciprocals formed once; <= 1e-12 from the reference), the default.  `exact = 1` (mgpu_set_option) selects the first.
 #include "mgpu_bds.cuh"
 #include "mgpu_recon.cuh"
+
+#ifdef MGPU_BDS_FAST
+#define BDS_OVER(x, d, rd) ((x) * (rd))
+#define BDS_FN(name) name##_fast
+#else
+#define BDS_OVER(x, d, rd) ((x) / (d))
+#define BDS_FN(name) name##_exact
+#endif
 
 namespace mgpu {
 
@@ -19,6 +30,7 @@ struct BdsArgs {
   bool is_cons;
   int lo[3], hi[3];
   double dt, dx[3];
+  double rdx[3];    // 1/dx (FAST build)
   Box3 tb, vb, nb;  // cells lo-1:hi+1, valid cells, nodes lo-1:hi+2
   DV s, force;      // single-component views
   DV umac[3];
@@ -96,14 +108,16 @@ __global__ void k_bds_slope(BdsArgs a) {
   const double* nq = a.sint.p + a.sint.off(ix[0], ix[1], ix[2]);
   const long ny = a.sint.stride(1), nz = a.sint.stride(2);
   const double hx = a.dx[0], hy = a.dx[1], hz = a.dx[2];
+  const double rhx = a.rdx[0], rhy = a.rdx[1], rhz = a.rdx[2];
+  (void)rhx; (void)rhy; (void)rhz;
   const double s0 = q[0];
   const long so = a.slope.off(ix[0], ix[1], ix[2]);
   if (a.dm == 2) {
     auto N = [&](int i, int j) { return nq[i + j * ny]; };
     auto S = [&](int i, int j) { return q[i + j * sy]; };
-    const double sx = 0.5 * (N(1, 1) + N(1, 0) - N(0, 1) - N(0, 0)) / hx;
-    const double sy_ = 0.5 * (N(1, 1) - N(1, 0) + N(0, 1) - N(0, 0)) / hy;
-    const double sxy = (N(1, 1) - N(1, 0) - N(0, 1) + N(0, 0)) / (hx * hy);
+    const double sx = BDS_OVER(0.5 * (N(1, 1) + N(1, 0) - N(0, 1) - N(0, 0)), hx, rhx);
+    const double sy_ = BDS_OVER(0.5 * (N(1, 1) - N(1, 0) + N(0, 1) - N(0, 0)), hy, rhy);
+    const double sxy = BDS_OVER((N(1, 1) - N(1, 0) - N(0, 1) + N(0, 0)), (hx * hy), (rhx * rhy));
     double sc[4], smin[4], smax[4];
     sc[3] = s0 + 0.5 * (hx * sx + hy * sy_) + 0.25 * hx * hy * sxy;
     sc[2] = s0 + 0.5 * (hx * sx - hy * sy_) - 0.25 * hx * hy * sxy;
@@ -118,21 +132,21 @@ __global__ void k_bds_slope(BdsArgs a) {
       sc[m] = dmax2(dmin2(sc[m], smax[m]), smin[m]);
     }
     for (int ll = 0; ll < 3; ++ll) bds_pass<4>(sc, smin, smax, s0, 0.25 * (sc[3] + sc[2] + sc[1] + sc[0]));
-    a.slope.p[so] = 0.5 * (sc[3] + sc[2] - sc[0] - sc[1]) / hx;
-    a.slope.p[so + a.slope.cs] = 0.5 * (sc[3] + sc[1] - sc[0] - sc[2]) / hy;
-    a.slope.p[so + 2 * a.slope.cs] = (sc[0] + sc[3] - sc[1] - sc[2]) / (hx * hy);
+    a.slope.p[so] = BDS_OVER(0.5 * (sc[3] + sc[2] - sc[0] - sc[1]), hx, rhx);
+    a.slope.p[so + a.slope.cs] = BDS_OVER(0.5 * (sc[3] + sc[1] - sc[0] - sc[2]), hy, rhy);
+    a.slope.p[so + 2 * a.slope.cs] = BDS_OVER((sc[0] + sc[3] - sc[1] - sc[2]), (hx * hy), (rhx * rhy));
     return;
   }
   auto N = [&](int i, int j, int k) { return nq[i + j * ny + k * nz]; };
   auto S = [&](int i, int j, int k) { return q[i + j * sy + k * sz]; };
   double sl[7];
-  sl[0] = 0.25 * ((N(1, 0, 0) + N(1, 1, 0) + N(1, 0, 1) + N(1, 1, 1)) - (N(0, 0, 0) + N(0, 1, 0) + N(0, 0, 1) + N(0, 1, 1))) / hx;
-  sl[1] = 0.25 * ((N(0, 1, 0) + N(1, 1, 0) + N(0, 1, 1) + N(1, 1, 1)) - (N(0, 0, 0) + N(1, 0, 0) + N(0, 0, 1) + N(1, 0, 1))) / hy;
-  sl[2] = 0.25 * ((N(0, 0, 1) + N(1, 0, 1) + N(0, 1, 1) + N(1, 1, 1)) - (N(0, 0, 0) + N(1, 0, 0) + N(0, 1, 0) + N(1, 1, 0))) / hz;
-  sl[3] = 0.5 * ((N(0, 0, 0) + N(0, 0, 1) + N(1, 1, 0) + N(1, 1, 1)) - (N(1, 0, 0) + N(1, 0, 1) + N(0, 1, 0) + N(0, 1, 1))) / (hx * hy);
-  sl[4] = 0.5 * ((N(0, 0, 0) + N(0, 1, 0) + N(1, 0, 1) + N(1, 1, 1)) - (N(1, 0, 0) + N(1, 1, 0) + N(0, 0, 1) + N(0, 1, 1))) / (hx * hz);
-  sl[5] = 0.5 * ((N(0, 0, 0) + N(1, 0, 0) + N(0, 1, 1) + N(1, 1, 1)) - (N(0, 0, 1) + N(1, 0, 1) + N(0, 1, 0) + N(1, 1, 0))) / (hy * hz);
-  sl[6] = (-N(0, 0, 0) + N(1, 0, 0) + N(0, 1, 0) + N(0, 0, 1) - N(1, 1, 0) - N(1, 0, 1) - N(0, 1, 1) + N(1, 1, 1)) / (hx * hy * hz);
+  sl[0] = BDS_OVER(0.25 * ((N(1, 0, 0) + N(1, 1, 0) + N(1, 0, 1) + N(1, 1, 1)) - (N(0, 0, 0) + N(0, 1, 0) + N(0, 0, 1) + N(0, 1, 1))), hx, rhx);
+  sl[1] = BDS_OVER(0.25 * ((N(0, 1, 0) + N(1, 1, 0) + N(0, 1, 1) + N(1, 1, 1)) - (N(0, 0, 0) + N(1, 0, 0) + N(0, 0, 1) + N(1, 0, 1))), hy, rhy);
+  sl[2] = BDS_OVER(0.25 * ((N(0, 0, 1) + N(1, 0, 1) + N(0, 1, 1) + N(1, 1, 1)) - (N(0, 0, 0) + N(1, 0, 0) + N(0, 1, 0) + N(1, 1, 0))), hz, rhz);
+  sl[3] = BDS_OVER(0.5 * ((N(0, 0, 0) + N(0, 0, 1) + N(1, 1, 0) + N(1, 1, 1)) - (N(1, 0, 0) + N(1, 0, 1) + N(0, 1, 0) + N(0, 1, 1))), (hx * hy), (rhx * rhy));
+  sl[4] = BDS_OVER(0.5 * ((N(0, 0, 0) + N(0, 1, 0) + N(1, 0, 1) + N(1, 1, 1)) - (N(1, 0, 0) + N(1, 1, 0) + N(0, 0, 1) + N(0, 1, 1))), (hx * hz), (rhx * rhz));
+  sl[5] = BDS_OVER(0.5 * ((N(0, 0, 0) + N(1, 0, 0) + N(0, 1, 1) + N(1, 1, 1)) - (N(0, 0, 1) + N(1, 0, 1) + N(0, 1, 0) + N(1, 1, 0))), (hy * hz), (rhy * rhz));
+  sl[6] = BDS_OVER((-N(0, 0, 0) + N(1, 0, 0) + N(0, 1, 0) + N(0, 0, 1) - N(1, 1, 0) - N(1, 0, 1) - N(0, 1, 1) + N(1, 1, 1)), (hx * hy * hz), (rhx * rhy * rhz));
   double sc[8], smin[8], smax[8];
   // sc(n), n = 1 + 4a + 2b + c with (a,b,c) = 1 for the + side in (x,y,z): bds.f90:405-452
 #pragma unroll
@@ -156,21 +170,23 @@ __global__ void k_bds_slope(BdsArgs a) {
   for (int ll = 0; ll < 3; ++ll)
     bds_pass<8>(sc, smin, smax, s0, 0.125 * (sc[0] + sc[1] + sc[2] + sc[3] + sc[4] + sc[5] + sc[6] + sc[7]));
   const long cs = a.slope.cs;
-  a.slope.p[so] = 0.25 * ((sc[4] + sc[6] + sc[5] + sc[7]) - (sc[0] + sc[2] + sc[1] + sc[3])) / hx;
-  a.slope.p[so + cs] = 0.25 * ((sc[2] + sc[6] + sc[3] + sc[7]) - (sc[0] + sc[4] + sc[1] + sc[5])) / hy;
-  a.slope.p[so + 2 * cs] = 0.25 * ((sc[1] + sc[5] + sc[3] + sc[7]) - (sc[0] + sc[4] + sc[2] + sc[6])) / hz;
-  a.slope.p[so + 3 * cs] = 0.5 * ((sc[0] + sc[1] + sc[6] + sc[7]) - (sc[4] + sc[5] + sc[2] + sc[3])) / (hx * hy);
-  a.slope.p[so + 4 * cs] = 0.5 * ((sc[0] + sc[2] + sc[5] + sc[7]) - (sc[4] + sc[6] + sc[1] + sc[3])) / (hx * hz);
-  a.slope.p[so + 5 * cs] = 0.5 * ((sc[0] + sc[4] + sc[3] + sc[7]) - (sc[1] + sc[5] + sc[2] + sc[6])) / (hy * hz);
-  a.slope.p[so + 6 * cs] = (-sc[0] + sc[4] + sc[2] + sc[1] - sc[6] - sc[5] - sc[3] + sc[7]) / (hx * hy * hz);
+  a.slope.p[so] = BDS_OVER(0.25 * ((sc[4] + sc[6] + sc[5] + sc[7]) - (sc[0] + sc[2] + sc[1] + sc[3])), hx, rhx);
+  a.slope.p[so + cs] = BDS_OVER(0.25 * ((sc[2] + sc[6] + sc[3] + sc[7]) - (sc[0] + sc[4] + sc[1] + sc[5])), hy, rhy);
+  a.slope.p[so + 2 * cs] = BDS_OVER(0.25 * ((sc[1] + sc[5] + sc[3] + sc[7]) - (sc[0] + sc[4] + sc[2] + sc[6])), hz, rhz);
+  a.slope.p[so + 3 * cs] = BDS_OVER(0.5 * ((sc[0] + sc[1] + sc[6] + sc[7]) - (sc[4] + sc[5] + sc[2] + sc[3])), (hx * hy), (rhx * rhy));
+  a.slope.p[so + 4 * cs] = BDS_OVER(0.5 * ((sc[0] + sc[2] + sc[5] + sc[7]) - (sc[4] + sc[6] + sc[1] + sc[3])), (hx * hz), (rhx * rhz));
+  a.slope.p[so + 5 * cs] = BDS_OVER(0.5 * ((sc[0] + sc[4] + sc[3] + sc[7]) - (sc[1] + sc[5] + sc[2] + sc[6])), (hy * hz), (rhy * rhz));
+  a.slope.p[so + 6 * cs] = BDS_OVER((-sc[0] + sc[4] + sc[2] + sc[1] - sc[6] - sc[5] - sc[3] + sc[7]), (hx * hy * hz), (rhx * rhy * rhz));
 }
 
 // polynomial of cell c evaluated at offset del: eval_2d :4204 / eval_3d :4215
 template <int DM>
 __device__ __forceinline__ double bds_eval(const BdsArgs& a, const int* c, const double* del) {
-  const double s = a.s(c[0], c[1], c[2]);
-  const double* sl = a.slope.p + a.slope.off(c[0], c[1], c[2]);
-  const long cs = a.slope.cs;
+  // (component-major slopes: a warp's eight loads touch two cache lines each; interleaving value + slopes per cell as
+  // 64 B records was measured 8 % slower -- four 128-bit loads per cell, each spread over 16 lines per warp)
+  const double s = a.s.p[a.s.off32(c[0], c[1], c[2])];
+  const double* sl = a.slope.p + a.slope.off32(c[0], c[1], c[2]);
+  const int cs = (int)a.slope.cs;
   if (DM == 2) return s + del[0] * sl[0] + del[1] * sl[cs] + del[0] * del[1] * sl[2 * cs];
   return s + del[0] * sl[0] + del[1] * sl[cs] + del[2] * sl[2 * cs] + del[0] * del[1] * sl[3 * cs] +
          del[0] * del[2] * sl[4 * cs] + del[1] * del[2] * sl[5 * cs] + del[0] * del[1] * del[2] * sl[6 * cs];
@@ -179,8 +195,8 @@ __device__ __forceinline__ double bds_eval(const BdsArgs& a, const int* c, const
 // d(velocity_q)/dx_q of cell c
 __device__ __forceinline__ double dvel(const BdsArgs& a, int q, const int* c) {
   const DV& u = a.umac[q];
-  const long o = u.off(c[0], c[1], c[2]);
-  return (u.p[o + u.stride(q)] - u.p[o]) / a.dx[q];
+  const int o = u.off32(c[0], c[1], c[2]);
+  return BDS_OVER((u.p[o + (int)u.stride(q)] - u.p[o]), a.dx[q], a.rdx[q]);
 }
 __device__ __forceinline__ double divu_of(const BdsArgs& a, int dm, const int* c) {
   double r = dvel(a, 0, c) + dvel(a, 1, c);
@@ -189,7 +205,7 @@ __device__ __forceinline__ double divu_of(const BdsArgs& a, int dm, const int* c
 }
 
 template <int DM, int D>
-__global__ void __launch_bounds__(128) k_bds_conc(BdsArgs a) {
+__global__ void __launch_bounds__(128, 4) k_bds_conc(BdsArgs a) {
   int ix[3];
   Box3 fb = a.vb;
   fb.hi[D] += 1;
@@ -198,7 +214,7 @@ __global__ void __launch_bounds__(128) k_bds_conc(BdsArgs a) {
   const double dt2 = dt / 2.0, dt3 = dt / 3.0, dt4 = dt / 4.0;
   const double half = 0.5, sixth = 1.0 / 6.0;
   const double* h = a.dx;
-  auto U = [&](int q, const int* c) { return a.umac[q](c[0], c[1], c[2]); };
+  auto U = [&](int q, const int* c) { return a.umac[q].p[a.umac[q].off32(c[0], c[1], c[2])]; };
   const double vn = U(D, ix);
   double sgn[3] = {0.0, 0.0, 0.0};
   int uc[3] = {ix[0], ix[1], ix[2]};
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(128) k_bds_conc(BdsArgs a) {
   double del[3] = {0.0, 0.0, 0.0};
   del[D] = sgn[D] * 0.5 * h[D] - 0.5 * vn * dt;
   double se = bds_eval<DM>(a, uc, del);
-  const double frc = a.force(uc[0], uc[1], uc[2]);
+  const double frc = a.force.p[a.force.off32(uc[0], uc[1], uc[2])];
   if (a.is_cons) {
     se = se * (1.0 - dt2 * dvel(a, D, uc)) + dt2 * frc;
   } else {
@@ -250,7 +266,7 @@ __global__ void __launch_bounds__(128) k_bds_conc(BdsArgs a) {
 #pragma unroll
       for (int l = 0; l < 3; ++l) del[l] = (p1[l] + p2[l]) / 2.0;
       const double val3 = bds_eval<DM>(a, c2, del);
-      double gamma = (val1 + val2 + val3) / 3.0;
+      double gamma = BDS_OVER((val1 + val2 + val3), 3.0, (1.0 / 3.0));
       if (DM == 2) {
         if (a.is_cons) gamma = gamma * (1.0 - dt3 * divu_of(a, 2, c2));
       } else {
@@ -311,13 +327,13 @@ __global__ void __launch_bounds__(128) k_bds_conc(BdsArgs a) {
           double gamma2 = -0.8 * w1 + 0.45 * (w2 + w3 + w4 + w5);
           if (a.is_cons) gamma2 = gamma2 * (1.0 - dt4 * divu_of(a, 3, c3));
           gamma2 = gamma2 * vr;
-          if (rside) gamma = gamma - dt * gamma2 / (3.0 * h[r]);
-          else gamma = gamma + dt * gamma2 / (3.0 * h[r]);
+          if (rside) gamma = gamma - BDS_OVER(dt * gamma2, (3.0 * h[r]), ((1.0 / 3.0) * a.rdx[r]));
+          else gamma = gamma + BDS_OVER(dt * gamma2, (3.0 * h[r]), ((1.0 / 3.0) * a.rdx[r]));
         }
       }
       gamma = gamma * vt;
-      if (side) se = se - dt * gamma / (2.0 * h[t]);
-      else se = se + dt * gamma / (2.0 * h[t]);
+      if (side) se = se - BDS_OVER(dt * gamma, (2.0 * h[t]), (0.5 * a.rdx[t]));
+      else se = se + BDS_OVER(dt * gamma, (2.0 * h[t]), (0.5 * a.rdx[t]));
     }
   }
   a.sedge[D](ix[0], ix[1], ix[2]) = se;
@@ -325,6 +341,10 @@ __global__ void __launch_bounds__(128) k_bds_conc(BdsArgs a) {
 
 }  // namespace
 
+void BDS_FN(bds_dev)(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
+                     const int* lo, const int* hi, int comp, bool is_cons, int ng_s, int ng_f);
+
+#ifndef MGPU_BDS_FAST
 size_t bds_scratch(const mgpu_params& P, const int* lo, const int* hi) {
   Box3 tb = grown(lo, hi, P.dm, 1);
   Box3 nb = tb;
@@ -333,11 +353,23 @@ size_t bds_scratch(const mgpu_params& P, const int* lo, const int* hi) {
          4096;
 }
 
+static int g_bds_fast = 1;
+void bds_set_fast(int on) { g_bds_fast = on; }
+void bds_dev_fast(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
+                  const int* lo, const int* hi, int comp, bool is_cons, int ng_s, int ng_f);
 void bds_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
              const int* lo, const int* hi, int comp, bool is_cons, int ng_s, int ng_f) {
+  if (g_bds_fast) bds_dev_fast(P, s_full, sedge_full, umac, force_full, lo, hi, comp, is_cons, ng_s, ng_f);
+  else bds_dev_exact(P, s_full, sedge_full, umac, force_full, lo, hi, comp, is_cons, ng_s, ng_f);
+}
+#endif
+
+void BDS_FN(bds_dev)(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,
+                     const int* lo, const int* hi, int comp, bool is_cons, int ng_s, int ng_f) {
   const int dm = P.dm;
   if (ng_s < 3) throw Error("bds: need at least 3 ghost cells");
   if (ng_f < 1) throw Error("bds: force needs at least 1 ghost cell");
+  if (s_full.cs * 8 >= (1L << 31)) throw Error("bds: box too large for the 32-bit cell indices of the kernels");
   BdsArgs a;
   a.dm = dm;
   a.is_cons = is_cons;
@@ -346,6 +378,7 @@ void bds_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* u
     a.lo[d] = d < dm ? lo[d] : 0;
     a.hi[d] = d < dm ? hi[d] : 0;
     a.dx[d] = P.dx[d < dm ? d : 0];
+    a.rdx[d] = 1.0 / a.dx[d];
     if (d < dm) {
       a.umac[d] = umac[d];
       a.sedge[d] = sedge_full[d].comp(comp);
@@ -367,8 +400,12 @@ void bds_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* u
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
-    const dim3 nb = grid3(fb, 128);
-    const int bt = block3(fb, 128);
+    // x-face boxes are nx + 1 wide: a power-of-two block would leave a third of the last block's threads idle
+    const int nxf = fb.hi[0] - fb.lo[0] + 1;
+    int bt = 128;
+    for (int b = 128; b >= 32; b -= 32)
+      if ((nxf + b - 1) / b * b < (nxf + bt - 1) / bt * bt) bt = b;
+    const dim3 nb((unsigned)((nxf + bt - 1) / bt), (unsigned)(fb.hi[1] - fb.lo[1] + 1), (unsigned)(fb.hi[2] - fb.lo[2] + 1));
     if (dm == 2) {
       if (d == 0) MGPU_TIMED(TAG_BDS, (k_bds_conc<2, 0><<<nb, bt, 0, st>>>(a)));
       else MGPU_TIMED(TAG_BDS, (k_bds_conc<2, 1><<<nb, bt, 0, st>>>(a)));

@@ -9,4 +9,7 @@ void bds_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* u
              const int* lo, const int* hi, int comp, bool is_cons, int ng_s, int ng_f);
 size_t bds_scratch(const mgpu_params& P, const int* lo, const int* hi);
 
+// 1 (default): the FAST build of the kernels (FMA, reciprocals; <= 1e-12); 0: the bit-identical build
+void bds_set_fast(int on);
+
 }  // namespace mgpu

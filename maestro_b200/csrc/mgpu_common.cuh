@@ -24,6 +24,8 @@ struct DV {
   __host__ __device__ inline long off(int i, int j, int k) const {
     return (long)(i - lo[0]) + (long)n[0] * ((long)(j - lo[1]) + (long)n[1] * (long)(k - lo[2]));
   }
+  // 32-bit element index for fabs below 2^31 elements (the caller checks): half the integer work of off()
+  __host__ __device__ inline int off32(int i, int j, int k) const { return (i - lo[0]) + n[0] * ((j - lo[1]) + n[1] * (k - lo[2])); }
   __host__ __device__ inline long stride(int d) const { return d == 0 ? 1 : (d == 1 ? (long)n[0] : (long)n[0] * n[1]); }
   __device__ inline double& operator()(int i, int j, int k) const { return p[off(i, j, k)]; }
   __device__ inline double& operator()(int i, int j, int k, int c) const { return p[off(i, j, k) + cs * c]; }
