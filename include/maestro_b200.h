@@ -373,6 +373,25 @@ int mgpu_density_advance_mf(const mgpu_params* p, int which_step, int nfabs, mgp
                             const double* p0_dummy, const double* rho0_predicted_edge, const int* adv_bc,
                             const int* pmask);
 
+/* The other three planar episodes over the nfabs boxes of this rank (arrays of nfabs fabs; umac / sedge / sflux: dm arrays
+ * of nfabs fabs; adv_bc / phys_bc: the DOMAIN's tables, the per-box ones are derived): the single-box episodes stage by
+ * stage, every ghost fill through the multifab fill.  enthalpy_advance: predict_rhoh / predict_rhohprime / predict_h. */
+int mgpu_velocity_advance_mf(const mgpu_params* p, int nfabs, const mgpu_fab* uold, mgpu_fab* unew, const mgpu_fab* sold,
+                             const mgpu_fab* rhohalf, mgpu_fab* const* umac, const mgpu_fab* gpi, const double* w0,
+                             const double* w0_force, const double* rho0_old, const double* rho0_nph,
+                             const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
+                             const int* adv_bc, const int* pmask);
+int mgpu_advance_premac_mf(const mgpu_params* p, int nfabs, const mgpu_fab* uold, const mgpu_fab* sold,
+                           mgpu_fab* const* umac, const mgpu_fab* gpi, const double* w0, const double* w0_force,
+                           const double* rho0_old, const double* grav_cell_old, const int* adv_bc, const int* phys_bc,
+                           const int* pmask);
+int mgpu_enthalpy_advance_mf(const mgpu_params* p, int which_step, int nfabs, mgpu_fab* sold, mgpu_fab* snew,
+                             mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
+                             const mgpu_fab* thermal, mgpu_fab* const* umac, const double* w0, const double* rho0_old,
+                             const double* rhoh0_old, const double* rho0_new, const double* rhoh0_new,
+                             const double* p0_old, const double* p0_new, const double* psi, const double* grav_old,
+                             const double* grav_nph, const int* adv_bc, const int* pmask);
+
 /* ---- force builders inside the L4 drivers ----------------------------------------
  * mkrhohforce (Source/mkscalforce.f90:31; _2d :249, _3d :310), planar: writes comp rhoh_comp of scal_force on the
  * valid cells (the caller follows with mgpu_fill_boundary, mkscalforce.f90:177).  grav is the 1-D array

@@ -205,6 +205,10 @@ MULTIBOX = {
     "mgpu_fill_boundary_mf": (C.c_int, [P_, C.c_int, F_, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p]),
     "mgpu_density_advance_mf": (C.c_int, [P_, C.c_int, C.c_int, F_, F_, FF_, FF_, F_, FF_, c_double_p, F_]
                                 + [c_double_p] * 4 + [c_int_p] * 2),
+    "mgpu_velocity_advance_mf": (C.c_int, [P_, C.c_int, F_, F_, F_, F_, FF_, F_] + [c_double_p] * 6 + [F_] + [c_int_p] * 2),
+    "mgpu_advance_premac_mf": (C.c_int, [P_, C.c_int, F_, F_, FF_, F_] + [c_double_p] * 4 + [c_int_p] * 3),
+    "mgpu_enthalpy_advance_mf": (C.c_int, [P_, C.c_int, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_] + [c_double_p] * 10
+                                 + [c_int_p] * 2),
 }
 
 # symbols only the library has

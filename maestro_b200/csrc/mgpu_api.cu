@@ -1393,6 +1393,284 @@ static void enthalpy_advance_dev(const mgpu_params& P, int which_step, DV& sold,
   fill_boundary_dev(P, snew, lo, hi, ng_s, nullptr, P.rhoh_comp, dm + P.rhoh_comp, 1, adv_bc, pmask, false);
 }
 
+// ---- the other three L4 episodes over several boxes of one rank (planar) -----------------------------------------------
+// Same statements as the single-box episodes above, stage by stage over the boxes, every ghost fill through the
+// multifab fill (box-to-box copies, periodic images, per-box physical BCs).  B.bc[i] is box i's adv_bc table.
+struct MfBase {  // base-state arrays of one level on the device
+  const double *w0, *w0_force, *rho0_a, *rho0_b, *grav_a, *grav_b;
+};
+static void vel_force_box(const mgpu_params& P, DV& force, bool is_final, const DV& uold, const DV* uedge, const double* w0,
+                          const DV& gpi, const DV& rho1, const double* rho0, const double* grav, const double* w0_force,
+                          const int* lo, const int* hi) {
+  VelForceArgs a;
+  a.dm = P.dm;
+  a.nr = P.nr;
+  a.is_final_update = is_final;
+  a.add_utilde = true;
+  a.dr = P.dx[P.dm - 1];
+  a.rho_cut = P.buoyancy_cutoff_factor * P.base_cutoff_density;
+  a.omega = P.omega; a.sin_theta = P.sin_theta; a.cos_theta = P.cos_theta; a.rotation_radius = P.rotation_radius;
+  a.vb = grown(lo, hi, P.dm, 0);
+  a.force = force; a.uold = uold; a.gpi = gpi; a.rho = rho1;
+  for (int d = 0; d < P.dm; ++d) a.uedge[d] = uedge[d];
+  a.w0 = w0; a.rho0 = rho0; a.grav = grav; a.w0_force = w0_force;
+  mk_vel_force_dev(a);
+}
+static void fill_faces_mf(const mgpu_params& P, const BoxSet& B, std::vector<DV>* u, const int* pmask) {
+  for (int d = 0; d < P.dm; ++d) fill_mf(P, B, u[d], 1, NODAL_OF[d], 1, 1, 1, pmask);
+}
+static void faces_of(std::vector<DV>* f, int i, int dm, DV* out) {
+  for (int d = 0; d < dm; ++d) out[d] = f[d][i];
+}
+
+// velocity_advance (velocity_advance.f90:16) over the boxes
+static void velocity_advance_mf_dev(const mgpu_params& P, const BoxSet& B, std::vector<DV>& uold, std::vector<DV>& unew,
+                                    std::vector<DV>& sold, std::vector<DV>& rhohalf, std::vector<DV>* umac,
+                                    std::vector<DV>& gpi, std::vector<DV>& sponge, const double* w0_h,
+                                    const double* w0_force_h, const double* rho0_old_h, const double* rho0_nph_h,
+                                    const double* grav_old_h, const double* grav_nph_h, int ng_u, const int* pmask) {
+  const int dm = P.dm, nr = P.nr, nf = B.n;
+  const int ng_f = P.ppm_trace_forces == 0 ? 1 : ng_u;  // :69-75
+  const double* w0 = upload_small(w0_h, nr + 1);
+  const double* w0_force = upload_small(w0_force_h, nr);
+  const double* rho0_old = upload_small(rho0_old_h, nr);
+  const double* rho0_nph = upload_small(rho0_nph_h, nr);
+  const double* grav_old = upload_small(grav_old_h, nr);
+  const double* grav_nph = upload_small(grav_nph_h, nr);
+  int z3[3] = {0, 0, 0};
+  std::vector<DV> force(nf), uedge[3];
+  for (int i = 0; i < nf; ++i) force[i] = arena_fab(B.lo[i], B.hi[i], dm, ng_f, z3, dm);
+  for (int d = 0; d < dm; ++d) {
+    uedge[d].resize(nf);
+    for (int i = 0; i < nf; ++i) uedge[d][i] = arena_fab(B.lo[i], B.hi[i], dm, 0, NODAL_D[d], dm);
+  }
+  auto force_stage = [&](bool is_final, std::vector<DV>& rho_src, int rho_c, const double* rho0, const double* grav) {
+    for (int i = 0; i < nf; ++i) {
+      DV u[3];
+      faces_of(umac, i, dm, u);
+      vel_force_box(P, force[i], is_final, uold[i], u, w0, gpi[i], rho_src[i].comp(rho_c), rho0, grav, w0_force, B.lo[i],
+                    B.hi[i]);
+    }
+    fill_mf(P, B, force, ng_f, nullptr, 1, 1, dm, pmask);  // mkforce.f90:209
+  };
+  auto addw0_stage = [&](double mult) {
+    for (int i = 0; i < nf; ++i) {
+      DV u[3];
+      faces_of(umac, i, dm, u);
+      addw0_dev(P, u, w0, mult, B.lo[i], B.hi[i]);
+    }
+    fill_faces_mf(P, B, umac, pmask);
+  };
+  force_stage(false, sold, P.rho_comp - 1, rho0_old, grav_old);  // :80
+  addw0_stage(1.0);                                              // :90
+  for (int i = 0; i < nf; ++i) {                                 // :102-109
+    DV u[3], ue[3];
+    faces_of(umac, i, dm, u);
+    faces_of(uedge, i, dm, ue);
+    for (int c = 0; c < dm; ++c) {
+      size_t mark = arena_mark();
+      if (P.bds_type != 0) bds_dev(P, uold[i], ue, u, force[i], B.lo[i], B.hi[i], c, false, ng_u, ng_f);
+      else edge_one_comp(P, uold[i], ue, u, force[i], B.lo[i], B.hi[i], B.bc[i], c, 1 + c, true, false, ng_u, ng_f);
+      arena_release(mark);
+    }
+  }
+  addw0_stage(-1.0);                                            // :115
+  force_stage(true, rhohalf, 0, rho0_nph, grav_nph);            // :122
+  for (int i = 0; i < nf; ++i) {                                // :132
+    VelArgs a;
+    a.dm = dm;
+    a.do_sponge = P.do_sponge != 0;
+    a.dt = P.dt;
+    for (int d = 0; d < 3; ++d) a.dx[d] = P.dx[d];
+    a.vb = grown(B.lo[i], B.hi[i], dm, 0);
+    a.uold = uold[i]; a.unew = unew[i]; a.force = force[i]; a.sponge = sponge[i];
+    for (int d = 0; d < dm; ++d) { a.umac[d] = umac[d][i]; a.uedge[d] = uedge[d][i]; }
+    a.w0 = w0;
+    update_velocity_dev(a);
+  }
+  fill_mf(P, B, unew, ng_u, nullptr, 1, 1, dm, pmask);  // update_vel.f90:121
+}
+
+// advance_premac (advance_premac.f90:21) over the boxes; phys[i]: box i's phys_bc table
+static void advance_premac_mf_dev(const mgpu_params& P, const BoxSet& B, const std::vector<const int*>& phys,
+                                  std::vector<DV>& uold, std::vector<DV>& sold, std::vector<DV>* umac, std::vector<DV>& gpi,
+                                  const double* w0_h, const double* w0_force_h, const double* rho0_old_h,
+                                  const double* grav_h, int ng_u, const int* pmask) {
+  const int dm = P.dm, nr = P.nr, nf = B.n;
+  const int ng_f = P.ppm_trace_forces == 1 ? ng_u : 1;  // :62-66
+  const double* w0 = upload_small(w0_h, nr + 1);
+  const double* w0_force = upload_small(w0_force_h, nr);
+  const double* rho0_old = upload_small(rho0_old_h, nr);
+  const double* grav = upload_small(grav_h, nr);
+  int z3[3] = {0, 0, 0};
+  std::vector<DV> ufull(nf), force(nf), utrans[3];
+  for (int i = 0; i < nf; ++i) {
+    ufull[i] = arena_fab(B.lo[i], B.hi[i], dm, ng_u, z3, dm);
+    force[i] = arena_fab(B.lo[i], B.hi[i], dm, ng_f, z3, dm);
+  }
+  for (int d = 0; d < dm; ++d) {
+    utrans[d].resize(nf);
+    for (int i = 0; i < nf; ++i) utrans[d][i] = arena_fab(B.lo[i], B.hi[i], dm, 1, NODAL_D[d], 1);
+  }
+  for (int i = 0; i < nf; ++i) radial_cell_avg_dev(P, ufull[i], w0, B.lo[i], B.hi[i]);  // :75
+  fill_mf(P, B, ufull, ng_u, nullptr, 1, 1, dm, pmask);
+  for (int i = 0; i < nf; ++i) {  // :76-78
+    if (ufull[i].size() != uold[i].size()) throw Error("advance_premac: uold must carry the ghost cells of the state");
+    add_dev(ufull[i].p, uold[i].p, ufull[i].size());
+  }
+  for (int i = 0; i < nf; ++i) {  // :90
+    DV ut[3];
+    faces_of(utrans, i, dm, ut);
+    mkutrans_dev(P, uold[i], ufull[i], ut, w0, B.lo[i], B.hi[i], B.bc[i], phys[i], ng_u);
+  }
+  fill_faces_mf(P, B, utrans, pmask);
+  for (int i = 0; i < nf; ++i) {  // :98
+    DV ut[3];
+    faces_of(utrans, i, dm, ut);
+    vel_force_box(P, force[i], false, uold[i], ut, w0, gpi[i], sold[i].comp(P.rho_comp - 1), rho0_old, grav, w0_force,
+                  B.lo[i], B.hi[i]);
+  }
+  fill_mf(P, B, force, ng_f, nullptr, 1, 1, dm, pmask);
+  for (int i = 0; i < nf; ++i) {  // :109
+    DV ut[3];
+    faces_of(utrans, i, dm, ut);
+    addw0_dev(P, ut, w0, 1.0, B.lo[i], B.hi[i]);
+  }
+  fill_faces_mf(P, B, utrans, pmask);
+  for (int i = 0; i < nf; ++i) {  // :116
+    DV ut[3], um[3];
+    faces_of(utrans, i, dm, ut);
+    faces_of(umac, i, dm, um);
+    size_t mark = arena_mark();
+    velpred_dev(P, uold[i], ufull[i], um, ut, force[i], w0, B.lo[i], B.hi[i], B.bc[i], phys[i], ng_u, ng_f);
+    arena_release(mark);
+  }
+}
+
+// enthalpy_advance (enthalpy_advance.f90:16) over the boxes: predict_rhoh / predict_rhohprime / predict_h (the
+// temperature-based predictions take one box per rank)
+static void enthalpy_advance_mf_dev(const mgpu_params& P, int which_step, const BoxSet& B, std::vector<DV>& sold,
+                                    std::vector<DV>& snew, std::vector<DV>* sedge, std::vector<DV>* sflux,
+                                    std::vector<DV>& scal_force, std::vector<DV>& thermal, std::vector<DV>* umac,
+                                    const double* w0_h, const double* rho0_old_h, const double* rhoh0_old_h,
+                                    const double* rho0_new_h, const double* rhoh0_new_h, const double* p0_old_h,
+                                    const double* p0_new_h, const double* psi_h, const double* grav_old_h,
+                                    const double* grav_nph_h, int ng_s, int ng_f, const int* pmask) {
+  const int dm = P.dm, nr = P.nr, nf = B.n;
+  const int ept = P.enthalpy_pred_type;
+  const int foextrap_comp = dm + P.nscal + 2;
+  if (ept == MGPU_PREDICT_HPRIME) throw Error("mk_rhoh_flux : predict_hprime not coded yet");  // mkflux.f90:1167
+  if (!(ept == MGPU_PREDICT_RHOH || ept == MGPU_PREDICT_RHOHPRIME || ept == MGPU_PREDICT_H))
+    throw Error("enthalpy_advance over several boxes: the temperature-based predictions take one box per rank");
+  std::vector<double> e[4] = {std::vector<double>(nr + 1), std::vector<double>(nr + 1), std::vector<double>(nr + 1),
+                              std::vector<double>(nr + 1)};
+  cell_to_edge_host(rho0_old_h, e[0].data(), nr);  // :114-117
+  cell_to_edge_host(rho0_new_h, e[1].data(), nr);
+  cell_to_edge_host(rhoh0_old_h, e[2].data(), nr);
+  cell_to_edge_host(rhoh0_new_h, e[3].data(), nr);
+  const double* w0 = upload_small(w0_h, nr + 1);
+  const double* rho0_old = upload_small(rho0_old_h, nr);
+  const double* rho0_new = upload_small(rho0_new_h, nr);
+  const double* rhoh0_old = upload_small(rhoh0_old_h, nr);
+  const double* rhoh0_new = upload_small(rhoh0_new_h, nr);
+  const double* p0_old = upload_small(p0_old_h, nr);
+  const double* p0_new = upload_small(p0_new_h, nr);
+  const double* psi = upload_small(psi_h, nr);
+  const double* grav_old = upload_small(grav_old_h, nr);
+  const double* grav_nph = upload_small(grav_nph_h, nr);
+  const double* r0e_old = upload_small(e[0].data(), nr + 1);
+  const double* r0e_new = upload_small(e[1].data(), nr + 1);
+  const double* rh0e_old = upload_small(e[2].data(), nr + 1);
+  const double* rh0e_new = upload_small(e[3].data(), nr + 1);
+  const int rhoh = P.rhoh_comp - 1, rho = P.rho_comp - 1;
+  auto rhoh_force = [&](bool is_pred, const double* p02, const double* r02, const double* grav, bool add_thermal) {
+    for (int i = 0; i < nf; ++i) {
+      RhohForceArgs a;
+      a.dm = dm; a.nr = nr; a.cutoff_coord = P.base_cutoff_density_coord;
+      a.with_psi = (is_pred && (ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_RHOH)) || !is_pred;
+      a.add_thermal = add_thermal;
+      a.dr = P.dx[dm - 1];
+      a.vb = grown(B.lo[i], B.hi[i], dm, 0);
+      a.f = scal_force[i].comp(rhoh); a.thermal = thermal[i]; a.wm = umac[dm - 1][i];
+      a.p0_1 = p0_old; a.p0_2 = p02; a.rho0_1 = rho0_old; a.rho0_2 = r02; a.grav = grav; a.psi = psi;
+      mkrhohforce_dev(a);
+    }
+    fill_mf(P, B, scal_force, ng_f, nullptr, P.rhoh_comp, foextrap_comp, 1, pmask);
+  };
+  auto rhoh_to_h = [&](bool flag) {  // convert_rhoh_to_h
+    for (int i = 0; i < nf; ++i) comp_muldiv_dev(P, sold[i], rhoh, sold[i], rho, flag ? 0 : 1, 0, B.lo[i], B.hi[i]);
+    fill_mf(P, B, sold, ng_s, nullptr, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, pmask);
+  };
+  auto pert = [&](bool flag) {
+    for (int i = 0; i < nf; ++i) put_in_pert_form_dev(P, sold[i], rhoh0_old, P.rhoh_comp, flag, B.lo[i], B.hi[i]);
+    fill_mf(P, B, sold, ng_s, nullptr, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, pmask);
+  };
+  auto addw0_stage = [&](double mult) {
+    for (int i = 0; i < nf; ++i) {
+      DV u[3];
+      faces_of(umac, i, dm, u);
+      addw0_dev(P, u, w0, mult, B.lo[i], B.hi[i]);
+    }
+    fill_faces_mf(P, B, umac, pmask);
+  };
+  if (ept == MGPU_PREDICT_H) rhoh_to_h(true);  // :122-126
+  for (int i = 0; i < nf; ++i) set_dev(scal_force[i].p, 0.0, scal_force[i].size());  // :132-134
+  rhoh_force(true, p0_old, rho0_old, grav_old, true);
+  if (ept == MGPU_PREDICT_RHOHPRIME) {  // :153-156
+    for (int i = 0; i < nf; ++i) {
+      DV u[3];
+      faces_of(umac, i, dm, u);
+      modify_scal_force_dev(P, scal_force[i], sold[i], u, rhoh0_old, rh0e_old, w0, P.rhoh_comp, false, B.lo[i], B.hi[i],
+                            g_opt_exact == 0);
+    }
+    fill_mf(P, B, scal_force, ng_f, nullptr, P.rhoh_comp, foextrap_comp, 1, pmask);
+  } else if (ept == MGPU_PREDICT_H) {  // :173-178
+    for (int i = 0; i < nf; ++i) comp_muldiv_dev(P, scal_force[i], rhoh, sold[i], rho, 0, 1, B.lo[i], B.hi[i]);
+  }
+  addw0_stage(1.0);                               // :201
+  if (ept == MGPU_PREDICT_RHOHPRIME) pert(true);  // :204-208
+  for (int i = 0; i < nf; ++i) {                  // :232-254
+    const bool cons = (ept == MGPU_PREDICT_RHOH);
+    DV u[3], se[3];
+    faces_of(umac, i, dm, u);
+    faces_of(sedge, i, dm, se);
+    size_t mark = arena_mark();
+    if (P.bds_type != 0) bds_dev(P, sold[i], se, u, scal_force[i], B.lo[i], B.hi[i], rhoh, cons, ng_s, ng_f);
+    else edge_one_comp(P, sold[i], se, u, scal_force[i], B.lo[i], B.hi[i], B.bc[i], rhoh, dm + P.rhoh_comp, false, cons, ng_s,
+                       ng_f);
+    arena_release(mark);
+  }
+  if (ept == MGPU_PREDICT_RHOHPRIME) pert(false);  // :257-261
+  if (ept == MGPU_PREDICT_H) rhoh_to_h(false);     // :272-276
+  addw0_stage(-1.0);                               // :293
+  const bool s1 = (which_step == 1);
+  for (int i = 0; i < nf; ++i) {  // :326 / :375
+    FluxArgs fa;
+    fill_flux_args(P, fa, B.lo[i], B.hi[i]);
+    for (int d = 0; d < dm; ++d) { fa.sflux[d] = sflux[d][i]; fa.sedge[d] = sedge[d][i]; fa.umac[d] = umac[d][i]; }
+    fa.w0 = w0;
+    fa.rho0_old = rho0_old; fa.rho0_edge_old = r0e_old;
+    fa.rho0_new = s1 ? rho0_old : rho0_new; fa.rho0_edge_new = s1 ? r0e_old : r0e_new;
+    fa.rhoh0_old = rhoh0_old; fa.rhoh0_edge_old = rh0e_old;
+    fa.rhoh0_new = s1 ? rhoh0_old : rhoh0_new; fa.rhoh0_edge_new = s1 ? rh0e_old : rh0e_new;
+    mk_rhoh_flux_dev(P, fa);
+  }
+  for (int i = 0; i < nf; ++i) set_dev(scal_force[i].p + scal_force[i].cs * rhoh, 0.0, scal_force[i].cs);  // :401-403
+  rhoh_force(false, s1 ? p0_old : p0_new, s1 ? rho0_old : rho0_new, s1 ? grav_old : grav_nph, false);  // :405-416
+  for (int i = 0; i < nf; ++i) {  // :431
+    UpdArgs ua;
+    ua.dm = dm;
+    ua.dt = P.dt;
+    for (int d = 0; d < 3; ++d) ua.dx[d] = P.dx[d];
+    ua.vb = grown(B.lo[i], B.hi[i], dm, 0);
+    ua.sold = sold[i]; ua.snew = snew[i]; ua.force = scal_force[i];
+    for (int d = 0; d < dm; ++d) ua.sflux[d] = sflux[d][i];
+    ua.p0_new = p0_new;
+    update_scal_dev(P, ua, P.rhoh_comp, P.rhoh_comp);
+  }
+  fill_mf(P, B, snew, ng_s, nullptr, P.rhoh_comp, dm + P.rhoh_comp, 1, pmask);
+}
+
 // which components of the caller's fabs an enthalpy_advance episode reads / writes (host-pointer calls copy only these)
 struct EnthalpyMasks {
   cmask_t mrhoh, sold_in, sold_out, snew_in, sedge_in, sedge_out, force_out;
@@ -2053,6 +2331,134 @@ int mgpu_density_advance_mf(const mgpu_params* p, int which_step, int nfabs, mgp
   }
   density_advance_mf_dev(*p, which_step, B, so, sn, se, sf, fv, um, w0, et, rho0_old, rho0_new, rho0_predicted_edge,
                          sold[0].ng, scal_force[0].ng, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+// per-box phys_bc tables: a side that is not on the domain boundary is INTERIOR
+static void box_phys_tables(const mgpu_params& P, int nfabs, const mgpu_fab* f, const int* phys_bc, std::vector<std::vector<int>>& out) {
+  const int dm = P.dm;
+  out.assign(nfabs, std::vector<int>(phys_bc, phys_bc + dm * 2));
+  for (int i = 0; i < nfabs; ++i)
+    for (int d = 0; d < dm; ++d) {
+      if (f[i].lo[d] != P.domlo[d]) out[i][d] = MGPU_BC_INTERIOR;
+      if (f[i].hi[d] != P.domhi[d]) out[i][d + dm] = MGPU_BC_INTERIOR;
+    }
+}
+static size_t boxset_scratch(int nfabs) { return (size_t)nfabs * nfabs * 27 * 256 * 16 + 65536; }
+static void mf_check(const mgpu_params* p, int nfabs, const char* who) {
+  if (p->spherical) throw Error(std::string(who) + ": spherical geometry takes one box per rank");
+  if (nfabs < 1) throw Error(std::string(who) + ": nfabs must be at least 1");
+}
+
+int mgpu_velocity_advance_mf(const mgpu_params* p, int nfabs, const mgpu_fab* uold, mgpu_fab* unew, const mgpu_fab* sold,
+                             const mgpu_fab* rhohalf, mgpu_fab* const* umac, const mgpu_fab* gpi, const double* w0,
+                             const double* w0_force, const double* rho0_old, const double* rho0_nph,
+                             const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
+                             const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  mf_check(p, nfabs, "mgpu_velocity_advance_mf");
+  const int dm = p->dm;
+  size_t scratch = 0, edge = 0;
+  for (int i = 0; i < nfabs; ++i) {
+    const int ng_f = p->ppm_trace_forces == 0 ? 1 : uold[i].ng;
+    scratch += fab_bytes(uold[i].lo, uold[i].hi, dm, ng_f, 0, dm) + dm * fab_bytes(uold[i].lo, uold[i].hi, dm, 0, 1, dm);
+    edge = std::max(edge, std::max(make_edge_scal_scratch(*p, uold[i].lo, uold[i].hi), bds_scratch(*p, uold[i].lo, uold[i].hi)));
+  }
+  Call c(p, scratch + edge + (size_t)(8 * (p->nr + 2)) * sizeof(double) + boxset_scratch(nfabs));
+  std::vector<std::vector<int>> bcs;
+  box_bc_tables(*p, nfabs, uold, adv_bc, bcs);
+  BoxSet B;
+  B.n = nfabs;
+  std::vector<DV> uo(nfabs), un(nfabs), so(nfabs), rh(nfabs), gp(nfabs), sp(nfabs), um[3];
+  for (int d = 0; d < dm; ++d) um[d].resize(nfabs);
+  for (int i = 0; i < nfabs; ++i) {
+    B.lo.push_back(uold[i].lo); B.hi.push_back(uold[i].hi); B.bc.push_back(bcs[i].data());
+    uo[i] = c.view(uold[i], true, false);
+    un[i] = c.view(unew[i], true, true);
+    so[i] = c.view(sold[i], crange(p->rho_comp - 1, 1), (cmask_t)0);
+    rh[i] = c.view(rhohalf[i], true, false);
+    gp[i] = c.view(gpi[i], true, false);
+    sp[i] = c.view(sponge[i], true, false);
+    for (int d = 0; d < dm; ++d) um[d][i] = c.view(umac[d][i], true, true);
+  }
+  velocity_advance_mf_dev(*p, B, uo, un, so, rh, um, gp, sp, w0, w0_force, rho0_old, rho0_nph, grav_cell_old, grav_cell_nph,
+                          uold[0].ng, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_advance_premac_mf(const mgpu_params* p, int nfabs, const mgpu_fab* uold, const mgpu_fab* sold,
+                           mgpu_fab* const* umac, const mgpu_fab* gpi, const double* w0, const double* w0_force,
+                           const double* rho0_old, const double* grav_cell_old, const int* adv_bc, const int* phys_bc,
+                           const int* pmask) {
+  MGPU_TRY
+  mf_check(p, nfabs, "mgpu_advance_premac_mf");
+  const int dm = p->dm;
+  size_t scratch = 0, vp = 0;
+  for (int i = 0; i < nfabs; ++i) {
+    const int ng_u = uold[i].ng, ng_f = p->ppm_trace_forces == 1 ? ng_u : 1;
+    scratch += fab_bytes(uold[i].lo, uold[i].hi, dm, ng_u, 0, dm) + fab_bytes(uold[i].lo, uold[i].hi, dm, ng_f, 0, dm) +
+               dm * fab_bytes(uold[i].lo, uold[i].hi, dm, 1, 1, 1);
+    vp = std::max(vp, velpred_scratch(*p, uold[i].lo, uold[i].hi));
+  }
+  Call c(p, scratch + vp + (size_t)(8 * (p->nr + 2)) * sizeof(double) + boxset_scratch(nfabs));
+  std::vector<std::vector<int>> bcs, phs;
+  box_bc_tables(*p, nfabs, uold, adv_bc, bcs);
+  box_phys_tables(*p, nfabs, uold, phys_bc, phs);
+  BoxSet B;
+  B.n = nfabs;
+  std::vector<const int*> phys;
+  std::vector<DV> uo(nfabs), so(nfabs), gp(nfabs), um[3];
+  for (int d = 0; d < dm; ++d) um[d].resize(nfabs);
+  for (int i = 0; i < nfabs; ++i) {
+    B.lo.push_back(uold[i].lo); B.hi.push_back(uold[i].hi); B.bc.push_back(bcs[i].data());
+    phys.push_back(phs[i].data());
+    uo[i] = c.view(uold[i], true, false);
+    so[i] = c.view(sold[i], crange(p->rho_comp - 1, 1), (cmask_t)0);
+    gp[i] = c.view(gpi[i], true, false);
+    for (int d = 0; d < dm; ++d) um[d][i] = c.view(umac[d][i], true, true);
+  }
+  advance_premac_mf_dev(*p, B, phys, uo, so, um, gp, w0, w0_force, rho0_old, grav_cell_old, uold[0].ng, pmask);
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_enthalpy_advance_mf(const mgpu_params* p, int which_step, int nfabs, mgpu_fab* sold, mgpu_fab* snew,
+                             mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
+                             const mgpu_fab* thermal, mgpu_fab* const* umac, const double* w0, const double* rho0_old,
+                             const double* rhoh0_old, const double* rho0_new, const double* rhoh0_new,
+                             const double* p0_old, const double* p0_new, const double* psi, const double* grav_old,
+                             const double* grav_nph, const int* adv_bc, const int* pmask) {
+  MGPU_TRY
+  mf_check(p, nfabs, "mgpu_enthalpy_advance_mf");
+  const int dm = p->dm;
+  size_t edge = 0;
+  for (int i = 0; i < nfabs; ++i)
+    edge = std::max(edge, std::max(make_edge_scal_scratch(*p, sold[i].lo, sold[i].hi), bds_scratch(*p, sold[i].lo, sold[i].hi)));
+  Call c(p, edge + (size_t)(16 * (p->nr + 2)) * sizeof(double) + boxset_scratch(nfabs));
+  std::vector<std::vector<int>> bcs;
+  box_bc_tables(*p, nfabs, sold, adv_bc, bcs);
+  const EnthalpyMasks m = enthalpy_masks(*p);
+  BoxSet B;
+  B.n = nfabs;
+  std::vector<DV> so(nfabs), sn(nfabs), fv(nfabs), th(nfabs), se[3], sf[3], um[3];
+  for (int d = 0; d < dm; ++d) { se[d].resize(nfabs); sf[d].resize(nfabs); um[d].resize(nfabs); }
+  for (int i = 0; i < nfabs; ++i) {
+    B.lo.push_back(sold[i].lo); B.hi.push_back(sold[i].hi); B.bc.push_back(bcs[i].data());
+    so[i] = c.view(sold[i], m.sold_in, m.sold_out);
+    sn[i] = c.view(snew[i], m.snew_in, m.mrhoh);
+    fv[i] = c.view(scal_force[i], (cmask_t)0, m.force_out);
+    c.zero_on_host(scal_force[i], ~m.force_out);
+    th[i] = c.view(thermal[i], true, false);
+    for (int d = 0; d < dm; ++d) {
+      se[d][i] = c.view(sedge[d][i], m.sedge_in | (sedge[d][i].ng > 0 ? m.sedge_out : (cmask_t)0), m.sedge_out);
+      sf[d][i] = c.view(sflux[d][i], (cmask_t)0, m.mrhoh);
+      um[d][i] = c.view(umac[d][i], true, true);
+    }
+  }
+  enthalpy_advance_mf_dev(*p, which_step, B, so, sn, se, sf, fv, th, um, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old,
+                          p0_new, psi, grav_old, grav_nph, sold[0].ng, scal_force[0].ng, pmask);
   c.finish();
   MGPU_CATCH
 }

@@ -164,3 +164,43 @@ def density_advance_mf(p, which_step, sold, snew, sedge, sflux, scal_force, umac
     _chk(load().mgpu_density_advance_mf(C.byref(p), which_step, len(sold), _fab_array(sold), _fab_array(snew), se, sf,
                                         _fab_array(scal_force), um, keep[0][1], _fab_array(etarhoflux), keep[1][1],
                                         keep[2][1], keep[3][1], keep[4][1], bcp, pmp))
+
+
+def velocity_advance_mf(p, uold, unew, sold, rhohalf, umac, gpi, w0, w0_force, rho0_old, rho0_nph, grav_cell_old,
+                        grav_cell_nph, sponge, adv_bc, pmask):
+    """velocity_advance over lists of boxes (umac: dm lists of boxes); adv_bc = the domain's table"""
+    from .fab import as_double_p, as_int_p
+
+    keep = [as_double_p(x) for x in (w0, w0_force, rho0_old, rho0_nph, grav_cell_old, grav_cell_nph)]
+    bc, bcp = as_int_p(adv_bc)
+    pm, pmp = as_int_p(pmask)
+    um, k1 = _fab_arrays(umac)
+    _chk(load().mgpu_velocity_advance_mf(C.byref(p), len(uold), _fab_array(uold), _fab_array(unew), _fab_array(sold),
+                                         _fab_array(rhohalf), um, _fab_array(gpi), *[k[1] for k in keep],
+                                         _fab_array(sponge), bcp, pmp))
+
+
+def advance_premac_mf(p, uold, sold, umac, gpi, w0, w0_force, rho0_old, grav_cell_old, adv_bc, phys_bc, pmask):
+    """advance_premac over lists of boxes; adv_bc / phys_bc = the domain's tables"""
+    from .fab import as_double_p, as_int_p
+
+    keep = [as_double_p(x) for x in (w0, w0_force, rho0_old, grav_cell_old)]
+    ints = [as_int_p(x) for x in (adv_bc, phys_bc, pmask)]
+    um, k1 = _fab_arrays(umac)
+    _chk(load().mgpu_advance_premac_mf(C.byref(p), len(uold), _fab_array(uold), _fab_array(sold), um, _fab_array(gpi),
+                                       *[k[1] for k in keep], *[k[1] for k in ints]))
+
+
+def enthalpy_advance_mf(p, which_step, sold, snew, sedge, sflux, scal_force, thermal, umac, w0, rho0_old, rhoh0_old,
+                        rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old, grav_nph, adv_bc, pmask):
+    """enthalpy_advance over lists of boxes (predict_rhoh / predict_rhohprime / predict_h)"""
+    from .fab import as_double_p, as_int_p
+
+    keep = [as_double_p(x) for x in (w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old, grav_nph)]
+    ints = [as_int_p(x) for x in (adv_bc, pmask)]
+    se, k1 = _fab_arrays(sedge)
+    sf, k2 = _fab_arrays(sflux)
+    um, k3 = _fab_arrays(umac)
+    _chk(load().mgpu_enthalpy_advance_mf(C.byref(p), which_step, len(sold), _fab_array(sold), _fab_array(snew), se, sf,
+                                         _fab_array(scal_force), _fab_array(thermal), um, *[k[1] for k in keep],
+                                         *[k[1] for k in ints]))

@@ -477,6 +477,44 @@ module maestro_b200_shim
        integer(c_int), intent(in) :: adv_bc(*), pmask(*)
      end function mgpu_density_advance_mf_c
 
+     ! velocity_advance.f90:16 / advance_premac.f90:21 / enthalpy_advance.f90:16 over the nfabs boxes of this rank
+     integer(c_int) function mgpu_velocity_advance_mf_c(p, nfabs, uold, unew, sold, rhohalf, umac, gpi, w0, w0_force, &
+          rho0_old, rho0_nph, grav_cell_old, grav_cell_nph, sponge, adv_bc, pmask) bind(C, name="mgpu_velocity_advance_mf")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(in) :: uold(*), sold(*), rhohalf(*), gpi(*), sponge(*)
+       type(mgpu_fab), intent(inout) :: unew(*)
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: w0(*), w0_force(*), rho0_old(*), rho0_nph(*), grav_cell_old(*), grav_cell_nph(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_velocity_advance_mf_c
+
+     integer(c_int) function mgpu_advance_premac_mf_c(p, nfabs, uold, sold, umac, gpi, w0, w0_force, rho0_old, &
+          grav_cell_old, adv_bc, phys_bc, pmask) bind(C, name="mgpu_advance_premac_mf")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs
+       type(mgpu_fab), intent(in) :: uold(*), sold(*), gpi(*)
+       type(c_ptr), intent(in) :: umac(*)
+       real(c_double), intent(in) :: w0(*), w0_force(*), rho0_old(*), grav_cell_old(*)
+       integer(c_int), intent(in) :: adv_bc(*), phys_bc(*), pmask(*)
+     end function mgpu_advance_premac_mf_c
+
+     integer(c_int) function mgpu_enthalpy_advance_mf_c(p, which_step, nfabs, sold, snew, sedge, sflux, scal_force, &
+          thermal, umac, w0, rho0_old, rhoh0_old, rho0_new, rhoh0_new, p0_old, p0_new, psi, grav_old, grav_nph, adv_bc, &
+          pmask) bind(C, name="mgpu_enthalpy_advance_mf")
+       import :: c_int, c_ptr, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: which_step, nfabs
+       type(mgpu_fab), intent(inout) :: sold(*), snew(*), scal_force(*)
+       type(mgpu_fab), intent(in) :: thermal(*)
+       type(c_ptr), intent(in) :: sedge(*), sflux(*), umac(*)
+       real(c_double), intent(in) :: w0(*), rho0_old(*), rhoh0_old(*), rho0_new(*), rhoh0_new(*), p0_old(*), p0_new(*)
+       real(c_double), intent(in) :: psi(*), grav_old(*), grav_nph(*)
+       integer(c_int), intent(in) :: adv_bc(*), pmask(*)
+     end function mgpu_enthalpy_advance_mf_c
+
      ! multifab_fill_boundary + multifab_physbc over the nfabs boxes of this rank's multifab
      integer(c_int) function mgpu_fill_boundary_mf_c(p, nfabs, s, scomp, bccomp, ncomp, adv_bc, pmask) &
           bind(C, name="mgpu_fill_boundary_mf")
@@ -821,6 +859,7 @@ module maestro_b200_shim
   public :: mgpu_mkutrans_sphr_c, mgpu_velpred_sphr_c, mgpu_modify_scal_force_sphr_c, mgpu_put_in_pert_form_sphr_c
   public :: mgpu_fill_boundary_c, mgpu_convert_rhoX_to_X_c, mgpu_modify_scal_force_c, mgpu_put_in_pert_form_c, mgpu_mkrhohforce_c, mgpu_mk_vel_force_c
   public :: mgpu_density_advance_mf_c, mgpu_fill_boundary_mf_c
+  public :: mgpu_velocity_advance_mf_c, mgpu_advance_premac_mf_c, mgpu_enthalpy_advance_mf_c
   public :: mgpu_mkrhohforce_sphr_c, mgpu_enthalpy_advance_sphr_c
   public :: mgpu_make_normal_c, mgpu_mk_vel_force_sphr_c, mgpu_advance_premac_sphr_c, mgpu_velocity_advance_sphr_c
   public :: mgpu_density_advance_c, mgpu_density_advance_sphr_c, mgpu_enthalpy_advance_c, mgpu_velocity_advance_c, mgpu_advance_premac_c

@@ -167,3 +167,116 @@ def test_reference_unit_test_in_its_own_box_layout(gpu_ops, oracle):
             assert same(mine, want)
     finally:
         lib.set_option("exact", 0)
+
+
+# ---- the other three episodes over several boxes (velocity_advance, advance_premac, enthalpy_advance) ----------------
+VWALLS = {2: [[abi.PERIODIC, abi.PERIODIC], [abi.SLIP_WALL, abi.OUTLET]],
+          3: [[abi.PERIODIC, abi.PERIODIC], [abi.NO_SLIP_WALL, abi.SLIP_WALL], [abi.INLET, abi.OUTLET]]}
+
+
+def _vel_inputs(oracle, dm, n, bcset, ppm_type):
+    from synth import fill_face_ghosts, make_episode_extras, make_vel_state
+
+    phys = None if bcset == "periodic" else VWALLS[dm]
+    st = make_vel_state(dm, [n] * dm, phys_bc=phys, ppm_type=ppm_type, do_sponge=1, oracle=oracle)
+    ex = make_episode_extras(st)
+    sc = make_state(dm, [n] * dm, phys_bc=phys, seed=5)
+    oracle.fill_boundary(sc["p"], sc["s"], 1, dm + 1, sc["p"].nscal, sc["adv_bc"], sc["pmask"])
+    nr = st["p"].nr
+    zr = (np.arange(nr) + 0.5) * st["p"].dx[dm - 1]
+    return st, ex, sc["s"], 1.0 + 0.5 * np.exp(-zr / 0.5)
+
+
+@pytest.mark.parametrize("dm,n,parts", [(2, 24, 2), (3, 16, 2)])
+@pytest.mark.parametrize("bcset,ppm_type", [("periodic", 1), ("walls", 2), ("walls", 0)])
+def test_velocity_advance_over_several_boxes(gpu_ops, oracle, dm, n, parts, bcset, ppm_type):
+    from maestro_b200 import lib
+    from synth import fill_face_ghosts
+
+    lib.set_option("exact", 1)
+    try:
+        st, ex, s, rho0 = _vel_inputs(oracle, dm, n, bcset, ppm_type)
+        p = st["p"]
+        rng = np.random.default_rng(8)
+        umac = face_fabs(st["lo"], st["hi"], 1, 1, dm)
+        for u in umac:
+            u.a[...] = rng.uniform(-1, 1, size=u.shape)
+        fill_face_ghosts(umac, st["pmask"], dm)
+        bx = boxes_of(n, parts, dm)
+        cut = lambda f: [take(f, lo, hi, dm) for lo, hi in bx]
+        m = dict(uold=cut(st["utilde"]), unew=cut(st["utilde"]), s=cut(s), rhohalf=cut(ex["rhohalf"]), gpi=cut(ex["gpi"]),
+                 sponge=cut(ex["sponge"]), umac=[cut(umac[d]) for d in range(dm)])
+        unew = st["utilde"].clone()
+        oracle.velocity_advance(p, st["utilde"], unew, s, ex["rhohalf"], umac, ex["gpi"], st["w0"], ex["w0_force"], rho0,
+                                ex["rho0_nph"], ex["grav_old"], ex["grav_nph"], ex["sponge"], st["adv_bc"], st["pmask"])
+        lib.velocity_advance_mf(p, m["uold"], m["unew"], m["s"], m["rhohalf"], m["umac"], m["gpi"], st["w0"], ex["w0_force"],
+                                rho0, ex["rho0_nph"], ex["grav_old"], ex["grav_nph"], m["sponge"], st["adv_bc"], st["pmask"])
+        for i in range(len(bx)):
+            assert valid_equal(m["unew"][i], unew, dm), ("unew", i)
+            for d in range(dm):
+                assert valid_equal(m["umac"][d][i], umac[d], dm), ("umac", d, i)
+    finally:
+        lib.set_option("exact", 0)
+
+
+@pytest.mark.parametrize("dm,n,parts", [(2, 24, 2), (3, 16, 2)])
+@pytest.mark.parametrize("bcset,ppm_type", [("periodic", 1), ("walls", 2), ("walls", 0)])
+def test_advance_premac_over_several_boxes(gpu_ops, oracle, dm, n, parts, bcset, ppm_type):
+    from maestro_b200 import lib
+
+    st, ex, s, rho0 = _vel_inputs(oracle, dm, n, bcset, ppm_type)
+    p = st["p"]
+    bx = boxes_of(n, parts, dm)
+    cut = lambda f: [take(f, lo, hi, dm) for lo, hi in bx]
+    umac = face_fabs(st["lo"], st["hi"], 1, 1, dm, fill=-777.0)
+    m = dict(uold=cut(st["utilde"]), s=cut(s), gpi=cut(ex["gpi"]), umac=[cut(umac[d]) for d in range(dm)])
+    oracle.advance_premac(p, st["utilde"], s, umac, ex["gpi"], st["w0"], ex["w0_force"], rho0, ex["grav_old"], st["adv_bc"],
+                          st["phys_bc"], st["pmask"])
+    lib.advance_premac_mf(p, m["uold"], m["s"], m["umac"], m["gpi"], st["w0"], ex["w0_force"], rho0, ex["grav_old"],
+                          st["adv_bc"], st["phys_bc"], st["pmask"])
+    for i in range(len(bx)):
+        for d in range(dm):
+            assert valid_equal(m["umac"][d][i], umac[d], dm), ("umac", d, i)
+
+
+@pytest.mark.parametrize("dm,n,parts", [(2, 24, 2), (3, 16, 2)])
+@pytest.mark.parametrize("bcset,ppm_type,ept,which_step", [("periodic", 1, 1, 1), ("walls", 2, 0, 2), ("walls", 1, 2, 2)])
+def test_enthalpy_advance_over_several_boxes(gpu_ops, oracle, dm, n, parts, bcset, ppm_type, ept, which_step):
+    from maestro_b200 import lib
+    from synth import make_episode_extras
+
+    lib.set_option("exact", 1)
+    try:
+        st = make_state(dm, n, phys_bc=None if bcset == "periodic" else WALLS[dm], ppm_type=ppm_type, enthalpy_pred_type=ept)
+        p, b = st["p"], st["base"]
+        p.rel_eps = 1e-8 * max(np.abs(u.a).max() for u in st["umac"])
+        ex = make_episode_extras(st)
+        rng = np.random.default_rng(21)
+        g = dict(sold=st["s"].clone(), umac=[u.clone() for u in st["umac"]], force=st["force"].clone(),
+                 sedge=face_fabs(st["lo"], st["hi"], 0, p.nscal, dm), sflux=face_fabs(st["lo"], st["hi"], 0, p.nscal, dm))
+        for f in g["sedge"]:  # density edge states "left by density_advance"
+            f.a[p.rho_comp - 1] = 1.0 + rng.uniform(0.0, 0.5, size=f.a[0].shape)
+        oracle.fill_boundary(p, g["sold"], 1, dm + 1, p.nscal, st["adv_bc"], st["pmask"])
+        g["snew"] = g["sold"].clone()
+        bx = boxes_of(n, parts, dm)
+        cut = lambda f: [take(f, lo, hi, dm) for lo, hi in bx]
+        m = dict(sold=cut(g["sold"]), snew=cut(g["snew"]), force=cut(g["force"]), thermal=cut(ex["thermal"]),
+                 umac=[cut(g["umac"][d]) for d in range(dm)], sedge=[cut(g["sedge"][d]) for d in range(dm)],
+                 sflux=[cut(g["sflux"][d]) for d in range(dm)])
+        args = (b["w0"], b["rho0_old"], b["rhoh0_old"], b["rho0_new"], b["rhoh0_new"], ex["p0_old"], ex["p0_new"], ex["psi"],
+                ex["grav_old"], ex["grav_nph"], st["adv_bc"], st["pmask"])
+        oracle.enthalpy_advance(p, which_step, g["sold"], g["snew"], g["sedge"], g["sflux"], g["force"], ex["thermal"], g["umac"],
+                                *args)
+        lib.enthalpy_advance_mf(p, which_step, m["sold"], m["snew"], m["sedge"], m["sflux"], m["force"], m["thermal"],
+                                m["umac"], *args)
+        c = [p.rhoh_comp - 1]
+        for i in range(len(bx)):
+            assert valid_equal(m["snew"][i], g["snew"], dm, c), ("snew", i)
+            assert valid_equal(m["sold"][i], g["sold"], dm, c), ("sold", i)
+            assert valid_equal(m["force"][i], g["force"], dm, c), ("force", i)
+            for d in range(dm):
+                assert valid_equal(m["sedge"][d][i], g["sedge"][d], dm, c), ("sedge", d, i)
+                assert valid_equal(m["sflux"][d][i], g["sflux"][d], dm, c), ("sflux", d, i)
+                assert valid_equal(m["umac"][d][i], g["umac"][d], dm), ("umac", d, i)
+    finally:
+        lib.set_option("exact", 0)
