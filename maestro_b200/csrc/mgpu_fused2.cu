@@ -791,7 +791,156 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge2d(FusedArgs a) {
 #undef PL2
 }
 
-// tile of the 2-D kernel: 0: 32x8, 1: 16x16, 2: 32x16.  Measured at 4096^2 (profiles/r01k_final.md): 32x16 is the
+// 2-D, marching in y: one thread per x column (BXM columns, one compute-halo column on each side), rows processed one
+// per step with the next row's inputs prefetched into registers.  Everything the y direction needs stays in the thread
+// (a 2H+1 row window of s, the parabola / face state / transverse term of the previous row); only the x direction
+// goes through shared memory (the row of s, the x parabolas, the x face states, the x transverse terms: one barrier
+// each).  Against the tile kernel: no halo rows (a 32x16 tile recomputes 2 of 16 rows and stages 22 for 16), loads
+// issued a row ahead instead of at the head of a short-lived CTA.  Same arithmetic as k_fused_edge2d.
+template <int PPM, int BXM, bool BC>
+__global__ void __launch_bounds__(BXM) k_fused_edge2d_march(FusedArgs a) {
+  constexpr int H = (PPM == 2) ? 3 : 2;
+  __shared__ double sS[BXM + 2 * H];
+  __shared__ double pAX0[BXM], pAX1[BXM], pSHX[BXM], pGX[BXM];
+  const int tx = threadIdx.x;
+  const int ibase = a.lo[0] - 1 + blockIdx.x * (BXM - 2);
+  const int i = ibase + tx;
+  const int ic = min(i, a.hi[0] + 1);
+  const int j0 = a.lo[1] + blockIdx.y * a.kchunk;            // first cell row this CTA finishes
+  const int j1 = min(j0 + a.kchunk - 1, a.hi[1]);            // last one
+  const bool top = (j1 == a.hi[1]);                          // this CTA also owns the y face hi + 1
+  const double* __restrict__ gs = a.s.p;
+  const double* __restrict__ gu = a.umac[0].p;
+  const double* __restrict__ gv = a.umac[1].p;
+  const int sx0 = a.s.lo[0], sx1 = a.s.lo[0] + a.s.n[0] - 1, sy0 = a.s.lo[1], sy1 = a.s.lo[1] + a.s.n[1] - 1;
+  const int isc = max(sx0, min(i, sx1));                     // this thread's column in s (clamped)
+  // the x halo of the row buffer: the first / last H threads also fetch the H columns outside the block
+  const int hcol = (tx < H) ? (ibase - H + tx) : (ibase + BXM + (tx - (BXM - H)));
+  const int hslot = (tx < H) ? tx : (BXM + H + (tx - (BXM - H)));
+  const bool hthr = (tx < H) || (tx >= BXM - H);
+  const int hcc = max(sx0, min(hcol, sx1));
+  auto srow = [&](int col, int row) { return gs[a.s.off(col, max(sy0, min(row, sy1)), 0)]; };
+  const LineBC nb = no_wall2();
+  const LineBC lbx = BC ? make_linebc(2, 0, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0]) : nb;
+  const LineBC lby = BC ? make_linebc(2, 1, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1]) : nb;
+  FaceRule frx;
+  frx.kind = FB_NONE;
+  frx.clamp = 0;
+  frx.low = false;
+  if constexpr (BC) frx = face_rule(i, a.lo[0], a.hi[0], a.bclo[0], a.bchi[0], a.velnorm[0]);
+  const double rel_eps = a.rel_eps;
+  const double tdx = a.dt / a.dx[0], tdy = a.dt / a.dx[1];
+  const double c4x = tdx * 0.25, c4y = tdy * 0.25, dt2 = 0.5 * a.dt;
+  const double* const S = sS + tx + H;
+  // row window of s: sw[m] = s(i, r - H + m) once row r is current
+  double sw[2 * H + 1];
+  const int r0 = j0 - 1;  // first row reconstructed
+#pragma unroll
+  for (int m = 0; m < 2 * H; ++m) sw[m + 1] = srow(isc, r0 - 1 - H + m + 1);  // rows r0-H .. r0+H-1 sit one slot high
+  // state carried from the previous row
+  double ay0_p = 0.0, ay1_p = 0.0, shy_p = 0.0, shx_p = 0.0, gy_p = 0.0, v0_p = 0.0, hf_p = 0.0;
+  bool upx_p = false, slowx_p = false;
+  // inputs of the first row, then always one row ahead
+  auto yc = [&](int row) { return min(row, a.hi[1] + 1); };
+  double s_n = srow(isc, r0 + H), hs_n = hthr ? srow(hcc, r0) : 0.0;
+  double u0_n = gu[a.umac[0].off(ic, min(max(r0, a.umac[0].lo[1]), a.hi[1] + 1), 0)];
+  double u1_n = gu[a.umac[0].off(ic, min(max(r0, a.umac[0].lo[1]), a.hi[1] + 1), 0) + 1];
+  double v0_n = gv[a.umac[1].off(ic, max(yc(r0), a.umac[1].lo[1]), 0)];
+  double f_n = a.force_zero ? 0.0 : a.force.p[a.force.off(ic, min(max(r0, a.force.lo[1]), a.hi[1] + 1), 0)];
+  for (int r = r0; r <= j1 + 1; ++r) {
+    // ---- this row's inputs; issue the next row's loads
+#pragma unroll
+    for (int m = 0; m < 2 * H; ++m) sw[m] = sw[m + 1];
+    sw[2 * H] = s_n;
+    const double u0 = u0_n, u1 = u1_n, v0 = v0_n, hf = dt2 * f_n, hs = hs_n;
+    if (r < j1 + 1) {
+      const int rn = r + 1;
+      s_n = srow(isc, rn + H);
+      if (hthr) hs_n = srow(hcc, rn);
+      const long ou = a.umac[0].off(ic, yc(rn), 0);
+      u0_n = gu[ou];
+      u1_n = gu[ou + 1];
+      v0_n = gv[a.umac[1].off(ic, yc(rn), 0)];
+      if (!a.force_zero) f_n = a.force.p[a.force.off(ic, yc(rn), 0)];
+    }
+    FaceRule fry;
+    fry.kind = FB_NONE;
+    fry.clamp = 0;
+    fry.low = false;
+    if constexpr (BC) fry = face_rule(r, a.lo[1], a.hi[1], a.bclo[1], a.bchi[1], a.velnorm[1]);
+    // ---- A: the row of s for the x stencils
+    sS[tx + H] = sw[H];
+    if (hthr) sS[hslot] = hs;
+    __syncthreads();
+    // ---- B: C1(r)
+    double ay0, ay1;
+    {
+      double a0, a1;
+      if constexpr (BC) cell_par_bc<PPM>(S, 1, i, a.slope_order, lbx, a0, a1);
+      else cell_par<PPM>(S, 1, a.slope_order, nb, a0, a1);
+      pAX0[tx] = a0;
+      if (PPM != 0) pAX1[tx] = a1;
+      if constexpr (BC) cell_par_bc<PPM>(&sw[H], 1, r, a.slope_order, lby, ay0, ay1);
+      else cell_par<PPM>(&sw[H], 1, a.slope_order, nb, ay0, ay1);
+    }
+    __syncthreads();
+    // ---- C: F1(r): x face i of row r, y face r (between rows r-1 and r)
+    bool upx = u0 > 0.0, slowx = !(fabs(u0) > rel_eps);
+    bool upy = v0 > 0.0, slowy = !(fabs(v0) > rel_eps);
+    double shx, shy;
+    const int txm = max(tx - 1, 0);
+    if (BC && frx.kind != FB_NONE) {
+      upx = frx.kind == FB_LEFT;
+      slowx = false;
+      const int q = upx ? txm : tx;
+      if (frx.kind == FB_GHOST) shx = frx.low ? S[-1] : S[0];
+      else if (frx.kind == FB_ZERO) shx = 0.0;
+      else shx = clamp_rule(forced_state<PPM>(upx, pAX0[q], PPM != 0 ? pAX1[q] : 0.0, S[upx ? -1 : 0], u0, tdx, rel_eps), frx.clamp);
+    } else {
+      const int q = upx ? txm : tx;
+      shx = trace1<PPM>(pAX0[q], PPM != 0 ? pAX1[q] : 0.0, S[upx ? -1 : 0], u0 * tdx, upx);
+      if (slowx) shx = trace_slow<PPM>(pAX0[txm], S[-1], pAX0[tx], S[0], u0 * tdx);
+    }
+    if (BC && fry.kind != FB_NONE) {
+      upy = fry.kind == FB_LEFT;
+      slowy = false;
+      if (fry.kind == FB_GHOST) shy = fry.low ? sw[H - 1] : sw[H];
+      else if (fry.kind == FB_ZERO) shy = 0.0;
+      else shy = clamp_rule(forced_state<PPM>(upy, upy ? ay0_p : ay0, upy ? ay1_p : ay1, upy ? sw[H - 1] : sw[H], v0, tdy, rel_eps),
+                            fry.clamp);
+    } else {
+      shy = trace1<PPM>(upy ? ay0_p : ay0, upy ? ay1_p : ay1, upy ? sw[H - 1] : sw[H], v0 * tdy, upy);
+      if (slowy) shy = trace_slow<PPM>(ay0_p, sw[H - 1], ay0, sw[H], v0 * tdy);
+    }
+    pSHX[tx] = shx;
+    __syncthreads();
+    // ---- D: C2: the x transverse term of row r-1 (both y faces known now), the y transverse term of row r
+    const double gy = c4x * (u1 + u0) * (pSHX[min(tx + 1, BXM - 1)] - shx) - hf;
+    pGX[tx] = c4y * (v0 + v0_p) * (shy - shy_p) - hf_p;
+    __syncthreads();
+    // ---- E: F3: x face (i, r-1), y face (i, r)
+    const int rm = r - 1;
+    if (rm >= j0 && rm <= j1 && tx >= 1 && (tx <= BXM - 2 || i == a.hi[0] + 1) && i <= a.hi[0] + 1) {
+      double g = pGX[upx_p ? txm : tx];
+      if (slowx_p) g = 0.5 * (pGX[txm] + pGX[tx]);
+      double e = shx_p - g;
+      if (BC && frx.kind != FB_NONE) e = (frx.kind >= FB_GHOST) ? shx_p : clamp_rule(e, frx.clamp);
+      a.sedge[0].p[a.sedge[0].off(i, rm, 0)] = e;
+    }
+    if (r >= j0 && (r <= j1 || (top && r == j1 + 1)) && tx >= 1 && tx <= BXM - 2 && i <= a.hi[0]) {
+      double g = upy ? gy_p : gy;
+      if (slowy) g = 0.5 * (gy_p + gy);
+      double e = shy - g;
+      if (BC && fry.kind != FB_NONE) e = (fry.kind >= FB_GHOST) ? shy : clamp_rule(e, fry.clamp);
+      a.sedge[1].p[a.sedge[1].off(i, r, 0)] = e;
+    }
+    // ---- carry
+    ay0_p = ay0; ay1_p = ay1; shy_p = shy; shx_p = shx; gy_p = gy; v0_p = v0; hf_p = hf;
+    upx_p = upx; slowx_p = slowx;
+  }
+}
+
+// tile of the 2-D kernel: 0: 32x8, 1: 16x16, 2: 32x16, 3: the y-marching kernel above.  Measured at 4096^2 (profiles/r01k_final.md): 32x16 is the
 // fastest for ppm_type 2 (3.66 ms for 4 components; 32x8: 4.84) and within 1 % of the best for ppm_type 1.  A variant
 // that loops over several tiles per CTA with the next tile's inputs prefetched into registers was slower (it needs
 // 100+ registers, one 512-thread CTA per SM).
@@ -804,6 +953,17 @@ void launch_fused2d_t(const FusedArgs& a, int nx, int ny) {
 }
 template <int PPM, bool BC>
 void launch_fused2d(const FusedArgs& a, int nx, int ny) {
+  if (g_tile2d == 3) {  // marching kernel: 128 columns per CTA, rows in chunks that fill the GPU a few times over
+    constexpr int BXM = 128;
+    const int ncol = (nx + BXM - 3) / (BXM - 2);
+    int chunk = 256;
+    while (chunk > 32 && (long)ncol * ((ny + chunk - 1) / chunk) < 148L * 8) chunk /= 2;
+    FusedArgs b = a;
+    b.kchunk = chunk;
+    dim3 grid((unsigned)ncol, (unsigned)((ny + chunk - 1) / chunk), 1);
+    MGPU_TIMED(TAG_FUSED_EDGE, (k_fused_edge2d_march<PPM, BXM, BC><<<grid, BXM, 0, ctx().stream>>>(b)));
+    return;
+  }
   if (g_tile2d == 1) launch_fused2d_t<PPM, BC, 16, 16>(a, nx, ny);
   else if (g_tile2d == 2) launch_fused2d_t<PPM, BC, 32, 16>(a, nx, ny);
   else launch_fused2d_t<PPM, BC, 32, 8>(a, nx, ny);

@@ -94,7 +94,7 @@ __device__ __forceinline__ void cs_limit_fast(const double* q, long st, EdgeFn E
     const double sgn = sign1(D2);
     const double D2LIM =
         dmax2(dmin2(dmin2(dmin2(sgn * D2, MGPU_CS_C * sgn * D2L), MGPU_CS_C * sgn * D2R), MGPU_CS_C * sgn * D2C), 0.0);
-    const double r = D2LIM / dmax2(fabs(D2), 1.e-10);
+    const double r = D2LIM * __drcp_rn(dmax2(fabs(D2), 1.e-10));  // FAST build: reciprocal + multiply (<= 2 ulp)
     alpham = alpham * r;
     alphap = alphap * r;
   } else if (bigp || bigm) {
@@ -102,7 +102,7 @@ __device__ __forceinline__ void cs_limit_fast(const double* q, long st, EdgeFn E
     const double a_b = bigp ? alphap : alpham;  // the big end, limited
     const double del = (bigp ? qm : qp) - sc;
     const double sgn = sign1(a_s);
-    const double amax = -(a_b * a_b) / (4 * (alpham + alphap));
+    const double amax = -(a_b * a_b) * __drcp_rn(4 * (alpham + alphap));
     double nb = a_b;
     if (sgn * amax >= sgn * del) {
       if (sgn * (del - a_s) >= 1.e-10) nb = (-2.0 * del - 2.0 * sgn * sqrt(del * del - del * a_s));

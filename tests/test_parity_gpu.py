@@ -128,7 +128,7 @@ def test_fused_edge_slow_faces(gpu_ops, oracle, ppm_type, variant, shape, kchunk
 @pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
 @pytest.mark.parametrize("shape", [(37, 9), (8, 33), (64, 16), (95, 70)])
 @pytest.mark.parametrize("slow", [False, True], ids=["moving", "slow-faces"])
-@pytest.mark.parametrize("tile", [2, 0, 1], ids=["32x16", "32x8", "16x16"])
+@pytest.mark.parametrize("tile", [2, 0, 1, 3], ids=["32x16", "32x8", "16x16", "march"])
 def test_fused_edge_2d(gpu_ops, oracle, ppm_type, bcset, shape, slow, tile):
     """FAST fused 2-D kernel (k_fused_edge2d, the whole of make_edge_scal_2d in one launch) on boxes that are not
     multiples of the CTA tile, scalar and velocity components, periodic / wall / inflow-outflow boxes, with and
