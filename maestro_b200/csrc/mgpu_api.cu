@@ -1761,7 +1761,7 @@ int mgpu_set_option(const char* key, int value) {
   std::string k(key ? key : "");
   if (k == "fused") g_opt_fused = value;
   else if (k == "kchunk") g_opt_kchunk = value;
-  else if (k == "exact") { g_opt_exact = value; bds_set_fast(value == 0); }
+  else if (k == "exact") { g_opt_exact = value; bds_set_fast(value == 0); velpred_set_fast(value == 0); }
   else if (k == "leanplus") g_opt_leanplus = value;
   else if (k == "split_tiles") fused_edge3_set_split(value);
   else if (k == "overlap") g_opt_overlap = value;

@@ -14,6 +14,17 @@
 #include "mgpu_recon.cuh"
 #include "mgpu_velpred.cuh"
 
+// Two builds of this file (like mgpu_bds.cu): the exact one (-fmad=false, the reference's divisions: bit-identical) and
+// the FAST one (mgpu_velpred_fast.cu: FMA contraction, dt/h and the dt/(4h), dt/(6h) factors as multiplications by
+// reciprocals formed on the host; <= 1e-12), the default.  `exact = 1` selects the first.
+#ifdef MGPU_VP_FAST
+#define VP_OVER(x, d, rd) ((x) * (rd))
+#define VP_FN(name) name##_fast
+#else
+#define VP_OVER(x, d, rd) ((x) / (d))
+#define VP_FN(name) name##_exact
+#endif
+
 namespace mgpu {
 
 namespace {
@@ -26,23 +37,28 @@ __device__ __forceinline__ bool wall3(int bc) {
 // form3d: velpred_3d writes the slope predictor as (1/2 - dt2*max(0,u)/h); mkutrans and velpred_2d as
 // (1/2 - (dt2/h)*max(0,u))  (velpred.f90:812-813 vs :384-392, mkutrans.f90:543-547)
 __device__ __forceinline__ void vel_cell_states(int ppm_type, int slope_order, bool form3d, const double* q, long st,
-                                                int c, const LineBC& b, double ucell, double dt, double h,
+                                                int c, const LineBC& b, double ucell, double dt, double h, double rh,
                                                 double rel_eps, double& Ip, double& Im) {
+  (void)rh;
   if (ppm_type == 0) {
     const double sl = slope_cell(q, st, c, b, slope_order);
     const double dt2 = 0.5 * dt;
     if (form3d) {
-      Ip = q[0] + (0.5 - dt2 * dmax2(0.0, ucell) / h) * sl;
-      Im = q[0] - (0.5 + dt2 * dmin2(0.0, ucell) / h) * sl;
+      Ip = q[0] + (0.5 - VP_OVER(dt2 * dmax2(0.0, ucell), h, rh)) * sl;
+      Im = q[0] - (0.5 + VP_OVER(dt2 * dmin2(0.0, ucell), h, rh)) * sl;
     } else {
-      Ip = q[0] + (0.5 - (dt2 / h) * dmax2(0.0, ucell)) * sl;
-      Im = q[0] - (0.5 + (dt2 / h) * dmin2(0.0, ucell)) * sl;
+      Ip = q[0] + (0.5 - VP_OVER(dt2, h, rh) * dmax2(0.0, ucell)) * sl;
+      Im = q[0] - (0.5 + VP_OVER(dt2, h, rh) * dmin2(0.0, ucell)) * sl;
     }
   } else {
     double sm, sp;
     if (ppm_type == 1) ppm1_cell(q, st, c, b, sm, sp);
     else ppm2_cell(q, st, c, b, sm, sp);
+#ifdef MGPU_VP_FAST
+    ppm_trace<true>(q[0], sm, sp, ucell, ucell, dt * rh, h, rel_eps, Ip, Im);
+#else
     ppm_trace<false>(q[0], sm, sp, ucell, ucell, dt, h, rel_eps, Ip, Im);
+#endif
   }
 }
 
@@ -120,7 +136,7 @@ __global__ void __launch_bounds__(256) k_mkutrans(VpArgs a) {
     q = u.p + u.off(ix[0], ix[1], ix[2]);
     double ip;
     vel_cell_states(PPM, a.slope_order, false, q, st, ix[d], b, uf.p[uf.off(ix[0], ix[1], ix[2])], a.dt, a.dx[d],
-                    a.rel_eps, ip, ur);
+                    a.rdx[d], a.rel_eps, ip, ur);
     sh_ip[slot] = ip;
   }
   __syncthreads();
@@ -164,7 +180,7 @@ __global__ void __launch_bounds__(256) k_vp_face(VpArgs a) {
       const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[c][d], a.bchi[c][d]);
       const double* q = a.utilde.p + uo + a.utilde.cs * c;
       double ip;
-      vel_cell_states(PPM, a.slope_order, dm == 3, q, st, ix[d], b, uc, a.dt, a.dx[d], a.rel_eps, ip, ur[c]);
+      vel_cell_states(PPM, a.slope_order, dm == 3, q, st, ix[d], b, uc, a.dt, a.dx[d], a.rdx[d], a.rel_eps, ip, ur[c]);
       sh_ip[c][slot] = ip;
     }
   }
@@ -239,8 +255,8 @@ __global__ void k_vp_trans(VpArgs a) {
       cl[d] -= 1;
       const long fo = a.UL[d].off(ix[0], ix[1], ix[2]) + a.UL[d].cs * c;
       const long qc = a.UIMH[t].cs * c;
-      double ql = a.UL[d].p[fo] - tterm(dt6 / a.dx[t], a.utrans[t], a.UIMH[t], qc, t, cl[0], cl[1], cl[2]);
-      double qr = a.UR[d].p[fo] - tterm(dt6 / a.dx[t], a.utrans[t], a.UIMH[t], qc, t, ix[0], ix[1], ix[2]);
+      double ql = a.UL[d].p[fo] - tterm(VP_OVER(dt6, a.dx[t], a.rdx[t]), a.utrans[t], a.UIMH[t], qc, t, cl[0], cl[1], cl[2]);
+      double qr = a.UR[d].p[fo] - tterm(VP_OVER(dt6, a.dx[t], a.rdx[t]), a.utrans[t], a.UIMH[t], qc, t, ix[0], ix[1], ix[2]);
       if (ix[d] == a.lo[d]) {
         const int p = a.plo[d];
         if (p == MGPU_BC_INLET) ql = qr = a.utilde(cl[0], cl[1], cl[2], c);
@@ -279,8 +295,8 @@ __global__ void k_vp_final(VpArgs a) {
       const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[d][d], a.bchi[d][d]);
       double dummy;
       vel_cell_states(PPM, a.slope_order, dm == 3, f.p + fo - fst, fst, ix[d] - 1, b, ufd.p[uo - ufd.stride(d)],
-                      a.dt, a.dx[d], a.rel_eps, fl, dummy);
-      vel_cell_states(PPM, a.slope_order, dm == 3, f.p + fo, fst, ix[d], b, ufd.p[uo], a.dt, a.dx[d], a.rel_eps,
+                      a.dt, a.dx[d], a.rdx[d], a.rel_eps, fl, dummy);
+      vel_cell_states(PPM, a.slope_order, dm == 3, f.p + fo, fst, ix[d], b, ufd.p[uo], a.dt, a.dx[d], a.rdx[d], a.rel_eps,
                       dummy, fr);
     } else {
       fl = f.p[fo - fst];
@@ -292,14 +308,14 @@ __global__ void k_vp_final(VpArgs a) {
   if (dm == 2) {
     const int t = 1 - d;
     const long qc = a.UIMH[t].cs * d;
-    ml = a.UL[d].p[fo] - tterm(dt4 / a.dx[t], a.utrans[t], a.UIMH[t], qc, t, cl[0], cl[1], cl[2]) + dt2 * fl;
-    mr = a.UR[d].p[fo] - tterm(dt4 / a.dx[t], a.utrans[t], a.UIMH[t], qc, t, ix[0], ix[1], ix[2]) + dt2 * fr;
+    ml = a.UL[d].p[fo] - tterm(VP_OVER(dt4, a.dx[t], a.rdx[t]), a.utrans[t], a.UIMH[t], qc, t, cl[0], cl[1], cl[2]) + dt2 * fl;
+    mr = a.UR[d].p[fo] - tterm(VP_OVER(dt4, a.dx[t], a.rdx[t]), a.utrans[t], a.UIMH[t], qc, t, ix[0], ix[1], ix[2]) + dt2 * fr;
   } else {
     const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
-    ml = a.UL[d].p[fo] - tterm(dt4 / a.dx[t1], a.utrans[t1], a.Q[d][t1], 0, t1, cl[0], cl[1], cl[2]) -
-         tterm(dt4 / a.dx[t2], a.utrans[t2], a.Q[d][t2], 0, t2, cl[0], cl[1], cl[2]) + dt2 * fl;
-    mr = a.UR[d].p[fo] - tterm(dt4 / a.dx[t1], a.utrans[t1], a.Q[d][t1], 0, t1, ix[0], ix[1], ix[2]) -
-         tterm(dt4 / a.dx[t2], a.utrans[t2], a.Q[d][t2], 0, t2, ix[0], ix[1], ix[2]) + dt2 * fr;
+    ml = a.UL[d].p[fo] - tterm(VP_OVER(dt4, a.dx[t1], a.rdx[t1]), a.utrans[t1], a.Q[d][t1], 0, t1, cl[0], cl[1], cl[2]) -
+         tterm(VP_OVER(dt4, a.dx[t2], a.rdx[t2]), a.utrans[t2], a.Q[d][t2], 0, t2, cl[0], cl[1], cl[2]) + dt2 * fl;
+    mr = a.UR[d].p[fo] - tterm(VP_OVER(dt4, a.dx[t1], a.rdx[t1]), a.utrans[t1], a.Q[d][t1], 0, t1, ix[0], ix[1], ix[2]) -
+         tterm(VP_OVER(dt4, a.dx[t2], a.rdx[t2]), a.utrans[t2], a.Q[d][t2], 0, t2, ix[0], ix[1], ix[2]) + dt2 * fr;
   }
   const bool radial = a.spherical || (d == dm - 1);
   const double w0f = a.spherical ? a.w0mac[d](ix[0], ix[1], ix[2]) : (radial ? a.w0[ix[d]] : 0.0);
@@ -384,6 +400,7 @@ void fill_common(VpArgs& a, const mgpu_params& P, const DV& utilde, const DV& uf
     a.lo[d] = d < dm ? lo[d] : 0;
     a.hi[d] = d < dm ? hi[d] : 0;
     a.dx[d] = P.dx[d < dm ? d : 0];
+    a.rdx[d] = 1.0 / a.dx[d];
     a.plo[d] = a.phi[d] = MGPU_BC_INTERIOR;
     for (int c = 0; c < 3; ++c) a.bclo[c][d] = a.bchi[c][d] = MGPU_BC_INTERIOR;
     if (d < dm) {
@@ -406,8 +423,34 @@ void fill_common(VpArgs& a, const mgpu_params& P, const DV& utilde, const DV& uf
 
 }  // namespace
 
+#ifndef MGPU_VP_FAST
+static int g_vp_fast = 1;
+void velpred_set_fast(int on) { g_vp_fast = on; }
+void mkutrans_dev_fast(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* utrans, const double* w0_dev,
+                       const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const DV* w0mac);
+void velpred_dev_fast(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans, const DV& force,
+                      const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
+                      int ng_f, const DV* w0mac);
+void mkutrans_dev_exact(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* utrans, const double* w0_dev,
+                        const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const DV* w0mac);
+void velpred_dev_exact(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans, const DV& force,
+                       const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
+                       int ng_f, const DV* w0mac);
 void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* utrans, const double* w0_dev,
                   const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const DV* w0mac) {
+  if (g_vp_fast) mkutrans_dev_fast(P, utilde, ufull, utrans, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, w0mac);
+  else mkutrans_dev_exact(P, utilde, ufull, utrans, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, w0mac);
+}
+void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans, const DV& force,
+                 const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
+                 int ng_f, const DV* w0mac) {
+  if (g_vp_fast) velpred_dev_fast(P, utilde, ufull, umac, utrans, force, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, ng_f, w0mac);
+  else velpred_dev_exact(P, utilde, ufull, umac, utrans, force, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, ng_f, w0mac);
+}
+#endif
+
+void VP_FN(mkutrans_dev)(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* utrans, const double* w0_dev,
+                         const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const DV* w0mac) {
   VpArgs a;
   fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "mkutrans", w0mac);
   for (int d = 0; d < P.dm; ++d) a.utrans[d] = utrans[d];
@@ -418,15 +461,17 @@ void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* u
   }
 }
 
+#ifndef MGPU_VP_FAST
 size_t velpred_scratch(const mgpu_params& P, const int* lo, const int* hi) {
   Box3 tb = grown(lo, hi, P.dm, 1);
   const size_t narr = (size_t)3 * P.dm * P.dm + (P.dm == 3 ? 6 : 0);
   return narr * ((size_t)tb.npts() * sizeof(double) + 256) + 4096;
 }
+#endif
 
-void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans, const DV& force,
-                 const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
-                 int ng_f, const DV* w0mac) {
+void VP_FN(velpred_dev)(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans,
+                        const DV& force, const double* w0_dev, const int* lo, const int* hi, const int* adv_bc,
+                        const int* phys_bc, int ng_u, int ng_f, const DV* w0mac) {
   VpArgs a;
   fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "velpred", w0mac);
   const int dm = P.dm;

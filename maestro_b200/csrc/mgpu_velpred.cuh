@@ -11,6 +11,7 @@ struct VpArgs {
   int bclo[3][3], bchi[3][3];  // [component][direction]: adv_bc(d, side, comp)
   int plo[3], phi[3];          // phys_bc(d, side)
   double dt, dx[3], rel_eps;
+  double rdx[3];  // 1/dx (FAST build)
   Box3 tb, vb;  // lo-1:hi+1 and lo:hi
   DV utilde, ufull, force;
   DV utrans[3], umac[3];
@@ -28,5 +29,7 @@ void velpred_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* um
                  const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
                  int ng_f, const DV* w0mac = nullptr);
 size_t velpred_scratch(const mgpu_params& P, const int* lo, const int* hi);
+// 1 (default): the FAST build of the kernels (mgpu_velpred_fast.cu: FMA, reciprocals; <= 1e-12); 0: the bit-identical one
+void velpred_set_fast(int on);
 
 }  // namespace mgpu
