@@ -135,7 +135,7 @@ def run_episode(ops, st, e):
                         b["rho0_old"], b["rho0_new"], b["p0"], b["rho0_predicted_edge"], st["adv_bc"], st["pmask"])
 
 
-def cpu_reference(config, n_sample, steps, warmup):
+def cpu_reference(config, n_sample, steps, warmup, budget_s=150.0):
     """restated reference algorithm (oracle) on the host cores over an n_sample box of the workload"""
     import ctypes
 
@@ -152,16 +152,28 @@ def cpu_reference(config, n_sample, steps, warmup):
             f.device, f.a = None, f.a.numpy()  # same memory, numpy view: the oracle takes host pointers
     else:
         w = build_workload(config, n_sample, None)
-    for _ in range(warmup):
-        w.reset()
-        w.step(oracle)
-    t = 0.0
-    for _ in range(steps):
+    # bounded: a 256^3 step of the restated reference takes ~17 s on 16 threads, so the whole run (warm-up included) is
+    # kept within `budget_s` by timing fewer steps than asked for once the first step has shown what one costs
+    t_start = time.perf_counter()
+    t, done, first = 0.0, 0, None
+    k_warm, k_timed = warmup, steps
+    i = 0
+    while i < k_warm + k_timed:
         w.reset()
         t0 = time.perf_counter()
         w.step(oracle)
-        t += time.perf_counter() - t0
-    dt = t / steps
+        d = time.perf_counter() - t0
+        if first is None:
+            first = d
+            if first * (warmup + steps) > budget_s:
+                k_warm = min(warmup, 1)
+                k_timed = max(1, min(steps, int((budget_s - first) / first) - k_warm + 1))
+        if i >= k_warm:
+            t += d
+            done += 1
+        i += 1
+    dt = t / done
+    cpu_reference.steps_timed, cpu_reference.wall_s = done, time.perf_counter() - t_start
     return w.zone_updates / dt, dt, w
 
 
@@ -234,9 +246,12 @@ def main():
         n_s = 96 if args.config == "c5" else n
         zups, dt, w = cpu_reference(args.config, n_s, max(args.steps, 1), max(args.warmup, 0))
         sample = "the full %s box, every step" % args.config if n_s == n else "%d^3 box of the same workload per step" % n_s
+        if cpu_reference.steps_timed != args.steps:
+            sample += " (%d of the %d steps timed: the run is bounded to ~150 s)" % (cpu_reference.steps_timed, args.steps)
         cfg = config_of(build_desc_only(args.config, n, args.gpus) if n_s != n else w, args.gpus)
         line = {"metric": METRIC, "value": zups, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "steps_timed": cpu_reference.steps_timed,
+                "ms_per_step": dt * 1e3, "higher_is_better": True,
                 "scaling": w.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": zups, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": "%s, OpenMP over %d threads (restated reference algorithm, oracle pinned on the "
