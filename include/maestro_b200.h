@@ -112,7 +112,8 @@ const char* mgpu_version(void);
 long mgpu_launch_count(int reset);
 /* tuning/testing switches: "fused" (1: fused 3-D edge kernel when applicable, 0: staged general path),
  * "kchunk" (z planes per CTA of the fused kernel), "exact" (1: bit-identical fp64 expression trees everywhere;
- * 0 (default): the fused kernel folds dt/dx and allows FMA contraction, <= 1e-12 relative from the reference) */
+ * 0 (default): the FAST builds of the edge-state, BDS and mkutrans / velpred kernels -- dt/dx folded, divisions as
+ * multiplications by reciprocals, FMA contraction -- <= 1e-12 relative from the reference) */
 int mgpu_set_option(const char* key, int value);
 /* per-kernel-class device timing with CUDA events on the launching stream (bench roofline line):
  * mgpu_profile(1) starts/reset, mgpu_profile_get(tag,...) returns accumulated ms and launch count.
