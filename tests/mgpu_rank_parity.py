@@ -85,6 +85,116 @@ def sphr_main(rank, world, local, ops, exact):
     finish(rank, local, worst)
 
 
+def compare(pairs, lo, hi, dm, interior_ghosts_only=True):
+    """max relative error (max-norm per field) of this rank's fabs against the same region of the global ones"""
+    worst = 0.0
+    for mine, glob, ng, nd in pairs:
+        want = take(glob, lo, hi, ng, nd, dm)
+        a, w = mine.a, want.a
+        if ng:  # valid cells + slab-direction ghost planes
+            sl = [slice(None)] * 4
+            for d in range(dm - 1):
+                sl[3 - d] = slice(ng, a.shape[3 - d] - ng)
+            a, w = a[tuple(sl)], w[tuple(sl)]
+        den = max(np.abs(w[np.isfinite(w)]).max(), 1e-300)
+        err = np.abs(a - w)
+        worst = max(worst, err[np.isfinite(err)].max() / den)
+    return worst
+
+
+def episodes_main(rank, world, local, ops, dm, bcset, ppm_type, exact):
+    """The other episodes and the reductions over slabs: velocity_advance, advance_premac, enthalpy_advance (NCCL halo
+    exchange in their ghost fills), firstdt and average (NCCL min / max / sum), against the oracle on the global box."""
+    from synth import fill_face_ghosts, make_episode_extras, make_vel_state
+    import ctypes as C
+
+    oracle = oracle_lib.load()
+    r = dm - 1
+    n = [16, 12, 10 * world] if dm == 3 else [24, 12 * world]
+    walls = [[abi.PERIODIC, abi.PERIODIC]] * (dm - 1) + [[abi.SLIP_WALL, abi.OUTLET]]
+    phys = None if bcset == "periodic" else walls
+    vs = make_vel_state(dm, n, phys_bc=phys, ppm_type=ppm_type, do_sponge=1, oracle=oracle)
+    st = make_state(dm, n, phys_bc=phys, ppm_type=ppm_type, enthalpy_pred_type=1)
+    p, q, b = st["p"], vs["p"], st["base"]
+    p.rel_eps = 1e-8 * max(np.abs(u.a).max() for u in st["umac"])
+    ex = make_episode_extras(vs)
+    sold_g = st["s"].clone()
+    oracle.fill_boundary(p, sold_g, 1, dm + 1, p.nscal, st["adv_bc"], st["pmask"])
+    rng = np.random.default_rng(8)
+    umac0 = face_fabs(vs["lo"], vs["hi"], 1, 1, dm)
+    for u in umac0:
+        u.a[...] = rng.uniform(-1, 1, size=u.shape)
+    fill_face_ghosts(umac0, vs["pmask"], dm)
+    nr = q.nr
+    zr = (np.arange(nr) + 0.5) * q.dx[r]
+    rho0 = 1.0 + 0.5 * np.exp(-zr / 0.5)
+    nod = lambda d: [1 if k == d else 0 for k in range(3)]
+    # ---- the global references
+    unew_g = vs["utilde"].clone()
+    um_v = [u.clone() for u in umac0]
+    oracle.velocity_advance(q, vs["utilde"], unew_g, sold_g, ex["rhohalf"], um_v, ex["gpi"], vs["w0"], ex["w0_force"], rho0,
+                            ex["rho0_nph"], ex["grav_old"], ex["grav_nph"], ex["sponge"], vs["adv_bc"], vs["pmask"])
+    um_p = face_fabs(vs["lo"], vs["hi"], 1, 1, dm, fill=-777.0)
+    oracle.advance_premac(q, vs["utilde"], sold_g, um_p, ex["gpi"], vs["w0"], ex["w0_force"], rho0, ex["grav_old"],
+                          vs["adv_bc"], vs["phys_bc"], vs["pmask"])
+    e_in = dict(sold=sold_g.clone(), umac=[u.clone() for u in st["umac"]], force=st["force"].clone())
+    e_g = dict(sold=sold_g.clone(), snew=sold_g.clone(), umac=[u.clone() for u in st["umac"]], force=st["force"].clone(),
+               sedge=face_fabs(st["lo"], st["hi"], 0, p.nscal, dm), sflux=face_fabs(st["lo"], st["hi"], 0, p.nscal, dm))
+    for f in e_g["sedge"]:
+        f.a[p.rho_comp - 1] = 1.0 + rng.uniform(0.0, 0.5, size=f.a[0].shape)
+    sedge_in = [f.clone() for f in e_g["sedge"]]
+    eargs = (b["w0"], b["rho0_old"], b["rhoh0_old"], b["rho0_new"], b["rhoh0_new"], ex["p0_old"], ex["p0_new"], ex["psi"],
+             ex["grav_old"], ex["grav_nph"])
+    oracle.enthalpy_advance(p, 2, e_g["sold"], e_g["snew"], e_g["sedge"], e_g["sflux"], e_g["force"], ex["thermal"], e_g["umac"],
+                            *eargs, st["adv_bc"], st["pmask"])
+    avg_g = oracle.average(p, sold_g, p.rhoh_comp)
+    # ---- my slab
+    klo, khi = slab.slab_bounds(n[r], rank, world)
+    lo, hi = list(st["lo"]), list(st["hi"])
+    lo[r], hi[r] = klo, khi
+    phys_r = slab.slab_phys_bc(st["phys_bc"], dm, rank, world)
+    adv_s, adv_v = make_adv_bc(p, phys_r), make_adv_bc(q, phys_r)
+    pb_r = np.ascontiguousarray(np.array(phys_r, dtype=np.int32).T)
+    cut = lambda f, ng, nd=(0, 0, 0): take(f, lo, hi, ng, list(nd), dm)
+    worst = 0.0
+    ut, s_r = cut(vs["utilde"], vs["utilde"].ng), cut(sold_g, 4)
+    gpi, rhohalf, sponge = cut(ex["gpi"], 1), cut(ex["rhohalf"], 1), cut(ex["sponge"], 0)
+    unew = ut.clone()
+    um = [cut(umac0[d], 1, nod(d)) for d in range(dm)]
+    ops.velocity_advance(q, ut, unew, s_r, rhohalf, um, gpi, vs["w0"], ex["w0_force"], rho0, ex["rho0_nph"], ex["grav_old"],
+                         ex["grav_nph"], sponge, adv_v, vs["pmask"])
+    worst = max(worst, compare([(unew, unew_g, unew.ng, [0, 0, 0])] + [(um[d], um_v[d], 1, nod(d)) for d in range(dm)], lo, hi, dm))
+    um2 = face_fabs(lo, hi, 1, 1, dm, fill=-777.0)
+    ops.advance_premac(q, ut, s_r, um2, gpi, vs["w0"], ex["w0_force"], rho0, ex["grav_old"], adv_v, pb_r, vs["pmask"])
+    worst = max(worst, compare([(Fab_valid(um2[d]), Fab_valid_of(um_p[d], lo, hi, nod(d), dm), 0, nod(d)) for d in range(dm)], lo, hi, dm))
+    e = dict(sold=cut(e_in["sold"], 4), umac=[cut(e_in["umac"][d], 1, nod(d)) for d in range(dm)], force=cut(e_in["force"], 1),
+             sedge=[cut(sedge_in[d], 0, nod(d)) for d in range(dm)], sflux=face_fabs(lo, hi, 0, p.nscal, dm),
+             thermal=cut(ex["thermal"], 1))
+    e["snew"] = e["sold"].clone()
+    ops.enthalpy_advance(p, 2, e["sold"], e["snew"], e["sedge"], e["sflux"], e["force"], e["thermal"], e["umac"], *eargs, adv_s,
+                         st["pmask"])
+    worst = max(worst, compare([(e["snew"], e_g["snew"], 4, [0, 0, 0])] +
+                               [(e["sedge"][d], e_g["sedge"][d], 0, nod(d)) for d in range(dm)] +
+                               [(e["sflux"][d], e_g["sflux"][d], 0, nod(d)) for d in range(dm)], lo, hi, dm))
+    avg = ops.average(p, s_r, p.rhoh_comp)
+    worst = max(worst, float(np.abs(avg - avg_g).max() / np.abs(avg_g).max()))
+    finish(rank, local, worst)
+
+
+def Fab_valid(f):
+    """a ghost-free copy of a face fab (advance_premac writes the valid faces only)"""
+    out = Fab(f.lo, f.hi, 0, f.nc, nodal=f.nodal, dm=f.dm)
+    out.a[...] = f.valid()
+    return out
+
+
+def Fab_valid_of(glob, lo, hi, nodal, dm):
+    """ghost-free global face fab (take() then cuts the rank's region out of it)"""
+    out = Fab(glob.lo, glob.hi, 0, glob.nc, nodal=glob.nodal, dm=dm)
+    out.a[...] = glob.valid()
+    return out
+
+
 def main():
     dm = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     bcset = sys.argv[2] if len(sys.argv) > 2 else "periodic"
@@ -99,6 +209,8 @@ def main():
     r = dm - 1
     if bcset == "sphr":
         return sphr_main(rank, world, local, ops, exact)
+    if bcset.startswith("episodes-"):
+        return episodes_main(rank, world, local, ops, dm, bcset.split("-", 1)[1], ppm_type, exact)
     n = ([16, 12, 8 * world] if exact else [40, 12, 20 * world]) if dm == 3 else [24, 10 * world]  # FAST: >= 4 ng planes per slab, so the overlapped exchange of the updated boundary planes runs
     walls = [[abi.PERIODIC, abi.PERIODIC]] * (dm - 1) + [[abi.SLIP_WALL, abi.OUTLET]]
     phys = None if bcset == "periodic" else walls

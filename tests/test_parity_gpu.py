@@ -475,7 +475,10 @@ def test_density_advance_bds(gpu_ops, oracle, dm, n, spt, exact):
 # ---- multi-GPU: slab partition + NCCL halo exchange (needs >= 2 GPUs; run with gpurun --gpus 2) -------------
 @pytest.mark.parametrize("dm,bcset,ppm_type,exact", [(3, "periodic", 1, 1), (3, "walls", 2, 1), (2, "walls", 2, 1),
                                                       (3, "periodic", 1, 0), (3, "periodic", 2, 0),
-                                                      (3, "sphr", 1, 1), (3, "sphr", 1, 0)])
+                                                      (3, "sphr", 1, 1), (3, "sphr", 1, 0),
+                                                      # velocity_advance, advance_premac, enthalpy_advance, average
+                                                      (3, "episodes-periodic", 1, 1), (3, "episodes-walls", 2, 1),
+                                                      (2, "episodes-walls", 1, 0), (3, "episodes-periodic", 2, 0)])
 def test_multi_gpu_density_advance(gpu_ops, dm, bcset, ppm_type, exact):
     import os
     import subprocess
