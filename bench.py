@@ -557,8 +557,10 @@ def selftest(ops, rank, world, local_rank, dev):
         oks = [ln for ln in r.stdout.splitlines() if ln.startswith("RANK")]
         res["dm%s_%s_ppm%s_%s" % (c[0], c[1], c[2], "exact" if c[3] == "1" else "fast")] = {"rc": r.returncode, "ranks": oks}
     ok = all(v["rc"] == 0 for v in res.values())
-    print(json.dumps({"selftest": "multi-rank density_advance against the single-box oracle, NCCL halo exchange in "
-                                  "every ghost fill", "n_gpus": world, "ok": ok, "cases": res}))
+    print(json.dumps({"selftest": "multi-rank episodes (density_advance; episodes-*: velocity_advance, advance_premac, "
+                                  "enthalpy_advance, average, firstdt) against the single-box oracle, NCCL halo exchange "
+                                  "in every ghost fill, NCCL min / max / sum in the reductions",
+                      "n_gpus": world, "ok": ok, "cases": res}))
     sys.exit(0 if ok else 1)
 
 

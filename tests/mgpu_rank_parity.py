@@ -178,6 +178,32 @@ def episodes_main(rank, world, local, ops, dm, bcset, ppm_type, exact):
                                [(e["sflux"][d], e_g["sflux"][d], 0, nod(d)) for d in range(dm)], lo, hi, dm))
     avg = ops.average(p, s_r, p.rhoh_comp)
     worst = max(worst, float(np.abs(avg - avg_g).max() / np.abs(avg_g).max()))
+    # firstdt (gamma-law EOS set in both libraries): min / max over the ranks, exact
+    e_ = abi.mgpu_eos()
+    e_.kind, e_.assume_neutral, e_.nspec, e_.gamma, e_.k_B, e_.n_A = 1, 1, p.nspec, 5.0 / 3.0, 1.3806488e-16, 6.02214129e23
+    for k in ("mintemp", "mindens", "mine", "minp", "minh"):
+        setattr(e_, k, 1e-200)
+    for k in ("maxtemp", "maxdens", "maxe", "maxp", "maxh"):
+        setattr(e_, k, 1e200)
+    for m in range(p.nspec):
+        e_.aion[m], e_.zion[m] = 4.0 * (m + 1), 2.0 * (m + 1)
+    sT_g = sold_g.clone()
+    sT_g.a[p.temp_comp - 1] = 10.0 ** rng.uniform(3.0, 5.0, size=sT_g.a[0].shape)
+    divU_g = Fab(st["lo"], st["hi"], 1, 1, dm=dm)
+    divU_g.a[...] = rng.uniform(-30, 30, size=divU_g.shape)
+    gamma1bar = 1.4 + 0.1 * np.cos(2 * np.pi * zr)
+    p0 = 10.0 * np.exp(-zr / 0.4)
+    for o in (oracle, ops):
+        o.set_eos(e_)
+    want = oracle.firstdt(q, vs["utilde"], ex["gpi"], sT_g, divU_g, rho0, p0, ex["grav_old"], gamma1bar, 0.5, 0.1, 1.0e20,
+                          use_soundspeed_firstdt=True, use_divu_firstdt=True)
+    got = ops.firstdt(q, ut, gpi, cut(sT_g, 4), cut(divU_g, 1), rho0, p0, ex["grav_old"], gamma1bar, 0.5, 0.1, 1.0e20,
+                      use_soundspeed_firstdt=True, use_divu_firstdt=True)
+    for o in (oracle, ops):
+        o.set_eos(None)
+    if got != want:
+        print("RANK %d firstdt %r != %r" % (rank, got, want), flush=True)
+        worst = 1.0
     finish(rank, local, worst)
 
 
