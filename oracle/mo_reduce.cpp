@@ -4,7 +4,9 @@
 //   sum_etarho_2d   Source/make_eta.f90:176   sum_etarho_3d   Source/make_eta.f90:213
 //   estdt_3d_sphr   Source/estdt.f90:620
 //   make_etarho_planar Source/make_eta.f90:36 (single level, one chunk: r_end_coord = nr-1)
-// Same loops, same order, same expressions.
+//   average         Source/average.f90:24 (planar :114-163; spherical :168-362 for one level) + sum_phi_3d_sphr :564
+// Same loops, same order, same expressions.  average: parity unpinned (the reference holds no numbers for it); the
+// tests anchor it on fields whose average is known (tests/test_average.py).
 #include <algorithm>
 #include <cmath>
 #include <limits>
