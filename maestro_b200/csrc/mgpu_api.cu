@@ -143,6 +143,53 @@ static inline cmask_t crange(int c0, int nc) {  // components c0 .. c0+nc-1 (0-b
   for (int c = c0; c < c0 + nc; ++c) m |= (1ull << c);
   return m;
 }
+// ---- asynchronous uploads ---------------------------------------------------------------------------------------------
+// A host-pointer call normally issues its host-to-device copies on the compute stream, so the first kernel starts after
+// the last byte has arrived.  An episode that knows the order in which it consumes its inputs (density_advance in its
+// lean+ form) switches uploads to a copy stream instead: every component is one copy + one event, and the episode makes
+// the compute stream wait for a component right before the first kernel that reads it (uploads_wait_range).  The PCIe
+// transfer of component n+1 then runs under the edge kernel of component n.
+struct PendingUpload {
+  const double *b, *e;  // device range
+  cudaEvent_t ev;
+};
+static bool g_async_uploads = false;       // set by the entry point for the duration of its view() calls
+static int g_opt_async_upload = 1;         // option "async_upload"
+static cudaStream_t g_copy_stream = nullptr;
+static std::vector<PendingUpload> g_pending;
+static std::vector<cudaEvent_t> g_ev_pool;
+static cudaEvent_t upload_event() {
+  if (g_ev_pool.empty()) {
+    cudaEvent_t e;
+    MGPU_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return e;
+  }
+  cudaEvent_t e = g_ev_pool.back();
+  g_ev_pool.pop_back();
+  return e;
+}
+// the compute stream waits for every pending upload that overlaps [b, e)
+static void uploads_wait_range(const double* b, const double* e) {
+  for (size_t i = 0; i < g_pending.size();) {
+    if (g_pending[i].b < e && b < g_pending[i].e) {
+      MGPU_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_pending[i].ev, 0));
+      g_ev_pool.push_back(g_pending[i].ev);
+      g_pending[i] = g_pending.back();
+      g_pending.pop_back();
+    } else {
+      ++i;
+    }
+  }
+}
+static void uploads_wait_all() {
+  for (auto& p : g_pending) {
+    MGPU_CUDA(cudaStreamWaitEvent(g_ctx.stream, p.ev, 0));
+    g_ev_pool.push_back(p.ev);
+  }
+  g_pending.clear();
+}
+static void uploads_wait_comp(const DV& f, int c) { uploads_wait_range(f.p + f.cs * c, f.p + f.cs * (c + 1)); }
+
 // ---- residency registry (lifecycle) ---------------------------------------------------------
 // A host fab registered with mgpu_register keeps ONE device mirror for as long as it is registered.  Per component
 // the registry knows which side holds the truth:
@@ -173,6 +220,12 @@ struct Call {
     arena_reset();
   }
   ~Call() {
+    if (!g_pending.empty()) {  // an exception cut the call short: let the copies finish before their buffers are reused
+      cudaStreamSynchronize(g_copy_stream);
+      for (auto& p : g_pending) g_ev_pool.push_back(p.ev);
+      g_pending.clear();
+    }
+    g_async_uploads = false;
     for (auto& it : items)
       if (!it.res) g_pool.put(it.d);
   }
@@ -195,9 +248,19 @@ struct Call {
     DV v = make_view(f, P.dm);
     auto upload = [&](double* d, cmask_t comps) {
       for_runs(comps, f.nc, [&](int c0, int n) {
+        g_h2d_bytes += (long)v.cs * n * (long)sizeof(double);
+        if (g_async_uploads) {  // one copy + one event per component, on the copy stream (see uploads_wait_range)
+          for (int c = c0; c < c0 + n; ++c) {
+            MGPU_CUDA(cudaMemcpyAsync(d + v.cs * c, f.ptr + v.cs * c, (size_t)v.cs * sizeof(double), cudaMemcpyHostToDevice,
+                                      g_copy_stream));
+            cudaEvent_t ev = upload_event();
+            MGPU_CUDA(cudaEventRecord(ev, g_copy_stream));
+            g_pending.push_back({d + v.cs * c, d + v.cs * (c + 1), ev});
+          }
+          return;
+        }
         MGPU_CUDA(cudaMemcpyAsync(d + v.cs * c0, f.ptr + v.cs * c0, (size_t)v.cs * n * sizeof(double),
                                   cudaMemcpyHostToDevice, g_ctx.stream));
-        g_h2d_bytes += (long)v.cs * n * (long)sizeof(double);
       });
     };
     const cmask_t all = f.nc >= 64 ? ALLC : ((cmask_t(1) << f.nc) - 1);
@@ -245,6 +308,8 @@ struct Call {
     for (int d = 0; d < P.dm; ++d) v[d] = view(f[d][i], in, out);
   }
   void finish() {
+    uploads_wait_all();  // nothing may still be in flight when the results travel back (or the call returns)
+    g_async_uploads = false;
     if (!host) return;
     for (auto& it : items) {
       if (it.res) {  // registered: the results stay on the device until mgpu_download
@@ -380,11 +445,19 @@ static void density_advance_leanplus(const mgpu_params& P, int which_step, DV& s
   const double* wadd_d = upload_small(wadd.data(), wadd.size());
   int nodal_d[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
 
+  // uploads still in flight (host-pointer call on one rank, see uploads_wait_range): the species are then waited for
+  // and ghost-filled one by one, right before the edge kernel that reads them
+  const bool piped = !g_pending.empty();
+  if (piped) {
+    for (int d = 0; d < dm; ++d) uploads_wait_comp(umac[d], 0);
+    uploads_wait_comp(sold, P.rho_comp - 1);
+  }
   {  // one batch: ghost cells of umac, of the raw rho / rhoX inputs and of the density force.  The inputs travel
      // (communication stream) while the force is built from the valid cells (modify_scal_force, :119-128)
     FillBatch fb;
     for (int d = 0; d < dm; ++d) fill_boundary_dev(P, umac[d], lo, hi, 1, nodal_d[d], 1, 1, 1, adv_bc, pmask, false);
-    fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
+    if (!piped)
+      fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
     fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rho_comp, dm + P.rho_comp, 1, adv_bc, pmask, false);
     if (g_opt_overlap) fb.start_exchange();
     set_dev(scal_force.p + scal_force.cs * (P.rho_comp - 1), 0.0, scal_force.cs);
@@ -398,15 +471,25 @@ static void density_advance_leanplus(const mgpu_params& P, int which_step, DV& s
   double* rinv = arena_alloc((size_t)sold.cs);
   recip_dev(rinv, sold.p + sold.cs * (P.rho_comp - 1), sold.cs);
   const double* rho_p = rinv;
-  for (int n = 0; n < P.nspec; ++n)  // X = rhoX / rho, zero force (:178-186)
+  for (int n = 0; n < P.nspec; ++n) {  // X = rhoX / rho, zero force (:178-186)
+    if (piped) {
+      uploads_wait_comp(sold, P.spec_comp - 1 + n);
+      FillBatch fb;
+      fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp + n, dm + P.spec_comp + n, 1, adv_bc, pmask, false);
+      fb.run();
+    }
     edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, P.spec_comp - 1 + n, dm + P.spec_comp + n, false,
                   false, ng_s, ng_f, true, rho_p, nullptr, wadd_d);
+  }
   // rho' = rho - rho0 (or rho itself for predict_rho_and_X), with its force (:216-224)
   edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, P.rho_comp - 1, dm + P.rho_comp, false, false, ng_s,
                 ng_f, false, nullptr, spt == MGPU_PREDICT_RHOPRIME_AND_X ? sub_d : nullptr, wadd_d);
-  for (int n = 0; n < P.ntrac; ++n)  // tracers (:242-252)
+  for (int n = 0; n < P.ntrac; ++n) {  // tracers (:242-252)
+    if (piped) uploads_wait_comp(sold, P.trac_comp - 1 + n);
     edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, P.trac_comp - 1 + n, dm + P.trac_comp + n, false,
                   false, ng_s, ng_f, true, nullptr, nullptr, wadd_d);
+  }
+  uploads_wait_all();
 
   FluxArgs fa;
   fill_flux_args(P, fa, lo, hi);
@@ -489,6 +572,7 @@ static void density_advance_dev(const mgpu_params& P, int which_step, DV& sold, 
                              (which_step == 1) ? rho0_edge_old : rho0_edge_new, rho0_pe, lo, hi, ng_s, ng_f, adv_bc, pmask);
     return;
   }
+  uploads_wait_all();  // (only the lean+ episode consumes its inputs component by component)
   if (lean) set_dev(scal_force.p + scal_force.cs * (P.rho_comp - 1), 0.0, scal_force.cs);
   else set_dev(scal_force.p, 0.0, scal_force.size());  // :101-103
   if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {  // :119-128
@@ -1722,6 +1806,7 @@ int mgpu_init(int device) {
   g_ctx.device = device;
   MGPU_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
   g_ctx.own_stream = true;
+  if (!g_copy_stream) MGPU_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
   g_ctx.initialised = true;
   MGPU_CATCH
 }
@@ -1761,6 +1846,7 @@ int mgpu_set_option(const char* key, int value) {
   std::string k(key ? key : "");
   if (k == "fused") g_opt_fused = value;
   else if (k == "kchunk") g_opt_kchunk = value;
+  else if (k == "async_upload") g_opt_async_upload = value;
   else if (k == "exact") { g_opt_exact = value; bds_set_fast(value == 0); velpred_set_fast(value == 0); }
   else if (k == "leanplus") g_opt_leanplus = value;
   else if (k == "split_tiles") fused_edge3_set_split(value);
@@ -2242,6 +2328,11 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
   // lean+ form: sold and umac are not rewritten and every ghost cell of the advanced components of snew is refilled,
   // so neither needs to travel back / in over PCIe
   const bool leanp = density_advance_is_leanplus(*p, adv_bc, pmask);
+  // lean+ on one rank consumes its inputs in a known order (umac, rho, species one by one, tracers): uploads go to the
+  // copy stream in that order and the episode waits for each component where it first reads it
+  g_async_uploads = leanp && c.host && g_opt_async_upload && comm_size() == 1 && p->dm == 3;
+  DV se[3], sf[3], um[3];
+  c.views((const mgpu_fab* const*)umac, 0, true, !leanp, um);
   // sold: rho and species are transformed in place and restored (round trips); tracers are read only
   DV so = c.view(*sold, adv, leanp ? (cmask_t)0 : (crange(p->rho_comp - 1, 1) | crange(p->spec_comp - 1, p->nspec)));
   // snew: only the advanced components are written; their ghost corners next to physical walls keep the caller's
@@ -2249,10 +2340,9 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
   DV sn = c.view(*snew, leanp ? (cmask_t)0 : adv, adv);
   DV fv = c.view(*scal_force, (cmask_t)0, (cmask_t)0);  // zeroed on entry (:101) and again before the update (:349)
   DV eta = c.view(*etarhoflux, true, true);
-  DV se[3], sf[3], um[3];
   c.views((const mgpu_fab* const*)sedge, 0, (cmask_t)0, edg, se);  // every face of the predicted components is written
   c.views((const mgpu_fab* const*)sflux, 0, (cmask_t)0, flx, sf);
-  c.views((const mgpu_fab* const*)umac, 0, true, !leanp, um);
+  g_async_uploads = false;  // (pending uploads stay pending until the episode or finish() waits for them)
   c.zero_on_host(*scal_force);
   density_advance_dev(*p, which_step, so, sn, se, sf, fv, um, w0, eta, rho0_old, rho0_new, rho0_predicted_edge,
                       sold->lo, sold->hi, sold->ng, scal_force->ng, adv_bc, pmask);
