@@ -113,7 +113,9 @@ long mgpu_launch_count(int reset);
 /* tuning/testing switches: "fused" (1: fused 3-D edge kernel when applicable, 0: staged general path),
  * "kchunk" (z planes per CTA of the fused kernel), "exact" (1: bit-identical fp64 expression trees everywhere;
  * 0 (default): the FAST builds of the edge-state, BDS and mkutrans / velpred kernels -- dt/dx folded, divisions as
- * multiplications by reciprocals, FMA contraction -- <= 1e-12 relative from the reference) */
+ * multiplications by reciprocals, FMA contraction -- <= 1e-12 relative from the reference), "premac_fuse" (1: on a box
+ * without physical boundaries advance_premac forms utrans inside velpred's face kernel), "defaults" (value ignored:
+ * every switch back to its initial value) */
 int mgpu_set_option(const char* key, int value);
 /* per-kernel-class device timing with CUDA events on the launching stream (bench roofline line):
  * mgpu_profile(1) starts/reset, mgpu_profile_get(tag,...) returns accumulated ms and launch count.
@@ -446,6 +448,13 @@ int mgpu_enthalpy_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, 
 int mgpu_estdt(const mgpu_params* p, int nfabs, const mgpu_fab* u, const mgpu_fab* s, const mgpu_fab* force,
                const mgpu_fab* divU, const mgpu_fab* dSdt, const double* w0, const double* p0,
                const double* gamma1bar, double rho_min, double cflfac, double* dt, double* umax);
+/* multifab_min_c / multifab_max_c (FBoxLib multifab_f.f90) over the valid zones of component `comp` (1-based) of
+ * one level, reduced over the ranks: the `verbose >= 1` report of density_advance.f90:374-402 (species as X = rhoX / rho:
+ * pass div_comp = rho_comp; 0: no division; the state is left untouched where the reference divides and multiplies
+ * back), enthalpy_advance.f90:440-449 and velocity_advance.f90:142-160.  The caller prints the lines (formats 2000-2003,
+ * 1001-1003 of those files). */
+int mgpu_minmax(const mgpu_params* p, int nfabs, const mgpu_fab* s, int comp, int div_comp, double* smin, double* smax);
+
 /* estdt for spherical geometry (estdt_3d_sphr, Source/estdt.f90:620): w0mac = make_w0mac's face fabs (zero when
  * evolve_base_state is off, :100-110); gp0 (:734-739) and its put_1d_array_on_cart (:741) happen inside. */
 int mgpu_estdt_sphr(const mgpu_params* p, const mgpu_geom* g, int nfabs, const mgpu_fab* u, const mgpu_fab* s,

@@ -125,6 +125,7 @@ OPERATORS = {
     "velocity_advance": (C.c_int, [P_, F_, F_, F_, F_, FF_, F_] + [c_double_p] * 6 + [F_] + [c_int_p] * 2),
     "enthalpy_advance": (C.c_int, [P_, C.c_int, F_, F_, FF_, FF_, F_, F_, FF_] + [c_double_p] * 11 + [c_int_p] * 2),
     "estdt": (C.c_int, [P_, C.c_int, F_, F_, F_, F_, F_] + [c_double_p] * 3 + [C.c_double] * 2 + [c_double_p] * 2),
+    "minmax": (C.c_int, [P_, C.c_int, F_, C.c_int, C.c_int, c_double_p, c_double_p]),
     "make_etarho_planar": (C.c_int, [P_, C.c_int, F_, c_double_p, c_double_p]),
     "estdt_sphr": (C.c_int, [P_, G_, C.c_int, F_, F_, F_, F_, F_, FF_] + [c_double_p] * 3 + [C.c_double] * 2
                    + [c_double_p] * 2),

@@ -28,6 +28,7 @@ static int g_opt_fused = 1;    // use the fused 3-D edge kernel when it covers t
 static int g_opt_kchunk = -1;  // z planes per CTA of the fused kernels; < 0: chosen per launch (fused2_auto_kchunk)
 static int g_opt_overlap = 1;   // slab runs: exchange the updated boundary planes while the interior is updated
 static int g_opt_leanplus = 1;  // density_advance: on-the-fly input transforms where the upwind-first kernel applies
+static int g_opt_premac_fuse = 1;  // advance_premac: utrans formed inside the face kernel of velpred where no physical boundary is near
 static int g_opt_exact = 0;    // 1: bit-identical arithmetic everywhere (fused kernel built with -fmad=false)
 Context& ctx() { return g_ctx; }
 
@@ -962,8 +963,8 @@ static void vel_force_dev(const mgpu_params& P, DV& force, bool is_final, const 
 static size_t advance_premac_scratch(const mgpu_params& P, const int* lo, const int* hi, int ng_u) {
   const int ng_f = P.ppm_trace_forces == 1 ? ng_u : 1;
   return fab_bytes(lo, hi, P.dm, ng_u, 0, P.dm) + fab_bytes(lo, hi, P.dm, ng_f, 0, P.dm) +
-         P.dm * fab_bytes(lo, hi, P.dm, 1, 1, 1) + velpred_scratch(P, lo, hi) + (size_t)(6 * (P.nr + 2)) * sizeof(double) +
-         8192;
+         (P.dm + 1) * fab_bytes(lo, hi, P.dm, 1, 1, 1) + velpred_scratch(P, lo, hi) +
+         (size_t)(6 * (P.nr + 2)) * sizeof(double) + 8192;
 }
 static void advance_premac_dev(const mgpu_params& P, const DV& uold, const DV& sold, DV* umac, const DV& gpi,
                                const double* w0_h, const double* w0_force_h, const double* rho0_old_h,
@@ -976,13 +977,32 @@ static void advance_premac_dev(const mgpu_params& P, const DV& uold, const DV& s
   const double* rho0_old = upload_small(rho0_old_h, nr);
   const double* grav = upload_small(grav_h, nr);
   int z3[3] = {0, 0, 0};
-  DV ufull = arena_fab(lo, hi, dm, ng_u, z3, dm), force = arena_fab(lo, hi, dm, ng_f, z3, dm);
+  const bool fuse = g_opt_premac_fuse && velpred_premac_fusable(P, phys_bc);
+  // fused path: the face kernel forms ufull = w0 on the cells + uold (:75-78) per cell; only traced forces read the
+  // array again afterwards
+  const bool need_ufull = !fuse || P.ppm_trace_forces == 1;
+  DV ufull = need_ufull ? arena_fab(lo, hi, dm, ng_u, z3, dm) : make_view(nullptr, lo, hi, dm, ng_u, z3, dm);
+  DV force = arena_fab(lo, hi, dm, ng_f, z3, dm);
   DV utrans[3];
   for (int d = 0; d < dm; ++d) utrans[d] = arena_fab(lo, hi, dm, 1, NODAL_D[d], 1);
-  radial_cell_avg_dev(P, ufull, w0, lo, hi);  // :75 put_1d_array_on_cart(w0, ufull, 1, .true., .true.)
-  fill_boundary_dev(P, ufull, lo, hi, ng_u, nullptr, 1, 1, dm, adv_bc, pmask, false);
-  if (ufull.size() != uold.size()) throw Error("advance_premac: internal size mismatch");
-  add_dev(ufull.p, uold.p, ufull.size());  // :76-78
+  if (need_ufull) {
+    radial_cell_avg_dev(P, ufull, w0, lo, hi);  // :75 put_1d_array_on_cart(w0, ufull, 1, .true., .true.)
+    fill_boundary_dev(P, ufull, lo, hi, ng_u, nullptr, 1, 1, dm, adv_bc, pmask, false);
+    if (ufull.size() != uold.size()) throw Error("advance_premac: internal size mismatch");
+    add_dev(ufull.p, uold.p, ufull.size());  // :76-78
+  }
+  if (fuse) {
+    // no physical boundary: utrans (:90), utrans + w0 (:109) and the face states of velpred (:116) come from one
+    // reconstruction per direction, ghost rows included, so neither ghost fill of utrans is needed
+    DV utfull[3];
+    for (int d = 0; d < dm; ++d) utfull[d] = (d == dm - 1) ? arena_fab(lo, hi, dm, 1, NODAL_D[d], 1) : utrans[d];
+    VpArgs st;
+    velpred_premac_begin(P, uold, ufull, utrans, utfull, w0, lo, hi, adv_bc, phys_bc, ng_u, &st);
+    vel_force_dev(P, force, false, uold, utrans, w0, gpi, sold.comp(P.rho_comp - 1), rho0_old, grav, w0_force, lo, hi,
+                  ng_f, adv_bc, pmask);  // :98
+    velpred_premac_finish(P, &st, umac, force, ng_u, ng_f);
+    return;
+  }
   mkutrans_dev(P, uold, ufull, utrans, w0, lo, hi, adv_bc, phys_bc, ng_u);  // :90
   fill_faces_dev(P, utrans, lo, hi, adv_bc, pmask);
   vel_force_dev(P, force, false, uold, utrans, w0, gpi, sold.comp(P.rho_comp - 1), rho0_old, grav, w0_force, lo, hi, ng_f,
@@ -1844,11 +1864,18 @@ int mgpu_finalize(void) {
 int mgpu_set_option(const char* key, int value) {
   MGPU_TRY
   std::string k(key ? key : "");
-  if (k == "fused") g_opt_fused = value;
+  if (k == "defaults") {  // every switch back to its initial value (tests call this between cases)
+    g_opt_fused = 1; g_opt_kchunk = -1; g_opt_async_upload = 1; g_opt_exact = 0; g_opt_leanplus = 1;
+    g_opt_premac_fuse = 1; g_opt_overlap = 1;
+    bds_set_fast(1); velpred_set_fast(1); fused_edge3_set_split(1); fused_edge_set_variant(1);
+    fused_edge2_set_by(MGPU_FUSED2_BY); fused_edge2d_set_tile(2);
+  }
+  else if (k == "fused") g_opt_fused = value;
   else if (k == "kchunk") g_opt_kchunk = value;
   else if (k == "async_upload") g_opt_async_upload = value;
   else if (k == "exact") { g_opt_exact = value; bds_set_fast(value == 0); velpred_set_fast(value == 0); }
   else if (k == "leanplus") g_opt_leanplus = value;
+  else if (k == "premac_fuse") g_opt_premac_fuse = value;
   else if (k == "split_tiles") fused_edge3_set_split(value);
   else if (k == "overlap") g_opt_overlap = value;
   else if (k == "fused_variant") fused_edge_set_variant(value);
@@ -3094,6 +3121,34 @@ int mgpu_estdt(const mgpu_params* p, int nfabs, const mgpu_fab* u, const mgpu_fa
     for (int d = 1; d < dm; ++d) dt_lev = std::min(dt_lev, p->dx[d]);
   }
   *dt = std::min(*dt, dt_lev);  // :220
+  c.finish();
+  MGPU_CATCH
+}
+
+int mgpu_minmax(const mgpu_params* p, int nfabs, const mgpu_fab* s, int comp, int div_comp, double* smin, double* smax) {
+  MGPU_TRY
+  if (nfabs < 1) throw Error("mgpu_minmax: needs at least one box");
+  Call c(p, (size_t)(2 * 148 * 8 + 64) * sizeof(double) * (size_t)nfabs + 8192);
+  double mn = std::numeric_limits<double>::max(), mx = -std::numeric_limits<double>::max();  // fab.f90: Huge(r) / -Huge(r)
+  for (int i = 0; i < nfabs; ++i) {
+    if (comp < 1 || comp > s[i].nc || div_comp > s[i].nc) throw Error("mgpu_minmax: component out of range");
+    cmask_t in = crange(comp - 1, 1);
+    if (div_comp >= 1) in |= crange(div_comp - 1, 1);
+    DV sv = c.view(s[i], in, (cmask_t)0);
+    minmax_box_dev(*p, sv, s[i].lo, s[i].hi, comp - 1, div_comp >= 1 ? div_comp - 1 : -1, &mn, &mx);
+  }
+  if (comm_size() > 1) {  // parallel_reduce MPI_MIN / MPI_MAX (multifab_f.f90 multifab_min_c / _max_c): one MIN over (min, -max)
+    double h[2] = {mn, -mx};
+    double* d = arena_alloc(2);
+    MGPU_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, g_ctx.stream));
+    allreduce_dev(d, 2, 1);
+    MGPU_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, g_ctx.stream));
+    MGPU_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    mn = h[0];
+    mx = -h[1];
+  }
+  *smin = mn;
+  *smax = mx;
   c.finish();
   MGPU_CATCH
 }

@@ -305,4 +305,54 @@ void plane_sums_dev(const mgpu_params& P, const DV& f, const int* lo, const int*
   MGPU_CUDA(cudaStreamSynchronize(cx.stream));
 }
 
+// multifab_min_c / multifab_max_c of one box (the `verbose >= 1` lines of density_advance.f90:374-402,
+// enthalpy_advance.f90:440-449, velocity_advance.f90:142-160): grid-stride running min / max per thread, warp shuffles,
+// per-CTA partials, the last few hundred partials on the host (min and max are exact in any order: bit-identical).
+// dcomp >= 0: the value is s(comp) / s(dcomp) (multifab_div_div_c before the reduction; the state stays as it is --
+// the reference multiplies it back, one rounding away from what it had).
+__global__ void __launch_bounds__(256) k_minmax(DV s, Box3 vb, int comp, int dcomp, double* out) {
+  const long nx = vb.hi[0] - vb.lo[0] + 1, ny = vb.hi[1] - vb.lo[1] + 1, nz = vb.hi[2] - vb.lo[2] + 1;
+  const long rows = ny * nz;
+  double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308;
+  for (long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int j = vb.lo[1] + (int)(r % ny), k = vb.lo[2] + (int)(r / ny);
+    for (long t = threadIdx.x; t < nx; t += blockDim.x) {
+      const int i = vb.lo[0] + (int)t;
+      double v = s(i, j, k, comp);
+      if (dcomp >= 0) v = v / s(i, j, k, dcomp);
+      lo = fmin(lo, v);
+      hi = fmax(hi, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ double shl[8], shh[8];
+  if ((threadIdx.x & 31) == 0) { shl[threadIdx.x >> 5] = lo; shh[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { lo = fmin(lo, shl[w]); hi = fmax(hi, shh[w]); }
+    out[2 * blockIdx.x] = lo;
+    out[2 * blockIdx.x + 1] = hi;
+  }
+}
+void minmax_box_dev(const mgpu_params& P, const DV& s, const int* lo, const int* hi, int comp, int dcomp, double* mn,
+                    double* mx) {
+  Context& cx = ctx();
+  const Box3 vb = grown(lo, hi, P.dm, 0);
+  const long rows = (long)(vb.hi[1] - vb.lo[1] + 1) * (vb.hi[2] - vb.lo[2] + 1);
+  const int nb = (int)std::min<long>(rows, 148 * 8);
+  double* d = arena_alloc((size_t)2 * nb);
+  MGPU_TIMED(TAG_GLUE, (k_minmax<<<nb, 256, 0, cx.stream>>>(s, vb, comp, dcomp, d)));
+  std::vector<double> h((size_t)2 * nb);
+  MGPU_CUDA(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, cx.stream));
+  MGPU_CUDA(cudaStreamSynchronize(cx.stream));
+  for (int b = 0; b < nb; ++b) {
+    *mn = std::min(*mn, h[2 * b]);
+    *mx = std::max(*mx, h[2 * b + 1]);
+  }
+}
+
 }  // namespace mgpu

@@ -17,6 +17,11 @@ void estdt_box_dev(const mgpu_params& P, const DV& u, const DV& s, const DV& for
 // sums of the slab-direction planes k0..k1 of a single-component fab over the valid transverse cells -> host
 void plane_sums_dev(const mgpu_params& P, const DV& f, const int* lo, const int* hi, int k0, int k1, double* sums_h);
 
+// min / max of component comp (0-based; divided by component dcomp when dcomp >= 0) over the valid cells of one box,
+// folded into *mn / *mx
+void minmax_box_dev(const mgpu_params& P, const DV& s, const int* lo, const int* hi, int comp, int dcomp, double* mn,
+                    double* mx);
+
 // average() with spherical == 1 (average.f90:168-362), one level: the binning of one box (atomics into phisum / ncell,
 // nr_irreg + 1 bins, radii(0:nr_irreg+1) on the device) and the host tail (normalise, drop the empty radii, interpolate)
 void sum_phi_sphr_dev(const mgpu_params& P, const mgpu_geom& g, const DV& phi1, const int* lo, const int* hi,

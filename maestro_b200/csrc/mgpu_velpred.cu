@@ -160,8 +160,14 @@ __global__ void __launch_bounds__(256) k_mkutrans(VpArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-template <int D, int PPM>
-__global__ void __launch_bounds__(256) k_vp_face(VpArgs a) {
+// UT = true (advance_premac on a box without physical boundaries, `velpred_premac_begin`): the face's transverse
+// velocity is formed here as well -- mkutrans reconstructs u_d along d exactly as this kernel does (mkutrans.f90:529,
+// 641,749 against velpred.f90:803,933,1063: the same ppm_3d call on the same data), so the d-component's (ul, ur) pair
+// goes through mkutrans' Riemann problem (mkutrans.f90:618-631) and the kernel stores utrans (for mk_vel_force) and
+// utrans + w0 (addw0, advance_premac.f90:109) on the whole face box, ghost rows included: no k_mkutrans launches, no
+// addw0, no ghost fill of utrans.
+template <int D, int PPM, bool UT>
+__device__ __forceinline__ void vp_face_body(const VpArgs& a) {
   constexpr int d = D;
   __shared__ double sh_ip[3][256];
   int ix[3], slot;
@@ -174,8 +180,18 @@ __global__ void __launch_bounds__(256) k_vp_face(VpArgs a) {
   const long st = a.utilde.stride(d);
   double ul[3], ur[3];
   if (in) {  // this cell's states in direction d, every component: Ip feeds the face above, Im this thread's face
-    const DV ufd = a.ufull.comp(d);
-    const double uc = ufd.p[ufd.off(ix[0], ix[1], ix[2])];
+    double uc;
+    if (UT && a.ufull_otf) {  // ufull = w0 on the cells + utilde (advance_premac.f90:75-78) formed here: the cell average
+      uc = a.utilde.p[uo + a.utilde.cs * d];  // of w0 at the periodic image of a ghost cell is what the ghost fill copies
+      if (d == dm - 1) {
+        int kk = ix[d] % a.nr;
+        if (kk < 0) kk += a.nr;
+        uc = 0.5 * (a.w0[kk] + a.w0[kk + 1]) + uc;
+      }
+    } else {
+      const DV ufd = a.ufull.comp(d);
+      uc = ufd.p[ufd.off(ix[0], ix[1], ix[2])];
+    }
     _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) {
       const LineBC b = make_linebc(dm, d, a.lo[d], a.hi[d], a.bclo[c][d], a.bchi[c][d]);
       const double* q = a.utilde.p + uo + a.utilde.cs * c;
@@ -187,7 +203,7 @@ __global__ void __launch_bounds__(256) k_vp_face(VpArgs a) {
   __syncthreads();
   if (!in || first) return;
   _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ul[c] = sh_ip[c][vp_left<D>(slot)];
-  if (ix[d] == a.lo[d]) {
+  if (!UT && ix[d] == a.lo[d]) {
     const int p = a.plo[d];
     if (p == MGPU_BC_INLET) {
       _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ul[c] = ur[c] = a.utilde.p[uo - st + a.utilde.cs * c];
@@ -208,7 +224,7 @@ __global__ void __launch_bounds__(256) k_vp_face(VpArgs a) {
       }
     }
   }
-  if (ix[d] == a.hi[d] + 1) {
+  if (!UT && ix[d] == a.hi[d] + 1) {
     const int p = a.phi[d];
     if (p == MGPU_BC_INLET) {
       _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ul[c] = ur[c] = a.utilde.p[uo + a.utilde.cs * c];
@@ -224,7 +240,17 @@ __global__ void __launch_bounds__(256) k_vp_face(VpArgs a) {
       _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) ur[c] = ul[c];
     }
   }
-  const double ut = a.utrans[d](ix[0], ix[1], ix[2]);
+  double ut;
+  if (UT) {
+    const bool radial = d == dm - 1;  // planar only (velpred_premac_fusable)
+    const double w0f = radial ? a.w0[ix[d]] : 0.0;
+    const double upre = riemann_full(ul[d], ur[d], radial, w0f, a.rel_eps);
+    ut = radial ? upre + w0f : upre;
+    a.utpre[d](ix[0], ix[1], ix[2]) = upre;
+    if (radial) a.utrans[d](ix[0], ix[1], ix[2]) = ut;
+  } else {
+    ut = a.utrans[d](ix[0], ix[1], ix[2]);
+  }
   const long to = a.UL[d].off(ix[0], ix[1], ix[2]);
   _Pragma("unroll") for (int c = 0; c < 3; ++c) if (c < dm) {
     a.UL[d].p[to + a.UL[d].cs * c] = ul[c];
@@ -232,6 +258,10 @@ __global__ void __launch_bounds__(256) k_vp_face(VpArgs a) {
     if (c != d) a.UIMH[d].p[to + a.UIMH[d].cs * c] = upwind_trans(ul[c], ur[c], ut, a.rel_eps);
   }
 }
+template <int D, int PPM>
+__global__ void __launch_bounds__(256) k_vp_face(VpArgs a) { vp_face_body<D, PPM, false>(a); }
+template <int D, int PPM>
+__global__ void __launch_bounds__(256) k_vp_face_ut(VpArgs a) { vp_face_body<D, PPM, true>(a); }
 
 // coef * (trans_t(cell+e_t) + trans_t(cell)) * (q(cell+e_t) - q(cell))
 __device__ __forceinline__ double tterm(double coef, const DV& tr, const DV& q, long qcomp_off, int t, int ci, int cj,
@@ -419,6 +449,8 @@ void fill_common(VpArgs& a, const mgpu_params& P, const DV& utilde, const DV& uf
   a.utilde = utilde;
   a.ufull = ufull;
   a.w0 = w0_dev;
+  a.ufull_otf = false;
+  a.nr = P.nr;
 }
 
 }  // namespace
@@ -436,6 +468,33 @@ void mkutrans_dev_exact(const mgpu_params& P, const DV& utilde, const DV& ufull,
 void velpred_dev_exact(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans, const DV& force,
                        const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u,
                        int ng_f, const DV* w0mac);
+void velpred_premac_begin_fast(const mgpu_params& P, const DV& utilde, const DV& ufull, const DV* utpre,
+                               const DV* utfull, const double* w0_dev, const int* lo, const int* hi, const int* adv_bc,
+                               const int* phys_bc, int ng_u, VpArgs* st);
+void velpred_premac_finish_fast(const mgpu_params& P, VpArgs* st, DV* umac, const DV& force, int ng_u, int ng_f);
+void velpred_premac_begin_exact(const mgpu_params& P, const DV& utilde, const DV& ufull, const DV* utpre,
+                                const DV* utfull, const double* w0_dev, const int* lo, const int* hi, const int* adv_bc,
+                                const int* phys_bc, int ng_u, VpArgs* st);
+void velpred_premac_finish_exact(const mgpu_params& P, VpArgs* st, DV* umac, const DV& force, int ng_u, int ng_f);
+// the two reconstructions coincide for ppm_type 1 / 2 (for ppm_type 0 velpred_3d rounds its predictor differently,
+// velpred.f90:812 against mkutrans.f90:543); a physical boundary hands the ghost rows of utrans to
+// multifab_physbc_edgevel, which the face kernel cannot reproduce, and w0mac (spherical) has no transverse ghost rows
+bool velpred_premac_fusable(const mgpu_params& P, const int* phys_bc) {
+  if (P.spherical || P.ppm_type == 0 || P.dm < 2) return false;
+  for (int i = 0; i < 2 * P.dm; ++i)
+    if (phys_bc[i] != MGPU_BC_INTERIOR && phys_bc[i] != MGPU_BC_PERIODIC) return false;
+  return true;
+}
+void velpred_premac_begin(const mgpu_params& P, const DV& utilde, const DV& ufull, const DV* utpre, const DV* utfull,
+                          const double* w0_dev, const int* lo, const int* hi, const int* adv_bc, const int* phys_bc,
+                          int ng_u, VpArgs* st) {
+  if (g_vp_fast) velpred_premac_begin_fast(P, utilde, ufull, utpre, utfull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, st);
+  else velpred_premac_begin_exact(P, utilde, ufull, utpre, utfull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, st);
+}
+void velpred_premac_finish(const mgpu_params& P, VpArgs* st, DV* umac, const DV& force, int ng_u, int ng_f) {
+  if (g_vp_fast) velpred_premac_finish_fast(P, st, umac, force, ng_u, ng_f);
+  else velpred_premac_finish_exact(P, st, umac, force, ng_u, ng_f);
+}
 void mkutrans_dev(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* utrans, const double* w0_dev,
                   const int* lo, const int* hi, const int* adv_bc, const int* phys_bc, int ng_u, const DV* w0mac) {
   if (g_vp_fast) mkutrans_dev_fast(P, utilde, ufull, utrans, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, w0mac);
@@ -469,20 +528,9 @@ size_t velpred_scratch(const mgpu_params& P, const int* lo, const int* hi) {
 }
 #endif
 
-void VP_FN(velpred_dev)(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans,
-                        const DV& force, const double* w0_dev, const int* lo, const int* hi, const int* adv_bc,
-                        const int* phys_bc, int ng_u, int ng_f, const DV* w0mac) {
-  VpArgs a;
-  fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "velpred", w0mac);
-  const int dm = P.dm;
-  a.trace = (P.ppm_trace_forces == 1) && P.ppm_type != 0;
-  if (a.trace && ng_f < ng_u) throw Error("velpred: ppm_trace_forces needs force with as many ghost cells as utilde");
-  if (ng_f < 1) throw Error("velpred: force needs at least 1 ghost cell");
-  a.force = force;
-  for (int d = 0; d < dm; ++d) {
-    a.utrans[d] = utrans[d];
-    a.umac[d] = umac[d];
-  }
+// temporaries of velpred on tb (arena) and the stages after the face states
+static void vp_alloc_tmp(VpArgs& a) {
+  const int dm = a.dm;
   const long nt = a.tb.npts();
   int z3[3] = {0, 0, 0};
   auto tmp = [&](int nc) { return make_view(arena_alloc((size_t)nt * nc), a.tb.lo, a.tb.hi, dm, 0, z3, nc); };
@@ -495,18 +543,72 @@ void VP_FN(velpred_dev)(const mgpu_params& P, const DV& utilde, const DV& ufull,
     for (int c = 0; c < 3; ++c)
       for (int d = 0; d < 3; ++d)
         if (c != d) a.Q[c][d] = tmp(1);
+}
+static void vp_set_force(VpArgs& a, const mgpu_params& P, const DV& force, int ng_u, int ng_f) {
+  a.trace = (P.ppm_trace_forces == 1) && P.ppm_type != 0;
+  if (a.trace && ng_f < ng_u) throw Error("velpred: ppm_trace_forces needs force with as many ghost cells as utilde");
+  if (ng_f < 1) throw Error("velpred: force needs at least 1 ghost cell");
+  a.force = force;
+}
+static void vp_trans_final(VpArgs& a) {
+  const int dm = a.dm;
   cudaStream_t s = ctx().stream;
-  for (int d = 0; d < dm; ++d) {
-    Box3 fb = a.tb;
-    fb.lo[d] = a.lo[d];
-    VPC_LAUNCH(k_vp_face, d, a.ppm_type, fb, s, a);
-  }
   if (dm == 3) MGPU_TIMED(TAG_VELPRED, (k_vp_trans<<<grid3(a.tb, 256), block3(a.tb, 256), 0, s>>>(a)));
   for (int d = 0; d < dm; ++d) {
     Box3 fb = a.vb;
     fb.hi[d] += 1;
     VP_LAUNCH(k_vp_final, d, a.ppm_type, grid3(fb, 256), block3(fb, 256), s, a);
   }
+}
+
+void VP_FN(velpred_dev)(const mgpu_params& P, const DV& utilde, const DV& ufull, DV* umac, const DV* utrans,
+                        const DV& force, const double* w0_dev, const int* lo, const int* hi, const int* adv_bc,
+                        const int* phys_bc, int ng_u, int ng_f, const DV* w0mac) {
+  VpArgs a;
+  fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "velpred", w0mac);
+  const int dm = P.dm;
+  vp_set_force(a, P, force, ng_u, ng_f);
+  for (int d = 0; d < dm; ++d) {
+    a.utrans[d] = utrans[d];
+    a.umac[d] = umac[d];
+  }
+  vp_alloc_tmp(a);
+  cudaStream_t s = ctx().stream;
+  for (int d = 0; d < dm; ++d) {
+    Box3 fb = a.tb;
+    fb.lo[d] = a.lo[d];
+    VPC_LAUNCH(k_vp_face, d, a.ppm_type, fb, s, a);
+  }
+  vp_trans_final(a);
+}
+
+// advance_premac without k_mkutrans (see vp_face_body<.., UT = true>): `begin` leaves utrans (utpre, what mk_vel_force
+// reads) and utrans + w0 (utfull; the same fab as utpre in the directions w0 does not act on) on the whole face box
+// and the face states in the arena; `finish` runs the transverse and final stages once the force exists.
+void VP_FN(velpred_premac_begin)(const mgpu_params& P, const DV& utilde, const DV& ufull, const DV* utpre,
+                                 const DV* utfull, const double* w0_dev, const int* lo, const int* hi,
+                                 const int* adv_bc, const int* phys_bc, int ng_u, VpArgs* st) {
+  VpArgs& a = *st;
+  fill_common(a, P, utilde, ufull, w0_dev, lo, hi, adv_bc, phys_bc, ng_u, "advance_premac", nullptr);
+  a.ufull_otf = ufull.p == nullptr;  // the caller did not build ufull (only traced forces read it after the faces)
+  const int dm = P.dm;
+  for (int d = 0; d < dm; ++d) {
+    a.utpre[d] = utpre[d];
+    a.utrans[d] = utfull[d];
+  }
+  vp_alloc_tmp(a);
+  cudaStream_t s = ctx().stream;
+  for (int d = 0; d < dm; ++d) {
+    Box3 fb = a.tb;
+    fb.lo[d] = a.lo[d];
+    VPC_LAUNCH(k_vp_face_ut, d, a.ppm_type, fb, s, a);
+  }
+}
+void VP_FN(velpred_premac_finish)(const mgpu_params& P, VpArgs* st, DV* umac, const DV& force, int ng_u, int ng_f) {
+  VpArgs& a = *st;
+  vp_set_force(a, P, force, ng_u, ng_f);
+  for (int d = 0; d < P.dm; ++d) a.umac[d] = umac[d];
+  vp_trans_final(a);
 }
 
 }  // namespace mgpu

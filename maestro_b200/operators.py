@@ -292,6 +292,44 @@ class Operators:
                    keep[0][1], keep[1][1], keep[2][1], float(rho_min), float(cflfac), C.byref(dt_c), C.byref(um_c))
         return dt_c.value, um_c.value
 
+    def minmax(self, p, s, comp, div_comp=0):
+        """multifab_min_c / multifab_max_c of component `comp` (1-based) over the valid zones, all ranks; div_comp > 0:
+        of s(comp) / s(div_comp) (the X = rhoX / rho of density_advance.f90:378-386). Returns (smin, smax)."""
+        lo, hi = C.c_double(0.0), C.c_double(0.0)
+        self._call("minmax", C.byref(p), 1, fab_ptr(s), int(comp), int(div_comp), C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    def verbose_report(self, p, episode, snew, spec_names=None, level=1):
+        """The `verbose >= 1` lines the reference prints at the end of an episode (density_advance.f90:374-402 formats
+        1999-2003, enthalpy_advance.f90:440-453 formats 1999/2001/2004, velocity_advance.f90:142-160 formats 999-1004),
+        as a list of strings (the I/O processor prints them)."""
+        lines = []
+        if episode == "density_advance":
+            lines.append("... Level %1d update:" % level)
+            for n in range(p.nspec):
+                name = (spec_names[n] if spec_names else "X(%d)" % (n + 1))[:16].ljust(16)
+                mn, mx = self.minmax(p, snew, p.spec_comp + n, p.rho_comp)
+                lines.append("... new min/max : %s  %s  %s" % (name, fortran_e(mn), fortran_e(mx)))
+            mn, mx = self.minmax(p, snew, p.rho_comp)
+            lines.append("... new min/max : density           %s  %s" % (fortran_e(mn), fortran_e(mx)))
+            if p.ntrac >= 1:
+                mn, mx = self.minmax(p, snew, p.trac_comp)
+                lines.append("... new min/max : tracer            %s  %s" % (fortran_e(mn), fortran_e(mx)))
+        elif episode == "enthalpy_advance":
+            mn, mx = self.minmax(p, snew, p.rhoh_comp)
+            lines.append("... Level %1d update:" % level)
+            lines.append("... new min/max : rho * H           %s  %s" % (fortran_e(mn), fortran_e(mx)))
+            lines.append(" ")
+        elif episode == "velocity_advance":
+            lines.append("... Level %1d update:" % level)
+            for d in range(p.dm):
+                mn, mx = self.minmax(p, snew, d + 1)
+                lines.append("... new min/max : %s-velocity       %s  %s" % ("xyz"[d], fortran_e(mn), fortran_e(mx)))
+            lines.append(" ")
+        else:
+            raise ValueError("verbose_report: unknown episode " + episode)
+        return lines
+
     def estdt_sphr(self, p, geom, u, s, force, divU, dSdt, w0mac, w0, p0, gamma1bar, cflfac, dt, umax=0.0,
                    rho_min=1.0e-20):
         """estdt_3d_sphr (Source/estdt.f90:620) for one level: returns (min(dt, dt_lev), max(umax, umax_lev))."""
@@ -430,3 +468,20 @@ class Operators:
                    keep[0][1], keep[1][1], fab_ptr(normal), int(nr_irreg), int(drdxfac),
                    ec.ctypes.data_as(C.POINTER(C.c_double)), cc.ctypes.data_as(C.POINTER(C.c_double)))
         return ec, cc
+
+
+def fortran_e(x, width=17, digits=10):
+    """Fortran's e<width>.<digits> edit descriptor: 0.dddddddddE+xx, right-justified"""
+    if x == 0.0:
+        m, e = 0.0, 0
+    else:
+        e = int(np.floor(np.log10(abs(x)))) + 1
+        m = x / 10.0 ** e
+        if abs(round(m, digits)) >= 1.0:
+            m, e = m / 10.0, e + 1
+    body = "%.*f" % (digits, m)
+    if abs(e) > 99:
+        tail = "%+04d" % e
+    else:
+        tail = "E%+03d" % e
+    return (body + tail).rjust(width)

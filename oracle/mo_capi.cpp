@@ -5,6 +5,9 @@
 #include <stdexcept>
 #include <string>
 
+#include <algorithm>
+#include <limits>
+
 #include "mo_kernels.h"
 
 namespace mo {
@@ -352,6 +355,32 @@ int mo_estdt(const mgpu_params* p, int nfabs, const mgpu_fab* u, const mgpu_fab*
              double rho_min, double cflfac, double* dt, double* umax) {
   MO_TRY
   estdt_level(*p, nfabs, u, s, force, divU, dSdt, w0, p0, gamma1bar, rho_min, cflfac, *dt, *umax);
+  MO_CATCH
+}
+
+// multifab_min_c / multifab_max_c over the valid zones (FBoxLib multifab_f.f90 -- not in /root/reference; the call
+// sites are density_advance.f90:374-402 with the multifab_div_div_c / multifab_mult_mult_c pair around the species,
+// enthalpy_advance.f90:440-449, velocity_advance.f90:142-160).  Unpinned: the reference holds no numbers for them.
+int mo_minmax(const mgpu_params* p, int nfabs, const mgpu_fab* s, int comp, int div_comp, double* smin, double* smax) {
+  MO_TRY
+  double mn = std::numeric_limits<double>::max(), mx = -std::numeric_limits<double>::max();
+  for (int n = 0; n < nfabs; ++n) {
+    if (comp < 1 || comp > s[n].nc || div_comp > s[n].nc) fail("mo_minmax: component out of range");
+    Arr a = Arr::view(s[n], p->dm);
+    const int* lo = s[n].lo;
+    const int* hi = s[n].hi;
+    const int k0 = p->dm == 3 ? lo[2] : 0, k1 = p->dm == 3 ? hi[2] : 0;
+    for (int k = k0; k <= k1; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+          double v = a(i, j, k, comp - 1);
+          if (div_comp >= 1) v = v / a(i, j, k, div_comp - 1);
+          mn = std::min(mn, v);
+          mx = std::max(mx, v);
+        }
+  }
+  *smin = mn;
+  *smax = mx;
   MO_CATCH
 }
 

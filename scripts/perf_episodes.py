@@ -20,6 +20,10 @@ WALLS = [[abi.PERIODIC, abi.PERIODIC], [abi.PERIODIC, abi.PERIODIC], [abi.SLIP_W
 
 if os.environ.get("PERF_VARIANT"):  # 3: upwind-first kernel for every box and ppm_type, 0: literal kernel everywhere
     lib.set_option("fused_variant", int(os.environ["PERF_VARIANT"]))
+for kv in os.environ.get("PERF_OPTS", "").split(","):  # e.g. "premac_fuse=0,exact=1"
+    if kv:
+        lib.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+EPISODES = os.environ.get("PERF_EPISODES", "density,enthalpy,premac,velocity").split(",")
 ONLY = os.environ.get("PERF_ONLY")  # e.g. "periodic,1": one configuration only (for ncu launch lists)
 
 

@@ -709,6 +709,17 @@ module maestro_b200_shim
        real(c_double), intent(inout) :: dt, umax
      end function mgpu_estdt_c
 
+     ! multifab_min_c / multifab_max_c of one component over the valid zones of a level, all ranks: the verbose >= 1
+     ! lines of density_advance.f90:374-402 (div_comp = rho_comp for the species), enthalpy_advance.f90:440-449,
+     ! velocity_advance.f90:142-160; the caller keeps its write(6, ...) statements
+     integer(c_int) function mgpu_minmax_c(p, nfabs, s, comp, div_comp, smin, smax) bind(C, name="mgpu_minmax")
+       import :: c_int, c_double, mgpu_params, mgpu_fab
+       type(mgpu_params), intent(in) :: p
+       integer(c_int), value :: nfabs, comp, div_comp
+       type(mgpu_fab), intent(in) :: s(*)
+       real(c_double), intent(out) :: smin, smax
+     end function mgpu_minmax_c
+
      ! estdt_3d_sphr (Source/estdt.f90:620) for one level; w0mac: the three face multifabs of make_w0mac
      integer(c_int) function mgpu_estdt_sphr_c(p, g, nfabs, u, s, force, divU, dSdt, w0mac, w0, p0, gamma1bar, &
           rho_min, cflfac, dt, umax) bind(C, name="mgpu_estdt_sphr")
@@ -865,7 +876,7 @@ module maestro_b200_shim
   public :: mgpu_density_advance_c, mgpu_density_advance_sphr_c, mgpu_enthalpy_advance_c, mgpu_velocity_advance_c, mgpu_advance_premac_c
   public :: mgpu_comm_unique_id, mgpu_comm_init, mgpu_comm_finalize, mgpu_set_option
   public :: mgpu_malloc, mgpu_free, mgpu_memcpy_h2d, mgpu_memcpy_d2h
-  public :: mgpu_fill_geom, mgpu_estdt_c, mgpu_estdt_sphr_c, mgpu_make_etarho_planar_c
+  public :: mgpu_fill_geom, mgpu_estdt_c, mgpu_estdt_sphr_c, mgpu_make_etarho_planar_c, mgpu_minmax_c
   public :: make_edge_scal_gpu
 
 contains

@@ -29,3 +29,21 @@ def gpu_ops():
     from maestro_b200 import lib
 
     return lib.init(0)
+
+
+@pytest.fixture(autouse=True)
+def _library_defaults(request):
+    """mgpu_set_option is process-global state: every GPU test starts and ends with the switches at their defaults"""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    import torch
+
+    if not torch.cuda.is_available():
+        yield
+        return
+    from maestro_b200 import lib
+
+    lib.set_option("defaults", 0)
+    yield
+    lib.set_option("defaults", 0)

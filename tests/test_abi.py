@@ -113,3 +113,15 @@ def test_no_cpu_fallback():
         lib.ops().make_edge_scal(p, s, face_fabs([0, 0, 0], [7, 7, 0], 0, p.nscal, 2),
                                  face_fabs([0, 0, 0], [7, 7, 0], 1, 1, 2), f,
                                  make_adv_bc(p, [[-1, -1], [-1, -1]]), False, 1, 3, 1, False)
+
+
+def test_fortran_e_format():
+    """e17.10 as gfortran prints it (the reference's formats 2000-2003)"""
+    from maestro_b200.operators import fortran_e
+
+    assert fortran_e(1.0) == " 0.1000000000E+01"
+    assert fortran_e(-0.105604113268602) == "-0.1056041133E+00"
+    assert fortran_e(0.0) == " 0.0000000000E+00"
+    assert fortran_e(9.99999999999e9) == " 0.1000000000E+11"
+    assert fortran_e(1.0e-10) == " 0.1000000000E-09"
+    assert fortran_e(-2.5e120) == "-0.2500000000+121"

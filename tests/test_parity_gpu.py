@@ -582,6 +582,33 @@ def test_advance_premac(gpu_ops, oracle, dm, n, ppm_type, bcset, exact):
         check(g.a, c.a, bitwise=bool(exact))
 
 
+@pytest.mark.parametrize("dm,n", [(2, (22, 15)), (3, (14, 9, 11)), (3, (40, 33, 19))])
+@pytest.mark.parametrize("ppm_type", [1, 2])
+@pytest.mark.parametrize("exact", [1, 0], ids=["exact", "fast"])
+def test_advance_premac_fused_and_staged_agree(gpu_ops, oracle, dm, n, ppm_type, exact):
+    """On a periodic box advance_premac forms utrans inside velpred's face kernel (option premac_fuse, the default):
+    the result equals the staged sequence (k_mkutrans, ghost fill, addw0, ghost fill, velpred) and the oracle bit for
+    bit in the exact build, and within the FAST tolerance otherwise."""
+    from maestro_b200 import lib
+    from synth import make_episode_extras, make_vel_state
+
+    lib.set_option("exact", exact)
+    st = make_vel_state(dm, list(n), phys_bc=None, ppm_type=ppm_type, oracle=oracle)
+    p = st["p"]
+    ex = make_episode_extras(st)
+    s = _scalar_like(st, oracle)
+    out = []
+    for o, fuse in ((gpu_ops, 1), (gpu_ops, 0), (oracle, 0)):
+        lib.set_option("premac_fuse", fuse)
+        umac = face_fabs(st["lo"], st["hi"], 1, 1, dm, fill=-777.0)
+        o.advance_premac(p, st["utilde"], s, umac, ex["gpi"], st["w0"], ex["w0_force"], _base_for_vel(st)["rho0_old"],
+                         ex["grav_old"], st["adv_bc"], st["phys_bc"], st["pmask"])
+        out.append(umac)
+    for f, g, c in zip(*out):
+        check(f.a, g.a, bitwise=bool(exact))
+        check(f.a, c.a, bitwise=bool(exact))
+
+
 @pytest.mark.parametrize("dm,n", [(2, (22, 15)), (3, (14, 9, 11))])
 @pytest.mark.parametrize("ppm_type,bds", [(0, 0), (1, 0), (2, 0), (1, 1)])
 @pytest.mark.parametrize("bcset", ["periodic", "walls", "inout"])
@@ -887,6 +914,51 @@ def test_make_etarho_planar(gpu_ops, oracle, dm, n):
     ec_w, cc_w = oracle.make_etarho_planar(p, eta)
     ec_g, cc_g = gpu_ops.make_etarho_planar(p, eta)
     assert relerr(ec_g, ec_w) <= TOL and relerr(cc_g, cc_w) <= TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dm,n", [(2, (70, 45)), (3, (33, 20, 27)), (3, (1, 1, 1))])
+@pytest.mark.parametrize("space", ["host", "device"])
+def test_minmax_verbose_report(gpu_ops, oracle, dm, n, space):
+    """multifab_min_c / multifab_max_c behind the `verbose >= 1` lines (density_advance.f90:374-402, enthalpy_advance
+    .f90:440-449, velocity_advance.f90:142-160): min and max are exact in any order, so the device reduction equals
+    numpy's over the valid zones bit for bit -- ghost cells (set to huge values here) must not enter, the species are
+    reported as rhoX / rho and the state is left untouched."""
+    from maestro_b200.operators import fortran_e
+
+    st = make_state(dm, list(n))
+    p = st["p"]
+    s = st["s"].clone()
+    v = s.valid().clone()
+    s.a[:] = 1.0e300 * np.where(np.arange(s.a.numel()).reshape(s.a.shape) % 2 == 0, 1.0, -1.0)
+    s.valid()[:] = v
+    before = s.a.clone()
+    f = s.to("cuda:0") if space == "device" else s
+    if space == "device":
+        p.mem_space = abi.DEVICE
+    try:
+        for comp in range(1, p.nscal + 1):
+            got = gpu_ops.minmax(p, f, comp)
+            want = (float(v[comp - 1].min()), float(v[comp - 1].max()))
+            assert got == want, (comp, got, want)
+            assert oracle.minmax(p, s, comp) == want
+        for n_ in range(p.nspec):
+            x = v[p.spec_comp - 1 + n_] / v[p.rho_comp - 1]
+            got = gpu_ops.minmax(p, f, p.spec_comp + n_, p.rho_comp)
+            assert got == (float(x.min()), float(x.max())), (n_, got)
+            assert oracle.minmax(p, s, p.spec_comp + n_, p.rho_comp) == got
+        lines = gpu_ops.verbose_report(p, "density_advance", f, spec_names=["helium-4", "carbon-12", "oxygen-16"])
+        lines += gpu_ops.verbose_report(p, "enthalpy_advance", f)
+    finally:
+        p.mem_space = abi.HOST
+    assert lines[0] == "... Level 1 update:"
+    x = v[p.spec_comp - 1] / v[p.rho_comp - 1]
+    assert lines[1] == "... new min/max : helium-4          %s  %s" % (fortran_e(float(x.min())), fortran_e(float(x.max())))
+    assert lines[1 + p.nspec].startswith("... new min/max : density           ")
+    assert lines[-2].startswith("... new min/max : rho * H           ") and lines[-1] == " "
+    assert (f.to("cpu").a if space == "device" else s.a).equal(before)  # nothing written
+    with pytest.raises(Exception):
+        gpu_ops.minmax(p, f, p.nscal + 1)
 
 
 @pytest.mark.gpu
