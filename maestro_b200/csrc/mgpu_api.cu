@@ -1059,7 +1059,7 @@ static void velocity_advance_dev(const mgpu_params& P, const DV& uold, DV& unew,
   a.uold = uold; a.unew = unew; a.force = force; a.sponge = sponge;
   for (int d = 0; d < dm; ++d) { a.umac[d] = umac[d]; a.uedge[d] = uedge[d]; }
   a.w0 = w0;
-  update_velocity_dev(a);  // :132
+  update_velocity_dev(a, g_opt_exact == 0);  // :132
   fill_boundary_dev(P, unew, lo, hi, ng_u, nullptr, 1, 1, dm, adv_bc, pmask, false);  // update_vel.f90:121
 }
 
@@ -1590,7 +1590,7 @@ static void velocity_advance_mf_dev(const mgpu_params& P, const BoxSet& B, std::
     a.uold = uold[i]; a.unew = unew[i]; a.force = force[i]; a.sponge = sponge[i];
     for (int d = 0; d < dm; ++d) { a.umac[d] = umac[d][i]; a.uedge[d] = uedge[d][i]; }
     a.w0 = w0;
-    update_velocity_dev(a);
+    update_velocity_dev(a, g_opt_exact == 0);
   }
   fill_mf(P, B, unew, ng_u, nullptr, 1, 1, dm, pmask);  // update_vel.f90:121
 }

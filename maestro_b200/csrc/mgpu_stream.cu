@@ -237,7 +237,10 @@ void copy_dev(double* dst, const double* src, long n) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_update_vel(VelArgs a) {
+// FAST: the divisions by dx as multiplications by reciprocals formed on the host (four fp64 divisions per component
+// otherwise: the kernel then runs at the fp64 pipe's pace instead of HBM's); <= 1e-12 relative like the other FAST builds
+template <bool FAST>
+__global__ void __launch_bounds__(256) k_update_vel(VelArgs a) {
   int ix[3];
   if (!decode3(a.vb, ix)) return;
   const int i = ix[0], j = ix[1], k = ix[2];
@@ -248,21 +251,28 @@ __global__ void k_update_vel(VelArgs a) {
   bar[2] = (dm == 3) ? 0.5 * (a.umac[2](i, j, k) + a.umac[2](i, j, k + 1)) : 0.0;
   const int ir = ix[r];
   const double wbar = 0.5 * (a.w0[ir] + a.w0[ir + 1]);
+  const double sp = a.do_sponge ? a.sponge(i, j, k) : 1.0;
   for (int n = 0; n < dm; ++n) {
-    double ugrad = bar[0] * (a.uedge[0](i + 1, j, k, n) - a.uedge[0](i, j, k, n)) / a.dx[0] +
-                   bar[1] * (a.uedge[1](i, j + 1, k, n) - a.uedge[1](i, j, k, n)) / a.dx[1];
-    if (dm == 3) ugrad = ugrad + bar[2] * (a.uedge[2](i, j, k + 1, n) - a.uedge[2](i, j, k, n)) / a.dx[2];
+    const double e0l = a.uedge[0](i, j, k, n), e0h = a.uedge[0](i + 1, j, k, n);
+    const double e1l = a.uedge[1](i, j, k, n), e1h = a.uedge[1](i, j + 1, k, n);
+    const double e2l = (dm == 3) ? a.uedge[2](i, j, k, n) : 0.0, e2h = (dm == 3) ? a.uedge[2](i, j, k + 1, n) : 0.0;
+    double ugrad;
+    if (FAST) ugrad = bar[0] * (e0h - e0l) * a.rdx[0] + bar[1] * (e1h - e1l) * a.rdx[1];
+    else ugrad = bar[0] * (e0h - e0l) / a.dx[0] + bar[1] * (e1h - e1l) / a.dx[1];
+    if (dm == 3) ugrad = ugrad + (FAST ? bar[2] * (e2h - e2l) * a.rdx[2] : bar[2] * (e2h - e2l) / a.dx[2]);
     double un = a.uold(i, j, k, n) - a.dt * ugrad + a.dt * a.force(i, j, k, n);
-    const double hi_e = (r == 1) ? a.uedge[1](i, j + 1, k, n) : a.uedge[2](i, j, k + 1, n);
-    const double lo_e = a.uedge[r](i, j, k, n);
-    un = un - a.dt * wbar * (hi_e - lo_e) / a.dx[r];
-    if (a.do_sponge) un = un * a.sponge(i, j, k);
+    const double hi_e = (r == 1) ? e1h : e2h;
+    const double lo_e = (r == 1) ? e1l : e2l;
+    if (FAST) un = un - a.dt * wbar * (hi_e - lo_e) * a.rdx[r];
+    else un = un - a.dt * wbar * (hi_e - lo_e) / a.dx[r];
+    if (a.do_sponge) un = un * sp;
     a.unew(i, j, k, n) = un;
   }
 }
-void update_velocity_dev(VelArgs& a) {
-  k_update_vel<<<grid3(a.vb, 256), block3(a.vb, 256), 0, ctx().stream>>>(a);
-  MGPU_LAUNCH_CHECK();
+void update_velocity_dev(VelArgs& a, bool fast) {
+  for (int d = 0; d < 3; ++d) a.rdx[d] = 1.0 / a.dx[d];
+  if (fast) MGPU_TIMED(TAG_UPDATE, (k_update_vel<true><<<grid3(a.vb, 256), block3(a.vb, 256), 0, ctx().stream>>>(a)));
+  else MGPU_TIMED(TAG_UPDATE, (k_update_vel<false><<<grid3(a.vb, 256), block3(a.vb, 256), 0, ctx().stream>>>(a)));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -41,11 +41,13 @@ struct VelArgs {
   int dm;
   bool do_sponge;
   double dt, dx[3];
+  double rdx[3];  // 1/dx, set by update_velocity_dev (FAST kernel)
   Box3 vb;
   DV uold, unew, force, sponge, umac[3], uedge[3];
   const double* w0;
 };
-void update_velocity_dev(VelArgs& a);
+// fast: divisions by dx as multiplications by reciprocals (the velocity_advance episodes outside the exact build)
+void update_velocity_dev(VelArgs& a, bool fast = false);
 
 // force builders
 struct RhohForceArgs {

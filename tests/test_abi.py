@@ -125,3 +125,76 @@ def test_fortran_e_format():
     assert fortran_e(9.99999999999e9) == " 0.1000000000E+11"
     assert fortran_e(1.0e-10) == " 0.1000000000E-09"
     assert fortran_e(-2.5e120) == "-0.2500000000+121"
+
+
+def _c_prototypes():
+    """name -> (return type, [("val" | "ptr", base type, number of stars)]) from include/maestro_b200.h"""
+    txt = open(os.path.join(ROOT, "include", "maestro_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//[^\n]*", "", txt)
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z_0-9 \*]*?)\b(mgpu_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+        params = []
+        if args and args != "void":
+            for a in args.split(","):
+                stars = a.count("*")
+                base = re.sub(r"\bconst\b|\*|\bunsigned\b|\bstruct\b", " ", a).split()
+                params.append(("ptr" if stars else "val", base[0], stars))
+        out[name] = (ret, params)
+    return out
+
+
+def _fortran_interfaces():
+    """C name -> (result kind, [(dummy, (type, has `value`, is an array))]) from the interface blocks of the shim"""
+    txt = open(os.path.join(ROOT, "shim", "maestro_b200_shim.f90")).read()
+    txt = re.sub(r"&\s*\n\s*&?", " ", txt)  # continuation lines
+    out = {}
+    pat = (r"^\s*(?:(integer\(c_int\)|integer\(c_long\)|type\(c_ptr\)|real\(c_double\))\s+function|subroutine)\s+(\w+)"
+           r"\s*\(([^)]*)\)\s*bind\(C,\s*name=\"(mgpu_\w+)\"\)(.*?)end (?:function|subroutine)")
+    for m in re.finditer(pat, txt, flags=re.S | re.M | re.I):
+        ret, _, dummies, cname, body = m.groups()
+        dummies = [d.strip() for d in dummies.split(",") if d.strip()]
+        decl = {}
+        for line in body.splitlines():
+            line = line.split("!")[0].strip()
+            if "::" not in line or line.lower().startswith("import"):
+                continue
+            left, names = line.split("::")
+            attrs = [x.strip().lower() for x in re.split(r",(?![^()]*\))", left)]
+            for nm in re.findall(r"([A-Za-z_]\w*)(\([^)]*\))?", names):
+                decl[nm[0].lower()] = (attrs[0], "value" in attrs, bool(nm[1]))
+        out[cname] = (ret, [(d, decl.get(d.lower())) for d in dummies])
+    return out
+
+
+def test_fortran_shim_argument_lists_match_header():
+    """every interface block of the shim against the C prototype it binds: the same number of arguments in the same
+    order, by value exactly where C passes by value (with the matching kind), by reference where C takes a pointer
+    (with the matching element type; `type(c_ptr), value` stands for any pointer and an array of `type(c_ptr)` for a
+    pointer to pointers), and the matching result kind.  No Fortran compiler is available to do this check."""
+    cp, fi = _c_prototypes(), _fortran_interfaces()
+    assert len(fi) >= 70
+    val_kind = {"int": "integer(c_int)", "long": "integer(c_long)", "double": "real(c_double)"}
+    ref_kind = {"int": "integer(c_int)", "double": "real(c_double)", "long": "integer(c_long)", "char": "character(kind=c_char)",
+                "mgpu_params": "type(mgpu_params)", "mgpu_fab": "type(mgpu_fab)", "mgpu_geom": "type(mgpu_geom)",
+                "mgpu_eos": "type(mgpu_eos)"}
+    ret_kind = {"int": "integer(c_int)", "long": "integer(c_long)", "const char*": "type(c_ptr)", "double": "real(c_double)"}
+    for name, (fret, fargs) in sorted(fi.items()):
+        cret, cargs = cp[name]
+        assert fret is not None and fret.lower() == ret_kind[cret], (name, fret, cret)
+        assert len(fargs) == len(cargs), (name, len(fargs), len(cargs))
+        for (dummy, d), (how, base, stars) in zip(fargs, cargs):
+            assert d is not None, (name, dummy, "dummy argument without a declaration")
+            ftype, by_value, is_array = d
+            where = (name, dummy, d, (how, base, stars))
+            if how == "val":
+                assert by_value and ftype == val_kind[base], where
+            elif by_value:
+                assert ftype == "type(c_ptr)", where  # an opaque address handed through
+            elif ftype == "type(c_ptr)":
+                assert stars == 2 or base == "void", where  # array of addresses <-> T* const* (or void** out)
+            elif base == "void":
+                assert stars == 1, where  # untyped buffer: any array by reference
+            else:
+                assert stars == 1 and ftype == ref_kind.get(base), where
