@@ -34,6 +34,9 @@ struct FusedArgs {
   // third design, boxes with physical boundaries: 0 every tile; 1 only the tiles no boundary rule can reach (run by the
   // plain kernel), 2 only the others (run by the boundary kernel) -- see fused_edge3_launch
   int tile_mode;
+  // third design: > 0: the first and the last z chunk are kedge planes thick and the chunks between them kchunk (a box
+  // with a physical boundary in z: the boundary kernel then runs thin chunks, the plain kernel everything else)
+  int kedge;
   DV s, force;  // single-component views
   DV umac[3];
   DV sedge[3];  // single-component views of the output
@@ -57,6 +60,8 @@ void fused_edge2_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz
 bool fused_edge3_supported(const FusedArgs& a, bool bc);
 void fused_edge3_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc);
 void fused_edge3_set_split(int on);  // boundary boxes: interior tiles through the plain kernel (default on)
+void fused_edge3_set_pair_streams(int on);  // tile split: the boundary kernel on a second stream (default on)
+void fused_edge3_set_thin_edge(int on);  // boundary in z: 8-plane end chunks for the boundary kernel (default on)
 // 2-D (mgpu_fused2.cu, k_fused_edge2d): FAST arithmetic only, non-conservative, ppm_trace_forces = 0, no REFLECT_ODD
 bool fused_edge2d_supported(const mgpu_params& P, bool is_cons, const int* adv_bc, int bccomp, bool exact);
 void fused_edge2d_dev(const mgpu_params& P, const DV& s_full, DV* sedge_full, const DV* umac, const DV& force_full,

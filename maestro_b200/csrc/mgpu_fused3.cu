@@ -114,8 +114,20 @@ __global__ void __launch_bounds__(BX* BY, 2)
   const int ibase = a.lo[0] - 1 + blockIdx.x * (BX - 2);
   const int jbase = a.lo[1] - 1 + blockIdx.y * (BY - 2);
   const int i = ibase + tx, j = jbase + ty;
-  const int kz0 = a.lo[2] + blockIdx.z * a.kchunk;
-  const int kz1 = min(kz0 + a.kchunk - 1, a.hi[2]);
+  int kz0 = a.lo[2] + blockIdx.z * a.kchunk;
+  int kz1 = min(kz0 + a.kchunk - 1, a.hi[2]);
+  if (a.kedge > 0) {  // thin first and last chunk (launch_fused3_xf: boxes with a physical boundary in z)
+    if (blockIdx.z == 0) {
+      kz0 = a.lo[2];
+      kz1 = a.lo[2] + a.kedge - 1;
+    } else if (blockIdx.z == gridDim.z - 1) {
+      kz0 = a.hi[2] - a.kedge + 1;
+      kz1 = a.hi[2];
+    } else {
+      kz0 = a.lo[2] + a.kedge + ((int)blockIdx.z - 1) * a.kchunk;
+      kz1 = min(kz0 + a.kchunk - 1, a.hi[2] - a.kedge);
+    }
+  }
   const bool top = (kz1 == a.hi[2]);
   const int ic = min(i, a.hi[0] + 1), jc = min(j, a.hi[1] + 1);
   if (a.tile_mode != 0) {
@@ -683,6 +695,7 @@ int fused3_auto_kchunk(int ncols, int nz, int slots) {
   return bk;
 }
 
+bool g_thin_edge = true;    // boxes with a boundary in z: 8-plane end chunks (mgpu_set_option "thin_edge")
 bool g_split_tiles = true;  // boundary boxes: interior tiles through the plain kernel (mgpu_set_option "split_tiles")
 
 typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -713,8 +726,9 @@ CUtensorMap make_tmap(const double* base, const DV& v, int bx, int by) {
   return tm;
 }
 
+// stream: nullptr = the library's stream; timed: false when the caller brackets several launches as one profile entry
 template <int PPM, int BX, int BY, int XF, bool WADD, bool BC>
-void launch_fused3(const FusedArgs& a0, int nx, int ny, int nz) {
+void launch_fused3(const FusedArgs& a0, int nx, int ny, int nz, cudaStream_t stream = nullptr, bool timed = true) {
   constexpr int H = (PPM == 2) ? 3 : 2;
   using SM = Smem3<H, BX, BY, XF == 1>;
   Context& c = ctx();
@@ -740,15 +754,37 @@ void launch_fused3(const FusedArgs& a0, int nx, int ny, int nz) {
   }
   a.dt2 = 0.5 * a.dt;
   const int gx = (nx + BX - 3) / (BX - 2), gy = (ny + BY - 3) / (BY - 2);
-  if (a.kchunk <= 0) a.kchunk = fused3_auto_kchunk(gx * gy, nz, slots);
+  if (a.kchunk <= 0) a.kchunk = fused3_auto_kchunk(gx * gy, nz - 2 * a.kedge, slots);
   if (a.kchunk > KMAX) a.kchunk = KMAX;
   const int smem = bytes;
   const CUtensorMap tm_s = make_tmap(a.s.p, a.s, SM::TXW, SM::TYW);
   const CUtensorMap tm_d = (XF == 1) ? make_tmap(a.sdiv, a.s, SM::TXW, SM::TYW) : tm_s;
   dim3 block(BX, BY, 1);
-  dim3 grid(gx, gy, (nz + a.kchunk - 1) / a.kchunk);
-  MGPU_TIMED(TAG_FUSED_EDGE, (kern<<<grid, block, smem, c.stream>>>(a, tm_s, tm_d)));
+  dim3 grid(gx, gy, a.kedge > 0 ? 2 + (nz - 2 * a.kedge + a.kchunk - 1) / a.kchunk : (nz + a.kchunk - 1) / a.kchunk);
+  cudaStream_t st = stream ? stream : c.stream;
+  if (timed) {
+    MGPU_TIMED(TAG_FUSED_EDGE, (kern<<<grid, block, smem, st>>>(a, tm_s, tm_d)));
+  } else {
+    kern<<<grid, block, smem, st>>>(a, tm_s, tm_d);
+    MGPU_LAUNCH_CHECK();
+  }
 }
+
+// the second stream of the tile split (boundary kernel next to the plain kernel) and its fork / join events
+struct PairStream {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+PairStream& pair_stream() {
+  static PairStream ps;
+  if (!ps.aux) {
+    MGPU_CUDA(cudaStreamCreateWithFlags(&ps.aux, cudaStreamNonBlocking));
+    MGPU_CUDA(cudaEventCreateWithFlags(&ps.fork, cudaEventDisableTiming));
+    MGPU_CUDA(cudaEventCreateWithFlags(&ps.join, cudaEventDisableTiming));
+  }
+  return ps;
+}
+bool g_pair_streams = true;  // mgpu_set_option "pair_streams"
 
 template <int PPM>
 void launch_fused3_xf(const FusedArgs& a0, int nx, int ny, int nz, bool bc) {
@@ -760,10 +796,43 @@ void launch_fused3_xf(const FusedArgs& a0, int nx, int ny, int nz, bool bc) {
     // boundary shell thin when the box has a boundary in z.
     FusedArgs a = a0;
     const bool zbc = a.bclo[2] != MGPU_BC_INTERIOR || a.bchi[2] != MGPU_BC_INTERIOR;
-    if (a.kchunk <= 0 && zbc && nz >= 128) a.kchunk = 32;
     const bool split = g_split_tiles && nx >= 3 * 14 && ny >= 3 * 14 && nz >= 24;
+    if (split && zbc && a.kchunk <= 0 && nz >= 64 && g_thin_edge) {
+      // a boundary in z: only the chunks at the two ends are boundary tiles, and the tile test (kernel prologue) lets a
+      // chunk be interior from the fifth plane off the low wall and up to the seventh below the high one -- so the end
+      // chunks are 8 planes thick and the plain kernel takes everything between them in chunks balanced over its slots
+      a.kedge = 8;
+      int slots = 296;
+      {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+          slots = 2 * sms;
+      }
+      const int gx = (nx + 16 - 3) / (16 - 2), gy = (ny + 16 - 3) / (16 - 2);
+      a.kchunk = fused3_auto_kchunk(gx * gy, nz - 2 * a.kedge, slots);
+      if (a.kchunk > 128 - 16) a.kchunk = 128 - 16;
+    }
+    if (a.kchunk <= 0 && zbc && nz >= 128) a.kchunk = 32;
     if (split) {
       if (a.kchunk <= 0) a.kchunk = nz >= 128 ? 64 : nz;  // both launches must cut the same chunks
+      if (g_pair_streams) {
+        // the two launches write disjoint tiles and read the same inputs: the boundary kernel goes to a second stream
+        // so that its CTAs fill the slots the plain kernel's partial last wave leaves idle (and the other way round).
+        // One profile entry for the pair = one component, the unit the roofline line counts.
+        Context& c = ctx();
+        PairStream& ps = pair_stream();
+        prof_begin(TAG_FUSED_EDGE);
+        MGPU_CUDA(cudaEventRecord(ps.fork, c.stream));
+        MGPU_CUDA(cudaStreamWaitEvent(ps.aux, ps.fork, 0));
+        a.tile_mode = 2;
+        launch_fused3<PPM, 16, 16, 0, false, true>(a, nx, ny, nz, ps.aux, false);
+        a.tile_mode = 1;
+        launch_fused3<PPM, 16, 16, 0, false, false>(a, nx, ny, nz, nullptr, false);
+        MGPU_CUDA(cudaEventRecord(ps.join, ps.aux));
+        MGPU_CUDA(cudaStreamWaitEvent(c.stream, ps.join, 0));
+        prof_end(TAG_FUSED_EDGE);
+        return;
+      }
       a.tile_mode = 1;
       launch_fused3<PPM, 16, 16, 0, false, false>(a, nx, ny, nz);
       a.tile_mode = 2;
@@ -796,6 +865,8 @@ bool fused_edge3_supported(const FusedArgs& a, bool bc) {
 }
 
 void fused_edge3_set_split(int on) { g_split_tiles = on != 0; }
+void fused_edge3_set_thin_edge(int on) { g_thin_edge = on != 0; }
+void fused_edge3_set_pair_streams(int on) { g_pair_streams = on != 0; }
 
 void fused_edge3_launch(const FusedArgs& a, int ppm_type, int nx, int ny, int nz, bool bc) {
   switch (ppm_type) {

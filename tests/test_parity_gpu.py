@@ -90,6 +90,32 @@ def test_fused_edge_ragged_boxes(gpu_ops, oracle, ppm_type, bcset, shape, kchunk
             check(gv[d].a[c_], cv[d].a[c_], bitwise=exact == 1)
 
 
+@pytest.mark.parametrize("ppm_type", [1, 2])
+@pytest.mark.parametrize("bcset", ["walls", "inout"])
+@pytest.mark.parametrize("shape", [(46, 44, 72), (44, 58, 131)])
+@pytest.mark.parametrize("thin,pair", [(1, 1), (1, 0), (0, 1)])
+def test_fused_edge_thin_end_chunks(gpu_ops, oracle, ppm_type, bcset, shape, thin, pair):
+    """Boxes with a physical boundary in z that are large enough for the tile split (option thin_edge, the default): the
+    boundary kernel runs 8-plane chunks at the two ends of every column and the plain kernel the planes between them in
+    chunks of its own size -- the seams between the three kinds of chunk must be written exactly once, and the result
+    must not depend on the chunking."""
+    from maestro_b200 import lib
+
+    lib.set_option("fused", 1)
+    lib.set_option("exact", 0)
+    lib.set_option("thin_edge", thin)
+    lib.set_option("pair_streams", pair)
+    phys = {"walls": WALLS_3D, "inout": INOUT_3D}[bcset]
+    st = make_state(3, shape, phys_bc=phys, ppm_type=ppm_type)
+    st["p"].rel_eps = 1e-8 * max(np.abs(u.a).max() for u in st["umac"])
+    g, c = edge_pair(gpu_ops, oracle, st, (1, 3))
+    gv, cv = edge_pair(gpu_ops, oracle, st, (1, 3), is_vel=True, bccomp0=1)
+    for d in range(3):
+        for c_ in range(3):
+            check(g[d].a[c_], c[d].a[c_], bitwise=False)
+            check(gv[d].a[c_], cv[d].a[c_], bitwise=False)
+
+
 @pytest.mark.parametrize("ppm_type", [0, 1, 2])
 @pytest.mark.parametrize("variant", [0, 1, 2], ids=["literal", "upwind-first", "upwind-first-16x16"])
 @pytest.mark.parametrize("shape,kchunk", [((37, 9, 11), 4), ((30, 6, 40), 16), ((70, 20, 9), 64), ((45, 33, 70), -1)])
