@@ -716,8 +716,44 @@ __global__ void __launch_bounds__(BX* BY) k_fused_edge2d(FusedArgs a) {
   const double* const S = sS + (ty + H) * SP + tx + H;
 #define PL2(A, dy, dx) pl[(A)*PL + (dy)*P + (dx)]
   __syncthreads();
-  // C1
-  {
+  // C0 (ppm_type 2): the limited edge values of the tile, once per face.  The limiter of a cell looks at the four faces
+  // i-1 .. i+2 of each direction (ppm.f90:1905-1974), so left to itself every thread evaluates eight edges and every
+  // edge is evaluated four times; here the (BX+3) x BY x-faces and BX x (BY+3) y-faces of the tile are shared out over
+  // the threads (2.3 per thread on a 32x16 tile) and land in the planes the later phases have not written yet.
+  // Tiles a boundary rule can reach (same test as the 3-D kernel's tile split) keep the per-cell wall stencils.
+  bool share = (PPM == 2);
+  if constexpr (PPM == 2 && BC) {
+    const int c0[2] = {ibase, jbase}, c1[2] = {ibase + BX - 1, jbase + BY - 1};
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      if (a.bclo[d] != MGPU_BC_INTERIOR && c0[d] <= a.lo[d] + 2) share = false;
+      if (a.bchi[d] != MGPU_BC_INTERIOR && c1[d] >= a.hi[d] - 2) share = false;
+    }
+  }
+  if (PPM == 2 && share) {
+    constexpr int NEX = (BX + 3) * BY, NEY = (BY + 3) * BX;
+    static_assert(NEX + NEY <= 4 * PL, "edge tables must fit the planes SHX .. GY");
+    double* const EX = planes + SHX * PL;
+    double* const EY = EX + NEX;
+    for (int e = tid; e < NEX; e += BX * BY) {
+      const int row = e / (BX + 3), fx = e - row * (BX + 3);
+      EX[e] = sedge2_of(sS + (row + H) * SP + fx - 1 + H, 1);
+    }
+    for (int e = tid; e < NEY; e += BX * BY) {
+      const int fy = e / BX, col = e - fy * BX;
+      EY[e] = sedge2_of(sS + (fy - 1 + H) * SP + col + H, SP);
+    }
+    __syncthreads();
+    const double* const ex = EX + ty * (BX + 3) + tx + 1;
+    const double* const ey = EY + (ty + 1) * BX + tx;
+    double a0, a1;
+    cs_limit_fast(S, 1, [&](int o) { return ex[o]; }, a0, a1);
+    PL2(AX0, 0, 0) = a0;
+    PL2(AX1, 0, 0) = a1;
+    cs_limit_fast(S, SP, [&](int o) { return ey[o * BX]; }, a0, a1);
+    PL2(AY0, 0, 0) = a0;
+    PL2(AY1, 0, 0) = a1;
+  } else {  // C1
     double a0, a1;
     if constexpr (BC) cell_par_bc<PPM>(S, 1, i, a.slope_order, lbx, a0, a1);
     else cell_par<PPM>(S, 1, a.slope_order, nb, a0, a1);
