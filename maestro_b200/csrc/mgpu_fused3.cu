@@ -53,7 +53,11 @@ struct Smem3 {
   static constexpr int RS = NRING * PL;
   static constexpr int NTILE = NS * SLOT * (DIV ? 2 : 1);
   static constexpr int NPLANES = NPL + 4 * NRING;
-  static constexpr int BYTES = (NTILE + NPLANES * PL) * 8 + 64 + 2 * KCAP * 8;  // + mbarriers + per-plane constants
+  // ppm_type 2 (H == 3): two tables of the limited edge values of a plane's tile, (BX+3) x BY x-faces and BX x (BY+3)
+  // y-faces (planes t and t+1), see the E phase of the kernel
+  static constexpr int NEX = (BX + 3) * BY, NEY = BX * (BY + 3), NE = NEX + NEY;
+  static constexpr int NEDGE = (H == 3) ? 2 * NE : 0;
+  static constexpr int BYTES = (NTILE + NPLANES * PL) * 8 + 64 + 2 * KCAP * 8 + NEDGE * 8;  // + mbarriers + per-plane constants + edge tables
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +111,8 @@ __global__ void __launch_bounds__(BX* BY, 2)
   // sWadd[m] = wadd of z-face t0 + m, sSub[m] = ssub of plane t0 + m
   double* const sWadd = reinterpret_cast<double*>(bars + 8);
   double* const sSub = sWadd + SM::KCAP;
+  constexpr bool ESH = (PPM == 2) && !BC;  // x / y edge values shared through the tables below
+  double* const etab = sSub + SM::KCAP;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * BX + tx;
   double* const pl = planes + ty * P + tx;       // this thread's cell in plane 0
   double* const rg = pl + SM::NPL * SM::PL;      // this thread's cell in ring slot 0, plane 0
@@ -219,6 +225,22 @@ __global__ void __launch_bounds__(BX* BY, 2)
     }
   };
 
+  // E phase (ppm_type 2, no boundary rules): the limiter of a cell reads the limited edge values on the four faces
+  // i-1 .. i+2 of each direction (ppm.f90:1905-1974); left to itself every thread evaluates eight of them per plane
+  // and every edge is evaluated four times.  Here the faces of a plane's tile are shared out over the CTA (608 edges
+  // for 256 threads) a step before the plane is reconstructed; T = the (transformed) tile of that plane.
+  auto edge_tables = [&](const double* T, double* E) {
+    for (int e = tid; e < SM::NE; e += NT) {
+      if (e < SM::NEX) {
+        const int row = e / (BX + 3), fx = e - row * (BX + 3);
+        E[e] = sedge2_of(T + (row + H) * SP + fx - 1 + H + xsh, 1);
+      } else {
+        const int e2 = e - SM::NEX, fy = e2 / BX, col = e2 - fy * BX;
+        E[e] = sedge2_of(T + (fy - 1 + H) * SP + col + H + xsh, SP);
+      }
+    }
+  };
+
   const int t0 = kz0 - 1;
   const int t1 = kz1 + 2 + (top ? 1 : 0);
   if (tid == 0) {
@@ -320,6 +342,10 @@ __global__ void __launch_bounds__(BX* BY, 2)
     mbar_wait(bars_a + n * 8, 0);
     transform(n, XF == 2 ? sSub[n] : 0.0);
   }
+  if constexpr (ESH) {  // the tables of plane t0 (slot 0) for the first step; barrier A of that step publishes them
+    if constexpr (XF != 0) __syncthreads();
+    edge_tables(tiles, etab);
+  }
   int c0 = 0;                // slot of plane t
   int slot_w = H + 1;        // slot (and parity) of the next tile to wait for: plane t+H+1
   unsigned par_w = 0;
@@ -347,14 +373,26 @@ __global__ void __launch_bounds__(BX* BY, 2)
     // C1(t): limited parabolas
     {
       double a0, a1;
-      if constexpr (BC) cell_par_bc<PPM>(S, 1, i, a.slope_order, lbx, a0, a1);
-      else cell_par<PPM>(S, 1, a.slope_order, nb, a0, a1);
-      PLN3(AX0, 0, 0) = a0;
-      if (PPM != 0) PLN3(AX1, 0, 0) = a1;
-      if constexpr (BC) cell_par_bc<PPM>(S, SP, j, a.slope_order, lby, a0, a1);
-      else cell_par<PPM>(S, SP, a.slope_order, nb, a0, a1);
-      PLN3(AY0, 0, 0) = a0;
-      if (PPM != 0) PLN3(AY1, 0, 0) = a1;
+      if constexpr (ESH) {  // edge values of plane t from the table written a step ago; the table of plane t+1 follows
+        const double* const ex = etab + (R & 1) * SM::NE + ty * (BX + 3) + tx + 1;
+        const double* const ey = etab + (R & 1) * SM::NE + SM::NEX + (ty + 1) * BX + tx;
+        cs_limit_fast(S, 1, [&](int o) { return ex[o]; }, a0, a1);
+        PLN3(AX0, 0, 0) = a0;
+        PLN3(AX1, 0, 0) = a1;
+        cs_limit_fast(S, SP, [&](int o) { return ey[o * BX]; }, a0, a1);
+        PLN3(AY0, 0, 0) = a0;
+        PLN3(AY1, 0, 0) = a1;
+        edge_tables(tiles + wrap(c0 + 1) * SM::SLOT, etab + ((R + 1) & 1) * SM::NE);
+      } else {
+        if constexpr (BC) cell_par_bc<PPM>(S, 1, i, a.slope_order, lbx, a0, a1);
+        else cell_par<PPM>(S, 1, a.slope_order, nb, a0, a1);
+        PLN3(AX0, 0, 0) = a0;
+        if (PPM != 0) PLN3(AX1, 0, 0) = a1;
+        if constexpr (BC) cell_par_bc<PPM>(S, SP, j, a.slope_order, lby, a0, a1);
+        else cell_par<PPM>(S, SP, a.slope_order, nb, a0, a1);
+        PLN3(AY0, 0, 0) = a0;
+        if (PPM != 0) PLN3(AY1, 0, 0) = a1;
+      }
       if constexpr (ZROT) {
         zs[AGE(0)] = znew;
         s0 = zs[AGE(2)];
