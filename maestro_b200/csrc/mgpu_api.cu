@@ -1867,13 +1867,13 @@ int mgpu_set_option(const char* key, int value) {
   if (k == "defaults") {  // every switch back to its initial value (tests call this between cases)
     g_opt_fused = 1; g_opt_kchunk = -1; g_opt_async_upload = 1; g_opt_exact = 0; g_opt_leanplus = 1;
     g_opt_premac_fuse = 1; g_opt_overlap = 1;
-    bds_set_fast(1); velpred_set_fast(1); fused_edge3_set_split(1); fused_edge3_set_thin_edge(1); fused_edge3_set_pair_streams(1); fused_edge_set_variant(1);
+    bds_set_fast(1); velpred_set_fast(1); sphr_set_fast(1); fused_edge3_set_split(1); fused_edge3_set_thin_edge(1); fused_edge3_set_pair_streams(1); fused_edge_set_variant(1);
     fused_edge2_set_by(MGPU_FUSED2_BY); fused_edge2d_set_tile(2);
   }
   else if (k == "fused") g_opt_fused = value;
   else if (k == "kchunk") g_opt_kchunk = value;
   else if (k == "async_upload") g_opt_async_upload = value;
-  else if (k == "exact") { g_opt_exact = value; bds_set_fast(value == 0); velpred_set_fast(value == 0); }
+  else if (k == "exact") { g_opt_exact = value; bds_set_fast(value == 0); velpred_set_fast(value == 0); sphr_set_fast(value == 0); }
   else if (k == "leanplus") g_opt_leanplus = value;
   else if (k == "premac_fuse") g_opt_premac_fuse = value;
   else if (k == "split_tiles") fused_edge3_set_split(value);

@@ -31,6 +31,20 @@ __device__ __forceinline__ double quad_interp(double x, double x0, double x1, do
   return y;
 }
 
+// FAST build (Geom::fast, every option but exact = 1): the radial grid is uniform, r_cc_loc(i) = (i + 1/2) dr and
+// r_edge_loc(i) = i dr, so the six divisions of quad_interp by differences of neighbouring radii (each dr or 2 dr to the
+// last bit or two) and the divisions by dr of the linear forms become multiplications by 1/dr: the kernels that map the
+// base state onto the grid (put_1d_array_on_cart, make_s0mac / make_w0mac, the spherical force builders) held ~10 fp64
+// divisions and a square root per zone and ran at the fp64 pipe's pace.  The bin index keeps its division (a rounding
+// there would pick another stencil).  <= 1e-14 relative from the exact form.
+__device__ __forceinline__ double quad_interp_fast(double x, double x0, double x1, double rdr, double y0, double y1,
+                                                   double y2) {
+  double y = y0 + (y1 - y0) * rdr * (x - x0) + ((y2 - y1) - (y1 - y0)) * (0.5 * rdr * rdr) * (x - x0) * (x - x1);
+  if (y > max3(y0, y1, y2)) y = max3(y0, y1, y2);
+  if (y < min3(y0, y1, y2)) y = min3(y0, y1, y2);
+  return y;
+}
+
 __device__ double interp_edge(const Geom& g, int type, const double* s0, double radius) {
   const double dr = g.dr;
   int index = (int)(radius / dr);
@@ -39,7 +53,7 @@ __device__ double interp_edge(const Geom& g, int type, const double* s0, double 
     return (rfac > 0.5) ? s0[index + 1] : s0[index];
   }
   if (type == 2) {
-    const double rfac = (radius - (double)index * dr) / dr;
+    const double rfac = g.fast ? (radius - (double)index * dr) * g.rdr : (radius - (double)index * dr) / dr;
     if (index < g.nr_fine) return rfac * s0[index + 1] + (1.0 - rfac) * s0[index];
     return s0[g.nr_fine];
   }
@@ -47,6 +61,9 @@ __device__ double interp_edge(const Geom& g, int type, const double* s0, double 
   if (index <= 0) index = 0;
   else if (index >= g.nr_fine - 1) index = g.nr_fine - 2;
   else if (radius - g.r_edge_loc[index] < g.r_edge_loc[index + 1]) index = index - 1;
+  if (g.fast)
+    return quad_interp_fast(radius, g.r_edge_loc[index], g.r_edge_loc[index + 1], g.rdr, s0[index], s0[index + 1],
+                            s0[index + 2]);
   return quad_interp(radius, g.r_edge_loc[index], g.r_edge_loc[index + 1], g.r_edge_loc[index + 2], s0[index],
                      s0[index + 1], s0[index + 2]);
 }
@@ -59,14 +76,21 @@ __device__ double interp_cc(const Geom& g, int type, const double* s0, double ra
   if (type == 2) {
     if (radius >= g.r_cc_loc[index]) {
       if (index >= nr - 1) return s0[nr - 1];
+      if (g.fast)
+        return s0[index + 1] * (radius - g.r_cc_loc[index]) * g.rdr + s0[index] * (g.r_cc_loc[index + 1] - radius) * g.rdr;
       return s0[index + 1] * (radius - g.r_cc_loc[index]) / dr + s0[index] * (g.r_cc_loc[index + 1] - radius) / dr;
     }
     if (index == 0) return s0[index];
     if (index > nr - 1) return s0[nr - 1];
+    if (g.fast)
+      return s0[index] * (radius - g.r_cc_loc[index - 1]) * g.rdr + s0[index - 1] * (g.r_cc_loc[index] - radius) * g.rdr;
     return s0[index] * (radius - g.r_cc_loc[index - 1]) / dr + s0[index - 1] * (g.r_cc_loc[index] - radius) / dr;
   }
   if (index == 0) index = 1;
   else if (index >= nr - 1) index = nr - 2;
+  if (g.fast)
+    return quad_interp_fast(radius, g.r_cc_loc[index - 1], g.r_cc_loc[index], g.rdr, s0[index - 1], s0[index],
+                            s0[index + 1]);
   return quad_interp(radius, g.r_cc_loc[index - 1], g.r_cc_loc[index], g.r_cc_loc[index + 1], s0[index - 1], s0[index],
                      s0[index + 1]);
 }
@@ -342,6 +366,8 @@ Box3 mac_box(const int* lo, const int* hi, int d) {
 
 }  // namespace
 
+static int g_sphr_fast = 1;
+void sphr_set_fast(int on) { g_sphr_fast = on != 0; }
 Geom make_geom(const mgpu_params& P, const mgpu_geom& g) {
   if (P.dm != 3) throw Error("spherical geometry is 3-D only");
   if (g.nr_fine < 3) throw Error("spherical geometry: nr_fine must be at least 3");
@@ -353,6 +379,8 @@ Geom make_geom(const mgpu_params& P, const mgpu_geom& g) {
     d.dx[q] = P.dx[q];
   }
   d.dr = g.dr;
+  d.rdr = 1.0 / g.dr;
+  d.fast = g_sphr_fast;
   d.nr_fine = g.nr_fine;
   d.r_cc_loc = upload_small(g.r_cc_loc, (size_t)g.nr_fine);
   d.r_edge_loc = upload_small(g.r_edge_loc, (size_t)g.nr_fine + 1);

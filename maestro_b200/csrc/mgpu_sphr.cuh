@@ -9,11 +9,14 @@ namespace mgpu {
 struct Geom {
   double center[3], prob_lo[3], dx[3];
   double dr;
+  double rdr;  // 1 / dr
+  int fast;    // interpolation with multiplications by 1/dr (see quad_interp_fast); 0 in the exact build
   int nr_fine;
   const double* r_cc_loc;
   const double* r_edge_loc;
 };
 Geom make_geom(const mgpu_params& P, const mgpu_geom& g);
+void sphr_set_fast(int on);  // 1 (default): Geom::fast = 1 for every geometry made afterwards
 
 struct SphrFluxArgs {
   int spt, rho, rhoh;

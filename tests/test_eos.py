@@ -12,7 +12,41 @@ import numpy as np
 import pytest
 
 from maestro_b200 import Fab, abi, face_fabs
-from synth import make_episode_extras, make_state, relerr, same
+from synth import make_episode_extras, make_state, relerr
+from synth import same as _same_bits
+
+_EXACT = [True]
+
+
+def same(a, b):
+    """bit-identical in the exact build; in the FAST build (the default: reciprocals instead of divisions, e.g. in the
+    interpolation of the base state onto the grid) the north-star tolerance, 1e-12 relative"""
+    return _same_bits(a, b) if _EXACT[0] else relerr(a, b) <= 1e-12
+
+
+@pytest.fixture(autouse=True, params=[1, 0], ids=["exact", "fast"])
+def build(request):
+    """every test of this file runs against both builds of the library, unless it chooses the build itself"""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    import torch
+
+    if not torch.cuda.is_available():
+        yield
+        return
+    from maestro_b200 import lib
+
+    if "exact" in request.fixturenames:
+        if request.param == 0:
+            pytest.skip("the test sets the build itself")
+        yield
+        return
+    lib.set_option("exact", request.param)
+    _EXACT[0] = bool(request.param)
+    yield
+    _EXACT[0] = True
+    lib.set_option("exact", 0)
 
 K_B, N_A = 1.3806488e-16, 6.02214129e23  # Source/constants_cgs.f90:15,24
 AION = [4.0, 12.0, 16.0]

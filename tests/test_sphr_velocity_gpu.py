@@ -4,9 +4,43 @@ import numpy as np
 import pytest
 
 from maestro_b200 import Fab, abi, face_fabs
-from synth import make_episode_extras, make_vel_state, relerr, same
+from synth import make_episode_extras, make_vel_state, relerr
+from synth import same as _same_bits
 
 pytestmark = pytest.mark.gpu
+
+_EXACT = [True]
+
+
+def same(a, b):
+    """bit-identical in the exact build; in the FAST build (the default: reciprocals instead of divisions, e.g. in the
+    interpolation of the base state onto the grid) the north-star tolerance, 1e-12 relative"""
+    return _same_bits(a, b) if _EXACT[0] else relerr(a, b) <= 1e-12
+
+
+@pytest.fixture(autouse=True, params=[1, 0], ids=["exact", "fast"])
+def build(request):
+    """every test of this file runs against both builds of the library, unless it chooses the build itself"""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    import torch
+
+    if not torch.cuda.is_available():
+        yield
+        return
+    from maestro_b200 import lib
+
+    if "exact" in request.fixturenames:
+        if request.param == 0:
+            pytest.skip("the test sets the build itself")
+        yield
+        return
+    lib.set_option("exact", request.param)
+    _EXACT[0] = bool(request.param)
+    yield
+    _EXACT[0] = True
+    lib.set_option("exact", 0)
 OUTLET = [[abi.OUTLET, abi.OUTLET]] * 3
 SHAPE = (12, 10, 14)
 
