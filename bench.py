@@ -340,7 +340,10 @@ def main():
 
     # roofline of the dominant kernel class
     hbm, peak_src = peaks()
-    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
+    # ("glue" is a bag of a dozen single-purpose streaming kernels, not a kernel: the roofline line is about the largest
+    # class that is ONE kernel -- on c5 that is still the edge-state kernel although the bag as a whole takes longer)
+    single = {k: v for k, v in prof.items() if k != "glue"} or prof
+    dom = max(single.items(), key=lambda kv: kv[1][0]) if single else (None, (0.0, 0))
     roof = None
     if dom[0] is not None and dom[1][1] > 0:
         name, (ms, nl) = dom
