@@ -56,7 +56,10 @@ struct Smem3 {
   // ppm_type 2 (H == 3): two tables of the limited edge values of a plane's tile, (BX+3) x BY x-faces and BX x (BY+3)
   // y-faces (planes t and t+1), see the E phase of the kernel
   static constexpr int NEX = (BX + 3) * BY, NEY = BX * (BY + 3), NE = NEX + NEY;
-  static constexpr int NEDGE = (H == 3) ? 2 * NE : 0;
+  // ppm_type 1 (H == 2): one table of the van Leer slopes of a plane's tile and of the cells just outside it,
+  // BY x (BX+2) in x and (BY+2) x BX in y (see the S phase of the kernel); same place as the edge tables
+  static constexpr int NSX = BY * (BX + 2), NSY = (BY + 2) * BX;
+  static constexpr int NEDGE = (H == 3) ? 2 * NE : NSX + NSY;
   static constexpr int BYTES = (NTILE + NPLANES * PL) * 8 + 64 + 2 * KCAP * 8 + NEDGE * 8;  // + mbarriers + per-plane constants + edge tables
 };
 
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(BX* BY, 2)
   double* const sWadd = reinterpret_cast<double*>(bars + 8);
   double* const sSub = sWadd + SM::KCAP;
   constexpr bool ESH = (PPM == 2) && !BC;  // x / y edge values shared through the tables below
+  constexpr bool SSH = (PPM == 1) && !BC;  // x / y van Leer slopes shared through the table below
   double* const etab = sSub + SM::KCAP;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * BX + tx;
   double* const pl = planes + ty * P + tx;       // this thread's cell in plane 0
@@ -241,6 +245,26 @@ __global__ void __launch_bounds__(BX* BY, 2)
     }
   };
 
+  // S phase (ppm_type 1, no boundary rules): the parabola of a cell needs the van Leer slopes of the cells i-1, i, i+1
+  // of each direction (ppm.f90:1697-1752); left to itself every thread evaluates six slopes per plane and every slope
+  // is evaluated three times.  Here every thread evaluates the two slopes of its own cell a step before the plane is
+  // reconstructed and two warps add the 4 x 16 cells just outside the tile; T = the (transformed) tile of that plane.
+  auto slope_tables = [&](const double* T) {
+    const double* q = T + sc_idx;
+    etab[ty * (BX + 2) + tx + 1] = dsvl_fast(q[-1], q[0], q[1]);
+    etab[SM::NSX + (ty + 1) * BX + tx] = dsvl_fast(q[-SP], q[0], q[SP]);
+    if (tid < 64) {  // (spread over eight lanes of every warp instead: measured slower, 3.34 against 3.25 ms per episode)
+      const int r = tid & 15, w = tid >> 4;  // w: 0 the column left of the tile, 1 right of it, 2 the row below, 3 above
+      if (w < 2) {
+        const double* c = T + (r + H) * SP + (w == 0 ? -1 : BX) + H + xsh;
+        etab[r * (BX + 2) + (w == 0 ? 0 : BX + 1)] = dsvl_fast(c[-1], c[0], c[1]);
+      } else {
+        const double* c = T + ((w == 2 ? -1 : BY) + H) * SP + r + H + xsh;
+        etab[SM::NSX + (w == 2 ? 0 : BY + 1) * BX + r] = dsvl_fast(c[-SP], c[0], c[SP]);
+      }
+    }
+  };
+
   const int t0 = kz0 - 1;
   const int t1 = kz1 + 2 + (top ? 1 : 0);
   if (tid == 0) {
@@ -346,6 +370,11 @@ __global__ void __launch_bounds__(BX* BY, 2)
     if constexpr (XF != 0) __syncthreads();
     edge_tables(tiles, etab);
   }
+  if constexpr (SSH) {
+    static_assert(BX == 16 && BY == 16, "slope_tables shares the outer cells out over 4 x 16 threads");
+    if constexpr (XF != 0) __syncthreads();
+    slope_tables(tiles);
+  }
   int c0 = 0;                // slot of plane t
   int slot_w = H + 1;        // slot (and parity) of the next tile to wait for: plane t+H+1
   unsigned par_w = 0;
@@ -383,6 +412,26 @@ __global__ void __launch_bounds__(BX* BY, 2)
         PLN3(AY0, 0, 0) = a0;
         PLN3(AY1, 0, 0) = a1;
         edge_tables(tiles + wrap(c0 + 1) * SM::SLOT, etab + ((R + 1) & 1) * SM::NE);
+      } else if constexpr (SSH) {  // slopes of plane t from the table written in the face phase of the last step
+        const double* const sx = etab + ty * (BX + 2) + tx + 1;
+        const double* const sy = etab + SM::NSX + (ty + 1) * BX + tx;
+        const double c0v = S[0];
+        {
+          const double m1 = S[-1], p1 = S[1], d0 = sx[0];
+          a0 = edge_fast(m1, c0v, sx[-1], d0);
+          a1 = edge_fast(c0v, p1, d0, sx[1]);
+          cw_limit(c0v, a0, a1);
+          PLN3(AX0, 0, 0) = a0;
+          PLN3(AX1, 0, 0) = a1;
+        }
+        {
+          const double m1 = S[-SP], p1 = S[SP], d0 = sy[0];
+          a0 = edge_fast(m1, c0v, sy[-BX], d0);
+          a1 = edge_fast(c0v, p1, d0, sy[BX]);
+          cw_limit(c0v, a0, a1);
+          PLN3(AY0, 0, 0) = a0;
+          PLN3(AY1, 0, 0) = a1;
+        }
       } else {
         if constexpr (BC) cell_par_bc<PPM>(S, 1, i, a.slope_order, lbx, a0, a1);
         else cell_par<PPM>(S, 1, a.slope_order, nb, a0, a1);
@@ -560,6 +609,9 @@ __global__ void __launch_bounds__(BX* BY, 2)
       slot_w = 0;
       par_w ^= 1u;
     }
+    // S(t+1): the slopes of plane t+1 (its tile was transformed before barrier A); every read of the table by C1(t)
+    // lies before barrier B, the next ones behind the next barrier A
+    if constexpr (SSH) slope_tables(tiles + wrap(c0 + 1) * SM::SLOT);
     // F1(t): simhx, simhy
     bool anyf;
     {
