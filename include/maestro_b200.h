@@ -361,7 +361,11 @@ int mgpu_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int whi
  * Signature mirrors the Fortran argument list; sold is modified in place exactly as the reference
  * does (rhoX->X->rhoX, rho->rho'->rho round trips), umac is (umac+w0)-w0 on return, sedge, sflux,
  * etarhoflux, scal_force and snew (valid + ghost cells) are fully populated on return.
- * pmask[d]=1 => periodic in d (FBoxLib layout pmask); single box per rank (slab). */
+ * Exception (FAST build, 3-D, fully periodic domain: the "lean+" episode): the input transforms
+ * happen inside the edge kernel, so sold and umac come back UNTOUCHED -- one rounding away from the reference's round
+ * trips (rhoX/rho)*rho and (umac+w0)-w0; option exact = 1 or leanplus = 0 restores the literal sequence.
+ * pmask[d]=1 => periodic in d (FBoxLib layout pmask); single box per rank (slab).
+ * spherical == 1: call mgpu_density_advance_sphr (this entry raises). */
 int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, mgpu_fab* snew,
                          mgpu_fab* const* sedge, mgpu_fab* const* sflux, mgpu_fab* scal_force,
                          mgpu_fab* const* umac, const double* w0, mgpu_fab* etarhoflux,

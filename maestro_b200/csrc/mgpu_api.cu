@@ -2222,7 +2222,7 @@ int mgpu_update_velocity(const mgpu_params* p, int nfabs, const mgpu_fab* uold, 
                          const mgpu_fab* const* umac, const mgpu_fab* const* uedge, const mgpu_fab* force,
                          const mgpu_fab* sponge, const double* w0) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_update_velocity: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_update_velocity: spherical == 1 is served by mgpu_update_velocity_sphr");
   Call c(p, (size_t)(p->nr + 2) * sizeof(double) + 4096);
   for (int i = 0; i < nfabs; ++i) {
     VelArgs a;
@@ -2246,7 +2246,7 @@ int mgpu_update_velocity(const mgpu_params* p, int nfabs, const mgpu_fab* uold, 
 
 int mgpu_addw0(const mgpu_params* p, int nfabs, mgpu_fab* const* umac, const double* w0, double mult) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_addw0: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_addw0: spherical == 1 is served by mgpu_addw0_sphr");
   Call c(p, (size_t)(p->nr + 2) * sizeof(double) + 4096);
   const double* w0d = upload_small(w0, p->nr + 1);
   for (int i = 0; i < nfabs; ++i) {
@@ -2298,7 +2298,7 @@ int mgpu_modify_scal_force(const mgpu_params* p, int nfabs, mgpu_fab* force, con
                            const mgpu_fab* const* umac, const double* s0, const double* s0_edge, const double* w0,
                            int comp, int fullform) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_modify_scal_force: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_modify_scal_force: spherical == 1 is served by mgpu_modify_scal_force_sphr");
   Call c(p, (size_t)(3 * (p->nr + 2)) * sizeof(double) + 4096);
   const double* s0d = upload_small(s0, p->nr);
   const double* s0ed = upload_small(s0_edge, p->nr + 1);
@@ -2326,7 +2326,7 @@ int mgpu_convert_rhoX_to_X(const mgpu_params* p, int nfabs, mgpu_fab* s, int fla
 
 int mgpu_put_in_pert_form(const mgpu_params* p, int nfabs, mgpu_fab* s, const double* base, int comp, int flag) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_put_in_pert_form: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_put_in_pert_form: spherical == 1 is served by mgpu_put_in_pert_form_sphr");
   Call c(p, (size_t)(p->nr + 2) * sizeof(double) + 4096);
   const double* bd = upload_small(base, p->nr);
   for (int i = 0; i < nfabs; ++i) {
@@ -2344,7 +2344,7 @@ int mgpu_density_advance(const mgpu_params* p, int which_step, mgpu_fab* sold, m
                          const int* adv_bc, const int* pmask) {
   MGPU_TRY
   (void)p0_dummy;
-  if (p->spherical) throw Error("mgpu_density_advance: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_density_advance: spherical == 1 is served by mgpu_density_advance_sphr");
   size_t one_comp = sizeof(double) + 256;  // the lean+ path keeps 1/rho of the whole fab in the arena
   for (int d = 0; d < p->dm; ++d) one_comp *= (size_t)(sold->hi[d] - sold->lo[d] + 1 + 2 * sold->ng);
   Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) + one_comp +
@@ -2423,7 +2423,7 @@ int mgpu_density_advance_mf(const mgpu_params* p, int which_step, int nfabs, mgp
                             const int* pmask) {
   MGPU_TRY
   (void)p0_dummy;
-  if (p->spherical) throw Error("mgpu_density_advance_mf: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_density_advance_mf: the spherical episode takes one box per rank (mgpu_density_advance_sphr)");
   if (nfabs < 1) throw Error("mgpu_density_advance_mf: nfabs must be at least 1");
   size_t scratch = 0;
   for (int i = 0; i < nfabs; ++i)
@@ -2586,7 +2586,7 @@ int mgpu_mkrhohforce(const mgpu_params* p, int nfabs, mgpu_fab* scal_force, int 
                      const mgpu_fab* const* umac, const double* p0_1, const double* p0_2, const double* rho0_1,
                      const double* rho0_2, const double* grav, const double* psi, int add_thermal) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_mkrhohforce: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_mkrhohforce: spherical == 1 is served by mgpu_mkrhohforce_sphr");
   const int ept = p->enthalpy_pred_type;
   if (is_prediction && !(ept == MGPU_PREDICT_RHOHPRIME || ept == MGPU_PREDICT_H || ept == MGPU_PREDICT_RHOH))
     throw Error("ERROR: should only call mkrhohforce when predicting rhoh', h, or rhoh");  // mkscalforce.f90:87-92
@@ -2619,7 +2619,7 @@ int mgpu_mk_vel_force(const mgpu_params* p, int nfabs, mgpu_fab* vel_force, int 
                       int index_rho, const double* rho0, const double* grav, const double* w0_force,
                       int do_add_utilde_force) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_mk_vel_force: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_mk_vel_force: spherical == 1 is served by mgpu_mk_vel_force_sphr");
   Call c(p, (size_t)(6 * (p->nr + 2)) * sizeof(double) + 8192);
   const int nr = p->nr;
   VelForceArgs a;
@@ -2649,7 +2649,7 @@ int mgpu_advance_premac(const mgpu_params* p, const mgpu_fab* uold, const mgpu_f
                         const mgpu_fab* gpi, const double* w0, const double* w0_force, const double* rho0_old,
                         const double* grav_cell_old, const int* adv_bc, const int* phys_bc, const int* pmask) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_advance_premac: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_advance_premac: spherical == 1 is served by mgpu_advance_premac_sphr");
   Call c(p, advance_premac_scratch(*p, uold->lo, uold->hi, uold->ng));
   DV uo = c.view(*uold, true, false), gp = c.view(*gpi, true, false);
   DV so = c.view(*sold, crange(p->rho_comp - 1, 1), (cmask_t)0);
@@ -2667,7 +2667,7 @@ int mgpu_velocity_advance(const mgpu_params* p, const mgpu_fab* uold, mgpu_fab* 
                           const double* grav_cell_old, const double* grav_cell_nph, const mgpu_fab* sponge,
                           const int* adv_bc, const int* pmask) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_velocity_advance: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_velocity_advance: spherical == 1 is served by mgpu_velocity_advance_sphr");
   Call c(p, velocity_advance_scratch(*p, uold->lo, uold->hi, uold->ng));
   DV uo = c.view(*uold, true, false), un = c.view(*unew, true, true), gp = c.view(*gpi, true, false);
   DV so = c.view(*sold, crange(p->rho_comp - 1, 1), (cmask_t)0), rh = c.view(*rhohalf, true, false);
@@ -3087,7 +3087,7 @@ int mgpu_estdt(const mgpu_params* p, int nfabs, const mgpu_fab* u, const mgpu_fa
                const mgpu_fab* divU, const mgpu_fab* dSdt, const double* w0, const double* p0,
                const double* gamma1bar, double rho_min, double cflfac, double* dt, double* umax) {
   MGPU_TRY
-  if (p->spherical) throw Error("mgpu_estdt: spherical geometry not available on the device yet");
+  if (p->spherical) throw Error("mgpu_estdt: spherical == 1 is served by mgpu_estdt_sphr");
   const int nr = p->nr, dm = p->dm;
   Call c(p, (size_t)(4 * (nr + 2) + 148 * 8 * 8 + 64) * sizeof(double) + 8192);
   const double* w0_d = upload_small(w0, nr + 1);
