@@ -161,7 +161,9 @@ __global__ void k_addw0_sphr(DV um, DV wm, Box3 fb, double mult) {
   um(ix[0], ix[1], ix[2]) = um(ix[0], ix[1], ix[2]) + mult * wm(ix[0], ix[1], ix[2]);
 }
 
-__global__ void k_rhoX_flux_sphr(SphrFluxArgs a, int d, int comp) {
+// components comp0 .. comp1 of one face direction in one pass: the velocity and the density factor of a face are
+// the same for every component (mkflux.f90:560-640), the product is formed in the reference's order, vel * rho * X
+__global__ void k_rhoX_flux_sphr(SphrFluxArgs a, int d, int comp0, int comp1) {
   int ix[3];
   Box3 fb = a.vb;
   fb.hi[d] += 1;
@@ -169,16 +171,16 @@ __global__ void k_rhoX_flux_sphr(SphrFluxArgs a, int d, int comp) {
   const int i = ix[0], j = ix[1], k = ix[2];
   const double vel = a.umac[d](i, j, k) + a.w0mac[d](i, j, k);
   const DV& se = a.sedge[d];
-  double f;
+  double vr;
   if (a.spt == MGPU_PREDICT_RHOPRIME_AND_X) {
     const double rho0_edge = 0.5 * (a.r0o[d](i, j, k) + a.r0n[d](i, j, k));
-    f = vel * (rho0_edge + se(i, j, k, a.rho)) * se(i, j, k, comp);
+    vr = vel * (rho0_edge + se(i, j, k, a.rho));
   } else if (a.spt == MGPU_PREDICT_RHOX) {
-    f = vel * se(i, j, k, comp);
+    vr = vel;
   } else {
-    f = vel * se(i, j, k, a.rho) * se(i, j, k, comp);
+    vr = vel * se(i, j, k, a.rho);
   }
-  a.sflux[d](i, j, k, comp) = f;
+  for (int comp = comp0; comp <= comp1; ++comp) a.sflux[d](i, j, k, comp) = vr * se(i, j, k, comp);
 }
 
 // mode: 0 h, 1 h', 2 rhoh, 3 (rho h)'
@@ -419,12 +421,11 @@ void addw0_sphr_dev(DV* umac, const DV* w0mac, double mult, const int* lo, const
 }
 
 void mk_rhoX_flux_sphr_dev(SphrFluxArgs& a, int startcomp, int endcomp) {
-  for (int comp = startcomp; comp <= endcomp; ++comp)
-    for (int d = 0; d < 3; ++d) {
-      Box3 fb = a.vb;
-      fb.hi[d] += 1;
-      MGPU_TIMED(TAG_FLUX, (k_rhoX_flux_sphr<<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a, d, comp - 1)));
-    }
+  for (int d = 0; d < 3; ++d) {
+    Box3 fb = a.vb;
+    fb.hi[d] += 1;
+    MGPU_TIMED(TAG_FLUX, (k_rhoX_flux_sphr<<<grid3(fb, 256), block3(fb, 256), 0, ctx().stream>>>(a, d, startcomp - 1, endcomp - 1)));
+  }
 }
 
 void mk_rhoh_flux_sphr_dev(const mgpu_params& P, SphrFluxArgs& a) {
