@@ -801,6 +801,52 @@ static void fill_faces_dev(const mgpu_params& P, DV* u, const int* lo, const int
   fb.run();
 }
 
+// umac + w0mac for the predictions of a spherical episode (addw0 with mult = 1, its ghost fill, and after the
+// predictions addw0 with mult = -1 and its ghost fill: density_advance.f90:148/258, enthalpy_advance.f90:201/293,
+// velocity_advance.f90:90/115).  Exact build: in place, as the reference.  FAST build: the sum goes into a scratch copy in
+// one pass and umac is left alone -- half the traffic, and umac comes back untouched where the reference returns
+// (umac + w0mac) - w0mac, one rounding away.
+struct UmacPlusW0 {
+  const mgpu_params& P;
+  DV* umac;
+  const DV* w0mac;
+  const int *lo, *hi, *adv_bc, *pmask;
+  DV utot[3];
+  bool copy;
+  UmacPlusW0(const mgpu_params& P_, DV* umac_, const DV* w0mac_, const int* lo_, const int* hi_, const int* adv_bc_,
+             const int* pmask_)
+      : P(P_), umac(umac_), w0mac(w0mac_), lo(lo_), hi(hi_), adv_bc(adv_bc_), pmask(pmask_), copy(g_opt_exact == 0) {
+    DV wm[3] = {w0mac[0], w0mac[1], w0mac[2]};
+    if (copy) {
+      for (int d = 0; d < 3; ++d) {
+        utot[d] = umac[d];
+        utot[d].p = arena_alloc((size_t)umac[d].size());
+      }
+      sum_faces_sphr_dev(utot, umac, wm, lo, hi);
+    } else {
+      addw0_sphr_dev(umac, wm, 1.0, lo, hi);
+    }
+    fill(copy ? utot : umac);
+  }
+  DV* faces() { return copy ? utot : umac; }
+  void restore() {
+    if (copy) return;
+    DV wm[3] = {w0mac[0], w0mac[1], w0mac[2]};
+    addw0_sphr_dev(umac, wm, -1.0, lo, hi);
+    fill(umac);
+  }
+  void fill(DV* u) {
+    FillBatch fb;
+    for (int d = 0; d < 3; ++d) fill_boundary_dev(P, u[d], lo, hi, 1, NODAL_OF[d], 1, 1, 1, adv_bc, pmask, false);
+    fb.run();
+  }
+};
+static size_t umac_copy_bytes(const int* lo, const int* hi) {
+  size_t n = 1;
+  for (int d = 0; d < 3; ++d) n *= (size_t)(hi[d] - lo[d] + 1 + 3);
+  return 3 * (n * sizeof(double) + 256);
+}
+
 // ---- density_advance, spherical (density_advance.f90:20 with spherical == 1) ---------------------------------------
 static void density_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, int which_step, DV& sold, DV& snew,
                                      DV* sedge, DV* sflux, DV& scal_force, DV* umac, const double* w0_h, const DV* w0mac,
@@ -819,11 +865,6 @@ static void density_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, i
     fill_boundary_dev(P, c, lo, hi, ng, nullptr, 1, dm + P.rho_comp, 1, adv_bc, pmask, false);
     return c;
   };
-  auto fill_umac = [&]() {
-    FillBatch fb;
-    for (int d = 0; d < dm; ++d) fill_boundary_dev(P, umac[d], lo, hi, 1, NODAL_D[d], 1, 1, 1, adv_bc, pmask, false);
-    fb.run();
-  };
   set_dev(scal_force.p, 0.0, scal_force.size());
   if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {
     DV rho0_old_cart = cart_of(rho0_old, 1);
@@ -831,11 +872,8 @@ static void density_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, i
                                spt == MGPU_PREDICT_RHO_AND_X, lo, hi);
     fill_boundary_dev(P, scal_force, lo, hi, ng_f, nullptr, P.rho_comp, foextrap_comp, 1, adv_bc, pmask, false);
   }
-  {
-    DV wm[3] = {w0mac[0], w0mac[1], w0mac[2]};
-    addw0_sphr_dev(umac, wm, 1.0, lo, hi);
-  }
-  fill_umac();
+  UmacPlusW0 uw(P, umac, w0mac, lo, hi, adv_bc, pmask);  // :148
+  DV* const ue = uw.faces();
   if (spt == MGPU_PREDICT_RHOPRIME_AND_X || spt == MGPU_PREDICT_RHO_AND_X) {
     convert_rhoX_to_X_dev(P, sold, true, lo, hi);
     fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, foextrap_comp, P.nspec, adv_bc, pmask, true);
@@ -848,11 +886,11 @@ static void density_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, i
     for (int n = 0; n < ncomp; ++n) {
       if (P.bds_type != 0) {
         size_t mark = arena_mark();
-        bds_dev(P, sold, sedge, umac, scal_force, lo, hi, scomp - 1 + n, cons, ng_s, ng_f);
+        bds_dev(P, sold, sedge, ue, scal_force, lo, hi, scomp - 1 + n, cons, ng_s, ng_f);
         arena_release(mark);
         continue;
       }
-      edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, scomp - 1 + n, dm + scomp + n, false, cons, ng_s,
+      edge_one_comp(P, sold, sedge, ue, scal_force, lo, hi, adv_bc, scomp - 1 + n, dm + scomp + n, false, cons, ng_s,
                     ng_f);
     }
   };
@@ -871,11 +909,7 @@ static void density_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, i
     fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.spec_comp, dm + P.spec_comp, P.nspec, adv_bc, pmask, false);
   }
   if (P.ntrac >= 1) edge(P.trac_comp, P.ntrac, false);
-  {
-    DV wm[3] = {w0mac[0], w0mac[1], w0mac[2]};
-    addw0_sphr_dev(umac, wm, -1.0, lo, hi);
-  }
-  fill_umac();
+  uw.restore();  // :258
   // rho0mac_old / rho0mac_new (make_s0mac, fill_3d_data.f90:942)
   auto mac_of = [&](const double* s0_dev, DV* mac) {
     for (int d = 0; d < 3; ++d) {
@@ -1118,16 +1152,14 @@ static void velocity_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
   for (int d = 0; d < dm; ++d) uedge[d] = arena_fab(lo, hi, dm, 0, NODAL_D[d], dm);
   vel_force_sphr_full(P, g, gd, force, false, uold, umac, w0_h, w0mac, gpi, sold.comp(P.rho_comp - 1), normal, rho0_old_h,
                       grav_old_h, w0fc, lo, hi, ng_f, adv_bc, pmask);  // :80
-  addw0_sphr_dev(umac, w0mac, 1.0, lo, hi);  // :90
-  fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
+  UmacPlusW0 uw(P, umac, w0mac, lo, hi, adv_bc, pmask);  // :90
   for (int c = 0; c < dm; ++c) {  // :102-109
     size_t mark = arena_mark();
-    if (P.bds_type != 0) bds_dev(P, uold, uedge, umac, force, lo, hi, c, false, ng_u, ng_f);
-    else edge_one_comp(P, uold, uedge, umac, force, lo, hi, adv_bc, c, 1 + c, true, false, ng_u, ng_f);
+    if (P.bds_type != 0) bds_dev(P, uold, uedge, uw.faces(), force, lo, hi, c, false, ng_u, ng_f);
+    else edge_one_comp(P, uold, uedge, uw.faces(), force, lo, hi, adv_bc, c, 1 + c, true, false, ng_u, ng_f);
     arena_release(mark);
   }
-  addw0_sphr_dev(umac, w0mac, -1.0, lo, hi);  // :115
-  fill_faces_dev(P, umac, lo, hi, adv_bc, pmask);
+  uw.restore();  // :115
   vel_force_sphr_full(P, g, gd, force, true, uold, umac, w0_h, w0mac, gpi, rhohalf.comp(0), normal, rho0_nph_h, grav_nph_h,
                       w0fc, lo, hi, ng_f, adv_bc, pmask);  // :122
   VelArgs a;
@@ -1221,7 +1253,6 @@ static void enthalpy_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
   }
   const double* h0_old = upload_small(h0o.data(), (size_t)nr);
   const double* h0_new = upload_small(h0n.data(), (size_t)nr);
-  auto fill_umac = [&]() { fill_faces_dev(P, umac, lo, hi, adv_bc, pmask); };
   auto rhoh_to_h = [&](bool flag) {  // convert_rhoh_to_h, convert_rhoX_to_X.f90:80
     comp_muldiv_dev(P, sold, rhoh, sold, rho, flag ? 0 : 1, 0, lo, hi);
     fill_boundary_dev(P, sold, lo, hi, ng_s, nullptr, P.rhoh_comp, flag ? foextrap_comp : dm + P.rhoh_comp, 1, adv_bc,
@@ -1268,16 +1299,15 @@ static void enthalpy_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
   } else if (ept == MGPU_PREDICT_H) {  // :173-178
     comp_muldiv_dev(P, scal_force, rhoh, sold, rho, 0, 1, lo, hi);
   }
-  addw0_sphr_dev(umac, w0mac, 1.0, lo, hi);  // :201
-  fill_umac();
+  UmacPlusW0 uw(P, umac, w0mac, lo, hi, adv_bc, pmask);  // :201
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(true);  // :204-208
   if (ept == MGPU_PREDICT_TPRIME_THEN_H) pert_T(true);
   {
     const bool cons = (ept == MGPU_PREDICT_RHOH);  // :232-254
     const int pc = pred_T ? temp : rhoh;           // :220-226
     size_t mark = arena_mark();
-    if (P.bds_type != 0) bds_dev(P, sold, sedge, umac, scal_force, lo, hi, pc, cons, ng_s, ng_f);
-    else edge_one_comp(P, sold, sedge, umac, scal_force, lo, hi, adv_bc, pc, dm + pc + 1, false, cons, ng_s, ng_f);
+    if (P.bds_type != 0) bds_dev(P, sold, sedge, uw.faces(), scal_force, lo, hi, pc, cons, ng_s, ng_f);
+    else edge_one_comp(P, sold, sedge, uw.faces(), scal_force, lo, hi, adv_bc, pc, dm + pc + 1, false, cons, ng_s, ng_f);
     arena_release(mark);
   }
   if (ept == MGPU_PREDICT_RHOHPRIME) pert(false);  // :257-261
@@ -1303,8 +1333,7 @@ static void enthalpy_advance_sphr_dev(const mgpu_params& P, const mgpu_geom& g, 
     h_from_rhot_edge_dev(ha);
     arena_release(mark);
   }
-  addw0_sphr_dev(umac, w0mac, -1.0, lo, hi);       // :293
-  fill_umac();
+  uw.restore();  // :293
   const bool s1 = (which_step == 1);
   {
     size_t mark = arena_mark();
@@ -2933,7 +2962,7 @@ int mgpu_density_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int whic
   size_t cell = 1;
   for (int d = 0; d < 3; ++d) cell *= (size_t)(sold->hi[d] - sold->lo[d] + 1 + 6);
   Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
-                10 * (cell * sizeof(double) + 256) + geom_scratch(g) + 8192);
+                10 * (cell * sizeof(double) + 256) + umac_copy_bytes(sold->lo, sold->hi) + geom_scratch(g) + 8192);
   DV so = c.view(*sold, true, true), sn = c.view(*snew, true, true), fv = c.view(*scal_force, false, true);
   DV se[3], sf[3], um[3], wm[3];
   c.views((const mgpu_fab* const*)sedge, 0, true, true, se);
@@ -3018,7 +3047,7 @@ int mgpu_velocity_advance_sphr(const mgpu_params* p, const mgpu_geom* g, const m
   need_sphr(p, g);
   if (!p->spherical) throw Error("velocity_advance_sphr: params.spherical must be 1");
   Call c(p, velocity_advance_scratch(*p, uold->lo, uold->hi, uold->ng) + sphr_force_scratch(uold->lo, uold->hi) +
-                geom_scratch(g) + (size_t)(6 * (g->nr_fine + 4)) * sizeof(double));
+                umac_copy_bytes(uold->lo, uold->hi) + geom_scratch(g) + (size_t)(6 * (g->nr_fine + 4)) * sizeof(double));
   DV uo = c.view(*uold, true, false), un = c.view(*unew, true, true), gp = c.view(*gpi, true, false);
   DV so = c.view(*sold, crange(p->rho_comp - 1, 1), (cmask_t)0), rh = c.view(*rhohalf, true, false);
   DV sp = c.view(*sponge, true, false), nm = c.view(*normal, true, false), wf = c.view(*w0_force_cart, true, false);
@@ -3063,7 +3092,7 @@ int mgpu_enthalpy_advance_sphr(const mgpu_params* p, const mgpu_geom* g, int whi
   need_sphr(p, g);
   if (!p->spherical) throw Error("enthalpy_advance_sphr: params.spherical must be 1");
   Call c(p, std::max(make_edge_scal_scratch(*p, sold->lo, sold->hi), bds_scratch(*p, sold->lo, sold->hi)) +
-                14 * fab_bytes(sold->lo, sold->hi, 3, 2, 1, 1) + geom_scratch(g) +
+                14 * fab_bytes(sold->lo, sold->hi, 3, 2, 1, 1) + umac_copy_bytes(sold->lo, sold->hi) + geom_scratch(g) +
                 (size_t)(16 * (g->nr_fine + 4)) * sizeof(double) + 16384);
   const EnthalpyMasks m = enthalpy_masks(*p);
   DV so = c.view(*sold, m.sold_in, m.sold_out), sn = c.view(*snew, m.snew_in, m.mrhoh);

@@ -412,6 +412,28 @@ void make_mac_dev(const mgpu_geom& g, const Geom& gd, const double* s0_dev, DV* 
   }
 }
 
+// utot = umac + w0mac on the valid faces and umac itself on the ghost faces (what addw0 leaves there), the whole fab
+// extent in one pass: the FAST spherical episodes predict with this copy and leave umac alone
+__global__ void k_sum_faces_sphr(DV ut, DV um, DV wm, Box3 all, Box3 fb) {
+  int ix[3];
+  if (!decode3(all, ix)) return;
+  const bool in = ix[0] >= fb.lo[0] && ix[0] <= fb.hi[0] && ix[1] >= fb.lo[1] && ix[1] <= fb.hi[1] && ix[2] >= fb.lo[2] &&
+                  ix[2] <= fb.hi[2];
+  const double u = um(ix[0], ix[1], ix[2]);
+  ut(ix[0], ix[1], ix[2]) = in ? u + 1.0 * wm(ix[0], ix[1], ix[2]) : u;
+}
+void sum_faces_sphr_dev(DV* utot, const DV* umac, const DV* w0mac, const int* lo, const int* hi) {
+  for (int d = 0; d < 3; ++d) {
+    Box3 fb = grown(lo, hi, 3, 0), all;
+    fb.hi[d] += 1;
+    for (int q = 0; q < 3; ++q) {
+      all.lo[q] = umac[d].lo[q];
+      all.hi[q] = umac[d].lo[q] + umac[d].n[q] - 1;
+    }
+    MGPU_TIMED(TAG_GLUE, (k_sum_faces_sphr<<<grid3(all, 256), block3(all, 256), 0, ctx().stream>>>(utot[d], umac[d], w0mac[d], all, fb)));
+  }
+}
+
 void addw0_sphr_dev(DV* umac, const DV* w0mac, double mult, const int* lo, const int* hi) {
   for (int d = 0; d < 3; ++d) {
     Box3 fb = grown(lo, hi, 3, 0);

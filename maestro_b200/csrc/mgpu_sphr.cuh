@@ -29,6 +29,8 @@ void put_1d_array_on_cart_dev(const mgpu_params& P, const mgpu_geom& g, const Ge
 // kind 0: make_w0mac, kind 1: make_s0mac
 void make_mac_dev(const mgpu_geom& g, const Geom& gd, const double* s0_dev, DV* mac, const DV* cart, int kind,
                   const int* lo, const int* hi);
+// utot (same layout as umac) = umac + w0mac on the valid faces, umac on the ghost faces
+void sum_faces_sphr_dev(DV* utot, const DV* umac, const DV* w0mac, const int* lo, const int* hi);
 void addw0_sphr_dev(DV* umac, const DV* w0mac, double mult, const int* lo, const int* hi);
 void mk_rhoX_flux_sphr_dev(SphrFluxArgs& a, int startcomp, int endcomp);
 void mk_rhoh_flux_sphr_dev(const mgpu_params& P, SphrFluxArgs& a);
