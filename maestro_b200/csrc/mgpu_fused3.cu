@@ -52,6 +52,9 @@ struct Smem3 {
   enum { R_SHX = 0, R_SHY, R_US, R_VS, NRING };
   static constexpr int RS = NRING * PL;
   static constexpr int NTILE = NS * SLOT * (DIV ? 2 : 1);
+  // thread (0, 0) reads plane AX0 one element below its start when its x face takes the low cell (a value no face
+  // uses): the pad keeps that read off the last tile slot, which the TMA unit and the tile transform write
+  static constexpr int PAD = 8;
   static constexpr int NPLANES = NPL + 4 * NRING;
   // ppm_type 2 (H == 3): two tables of the limited edge values of a plane's tile, (BX+3) x BY x-faces and BX x (BY+3)
   // y-faces (planes t and t+1), see the E phase of the kernel
@@ -60,7 +63,7 @@ struct Smem3 {
   // BY x (BX+2) in x and (BY+2) x BX in y (see the S phase of the kernel); same place as the edge tables
   static constexpr int NSX = BY * (BX + 2), NSY = (BY + 2) * BX;
   static constexpr int NEDGE = (H == 3) ? 2 * NE : NSX + NSY;
-  static constexpr int BYTES = (NTILE + NPLANES * PL) * 8 + 64 + 2 * KCAP * 8 + NEDGE * 8;  // + mbarriers + per-plane constants + edge tables
+  static constexpr int BYTES = (NTILE + PAD + NPLANES * PL) * 8 + 64 + 2 * KCAP * 8 + NEDGE * 8;  // + mbarriers + per-plane constants + edge tables
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(BX* BY, 2)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* const tiles = reinterpret_cast<double*>(smem_raw);
   double* const dtiles = tiles + NS * SM::SLOT;
-  double* const planes = tiles + SM::NTILE;
+  double* const planes = tiles + SM::NTILE + SM::PAD;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(planes + SM::NPLANES * SM::PL);
   // per-plane constants of the on-the-fly transforms, staged once per CTA (KCAP doubles each, kchunk + 16 <= KCAP):
   // sWadd[m] = wadd of z-face t0 + m, sSub[m] = ssub of plane t0 + m
