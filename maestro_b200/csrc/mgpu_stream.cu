@@ -1092,7 +1092,7 @@ struct FU3 {
   const double *w0, *rho0_old, *rho0_edge_old, *rho0_new, *rho0_edge_new, *rho0_predicted_edge;
 };
 
-__global__ void __launch_bounds__(256, 3) k_flux_update3_fast(const __grid_constant__ FU3 a) {
+__global__ void __launch_bounds__(256, 4) k_flux_update3_fast(const __grid_constant__ FU3 a) {
   const int i = a.lo[0] + (int)(blockIdx.x * blockDim.x + threadIdx.x);
   const int j = a.lo[1] + (int)blockIdx.y, k = a.kb + (int)blockIdx.z;
   if (i > a.hi[0]) return;
