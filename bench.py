@@ -548,7 +548,7 @@ def selftest(ops, rank, world, local_rank, dev):
     if rank != 0:
         return
     cases = [("3", "periodic", "1", "1"), ("3", "walls", "2", "1"), ("2", "walls", "1", "1"), ("3", "periodic", "1", "0"),
-             ("3", "walls", "2", "0"), ("2", "periodic", "2", "0"), ("3", "sphr", "1", "1"),
+             ("3", "walls", "2", "0"), ("2", "periodic", "2", "0"), ("3", "sphr", "1", "1"), ("3", "sphr", "1", "0"),
              # velocity_advance, advance_premac, enthalpy_advance, average over slabs (exact and FAST builds)
              ("3", "episodes-periodic", "1", "1"), ("3", "episodes-walls", "2", "1"), ("2", "episodes-walls", "1", "0")]
     res = {}
