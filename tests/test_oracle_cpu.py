@@ -692,3 +692,31 @@ def test_python_driven_test_advect_reproduces_a_golden_case(oracle):
     c = GOLD["cases"]["dm2_n64_ppm1_dir+1"]
     a, r, _ = python_test_advect(oracle, c["dm"], c["n"], c["ppm_type"], c["dir"], stop_time=c["stop_time"])
     assert abs(a - c["abs"]) <= 1e-13 * c["abs"] and abs(r - c["rel"]) <= 1e-13 * c["rel"]
+
+
+# ---- the `verbose >= 1` report (density_advance.f90:374-402, enthalpy_advance.f90:440-449, velocity_advance.f90:142-160) --
+@pytest.mark.parametrize("dm,n", [(2, (17, 11)), (3, (9, 8, 7))])
+def test_minmax_and_verbose_report_against_numpy(oracle, dm, n):
+    """multifab_min_c / multifab_max_c as restated by the oracle: min and max over the valid zones only (ghost cells hold
+    huge values here), the species as rhoX / rho, and the lines of the report in the reference's formats."""
+    from maestro_b200.operators import fortran_e
+
+    st = make_state(dm, list(n))
+    p, s = st["p"], st["s"].clone()
+    v = np.array(s.valid(), copy=True)
+    s.a[...] = 1.0e300
+    s.valid()[...] = v
+    for comp in range(1, p.nscal + 1):
+        assert oracle.minmax(p, s, comp) == (float(v[comp - 1].min()), float(v[comp - 1].max()))
+    x = v[p.spec_comp - 1] / v[p.rho_comp - 1]
+    assert oracle.minmax(p, s, p.spec_comp, p.rho_comp) == (float(x.min()), float(x.max()))
+    lines = oracle.verbose_report(p, "density_advance", s, spec_names=["helium-4", "carbon-12", "oxygen-16"])
+    assert lines[0] == "... Level 1 update:"
+    assert lines[1] == "... new min/max : helium-4          %s  %s" % (fortran_e(float(x.min())), fortran_e(float(x.max())))
+    assert lines[1 + p.nspec] == "... new min/max : density           %s  %s" % (
+        fortran_e(float(v[p.rho_comp - 1].min())), fortran_e(float(v[p.rho_comp - 1].max())))
+    assert len(lines) == 1 + p.nspec + 1 + (1 if p.ntrac >= 1 else 0)
+    vel = oracle.verbose_report(p, "velocity_advance", s)
+    assert vel[1].startswith("... new min/max : x-velocity       ") and vel[-1] == " " and len(vel) == 2 + dm
+    with pytest.raises(Exception):
+        oracle.minmax(p, s, p.nscal + 1)
