@@ -1011,7 +1011,13 @@ static void advance_premac_dev(const mgpu_params& P, const DV& uold, const DV& s
   const double* rho0_old = upload_small(rho0_old_h, nr);
   const double* grav = upload_small(grav_h, nr);
   int z3[3] = {0, 0, 0};
-  const bool fuse = g_opt_premac_fuse && velpred_premac_fusable(P, phys_bc);
+  // The fused path skips both ghost fills of utrans, i.e. their halo exchanges: every rank of a slab run must take the
+  // same branch, so the decision rests on a global property -- the domain is periodic in every direction (pmask) -- and
+  // not on this rank's own boundaries (a middle slab of a box with walls in the slab direction has none either, while
+  // its neighbours do and would wait for its sends).
+  bool all_periodic = true;
+  for (int d = 0; d < dm; ++d) all_periodic = all_periodic && pmask[d] != 0;
+  const bool fuse = g_opt_premac_fuse && all_periodic && velpred_premac_fusable(P, phys_bc);
   // fused path: the face kernel forms ufull = w0 on the cells + uold (:75-78) per cell; only traced forces read the
   // array again afterwards
   const bool need_ufull = !fuse || P.ppm_trace_forces == 1;
